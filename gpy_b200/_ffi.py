@@ -1,0 +1,207 @@
+"""ctypes binding of libgpx.so (C ABI: include/gpx.h). The CUDA library is the product: if it is missing or
+cannot be loaded this module raises — there is NO CPU fallback anywhere in gpy_b200."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgpx.so")
+
+KIND = {"rbf": 0, "exponential": 1, "matern32": 2, "matern52": 3}
+GET = {"L": 0, "alpha": 1, "Kinv": 2, "dL_dK": 3, "K": 4, "Linv": 5}
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+
+
+class GpxStats(ctypes.Structure):
+    _fields_ = [("total_ms", ctypes.c_float), ("kbuild_ms", ctypes.c_float), ("sweep_ms", ctypes.c_float),
+                ("update_ms", ctypes.c_float), ("lauum_ms", ctypes.c_float), ("solve_ms", ctypes.c_float),
+                ("update_flops", ctypes.c_double), ("lauum_flops", ctypes.c_double), ("kbuild_bytes", ctypes.c_double),
+                ("launches", ctypes.c_int64), ("update_launches", ctypes.c_int32), ("tries", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "gpx_last_error": (ctypes.c_char_p, []),
+    "gpx_version": (ctypes.c_char_p, []),
+    "gpx_device_count": (ctypes.c_int, []),
+    "gpx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "gpx_destroy": (ctypes.c_int, [_vp]),
+    "gpx_set_data": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, ctypes.c_int]),
+    "gpx_exact_eval": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_int, _dp, _dp, _dp]),
+    "gpx_get": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
+    "gpx_predict": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp]),
+    "gpx_kern_K": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64, _dp,
+                                  ctypes.c_int64, ctypes.c_int, _dp]),
+    "gpx_kern_Kdiag": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int64, _dp]),
+    "gpx_kern_grad_full": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64,
+                                          _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp]),
+    "gpx_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(GpxStats)]),
+    "gpx_total_launches": (ctypes.c_int64, [_vp]),
+    "gpx_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
+    "gpx_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+    "gpx_comm_init": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libgpx.so (once). Raises RuntimeError if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("gpy_b200: CUDA library %s not built (run `python -c 'import __graft_entry__ as g; "
+                               "g.build()'` or `make -C gpy_b200/csrc`); there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class GpxError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def check(rc, what):
+    """rc < 0: CUDA/argument error -> GpxError; rc > 0: not positive definite -> numpy.linalg.LinAlgError, the class
+    GPy raises from jitchol (GPy/util/linalg.py:64,75)."""
+    if rc == 0:
+        return
+    msg = lib().gpx_last_error().decode()
+    if rc > 0:
+        raise np.linalg.LinAlgError("not positive definite, even with jitter. (leading minor %d)" % rc)
+    raise GpxError("%s failed (%d): %s" % (what, rc, msg))
+
+
+def _theta(kind, ARD, lengthscale, D):
+    ls = _f64(np.atleast_1d(lengthscale)).reshape(-1)
+    if ARD:
+        if ls.size != D:
+            raise ValueError("ARD lengthscale must have %d entries" % D)
+    elif ls.size != 1:
+        raise ValueError("isotropic lengthscale must be a scalar")
+    return KIND[kind], int(bool(ARD)), ls
+
+
+class Engine(object):
+    """One device context (gpx_ctx): owns the HBM-resident X, Y and the N x N factor workspace of one model."""
+
+    def __init__(self, device=0):
+        self._h = _vp()
+        self._L = lib()
+        check(self._L.gpx_create(int(device), ctypes.byref(self._h)), "gpx_create")
+        self.N = self.D = self.P = 0
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.gpx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        check(self._L.gpx_set_option(self._h, name.encode(), int(value)), "gpx_set_option")
+
+    def set_data(self, X, Y):
+        X, Y = _f64(X), _f64(Y)
+        if X.ndim != 2 or Y.ndim != 2 or X.shape[0] != Y.shape[0]:
+            raise ValueError("X must be N x D and Y N x P")
+        self.N, self.D = X.shape
+        self.P = Y.shape[1]
+        check(self._L.gpx_set_data(self._h, _ptr(X), self.N, self.D, _ptr(Y), self.P), "gpx_set_data")
+
+    def exact_eval(self, kind, ARD, variance, lengthscale, noise, jitter=1e-8, max_tries=5):
+        """-> (log_marginal, gradient[variance, lengthscale.., noise], extra_jitter_used)"""
+        k, a, ls = _theta(kind, ARD, lengthscale, self.D)
+        lml = ctypes.c_double()
+        jit = ctypes.c_double()
+        grad = np.zeros(ls.size + 2)
+        rc = self._L.gpx_exact_eval(self._h, k, a, float(variance), _ptr(ls), float(noise), float(jitter), int(max_tries),
+                                    ctypes.byref(lml), _ptr(grad), ctypes.byref(jit))
+        check(rc, "gpx_exact_eval")
+        return lml.value, grad, jit.value
+
+    def get(self, which):
+        if which == "alpha":
+            out = np.empty((self.N, self.P))
+        else:
+            out = np.empty((self.N, self.N), order="F")
+        check(self._L.gpx_get(self._h, GET[which], _ptr(out)), "gpx_get")
+        return out
+
+    def predict(self, Xnew, full_cov=False):
+        Xnew = _f64(Xnew)
+        M = Xnew.shape[0]
+        mu = np.empty((M, self.P))
+        var = np.empty((M, M), order="F") if full_cov else np.empty(M)
+        check(self._L.gpx_predict(self._h, _ptr(Xnew), M, int(full_cov), _ptr(mu), _ptr(var)), "gpx_predict")
+        return mu, (var if full_cov else var[:, None])
+
+    def stats(self):
+        s = GpxStats()
+        check(self._L.gpx_get_stats(self._h, ctypes.byref(s)), "gpx_get_stats")
+        return s.as_dict()
+
+    def total_launches(self):
+        return int(self._L.gpx_total_launches(self._h))
+
+
+def kern_K(kind, ARD, variance, lengthscale, X, X2=None):
+    X = _f64(X)
+    N, D = X.shape
+    k, a, ls = _theta(kind, ARD, lengthscale, D)
+    if X2 is not None:
+        X2 = _f64(X2)
+        M = X2.shape[0]
+    else:
+        M = N
+    out = np.empty((N, M))
+    check(lib().gpx_kern_K(None, k, a, float(variance), _ptr(ls), _ptr(X), N, _ptr(X2), M, D, _ptr(out)), "gpx_kern_K")
+    return out
+
+
+def kern_Kdiag(kind, variance, N):
+    out = np.empty(N)
+    check(lib().gpx_kern_Kdiag(KIND[kind], float(variance), N, _ptr(out)), "gpx_kern_Kdiag")
+    return out
+
+
+def kern_grad_full(kind, ARD, variance, lengthscale, X, dL_dK, X2=None):
+    X = _f64(X)
+    N, D = X.shape
+    k, a, ls = _theta(kind, ARD, lengthscale, D)
+    if X2 is not None:
+        X2 = _f64(X2)
+        M = X2.shape[0]
+    else:
+        M = N
+    dL_dK = _f64(dL_dK)
+    if dL_dK.shape != (N, M):
+        raise ValueError("dL_dK must be %d x %d" % (N, M))
+    dv = ctypes.c_double()
+    dl = np.zeros(ls.size)
+    check(lib().gpx_kern_grad_full(None, k, a, float(variance), _ptr(ls), _ptr(X), N, _ptr(X2), M, D, _ptr(dL_dK),
+                                   ctypes.byref(dv), _ptr(dl)), "gpx_kern_grad_full")
+    return dv.value, dl

@@ -1,0 +1,727 @@
+// gpx_api.cu — C ABI (include/gpx.h) and host orchestration of the exact-GP evaluation on one B200.
+//
+// One evaluation (= one GP.parameters_changed(), GPy/core/gp.py:269-282):
+//   prep_x -> kbuild (Ky into the workspace S) -> unified blocked factor-and-invert sweep (S: lower = L, upper = U = L^-T)
+//   -> t = U^T y, alpha = U t -> LAUUM K^-1 = U U^T with the fused gradient epilogue -> finalize (LML + gradient).
+// Nothing of size N^2 crosses PCIe unless gpx_get asks for it.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "gpx_common.cuh"
+#include "gpx_kernels.cuh"
+
+namespace gpx {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace gpx
+
+using namespace gpx;
+
+#define GPX_CHECK(x)        \
+  do {                      \
+    int rc__ = (x);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+#define GPX_FAIL(msg)       \
+  do {                      \
+    gpx::set_error(msg);    \
+    return -2;              \
+  } while (0)
+
+struct gpx_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  // data
+  long N = 0, Npad = 0;
+  int D = 0, P = 0;
+  double* dX = nullptr;      // N x D row-major (as given)
+  double* dXsT = nullptr;    // [D][Npad] scaled SoA
+  double* dsq = nullptr;     // [Npad]
+  double* dY = nullptr;      // [P][Npad]
+  double* dT = nullptr;      // [P][Npad]  L^-1 y
+  double* dAlpha = nullptr;  // [P][Npad]
+  double* dUvPart = nullptr; // [KSPLIT][P][Npad]
+  // workspace
+  double* S = nullptr;       // Npad x Npad column-major: lower L, upper U
+  double* Pbuf = nullptr;    // Npad x NB
+  double* Tm = nullptr;      // NB x NB
+  double* Ldiag = nullptr;   // nt tiles of 128x128
+  double* Dinv = nullptr;    // nt tiles of 128x128
+  double* logdet_part = nullptr;
+  double* partials = nullptr;
+  int* info = nullptr;
+  double* res = nullptr;     // device result vector
+  double* h_res = nullptr;   // pinned
+  int* h_info = nullptr;     // pinned
+  double* Kinv = nullptr;    // lazy, Npad x Npad (lower tiles)
+  double* staging = nullptr; // lazy, N x N dense
+  long NB = 0;               // outer block (0 = auto)
+  // last evaluation
+  bool have_eval = false;
+  bool have_kinv = false;
+  KernParams kp{};
+  double noise = 0, jitter = 0, jitter_extra = 0;
+  // accounting
+  gpx_stats stats{};
+  int64_t total_launches = 0;
+  int64_t eval_launches = 0;
+  std::vector<cudaEvent_t> ev;
+  int profile = 1;
+};
+
+static const int KSPLIT = 32;
+
+static void free_data(gpx_ctx* c) {
+  double** ptrs[] = {&c->dX, &c->dXsT, &c->dsq, &c->dY, &c->dT, &c->dAlpha, &c->dUvPart, &c->S, &c->Pbuf, &c->Tm,
+                     &c->Ldiag, &c->Dinv, &c->logdet_part, &c->partials, &c->Kinv, &c->staging};
+  for (auto p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  c->have_eval = false;
+  c->have_kinv = false;
+}
+
+static long pick_nb(const gpx_ctx* c) {
+  if (c->NB > 0) return std::min<long>(c->NB, c->Npad);
+  const char* e = getenv("GPX_NB");
+  if (e && atol(e) >= TILE && atol(e) % TILE == 0) return std::min<long>(atol(e), c->Npad);
+  if (c->Npad >= 8192) return 1024;
+  if (c->Npad >= 2048) return 512;
+  return std::min<long>(256, c->Npad);
+}
+
+static int fill_kp(KernParams& kp, int kind, int ard, int D, double variance, const double* ls) {
+  if (kind < 0 || kind > 3) GPX_FAIL("unknown kernel kind");
+  if (D < 1 || D > MAX_D) GPX_FAIL("input dimension must be in [1, 64]");
+  if (!(variance > 0)) GPX_FAIL("variance must be positive");
+  kp.kind = kind; kp.ard = ard ? 1 : 0; kp.D = D; kp.variance = variance;
+  const int nl = ard ? D : 1;
+  for (int q = 0; q < nl; q++) {
+    if (!(ls[q] > 0)) GPX_FAIL("lengthscale must be positive");
+    kp.ls[q] = ls[q];
+  }
+  for (int q = nl; q < MAX_D; q++) kp.ls[q] = 1.0;
+  kp.inv_ls_iso = ard ? 1.0 : 1.0 / ls[0];
+  return 0;
+}
+
+extern "C" {
+
+const char* gpx_last_error(void) { return gpx::g_err.c_str(); }
+const char* gpx_version(void) { return "gpx 0.1 (sm_100a, fp64 DMMA)"; }
+
+int gpx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
+int gpx_create(int device, gpx_ctx** out) {
+  if (!out) GPX_FAIL("null out pointer");
+  int n = 0;
+  GPX_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) GPX_FAIL("no such CUDA device");
+  GPX_CUDA(cudaSetDevice(device));
+  gpx_ctx* c = new gpx_ctx();
+  c->device = device;
+  GPX_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  GPX_CUDA(cudaMalloc(&c->res, (MAX_D + 8) * sizeof(double)));
+  GPX_CUDA(cudaMalloc(&c->info, sizeof(int)));
+  GPX_CUDA(cudaMallocHost(&c->h_res, (MAX_D + 8) * sizeof(double)));
+  GPX_CUDA(cudaMallocHost(&c->h_info, sizeof(int)));
+  GPX_CHECK(gemm_init());
+  *out = c;
+  return 0;
+}
+
+int gpx_destroy(gpx_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  free_data(c);
+  for (auto e : c->ev) cudaEventDestroy(e);
+  if (c->res) cudaFree(c->res);
+  if (c->info) cudaFree(c->info);
+  if (c->h_res) cudaFreeHost(c->h_res);
+  if (c->h_info) cudaFreeHost(c->h_info);
+  cudaStreamDestroy(c->st);
+  delete c;
+  return 0;
+}
+
+int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
+  if (!c || !name) GPX_FAIL("null argument");
+  if (!strcmp(name, "nb")) {
+    if (value != 0 && (value < TILE || value % TILE)) GPX_FAIL("nb must be a multiple of 128");
+    c->NB = value;
+    return 0;
+  }
+  if (!strcmp(name, "profile")) { c->profile = (int)value; return 0; }
+  if (!strcmp(name, "lookahead")) return 0;
+  GPX_FAIL("unknown option");
+}
+
+int gpx_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y, int P) {
+  if (!c || !X || !Y) GPX_FAIL("null argument");
+  if (N < 1) GPX_FAIL("N must be positive");
+  if (D < 1 || D > MAX_D) GPX_FAIL("input dimension must be in [1, 64]");
+  if (P < 1 || P > MAX_P) GPX_FAIL("number of output columns must be in [1, 8]");
+  GPX_CUDA(cudaSetDevice(c->device));
+  const long Npad = (N + TILE - 1) / TILE * TILE;
+  if (Npad != c->Npad || D != c->D || P != c->P) {
+    GPX_CUDA(cudaStreamSynchronize(c->st));
+    free_data(c);
+    c->Npad = Npad; c->D = D; c->P = P;
+    const long nt = Npad / TILE;
+    const long NB = pick_nb(c);
+    GPX_CUDA(cudaMalloc(&c->dX, (size_t)Npad * D * 8));
+    GPX_CUDA(cudaMalloc(&c->dXsT, (size_t)Npad * D * 8));
+    GPX_CUDA(cudaMalloc(&c->dsq, (size_t)Npad * 8));
+    GPX_CUDA(cudaMalloc(&c->dY, (size_t)Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->dT, (size_t)Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->dAlpha, (size_t)Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->dUvPart, (size_t)KSPLIT * Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->S, (size_t)Npad * Npad * 8));
+    GPX_CUDA(cudaMalloc(&c->Pbuf, (size_t)Npad * NB * 8));
+    GPX_CUDA(cudaMalloc(&c->Tm, (size_t)NB * NB * 8));
+    GPX_CUDA(cudaMalloc(&c->Ldiag, (size_t)Npad * TILE * 8));
+    GPX_CUDA(cudaMalloc(&c->Dinv, (size_t)Npad * TILE * 8));
+    GPX_CUDA(cudaMalloc(&c->logdet_part, (size_t)nt * 8));
+    GPX_CUDA(cudaMalloc(&c->partials, (size_t)nt * nt * (MAX_D + 2) * 8));
+  }
+  c->N = N;
+  c->have_eval = false;
+  c->have_kinv = false;
+  // X: keep the caller's row-major layout on device; Y: SoA [P][Npad] zero padded (staged through dT)
+  GPX_CUDA(cudaMemcpyAsync(c->dX, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, c->st));
+  GPX_CUDA(cudaMemcpyAsync(c->dT, Y, (size_t)N * P * 8, cudaMemcpyHostToDevice, c->st));
+  GPX_CHECK(launch_transpose_pad(c->dT, N, P, Npad, c->dY, c->st));
+  c->total_launches += 1;
+  GPX_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// event helpers for per-phase accounting on the launching stream
+// ---------------------------------------------------------------------------------------------------------------
+struct EvSpan { int a, b; int phase; double flops; };
+enum { PH_KBUILD = 0, PH_SWEEP = 1, PH_UPDATE = 2, PH_LAUUM = 3, PH_SOLVE = 4, PH_TOTAL = 5 };
+
+static int ev_get(gpx_ctx* c, size_t idx, cudaEvent_t* out) {
+  while (c->ev.size() <= idx) {
+    cudaEvent_t e;
+    GPX_CUDA(cudaEventCreate(&e));
+    c->ev.push_back(e);
+  }
+  *out = c->ev[idx];
+  return 0;
+}
+
+struct Recorder {
+  gpx_ctx* c;
+  std::vector<EvSpan> spans;
+  size_t next = 0;
+  int begin(int phase, double flops = 0) {
+    if (!c->profile && phase != PH_TOTAL) return -1;
+    cudaEvent_t e;
+    if (ev_get(c, next, &e)) return -1;
+    cudaEventRecord(e, c->st);
+    spans.push_back({(int)next, -1, phase, flops});
+    next++;
+    return (int)spans.size() - 1;
+  }
+  void end(int h) {
+    if (h < 0) return;
+    cudaEvent_t e;
+    if (ev_get(c, next, &e)) return;
+    cudaEventRecord(e, c->st);
+    spans[h].b = (int)next;
+    next++;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// the unified blocked factor-and-invert sweep
+// ---------------------------------------------------------------------------------------------------------------
+static GemmParams gemm_defaults() {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.sub_tile = -1;
+  p.krow_mod = 1;
+  p.krow_rem = 0;
+  return p;
+}
+
+static int run_sweep(gpx_ctx* c, Recorder& rec) {
+  const long ld = c->Npad, Npad = c->Npad;
+  const int nt = (int)(Npad / TILE);
+  const long NB = pick_nb(c);
+  cudaStream_t st = c->st;
+  for (long o = 0; o < Npad; o += NB) {
+    const long nb = std::min(NB, Npad - o);
+    const int nbt = (int)(nb / TILE), kt0 = (int)(o / TILE), kt1 = kt0 + nbt;
+    double* Sblk = c->S + o + o * ld;
+    // ---- inner sweep of the nb x nb diagonal block, 128 columns at a time -----------------------------------
+    for (int d = 0; d < nbt; d++) {
+      const int g = kt0 + d;
+      double* tile = Sblk + (long)d * TILE + (long)d * TILE * ld;
+      GPX_CHECK(launch_base(tile, ld, c->Ldiag + (long)g * TILE * TILE, c->Dinv + (long)g * TILE * TILE,
+                            c->logdet_part + g, c->info, g * TILE, st));
+      c->eval_launches++;
+      if (nbt > 1) {
+        GemmParams pp = gemm_defaults();
+        pp.mode = GEMM_PANEL;
+        pp.A = Sblk + (long)d * TILE * ld; pp.lda = ld;
+        pp.B = c->Dinv + (long)g * TILE * TILE; pp.ldb = TILE;
+        pp.C = Sblk + (long)d * TILE * ld; pp.ldc = ld;      // in place: one k-tile deep, tile-local dependence only
+        pp.K = TILE; pp.nt = nbt; pp.skip0 = d; pp.skip1 = d + 1; pp.tri = 0;
+        GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), st));
+        c->eval_launches++;
+        if (d + 1 < nbt) {
+          GemmParams pu = gemm_defaults();
+          pu.mode = GEMM_UPDATE;
+          pu.A = Sblk + (long)d * TILE * ld; pu.lda = ld;
+          pu.B = pu.A; pu.ldb = ld;
+          pu.C = Sblk; pu.ldc = ld;
+          pu.K = TILE; pu.nt = nbt; pu.c0 = d + 1; pu.rlow = d + 1;
+          GPX_CHECK(launch_gemm(pu, dim3(nbt - d - 1, nbt), st));
+          c->eval_launches++;
+        }
+      }
+    }
+    if (nbt == nt) break;  // single block: done
+    // ---- outer panel: P = S(:, block) * Linv_kk^T, rows of the diagonal block get U_kk ------------------------
+    GPX_CHECK(launch_assemble(Sblk, ld, (int)nb, c->Pbuf + o, Npad, c->Tm, st));
+    c->eval_launches++;
+    {
+      GemmParams pp = gemm_defaults();
+      pp.mode = GEMM_PANEL;
+      pp.A = c->S + o * ld; pp.lda = ld;
+      pp.B = c->Tm; pp.ldb = nb;
+      pp.C = c->Pbuf; pp.ldc = Npad;
+      pp.K = (int)nb; pp.nt = nt; pp.skip0 = kt0; pp.skip1 = kt1; pp.tri = 1;
+      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), st));
+      c->eval_launches++;
+    }
+    if (o > 0)
+      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, c->Pbuf, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, st));
+    if (kt1 < nt)
+      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, c->Pbuf + (o + nb), Npad * 8,
+                                 (size_t)(Npad - o - nb) * 8, nb, cudaMemcpyDeviceToDevice, st));
+    // ---- unified trailing update: S(r,c) -= P_r P_c^T for c >= kt1, r in [0,kt1) U [c,nt) ----------------------
+    if (kt1 < nt) {
+      GemmParams pu = gemm_defaults();
+      pu.mode = GEMM_UPDATE;
+      pu.A = c->Pbuf; pu.lda = Npad;
+      pu.B = c->Pbuf; pu.ldb = Npad;
+      pu.C = c->S; pu.ldc = ld;
+      pu.K = (int)nb; pu.nt = nt; pu.c0 = kt1; pu.rlow = kt1;
+      double tiles = 0;
+      for (int cc = kt1; cc < nt; cc++) tiles += kt1 + (nt - cc);
+      const double flops = tiles * 2.0 * TILE * TILE * (double)nb;
+      const int h = rec.begin(PH_UPDATE, flops);
+      GPX_CHECK(launch_gemm(pu, dim3(nt - kt1, nt), st));
+      rec.end(h);
+      c->eval_launches++;
+      c->stats.update_launches++;
+    }
+  }
+  return 0;
+}
+
+static int run_lauum(gpx_ctx* c, double* kinv_out, Recorder* rec) {
+  const long ld = c->Npad;
+  const int nt = (int)(c->Npad / TILE);
+  const int nl = c->kp.ard ? c->D : 1;
+  GPX_CUDA(cudaMemsetAsync(c->partials, 0, (size_t)nt * nt * (nl + 2) * 8, c->st));
+  GemmParams pl = gemm_defaults();
+  pl.mode = GEMM_LAUUM;
+  pl.A = c->S; pl.lda = ld;
+  pl.B = c->S; pl.ldb = ld;
+  pl.C = nullptr; pl.ldc = ld;
+  pl.K = (int)c->Npad; pl.nt = nt;
+  pl.XsT = c->dXsT; pl.sq = c->dsq; pl.alpha = c->dAlpha; pl.ldx = c->Npad;
+  pl.N = (int)c->N; pl.P = c->P;
+  pl.partials = c->partials;
+  pl.kinv_out = kinv_out;
+  pl.kp = c->kp;
+  double flops = 0;
+  for (int r = 0; r < nt; r++) flops += (double)(r + 1) * 2.0 * TILE * TILE * (double)(c->Npad - (long)r * TILE);
+  int h = rec ? rec->begin(PH_LAUUM, flops) : -1;
+  GPX_CHECK(launch_gemm(pl, dim3(nt, nt), c->st));
+  if (rec) rec->end(h);
+  c->eval_launches++;
+  return 0;
+}
+
+static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
+  cudaStream_t st = c->st;
+  const long ld = c->Npad;
+  const int nt = (int)(c->Npad / TILE);
+  const int nl = c->kp.ard ? c->D : 1;
+  GPX_CUDA(cudaMemsetAsync(c->info, 0, sizeof(int), st));
+  GPX_CHECK(launch_prep_x(c->dX, c->N, c->Npad, c->kp, c->dXsT, c->dsq, st));
+  c->eval_launches++;
+  {
+    KBuildParams kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.rowsT = c->dXsT; kb.ld_rows = c->Npad;
+    kb.colsT = c->dXsT; kb.ld_cols = c->Npad;
+    kb.sq_rows = c->dsq; kb.sq_cols = c->dsq;
+    kb.out = c->S; kb.ld = ld;
+    kb.nrows = c->N; kb.ncols = c->N;
+    kb.sym = 1; kb.same = 1;
+    kb.diag_add = (c->noise + c->jitter) + extra_jitter;
+    kb.kp = c->kp;
+    const int h = rec.begin(PH_KBUILD);
+    GPX_CHECK(launch_kbuild(kb, nt, nt, st));
+    rec.end(h);
+    c->eval_launches++;
+  }
+  {
+    const int h = rec.begin(PH_SWEEP);
+    GPX_CHECK(run_sweep(c, rec));
+    rec.end(h);
+  }
+  {
+    const int h = rec.begin(PH_SOLVE);
+    GPX_CHECK(launch_utv(c->S, ld, c->Npad, c->P, c->dY, c->dT, st));
+    GPX_CHECK(launch_uv(c->S, ld, c->Npad, c->P, c->dT, KSPLIT, c->dUvPart, c->dAlpha, st));
+    rec.end(h);
+    c->eval_launches += 3;
+  }
+  GPX_CHECK(run_lauum(c, nullptr, &rec));
+  {
+    FinalizeParams f;
+    memset(&f, 0, sizeof(f));
+    f.partials = c->partials; f.ntiles = (long)nt * nt; f.nl = nl;
+    f.logdet_part = c->logdet_part; f.nt = nt;
+    f.T = c->dT; f.ld = ld; f.N = c->N; f.P = c->P;
+    f.kp = c->kp;
+    f.res = c->res;
+    GPX_CHECK(launch_finalize(f, st));
+    c->eval_launches++;
+  }
+  GPX_CUDA(cudaMemcpyAsync(c->h_res, c->res, (nl + 5) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPX_CUDA(cudaMemcpyAsync(c->h_info, c->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" {
+
+int gpx_exact_eval(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, double noise,
+                   double jitter, int max_tries, double* lml, double* grad, double* jitter_used) {
+  if (!c || !lengthscale || !lml || !grad) GPX_FAIL("null argument");
+  if (!c->S) GPX_FAIL("gpx_set_data has not been called");
+  if (!(noise >= 0)) GPX_FAIL("noise variance must be non-negative");
+  GPX_CUDA(cudaSetDevice(c->device));
+  GPX_CHECK(fill_kp(c->kp, kind, ard, c->D, variance, lengthscale));
+  c->noise = noise;
+  c->jitter = jitter;
+  c->have_eval = false;
+  c->have_kinv = false;
+  const int nl = ard ? c->D : 1;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->eval_launches = 0;
+  Recorder rec{c};
+  const int htot = rec.begin(PH_TOTAL);
+  double extra = 0.0;
+  int tries = 0;
+  int info = 0;
+  for (;;) {
+    tries++;
+    GPX_CHECK(eval_once(c, extra, rec));
+    GPX_CUDA(cudaStreamSynchronize(c->st));
+    info = *c->h_info;
+    if (info == 0) break;
+    // jitchol ladder (GPy/util/linalg.py:61-75): the diagonal of Ky is variance + noise + jitter (> 0 here),
+    // extra jitter = mean(diag) * 1e-6 * 10^k for k = 0 .. max_tries-1
+    if (tries > max_tries) break;
+    const double mean_diag = variance + (noise + jitter);
+    extra = mean_diag * 1e-6 * pow(10.0, tries - 1);
+    if (!std::isfinite(extra)) break;
+  }
+  rec.end(htot);
+  GPX_CUDA(cudaStreamSynchronize(c->st));
+  c->jitter_extra = extra;
+  c->stats.tries = tries;
+  // accounting
+  for (auto& s : rec.spans) {
+    if (s.b < 0) continue;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[s.a], c->ev[s.b]);
+    switch (s.phase) {
+      case PH_KBUILD: c->stats.kbuild_ms += ms; break;
+      case PH_SWEEP: c->stats.sweep_ms += ms; break;
+      case PH_UPDATE: c->stats.update_ms += ms; c->stats.update_flops += s.flops; break;
+      case PH_LAUUM: c->stats.lauum_ms += ms; c->stats.lauum_flops += s.flops; break;
+      case PH_SOLVE: c->stats.solve_ms += ms; break;
+      case PH_TOTAL: c->stats.total_ms += ms; break;
+    }
+  }
+  c->stats.kbuild_bytes = 8.0 * (double)c->N * c->N + 8.0 * (double)c->N * c->D;
+  c->stats.launches = c->eval_launches;
+  c->total_launches += c->eval_launches;
+  if (jitter_used) *jitter_used = extra;
+  if (info != 0) {
+    gpx::set_error("not positive definite, even with jitter.");
+    return info;
+  }
+  *lml = c->h_res[0];
+  for (int q = 0; q < nl + 2; q++) grad[q] = c->h_res[1 + q];
+  c->have_eval = true;
+  return 0;
+}
+
+int gpx_get_stats(gpx_ctx* c, gpx_stats* out) {
+  if (!c || !out) GPX_FAIL("null argument");
+  *out = c->stats;
+  return 0;
+}
+int64_t gpx_total_launches(gpx_ctx* c) { return c ? c->total_launches : -1; }
+
+static int ensure_staging(gpx_ctx* c) {
+  if (!c->staging) GPX_CUDA(cudaMalloc(&c->staging, (size_t)c->N * c->N * 8));
+  return 0;
+}
+
+int gpx_get(gpx_ctx* c, int which, double* out) {
+  if (!c || !out) GPX_FAIL("null argument");
+  if (!c->have_eval) GPX_FAIL("no successful gpx_exact_eval to fetch results from");
+  GPX_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->st;
+  const long N = c->N, ld = c->Npad;
+  if (which == GPX_GET_ALPHA) {
+    GPX_CHECK(launch_untranspose(c->dAlpha, N, c->P, ld, c->dUvPart, st));
+    c->total_launches++;
+    GPX_CUDA(cudaMemcpyAsync(out, c->dUvPart, (size_t)N * c->P * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  GPX_CHECK(ensure_staging(c));
+  if (which == GPX_GET_K) {
+    KBuildParams kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.rowsT = c->dXsT; kb.ld_rows = ld; kb.colsT = c->dXsT; kb.ld_cols = ld;
+    kb.sq_rows = c->dsq; kb.sq_cols = c->dsq;
+    kb.out = c->staging; kb.ld = N; kb.nrows = N; kb.ncols = N; kb.sym = 0; kb.same = 1; kb.kp = c->kp;
+    GPX_CHECK(launch_kbuild(kb, (int)(ld / TILE), (int)(ld / TILE), st));
+    c->total_launches++;
+  } else if (which == GPX_GET_L || which == GPX_GET_LINV) {
+    GPX_CHECK(launch_extract(which, c->S, ld, c->Ldiag, nullptr, nullptr, 0, N, c->staging, st));
+    c->total_launches++;
+  } else if (which == GPX_GET_KINV || which == GPX_GET_DLDK) {
+    if (!c->have_kinv) {
+      if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)ld * ld * 8));
+      const int64_t keep = c->eval_launches;
+      GPX_CHECK(run_lauum(c, c->Kinv, nullptr));
+      c->total_launches += c->eval_launches - keep;
+      c->eval_launches = keep;
+      c->have_kinv = true;
+    }
+    GPX_CHECK(launch_extract(which, c->S, ld, c->Ldiag, c->Kinv, c->dAlpha, c->P, N, c->staging, st));
+    c->total_launches++;
+  } else {
+    GPX_FAIL("unknown gpx_get selector");
+  }
+  GPX_CUDA(cudaMemcpyAsync(out, c->staging, (size_t)N * N * 8, cudaMemcpyDeviceToHost, st));
+  GPX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// standalone kernel-plugin calls
+// ---------------------------------------------------------------------------------------------------------------
+static std::mutex g_scratch_mu;
+static gpx_ctx* g_scratch = nullptr;
+static int scratch_ctx(gpx_ctx** out) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  if (!g_scratch) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    GPX_CHECK(gpx_create(dev, &g_scratch));
+  }
+  *out = g_scratch;
+  return 0;
+}
+
+struct PointSet {
+  double* raw = nullptr; double* xT = nullptr; double* sq = nullptr; long n = 0, ld = 0;
+  ~PointSet() { if (raw) cudaFree(raw); if (xT) cudaFree(xT); if (sq) cudaFree(sq); }
+};
+static int upload_points(gpx_ctx* c, const double* X, long n, const KernParams& kp, PointSet& ps) {
+  ps.n = n; ps.ld = (n + TILE - 1) / TILE * TILE;
+  GPX_CUDA(cudaMalloc(&ps.raw, (size_t)n * kp.D * 8));
+  GPX_CUDA(cudaMalloc(&ps.xT, (size_t)ps.ld * kp.D * 8));
+  GPX_CUDA(cudaMalloc(&ps.sq, (size_t)ps.ld * 8));
+  GPX_CUDA(cudaMemcpyAsync(ps.raw, X, (size_t)n * kp.D * 8, cudaMemcpyHostToDevice, c->st));
+  GPX_CHECK(launch_prep_x(ps.raw, n, ps.ld, kp, ps.xT, ps.sq, c->st));
+  c->total_launches++;
+  return 0;
+}
+
+int gpx_kern_K(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* X, int64_t N,
+               const double* X2, int64_t M, int D, double* out) {
+  if (!X || !out || !lengthscale) GPX_FAIL("null argument");
+  if (!c) GPX_CHECK(scratch_ctx(&c));
+  GPX_CUDA(cudaSetDevice(c->device));
+  KernParams kp;
+  GPX_CHECK(fill_kp(kp, kind, ard, D, variance, lengthscale));
+  if (!X2) M = N;
+  if (N < 1 || M < 1) GPX_FAIL("empty input");
+  PointSet p1, p2;
+  GPX_CHECK(upload_points(c, X, N, kp, p1));
+  if (X2) GPX_CHECK(upload_points(c, X2, M, kp, p2));
+  PointSet& pj = X2 ? p2 : p1;   // thread-mapped operand = X2 points (contiguous index of the row-major output)
+  double* dout = nullptr;
+  GPX_CUDA(cudaMalloc(&dout, (size_t)N * M * 8));
+  KBuildParams kb;
+  memset(&kb, 0, sizeof(kb));
+  kb.rowsT = pj.xT; kb.ld_rows = pj.ld; kb.sq_rows = pj.sq;
+  kb.colsT = p1.xT; kb.ld_cols = p1.ld; kb.sq_cols = p1.sq;
+  kb.out = dout; kb.ld = M; kb.nrows = M; kb.ncols = N; kb.sym = 0; kb.same = X2 ? 0 : 1; kb.kp = kp;
+  int rc = launch_kbuild(kb, (int)(pj.ld / TILE), (int)(p1.ld / TILE), c->st);
+  c->total_launches++;
+  if (rc == 0 && cudaMemcpyAsync(out, dout, (size_t)N * M * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
+  if (cudaStreamSynchronize(c->st) != cudaSuccess) { gpx::set_error("gpx_kern_K: device failure"); rc = -1; }
+  cudaFree(dout);
+  return rc;
+}
+
+int gpx_kern_Kdiag(int kind, double variance, int64_t N, double* out) {
+  (void)kind;
+  if (!out) GPX_FAIL("null argument");
+  for (int64_t i = 0; i < N; i++) out[i] = variance;   // stationary.py:170-173
+  return 0;
+}
+
+int gpx_kern_grad_full(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* X,
+                       int64_t N, const double* X2, int64_t M, int D, const double* dL_dK, double* dvariance,
+                       double* dlengthscale) {
+  if (!X || !dL_dK || !lengthscale || !dvariance || !dlengthscale) GPX_FAIL("null argument");
+  if (!c) GPX_CHECK(scratch_ctx(&c));
+  GPX_CUDA(cudaSetDevice(c->device));
+  KernParams kp;
+  GPX_CHECK(fill_kp(kp, kind, ard, D, variance, lengthscale));
+  if (!X2) M = N;
+  PointSet p1, p2;
+  GPX_CHECK(upload_points(c, X, N, kp, p1));
+  if (X2) GPX_CHECK(upload_points(c, X2, M, kp, p2));
+  PointSet& pj = X2 ? p2 : p1;
+  double* dd = nullptr; double* dpart = nullptr;
+  const int tj = (int)(pj.ld / TILE), ti = (int)(p1.ld / TILE);
+  const int nl = ard ? D : 1, nred = nl + 1;
+  GPX_CUDA(cudaMalloc(&dd, (size_t)N * M * 8));
+  GPX_CUDA(cudaMalloc(&dpart, (size_t)tj * ti * nred * 8));
+  GPX_CUDA(cudaMemcpyAsync(dd, dL_dK, (size_t)N * M * 8, cudaMemcpyHostToDevice, c->st));
+  GradFullParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.x1T = p1.xT; gp.ld1 = p1.ld; gp.sq1 = p1.sq; gp.N = N;
+  gp.x2T = pj.xT; gp.ld2 = pj.ld; gp.sq2 = pj.sq; gp.M = M;
+  gp.dL_dK = dd; gp.same = X2 ? 0 : 1; gp.partials = dpart; gp.kp = kp;
+  int rc = launch_grad_full(gp, tj, ti, c->st);
+  c->total_launches++;
+  std::vector<double> hp((size_t)tj * ti * nred);
+  if (rc == 0 && cudaMemcpyAsync(hp.data(), dpart, hp.size() * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
+  if (cudaStreamSynchronize(c->st) != cudaSuccess) { gpx::set_error("gpx_kern_grad_full: device failure"); rc = -1; }
+  cudaFree(dd); cudaFree(dpart);
+  if (rc) return rc;
+  std::vector<double> tot(nred, 0.0);
+  for (size_t t = 0; t < (size_t)tj * ti; t++)
+    for (int q = 0; q < nred; q++) tot[q] += hp[t * nred + q];
+  *dvariance = tot[0];
+  for (int q = 0; q < nl; q++) dlengthscale[q] = -tot[1 + q] / lengthscale[q];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prediction with the factor of the last evaluation (posterior.py:273-302)
+// ---------------------------------------------------------------------------------------------------------------
+int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double* mu, double* var) {
+  if (!c || !Xnew || !mu || !var) GPX_FAIL("null argument");
+  if (!c->have_eval) GPX_FAIL("no successful gpx_exact_eval to predict from");
+  if (M < 1) GPX_FAIL("empty Xnew");
+  GPX_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->st;
+  const long ld = c->Npad, N = c->N;
+  PointSet pn;
+  GPX_CHECK(upload_points(c, Xnew, M, c->kp, pn));
+  // Kx as [M][ld] (each new point one zero-padded column of length ld): thread-mapped operand = training points
+  double* Kx = nullptr; double* Tx = nullptr;
+  GPX_CUDA(cudaMalloc(&Kx, (size_t)pn.ld * ld * 8));
+  GPX_CUDA(cudaMalloc(&Tx, (size_t)pn.ld * ld * 8));
+  GPX_CUDA(cudaMemsetAsync(Kx, 0, (size_t)pn.ld * ld * 8, st));
+  KBuildParams kb;
+  memset(&kb, 0, sizeof(kb));
+  kb.rowsT = c->dXsT; kb.ld_rows = ld; kb.sq_rows = c->dsq;
+  kb.colsT = pn.xT; kb.ld_cols = pn.ld; kb.sq_cols = pn.sq;
+  kb.out = Kx; kb.ld = ld; kb.nrows = N; kb.ncols = M; kb.sym = 0; kb.same = 0; kb.kp = c->kp;
+  int rc = launch_kbuild(kb, (int)(ld / TILE), (int)(pn.ld / TILE), st);
+  c->total_launches++;
+  // tmp = L^-1 Kx = U^T Kx, MAX_P columns per pass
+  for (long m0 = 0; rc == 0 && m0 < M; m0 += MAX_P) {
+    const int pc = (int)std::min<long>(MAX_P, M - m0);
+    rc = launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st);
+    c->total_launches++;
+  }
+  std::vector<double> hK, hT;
+  if (rc == 0) {
+    hK.resize((size_t)M * ld); hT.resize((size_t)M * ld);
+    if (cudaMemcpyAsync(hK.data(), Kx, hK.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (cudaMemcpyAsync(hT.data(), Tx, hT.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+  }
+  std::vector<double> hA((size_t)c->P * ld);
+  if (rc == 0 && cudaMemcpyAsync(hA.data(), c->dAlpha, hA.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
+  cudaFree(Kx); cudaFree(Tx);
+  if (rc) return rc;
+  // small host epilogue: mu = Kx^T alpha, var = Kdiag - colsum(tmp^2) (or Kxx - tmp^T tmp)
+  for (long m = 0; m < M; m++)
+    for (int q = 0; q < c->P; q++) {
+      double s = 0.0;
+      for (long i = 0; i < N; i++) s += hK[m * ld + i] * hA[(size_t)q * ld + i];
+      mu[m * c->P + q] = s;
+    }
+  if (!full_cov) {
+    for (long m = 0; m < M; m++) {
+      double s = 0.0;
+      for (long i = 0; i < N; i++) s += hT[m * ld + i] * hT[m * ld + i];
+      var[m] = c->kp.variance - s;
+    }
+  } else {
+    std::vector<double> kxx((size_t)M * M);
+    double lsv[MAX_D];
+    for (int q = 0; q < MAX_D; q++) lsv[q] = c->kp.ls[q];
+    rc = gpx_kern_K(c, c->kp.kind, c->kp.ard, c->kp.variance, lsv, Xnew, M, nullptr, M, c->D, kxx.data());
+    if (rc) return rc;
+    for (long a = 0; a < M; a++)
+      for (long b = 0; b < M; b++) {
+        double s = 0.0;
+        for (long i = 0; i < N; i++) s += hT[a * ld + i] * hT[b * ld + i];
+        var[a + b * M] = kxx[a * M + b] - s;
+      }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi-GPU entry points (implemented in gpx_dist.cu when built with NCCL)
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef GPX_WITH_NCCL
+int gpx_comm_unique_id(char id_out[128]) { (void)id_out; GPX_FAIL("libgpx built without NCCL"); }
+int gpx_comm_init(gpx_ctx* ctx, const char id[128], int rank, int nranks) {
+  (void)ctx; (void)id; (void)rank; (void)nranks;
+  GPX_FAIL("libgpx built without NCCL");
+}
+#endif
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// gpx_gemm.cu — the one fp64 tensor-core GEMM of the engine:  C(tile r,c) (op)= A_r * B_c^T  (NT form).
+//
+// Every O(N^3) step of the exact-GP evaluation is expressed through this kernel:
+//   GEMM_UPDATE : S(r,c) -= P_r P_c^T      trailing update of the unified factor-and-invert sweep
+//                                          (replaces LAPACK dpotrf's dsyrk/dgemm and dtrtri's trmm, GPy/util/linalg.py:58,209)
+//   GEMM_PANEL  : P(r,c') = S(r,panel) Linv_kk^T   panel "solve" as a product with the inverted diagonal block
+//   GEMM_LAUUM  : Kinv(r,c) = sum_{k>=r} U_rk U_ck^T   (replaces dpotri, linalg.py:142,210) with the FUSED epilogue that
+//                 reduces dL_dK -> (variance, lengthscale, noise) gradients (replaces exact_gaussian_inference.py:70-72,
+//                 stationary.py:193-243, stationary_cython.pyx:53-62, likelihoods/gaussian.py:78-79) without writing K^-1.
+//
+// Machine mapping (sm_100a): tcgen05.mma has no f64 kind, so the fp64 tensor path is DMMA.8x8x4 (mma.sync m8n8k4).
+// A 128x128 CTA tile is computed by 8 consumer warps (64x32 each, 64 fp64 accumulators per lane); a 9th producer
+// warp streams 16-deep k-slabs of both operands into a 4-stage shared-memory ring with 1-D bulk async copies
+// (cp.async.bulk -> SASS UBLKCP, the TMA engine) signalled through mbarriers. Operands are m-contiguous
+// (column-major), a slab column is one 1 KiB bulk copy; the smem pitch of 132 doubles makes the DMMA fragment
+// loads bank-conflict free. Measured DMMA issue peak on B200: 37.1 TFLOP/s (tools/microbench.cu).
+#include "gpx_common.cuh"
+
+namespace gpx {
+
+constexpr int SLAB_DOUBLES = KSLAB * PITCH;                       // one operand, one stage
+constexpr int PIPE_BYTES = 2 * STAGES * SLAB_DOUBLES * 8;         // 135168
+constexpr int EPI_DOUBLES = (2 * MAX_D + 2 + 2 * MAX_P) * TILE + CONSUMER_WARPS * (MAX_D + 3);
+constexpr int EPI_BYTES = EPI_DOUBLES * 8;
+constexpr int DATA_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
+constexpr int SMEM_BYTES = DATA_BYTES + 2 * STAGES * 8 + 64;
+
+size_t gemm_smem_bytes() { return SMEM_BYTES; }
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sA = reinterpret_cast<double*>(smem_raw);
+  double* sB = sA + STAGES * SLAB_DOUBLES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + DATA_BYTES);
+  uint64_t* empty = full + STAGES;
+
+  // ---- tile mapping ------------------------------------------------------------------------------------------
+  int r, c, kt_first = 0, nkt;
+  const int kt_step = p.krow_mod;
+  if (MODE == GEMM_UPDATE) {
+    c = p.c0 + blockIdx.x;
+    const int slot = blockIdx.y;
+    r = slot < p.rlow ? slot : c + (slot - p.rlow);
+    if (r >= p.nt) return;
+    nkt = p.K / TILE;
+  } else if (MODE == GEMM_PANEL) {
+    c = blockIdx.x;
+    const int slot = blockIdx.y;
+    r = slot < p.skip0 ? slot : slot + (p.skip1 - p.skip0);
+    if (r >= p.nt) return;
+    nkt = p.tri ? (c + 1) : p.K / TILE;
+  } else {  // GEMM_LAUUM
+    c = blockIdx.x;
+    r = c + blockIdx.y;
+    if (r >= p.nt) return;
+    // k-tiles kt in [r, nt) with kt % krow_mod == krow_rem
+    kt_first = r + ((p.krow_rem - r) % kt_step + kt_step) % kt_step;
+    nkt = kt_first < p.nt ? (p.nt - 1 - kt_first) / kt_step + 1 : 0;
+  }
+  const double* Aptr;
+  long lda;
+  if (r == p.sub_tile) { Aptr = p.subA; lda = TILE; } else { Aptr = p.A + (long)r * TILE; lda = p.lda; }
+  const double* Bptr = p.B + (long)c * TILE;
+  const long ldb = p.ldb;
+  const int nslab = nkt * (TILE / KSLAB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == CONSUMER_WARPS) {
+    // ================= producer warp: one bulk copy per lane per stage (16 A columns + 16 B columns) =========
+    const bool isA = lane < KSLAB;
+    const int kc = lane & (KSLAB - 1);
+    const double* src_base = isA ? Aptr : Bptr;
+    const long ld = isA ? lda : ldb;
+    double* dst_base = (isA ? sA : sB) + kc * PITCH;
+    for (int it = 0; it < nslab; ++it) {
+      const int s = it % STAGES;
+      const uint32_t n = it / STAGES;
+      if (it >= STAGES) mbar_wait(&empty[s], (n & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], 2 * KSLAB * TILE * 8);
+      __syncwarp();
+      const long k = (long)(kt_first + (it >> 3) * kt_step) * TILE + (it & 7) * KSLAB + kc;
+      bulk_g2s(dst_base + s * SLAB_DOUBLES, src_base + k * ld, TILE * 8, &full[s]);
+    }
+    return;
+  }
+
+  // ================= consumer warps ==========================================================================
+  const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps -> 64 x 32 sub-tiles
+  const int g = lane >> 2, tg = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int mb = 0; mb < 8; mb++)
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+
+  for (int it = 0; it < nslab; ++it) {
+    const int s = it % STAGES;
+    const uint32_t n = it / STAGES;
+    mbar_wait(&full[s], n & 1);
+    const double* a = sA + s * SLAB_DOUBLES + wm * 64 + g;
+    const double* b = sB + s * SLAB_DOUBLES + wn * 32 + g;
+#pragma unroll
+    for (int k4 = 0; k4 < KSLAB / 4; k4++) {
+      const int kk = (k4 * 4 + tg) * PITCH;
+      double af[8], bf[4];
+#pragma unroll
+      for (int mb = 0; mb < 8; mb++) af[mb] = a[kk + mb * 8];
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) bf[nb] = b[kk + nb * 8];
+#pragma unroll
+      for (int mb = 0; mb < 8; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ================= epilogues ===============================================================================
+  if (MODE != GEMM_LAUUM) {
+    double* Ct = p.C + (long)r * TILE + (long)c * TILE * p.ldc;
+    constexpr bool accumulate = (MODE == GEMM_UPDATE);
+#pragma unroll
+    for (int mb = 0; mb < 8; mb++) {
+      const int i = wm * 64 + mb * 8 + g;
+      double old[4][2];
+      if (accumulate) {
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) old[nb][e] = Ct[i + (long)(wn * 32 + nb * 8 + 2 * tg + e) * p.ldc];
+      }
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const long off = i + (long)(wn * 32 + nb * 8 + 2 * tg + e) * p.ldc;
+          Ct[off] = accumulate ? old[nb][e] - acc[mb][nb][e] : acc[mb][nb][e];
+        }
+    }
+    return;
+  }
+
+  // ---- LAUUM: fused dL_dK -> gradient reductions ---------------------------------------------------------------
+  const int D = p.kp.D, P = p.P;
+  const int nl = p.kp.ard ? D : 1;
+  const int nred = nl + 2;
+  consumer_bar();  // every consumer is done reading the pipeline buffers; reuse them
+  double* sXr = reinterpret_cast<double*>(smem_raw);
+  double* sXc = sXr + D * TILE;
+  double* sSr = sXc + D * TILE;
+  double* sSc = sSr + TILE;
+  double* sAr = sSc + TILE;
+  double* sAc = sAr + P * TILE;
+  double* sRed = sAc + P * TILE;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < D * TILE; idx += CONSUMER_WARPS * 32) {
+    const int q = idx / TILE, m = idx % TILE;
+    sXr[idx] = p.XsT[(long)q * p.ldx + (long)r * TILE + m];
+    sXc[idx] = p.XsT[(long)q * p.ldx + (long)c * TILE + m];
+  }
+  for (int idx = tid; idx < P * TILE; idx += CONSUMER_WARPS * 32) {
+    const int q = idx / TILE, m = idx % TILE;
+    sAr[idx] = p.alpha[(long)q * p.ldx + (long)r * TILE + m];
+    sAc[idx] = p.alpha[(long)q * p.ldx + (long)c * TILE + m];
+  }
+  if (tid < TILE) { sSr[tid] = p.sq[(long)r * TILE + tid]; sSc[tid] = p.sq[(long)c * TILE + tid]; }
+  consumer_bar();
+
+  const double w = (r > c) ? 2.0 : 1.0;   // strictly-lower tiles stand for their mirror image as well
+  const int kind = p.kp.kind;
+  const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  const bool ard = p.kp.ard != 0;
+  double gvar = 0.0, giso = 0.0, gnoise = 0.0;
+  double* kout = p.kinv_out ? p.kinv_out + (long)r * TILE + (long)c * TILE * p.ldc : nullptr;
+#pragma unroll
+  for (int mb = 0; mb < 8; mb++) {
+    const int il = wm * 64 + mb * 8 + g;
+    const long gi = (long)r * TILE + il;
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int jl = wn * 32 + nb * 8 + 2 * tg + e;
+        const long gj = (long)c * TILE + jl;
+        const double kinv = acc[mb][nb][e];
+        if (kout) kout[il + (long)jl * p.ldc] = kinv;
+        double dot = 0.0;
+        for (int q = 0; q < D; q++) dot = fma(sXr[q * TILE + il], sXc[q * TILE + jl], dot);
+        double r2 = sSr[il] + sSc[jl] - 2.0 * dot;
+        if (gi == gj) r2 = 0.0;
+        r2 = fmax(r2, 0.0);
+        const double rr = sqrt(r2) * inv_ls;
+        double k, dk;
+        k_dk_of_r_unit(kind, rr, k, dk);
+        double aa = 0.0;
+        for (int q = 0; q < P; q++) aa = fma(sAr[q * TILE + il], sAc[q * TILE + jl], aa);
+        double dl = 0.5 * (aa - (double)P * kinv);
+        if (gi >= p.N || gj >= p.N) dl = 0.0;
+        gvar = fma(w * k, dl, gvar);
+        if (gi == gj) gnoise += dl;
+        const double G = variance * dk * dl;
+        if (ard) {
+          acc[mb][nb][e] = (rr != 0.0) ? w * G / rr : 0.0;   // stationary.py:205,225-232: 1/r with 1/0 := 0
+        } else {
+          giso = fma(w * G, rr, giso);
+        }
+      }
+  }
+  double* red = sRed + warp * nred;
+  gvar = warp_sum(gvar);
+  gnoise = warp_sum(gnoise);
+  if (lane == 0) { red[0] = gvar; red[nred - 1] = gnoise; }
+  if (ard) {
+    for (int q = 0; q < D; q++) {
+      double s = 0.0;
+#pragma unroll
+      for (int mb = 0; mb < 8; mb++) {
+        const double xi = sXr[q * TILE + wm * 64 + mb * 8 + g];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const double df = xi - sXc[q * TILE + wn * 32 + nb * 8 + 2 * tg + e];
+            s = fma(acc[mb][nb][e], df * df, s);
+          }
+      }
+      s = warp_sum(s);
+      if (lane == 0) red[1 + q] = s;
+    }
+  } else {
+    giso = warp_sum(giso);
+    if (lane == 0) red[1] = giso;
+  }
+  consumer_bar();
+  if (tid < nred) {
+    double s = 0.0;
+#pragma unroll
+    for (int wdx = 0; wdx < CONSUMER_WARPS; wdx++) s += sRed[wdx * nred + tid];
+    p.partials[((long)blockIdx.y * gridDim.x + blockIdx.x) * nred + tid] = s;
+  }
+}
+
+int gemm_init() {
+  GPX_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<GEMM_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<GEMM_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<GEMM_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return 0;
+}
+
+int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t st) {
+  if (grid.x == 0 || grid.y == 0) return 0;
+  if (p.mode == GEMM_UPDATE) gemm_nt_kernel<GEMM_UPDATE><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  else if (p.mode == GEMM_PANEL) gemm_nt_kernel<GEMM_PANEL><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  else gemm_nt_kernel<GEMM_LAUUM><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gpx

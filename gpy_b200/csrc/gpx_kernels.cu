@@ -1,0 +1,548 @@
+// gpx_kernels.cu — the non-GEMM kernels of the exact-GP path: input scaling, covariance build, the 128x128 base
+// factor-and-invert block, triangular matrix-vector products, block assembly, result extraction, final reduction.
+#include "gpx_common.cuh"
+#include "gpx_kernels.cuh"
+
+namespace gpx {
+
+// =================================================================================================================
+// prep: scaled inputs in SoA layout + squared norms.
+// Reference: Stationary._scaled_dist (stationary.py:151-168: ARD divides X by the lengthscale BEFORE the distance
+// expansion; iso leaves X alone and divides r afterwards) and the Xsq row sums of _unscaled_dist (:136).
+// =================================================================================================================
+__global__ void prep_x_kernel(const double* __restrict__ X, long N, long ldx, KernParams kp, double* __restrict__ XsT,
+                              double* __restrict__ sq) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ldx) return;
+  double s = 0.0;
+  for (int q = 0; q < kp.D; q++) {
+    double v = 0.0;
+    if (i < N) {
+      v = X[i * kp.D + q];
+      if (kp.ard) v = v / kp.ls[q];
+    }
+    XsT[(long)q * ldx + i] = v;
+    s += v * v;
+  }
+  sq[i] = s;
+}
+
+int launch_prep_x(const double* X, long N, long ldx, const KernParams& kp, double* XsT, double* sq, cudaStream_t st) {
+  prep_x_kernel<<<(unsigned)((ldx + 255) / 256), 256, 0, st>>>(X, N, ldx, kp, XsT, sq);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
+// covariance build.  out(rowidx, colidx) at out[rowidx + colidx*ld]; the thread-mapped (contiguous) index is the
+// ROW operand. One CTA = one 128x128 tile; the two D x 128 input tiles (SoA) and their squared norms are staged in
+// shared memory by 1-D bulk async copies (TMA engine) on an mbarrier; each thread keeps its row point in registers
+// and walks 64 columns, writing 256-byte-per-warp coalesced column segments.
+// Reference: stationary.py:130-148 (_unscaled_dist: |x|^2+|x'|^2-2x.x', diagonal forced to 0, clip at 0, sqrt),
+// :151-168 (scaling), K_of_r (rbf.py:51-52; stationary.py:382-383,488-489,585-586), and, in `sym` mode,
+// Ky = K + (noise + jitter) I (exact_gaussian_inference.py:55-56) written straight into the factor workspace
+// (lower tiles; upper tiles zero = the initial state of the inverse-factor region; padding = identity).
+// =================================================================================================================
+template <int DREG>
+__global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int D = p.kp.D;
+  double* sR = reinterpret_cast<double*>(smem_raw);          // [D][128] row-operand points
+  double* sC = sR + (size_t)D * TILE;                        // [D][128] col-operand points
+  double* sSr = sC + (size_t)D * TILE;
+  double* sSc = sSr + TILE;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sSc + TILE);
+
+  const int ct = blockIdx.x, rt = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int il = tid & (TILE - 1), half = tid >> 7;
+  const long gi = (long)rt * TILE + il;
+  double* outp = p.out + gi + ((long)ct * TILE + half * 64) * p.ld;
+
+  if (p.sym && rt < ct) {  // strictly-upper tile of the factor workspace: the inverse-factor region starts at zero
+    for (int j = 0; j < 64; j++) outp[(long)j * p.ld] = 0.0;
+    return;
+  }
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar, (uint32_t)((2 * D + 2) * TILE * 8));
+    for (int q = 0; q < D; q++) {
+      bulk_g2s(sR + q * TILE, p.rowsT + (long)q * p.ld_rows + (long)rt * TILE, TILE * 8, bar);
+      bulk_g2s(sC + q * TILE, p.colsT + (long)q * p.ld_cols + (long)ct * TILE, TILE * 8, bar);
+    }
+    bulk_g2s(sSr, p.sq_rows + (long)rt * TILE, TILE * 8, bar);
+    bulk_g2s(sSc, p.sq_cols + (long)ct * TILE, TILE * 8, bar);
+  }
+  mbar_wait(bar, 0);
+
+  double xi[DREG];
+#pragma unroll
+  for (int q = 0; q < DREG; q++) xi[q] = q < D ? sR[q * TILE + il] : 0.0;
+  const double si = sSr[il];
+  const int kind = p.kp.kind;
+  const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  const bool row_valid = gi < p.nrows;
+#pragma unroll 2
+  for (int j = 0; j < 64; j++) {
+    const int jl = half * 64 + j;
+    const long gj = (long)ct * TILE + jl;
+    double dot = 0.0;
+#pragma unroll
+    for (int q = 0; q < DREG; q++)
+      if (q < D) dot = fma(xi[q], sC[q * TILE + jl], dot);
+    double r2 = si + sSc[jl] - 2.0 * dot;
+    if (p.same && gi == gj) r2 = 0.0;
+    r2 = fmax(r2, 0.0);
+    const double rr = sqrt(r2) * inv_ls;
+    double v = variance * k_of_r_unit(kind, rr);
+    if (p.sym) {
+      if (gi == gj) v = v + p.diag_add;
+      if (!row_valid || gj >= p.ncols) v = (gi == gj) ? 1.0 : 0.0;
+      outp[(long)j * p.ld] = v;
+    } else if (row_valid && gj < p.ncols) {
+      outp[(long)j * p.ld] = v;
+    }
+  }
+}
+
+int launch_kbuild(const KBuildParams& p, int row_tiles, int col_tiles, cudaStream_t st) {
+  const int D = p.kp.D;
+  const size_t smem = (size_t)(2 * D + 2) * TILE * 8 + 16;
+  dim3 grid(col_tiles, row_tiles);
+#define GPX_KB(DR)                                                                                              \
+  do {                                                                                                          \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      GPX_CUDA(cudaFuncSetAttribute(kbuild_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                    (int)((2 * MAX_D + 2) * TILE * 8 + 16)));                                   \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    kbuild_kernel<DR><<<grid, 256, smem, st>>>(p);                                                              \
+  } while (0)
+  if (D <= 8) GPX_KB(8);
+  else if (D <= 16) GPX_KB(16);
+  else if (D <= 32) GPX_KB(32);
+  else GPX_KB(64);
+#undef GPX_KB
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
+// base block: unified factor-and-invert sweep of one 128x128 diagonal tile, register resident.
+// 512 threads; lane a owns rows a+32s (s<4), warp b owns columns b+16t (t<8): 32 fp64 values per thread.
+// Column j: the owner warp turns column j of the tile (lower part = A, upper part = inverse region) into the vector
+// p = column / l_jj with p_j = 1/l_jj, publishes it through a double-buffered shared vector (ONE barrier per column),
+// and every thread applies  v(row,col) -= p_row p_col  for col > j and (row >= col or row <= j).
+// On exit: lower = L_dd (to the Ldiag strip), strict upper + reciprocal diagonal = U_dd = L_dd^-T (written back to
+// the tile itself: the diagonal tiles of the workspace hold U), Dinv strip = L_dd^-1 (lower, column-major).
+// Replaces, for one block: lapack.dpotrf (GPy/util/linalg.py:58) and lapack.dtrtri (:227) incl. the
+// "not positive definite" detection that drives jitchol (:59-75).
+// =================================================================================================================
+__global__ void __launch_bounds__(512, 1)
+base_sweep_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, double* __restrict__ Dinv,
+                  double* __restrict__ logdet_part, int* __restrict__ info, int gcol0) {
+  __shared__ double pbuf[2][TILE];
+  __shared__ double ldiag[TILE];
+  const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
+  double v[4][8];
+#pragma unroll
+  for (int t = 0; t < 8; t++)
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int row = a + 32 * s, col = b + 16 * t;
+      v[s][t] = row >= col ? S[row + (long)col * ld] : 0.0;
+    }
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    for (int jb = 0; jb < 16; jb++) {
+      const int j = t * 16 + jb;
+      if (b == jb) {  // owner warp of column j (slot t); the diagonal element sits in lane j&31, row slot t>>1
+        const double d = __shfl_sync(0xffffffffu, v[t >> 1][t], j & 31);
+        if (!(d > 0.0) && a == 0) atomicCAS(info, 0, gcol0 + j + 1);
+        const double l = sqrt(d);
+        const double inv = 1.0 / l;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int row = a + 32 * s;
+          const double val = (row == j) ? inv : v[s][t] * inv;
+          pbuf[j & 1][row] = val;
+          v[s][t] = (row == j) ? l : val;
+        }
+        if (a == (j & 31)) ldiag[j] = l;
+      }
+      __syncthreads();
+      const double* p = pbuf[j & 1];
+      double pr[4];
+#pragma unroll
+      for (int s = 0; s < 4; s++) pr[s] = p[a + 32 * s];
+#pragma unroll
+      for (int t2 = 0; t2 < 8; t2++) {
+        if (t2 < t) continue;
+        if (t2 == t && b <= jb) continue;
+        const int col = b + 16 * t2;
+        const double pc = p[col];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int row = a + 32 * s;
+          if (row >= col || row <= j) v[s][t2] = fma(-pr[s], pc, v[s][t2]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // outputs
+#pragma unroll
+  for (int t = 0; t < 8; t++)
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int row = a + 32 * s, col = b + 16 * t;
+      const double x = v[s][t];
+      if (row > col) {
+        Ldiag[row + col * TILE] = x;          // L_dd strictly lower
+        S[row + (long)col * ld] = 0.0;        // U_dd is upper triangular
+        Dinv[col + row * TILE] = 0.0;         // L_dd^-1 is lower triangular: (col,row) above the diagonal
+      } else if (row == col) {
+        const double inv = 1.0 / x;
+        Ldiag[row + col * TILE] = x;
+        S[row + (long)col * ld] = inv;
+        Dinv[row + col * TILE] = inv;
+      } else {
+        Ldiag[row + col * TILE] = 0.0;
+        S[row + (long)col * ld] = x;          // U_dd(row,col) = (L_dd^-1)(col,row)
+        Dinv[col + row * TILE] = x;
+      }
+    }
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int j = threadIdx.x; j < TILE; j += 32) s += log(ldiag[j]);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *logdet_part = 2.0 * s;
+  }
+}
+
+int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
+                cudaStream_t st) {
+  base_sweep_kernel<<<1, 512, 0, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
+// assemble: after the inner sweep of an nb x nb diagonal block (lower tiles = L, upper tiles incl. diagonal = U_kk),
+// write  P[o.., :] = U_kk (block-upper part, zeros below) and Tm = U_kk^T = Linv_kk (nb x nb, column-major, ld = nb).
+// =================================================================================================================
+__global__ void assemble_kernel(const double* __restrict__ Sblk, long ld, int nb, double* __restrict__ Prows, long ldp,
+                                double* __restrict__ Tm) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // bx: column block, by: row block
+  const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int row = by + tx, col = bx + k;
+    const double x = (row / TILE <= col / TILE) ? Sblk[row + (long)col * ld] : 0.0;
+    Prows[row + (long)col * ldp] = x;
+    tile[k][tx] = x;   // tile[col_local][row_local]
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    // Tm(row' = col, col' = row): write contiguous in row' -> threads along col
+    Tm[(bx + tx) + (long)(by + k) * nb] = tile[tx][k];
+  }
+}
+
+int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp, double* Tm, cudaStream_t st) {
+  dim3 grid(nb / 32, nb / 32), block(32, 8);
+  assemble_kernel<<<grid, block, 0, st>>>(Sblk, ld, nb, Prows, ldp, Tm);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
+// triangular matrix-vector products with U = L^-T (upper, column-major, diagonal tiles included):
+//   t = U^T y  (= L^-1 y)      one warp per column, coalesced column walk
+//   a = U t    (= Ky^-1 y)     thread per row, k-range split over blockIdx.y, partials reduced in fixed order
+// Replaces lapack.dpotrs (GPy/util/linalg.py:116-125; exact_gaussian_inference.py:60).
+// =================================================================================================================
+__global__ void __launch_bounds__(256) utv_kernel(const double* __restrict__ U, long ld, long n, int P,
+                                                  const double* __restrict__ Y /*[P][ld]*/, double* __restrict__ T) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long col = (long)blockIdx.x * 8 + warp;
+  if (col >= n) return;
+  const long kend = (col / TILE + 1) * TILE;  // zeros below the diagonal inside the diagonal tile
+  const double* u = U + col * ld;
+  double acc[MAX_P];
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+  for (long k = lane; k < kend; k += 32) {
+    const double x = u[k];
+#pragma unroll
+    for (int q = 0; q < MAX_P; q++)
+      if (q < P) acc[q] = fma(x, Y[(long)q * ld + k], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++)
+    if (q < P) {
+      const double s = warp_sum(acc[q]);
+      if (lane == 0) T[(long)q * ld + col] = s;
+    }
+}
+
+__global__ void __launch_bounds__(TILE) uv_partial_kernel(const double* __restrict__ U, long ld, long n, int P,
+                                                          const double* __restrict__ T, int ksplit,
+                                                          double* __restrict__ part /*[ksplit][P][ld]*/) {
+  const long row = (long)blockIdx.x * TILE + threadIdx.x;
+  const long k0 = (long)blockIdx.x * TILE;   // U(row, k) = 0 for k < row's tile start (upper triangular)
+  const long span = n - k0;
+  const long chunk = ((span + ksplit - 1) / ksplit + 7) / 8 * 8;
+  const long kb = k0 + (long)blockIdx.y * chunk;
+  const long ke = kb + chunk < n ? kb + chunk : n;
+  double acc[MAX_P];
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+  for (long k = kb; k < ke; k++) {
+    const double x = U[row + k * ld];
+#pragma unroll
+    for (int q = 0; q < MAX_P; q++)
+      if (q < P) acc[q] = fma(x, T[(long)q * ld + k], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++)
+    if (q < P) part[((long)blockIdx.y * P + q) * ld + row] = acc[q];
+}
+
+__global__ void uv_reduce_kernel(const double* __restrict__ part, long ld, int P, int ksplit, double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld * P) return;
+  const long q = i / ld, row = i % ld;
+  double s = 0.0;
+  for (int k = 0; k < ksplit; k++) s += part[((long)k * P + q) * ld + row];
+  out[q * ld + row] = s;
+}
+
+int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st) {
+  utv_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(U, ld, n, P, Y, T);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_uv(const double* U, long ld, long n, int P, const double* T, int ksplit, double* part, double* out,
+              cudaStream_t st) {
+  dim3 grid((unsigned)(n / TILE), ksplit);
+  uv_partial_kernel<<<grid, TILE, 0, st>>>(U, ld, n, P, T, ksplit, part);
+  GPX_CUDA(cudaGetLastError());
+  uv_reduce_kernel<<<(unsigned)((ld * P + 255) / 256), 256, 0, st>>>(part, ld, P, ksplit, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
+// finalize: fixed-order reduction of the per-tile gradient partials, log-determinant and quadratic form;
+// assembles the log marginal likelihood (exact_gaussian_inference.py:62) and the gradient vector
+// [d/d variance, d/d lengthscale(s), d/d noise] (stationary.py:199,210,213; gaussian.py:78-79).
+// res: [0]=lml, [1..nl+2]=gradient, [nl+3]=logdet, [nl+4]=y^T Ky^-1 y
+// =================================================================================================================
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams f) {
+  __shared__ double sh[256];
+  __shared__ double tot[MAX_D + 8];
+  const int tid = threadIdx.x;
+  const int nred = f.nl + 2;
+  for (int t = 0; t < nred; t++) {
+    double s = 0.0;
+    for (long i = tid; i < f.ntiles; i += 256) s += f.partials[i * nred + t];
+    sh[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) sh[tid] += sh[tid + o]; __syncthreads(); }
+    if (tid == 0) tot[t] = sh[0];
+    __syncthreads();
+  }
+  {  // logdet
+    double s = 0.0;
+    for (long i = tid; i < f.nt; i += 256) s += f.logdet_part[i];
+    sh[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) sh[tid] += sh[tid + o]; __syncthreads(); }
+    if (tid == 0) tot[nred] = sh[0];
+    __syncthreads();
+  }
+  {  // y^T Ky^-1 y = |L^-1 y|^2
+    double s = 0.0;
+    for (int q = 0; q < f.P; q++)
+      for (long i = tid; i < f.N; i += 256) { const double x = f.T[(long)q * f.ld + i]; s = fma(x, x, s); }
+    sh[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) sh[tid] += sh[tid + o]; __syncthreads(); }
+    if (tid == 0) tot[nred + 1] = sh[0];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double logdet = tot[nred], quad = tot[nred + 1];
+    const double log2pi = 1.8378770664093453;
+    f.res[0] = 0.5 * (-(double)f.N * f.P * log2pi - (double)f.P * logdet - quad);
+    f.res[1] = tot[0];
+    if (f.kp.ard) {
+      for (int q = 0; q < f.nl; q++) f.res[2 + q] = -tot[1 + q] / f.kp.ls[q];   // -(sum T (x-x')^2)/l^3, x unscaled
+    } else {
+      f.res[2] = -tot[1] / f.kp.ls[0];
+    }
+    f.res[2 + f.nl] = tot[nred - 1];
+    f.res[3 + f.nl] = logdet;
+    f.res[4 + f.nl] = quad;
+  }
+}
+
+int launch_finalize(const FinalizeParams& f, cudaStream_t st) {
+  finalize_kernel<<<1, 256, 0, st>>>(f);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
+// extraction of N x N results into a dense column-major N x N staging buffer (ld = N) for the device->host copy
+// =================================================================================================================
+__global__ void extract_kernel(int which, const double* __restrict__ S, long ld, const double* __restrict__ Ldiag,
+                               const double* __restrict__ Kinv, const double* __restrict__ alpha, int P, long N,
+                               double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // row (contiguous in out)
+  const long j = blockIdx.y;
+  if (i >= N) return;
+  const long ti = i / TILE, tj = j / TILE;
+  double v = 0.0;
+  if (which == GPX_GET_L) {
+    if (ti > tj) v = S[i + j * ld];
+    else if (ti == tj) v = Ldiag[ti * TILE * TILE + (i % TILE) + (j % TILE) * TILE];
+  } else if (which == GPX_GET_LINV) {
+    if (i >= j) v = S[j + i * ld];   // Linv(i,j) = U(j,i)
+  } else {  // KINV / DLDK from the lower-tile K^-1 store
+    const double kinv = (ti > tj || (ti == tj)) ? Kinv[i + j * ld] : Kinv[j + i * ld];
+    if (which == GPX_GET_KINV) v = kinv;
+    else {
+      double aa = 0.0;
+      for (int q = 0; q < P; q++) aa += alpha[(long)q * ld + i] * alpha[(long)q * ld + j];
+      v = 0.5 * (aa - (double)P * kinv);
+    }
+  }
+  out[i + j * N] = v;
+}
+
+int launch_extract(int which, const double* S, long ld, const double* Ldiag, const double* Kinv, const double* alpha,
+                   int P, long N, double* out, cudaStream_t st) {
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)N);
+  extract_kernel<<<grid, 256, 0, st>>>(which, S, ld, Ldiag, Kinv, alpha, P, N, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// transpose helpers for host layouts: in [rows][ld_in] (row index slow) -> out[cols... ] generic small kernels
+__global__ void transpose_pad_kernel(const double* __restrict__ in, long n, int p, long ld, double* __restrict__ out) {
+  // in: n x p row-major (host Y layout) -> out: [p][ld] (SoA), zero padded
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  for (int q = 0; q < p; q++) out[(long)q * ld + i] = i < n ? in[i * p + q] : 0.0;
+}
+int launch_transpose_pad(const double* in, long n, int p, long ld, double* out, cudaStream_t st) {
+  transpose_pad_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, st>>>(in, n, p, ld, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void untranspose_kernel(const double* __restrict__ in, long n, int p, long ld, double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int q = 0; q < p; q++) out[i * p + q] = in[(long)q * ld + i];
+}
+int launch_untranspose(const double* in, long n, int p, long ld, double* out, cudaStream_t st) {
+  untranspose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, n, p, ld, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
+// generic (unfused) gradient reduction for a caller-supplied dL_dK: Stationary.update_gradients_full
+// (stationary.py:193-243) for K(X, X2), dL_dK row-major N x M. One CTA per (128 x 128) tile, thread-mapped index is
+// the X2 point (contiguous in the row-major dL_dK), per-tile partials reduced by finalize-style fixed order on host.
+// =================================================================================================================
+__global__ void __launch_bounds__(256) grad_full_kernel(GradFullParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int D = p.kp.D;
+  double* sR = reinterpret_cast<double*>(smem_raw);   // [D][128] thread-mapped operand (X2 points, index j)
+  double* sC = sR + (size_t)D * TILE;                 // [D][128] walked operand (X points, index i)
+  double* sSr = sC + (size_t)D * TILE;
+  double* sSc = sSr + TILE;
+  double* sRed = sSc + TILE;                          // [8 warps][nred]
+  const int jt = blockIdx.x, it = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < D * TILE; idx += 256) {
+    const int q = idx / TILE, m = idx % TILE;
+    sR[idx] = p.x2T[(long)q * p.ld2 + (long)jt * TILE + m];
+    sC[idx] = p.x1T[(long)q * p.ld1 + (long)it * TILE + m];
+  }
+  if (tid < TILE) { sSr[tid] = p.sq2[(long)jt * TILE + tid]; sSc[tid] = p.sq1[(long)it * TILE + tid]; }
+  __syncthreads();
+  const int jl = tid & (TILE - 1), half = tid >> 7;
+  const long gj = (long)jt * TILE + jl;
+  const int nl = p.kp.ard ? D : 1;
+  const int nred = nl + 1;
+  const int warp = tid >> 5, lane = tid & 31;
+  double gvar = 0.0, giso = 0.0;
+  // ARD accumulators live in shared memory per thread column to keep registers bounded: loop q outermost instead
+  const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  // pass 1: variance + iso lengthscale, and (ARD) nothing cached: recompute per q (D small) — simple and exact
+  for (int qq = -1; qq < (p.kp.ard ? D : 0); qq++) {
+    double gq = 0.0;
+    for (int ii = 0; ii < 64; ii++) {
+      const int il = half * 64 + ii;
+      const long gi = (long)it * TILE + il;
+      if (gi >= p.N || gj >= p.M) continue;
+      double dot = 0.0;
+      for (int q = 0; q < D; q++) dot = fma(sR[q * TILE + jl], sC[q * TILE + il], dot);
+      double r2 = sSr[jl] + sSc[il] - 2.0 * dot;
+      if (p.same && gi == gj) r2 = 0.0;
+      r2 = fmax(r2, 0.0);
+      const double rr = sqrt(r2) * inv_ls;
+      double k, dk;
+      k_dk_of_r_unit(p.kp.kind, rr, k, dk);
+      const double dl = p.dL_dK[gi * p.M + gj];
+      const double G = variance * dk * dl;
+      if (qq < 0) {
+        gvar = fma(k, dl, gvar);
+        giso = fma(G, rr, giso);
+      } else {
+        const double tmpv = (rr != 0.0) ? G / rr : 0.0;
+        const double df = sR[qq * TILE + jl] - sC[qq * TILE + il];
+        gq = fma(tmpv, df * df, gq);
+      }
+    }
+    if (qq >= 0) {
+      gq = warp_sum(gq);
+      if (lane == 0) sRed[warp * nred + 1 + qq] = gq;
+    }
+  }
+  gvar = warp_sum(gvar);
+  giso = warp_sum(giso);
+  if (lane == 0) {
+    sRed[warp * nred + 0] = gvar;
+    if (!p.kp.ard) sRed[warp * nred + 1] = giso;
+  }
+  __syncthreads();
+  if (tid < nred) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += sRed[w * nred + tid];
+    p.partials[((long)blockIdx.y * gridDim.x + blockIdx.x) * nred + tid] = s;
+  }
+}
+
+int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStream_t st) {
+  const int D = p.kp.D;
+  const size_t smem = (size_t)(2 * D + 2) * TILE * 8 + 8 * (MAX_D + 2) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPX_CUDA(cudaFuncSetAttribute(grad_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((2 * MAX_D + 2) * TILE * 8 + 8 * (MAX_D + 2) * 8)));
+    attr_set = true;
+  }
+  dim3 grid(tiles_j, tiles_i);
+  grad_full_kernel<<<grid, 256, smem, st>>>(p);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gpx

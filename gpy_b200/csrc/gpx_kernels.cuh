@@ -1,0 +1,51 @@
+// gpx_kernels.cuh — launch wrappers of the non-GEMM kernels (internal).
+#pragma once
+#include "gpx_common.cuh"
+
+namespace gpx {
+
+struct KBuildParams {
+  const double* rowsT; long ld_rows;   // thread-mapped operand, SoA [D][ld_rows]
+  const double* colsT; long ld_cols;   // walked operand
+  const double* sq_rows; const double* sq_cols;
+  double* out; long ld;                // out[rowidx + colidx*ld]
+  long nrows, ncols;                   // logical extents (beyond: padding)
+  int sym;                             // 1: factor workspace mode (lower tiles, zero upper tiles, identity padding, +diag_add)
+  int same;                            // 1: both operands are the same point set -> exact zero distance on the diagonal
+  double diag_add;                     // noise + jitter (sym mode)
+  KernParams kp;
+};
+
+struct FinalizeParams {
+  const double* partials; long ntiles; int nl;
+  const double* logdet_part; long nt;
+  const double* T; long ld; long N; int P;
+  KernParams kp;
+  double* res;
+};
+
+struct GradFullParams {
+  const double* x1T; long ld1; const double* sq1; long N;   // X  (index i, rows of dL_dK)
+  const double* x2T; long ld2; const double* sq2; long M;   // X2 (index j, contiguous in dL_dK)
+  const double* dL_dK;                                       // N x M row-major
+  int same;
+  double* partials;
+  KernParams kp;
+};
+
+int launch_prep_x(const double* X, long N, long ldx, const KernParams& kp, double* XsT, double* sq, cudaStream_t st);
+int launch_kbuild(const KBuildParams& p, int row_tiles, int col_tiles, cudaStream_t st);
+int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
+                cudaStream_t st);
+int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp, double* Tm, cudaStream_t st);
+int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st);
+int launch_uv(const double* U, long ld, long n, int P, const double* T, int ksplit, double* part, double* out,
+              cudaStream_t st);
+int launch_finalize(const FinalizeParams& f, cudaStream_t st);
+int launch_extract(int which, const double* S, long ld, const double* Ldiag, const double* Kinv, const double* alpha,
+                   int P, long N, double* out, cudaStream_t st);
+int launch_transpose_pad(const double* in, long n, int p, long ld, double* out, cudaStream_t st);
+int launch_untranspose(const double* in, long n, int p, long ld, double* out, cudaStream_t st);
+int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStream_t st);
+
+}  // namespace gpx

@@ -1,0 +1,177 @@
+"""Host-side mirror of GPy's stationary-kernel plugin interface, computing on the B200 through libgpx.
+
+Same names, argument meaning and error behaviour as the reference classes:
+    GPy.kern.RBF           GPy/kern/src/rbf.py:13-52,177-178
+    GPy.kern.Exponential   GPy/kern/src/stationary.py:378-386
+    GPy.kern.Matern32      GPy/kern/src/stationary.py:457-492
+    GPy.kern.Matern52      GPy/kern/src/stationary.py:556-589
+base: GPy.kern.src.stationary.Stationary (stationary.py:23-243) and GPy.kern.Kern (kern.py:12-145).
+`K`, `Kdiag`, `update_gradients_full`, `update_gradients_diag` take/return NumPy arrays exactly like the reference;
+there is no NumPy implementation behind them — every call goes through the C ABI (include/gpx.h).
+"""
+import numpy as np
+
+from . import _ffi
+from .param import Param, Parameterized
+
+
+class DeviceGradient(object):
+    """Lazy, device-backed stand-in for the N x N `dL_dK` that ExactGaussianInference hands to
+    `kern.update_gradients_full` (GPy/core/gp.py:278-280). The fused device evaluation has already reduced it to
+    the kernel's parameter gradients; this handle carries them (keyed by the kernel state they were computed for)
+    and only materialises the matrix (2 GiB at N=16384) if somebody treats it as an ndarray."""
+
+    def __init__(self, engine, key, dvariance, dlengthscale, N):
+        self._engine, self._key = engine, key
+        self.dvariance, self.dlengthscale = dvariance, dlengthscale
+        self.shape = (N, N)
+        self.ndim = 2
+        self.dtype = np.dtype(np.float64)
+        self._host = None
+
+    def matches(self, key):
+        return self._key == key
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            self._host = np.ascontiguousarray(self._engine.get("dL_dK"))  # symmetric: C == F order
+        return self._host if dtype is None else self._host.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.__array__()[idx]
+
+
+class Kern(Parameterized):
+    """Subset of GPy.kern.Kern (kern.py:12-145) the exact-GP path uses: active_dims slicing + the abstract plugin
+    methods."""
+
+    def __init__(self, input_dim, active_dims, name):
+        super(Kern, self).__init__(name)
+        self.input_dim = int(input_dim)
+        if active_dims is None:
+            active_dims = np.arange(self.input_dim)
+        self.active_dims = np.atleast_1d(np.asarray(active_dims, dtype=np.int64))
+        assert self.active_dims.size == self.input_dim, "input_dim=%d does not match len(active_dim)=%d" % (
+            self.input_dim, self.active_dims.size)
+
+    def _slice_X(self, X):
+        """kern.py:112-117: column-select the active dims and cast to float."""
+        X = np.asarray(X)
+        if X.shape[1] == self.input_dim and np.array_equal(self.active_dims, np.arange(self.input_dim)):
+            return np.ascontiguousarray(X, dtype=np.float64)
+        return np.ascontiguousarray(X[:, self.active_dims], dtype=np.float64)
+
+    def K(self, X, X2=None):
+        raise NotImplementedError
+
+    def Kdiag(self, X):
+        raise NotImplementedError
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        raise NotImplementedError
+
+
+class Stationary(Kern):
+    """GPy.kern.src.stationary.Stationary (stationary.py:23-243): variance + (ARD) lengthscale, K = K_of_r(r)."""
+
+    _kind = None
+
+    def __init__(self, input_dim, variance=1., lengthscale=None, ARD=False, active_dims=None, name="stationary"):
+        super(Stationary, self).__init__(input_dim, active_dims, name)
+        self.ARD = bool(ARD)
+        # stationary.py:61-77: default / shape checking of the lengthscale
+        if not ARD:
+            if lengthscale is None:
+                lengthscale = np.ones(1)
+            else:
+                lengthscale = np.asarray(lengthscale, dtype=np.float64)
+                assert lengthscale.size == 1, "Only 1 lengthscale needed for non-ARD kernel"
+        else:
+            if lengthscale is not None:
+                lengthscale = np.asarray(lengthscale, dtype=np.float64)
+                assert lengthscale.size in [1, input_dim], "Bad number of lengthscales"
+                if lengthscale.size != input_dim:
+                    lengthscale = np.ones(input_dim) * lengthscale
+            else:
+                lengthscale = np.ones(self.input_dim)
+        self.lengthscale = Param("lengthscale", lengthscale)
+        self.variance = Param("variance", variance)
+        assert self.variance.size == 1
+        self.link_parameters(self.variance, self.lengthscale)  # stationary.py:81
+
+    # -- state key used to recognise gradients precomputed by the fused evaluation ------------------------------
+    def _state_key(self):
+        return (self._kind, self.ARD, float(self.variance[0]), tuple(self.lengthscale.values.tolist()),
+                tuple(self.active_dims.tolist()))
+
+    def _theta(self):
+        ls = self.lengthscale.values if self.ARD else self.lengthscale.values[0]
+        return self._kind, self.ARD, float(self.variance[0]), ls
+
+    # -- plugin interface -------------------------------------------------------------------------------------
+    def K(self, X, X2=None):
+        """stationary.py:105-115 -> gpx_kern_K."""
+        X = self._slice_X(X)
+        X2 = None if X2 is None else self._slice_X(X2)
+        kind, ard, var, ls = self._theta()
+        return _ffi.kern_K(kind, ard, var, ls, X, X2)
+
+    def Kdiag(self, X):
+        """stationary.py:170-173 -> gpx_kern_Kdiag."""
+        return _ffi.kern_Kdiag(self._kind, float(self.variance[0]), int(np.asarray(X).shape[0]))
+
+    def update_gradients_full(self, dL_dK, X, X2=None, reset=True):
+        """stationary.py:193-213. A DeviceGradient handle from our ExactGaussianInference short-circuits to the
+        gradients the fused epilogue already reduced on the device; any other dL_dK goes through gpx_kern_grad_full."""
+        if isinstance(dL_dK, DeviceGradient) and X2 is None and dL_dK.matches(self._state_key()):
+            self.variance.gradient = np.atleast_1d(dL_dK.dvariance)
+            self.lengthscale.gradient = np.atleast_1d(dL_dK.dlengthscale).copy()
+            return
+        Xs = self._slice_X(X)
+        X2s = None if X2 is None else self._slice_X(X2)
+        kind, ard, var, ls = self._theta()
+        dv, dl = _ffi.kern_grad_full(kind, ard, var, ls, Xs, np.asarray(dL_dK, dtype=np.float64), X2s)
+        self.variance.gradient = np.atleast_1d(dv)
+        self.lengthscale.gradient = np.atleast_1d(dl)
+
+    def update_gradients_diag(self, dL_dKdiag, X):
+        """stationary.py:182-192."""
+        self.variance.gradient = np.atleast_1d(np.sum(dL_dKdiag))
+        self.lengthscale.gradient = np.zeros_like(self.lengthscale.values)
+
+    def reset_gradients(self):
+        """stationary.py:175-180."""
+        self.variance.gradient = np.zeros(1)
+        self.lengthscale.gradient = np.zeros_like(self.lengthscale.values)
+
+
+class RBF(Stationary):
+    """GPy.kern.RBF (rbf.py:13-52): k(r) = variance * exp(-0.5 r^2)."""
+    _kind = "rbf"
+
+    def __init__(self, input_dim, variance=1., lengthscale=None, ARD=False, active_dims=None, name="rbf"):
+        super(RBF, self).__init__(input_dim, variance, lengthscale, ARD, active_dims, name)
+
+
+class Exponential(Stationary):
+    """GPy.kern.Exponential (stationary.py:378-386): k(r) = variance * exp(-r)."""
+    _kind = "exponential"
+
+    def __init__(self, input_dim, variance=1., lengthscale=None, ARD=False, active_dims=None, name="Exponential"):
+        super(Exponential, self).__init__(input_dim, variance, lengthscale, ARD, active_dims, name)
+
+
+class Matern32(Stationary):
+    """GPy.kern.Matern32 (stationary.py:457-492)."""
+    _kind = "matern32"
+
+    def __init__(self, input_dim, variance=1., lengthscale=None, ARD=False, active_dims=None, name="Mat32"):
+        super(Matern32, self).__init__(input_dim, variance, lengthscale, ARD, active_dims, name)
+
+
+class Matern52(Stationary):
+    """GPy.kern.Matern52 (stationary.py:556-589)."""
+    _kind = "matern52"
+
+    def __init__(self, input_dim, variance=1., lengthscale=None, ARD=False, active_dims=None, name="Mat52"):
+        super(Matern52, self).__init__(input_dim, variance, lengthscale, ARD, active_dims, name)

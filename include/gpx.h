@@ -1,0 +1,120 @@
+/* gpx.h — C ABI of the B200-native exact-GP engine (libgpx.so).
+ *
+ * This is the drop-in boundary for ONE hot path of SheffieldML/GPy:
+ *     GPRegression -> GP.parameters_changed -> ExactGaussianInference.inference -> Kern.K/Kdiag/update_gradients_full
+ * Each entry point names the reference interface it replaces (paths relative to the GPy repository root).
+ * Plain C: pointers and sizes only, no torch / numpy types. All arithmetic is IEEE fp64.
+ *
+ * Conventions
+ *   - Return value: 0 ok; >0 "matrix not positive definite, leading minor <ret>" (the caller raises
+ *     numpy.linalg.LinAlgError as GPy/util/linalg.py:64,75 does); <0 CUDA / argument error, text via gpx_last_error().
+ *   - Host buffers are caller-owned and only read/written during the call. Device state lives behind gpx_ctx.
+ *   - Matrices returned to the host are column-major (Fortran order) N x N unless stated, which is the layout
+ *     LAPACK hands GPy (GPy/util/linalg.py:31-38 force_F_ordered); symmetric results are fully populated.
+ *   - kind: 0 RBF (GPy/kern/src/rbf.py:51-52,177-178), 1 Exponential (stationary.py:382-386),
+ *           2 Matern32 (stationary.py:488-492), 3 Matern52 (stationary.py:585-589).
+ *   - ard:  0 -> `lengthscale` points at 1 double; 1 -> at D doubles (stationary.py:64-79).
+ *   - Gradient vector order is paramz's: [kern.variance, kern.lengthscale (1 or D), Gaussian_noise.variance]
+ *     (link order stationary.py:81, GPy/core/gp.py:106-107).
+ */
+#ifndef GPX_H_
+#define GPX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpx_ctx gpx_ctx;
+
+enum { GPX_RBF = 0, GPX_EXPONENTIAL = 1, GPX_MATERN32 = 2, GPX_MATERN52 = 3 };
+
+/* gpx_get selectors */
+enum {
+  GPX_GET_L = 0,     /* woodbury_chol: lower Cholesky factor of K + (noise+jitter) I, N x N col-major, zeros above diag
+                        (GPy/inference/latent_function_inference/exact_gaussian_inference.py:58,74) */
+  GPX_GET_ALPHA = 1, /* woodbury_vector alpha = Ky^-1 Y, N x P row-major (exact_gaussian_inference.py:60) */
+  GPX_GET_KINV = 2,  /* Wi = Ky^-1, symmetric N x N (GPy/util/linalg.py:210-212) */
+  GPX_GET_DLDK = 3,  /* dL_dK = 0.5 (alpha alpha^T - P Ky^-1), symmetric N x N (exact_gaussian_inference.py:70) */
+  GPX_GET_K = 4,     /* noise-free K(X,X), symmetric N x N (exact_gaussian_inference.py:53) */
+  GPX_GET_LINV = 5   /* L^-1 lower, N x N col-major (GPy/util/linalg.py:209 dtrtri; unused by the exact-GP caller) */
+};
+
+/* Library / device ----------------------------------------------------------------------------------------------- */
+const char* gpx_last_error(void);      /* thread-local text of the last <0 return */
+const char* gpx_version(void);
+int gpx_device_count(void);            /* number of visible CUDA devices, <0 on error */
+
+/* One context per model: owns the stream(s), the N x N workspace and (multi-GPU) the NCCL communicator. */
+int gpx_create(int device, gpx_ctx** out);
+int gpx_destroy(gpx_ctx* ctx);
+
+/* Replaces Kern._slice_X + ObsAr wiring (GPy/kern/src/kern.py:112-117, GPy/core/gp.py:42-62): host X (N x D, row-major,
+ * already sliced to active dims) and Y (N x P row-major) are copied to HBM once per (X, Y) identity. */
+int gpx_set_data(gpx_ctx* ctx, const double* X, int64_t N, int D, const double* Y, int P);
+
+/* The hot call. Replaces, fused: Stationary.K (stationary.py:105-168) -> diag.add (exact_gaussian_inference.py:55-56)
+ * -> pdinv/jitchol/dpotri (GPy/util/linalg.py:56-75,193-214) -> dpotrs (:116-125) -> log marginal + dL_dK
+ * (exact_gaussian_inference.py:62-72) -> Stationary.update_gradients_full (stationary.py:193-243, incl.
+ * stationary_cython.pyx:53-62) -> Gaussian.exact_inference_gradients (GPy/likelihoods/gaussian.py:78-79).
+ *   jitter     : added unconditionally to the diagonal (the reference uses 1e-8, exact_gaussian_inference.py:56)
+ *   max_tries  : jitchol ladder length (reference: 5). On a non-PD factorisation the diagonal gets
+ *                mean(diag)*1e-6*10^k, k = 0..max_tries-1 (linalg.py:66-74); *jitter_used reports the extra jitter.
+ *   lml        : out, log marginal likelihood;  grad: out, (1 + (ard?D:1) + 1) doubles. */
+int gpx_exact_eval(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, double noise,
+                   double jitter, int max_tries, double* lml, double* grad, double* jitter_used);
+
+/* Lazy device->host fetch of N^2 / N*P results of the last gpx_exact_eval (Posterior / grad_dict consumers:
+ * GPy/inference/latent_function_inference/posterior.py:21-77; exact_gaussian_inference.py:74). */
+int gpx_get(gpx_ctx* ctx, int which, double* out_host);
+
+/* PosteriorExact._raw_predict (posterior.py:273-302) on device with the factor of the last eval:
+ * mu (M x P row-major) = K(X,Xnew)^T alpha; var (M) = Kdiag(Xnew) - colsum((L^-1 K(X,Xnew))^2)   [full_cov = 0]
+ * or var (M x M col-major) = K(Xnew) - tmp^T tmp                                                 [full_cov = 1]. */
+int gpx_predict(gpx_ctx* ctx, const double* Xnew, int64_t M, int full_cov, double* mu, double* var);
+
+/* Standalone kernel plugin calls (no context needed beyond a device; ctx may be NULL -> device 0 scratch context).
+ * Replaces Stationary.K (stationary.py:105-168): out is N x M ROW-major (what Kern.K returns to NumPy callers). */
+int gpx_kern_K(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* X, int64_t N,
+               const double* X2 /* NULL -> K(X,X) with exact zero-distance diagonal */, int64_t M, int D, double* out);
+/* Replaces Stationary.Kdiag (stationary.py:170-173). */
+int gpx_kern_Kdiag(int kind, double variance, int64_t N, double* out);
+/* Replaces Stationary.update_gradients_full (stationary.py:193-243) for a caller-supplied dL_dK (N x M row-major). */
+int gpx_kern_grad_full(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* X,
+                       int64_t N, const double* X2, int64_t M, int D, const double* dL_dK, double* dvariance,
+                       double* dlengthscale);
+
+/* Measurement hooks (bench.py): device time of the last eval between CUDA events on the launching stream, the number
+ * of kernels this library launched since creation, and per-phase accounting of the last eval. */
+typedef struct {
+  float total_ms;       /* whole eval, H2D of theta .. D2H of (lml, grad) */
+  float kbuild_ms;      /* covariance build kernel */
+  float sweep_ms;       /* blocked factor-and-invert sweep (all launches) */
+  float update_ms;      /* sum over the outer trailing-update GEMM launches (dominant kernel) */
+  float lauum_ms;       /* K^-1 = U U^T + fused gradient epilogue */
+  float solve_ms;       /* alpha / quadratic form */
+  double update_flops;  /* algorithmic flops executed by the outer trailing-update launches */
+  double lauum_flops;
+  double kbuild_bytes;  /* algorithmic bytes of the covariance build (8 N^2 + 8 N D) */
+  int64_t launches;     /* kernels launched by the last eval */
+  int32_t update_launches;
+  int32_t tries;        /* factorisation attempts (1 = no jitter ladder) */
+} gpx_stats;
+int gpx_get_stats(gpx_ctx* ctx, gpx_stats* out);
+int64_t gpx_total_launches(gpx_ctx* ctx);
+
+/* Tunables (block sizes etc.), mainly for tests: name in {"nb", "lookahead", "profile"}. */
+int gpx_set_option(gpx_ctx* ctx, const char* name, int64_t value);
+
+/* Multi-GPU (one process per GPU). The caller obtains a 128-byte NCCL unique id on rank 0 (gpx_comm_unique_id),
+ * ships it to the other ranks with its own plumbing (torch.distributed broadcast), and every rank calls
+ * gpx_comm_init. Afterwards gpx_set_data / gpx_exact_eval are collective: block rows are dealt block-cyclically
+ * to the ranks, panels are broadcast with ncclBroadcast over NVLink, scalars all-reduced. */
+int gpx_comm_unique_id(char id_out[128]);
+int gpx_comm_init(gpx_ctx* ctx, const char id[128], int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPX_H_ */

@@ -1,0 +1,363 @@
+"""CPU oracle: a line-by-line NumPy/SciPy restatement of the reference's exact-GP hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). Every function cites the reference file:line it
+follows (paths relative to /root/reference). The restatement issues the SAME LAPACK/BLAS entry points as
+the reference (dsyrk, dpotrf, dtrtri, dpotri, dpotrs, dtrtrs) in the same order, including the work the
+reference wastes (unused dtrtri, double symmetrify, second exp pass), so that timing it is timing the
+reference's operation sequence.
+"""
+import ctypes
+import os
+
+import numpy as np
+from scipy import linalg
+from scipy.linalg import blas, lapack
+
+KINDS = ("rbf", "exponential", "matern32", "matern52")
+LOG_2_PI = np.log(2.0 * np.pi)  # GPy/inference/latent_function_inference/exact_gaussian_inference.py:8
+JITTER = 1e-8  # exact_gaussian_inference.py:56 (unconditional)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPy/util/linalg.py, GPy/util/diag.py
+# ----------------------------------------------------------------------------------------------------------
+def symmetrify(A, upper=False):
+    """GPy/util/linalg.py:356-379 (+ linalg_cython.pyx:9-18): mirror one triangle onto the other, in place."""
+    triu = np.triu_indices_from(A, k=1)
+    if upper:
+        A.T[triu] = A[triu]
+    else:
+        A[triu] = A.T[triu]
+
+
+def tdot(mat):
+    """GPy/util/linalg.py:299-320 tdot_blas: X X^T via dsyrk(lower=0) then symmetrify(upper=True)."""
+    if mat.dtype != np.float64 or mat.ndim != 2:
+        return np.dot(mat, mat.T)
+    nn = mat.shape[0]
+    out = np.zeros((nn, nn))
+    mat = np.asfortranarray(mat)
+    out = blas.dsyrk(alpha=1.0, a=mat, beta=0.0, c=out, overwrite_c=1, trans=0, lower=0)
+    symmetrify(out, upper=True)
+    return np.ascontiguousarray(out)
+
+
+def diag_view(A):
+    """GPy/util/diag.py:6-40: strided view of the main diagonal."""
+    from numpy.lib.stride_tricks import as_strided
+    assert A.ndim == 2 and A.shape[0] == A.shape[1]
+    return as_strided(A, shape=(A.shape[0],), strides=((A.shape[0] + 1) * A.itemsize,))
+
+
+def diag_add(A, b):
+    """GPy/util/diag.py:48-52,85-98: A[i,i] += b in place (b squeezed)."""
+    b = np.squeeze(b)
+    dA = diag_view(A)
+    np.add(dA, b, dA)
+    return A
+
+
+def jitchol(A, maxtries=5):
+    """GPy/util/linalg.py:56-75: dpotrf(lower=1); on failure the jitter ladder mean(diag)*1e-6*10^k, k<maxtries.
+
+    Returns (L, jitter_used). Raises numpy.linalg.LinAlgError like the reference."""
+    A = np.ascontiguousarray(A)
+    L, info = lapack.dpotrf(A, lower=1)
+    if info == 0:
+        return L, 0.0
+    diagA = np.diag(A)
+    if np.any(diagA <= 0.0):
+        raise np.linalg.LinAlgError("not pd: non-positive diagonal elements")
+    jitter = diagA.mean() * 1e-6
+    num_tries = 1
+    while num_tries <= maxtries and np.isfinite(jitter):
+        try:
+            L = linalg.cholesky(A + np.eye(A.shape[0]) * jitter, lower=True)
+            return L, jitter
+        except Exception:
+            jitter *= 10
+        finally:
+            num_tries += 1
+    raise np.linalg.LinAlgError("not positive definite, even with jitter.")
+
+
+def dtrtri(L):
+    """GPy/util/linalg.py:217-227."""
+    return lapack.dtrtri(np.asfortranarray(L), lower=1)[0]
+
+
+def dpotri(L, lower=1):
+    """GPy/util/linalg.py:127-145: dpotri + symmetrify."""
+    R, info = lapack.dpotri(np.asfortranarray(L), lower=lower)
+    symmetrify(R)
+    return R, info
+
+
+def dpotrs(L, B, lower=1):
+    """GPy/util/linalg.py:116-125."""
+    return lapack.dpotrs(np.asfortranarray(L), B, lower=lower)
+
+
+def dtrtrs(A, B, lower=1, trans=0, unitdiag=0):
+    """GPy/util/linalg.py:95-114."""
+    return lapack.dtrtrs(np.asfortranarray(A), B, lower=lower, trans=trans, unitdiag=unitdiag)
+
+
+def pdinv(A):
+    """GPy/util/linalg.py:193-214: (Ai, L, Li, logdet) — including the dtrtri whose result the exact-GP caller
+    never uses (:209) and the second symmetrify (:212)."""
+    L, jit = jitchol(A)
+    logdet = 2.0 * np.sum(np.log(np.diag(L)))
+    Li = dtrtri(L)
+    Ai, _ = dpotri(L, lower=1)
+    symmetrify(Ai)
+    return Ai, L, Li, logdet
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPy/kern/src/stationary.py, rbf.py
+# ----------------------------------------------------------------------------------------------------------
+def unscaled_dist(X, X2=None):
+    """GPy/kern/src/stationary.py:130-148."""
+    if X2 is None:
+        Xsq = np.sum(np.square(X), 1)
+        r2 = -2.0 * tdot(X) + (Xsq[:, None] + Xsq[None, :])
+        diag_view(r2)[:, ] = 0.0  # :138 force diagonal to be zero
+        r2 = np.clip(r2, 0, np.inf)
+        return np.sqrt(r2)
+    X1sq = np.sum(np.square(X), 1)
+    X2sq = np.sum(np.square(X2), 1)
+    r2 = -2.0 * np.dot(X, X2.T) + (X1sq[:, None] + X2sq[None, :])
+    r2 = np.clip(r2, 0, np.inf)
+    return np.sqrt(r2)
+
+
+def scaled_dist(X, X2, lengthscale, ARD):
+    """GPy/kern/src/stationary.py:151-168: ARD divides X by l BEFORE the expansion, iso divides r AFTER."""
+    if ARD:
+        if X2 is not None:
+            X2 = X2 / lengthscale
+        return unscaled_dist(X / lengthscale, X2)
+    return unscaled_dist(X, X2) / lengthscale
+
+
+def K_of_r(kind, variance, r):
+    """rbf.py:51-52; stationary.py:382-383 (Exponential), :488-489 (Matern32), :585-586 (Matern52)."""
+    if kind == "rbf":
+        return variance * np.exp(-0.5 * r ** 2)
+    if kind == "exponential":
+        return variance * np.exp(-r)
+    if kind == "matern32":
+        return variance * (1.0 + np.sqrt(3.0) * r) * np.exp(-np.sqrt(3.0) * r)
+    if kind == "matern52":
+        return variance * (1 + np.sqrt(5.0) * r + 5.0 / 3 * r ** 2) * np.exp(-np.sqrt(5.0) * r)
+    raise ValueError(kind)
+
+
+def dK_dr(kind, variance, r):
+    """rbf.py:177-178; stationary.py:385-386, :491-492, :588-589."""
+    if kind == "rbf":
+        return -r * K_of_r(kind, variance, r)
+    if kind == "exponential":
+        return -K_of_r(kind, variance, r)
+    if kind == "matern32":
+        return -3.0 * variance * r * np.exp(-np.sqrt(3.0) * r)
+    if kind == "matern52":
+        return variance * (10.0 / 3 * r - 5.0 * r - 5.0 * np.sqrt(5.0) / 3 * r ** 2) * np.exp(-np.sqrt(5.0) * r)
+    raise ValueError(kind)
+
+
+def inv_dist(X, X2, lengthscale, ARD):
+    """GPy/kern/src/stationary.py:225-232: 1/r with 1/0 := 0."""
+    dist = scaled_dist(X, X2, lengthscale, ARD).copy()
+    return 1.0 / np.where(dist != 0.0, dist, np.inf)
+
+
+def lengthscale_grads_pure(tmp, X, X2, lengthscale):
+    """GPy/kern/src/stationary.py:234-235."""
+    Q = X.shape[1]
+    return -np.array([np.sum(tmp * np.square(X[:, q:q + 1] - X2[:, q:q + 1].T)) for q in range(Q)]) / lengthscale ** 3
+
+
+_native = {}
+
+
+def _load_native():
+    """Optional compiled helpers. `oracle/_ref/libstationary_utils.so` is the reference's own
+    GPy/kern/src/stationary_utils.c compiled where it lies (oracle/Makefile); `oracle/_build/liboracle_c.so`
+    is our C restatement of the serial Cython loop stationary_cython.pyx:53-62."""
+    if _native:
+        return _native
+    for key, rel in (("ref", "_ref/libstationary_utils.so"), ("port", "_build/liboracle_c.so")):
+        p = os.path.join(_HERE, rel)
+        _native[key] = ctypes.CDLL(p) if os.path.exists(p) else None
+    return _native
+
+
+def lengthscale_grads_native(tmp, X, X2, lengthscale, which="port"):
+    """stationary.py:237-243 -> stationary_cython.pyx:53-62 (serial q,n,m loop). `which='ref'` calls the
+    reference's own C `_lengthscale_grads` (stationary_utils.c:34-48, OpenMP over q)."""
+    lib = _load_native()[which]
+    if lib is None:
+        raise RuntimeError("native oracle helper '%s' not built (run `make -C oracle`)" % which)
+    N, M = tmp.shape
+    Q = X.shape[1]
+    X, X2, tmp = np.ascontiguousarray(X), np.ascontiguousarray(X2), np.ascontiguousarray(tmp)
+    grads = np.zeros(Q)
+    fn = lib._lengthscale_grads if which == "ref" else lib.oracle_lengthscale_grads
+    dp = ctypes.POINTER(ctypes.c_double)
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp]
+    fn.restype = None
+    fn(N, M, Q, tmp.ctypes.data_as(dp), X.ctypes.data_as(dp), X2.ctypes.data_as(dp), grads.ctypes.data_as(dp))
+    return -grads / lengthscale ** 3
+
+
+class StationaryOracle(object):
+    """Restates GPy.kern.src.stationary.Stationary (stationary.py:23-243) for the four hot-path kernels.
+    `lengthscale` is a scalar (iso) or a length-D vector (ARD), as in stationary.py:64-79."""
+
+    def __init__(self, kind, input_dim, variance=1.0, lengthscale=None, ARD=False, native=None):
+        assert kind in KINDS
+        self.kind, self.input_dim, self.ARD = kind, input_dim, ARD
+        self.variance = float(variance)
+        if lengthscale is None:
+            lengthscale = np.ones(input_dim) if ARD else 1.0
+        self.lengthscale = np.asarray(lengthscale, dtype=np.float64).reshape(-1)
+        if ARD:
+            assert self.lengthscale.size == input_dim
+        else:
+            assert self.lengthscale.size == 1
+        self.native = native  # None -> pure NumPy ARD reduction; "port"/"ref" -> compiled loops
+        self.variance_gradient = None
+        self.lengthscale_gradient = None
+
+    def _r(self, X, X2=None):
+        return scaled_dist(X, X2, self.lengthscale, self.ARD)
+
+    def K(self, X, X2=None):
+        """stationary.py:105-115."""
+        return K_of_r(self.kind, self.variance, self._r(X, X2))
+
+    def Kdiag(self, X):
+        """stationary.py:170-173."""
+        ret = np.empty(X.shape[0])
+        ret[:] = self.variance
+        return ret
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        """stationary.py:193-213."""
+        self.variance_gradient = np.sum(self.K(X, X2) * dL_dK) / self.variance
+        dL_dr = dK_dr(self.kind, self.variance, self._r(X, X2)) * dL_dK  # recomputes exp like dK_dr_via_X
+        if self.ARD:
+            tmp = dL_dr * inv_dist(X, X2, self.lengthscale, self.ARD)
+            if X2 is None:
+                X2 = X
+            if self.native:
+                self.lengthscale_gradient = lengthscale_grads_native(tmp, X, X2, self.lengthscale, self.native)
+            else:
+                self.lengthscale_gradient = lengthscale_grads_pure(tmp, X, X2, self.lengthscale)
+        else:
+            r = self._r(X, X2)
+            self.lengthscale_gradient = np.atleast_1d(-np.sum(dL_dr * r) / self.lengthscale)
+        return self.variance_gradient, self.lengthscale_gradient
+
+    def update_gradients_diag(self, dL_dKdiag, X):
+        """stationary.py:175-183 (reset-style diag gradient: variance only)."""
+        self.variance_gradient = np.sum(dL_dKdiag)
+        self.lengthscale_gradient = np.zeros_like(self.lengthscale)
+        return self.variance_gradient, self.lengthscale_gradient
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPy/inference/latent_function_inference/exact_gaussian_inference.py, posterior.py, likelihoods/gaussian.py
+# ----------------------------------------------------------------------------------------------------------
+def exact_inference(kern, X, Y, noise_variance, K=None):
+    """exact_gaussian_inference.py:37-74 with mean_function=None, Z_tilde=None.
+
+    Returns dict(L, alpha, K, Wi, logdet, log_marginal, dL_dK, dL_dthetaL, dL_dm)."""
+    YYT_factor = Y - 0  # :50
+    if K is None:
+        K = kern.K(X)  # :53
+    Ky = K.copy()  # :55
+    diag_add(Ky, noise_variance + JITTER)  # :56
+    Wi, LW, LWi, W_logdet = pdinv(Ky)  # :58
+    alpha, _ = dpotrs(LW, YYT_factor, lower=1)  # :60
+    log_marginal = 0.5 * (-Y.size * LOG_2_PI - Y.shape[1] * W_logdet - np.sum(alpha * YYT_factor))  # :62
+    dL_dK = 0.5 * (tdot(alpha) - Y.shape[1] * Wi)  # :70
+    dL_dthetaL = np.sum(np.diag(dL_dK))  # :72 -> likelihoods/gaussian.py:78-79
+    return dict(L=LW, alpha=alpha, K=K, Wi=Wi, logdet=W_logdet, log_marginal=float(log_marginal), dL_dK=dL_dK,
+                dL_dthetaL=float(dL_dthetaL), dL_dm=alpha)
+
+
+def eval_lml_grad(X, Y, kind, ARD, variance, lengthscale, noise_variance, native=None):
+    """One GP.parameters_changed() (GPy/core/gp.py:269-282): returns (log_marginal, gradient) with the gradient in
+    the order paramz exposes it: [kern.variance, kern.lengthscale (1 or D), Gaussian_noise.variance]
+    (link order stationary.py:81, gp.py:106-107)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    kern = StationaryOracle(kind, X.shape[1], variance, lengthscale, ARD, native=native)
+    res = exact_inference(kern, X, Y, noise_variance)
+    dvar, dlen = kern.update_gradients_full(res["dL_dK"], X)  # gp.py:280
+    grad = np.concatenate([[dvar], np.atleast_1d(dlen), [res["dL_dthetaL"]]])
+    return res["log_marginal"], grad, res
+
+
+def raw_predict(kern, X, L, alpha, Xnew, full_cov=False):
+    """posterior.py:273-302 (PosteriorExact._raw_predict, 2-D woodbury_chol)."""
+    Kx = kern.K(X, Xnew)
+    mu = np.dot(Kx.T, alpha)
+    if mu.ndim == 1:
+        mu = mu.reshape(-1, 1)
+    tmp = dtrtrs(L, Kx)[0]
+    if full_cov:
+        var = kern.K(Xnew) - tdot(tmp.T)
+    else:
+        var = (kern.Kdiag(Xnew) - np.square(tmp).sum(0))[:, None]
+    return mu, var
+
+
+def predict(kern, X, L, alpha, Xnew, noise_variance, full_cov=False):
+    """gp.py:290-365 predict with the Gaussian likelihood (likelihoods/gaussian.py:102-110): adds the noise."""
+    mu, var = raw_predict(kern, X, L, alpha, Xnew, full_cov)
+    if full_cov:
+        var = var + np.eye(var.shape[0]) * noise_variance
+    else:
+        var = var + noise_variance
+    return mu, var
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic workload of record and the Logexp transform paramz applies to all three parameters
+# ----------------------------------------------------------------------------------------------------------
+def synthetic(N, D, seed=0):
+    """rng=default_rng(seed); X~U(-3,3); Y=sum(sin X)/sqrt(D)+0.1 eps (mirrors test_model.py:796-807)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (N, D))
+    f = np.sin(X).sum(1, keepdims=True) / np.sqrt(D)
+    Y = f + 0.1 * rng.standard_normal((N, 1))
+    return X, Y
+
+
+def theta_bench(D, ARD=True):
+    """theta_bench of SURVEY.md §8(d): variance 1, lengthscale sqrt(D) (per dim if ARD), noise 0.01."""
+    ls = np.full(D, np.sqrt(D)) if ARD else np.sqrt(D)
+    return 1.0, ls, 0.01
+
+
+def logexp_f(x):
+    """paramz.transformations.Logexp.f: theta = log(1+exp(x)) (stable form)."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.where(x > 36.0, x, np.log1p(np.exp(np.clip(x, -np.inf, 36.0))))
+
+
+def logexp_finv(f):
+    f = np.asarray(f, dtype=np.float64)
+    return np.where(f > 36.0, f, np.log(np.expm1(f)))
+
+
+def logexp_gradfactor(f):
+    """d theta / d x for theta = log(1+e^x): 1 - exp(-theta)."""
+    f = np.asarray(f, dtype=np.float64)
+    return np.where(f > 36.0, 1.0, -np.expm1(-f))
