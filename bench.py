@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — exact-GP log-marginal + gradient evaluations per second (fp64), the metric of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 16384] [--d 8]
+
+One "step" = one evaluation (= one GP.parameters_changed(), GPy/core/gp.py:269-282): theta -> log marginal likelihood and
+its gradient w.r.t. (variance, D lengthscales, noise) for GPRegression RBF ARD on the synthetic workload of
+SURVEY.md §8(d) (BASELINE.json configs[1]: N=16384, D=8, fp64, 1xB200).
+
+`value`  : evaluations/s with X, Y resident in HBM (theta in, (LML, grad) out each step), device-timed.
+`e2e`    : the same metric through the reference-facing plugin API (gpy_b200.GPRegression over the C ABI) with HOST
+           buffers: every step copies X and Y host->device and reads (LML, grad) back, inside the timed region.
+`roofline`: dominant kernel = the trailing-update DMMA GEMM; achieved = its algorithmic flops / its CUDA-event time,
+           measured live over the timed steps; peak = fp64 DMMA issue rate measured in the same run.
+`cpu_baseline` / `--impl reference`: the reference's own CPU operation sequence (oracle/gpy_oracle.py: same LAPACK/BLAS
+           calls incl. the wasted dtrtri, two exp passes, the serial ARD loop compiled from C) on this box's cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "exact-GP log-marginal+grad evals/sec (fp64) at N=16k D=8"
+UNIT = "evals/s"
+
+
+def synthetic(N, D, seed=0):
+    """SURVEY.md §8(d) workload (same generator as oracle.gpy_oracle.synthetic, restated so the product arm does not
+    import the oracle)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (N, D))
+    f = np.sin(X).sum(1, keepdims=True) / np.sqrt(D)
+    Y = f + 0.1 * rng.standard_normal((N, 1))
+    return X, Y
+
+
+def theta_for_step(D, step):
+    """theta_bench (variance 1, lengthscale sqrt(D), noise 0.01) perturbed deterministically per step, the way an
+    optimizer iterate moves: nothing can be cached between steps."""
+    rng = np.random.default_rng(1000 + step)
+    var = 1.0 * (1.0 + 0.05 * rng.uniform(-1, 1))
+    ls = np.sqrt(D) * (1.0 + 0.05 * rng.uniform(-1, 1, D))
+    noise = 0.01 * (1.0 + 0.05 * rng.uniform(-1, 1))
+    return var, ls, noise
+
+
+class ClockSampler(object):
+    """nvidia-smi sampler for the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "power_w_max": float(np.max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: GPy's CPU operation sequence on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_eval_timed(N, D, step, native="port"):
+    from oracle import gpy_oracle as o
+    X, Y = synthetic(N, D)
+    var, ls, noise = theta_for_step(D, step)
+    t0 = time.perf_counter()
+    lml, grad, _ = o.eval_lml_grad(X, Y, "rbf", True, var, ls, noise, native=native)
+    return time.perf_counter() - t0, lml, grad
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        infos = threadpool_info()
+        return max([i.get("num_threads", 1) for i in infos] or [1]), infos
+    except Exception:
+        return os.cpu_count() or 1, []
+
+
+def ensure_oracle_native():
+    """build the checker's C helper if it is missing (the reference's serial Cython ARD loop, restated in C)."""
+    so = os.path.join(ROOT, "oracle", "_build", "liboracle_c.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_build/liboracle_c.so"],
+                              stdout=subprocess.DEVNULL)
+    return "port"
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    native = ensure_oracle_native()
+    N, D = args.n, args.d
+    threads, infos = cpu_threads()
+    for w in range(args.warmup):
+        cpu_eval_timed(min(N, 2048), D, -1 - w, native)   # warm-up on a small instance: BLAS threads, page cache
+    times = []
+    t_start = time.perf_counter()
+    for s in range(args.steps):
+        dt, lml, grad = cpu_eval_timed(N, D, s, native)
+        times.append(dt)
+    total = time.perf_counter() - t_start
+    per = float(np.mean(times))
+    blas = ", ".join(sorted({"%s %s" % (i.get("internal_api"), i.get("version")) for i in infos}))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": 1.0 / per, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "GPRegression RBF ARD N=%d D=%d fp64 (BASELINE.json configs[1])" % (N, D),
+                   "path": "GPy CPU operation sequence restated in oracle/gpy_oracle.py (GPy itself needs paramz, "
+                           "absent from this image): dsyrk+symmetrify, 2 exp passes, dpotrf, dtrtri (unused), dpotri, "
+                           "dpotrs, serial ARD loop in C"},
+        "cpu_baseline": {"value": 1.0 / per, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d full evaluations at N=%d (every step is one complete evaluation; warm-up at N=2048)"
+                                   % (args.steps, N), "host_cpus": os.cpu_count(), "blas": blas},
+        "e2e": {"value": 1.0 / per, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": total,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    N, D = args.n, args.d
+    use_dist = world > 1
+    torch.cuda.set_device(local)
+    if use_dist:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gpy_b200 import _ffi
+    import gpy_b200
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    X, Y = synthetic(N, D)
+    eng = _ffi.Engine(local)
+    eng.set_data(X, Y)
+
+    # ---- device-resident throughput ------------------------------------------------------------------------------
+    for w in range(args.warmup):
+        eng.exact_eval("rbf", True, *theta_for_step(D, -1 - w))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.total_launches()
+    dev_ms, upd_ms, upd_flops, lau_ms, lau_flops, kb_ms, kb_bytes = [], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for s in range(args.steps):
+        last = eng.exact_eval("rbf", True, *theta_for_step(D, s))
+        st = eng.stats()
+        dev_ms.append(st["total_ms"])
+        upd_ms += st["update_ms"]; upd_flops += st["update_flops"]
+        lau_ms += st["lauum_ms"]; lau_flops += st["lauum_flops"]
+        kb_ms += st["kbuild_ms"]; kb_bytes += st["kbuild_bytes"]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = eng.total_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = float(np.sum(dev_ms)) * 1e-3          # CUDA-event time of the K evaluations on the launching stream
+    t_dev_t = torch.tensor([t_dev, wall], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(t_dev_t, op=dist.ReduceOp.MAX)
+    t_dev, wall = float(t_dev_t[0]), float(t_dev_t[1])
+    # N>1 (until the sharded factorisation lands in bench): independent replicas, one evaluation stream per GPU
+    value = world * args.steps / t_dev
+
+    # ---- end to end through the plugin API with host buffers --------------------------------------------------------
+    m = gpy_b200.GPRegression(X, Y, gpy_b200.RBF(D, ARD=True), noise_var=0.01, device=local, engine=eng)
+    e2e_steps = args.steps
+    for w in range(min(args.warmup, 2)):
+        m.set_XY(X.copy(), Y.copy())
+        m.set_theta(*theta_for_step(D, -1 - w))
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        m.set_XY(X.copy(), Y.copy())           # fresh host buffers: forces the host->device copy of the inputs
+        m.set_theta(*theta_for_step(D, s))     # -> parameters_changed(): inference + kernel gradients
+        ll = m.log_likelihood()
+        g = m.gradient
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(e2e_t[0])
+
+    if rank == 0:
+        peak = eng.measure_fp64_peak()
+        ach = upd_flops / upd_ms * 1e-9 if upd_ms > 0 else 0.0
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            native = ensure_oracle_native()
+            threads, infos = cpu_threads()
+            cpu_eval_timed(2048, D, -1, native)
+            dt, lml_c, grad_c = cpu_eval_timed(N, D, args.steps - 1, native)
+            lml_g, grad_g, _ = last
+            cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "1 full evaluation at N=%d on the host cores (same theta as the last GPU step)" % N,
+                   "seconds": dt, "host_cpus": os.cpu_count(),
+                   "parity_vs_gpu": {"lml_abs": abs(lml_c - lml_g),
+                                     "grad_rel_max": float(np.max(np.abs(grad_c - grad_g) / np.abs(grad_c)))}}
+        nl = D
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "GPRegression RBF ARD N=%d D=%d fp64 (BASELINE.json configs[1])" % (N, D),
+                       "theta": "theta_bench (variance 1, lengthscale sqrt(D), noise 0.01) +-5% per step",
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
+                       "l2": "inputs larger than L2: the %.1f GiB workspace is rebuilt and streamed every step"
+                             % (N * N * 8 / 2**30),
+                       "timing": "CUDA events on the launching stream around each evaluation, max over ranks"},
+            "wall_ms_per_step": wall / args.steps * 1e3,
+            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + (D + 2) * 8),
+                    "d2h_bytes_per_step": int((nl + 3) * 8), "steps": e2e_steps,
+                    "api": "gpy_b200.GPRegression.set_XY/set_theta -> log_likelihood(), gradient (host ndarrays in/out)"},
+            "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel<UPDATE> (fp64 DMMA trailing update)",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                         "peak_source": "fp64 DMMA.8x8x4 issue rate measured in this run (gpx_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json holds no fp64 entry",
+                         "launches": None, "traffic": None,
+                         "share_of_step": upd_ms / (t_dev * 1e3) if t_dev else None,
+                         "whole_eval_tflops": float(N) ** 3 * args.steps / t_dev * 1e-12,
+                         "whole_eval_frac": float(N) ** 3 * args.steps / t_dev * 1e-12 / peak if peak else None,
+                         "lauum_tflops": lau_flops / lau_ms * 1e-9 if lau_ms else None,
+                         "kbuild_gbs": kb_bytes / kb_ms * 1e-6 if kb_ms else None},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--d", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

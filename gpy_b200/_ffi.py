@@ -44,6 +44,7 @@ EXPORTS = {
                                           _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp]),
     "gpx_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(GpxStats)]),
     "gpx_total_launches": (ctypes.c_int64, [_vp]),
+    "gpx_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
     "gpx_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
     "gpx_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "gpx_comm_init": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
@@ -163,6 +164,12 @@ class Engine(object):
         s = GpxStats()
         check(self._L.gpx_get_stats(self._h, ctypes.byref(s)), "gpx_get_stats")
         return s.as_dict()
+
+    def measure_fp64_peak(self):
+        """fp64 DMMA issue peak of this device in TFLOP/s (roofline denominator, measured live)."""
+        v = ctypes.c_double()
+        check(self._L.gpx_measure_fp64_peak(self._h, ctypes.byref(v)), "gpx_measure_fp64_peak")
+        return v.value
 
     def total_launches(self):
         return int(self._L.gpx_total_launches(self._h))

@@ -160,6 +160,12 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
   if (!c || !name) GPX_FAIL("null argument");
   if (!strcmp(name, "nb")) {
     if (value != 0 && (value < TILE || value % TILE)) GPX_FAIL("nb must be a multiple of 128");
+    if (value != c->NB) {  // the panel buffers are sized by the block: force a re-allocation at the next gpx_set_data
+      GPX_CUDA(cudaSetDevice(c->device));
+      GPX_CUDA(cudaStreamSynchronize(c->st));
+      free_data(c);
+      c->Npad = 0;
+    }
     c->NB = value;
     return 0;
   }
@@ -480,6 +486,12 @@ int gpx_exact_eval(gpx_ctx* c, int kind, int ard, double variance, const double*
   for (int q = 0; q < nl + 2; q++) grad[q] = c->h_res[1 + q];
   c->have_eval = true;
   return 0;
+}
+
+int gpx_measure_fp64_peak(gpx_ctx* c, double* tflops) {
+  if (!c || !tflops) GPX_FAIL("null argument");
+  GPX_CUDA(cudaSetDevice(c->device));
+  return measure_dmma_peak(c->st, tflops);
 }
 
 int gpx_get_stats(gpx_ctx* c, gpx_stats* out) {

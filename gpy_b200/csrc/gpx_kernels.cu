@@ -545,4 +545,50 @@ int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStre
   return 0;
 }
 
+
+// =================================================================================================================
+// roofline denominator: DMMA.8x8x4 issue rate of this device (8 independent accumulator chains per warp,
+// 8 warps per CTA, 2 CTAs per SM), timed with CUDA events. tools/microbench.cu is the stand-alone version.
+// =================================================================================================================
+__global__ void dmma_rate_kernel(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  out[(long)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int measure_dmma_peak(cudaStream_t st, double* tflops) {
+  int dev = 0, sms = 0;
+  GPX_CUDA(cudaGetDevice(&dev));
+  GPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = sms * 2, threads = 256, iters = 20000;
+  double* out = nullptr;
+  GPX_CUDA(cudaMalloc(&out, (size_t)grid * threads * 8));
+  cudaEvent_t e0, e1;
+  GPX_CUDA(cudaEventCreate(&e0));
+  GPX_CUDA(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    GPX_CUDA(cudaEventRecord(e0, st));
+    dmma_rate_kernel<<<grid, threads, 0, st>>>(out, iters);
+    GPX_CUDA(cudaEventRecord(e1, st));
+    GPX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    GPX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = (double)grid * (threads / 32) * iters * 8 * 512.0 / ms * 1e-9;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return 0;
+}
+
 }  // namespace gpx

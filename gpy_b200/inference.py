@@ -1,0 +1,154 @@
+"""Host-side mirror of GPy's exact Gaussian inference plugin, computing on the B200 through libgpx.
+
+Mirrors (same names, argument meaning, return structure and error behaviour):
+    GPy.inference.latent_function_inference.ExactGaussianInference.inference
+        GPy/inference/latent_function_inference/exact_gaussian_inference.py:37-74
+    GPy.inference.latent_function_inference.posterior.PosteriorExact
+        GPy/inference/latent_function_inference/posterior.py:9-77,273-302
+    GPy.likelihoods.Gaussian (the three one-liners on the path)  GPy/likelihoods/gaussian.py:69-79,102-110
+"""
+import numpy as np
+
+from . import _ffi
+from .kern import DeviceGradient, Stationary
+from .param import Param, Parameterized
+
+
+class Gaussian(Parameterized):
+    """GPy.likelihoods.Gaussian restricted to what exact inference touches (gaussian.py:35-79,102-110)."""
+
+    def __init__(self, variance=1., name="Gaussian_noise"):
+        super(Gaussian, self).__init__(name)
+        self.variance = Param("variance", variance)
+        self.link_parameter(self.variance)
+
+    def gaussian_variance(self, Y_metadata=None):
+        return self.variance
+
+    def update_gradients(self, grad):
+        self.variance.gradient = np.atleast_1d(grad)
+
+    def exact_inference_gradients(self, dL_dKdiag, Y_metadata=None):
+        return np.asarray(dL_dKdiag).sum()
+
+    def predictive_values(self, mu, var, full_cov=False, Y_metadata=None):
+        if full_cov:
+            var = var + np.eye(var.shape[0]) * float(self.variance[0])
+        else:
+            var = var + float(self.variance[0])
+        return mu, var
+
+
+class PosteriorExact(object):
+    """Posterior whose big members live in HBM and are fetched lazily (posterior.py:21-77 constructor contract:
+    woodbury_chol = L, woodbury_vector = alpha, K = noise-free kernel matrix)."""
+
+    def __init__(self, engine, N, P):
+        self._engine, self._N, self._P = engine, N, P
+        self._cache = {}
+
+    def _get(self, which):
+        if which not in self._cache:
+            self._cache[which] = self._engine.get(which)
+        return self._cache[which]
+
+    @property
+    def woodbury_chol(self):
+        return self._get("L")
+
+    @property
+    def woodbury_vector(self):
+        return self._get("alpha")
+
+    @property
+    def woodbury_inv(self):
+        """posterior.py:183-203: (K + noise)^-1."""
+        return self._get("Kinv")
+
+    @property
+    def K(self):
+        return self._get("K")
+
+    @property
+    def mean(self):
+        """posterior.py:98-110: K alpha."""
+        return np.dot(self.K, self.woodbury_vector)
+
+    def _raw_predict(self, kern, Xnew, pred_var=None, full_cov=False):
+        """posterior.py:273-302 on the device (gpx_predict). `pred_var` (the training inputs) is what the engine holds."""
+        Xn = kern._slice_X(Xnew) if hasattr(kern, "_slice_X") else np.asarray(Xnew, dtype=np.float64)
+        return self._engine.predict(Xn, full_cov=full_cov)
+
+
+def _fingerprint(A):
+    A = np.asarray(A)
+    return (A.__array_interface__["data"][0], A.shape, A.strides, float(A.sum()), float(np.square(A).sum()))
+
+
+class ExactGaussianInference(object):
+    """Drop-in for GPy's ExactGaussianInference: `inference(kern, X, likelihood, Y, ...)` returns
+    (posterior, log_marginal, {'dL_dK', 'dL_dthetaL', 'dL_dm'}). For the stationary kernels of gpy_b200.kern the whole
+    evaluation (K build, factorisation, solves, K^-1, gradient reductions) is ONE C-ABI call; `dL_dK` comes back as a
+    DeviceGradient handle that `kern.update_gradients_full` recognises."""
+
+    def __init__(self, device=0, engine=None):
+        self.device = device
+        self._engine = engine
+        self._data_key = None
+
+    def on_optimization_start(self):
+        pass
+
+    def on_optimization_end(self):
+        pass
+
+    def to_dict(self):
+        return {"class": "gpy_b200.inference.ExactGaussianInference", "name": "ExactGaussianInference"}
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = _ffi.Engine(self.device)
+        return self._engine
+
+    def _bind(self, X, Y, force=False):
+        key = (_fingerprint(X), _fingerprint(Y))
+        if force or key != self._data_key:
+            self.engine.set_data(X, Y)
+            self._data_key = key
+
+    def inference(self, kern, X, likelihood, Y, mean_function=None, Y_metadata=None, K=None, variance=None,
+                  Z_tilde=None):
+        if mean_function is not None:
+            raise NotImplementedError("mean functions are outside the accelerated hot path (SURVEY.md §8f)")
+        if K is not None:
+            raise NotImplementedError("precomputed K is outside the accelerated hot path (SURVEY.md §8f)")
+        if not isinstance(kern, Stationary):
+            raise TypeError("gpy_b200.ExactGaussianInference accelerates gpy_b200.kern stationary kernels only")
+        if variance is None:
+            variance = likelihood.gaussian_variance(Y_metadata)
+        noise = float(np.squeeze(np.asarray(variance)))
+        Xs = kern._slice_X(X)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        self._bind(Xs, Y)
+        kind, ard, var, ls = kern._theta()
+        # exact_gaussian_inference.py:56: +1e-8 on the diagonal, always; jitchol ladder of 5 (util/linalg.py:56)
+        lml, grad, _ = self.engine.exact_eval(kind, ard, var, ls, noise, jitter=1e-8, max_tries=5)
+        if Z_tilde is not None:
+            lml += Z_tilde
+        N, P = Y.shape
+        post = PosteriorExact(self.engine, N, P)
+        dL_dK = DeviceGradient(self.engine, kern._state_key(), grad[0], grad[1:-1], N)
+        grad_dict = {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
+        return post, lml, grad_dict
+
+
+class _LazyAlpha(object):
+    """grad_dict['dL_dm'] is alpha (exact_gaussian_inference.py:74); fetched only if used."""
+
+    def __init__(self, post):
+        self._post = post
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._post.woodbury_vector
+        return a if dtype is None else a.astype(dtype)

@@ -103,6 +103,8 @@ typedef struct {
 } gpx_stats;
 int gpx_get_stats(gpx_ctx* ctx, gpx_stats* out);
 int64_t gpx_total_launches(gpx_ctx* ctx);
+/* Roofline denominator measured on this device: fp64 tensor (DMMA.8x8x4) issue rate in TFLOP/s, CUDA-event timed. */
+int gpx_measure_fp64_peak(gpx_ctx* ctx, double* tflops);
 
 /* Tunables (block sizes etc.), mainly for tests: name in {"nb", "lookahead", "profile"}. */
 int gpx_set_option(gpx_ctx* ctx, const char* name, int64_t value);

@@ -1,0 +1,72 @@
+"""Generates tests/golden/*.npz. Run in the build container (has /root/reference):  python tests/golden/make_golden.py
+
+Source of the numbers:
+  * if the unmodified reference can be imported (GPy from /root/reference through the test-only paramz stand-in in
+    oracle/paramz_shim), every fixture is produced by the REFERENCE ITSELF — GPy.models.GPRegression(...):
+    m.log_likelihood(), m.gradient, posterior.woodbury_vector, m.predict — and the oracle is asserted against it here;
+  * otherwise by the oracle restatement (fixtures then carry source='oracle').
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import gpy_oracle as o  # noqa: E402
+
+CASES = [
+    # name, kind, ARD, N, D, seed
+    ("rbf_iso_n512_d2", "rbf", False, 512, 2, 0),          # BASELINE.json configs[0]
+    ("rbf_ard_n300_d8", "rbf", True, 300, 8, 1),
+    ("matern52_ard_n257_d5", "matern52", True, 257, 5, 2),
+    ("matern32_iso_n128_d3", "matern32", False, 128, 3, 3),
+    ("exponential_ard_n200_d4", "exponential", True, 200, 4, 4),
+    ("rbf_ard_n1100_d8", "rbf", True, 1100, 8, 5),
+    ("matern52_iso_n40_d1", "matern52", False, 40, 1, 6),
+]
+
+
+def try_reference():
+    try:
+        from oracle import ref_gpy
+        return ref_gpy.load()
+    except Exception as e:  # noqa: BLE001
+        print("reference not importable (%r): fixtures come from the oracle" % (e,))
+        return None
+
+
+def main():
+    GPy = try_reference()
+    for name, kind, ARD, N, D, seed in CASES:
+        X, Y = o.synthetic(N, D, seed)
+        rng = np.random.default_rng(100 + seed)
+        var = float(rng.uniform(0.5, 2.0))
+        ls = np.sqrt(D) * rng.uniform(0.6, 1.5, D) if ARD else float(np.sqrt(D) * rng.uniform(0.6, 1.5))
+        noise = float(rng.uniform(0.005, 0.1))
+        Xn = rng.uniform(-3, 3, (7, D))
+        lml, grad, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, noise)
+        kern = o.StationaryOracle(kind, D, var, ls, ARD)
+        mu, pv = o.predict(kern, X, res["L"], res["alpha"], Xn, noise)
+        source = "oracle"
+        if GPy is not None:
+            from oracle import ref_gpy
+            r = ref_gpy.evaluate(GPy, X, Y, kind, ARD, var, ls, noise, Xn)
+            assert abs(r["lml"] - lml) <= 1e-9 * max(1, abs(lml)), (name, r["lml"], lml)
+            np.testing.assert_allclose(r["grad"], grad, rtol=1e-8, atol=1e-10, err_msg=name)
+            np.testing.assert_allclose(r["alpha"], res["alpha"], rtol=1e-7, atol=1e-10, err_msg=name)
+            np.testing.assert_allclose(r["mu"], mu, rtol=1e-8, atol=1e-10, err_msg=name)
+            np.testing.assert_allclose(r["var"], pv, rtol=1e-7, atol=1e-10, err_msg=name)
+            lml, grad, alpha, mu, pv = r["lml"], r["grad"], r["alpha"], r["mu"], r["var"]
+            source = "GPy %s (unmodified /root/reference via oracle/paramz_shim)" % GPy.__version__
+        else:
+            alpha = res["alpha"]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), X=X, Y=Y, kind=kind, ARD=ARD, variance=var,
+                            lengthscale=ls, noise=noise, lml=lml, grad=grad, alpha=alpha, Xnew=Xn, mu=mu, var=pv,
+                            source=source)
+        print("%-28s lml %.10f source %s" % (name, lml, source))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,212 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path through the C ABI against the CPU oracle on the same
+seeded inputs. Tolerances are those of BASELINE.json's north star: 1e-8 absolute on the log marginal likelihood,
+1e-6 relative on gradients (fp64 throughout)."""
+import os
+
+import numpy as np
+import pytest
+
+import gpy_b200
+from gpy_b200 import _ffi
+from oracle import gpy_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+LML_ATOL = 1e-8
+GRAD_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = _ffi.Engine(0)
+    yield e
+    e.close()
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def theta(D, ARD, seed):
+    rng = np.random.default_rng(seed)
+    ls = np.sqrt(D) * rng.uniform(0.7, 1.4, D) if ARD else float(np.sqrt(D) * rng.uniform(0.7, 1.4))
+    return float(rng.uniform(0.5, 2.0)), ls, float(rng.uniform(0.01, 0.1))
+
+
+CASES = [(k, a, n, d) for (k, a, d) in [("rbf", True, 8), ("rbf", False, 2), ("matern52", True, 5), ("matern32", False, 3),
+                                       ("exponential", True, 4), ("exponential", False, 1), ("matern32", True, 7),
+                                       ("matern52", False, 6)]
+         for n in (1, 2, 127, 128, 129, 500, 1300)]
+
+
+@pytest.mark.parametrize("kind,ARD,N,D", CASES)
+def test_lml_and_gradient_match_oracle(eng, kind, ARD, N, D):
+    X, Y = o.synthetic(N, D, seed=N + D)
+    var, ls, noise = theta(D, ARD, N)
+    lml0, g0, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, noise)
+    eng.set_data(X, Y)
+    lml, g, jit = eng.exact_eval(kind, ARD, var, ls, noise)
+    assert jit == 0.0
+    assert abs(lml - lml0) <= LML_ATOL, (lml, lml0)
+    np.testing.assert_allclose(g, g0, rtol=GRAD_RTOL, atol=1e-9)
+    if N <= 500:
+        assert rel(eng.get("L"), res["L"]) < 1e-10
+        assert rel(eng.get("alpha"), res["alpha"]) < 1e-9
+        assert rel(eng.get("Kinv"), res["Wi"]) < 1e-9
+        assert rel(eng.get("dL_dK"), res["dL_dK"]) < 1e-9
+        assert rel(eng.get("K"), res["K"]) < 1e-12
+        assert rel(eng.get("Linv"), np.linalg.inv(res["L"])) < 1e-9
+
+
+@pytest.mark.parametrize("nb", [128, 256, 384, 1024])
+def test_block_size_does_not_change_the_answer(nb):
+    e = _ffi.Engine(0)
+    e.set_option("nb", nb)
+    X, Y = o.synthetic(1700, 4, seed=11)
+    var, ls, noise = theta(4, True, 5)
+    lml0, g0, _ = o.eval_lml_grad(X, Y, "rbf", True, var, ls, noise)
+    e.set_data(X, Y)
+    lml, g, _ = e.exact_eval("rbf", True, var, ls, noise)
+    assert abs(lml - lml0) <= LML_ATOL
+    np.testing.assert_allclose(g, g0, rtol=GRAD_RTOL)
+    e.close()
+
+
+def test_multiple_outputs_and_large_D(eng):
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-3, 3, (400, 64))
+    Y = rng.standard_normal((400, 3))
+    ls = 8.0 * rng.uniform(0.8, 1.2, 64)
+    lml0, g0, res = o.eval_lml_grad(X, Y, "matern52", True, 1.2, ls, 0.3)
+    eng.set_data(X, Y)
+    lml, g, _ = eng.exact_eval("matern52", True, 1.2, ls, 0.3)
+    assert abs(lml - lml0) <= LML_ATOL
+    np.testing.assert_allclose(g, g0, rtol=GRAD_RTOL, atol=1e-9)
+    assert rel(eng.get("alpha"), res["alpha"]) < 1e-9
+
+
+def test_golden_fixtures(eng):
+    """tests/golden/*.npz (tests/golden/make_golden.py): LML, gradient, alpha and predictions."""
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".npz"))
+    assert files
+    for fn in files:
+        z = np.load(os.path.join(gdir, fn))
+        kind, ARD = str(z["kind"]), bool(z["ARD"])
+        ls = z["lengthscale"] if ARD else float(z["lengthscale"])
+        eng.set_data(z["X"], z["Y"])
+        lml, g, _ = eng.exact_eval(kind, ARD, float(z["variance"]), ls, float(z["noise"]))
+        assert abs(lml - float(z["lml"])) <= LML_ATOL, fn
+        np.testing.assert_allclose(g, z["grad"], rtol=GRAD_RTOL, atol=1e-9, err_msg=fn)
+        assert rel(eng.get("alpha"), z["alpha"]) < 1e-8, fn
+        mu, var = eng.predict(z["Xnew"])
+        np.testing.assert_allclose(mu, z["mu"], rtol=1e-8, atol=1e-10, err_msg=fn)
+        np.testing.assert_allclose(var + float(z["noise"]), z["var"], rtol=1e-7, atol=1e-10, err_msg=fn)
+
+
+@pytest.mark.parametrize("kind", o.KINDS)
+@pytest.mark.parametrize("ARD", [False, True])
+def test_kernel_plugin_calls(kind, ARD):
+    """Kern.K / Kdiag / update_gradients_full as stand-alone plugin calls (test_kernel.py fixtures: 10x6 and 20x6
+    standard normal; test_cython.py: 300x10 / 20x10)."""
+    rng = np.random.default_rng(7)
+    for (n, m, d) in ((10, 20, 6), (300, 20, 10), (257, 131, 3)):
+        X, X2 = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+        ls = rng.uniform(0.8, 2.0, d) if ARD else float(rng.uniform(0.8, 2.0))
+        cls = {"rbf": gpy_b200.RBF, "exponential": gpy_b200.Exponential, "matern32": gpy_b200.Matern32,
+               "matern52": gpy_b200.Matern52}[kind]
+        k = cls(d, variance=0.7, lengthscale=ls, ARD=ARD)
+        ko = o.StationaryOracle(kind, d, 0.7, ls, ARD)
+        assert rel(k.K(X), ko.K(X)) < 1e-13
+        assert rel(k.K(X, X2), ko.K(X, X2)) < 1e-13
+        np.testing.assert_array_equal(k.Kdiag(X), ko.Kdiag(X))
+        for XX2, shape in ((None, (n, n)), (X2, (n, m))):
+            dL = rng.standard_normal(shape)
+            k.update_gradients_full(dL, X, XX2)
+            v0, l0 = ko.update_gradients_full(dL, X, XX2)
+            np.testing.assert_allclose(k.variance.gradient, v0, rtol=1e-10)
+            np.testing.assert_allclose(k.lengthscale.gradient, l0, rtol=1e-9, atol=1e-12)
+
+
+def test_jitter_ladder_and_failure(eng):
+    """jitchol semantics (GPy/util/linalg.py:56-75; test_linalg.py:20-37): duplicated inputs with zero noise are
+    singular -> the ladder adds mean(diag)*1e-6*10^k; the result equals the oracle run with the same ladder."""
+    Xd = np.repeat(o.synthetic(100, 2, 9)[0], 2, axis=0)
+    Yd = np.sin(Xd[:, :1])
+    eng.set_data(Xd, Yd)
+    lml, g, jit = eng.exact_eval("rbf", False, 1.0, 2.0, 0.0, jitter=0.0)
+    assert jit > 0
+    k = o.StationaryOracle("rbf", 2, 1.0, 2.0, False)
+    Ky = k.K(Xd)
+    L, jit0 = o.jitchol(Ky)
+    assert np.isclose(jit, jit0, rtol=1e-12)
+    alpha = o.dpotrs(L, Yd)[0]
+    lml0 = 0.5 * (-Yd.size * o.LOG_2_PI - 2 * np.sum(np.log(np.diag(L))) - np.sum(alpha * Yd))
+    assert abs(lml - lml0) <= 1e-6 * abs(lml0)   # ill-conditioned by construction (cond ~ 1e6 / jitter)
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.exact_eval("rbf", False, 1.0, 2.0, 0.0, jitter=0.0, max_tries=0)
+
+
+def test_gpregression_model_api():
+    """GPRegression through the plugin mirror: log_likelihood/gradient, checkgrad (test_model.py:790-833), predict vs the
+    pinv formula (test_model.py:83-105), optimize improves the objective (test_model.py:510-517)."""
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-3, 3, (40, 2))
+    Y = np.sin(X[:, :1]) + 0.05 * rng.standard_normal((40, 1))
+    for kern in (gpy_b200.RBF(2, ARD=True), gpy_b200.Matern52(2), gpy_b200.Matern32(2, ARD=True), gpy_b200.Exponential(2)):
+        m = gpy_b200.GPRegression(X, Y, kern)
+        kind, ard, var, ls = kern._theta()
+        lml0, g0, _ = o.eval_lml_grad(X, Y, kind, ard, var, ls, 1.0)
+        assert abs(m.log_likelihood() - lml0) <= LML_ATOL
+        np.testing.assert_allclose(m.gradient, g0, rtol=GRAD_RTOL)
+        assert m.checkgrad()
+    m = gpy_b200.GPRegression(X, Y, gpy_b200.RBF(2, ARD=True))
+    f0 = m.objective_function()
+    m.optimize(max_iters=60)
+    assert m.objective_function() < f0 - 1.0
+    # predict_noiseless vs explicit pinv
+    Xn = rng.uniform(-3, 3, (9, 2))
+    k = m.kern
+    Kinv = np.linalg.pinv(k.K(X) + np.eye(40) * (float(m.likelihood.variance[0]) + 1e-8))
+    mu_hat = k.K(Xn, X).dot(Kinv).dot(Y)
+    K_hat = k.K(Xn) - k.K(Xn, X).dot(Kinv).dot(k.K(X, Xn))
+    mu, cov = m.predict_noiseless(Xn, full_cov=True)
+    np.testing.assert_allclose(mu, mu_hat, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cov, K_hat, rtol=1e-5, atol=1e-7)
+    mu, var = m.predict(Xn)
+    np.testing.assert_allclose(var, np.diag(K_hat)[:, None] + float(m.likelihood.variance[0]), rtol=1e-5, atol=1e-7)
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (N=16384, D=8, RBF ARD): size-independent checks.
+    (1) analytic gradient == central finite difference of the device LML; (2) LML is invariant under a permutation of
+    the data; (3) alpha solves Ky alpha = y (residual through an independent device K build of a row block)."""
+    N, D = 16384, 8
+    X, Y = o.synthetic(N, D)
+    var, ls, noise = o.theta_bench(D, True)
+    e = _ffi.Engine(0)
+    e.set_data(X, Y)
+    lml, g, _ = e.exact_eval("rbf", True, var, ls, noise)
+    th = np.concatenate([[var], ls, [noise]])
+    for i in (0, 3, D + 1):
+        h = 1e-5 * th[i]
+        tp, tm = th.copy(), th.copy()
+        tp[i] += h
+        tm[i] -= h
+        fp = e.exact_eval("rbf", True, tp[0], tp[1:-1], tp[-1])[0]
+        fm = e.exact_eval("rbf", True, tm[0], tm[1:-1], tm[-1])[0]
+        fd = (fp - fm) / (2 * h)
+        assert abs(fd - g[i]) <= 2e-5 * abs(g[i]), (i, fd, g[i])
+    lml_again, g_again, _ = e.exact_eval("rbf", True, var, ls, noise)
+    assert lml_again == lml and np.array_equal(g_again, g)     # deterministic: fixed-order reductions
+    alpha = e.get("alpha")
+    rows = np.arange(0, N, 257)
+    Krows = _ffi.kern_K("rbf", True, var, ls, X[rows], X)
+    resid = Krows.dot(alpha) + (noise + 1e-8) * alpha[rows] - Y[rows]
+    assert np.max(np.abs(resid)) < 1e-8
+    perm = np.random.default_rng(0).permutation(N)
+    e.set_data(X[perm], Y[perm])
+    lml_p, g_p, _ = e.exact_eval("rbf", True, var, ls, noise)
+    assert abs(lml_p - lml) <= 1e-7
+    np.testing.assert_allclose(g_p, g, rtol=1e-8)
+    e.close()
