@@ -280,7 +280,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + (D + 2) * 8),
                     "d2h_bytes_per_step": int((nl + 3) * 8), "steps": e2e_steps,
                     "api": "gpy_b200.GPRegression.set_XY/set_theta -> log_likelihood(), gradient (host ndarrays in/out)"},
-            "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel<UPDATE> (fp64 DMMA trailing update)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_update_kernel (fp64 DMMA trailing update)",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                          "peak_source": "fp64 DMMA.8x8x4 issue rate measured in this run (gpx_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json holds no fp64 entry",

@@ -37,6 +37,9 @@ using namespace gpx;
 struct gpx_ctx {
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;   // high-priority side stream: diagonal-block work + panel of the NEXT step (look-ahead)
+  int lookahead = 1;
+  std::vector<cudaEvent_t> sync_ev;
   // data
   long N = 0, Npad = 0;
   int D = 0, P = 0;
@@ -131,7 +134,10 @@ int gpx_create(int device, gpx_ctx** out) {
   GPX_CUDA(cudaSetDevice(device));
   gpx_ctx* c = new gpx_ctx();
   c->device = device;
-  GPX_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  GPX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  GPX_CUDA(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio_lo));
+  GPX_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_hi));
   GPX_CUDA(cudaMalloc(&c->res, (MAX_D + 8) * sizeof(double)));
   GPX_CUDA(cudaMalloc(&c->info, sizeof(int)));
   GPX_CUDA(cudaMallocHost(&c->h_res, (MAX_D + 8) * sizeof(double)));
@@ -147,6 +153,8 @@ int gpx_destroy(gpx_ctx* c) {
   cudaStreamSynchronize(c->st);
   free_data(c);
   for (auto e : c->ev) cudaEventDestroy(e);
+  for (auto e : c->sync_ev) cudaEventDestroy(e);
+  if (c->st2) cudaStreamDestroy(c->st2);
   if (c->res) cudaFree(c->res);
   if (c->info) cudaFree(c->info);
   if (c->h_res) cudaFreeHost(c->h_res);
@@ -170,7 +178,7 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "profile")) { c->profile = (int)value; return 0; }
-  if (!strcmp(name, "lookahead")) return 0;
+  if (!strcmp(name, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
   GPX_FAIL("unknown option");
 }
 
@@ -195,7 +203,7 @@ int gpx_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y,
     GPX_CUDA(cudaMalloc(&c->dAlpha, (size_t)Npad * P * 8));
     GPX_CUDA(cudaMalloc(&c->dUvPart, (size_t)KSPLIT * Npad * P * 8));
     GPX_CUDA(cudaMalloc(&c->S, (size_t)Npad * Npad * 8));
-    GPX_CUDA(cudaMalloc(&c->Pbuf, (size_t)Npad * NB * 8));
+    GPX_CUDA(cudaMalloc(&c->Pbuf, (size_t)2 * Npad * NB * 8));   // double-buffered for the look-ahead
     GPX_CUDA(cudaMalloc(&c->Tm, (size_t)NB * NB * 8));
     GPX_CUDA(cudaMalloc(&c->Ldiag, (size_t)Npad * TILE * 8));
     GPX_CUDA(cudaMalloc(&c->Dinv, (size_t)Npad * TILE * 8));
@@ -267,21 +275,49 @@ static GemmParams gemm_defaults() {
   return p;
 }
 
+static int sync_event(gpx_ctx* c, size_t idx, cudaEvent_t* out) {
+  while (c->sync_ev.size() <= idx) {
+    cudaEvent_t e;
+    GPX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->sync_ev.push_back(e);
+  }
+  *out = c->sync_ev[idx];
+  return 0;
+}
+
+// Step k of the sweep (block column k of width nb):
+//   D(k)  inner sweep of the diagonal block (128 columns at a time) + assemble of U_kk / Linv_kk      [side stream]
+//   Pn(k) panel GEMM  P = S(:,block k) Linv_kk^T -> Pbuf[k&1], copied back into S                     [side stream]
+//   U1(k) trailing update restricted to the columns of block k+1                                        [main stream]
+//   U2(k) trailing update of the remaining columns                                                      [main stream]
+// Look-ahead: D(k+1), Pn(k+1) only need U1(k), so they run on the high-priority side stream while U2(k) keeps the
+// machine busy; U1(k+1) waits for Pn(k+1). Without look-ahead everything is issued on the main stream.
 static int run_sweep(gpx_ctx* c, Recorder& rec) {
   const long ld = c->Npad, Npad = c->Npad;
   const int nt = (int)(Npad / TILE);
   const long NB = pick_nb(c);
-  cudaStream_t st = c->st;
-  for (long o = 0; o < Npad; o += NB) {
+  const bool la = c->lookahead && NB < Npad;
+  cudaStream_t sm = c->st;
+  cudaStream_t ss = la ? c->st2 : c->st;
+  size_t evi = 0;
+  cudaEvent_t ev;
+  if (la) {  // side stream starts after everything queued so far on the main stream (K build)
+    GPX_CHECK(sync_event(c, evi++, &ev));
+    GPX_CUDA(cudaEventRecord(ev, sm));
+    GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+  }
+  int kblk = 0;
+  for (long o = 0; o < Npad; o += NB, kblk++) {
     const long nb = std::min(NB, Npad - o);
     const int nbt = (int)(nb / TILE), kt0 = (int)(o / TILE), kt1 = kt0 + nbt;
     double* Sblk = c->S + o + o * ld;
-    // ---- inner sweep of the nb x nb diagonal block, 128 columns at a time -----------------------------------
+    double* Pb = c->Pbuf + (size_t)(kblk & 1) * Npad * NB;
+    // ---- D(k): inner sweep of the nb x nb diagonal block ------------------------------------------------------
     for (int d = 0; d < nbt; d++) {
       const int g = kt0 + d;
       double* tile = Sblk + (long)d * TILE + (long)d * TILE * ld;
       GPX_CHECK(launch_base(tile, ld, c->Ldiag + (long)g * TILE * TILE, c->Dinv + (long)g * TILE * TILE,
-                            c->logdet_part + g, c->info, g * TILE, st));
+                            c->logdet_part + g, c->info, g * TILE, ss));
       c->eval_launches++;
       if (nbt > 1) {
         GemmParams pp = gemm_defaults();
@@ -290,7 +326,7 @@ static int run_sweep(gpx_ctx* c, Recorder& rec) {
         pp.B = c->Dinv + (long)g * TILE * TILE; pp.ldb = TILE;
         pp.C = Sblk + (long)d * TILE * ld; pp.ldc = ld;      // in place: one k-tile deep, tile-local dependence only
         pp.K = TILE; pp.nt = nbt; pp.skip0 = d; pp.skip1 = d + 1; pp.tri = 0;
-        GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), st));
+        GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), ss));
         c->eval_launches++;
         if (d + 1 < nbt) {
           GemmParams pu = gemm_defaults();
@@ -299,47 +335,69 @@ static int run_sweep(gpx_ctx* c, Recorder& rec) {
           pu.B = pu.A; pu.ldb = ld;
           pu.C = Sblk; pu.ldc = ld;
           pu.K = TILE; pu.nt = nbt; pu.c0 = d + 1; pu.rlow = d + 1;
-          GPX_CHECK(launch_gemm(pu, dim3(nbt - d - 1, nbt), st));
+          GPX_CHECK(launch_gemm(pu, dim3(1, 1), ss));
           c->eval_launches++;
         }
       }
     }
     if (nbt == nt) break;  // single block: done
-    // ---- outer panel: P = S(:, block) * Linv_kk^T, rows of the diagonal block get U_kk ------------------------
-    GPX_CHECK(launch_assemble(Sblk, ld, (int)nb, c->Pbuf + o, Npad, c->Tm, st));
+    // ---- Pn(k): P = S(:, block) * Linv_kk^T; rows of the diagonal block get U_kk ------------------------------
+    GPX_CHECK(launch_assemble(Sblk, ld, (int)nb, Pb + o, Npad, c->Tm, ss));
     c->eval_launches++;
     {
       GemmParams pp = gemm_defaults();
       pp.mode = GEMM_PANEL;
       pp.A = c->S + o * ld; pp.lda = ld;
       pp.B = c->Tm; pp.ldb = nb;
-      pp.C = c->Pbuf; pp.ldc = Npad;
+      pp.C = Pb; pp.ldc = Npad;
       pp.K = (int)nb; pp.nt = nt; pp.skip0 = kt0; pp.skip1 = kt1; pp.tri = 1;
-      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), st));
+      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), ss));
       c->eval_launches++;
     }
     if (o > 0)
-      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, c->Pbuf, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, st));
+      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, Pb, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, ss));
     if (kt1 < nt)
-      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, c->Pbuf + (o + nb), Npad * 8,
-                                 (size_t)(Npad - o - nb) * 8, nb, cudaMemcpyDeviceToDevice, st));
-    // ---- unified trailing update: S(r,c) -= P_r P_c^T for c >= kt1, r in [0,kt1) U [c,nt) ----------------------
-    if (kt1 < nt) {
-      GemmParams pu = gemm_defaults();
-      pu.mode = GEMM_UPDATE;
-      pu.A = c->Pbuf; pu.lda = Npad;
-      pu.B = c->Pbuf; pu.ldb = Npad;
-      pu.C = c->S; pu.ldc = ld;
-      pu.K = (int)nb; pu.nt = nt; pu.c0 = kt1; pu.rlow = kt1;
-      double tiles = 0;
-      for (int cc = kt1; cc < nt; cc++) tiles += kt1 + (nt - cc);
-      const double flops = tiles * 2.0 * TILE * TILE * (double)nb;
-      const int h = rec.begin(PH_UPDATE, flops);
-      GPX_CHECK(launch_gemm(pu, dim3(nt - kt1, nt), st));
-      rec.end(h);
-      c->eval_launches++;
-      c->stats.update_launches++;
+      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8,
+                                 (size_t)(Npad - o - nb) * 8, nb, cudaMemcpyDeviceToDevice, ss));
+    if (la) {
+      GPX_CHECK(sync_event(c, evi++, &ev));
+      GPX_CUDA(cudaEventRecord(ev, ss));
+      GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
     }
+    // ---- trailing update: S(r,c) -= P_r P_c^T for c >= kt1, r in [0,kt1) U [c,nt), split U1 | U2 ---------------
+    if (kt1 < nt) {
+      const int next_nbt = (int)(std::min(NB, Npad - (o + nb)) / TILE);
+      for (int part = 0; part < 2; part++) {
+        const int cbeg = part == 0 ? kt1 : kt1 + next_nbt;
+        const int cend = part == 0 ? kt1 + next_nbt : nt;
+        if (cbeg < cend) {
+          GemmParams pu = gemm_defaults();
+          pu.mode = GEMM_UPDATE;
+          pu.A = Pb; pu.lda = Npad;
+          pu.B = Pb; pu.ldb = Npad;
+          pu.C = c->S; pu.ldc = ld;
+          pu.K = (int)nb; pu.nt = nt; pu.c0 = cbeg; pu.ncols = cend - cbeg; pu.rlow = kt1;
+          double tiles = 0;
+          for (int cc = cbeg; cc < cend; cc++) tiles += kt1 + (nt - cc);
+          const double flops = tiles * 2.0 * TILE * TILE * (double)nb;
+          const int h = rec.begin(PH_UPDATE, flops);
+          GPX_CHECK(launch_gemm(pu, dim3(1, 1), sm));
+          rec.end(h);
+          c->eval_launches++;
+          c->stats.update_launches++;
+        }
+        if (part == 0 && la) {  // block column k+1 is final: the side stream may start D(k+1)
+          GPX_CHECK(sync_event(c, evi++, &ev));
+          GPX_CUDA(cudaEventRecord(ev, sm));
+          GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+        }
+      }
+    }
+  }
+  if (la) {  // join: the main stream continues after the last side-stream work
+    GPX_CHECK(sync_event(c, evi++, &ev));
+    GPX_CUDA(cudaEventRecord(ev, ss));
+    GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
   }
   return 0;
 }

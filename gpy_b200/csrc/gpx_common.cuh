@@ -132,6 +132,7 @@ struct GemmParams {
   int K;        // k-depth (UPDATE / PANEL); LAUUM: padded order of the matrix
   int nt;       // number of row tiles of the (sub)matrix
   int c0;       // first column tile handled (UPDATE: kt1; PANEL: 0)
+  int ncols;    // UPDATE/LAUUM: number of column tiles handled (0 = up to nt)
   int rlow;     // UPDATE: rows [0, rlow) above the trailing part take part (upper, inverse region)
   int skip0, skip1;  // PANEL: row tiles [skip0, skip1) (the diagonal block) are skipped
   int tri;      // PANEL: B is lower triangular -> k range of output column tile c' is [0, (c'+1)*TILE)

@@ -24,13 +24,14 @@ constexpr int EPI_DOUBLES = (2 * MAX_D + 2 + 2 * MAX_P) * TILE + CONSUMER_WARPS 
 constexpr int EPI_BYTES = EPI_DOUBLES * 8;
 constexpr int DATA_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
 constexpr int SMEM_BYTES = DATA_BYTES + 2 * STAGES * 8 + 64;
+constexpr int SB = 12;   // super-block edge of the tile schedule (SB*SB = 144 <= 148 SMs)
 
 size_t gemm_smem_bytes() { return SMEM_BYTES; }
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory"); }
 
 template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmParams p) {
+__device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sA = reinterpret_cast<double*>(smem_raw);
   double* sB = sA + STAGES * SLAB_DOUBLES;
@@ -38,27 +39,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmPara
   uint64_t* empty = full + STAGES;
 
   // ---- tile mapping ------------------------------------------------------------------------------------------
+  // UPDATE / LAUUM run on a 1-D grid decoded into (slot, column) through SB x SB super-blocks, so that the ~148 CTAs in
+  // flight share <= 2*SB row panels and SB column panels and the operand streams stay L2-resident.
   int r, c, kt_first = 0, nkt;
   const int kt_step = p.krow_mod;
-  if (MODE == GEMM_UPDATE) {
-    c = p.c0 + blockIdx.x;
-    const int slot = blockIdx.y;
+  if (MODE == GEMM_UPDATE || MODE == GEMM_LAUUM) {
+    const int ncols = p.ncols > 0 ? p.ncols : p.nt - p.c0;
+    const int sbcols = (ncols + SB - 1) / SB;
+    const int sb = blockIdx.x / (SB * SB), t = blockIdx.x % (SB * SB);
+    const int slot = (sb / sbcols) * SB + t / SB;
+    const int col = (sb % sbcols) * SB + t % SB;
+    if (col >= ncols) return;
+    c = p.c0 + col;
     r = slot < p.rlow ? slot : c + (slot - p.rlow);
     if (r >= p.nt) return;
-    nkt = p.K / TILE;
-  } else if (MODE == GEMM_PANEL) {
+    if (MODE == GEMM_UPDATE) {
+      nkt = p.K / TILE;
+    } else {
+      // k-tiles kt in [r, nt) with kt % krow_mod == krow_rem
+      kt_first = r + ((p.krow_rem - r) % kt_step + kt_step) % kt_step;
+      nkt = kt_first < p.nt ? (p.nt - 1 - kt_first) / kt_step + 1 : 0;
+    }
+  } else {  // GEMM_PANEL
     c = blockIdx.x;
     const int slot = blockIdx.y;
     r = slot < p.skip0 ? slot : slot + (p.skip1 - p.skip0);
     if (r >= p.nt) return;
     nkt = p.tri ? (c + 1) : p.K / TILE;
-  } else {  // GEMM_LAUUM
-    c = blockIdx.x;
-    r = c + blockIdx.y;
-    if (r >= p.nt) return;
-    // k-tiles kt in [r, nt) with kt % krow_mod == krow_rem
-    kt_first = r + ((p.krow_rem - r) % kt_step + kt_step) % kt_step;
-    nkt = kt_first < p.nt ? (p.nt - 1 - kt_first) / kt_step + 1 : 0;
   }
   const double* Aptr;
   long lda;
@@ -98,10 +105,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmPara
   const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps -> 64 x 32 sub-tiles
   const int g = lane >> 2, tg = lane & 3;
   double acc[8][4][2];
+  if (MODE == GEMM_UPDATE) {
+    // C -= A B^T  ==  C + (-A) B^T : the accumulators start from the old C tile (loads overlap the pipeline fill),
+    // the A fragments are negated on the way in, and the epilogue is store-only.
+    const double* Ct = p.C + (long)r * TILE + (long)c * TILE * p.ldc;
 #pragma unroll
-  for (int mb = 0; mb < 8; mb++)
+    for (int mb = 0; mb < 8; mb++)
 #pragma unroll
-    for (int nb = 0; nb < 4; nb++) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+      for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          acc[mb][nb][e] = Ct[wm * 64 + mb * 8 + g + (long)(wn * 32 + nb * 8 + 2 * tg + e) * p.ldc];
+  } else {
+#pragma unroll
+    for (int mb = 0; mb < 8; mb++)
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+  }
 
   for (int it = 0; it < nslab; ++it) {
     const int s = it % STAGES;
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmPara
       const int kk = (k4 * 4 + tg) * PITCH;
       double af[8], bf[4];
 #pragma unroll
-      for (int mb = 0; mb < 8; mb++) af[mb] = a[kk + mb * 8];
+      for (int mb = 0; mb < 8; mb++) af[mb] = (MODE == GEMM_UPDATE) ? -a[kk + mb * 8] : a[kk + mb * 8];
 #pragma unroll
       for (int nb = 0; nb < 4; nb++) bf[nb] = b[kk + nb * 8];
 #pragma unroll
@@ -129,24 +149,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmPara
   // ================= epilogues ===============================================================================
   if (MODE != GEMM_LAUUM) {
     double* Ct = p.C + (long)r * TILE + (long)c * TILE * p.ldc;
-    constexpr bool accumulate = (MODE == GEMM_UPDATE);
 #pragma unroll
     for (int mb = 0; mb < 8; mb++) {
       const int i = wm * 64 + mb * 8 + g;
-      double old[4][2];
-      if (accumulate) {
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) old[nb][e] = Ct[i + (long)(wn * 32 + nb * 8 + 2 * tg + e) * p.ldc];
-      }
 #pragma unroll
       for (int nb = 0; nb < 4; nb++)
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const long off = i + (long)(wn * 32 + nb * 8 + 2 * tg + e) * p.ldc;
-          Ct[off] = accumulate ? old[nb][e] - acc[mb][nb][e] : acc[mb][nb][e];
-        }
+        for (int e = 0; e < 2; e++) Ct[i + (long)(wn * 32 + nb * 8 + 2 * tg + e) * p.ldc] = acc[mb][nb][e];
     }
     return;
   }
@@ -247,22 +256,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmPara
     double s = 0.0;
 #pragma unroll
     for (int wdx = 0; wdx < CONSUMER_WARPS; wdx++) s += sRed[wdx * nred + tid];
-    p.partials[((long)blockIdx.y * gridDim.x + blockIdx.x) * nred + tid] = s;
+    p.partials[((long)r * p.nt + c) * nred + tid] = s;
   }
 }
 
+// one __global__ entry per mode so that profiles name them apart
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_update_kernel(const GemmParams p) { gemm_nt_body<GEMM_UPDATE>(p); }
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_panel_kernel(const GemmParams p) { gemm_nt_body<GEMM_PANEL>(p); }
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_lauum_kernel(const GemmParams p) { gemm_nt_body<GEMM_LAUUM>(p); }
+
 int gemm_init() {
-  GPX_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<GEMM_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  GPX_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<GEMM_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  GPX_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<GEMM_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return 0;
 }
 
 int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t st) {
+  if (p.mode != GEMM_PANEL) {
+    // (slots, columns) domain: UPDATE rows [0, rlow) U [c, nt) for columns [c0, nt); LAUUM: rlow = 0, c0 = 0
+    const int ncols = p.ncols > 0 ? p.ncols : p.nt - p.c0, nslots = p.rlow + (p.nt - p.c0);
+    if (ncols <= 0) return 0;
+    grid = dim3((unsigned)(((nslots + SB - 1) / SB) * ((ncols + SB - 1) / SB) * SB * SB), 1, 1);
+  }
   if (grid.x == 0 || grid.y == 0) return 0;
-  if (p.mode == GEMM_UPDATE) gemm_nt_kernel<GEMM_UPDATE><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
-  else if (p.mode == GEMM_PANEL) gemm_nt_kernel<GEMM_PANEL><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
-  else gemm_nt_kernel<GEMM_LAUUM><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  if (p.mode == GEMM_UPDATE) gemm_update_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  else if (p.mode == GEMM_PANEL) gemm_panel_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  else gemm_lauum_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,1 @@
+"""TEST-ONLY paramz.core stand-in module (import-time only)."""

@@ -1,0 +1,118 @@
+"""TEST INFRASTRUCTURE (build container only): run the UNMODIFIED reference from /root/reference.
+
+`load()` makes the reference's own modules importable without executing GPy/__init__.py (which eagerly imports
+plotting, examples, every model ...): the packages on the way (GPy, GPy.kern, GPy.kern.src, GPy.core, GPy.util,
+GPy.likelihoods, GPy.inference, GPy.inference.latent_function_inference) are registered as empty stub packages whose
+__path__ points into /root/reference, so `import GPy.kern.src.rbf` executes the reference's rbf.py, stationary.py,
+kern.py, kernel_slice_operations.py, util/linalg.py, util/diag.py ... verbatim. The missing third-party dependency
+`paramz` is supplied by the test-only stand-in in oracle/paramz_shim (see its header).
+
+What is NOT the reference's code on this path and is restated here (5 lines in total):
+  * GP.parameters_changed's three calls (GPy/core/gp.py:278-280) in `evaluate()` below,
+  * the two hook methods of LatentFunctionInference (inference/latent_function_inference/__init__.py:38-49),
+  * psi-statistics helpers (kern/src/psi_comp) are replaced by empty classes: they are constructed by RBF.__init__
+    (rbf.py:29-32) but never called on the exact-GP path.
+Used by tests/golden/make_golden.py and tests/test_reference_crosscheck.py; never by the product or by GPU-side tests
+(/root/reference does not exist on the GPU box).
+"""
+import importlib
+import os
+import sys
+import types
+
+REF = os.environ.get("GPX_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_loaded = None
+
+
+def _stub(name, relpath):
+    m = types.ModuleType(name)
+    m.__path__ = [os.path.join(REF, relpath)]
+    m.__package__ = name
+    sys.modules[name] = m
+    parent, _, child = name.rpartition(".")
+    if parent:
+        setattr(sys.modules[parent], child, m)
+    return m
+
+
+def load():
+    """-> namespace with RBF, Exponential, Matern32, Matern52, ExactGaussianInference, Gaussian, linalg, version."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not os.path.isdir(os.path.join(REF, "GPy")):
+        raise ImportError("reference tree %s not present" % REF)
+    if "GPy" in sys.modules and not getattr(sys.modules["GPy"], "_gpx_stub", False):
+        raise ImportError("a real GPy is already imported")
+    shim = os.path.join(_HERE, "paramz_shim")
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    g = _stub("GPy", "GPy")
+    g._gpx_stub = True
+    for name, rel in (("GPy.kern", "GPy/kern"), ("GPy.kern.src", "GPy/kern/src"), ("GPy.core", "GPy/core"),
+                      ("GPy.util", "GPy/util"), ("GPy.likelihoods", "GPy/likelihoods"),
+                      ("GPy.inference", "GPy/inference"),
+                      ("GPy.inference.latent_function_inference", "GPy/inference/latent_function_inference")):
+        _stub(name, rel)
+    # psi-statistics (out of scope) -> empty classes, so that rbf.py / kern.py import and construct
+    psi = types.ModuleType("GPy.kern.src.psi_comp")
+    for cls in ("PSICOMP_RBF", "PSICOMP_RBF_GPU", "PSICOMP_GH", "PSICOMP_Linear", "PSICOMP_SSRBF"):
+        setattr(psi, cls, type(cls, (object,), {"__init__": lambda self, *a, **kw: None}))
+    sys.modules["GPy.kern.src.psi_comp"] = psi
+    sys.modules["GPy.kern.src"].psi_comp = psi
+
+    class LatentFunctionInference(object):  # inference/latent_function_inference/__init__.py:38-49 (hooks only)
+        def on_optimization_start(self):
+            pass
+
+        def on_optimization_end(self):
+            pass
+
+        def _save_to_input_dict(self):
+            return {}
+
+    sys.modules["GPy.inference.latent_function_inference"].LatentFunctionInference = LatentFunctionInference
+
+    for mod in ("GPy.util.config", "GPy.util.diag", "GPy.util.linalg", "GPy.util.misc"):
+        importlib.import_module(mod)
+    par = importlib.import_module("GPy.core.parameterization")
+    sys.modules["GPy.core"].Param = par.Param
+    sys.modules["GPy.core"].parameterization = par
+    rbf = importlib.import_module("GPy.kern.src.rbf")
+    stat = importlib.import_module("GPy.kern.src.stationary")
+    egi = importlib.import_module("GPy.inference.latent_function_inference.exact_gaussian_inference")
+    gauss = importlib.import_module("GPy.likelihoods.gaussian")
+    ns = types.SimpleNamespace(
+        RBF=rbf.RBF, Exponential=stat.Exponential, Matern32=stat.Matern32, Matern52=stat.Matern52,
+        ExactGaussianInference=egi.ExactGaussianInference, Gaussian=gauss.Gaussian,
+        linalg=sys.modules["GPy.util.linalg"], diag=sys.modules["GPy.util.diag"], stationary=stat,
+        __version__=open(os.path.join(REF, "GPy", "__version__.py")).read().split('"')[1])
+    _loaded = ns
+    return ns
+
+
+KERNELS = {"rbf": "RBF", "exponential": "Exponential", "matern32": "Matern32", "matern52": "Matern52"}
+
+
+def evaluate(G, X, Y, kind, ARD, variance, lengthscale, noise, Xnew=None):
+    """One GP.parameters_changed() with the reference's own kernel / inference / likelihood objects.
+    The three calls are GPy/core/gp.py:278-280."""
+    import numpy as np
+    D = X.shape[1]
+    kern = getattr(G, KERNELS[kind])(D, variance=variance, lengthscale=lengthscale, ARD=ARD)
+    lik = G.Gaussian(variance=noise)
+    inf = G.ExactGaussianInference()
+    posterior, lml, grad_dict = inf.inference(kern, X, lik, Y, None, None)      # gp.py:278
+    lik.update_gradients(grad_dict["dL_dthetaL"])                                # gp.py:279
+    kern.update_gradients_full(grad_dict["dL_dK"], X)                            # gp.py:280
+    grad = np.concatenate([np.atleast_1d(kern.variance.gradient).reshape(-1),
+                           np.atleast_1d(kern.lengthscale.gradient).reshape(-1),
+                           np.atleast_1d(lik.variance.gradient).reshape(-1)])
+    out = dict(lml=float(lml), grad=grad, alpha=np.asarray(posterior.woodbury_vector),
+               L=np.asarray(posterior.woodbury_chol), K=np.asarray(kern.K(X)), dL_dK=np.asarray(grad_dict["dL_dK"]))
+    if Xnew is not None:
+        mu, var = posterior._raw_predict(kern, Xnew, X)                          # posterior.py:273-302
+        mu, var = lik.predictive_values(mu, var)                                  # gaussian.py:102-110
+        out["mu"], out["var"] = np.asarray(mu), np.asarray(var)
+    return out

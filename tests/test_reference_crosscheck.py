@@ -1,0 +1,75 @@
+"""Build-container-only tests: the oracle restatement against the UNMODIFIED reference (/root/reference, GPy 1.14.2)
+imported through oracle/ref_gpy.py + the test-only paramz stand-in. Skipped where /root/reference is absent (GPU box)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gpy_oracle as o
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/GPy"), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def G():
+    from oracle import ref_gpy
+    return ref_gpy.load()
+
+
+@pytest.mark.parametrize("kind", o.KINDS)
+@pytest.mark.parametrize("ARD", [False, True])
+def test_oracle_equals_reference(G, kind, ARD):
+    from oracle import ref_gpy
+    for (N, D, seed) in ((60, 1, 0), (150, 4, 1), (333, 8, 2)):
+        X, Y = o.synthetic(N, D, seed)
+        rng = np.random.default_rng(seed)
+        ls = rng.uniform(0.8, 2.5, D) if ARD else float(rng.uniform(0.8, 2.5))
+        var, noise = float(rng.uniform(0.5, 2)), float(rng.uniform(0.01, 0.2))
+        Xn = rng.uniform(-3, 3, (6, D))
+        r = ref_gpy.evaluate(G, X, Y, kind, ARD, var, ls, noise, Xn)
+        lml, g, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, noise)
+        assert abs(r["lml"] - lml) <= 1e-10 * max(1.0, abs(lml))
+        np.testing.assert_allclose(g, r["grad"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(res["K"], r["K"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(res["L"], r["L"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(res["alpha"], r["alpha"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(res["dL_dK"], r["dL_dK"], rtol=1e-10, atol=1e-12)
+        kern = o.StationaryOracle(kind, D, var, ls, ARD)
+        mu, pv = o.predict(kern, X, res["L"], res["alpha"], Xn, noise)
+        np.testing.assert_allclose(mu, r["mu"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(pv, r["var"], rtol=1e-9, atol=1e-12)
+
+
+def test_oracle_linalg_equals_reference_linalg(G):
+    """jitchol ladder / pdinv / tdot / symmetrify of GPy/util/linalg.py, same inputs as GPy/testing/test_linalg.py:8-18."""
+    from test_oracle import _corrupt
+    A = _corrupt(3)
+    L_ref = G.linalg.jitchol(A, maxtries=5)
+    L, jit = o.jitchol(A, maxtries=5)
+    np.testing.assert_array_equal(L, L_ref)
+    with pytest.raises(np.linalg.LinAlgError):
+        G.linalg.jitchol(A, maxtries=4)
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((50, 7))
+    np.testing.assert_array_equal(o.tdot(B), G.linalg.tdot(B))
+    S = B.dot(B.T) + 50 * np.eye(50)
+    Ai, Lr, Li, ld = G.linalg.pdinv(S)
+    Ai2, L2, Li2, ld2 = o.pdinv(S)
+    np.testing.assert_array_equal(Ai, Ai2)
+    np.testing.assert_array_equal(Lr, L2)
+    assert ld == ld2
+
+
+def test_reference_native_helper_matches(G):
+    """The reference's own stationary_utils.c (compiled by oracle/Makefile into oracle/_ref) against the reference's
+    NumPy reduction Stationary._lengthscale_grads_pure (stationary.py:234-235): mirrors GPy/testing/test_cython.py:83-98."""
+    libs = o._load_native()
+    if libs["ref"] is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(1)
+    X, Z = rng.standard_normal((300, 10)), rng.standard_normal((20, 10))
+    k = G.RBF(10)
+    for tmp, A, B in ((rng.standard_normal((300, 300)), X, X), (rng.standard_normal((300, 20)), X, Z)):
+        g_ref = k._lengthscale_grads_pure(tmp, A, B)
+        g_c = o.lengthscale_grads_native(tmp, A, B, np.ones(10), "ref")
+        assert np.allclose(g_ref, g_c)
