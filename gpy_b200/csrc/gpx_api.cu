@@ -64,6 +64,7 @@ struct gpx_ctx {
   int* h_info = nullptr;     // pinned
   double* Kinv = nullptr;    // lazy, Npad x Npad (lower tiles)
   double* staging = nullptr; // lazy, N x N dense
+  size_t staging_cap = 0;
   long NB = 0;               // outer block (0 = auto)
   // last evaluation
   bool have_eval = false;
@@ -87,6 +88,7 @@ static void free_data(gpx_ctx* c) {
     if (*p) cudaFree(*p);
     *p = nullptr;
   }
+  c->staging_cap = 0;
   c->have_eval = false;
   c->have_kinv = false;
 }
@@ -560,7 +562,9 @@ int gpx_get_stats(gpx_ctx* c, gpx_stats* out) {
 int64_t gpx_total_launches(gpx_ctx* c) { return c ? c->total_launches : -1; }
 
 static int ensure_staging(gpx_ctx* c) {
-  if (!c->staging) GPX_CUDA(cudaMalloc(&c->staging, (size_t)c->N * c->N * 8));
+  const size_t need = (size_t)c->N * c->N * 8;
+  if (c->staging && c->staging_cap < need) { cudaFree(c->staging); c->staging = nullptr; }
+  if (!c->staging) { GPX_CUDA(cudaMalloc(&c->staging, need)); c->staging_cap = need; }
   return 0;
 }
 

@@ -63,8 +63,10 @@ class GP(Parameterized):
             self.parameters_changed()
 
     def update_model(self, flag):
+        """paramz Parameterizable.update_model: False defers re-evaluation while several things are written."""
+        was = self.update_model_flag
         self.update_model_flag = bool(flag)
-        if flag:
+        if flag and not was:
             self.parameters_changed()
 
     def set_theta(self, variance, lengthscale, noise_variance):

@@ -23,8 +23,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ----------------------------------------------------------------------------------------------------------
 # GPy/util/linalg.py, GPy/util/diag.py
 # ----------------------------------------------------------------------------------------------------------
+NATIVE_LINALG = False  # True: mirror `use_linalg_cython` (GPy/util/linalg.py:14-18) with the C loop of oracle_c.c
+
+
 def symmetrify(A, upper=False):
-    """GPy/util/linalg.py:356-379 (+ linalg_cython.pyx:9-18): mirror one triangle onto the other, in place."""
+    """GPy/util/linalg.py:356-379: the Cython double loop (linalg_cython.pyx:9-18, restated in oracle_c.c) when the
+    native helpers are enabled, else the NumPy fallback (_symmetrify_numpy, :374-379). In place."""
+    if NATIVE_LINALG and A.flags.c_contiguous or (NATIVE_LINALG and A.flags.f_contiguous):
+        lib = _load_native()["port"]
+        if lib is not None and A.dtype == np.float64 and A.ndim == 2 and A.shape[0] == A.shape[1]:
+            lib.oracle_symmetrify.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
+            lib.oracle_symmetrify.restype = None
+            # an F-ordered array is the transpose of a C-ordered one: swap the direction
+            up = bool(upper) if A.flags.c_contiguous else not bool(upper)
+            lib.oracle_symmetrify(A.shape[0], A.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(up))
+            return
     triu = np.triu_indices_from(A, k=1)
     if upper:
         A.T[triu] = A[triu]
@@ -232,13 +245,26 @@ class StationaryOracle(object):
         self.native = native  # None -> pure NumPy ARD reduction; "port"/"ref" -> compiled loops
         self.variance_gradient = None
         self.lengthscale_gradient = None
+        # paramz `Cache_this(limit=3)` on _scaled_dist / K / dK_dr_via_X (stationary.py:105,117,130,150): results are
+        # memoised per (X, X2) object identity while the parameters are unchanged. The parameters of an oracle
+        # object never change, so an identity-keyed dict reproduces which passes the reference recomputes.
+        self._cache = {}
+
+    def _memo(self, tag, X, X2, fn):
+        key = (tag, id(X), id(X2))
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] is X and hit[1] is X2:
+            return hit[2]
+        val = fn()
+        self._cache[key] = (X, X2, val)
+        return val
 
     def _r(self, X, X2=None):
-        return scaled_dist(X, X2, self.lengthscale, self.ARD)
+        return self._memo("r", X, X2, lambda: scaled_dist(X, X2, self.lengthscale, self.ARD))
 
     def K(self, X, X2=None):
-        """stationary.py:105-115."""
-        return K_of_r(self.kind, self.variance, self._r(X, X2))
+        """stationary.py:105-115 (cached)."""
+        return self._memo("K", X, X2, lambda: K_of_r(self.kind, self.variance, self._r(X, X2)))
 
     def Kdiag(self, X):
         """stationary.py:170-173."""
@@ -249,9 +275,10 @@ class StationaryOracle(object):
     def update_gradients_full(self, dL_dK, X, X2=None):
         """stationary.py:193-213."""
         self.variance_gradient = np.sum(self.K(X, X2) * dL_dK) / self.variance
-        dL_dr = dK_dr(self.kind, self.variance, self._r(X, X2)) * dL_dK  # recomputes exp like dK_dr_via_X
+        dL_dr = dK_dr(self.kind, self.variance, self._r(X, X2)) * dL_dK  # dK_dr_via_X: second exp pass, r from cache
         if self.ARD:
-            tmp = dL_dr * inv_dist(X, X2, self.lengthscale, self.ARD)
+            dist = self._r(X, X2).copy()  # _inv_dist, stationary.py:225-232 (r from cache, then copy/where/divide)
+            tmp = dL_dr * (1.0 / np.where(dist != 0.0, dist, np.inf))
             if X2 is None:
                 X2 = X
             if self.native:
@@ -295,11 +322,17 @@ def eval_lml_grad(X, Y, kind, ARD, variance, lengthscale, noise_variance, native
     """One GP.parameters_changed() (GPy/core/gp.py:269-282): returns (log_marginal, gradient) with the gradient in
     the order paramz exposes it: [kern.variance, kern.lengthscale (1 or D), Gaussian_noise.variance]
     (link order stationary.py:81, gp.py:106-107)."""
+    global NATIVE_LINALG
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
     kern = StationaryOracle(kind, X.shape[1], variance, lengthscale, ARD, native=native)
-    res = exact_inference(kern, X, Y, noise_variance)
-    dvar, dlen = kern.update_gradients_full(res["dL_dK"], X)  # gp.py:280
+    prev = NATIVE_LINALG
+    NATIVE_LINALG = bool(native)  # an installed GPy has its Cython helpers built: symmetrify + lengthscale_grads in C
+    try:
+        res = exact_inference(kern, X, Y, noise_variance)
+        dvar, dlen = kern.update_gradients_full(res["dL_dK"], X)  # gp.py:280
+    finally:
+        NATIVE_LINALG = prev
     grad = np.concatenate([[dvar], np.atleast_1d(dlen), [res["dL_dthetaL"]]])
     return res["log_marginal"], grad, res
 
