@@ -1,0 +1,128 @@
+"""The reference-side binding: plugin classes that subclass GPy's OWN kernel / inference classes and route the hot
+path through libgpx. Use where GPy (+ paramz) is importable:
+
+    import GPy
+    from gpy_b200 import gpy_plugin
+    B = gpy_plugin.load()                       # subclasses of GPy.kern.RBF/Matern32/Matern52/Exponential + inference
+    m = GPy.models.GPRegression(X, Y, kernel=B.RBF(D, ARD=True))
+    m.inference_method = B.ExactGaussianInference()      # same hook the reference's tests use (GPy/testing/fitc.py:31)
+    m.optimize()                                # paramz loop unchanged; one gpx_exact_eval per iterate
+
+`make(...)` takes the base classes explicitly so that the wiring can be exercised against the unmodified reference
+modules in the build container (tests/test_gpy_plugin_cpu.py) where the full `import GPy` is impossible (no paramz).
+
+The methods `K`, `Kdiag`, `update_gradients_full`, `update_gradients_diag` are defined in the class bodies on purpose:
+`KernCallsViaSlicerMeta` only wraps names it finds in the class dict (GPy/kern/src/kernel_slice_operations.py:14-57), and
+the wrapper hands them X already sliced to `active_dims` (GPy/kern/src/kern.py:112-117).
+"""
+import types
+
+import numpy as np
+
+from . import _ffi
+from .inference import PosteriorExact, _LazyAlpha, _fingerprint
+from .kern import DeviceGradient
+
+_KINDS = {"RBF": "rbf", "Exponential": "exponential", "Matern32": "matern32", "Matern52": "matern52"}
+
+
+def _make_kernel(base, kind, ffi):
+    class B200Kernel(base):
+        _gpx_kind = kind
+
+        def _gpx_theta(self):
+            ls = np.asarray(self.lengthscale.values if hasattr(self.lengthscale, "values") else self.lengthscale,
+                            dtype=np.float64).reshape(-1)
+            return kind, bool(self.ARD), float(np.asarray(self.variance).reshape(-1)[0]), (ls if self.ARD else float(ls[0]))
+
+        def _gpx_state_key(self):
+            k, ard, var, ls = self._gpx_theta()
+            return (k, ard, var, tuple(np.atleast_1d(ls).tolist()), tuple(np.atleast_1d(self.active_dims).tolist()))
+
+        def K(self, X, X2=None):
+            k, ard, var, ls = self._gpx_theta()
+            return ffi.kern_K(k, ard, var, ls, np.asarray(X, dtype=np.float64),
+                              None if X2 is None else np.asarray(X2, dtype=np.float64))
+
+        def Kdiag(self, X):
+            return ffi.kern_Kdiag(kind, float(np.asarray(self.variance).reshape(-1)[0]), int(np.asarray(X).shape[0]))
+
+        def update_gradients_full(self, dL_dK, X, X2=None, reset=True):
+            if isinstance(dL_dK, DeviceGradient) and X2 is None and dL_dK.matches(self._gpx_state_key()):
+                self.variance.gradient = dL_dK.dvariance
+                self.lengthscale.gradient = dL_dK.dlengthscale
+                return
+            k, ard, var, ls = self._gpx_theta()
+            dv, dl = ffi.kern_grad_full(k, ard, var, ls, np.asarray(X, dtype=np.float64),
+                                        np.asarray(dL_dK, dtype=np.float64),
+                                        None if X2 is None else np.asarray(X2, dtype=np.float64))
+            self.variance.gradient = dv
+            self.lengthscale.gradient = dl if self.ARD else dl[0]
+
+        def update_gradients_diag(self, dL_dKdiag, X):
+            self.variance.gradient = np.sum(dL_dKdiag)
+            self.lengthscale.gradient = 0.
+
+    B200Kernel.__name__ = B200Kernel.__qualname__ = base.__name__
+    return B200Kernel
+
+
+def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi):
+    """Build the plugin classes on top of the given GPy base classes."""
+    kernels = {n: _make_kernel(b, _KINDS[n], ffi) for n, b in
+               (("RBF", RBF), ("Exponential", Exponential), ("Matern32", Matern32), ("Matern52", Matern52))}
+    kernel_types = tuple(kernels.values())
+
+    class B200ExactGaussianInference(ExactGaussianInference):
+        """GPy.inference.latent_function_inference.ExactGaussianInference with the fused device evaluation; anything the
+        accelerated path does not cover (mean function, precomputed K, foreign kernels) goes to the stock method."""
+
+        def __init__(self, device=0, engine=None):
+            super(B200ExactGaussianInference, self).__init__()
+            self.device, self._engine, self._data_key = device, engine, None
+
+        @property
+        def engine(self):
+            if self._engine is None:
+                self._engine = ffi.Engine(self.device)
+            return self._engine
+
+        def inference(self, kern, X, likelihood, Y, mean_function=None, Y_metadata=None, K=None, variance=None,
+                      Z_tilde=None):
+            if mean_function is not None or K is not None or not isinstance(kern, kernel_types):
+                return super(B200ExactGaussianInference, self).inference(kern, X, likelihood, Y, mean_function,
+                                                                         Y_metadata, K, variance, Z_tilde)
+            if variance is None:
+                variance = likelihood.gaussian_variance(Y_metadata)
+            noise = float(np.squeeze(np.asarray(variance)))
+            Xs = np.ascontiguousarray(kern._slice_X(X)[0] if _returns_tuple(kern, X) else kern._slice_X(X),
+                                      dtype=np.float64)
+            Yc = np.ascontiguousarray(Y, dtype=np.float64)
+            key = (_fingerprint(Xs), _fingerprint(Yc))
+            if key != self._data_key:
+                self.engine.set_data(Xs, Yc)
+                self._data_key = key
+            k, ard, var, ls = kern._gpx_theta()
+            lml, grad, _ = self.engine.exact_eval(k, ard, var, ls, noise, jitter=1e-8, max_tries=5)
+            if Z_tilde is not None:
+                lml += Z_tilde
+            post = PosteriorExact(self.engine, Yc.shape[0], Yc.shape[1])
+            dlen = grad[1:-1] if ard else grad[1]
+            dL_dK = DeviceGradient(self.engine, kern._gpx_state_key(), grad[0], dlen, Yc.shape[0])
+            return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
+
+    B200ExactGaussianInference.__name__ = B200ExactGaussianInference.__qualname__ = "ExactGaussianInference"
+    return types.SimpleNamespace(ExactGaussianInference=B200ExactGaussianInference, **kernels)
+
+
+def _returns_tuple(kern, X):
+    """Kern._slice_X returns the sliced array; some paramz versions wrap cached results — accept both."""
+    r = kern._slice_X(X)
+    return isinstance(r, tuple)
+
+
+def load():
+    """Plugin classes over an installed GPy."""
+    import GPy
+    from GPy.inference.latent_function_inference import ExactGaussianInference
+    return make(GPy.kern.RBF, GPy.kern.Exponential, GPy.kern.Matern32, GPy.kern.Matern52, ExactGaussianInference)

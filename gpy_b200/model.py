@@ -59,6 +59,8 @@ class GP(Parameterized):
         if Y is not None:
             self.Y = np.asarray(Y, dtype=np.float64)
         self.num_data = self.X.shape[0]
+        if hasattr(self.inference_method, "invalidate_data"):
+            self.inference_method.invalidate_data()
         if self.update_model_flag:
             self.parameters_changed()
 
