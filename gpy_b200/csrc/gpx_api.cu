@@ -15,6 +15,7 @@
 
 #include "gpx_common.cuh"
 #include "gpx_kernels.cuh"
+#include "gpx_ctx.cuh"
 
 namespace gpx {
 static thread_local std::string g_err;
@@ -34,52 +35,6 @@ using namespace gpx;
     return -2;              \
   } while (0)
 
-struct gpx_ctx {
-  int device = 0;
-  cudaStream_t st = nullptr;
-  cudaStream_t st2 = nullptr;   // high-priority side stream: diagonal-block work + panel of the NEXT step (look-ahead)
-  int lookahead = 1;
-  std::vector<cudaEvent_t> sync_ev;
-  // data
-  long N = 0, Npad = 0;
-  int D = 0, P = 0;
-  double* dX = nullptr;      // N x D row-major (as given)
-  double* dXsT = nullptr;    // [D][Npad] scaled SoA
-  double* dsq = nullptr;     // [Npad]
-  double* dY = nullptr;      // [P][Npad]
-  double* dT = nullptr;      // [P][Npad]  L^-1 y
-  double* dAlpha = nullptr;  // [P][Npad]
-  double* dUvPart = nullptr; // [KSPLIT][P][Npad]
-  // workspace
-  double* S = nullptr;       // Npad x Npad column-major: lower L, upper U
-  double* Pbuf = nullptr;    // Npad x NB
-  double* Tm = nullptr;      // NB x NB
-  double* Ldiag = nullptr;   // nt tiles of 128x128
-  double* Dinv = nullptr;    // nt tiles of 128x128
-  double* logdet_part = nullptr;
-  double* partials = nullptr;
-  int* info = nullptr;
-  double* res = nullptr;     // device result vector
-  double* h_res = nullptr;   // pinned
-  int* h_info = nullptr;     // pinned
-  double* Kinv = nullptr;    // lazy, Npad x Npad (lower tiles)
-  double* staging = nullptr; // lazy, N x N dense
-  size_t staging_cap = 0;
-  long NB = 0;               // outer block (0 = auto)
-  // last evaluation
-  bool have_eval = false;
-  bool have_kinv = false;
-  KernParams kp{};
-  double noise = 0, jitter = 0, jitter_extra = 0;
-  // accounting
-  gpx_stats stats{};
-  int64_t total_launches = 0;
-  int64_t eval_launches = 0;
-  std::vector<cudaEvent_t> ev;
-  int profile = 1;
-};
-
-static const int KSPLIT = 32;
 
 static void free_data(gpx_ctx* c) {
   double** ptrs[] = {&c->dX, &c->dXsT, &c->dsq, &c->dY, &c->dT, &c->dAlpha, &c->dUvPart, &c->S, &c->Pbuf, &c->Tm,
@@ -153,6 +108,7 @@ int gpx_destroy(gpx_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
+  dist_free(c);
   free_data(c);
   for (auto e : c->ev) cudaEventDestroy(e);
   for (auto e : c->sync_ev) cudaEventDestroy(e);
@@ -190,6 +146,7 @@ int gpx_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y,
   if (D < 1 || D > MAX_D) GPX_FAIL("input dimension must be in [1, 64]");
   if (P < 1 || P > MAX_P) GPX_FAIL("number of output columns must be in [1, 8]");
   GPX_CUDA(cudaSetDevice(c->device));
+  if (c->dist) return dist_set_data(c, X, N, D, Y, P);
   const long Npad = (N + TILE - 1) / TILE * TILE;
   if (Npad != c->Npad || D != c->D || P != c->P) {
     GPX_CUDA(cudaStreamSynchronize(c->st));
@@ -268,12 +225,9 @@ struct Recorder {
 // ---------------------------------------------------------------------------------------------------------------
 // the unified blocked factor-and-invert sweep
 // ---------------------------------------------------------------------------------------------------------------
-static GemmParams gemm_defaults() {
+GemmParams gpx::gemm_defaults() {
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.sub_tile = -1;
-  p.krow_mod = 1;
-  p.krow_rem = 0;
   return p;
 }
 
@@ -505,8 +459,12 @@ int gpx_exact_eval(gpx_ctx* c, int kind, int ard, double variance, const double*
   int info = 0;
   for (;;) {
     tries++;
-    GPX_CHECK(eval_once(c, extra, rec));
-    GPX_CUDA(cudaStreamSynchronize(c->st));
+    if (c->dist) {
+      GPX_CHECK(dist_exact_eval(c, extra));
+    } else {
+      GPX_CHECK(eval_once(c, extra, rec));
+      GPX_CUDA(cudaStreamSynchronize(c->st));
+    }
     info = *c->h_info;
     if (info == 0) break;
     // jitchol ladder (GPy/util/linalg.py:61-75): the diagonal of Ky is variance + noise + jitter (> 0 here),
@@ -571,6 +529,7 @@ static int ensure_staging(gpx_ctx* c) {
 int gpx_get(gpx_ctx* c, int which, double* out) {
   if (!c || !out) GPX_FAIL("null argument");
   if (!c->have_eval) GPX_FAIL("no successful gpx_exact_eval to fetch results from");
+  if (c->dist && which != GPX_GET_ALPHA) GPX_FAIL("only alpha can be fetched in multi-GPU mode (the factor is distributed)");
   GPX_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->st;
   const long N = c->N, ld = c->Npad;
@@ -723,6 +682,7 @@ int gpx_kern_grad_full(gpx_ctx* c, int kind, int ard, double variance, const dou
 int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double* mu, double* var) {
   if (!c || !Xnew || !mu || !var) GPX_FAIL("null argument");
   if (!c->have_eval) GPX_FAIL("no successful gpx_exact_eval to predict from");
+  if (c->dist) GPX_FAIL("gpx_predict is single-GPU in this version");
   if (M < 1) GPX_FAIL("empty Xnew");
   GPX_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->st;
@@ -786,16 +746,5 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   }
   return 0;
 }
-
-// ---------------------------------------------------------------------------------------------------------------
-// multi-GPU entry points (implemented in gpx_dist.cu when built with NCCL)
-// ---------------------------------------------------------------------------------------------------------------
-#ifndef GPX_WITH_NCCL
-int gpx_comm_unique_id(char id_out[128]) { (void)id_out; GPX_FAIL("libgpx built without NCCL"); }
-int gpx_comm_init(gpx_ctx* ctx, const char id[128], int rank, int nranks) {
-  (void)ctx; (void)id; (void)rank; (void)nranks;
-  GPX_FAIL("libgpx built without NCCL");
-}
-#endif
 
 }  // extern "C"

@@ -127,8 +127,6 @@ struct GemmParams {
   const double* A; long lda;
   const double* B; long ldb;
   double* C; long ldc;
-  // row-tile `sub_tile` of the A operand is taken from subA (ld = TILE) instead (inverse diagonal tile), -1 = none
-  const double* subA; int sub_tile;
   int K;        // k-depth (UPDATE / PANEL); LAUUM: padded order of the matrix
   int nt;       // number of row tiles of the (sub)matrix
   int c0;       // first column tile handled (UPDATE: kt1; PANEL: 0)
@@ -145,7 +143,13 @@ struct GemmParams {
   int P;
   double* partials;     // [tiles][nred]
   double* kinv_out;     // optional: store K^-1 lower tiles (ld = ldc), may be null
-  int krow_mod, krow_rem;  // multi-GPU: only k-tiles with (ktile % krow_mod) == krow_rem contribute (1,0 = all)
+  // ---- multi-GPU (all zero / one on a single GPU) ---------------------------------------------------------------
+  // block-mapped operands: row tile r of a mapped matrix lives in chunk pos(R) = (R % map_G) * map_npr + R / map_G,
+  // R = r / map_blk, at  base + pos * map_stride + (r % map_blk) * TILE  (chunks are map_blk*TILE rows, column-major)
+  int map_A, map_B, map_C;     // which of A / B / C use the block mapping
+  int map_blk, map_G, map_npr; long map_stride;
+  int own_G, own_g, own_blk;   // UPDATE / PANEL: a tile is processed iff ((r / own_blk) % own_G) == own_g
+  int k_G, k_g, k_blk;         // LAUUM: only k-tiles inside column blocks kb == k_g (mod k_G), k_blk tiles per block
   KernParams kp;
 };
 

@@ -1,0 +1,63 @@
+// gpx_ctx.cuh — the device context behind the opaque gpx_ctx of include/gpx.h (internal).
+#pragma once
+#include <vector>
+
+#include "gpx_common.cuh"
+
+struct DistState;
+
+struct gpx_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;   // high-priority side stream: diagonal-block work + panel of the NEXT step (look-ahead)
+  int lookahead = 1;
+  std::vector<cudaEvent_t> sync_ev;
+  // data
+  long N = 0, Npad = 0;
+  int D = 0, P = 0;
+  double* dX = nullptr;      // N x D row-major (as given)
+  double* dXsT = nullptr;    // [D][Npad] scaled SoA
+  double* dsq = nullptr;     // [Npad]
+  double* dY = nullptr;      // [P][Npad]
+  double* dT = nullptr;      // [P][Npad]  L^-1 y
+  double* dAlpha = nullptr;  // [P][Npad]
+  double* dUvPart = nullptr; // [KSPLIT][P][Npad]
+  // workspace
+  double* S = nullptr;       // Npad x Npad column-major: lower L, upper U
+  double* Pbuf = nullptr;    // Npad x NB
+  double* Tm = nullptr;      // NB x NB
+  double* Ldiag = nullptr;   // nt tiles of 128x128
+  double* Dinv = nullptr;    // nt tiles of 128x128
+  double* logdet_part = nullptr;
+  double* partials = nullptr;
+  int* info = nullptr;
+  double* res = nullptr;     // device result vector
+  double* h_res = nullptr;   // pinned
+  int* h_info = nullptr;     // pinned
+  double* Kinv = nullptr;    // lazy, Npad x Npad (lower tiles)
+  double* staging = nullptr; // lazy, N x N dense
+  size_t staging_cap = 0;
+  long NB = 0;               // outer block (0 = auto)
+  // last evaluation
+  bool have_eval = false;
+  bool have_kinv = false;
+  gpx::KernParams kp{};
+  double noise = 0, jitter = 0, jitter_extra = 0;
+  // accounting
+  gpx_stats stats{};
+  int64_t total_launches = 0;
+  int64_t eval_launches = 0;
+  std::vector<cudaEvent_t> ev;
+  int profile = 1;
+  struct DistState* dist = nullptr;   // multi-GPU state (gpx_dist.cu), null on a single GPU
+};
+
+
+namespace gpx {
+constexpr int KSPLIT = 32;
+GemmParams gemm_defaults();
+// multi-GPU hooks implemented in gpx_dist.cu
+int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y, int P);
+int dist_exact_eval(gpx_ctx* c, double extra_jitter);
+void dist_free(gpx_ctx* c);
+}  // namespace gpx

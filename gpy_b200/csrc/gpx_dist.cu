@@ -1,0 +1,348 @@
+// gpx_dist.cu — multi-GPU exact-GP evaluation: one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// The reference has NO multi-device strategy for the exact path (its only collectives are mpi4py sums for
+// the sparse model, GPy/inference/latent_function_inference/var_dtc_parallel.py:127-130), so this is new design:
+//
+//   * block rows of width NB are dealt block-cyclically: rank (R mod G) owns block row R of the unified workspace S
+//     (its Cholesky rows AND its rows of the inverse region). X, Y are replicated (<= a few MiB).
+//   * step k of the sweep: the owner factors-and-inverts the diagonal block and BROADCASTS L_kk^-1 (NB x NB);
+//     every rank forms the panel rows it owns, P_R = S(R,k) L_kk^-T, into a chunked panel buffer whose chunks are
+//     ordered by owner, so ONE in-place ncclAllGather hands every rank the whole panel; every rank then updates the
+//     tiles of its own block rows,  S(r,c) -= P_r P_c^T.
+//   * the panel rows above the diagonal block are exactly block column k of U = L^-T, and every rank sees them in the
+//     all-gather: the rank that owns COLUMN block k keeps them. U thereby ends up column-distributed at no extra cost,
+//     which is what K^-1 = U U^T needs: each rank runs the LAUUM over the k-range of its own column blocks and reduces its
+//     gradient partials locally — K^-1 is never communicated; nl+2 scalars (+ logdet) are all-reduced.
+//   * alpha = U (U^T y): each rank contributes the entries / partial sums of its column blocks, two N-vector all-reduces.
+//
+// NCCL is loaded with dlopen at gpx_comm_init time (the library shipped with PyTorch), so libgpx.so itself has no link
+// dependency on it.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "gpx_common.cuh"
+#include "gpx_ctx.cuh"
+#include "gpx_kernels.cuh"
+
+// ---- minimal NCCL surface (types as in nccl.h 2.x) ---------------------------------------------------------------
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1, ncclInt32 = 2, ncclInt = 2, ncclUint32 = 3, ncclInt64 = 4,
+               ncclUint64 = 5, ncclFloat16 = 6, ncclHalf = 6, ncclFloat32 = 7, ncclFloat = 7, ncclFloat64 = 8,
+               ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+}
+
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return 0;
+  const char* cands[] = {getenv("GPX_NCCL_LIB"),
+                         "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2",
+                         "libnccl.so.2", "libnccl.so"};
+  for (const char* cnd : cands) {
+    if (!cnd) continue;
+    g_nccl.handle = dlopen(cnd, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) { gpx::set_error("cannot dlopen libnccl.so.2 (set GPX_NCCL_LIB)"); return -3; }
+#define GPX_SYM(field, name)                                                                  \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.handle, name);                                      \
+  if (!g_nccl.field) { gpx::set_error(std::string("libnccl lacks ") + name); return -3; }
+  GPX_SYM(GetUniqueId, "ncclGetUniqueId")
+  GPX_SYM(CommInitRank, "ncclCommInitRank")
+  GPX_SYM(CommDestroy, "ncclCommDestroy")
+  GPX_SYM(Broadcast, "ncclBroadcast")
+  GPX_SYM(AllGather, "ncclAllGather")
+  GPX_SYM(AllReduce, "ncclAllReduce")
+  GPX_SYM(GetErrorString, "ncclGetErrorString")
+#undef GPX_SYM
+  return 0;
+}
+}  // namespace
+
+#define GPX_NCCL(call)                                                                                       \
+  do {                                                                                                       \
+    ncclResult_t r__ = (call);                                                                               \
+    if (r__ != ncclSuccess) {                                                                                \
+      gpx::set_error(std::string(#call) + " failed: " + g_nccl.GetErrorString(r__) + " at " + __FILE__ + ":" + \
+                     std::to_string(__LINE__));                                                              \
+      return -4;                                                                                             \
+    }                                                                                                        \
+  } while (0)
+#define GPX_CHECK(x)            \
+  do {                          \
+    int rc__ = (x);             \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+struct DistState {
+  ncclComm_t comm = nullptr;
+  int rank = 0, G = 1;
+  long NB = 0, npr = 0, nblk = 0;
+  double* Bc = nullptr;        // NB x NB broadcast buffer (L_kk^-1)
+  double* raw = nullptr;       // device: raw sums for the scalar all-reduce
+  double* h_raw = nullptr;     // pinned
+  double* blkpart = nullptr;   // [nblk][P][Npad] partials of alpha
+};
+
+using namespace gpx;
+
+namespace gpx {
+
+void dist_free(gpx_ctx* c) {
+  if (!c->dist) return;
+  DistState* d = c->dist;
+  if (d->Bc) cudaFree(d->Bc);
+  if (d->blkpart) cudaFree(d->blkpart);
+  d->Bc = d->blkpart = nullptr;
+}
+
+static long dist_pick_nb(const gpx_ctx* c, long N) {
+  if (c->NB > 0) return c->NB;
+  const char* e = getenv("GPX_NB");
+  if (e && atol(e) >= TILE && atol(e) % TILE == 0) return atol(e);
+  if (N >= 32768) return 1024;
+  if (N >= 8192) return 512;
+  return 256;
+}
+
+int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y, int P) {
+  DistState* d = c->dist;
+  const long NB = std::min<long>(dist_pick_nb(c, N), (N + TILE - 1) / TILE * TILE);
+  const long Npad = (N + NB - 1) / NB * NB;      // whole blocks: every rank sees the same block structure
+  const long nblk = Npad / NB, npr = (nblk + d->G - 1) / d->G;
+  if (Npad != c->Npad || D != c->D || P != c->P || NB != d->NB) {
+    GPX_CUDA(cudaStreamSynchronize(c->st));
+    // release the single-GPU style allocations of this context
+    double** ptrs[] = {&c->dX, &c->dXsT, &c->dsq, &c->dY, &c->dT, &c->dAlpha, &c->dUvPart, &c->S, &c->Pbuf, &c->Tm,
+                       &c->Ldiag, &c->Dinv, &c->logdet_part, &c->partials, &c->Kinv, &c->staging};
+    for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    c->staging_cap = 0;
+    dist_free(c);
+    c->Npad = Npad; c->D = D; c->P = P;
+    d->NB = NB; d->nblk = nblk; d->npr = npr;
+    const long nt = Npad / TILE;
+    GPX_CUDA(cudaMalloc(&c->dX, (size_t)Npad * D * 8));
+    GPX_CUDA(cudaMalloc(&c->dXsT, (size_t)Npad * D * 8));
+    GPX_CUDA(cudaMalloc(&c->dsq, (size_t)Npad * 8));
+    GPX_CUDA(cudaMalloc(&c->dY, (size_t)Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->dT, (size_t)Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->dAlpha, (size_t)Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->dUvPart, (size_t)Npad * P * 8));
+    GPX_CUDA(cudaMalloc(&c->S, (size_t)Npad * Npad * 8));
+    GPX_CUDA(cudaMalloc(&c->Pbuf, (size_t)d->G * npr * NB * NB * 8));
+    GPX_CUDA(cudaMalloc(&c->Tm, (size_t)NB * NB * 8));
+    GPX_CUDA(cudaMalloc(&d->Bc, (size_t)NB * NB * 8));
+    GPX_CUDA(cudaMalloc(&c->Ldiag, (size_t)Npad * TILE * 8));
+    GPX_CUDA(cudaMalloc(&c->Dinv, (size_t)Npad * TILE * 8));
+    GPX_CUDA(cudaMalloc(&c->logdet_part, (size_t)nt * 8));
+    GPX_CUDA(cudaMalloc(&c->partials, (size_t)nt * nt * (MAX_D + 2) * 8));
+    GPX_CUDA(cudaMalloc(&d->blkpart, (size_t)nblk * P * Npad * 8));
+    GPX_CUDA(cudaMemsetAsync(c->Pbuf, 0, (size_t)d->G * npr * NB * NB * 8, c->st));
+  }
+  c->N = N;
+  c->have_eval = false;
+  c->have_kinv = false;
+  GPX_CUDA(cudaMemcpyAsync(c->dX, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, c->st));
+  GPX_CUDA(cudaMemcpyAsync(c->dT, Y, (size_t)N * P * 8, cudaMemcpyHostToDevice, c->st));
+  GPX_CHECK(launch_transpose_pad(c->dT, N, P, Npad, c->dY, c->st));
+  c->total_launches += 1;
+  GPX_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// One distributed evaluation; results (raw sums) land in d->h_raw, the info flag in *c->h_info. Collective.
+int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
+  DistState* d = c->dist;
+  cudaStream_t st = c->st;
+  const long ld = c->Npad, Npad = c->Npad, NB = d->NB;
+  const int nt = (int)(Npad / TILE), nbt = (int)(NB / TILE);
+  const int G = d->G, g = d->rank;
+  const int nl = c->kp.ard ? c->D : 1, nred = nl + 2;
+  GPX_CUDA(cudaMemsetAsync(c->info, 0, sizeof(int), st));
+  GPX_CUDA(cudaMemsetAsync(c->logdet_part, 0, (size_t)nt * 8, st));
+  GPX_CHECK(launch_prep_x(c->dX, c->N, Npad, c->kp, c->dXsT, c->dsq, st));
+  c->eval_launches++;
+  {
+    KBuildParams kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.rowsT = c->dXsT; kb.ld_rows = Npad; kb.colsT = c->dXsT; kb.ld_cols = Npad;
+    kb.sq_rows = c->dsq; kb.sq_cols = c->dsq;
+    kb.out = c->S; kb.ld = ld; kb.nrows = c->N; kb.ncols = c->N; kb.sym = 1; kb.same = 1;
+    kb.diag_add = (c->noise + c->jitter) + extra_jitter;
+    kb.own_G = G; kb.own_g = g; kb.own_blk = nbt;
+    kb.kp = c->kp;
+    GPX_CHECK(launch_kbuild(kb, nt, nt, st));
+    c->eval_launches++;
+  }
+  // ---- sweep -----------------------------------------------------------------------------------------------------
+  for (int k = 0; k < (int)d->nblk; k++) {
+    const long o = (long)k * NB;
+    const int kt0 = k * nbt, kt1 = kt0 + nbt;
+    const int root = k % G;
+    const long pos_k = (long)(k % G) * d->npr + k / G;
+    if (g == root) {
+      double* Sblk = c->S + o + o * ld;
+      for (int dd = 0; dd < nbt; dd++) {
+        const int gt = kt0 + dd;
+        double* tile = Sblk + (long)dd * TILE + (long)dd * TILE * ld;
+        GPX_CHECK(launch_base(tile, ld, c->Ldiag + (long)gt * TILE * TILE, c->Dinv + (long)gt * TILE * TILE,
+                              c->logdet_part + gt, c->info, gt * TILE, st));
+        c->eval_launches++;
+        if (nbt > 1) {
+          GemmParams pp = gemm_defaults();
+          pp.mode = GEMM_PANEL;
+          pp.A = Sblk + (long)dd * TILE * ld; pp.lda = ld;
+          pp.B = c->Dinv + (long)gt * TILE * TILE; pp.ldb = TILE;
+          pp.C = Sblk + (long)dd * TILE * ld; pp.ldc = ld;
+          pp.K = TILE; pp.nt = nbt; pp.skip0 = dd; pp.skip1 = dd + 1;
+          GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), st));
+          c->eval_launches++;
+          if (dd + 1 < nbt) {
+            GemmParams pu = gemm_defaults();
+            pu.mode = GEMM_UPDATE;
+            pu.A = Sblk + (long)dd * TILE * ld; pu.lda = ld; pu.B = pu.A; pu.ldb = ld;
+            pu.C = Sblk; pu.ldc = ld; pu.K = TILE; pu.nt = nbt; pu.c0 = dd + 1; pu.rlow = dd + 1;
+            GPX_CHECK(launch_gemm(pu, dim3(1, 1), st));
+            c->eval_launches++;
+          }
+        }
+      }
+      // U_kk into this rank's chunk of the panel buffer, L_kk^-1 into the broadcast buffer
+      GPX_CHECK(launch_assemble(Sblk, ld, (int)NB, c->Pbuf + pos_k * NB * NB, NB, d->Bc, st));
+      c->eval_launches++;
+    }
+    if (d->nblk == 1) break;
+    GPX_NCCL(g_nccl.Broadcast(d->Bc, d->Bc, (size_t)NB * NB, ncclDouble, root, d->comm, st));
+    {
+      GemmParams pp = gemm_defaults();
+      pp.mode = GEMM_PANEL;
+      pp.A = c->S + o * ld; pp.lda = ld;
+      pp.B = d->Bc; pp.ldb = NB;
+      pp.C = c->Pbuf; pp.ldc = NB; pp.map_C = 1;
+      pp.map_blk = nbt; pp.map_G = G; pp.map_npr = (int)d->npr; pp.map_stride = NB * NB;
+      pp.own_G = G; pp.own_g = g; pp.own_blk = nbt;
+      pp.K = (int)NB; pp.nt = nt; pp.skip0 = kt0; pp.skip1 = kt1; pp.tri = 1;
+      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), st));
+      c->eval_launches++;
+    }
+    GPX_NCCL(g_nccl.AllGather(c->Pbuf + (size_t)g * d->npr * NB * NB, c->Pbuf, (size_t)d->npr * NB * NB, ncclDouble,
+                              d->comm, st));
+    GPX_CHECK(launch_copyback(c->S, ld, c->Pbuf, NB, G, g, d->npr, k, nt, st));
+    c->eval_launches++;
+    if (kt1 < nt) {
+      GemmParams pu = gemm_defaults();
+      pu.mode = GEMM_UPDATE;
+      pu.A = c->Pbuf; pu.lda = NB; pu.map_A = 1;
+      pu.B = c->Pbuf; pu.ldb = NB; pu.map_B = 1;
+      pu.map_blk = nbt; pu.map_G = G; pu.map_npr = (int)d->npr; pu.map_stride = NB * NB;
+      pu.own_G = G; pu.own_g = g; pu.own_blk = nbt;
+      pu.C = c->S; pu.ldc = ld;
+      pu.K = (int)NB; pu.nt = nt; pu.c0 = kt1; pu.rlow = kt1;
+      GPX_CHECK(launch_gemm(pu, dim3(1, 1), st));
+      c->eval_launches++;
+      c->stats.update_launches++;
+    }
+  }
+  // ---- alpha = U (U^T y): owned column blocks, two vector all-reduces ------------------------------------------------
+  GPX_CUDA(cudaMemsetAsync(c->dT, 0, (size_t)Npad * c->P * 8, st));
+  GPX_CHECK(launch_utv(c->S, ld, Npad, c->P, c->dY, c->dT, st, G, g, NB));
+  GPX_NCCL(g_nccl.AllReduce(c->dT, c->dT, (size_t)Npad * c->P, ncclDouble, ncclSum, d->comm, st));
+  GPX_CHECK(launch_uv_blk(c->S, ld, Npad, c->P, c->dT, NB, G, g, d->blkpart, c->dAlpha, st));
+  GPX_NCCL(g_nccl.AllReduce(c->dAlpha, c->dAlpha, (size_t)Npad * c->P, ncclDouble, ncclSum, d->comm, st));
+  c->eval_launches += 3;
+  // ---- K^-1 = U U^T over the owned k-range with the fused gradient epilogue ------------------------------------------
+  GPX_CUDA(cudaMemsetAsync(c->partials, 0, (size_t)nt * nt * nred * 8, st));
+  {
+    GemmParams pl = gemm_defaults();
+    pl.mode = GEMM_LAUUM;
+    pl.A = c->S; pl.lda = ld; pl.B = c->S; pl.ldb = ld; pl.C = nullptr; pl.ldc = ld;
+    pl.K = (int)Npad; pl.nt = nt;
+    pl.XsT = c->dXsT; pl.sq = c->dsq; pl.alpha = c->dAlpha; pl.ldx = Npad;
+    pl.N = (int)c->N; pl.P = c->P; pl.partials = c->partials; pl.kinv_out = nullptr;
+    pl.k_G = G; pl.k_g = g; pl.k_blk = nbt;
+    pl.kp = c->kp;
+    GPX_CHECK(launch_gemm(pl, dim3(1, 1), st));
+    c->eval_launches++;
+  }
+  {
+    FinalizeParams f;
+    memset(&f, 0, sizeof(f));
+    f.partials = c->partials; f.ntiles = (long)nt * nt; f.nl = nl;
+    f.logdet_part = c->logdet_part; f.nt = nt;
+    f.T = c->dT; f.ld = ld; f.N = c->N; f.P = c->P; f.kp = c->kp; f.res = d->raw;
+    GPX_CHECK(launch_finalize_raw(f, st));
+    c->eval_launches++;
+  }
+  GPX_NCCL(g_nccl.AllReduce(d->raw, d->raw, (size_t)nred + 1, ncclDouble, ncclSum, d->comm, st));   // not |T|^2
+  GPX_NCCL(g_nccl.AllReduce(c->info, c->info, 1, ncclInt32, ncclMax, d->comm, st));
+  GPX_CUDA(cudaMemcpyAsync(d->h_raw, d->raw, (nred + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPX_CUDA(cudaMemcpyAsync(c->h_info, c->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GPX_CUDA(cudaStreamSynchronize(st));
+  // assemble (lml, gradient) exactly as finalize_kernel does on a single GPU
+  const double* tot = d->h_raw;
+  const double logdet = tot[nred], quad = tot[nred + 1];
+  const double log2pi = 1.8378770664093453;
+  c->h_res[0] = 0.5 * (-(double)c->N * c->P * log2pi - (double)c->P * logdet - quad);
+  c->h_res[1] = tot[0];
+  if (c->kp.ard) {
+    for (int q = 0; q < nl; q++) c->h_res[2 + q] = -tot[1 + q] / c->kp.ls[q];
+  } else {
+    c->h_res[2] = -tot[1] / c->kp.ls[0];
+  }
+  c->h_res[2 + nl] = tot[nred - 1];
+  c->h_res[3 + nl] = logdet;
+  c->h_res[4 + nl] = quad;
+  return 0;
+}
+
+}  // namespace gpx
+
+extern "C" {
+
+int gpx_comm_unique_id(char id_out[128]) {
+  if (!id_out) { gpx::set_error("null argument"); return -2; }
+  GPX_CHECK(load_nccl());
+  ncclUniqueId id;
+  GPX_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+int gpx_comm_init(gpx_ctx* c, const char id[128], int rank, int nranks) {
+  if (!c || !id) { gpx::set_error("null argument"); return -2; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { gpx::set_error("bad rank / nranks"); return -2; }
+  GPX_CHECK(load_nccl());
+  GPX_CUDA(cudaSetDevice(c->device));
+  if (!c->dist) c->dist = new DistState();
+  DistState* d = c->dist;
+  ncclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  GPX_NCCL(g_nccl.CommInitRank(&d->comm, nranks, uid, rank));
+  d->rank = rank; d->G = nranks;
+  GPX_CUDA(cudaMalloc(&d->raw, (MAX_D + 8) * sizeof(double)));
+  GPX_CUDA(cudaMallocHost(&d->h_raw, (MAX_D + 8) * sizeof(double)));
+  c->Npad = 0;   // force re-allocation in the distributed layout at the next gpx_set_data
+  return 0;
+}
+
+}  // extern "C"

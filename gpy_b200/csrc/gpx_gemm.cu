@@ -14,64 +14,112 @@
 // (cp.async.bulk -> SASS UBLKCP, the TMA engine) signalled through mbarriers. Operands are m-contiguous
 // (column-major), a slab column is one 1 KiB bulk copy; the smem pitch of 132 doubles makes the DMMA fragment
 // loads bank-conflict free. Measured DMMA issue peak on B200: 37.1 TFLOP/s (tools/microbench.cu).
+#include <algorithm>
+
 #include "gpx_common.cuh"
 
 namespace gpx {
 
 constexpr int SLAB_DOUBLES = KSLAB * PITCH;                       // one operand, one stage
 constexpr int PIPE_BYTES = 2 * STAGES * SLAB_DOUBLES * 8;         // 135168
-constexpr int EPI_DOUBLES = (2 * MAX_D + 2 + 2 * MAX_P) * TILE + CONSUMER_WARPS * (MAX_D + 3);
-constexpr int EPI_BYTES = EPI_DOUBLES * 8;
-constexpr int DATA_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
-constexpr int SMEM_BYTES = DATA_BYTES + 2 * STAGES * 8 + 64;
+constexpr int BAR_BYTES = 128;                                    // 2*STAGES mbarriers at the front of the dynamic smem
+// epilogue footprint of the LAUUM kernel: staged accumulators + input tiles + alpha tiles + reduction scratch
+static int epi_bytes(int D, int P) {
+  const int nphase = D > 32 ? 2 : 1;
+  return (64 * (CONSUMER_WARPS * 32 / nphase) + (2 * D + 2 + 2 * P) * TILE + CONSUMER_WARPS * (D + 3)) * 8;
+}
+constexpr int SMEM_PIPE = BAR_BYTES + PIPE_BYTES;
+constexpr int SMEM_MAX = 227 * 1024;
 constexpr int SB = 12;   // super-block edge of the tile schedule (SB*SB = 144 <= 148 SMs)
 
-size_t gemm_smem_bytes() { return SMEM_BYTES; }
+size_t gemm_smem_bytes() { return SMEM_PIPE; }
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory"); }
 
-template <int MODE>
-__device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* sA = reinterpret_cast<double*>(smem_raw);
-  double* sB = sA + STAGES * SLAB_DOUBLES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + DATA_BYTES);
-  uint64_t* empty = full + STAGES;
+// Tile schedule. UPDATE / LAUUM run on a 1-D grid decoded through SB x SB super-blocks so that the ~148 CTAs in flight
+// share <= 2*SB row panels and SB column panels (operand streams stay L2-resident). LAUUM enumerates the super-blocks of
+// the lower triangle row by row: small r first = longest k-ranges first, so the tail of the launch is made of short tiles.
+// block-mapped operand base of row tile r (see GemmParams)
+__device__ __forceinline__ long mapped_offset(const GemmParams& p, int r) {
+  const int R = r / p.map_blk, t = r % p.map_blk;
+  const long pos = (long)(R % p.map_G) * p.map_npr + R / p.map_G;
+  return pos * p.map_stride + (long)t * TILE;
+}
 
-  // ---- tile mapping ------------------------------------------------------------------------------------------
-  // UPDATE / LAUUM run on a 1-D grid decoded into (slot, column) through SB x SB super-blocks, so that the ~148 CTAs in
-  // flight share <= 2*SB row panels and SB column panels and the operand streams stay L2-resident.
-  int r, c, kt_first = 0, nkt;
-  const int kt_step = p.krow_mod;
-  if (MODE == GEMM_UPDATE || MODE == GEMM_LAUUM) {
+// LAUUM k-tile sequence of tile row r: all k-tiles >= r, or (multi-GPU) those inside the owned column blocks.
+struct KSeq { int first, n0, kb0; };
+__device__ __forceinline__ int kseq_init(const GemmParams& p, int r, KSeq& q) {
+  if (p.k_G <= 1) { q.first = r; q.n0 = p.nt - r; q.kb0 = 0; return p.nt - r; }
+  const int nblk = p.nt / p.k_blk;
+  const int kbmin = r / p.k_blk;
+  q.kb0 = kbmin + ((p.k_g - kbmin) % p.k_G + p.k_G) % p.k_G;
+  if (q.kb0 >= nblk) { q.first = 0; q.n0 = 0; return 0; }
+  const int t0 = q.kb0 == kbmin ? r - kbmin * p.k_blk : 0;
+  q.first = q.kb0 * p.k_blk + t0;
+  q.n0 = p.k_blk - t0;
+  return q.n0 + ((nblk - 1 - q.kb0) / p.k_G) * p.k_blk;
+}
+__device__ __forceinline__ int kseq_tile(const GemmParams& p, const KSeq& q, int j) {
+  if (p.k_G <= 1 || j < q.n0) return q.first + j;
+  const int jj = j - q.n0;
+  return (q.kb0 + p.k_G * (1 + jj / p.k_blk)) * p.k_blk + jj % p.k_blk;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool decode_tile(const GemmParams& p, int& r, int& c) {
+  if (MODE == GEMM_UPDATE) {
     const int ncols = p.ncols > 0 ? p.ncols : p.nt - p.c0;
     const int sbcols = (ncols + SB - 1) / SB;
     const int sb = blockIdx.x / (SB * SB), t = blockIdx.x % (SB * SB);
     const int slot = (sb / sbcols) * SB + t / SB;
     const int col = (sb % sbcols) * SB + t % SB;
-    if (col >= ncols) return;
+    if (col >= ncols) return false;
     c = p.c0 + col;
     r = slot < p.rlow ? slot : c + (slot - p.rlow);
-    if (r >= p.nt) return;
-    if (MODE == GEMM_UPDATE) {
-      nkt = p.K / TILE;
-    } else {
-      // k-tiles kt in [r, nt) with kt % krow_mod == krow_rem
-      kt_first = r + ((p.krow_rem - r) % kt_step + kt_step) % kt_step;
-      nkt = kt_first < p.nt ? (p.nt - 1 - kt_first) / kt_step + 1 : 0;
-    }
-  } else {  // GEMM_PANEL
-    c = blockIdx.x;
+    if (r >= p.nt) return false;
+    return p.own_G <= 1 || ((r / p.own_blk) % p.own_G) == p.own_g;
+  } else if (MODE == GEMM_LAUUM) {
+    const int sb = blockIdx.x / (SB * SB), t = blockIdx.x % (SB * SB);
+    int R = (int)((sqrtf(8.f * (float)sb + 1.f) - 1.f) * 0.5f);
+    while (R * (R + 1) / 2 > sb) --R;
+    while ((R + 1) * (R + 2) / 2 <= sb) ++R;
+    const int C = sb - R * (R + 1) / 2;
+    r = R * SB + t / SB;
+    c = C * SB + t % SB;
+    return r < p.nt && c <= r;
+  } else {  // GEMM_PANEL: 2-D grid (output column tile, row slot); triangular B: longest k-range first
+    c = p.tri ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
     const int slot = blockIdx.y;
     r = slot < p.skip0 ? slot : slot + (p.skip1 - p.skip0);
-    if (r >= p.nt) return;
+    if (r >= p.nt) return false;
+    return p.own_G <= 1 || ((r / p.own_blk) % p.own_G) == p.own_g;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + STAGES;
+  double* sA = reinterpret_cast<double*>(smem_raw + BAR_BYTES);
+  double* sB = sA + STAGES * SLAB_DOUBLES;
+
+  // ---- tile mapping (decode_tile) ---------------------------------------------------------------------------------
+  int r, c;
+  if (!decode_tile<MODE>(p, r, c)) return;
+  int nkt;
+  KSeq kq;
+  kq.first = 0; kq.n0 = 1 << 30; kq.kb0 = 0;
+  if (MODE == GEMM_UPDATE) {
+    nkt = p.K / TILE;
+  } else if (MODE == GEMM_LAUUM) {
+    nkt = kseq_init(p, r, kq);
+  } else {
     nkt = p.tri ? (c + 1) : p.K / TILE;
   }
-  const double* Aptr;
-  long lda;
-  if (r == p.sub_tile) { Aptr = p.subA; lda = TILE; } else { Aptr = p.A + (long)r * TILE; lda = p.lda; }
-  const double* Bptr = p.B + (long)c * TILE;
-  const long ldb = p.ldb;
+  const double* Aptr = p.A + (p.map_A ? mapped_offset(p, r) : (long)r * TILE);
+  const double* Bptr = p.B + (p.map_B ? mapped_offset(p, c) : (long)c * TILE);
+  const long lda = p.lda, ldb = p.ldb;
   const int nslab = nkt * (TILE / KSLAB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +143,7 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
       if (it >= STAGES) mbar_wait(&empty[s], (n & 1) ^ 1);
       if (lane == 0) mbar_arrive_expect_tx(&full[s], 2 * KSLAB * TILE * 8);
       __syncwarp();
-      const long k = (long)(kt_first + (it >> 3) * kt_step) * TILE + (it & 7) * KSLAB + kc;
+      const long k = (long)(MODE == GEMM_LAUUM ? kseq_tile(p, kq, it >> 3) : (it >> 3)) * TILE + (it & 7) * KSLAB + kc;
       bulk_g2s(dst_base + s * SLAB_DOUBLES, src_base + k * ld, TILE * 8, &full[s]);
     }
     return;
@@ -108,7 +156,7 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   if (MODE == GEMM_UPDATE) {
     // C -= A B^T  ==  C + (-A) B^T : the accumulators start from the old C tile (loads overlap the pipeline fill),
     // the A fragments are negated on the way in, and the epilogue is store-only.
-    const double* Ct = p.C + (long)r * TILE + (long)c * TILE * p.ldc;
+    const double* Ct = p.C + (p.map_C ? mapped_offset(p, r) : (long)r * TILE) + (long)c * TILE * p.ldc;
 #pragma unroll
     for (int mb = 0; mb < 8; mb++)
 #pragma unroll
@@ -148,7 +196,8 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
 
   // ================= epilogues ===============================================================================
   if (MODE != GEMM_LAUUM) {
-    double* Ct = p.C + (long)r * TILE + (long)c * TILE * p.ldc;
+    decode_tile<MODE>(p, r, c);
+    double* Ct = p.C + (p.map_C ? mapped_offset(p, r) : (long)r * TILE) + (long)c * TILE * p.ldc;
 #pragma unroll
     for (int mb = 0; mb < 8; mb++) {
       const int i = wm * 64 + mb * 8 + g;
@@ -161,11 +210,18 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   }
 
   // ---- LAUUM: fused dL_dK -> gradient reductions ---------------------------------------------------------------
+  // The accumulators are staged through shared memory (thread-private columns, conflict-free) and the per-element
+  // work runs as a ROLLED loop: unrolled over the 64 accumulators it was ~160 KB of straight-line code per tile and
+  // the kernel stalled on instruction fetch (ncu: stalled_no_instruction ~1.1 per issue, DMMA pipe 83 % vs 93 %).
+  decode_tile<MODE>(p, r, c);   // recomputed here so that r, c are not live across the main loop
   const int D = p.kp.D, P = p.P;
   const int nl = p.kp.ard ? D : 1;
   const int nred = nl + 2;
+  const int nphase = D > 32 ? 2 : 1;            // large D: the two 64-row halves take turns in the staging area
+  const int sthr = CONSUMER_WARPS * 32 / nphase;  // threads per phase
   consumer_bar();  // every consumer is done reading the pipeline buffers; reuse them
-  double* sXr = reinterpret_cast<double*>(smem_raw);
+  double* sSt = reinterpret_cast<double*>(smem_raw + BAR_BYTES);          // [64][sthr] staged accumulators
+  double* sXr = sSt + 64 * sthr;
   double* sXc = sXr + D * TILE;
   double* sSr = sXc + D * TILE;
   double* sSc = sSr + TILE;
@@ -184,7 +240,6 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
     sAc[idx] = p.alpha[(long)q * p.ldx + (long)c * TILE + m];
   }
   if (tid < TILE) { sSr[tid] = p.sq[(long)r * TILE + tid]; sSc[tid] = p.sq[(long)c * TILE + tid]; }
-  consumer_bar();
 
   const double w = (r > c) ? 2.0 : 1.0;   // strictly-lower tiles stand for their mirror image as well
   const int kind = p.kp.kind;
@@ -192,17 +247,28 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   const bool ard = p.kp.ard != 0;
   double gvar = 0.0, giso = 0.0, gnoise = 0.0;
   double* kout = p.kinv_out ? p.kinv_out + (long)r * TILE + (long)c * TILE * p.ldc : nullptr;
+  double* red = sRed + warp * nred;
+  const int lt = nphase == 1 ? tid : (warp >> 1) * 32 + lane;   // thread slot inside the staging area
+  double* st = sSt + lt;
+  const int i0 = wm * 64 + g, j0 = wn * 32 + 2 * tg;
+
+  for (int ph = 0; ph < nphase; ph++) {
+    const bool mine = (nphase == 1) || (wm == ph);
+    if (mine) {
 #pragma unroll
-  for (int mb = 0; mb < 8; mb++) {
-    const int il = wm * 64 + mb * 8 + g;
-    const long gi = (long)r * TILE + il;
+      for (int mb = 0; mb < 8; mb++)
 #pragma unroll
-    for (int nb = 0; nb < 4; nb++)
+        for (int nb = 0; nb < 4; nb++)
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int jl = wn * 32 + nb * 8 + 2 * tg + e;
-        const long gj = (long)c * TILE + jl;
-        const double kinv = acc[mb][nb][e];
+          for (int e = 0; e < 2; e++) st[((mb * 4 + nb) * 2 + e) * sthr] = acc[mb][nb][e];
+    }
+    consumer_bar();   // staging (and, first time round, the input tiles) visible
+    if (mine) {
+#pragma unroll 1
+      for (int e = 0; e < 64; e++) {
+        const int il = i0 + (e >> 3) * 8, jl = j0 + ((e >> 1) & 3) * 8 + (e & 1);
+        const long gi = (long)r * TILE + il, gj = (long)c * TILE + jl;
+        const double kinv = st[e * sthr];
         if (kout) kout[il + (long)jl * p.ldc] = kinv;
         double dot = 0.0;
         for (int q = 0; q < D; q++) dot = fma(sXr[q * TILE + il], sXc[q * TILE + jl], dot);
@@ -220,34 +286,33 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
         if (gi == gj) gnoise += dl;
         const double G = variance * dk * dl;
         if (ard) {
-          acc[mb][nb][e] = (rr != 0.0) ? w * G / rr : 0.0;   // stationary.py:205,225-232: 1/r with 1/0 := 0
+          st[e * sthr] = (rr != 0.0) ? w * G / rr : 0.0;   // stationary.py:205,225-232: 1/r with 1/0 := 0
         } else {
           giso = fma(w * G, rr, giso);
         }
       }
+      if (ard) {
+        for (int q = 0; q < D; q++) {
+          const double* xr = sXr + q * TILE;
+          const double* xc = sXc + q * TILE;
+          double s = 0.0;
+#pragma unroll 4
+          for (int e = 0; e < 64; e++) {
+            const int il = i0 + (e >> 3) * 8, jl = j0 + ((e >> 1) & 3) * 8 + (e & 1);
+            const double df = xr[il] - xc[jl];
+            s = fma(st[e * sthr], df * df, s);
+          }
+          s = warp_sum(s);
+          if (lane == 0) red[1 + q] = s;
+        }
+      }
+    }
+    if (nphase > 1) consumer_bar();   // the other half may now overwrite the staging area
   }
-  double* red = sRed + warp * nred;
   gvar = warp_sum(gvar);
   gnoise = warp_sum(gnoise);
   if (lane == 0) { red[0] = gvar; red[nred - 1] = gnoise; }
-  if (ard) {
-    for (int q = 0; q < D; q++) {
-      double s = 0.0;
-#pragma unroll
-      for (int mb = 0; mb < 8; mb++) {
-        const double xi = sXr[q * TILE + wm * 64 + mb * 8 + g];
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const double df = xi - sXc[q * TILE + wn * 32 + nb * 8 + 2 * tg + e];
-            s = fma(acc[mb][nb][e], df * df, s);
-          }
-      }
-      s = warp_sum(s);
-      if (lane == 0) red[1 + q] = s;
-    }
-  } else {
+  if (!ard) {
     giso = warp_sum(giso);
     if (lane == 0) red[1] = giso;
   }
@@ -266,23 +331,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_panel_kernel(const GemmP
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_lauum_kernel(const GemmParams p) { gemm_nt_body<GEMM_LAUUM>(p); }
 
 int gemm_init() {
-  GPX_CUDA(cudaFuncSetAttribute(gemm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  GPX_CUDA(cudaFuncSetAttribute(gemm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  GPX_CUDA(cudaFuncSetAttribute(gemm_lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
   return 0;
 }
 
 int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t st) {
-  if (p.mode != GEMM_PANEL) {
-    // (slots, columns) domain: UPDATE rows [0, rlow) U [c, nt) for columns [c0, nt); LAUUM: rlow = 0, c0 = 0
+  if (p.mode == GEMM_UPDATE) {
+    // (slots, columns) domain: rows [0, rlow) U [c, nt) for columns [c0, c0 + ncols)
     const int ncols = p.ncols > 0 ? p.ncols : p.nt - p.c0, nslots = p.rlow + (p.nt - p.c0);
     if (ncols <= 0) return 0;
     grid = dim3((unsigned)(((nslots + SB - 1) / SB) * ((ncols + SB - 1) / SB) * SB * SB), 1, 1);
+  } else if (p.mode == GEMM_LAUUM) {
+    const int nsr = (p.nt + SB - 1) / SB;
+    grid = dim3((unsigned)(nsr * (nsr + 1) / 2 * SB * SB), 1, 1);
   }
   if (grid.x == 0 || grid.y == 0) return 0;
-  if (p.mode == GEMM_UPDATE) gemm_update_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
-  else if (p.mode == GEMM_PANEL) gemm_panel_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
-  else gemm_lauum_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  if (p.mode == GEMM_UPDATE) gemm_update_kernel<<<grid, GEMM_THREADS, SMEM_PIPE, st>>>(p);
+  else if (p.mode == GEMM_PANEL) gemm_panel_kernel<<<grid, GEMM_THREADS, SMEM_PIPE, st>>>(p);
+  else {
+    const int smem = BAR_BYTES + std::max(PIPE_BYTES, epi_bytes(p.kp.D, p.P));
+    if (smem > SMEM_MAX) { set_error("LAUUM epilogue does not fit in shared memory"); return -2; }
+    gemm_lauum_kernel<<<grid, GEMM_THREADS, smem, st>>>(p);
+  }
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

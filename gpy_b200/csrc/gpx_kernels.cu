@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
   const long gi = (long)rt * TILE + il;
   double* outp = p.out + gi + ((long)ct * TILE + half * 64) * p.ld;
 
+  if (p.own_G > 1 && ((rt / p.own_blk) % p.own_G) != p.own_g) return;   // block row owned by another rank
   if (p.sym && rt < ct) {  // strictly-upper tile of the factor workspace: the inverse-factor region starts at zero
     for (int j = 0; j < 64; j++) outp[(long)j * p.ld] = 0.0;
     return;
@@ -154,43 +155,58 @@ base_sweep_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, d
       const int row = a + 32 * s, col = b + 16 * t;
       v[s][t] = row >= col ? S[row + (long)col * ld] : 0.0;
     }
+  // software pipeline: while every warp applies column j, the owner warp of column j+1 first brings its own column
+  // up to date, turns it into p_{j+1} and publishes it -- the serial sqrt/divide chain overlaps the rank-1 update.
+#define GPX_APPLY(T2, J)                                                       \
+  {                                                                            \
+    const int col_ = b + 16 * (T2);                                            \
+    const double pc_ = p[col_];                                                \
+    _Pragma("unroll") for (int s = 0; s < 4; s++) {                            \
+      const int row_ = a + 32 * s;                                             \
+      if (row_ >= col_ || row_ <= (J)) v[s][T2] = fma(-pr[s], pc_, v[s][T2]);  \
+    }                                                                          \
+  }
+#define GPX_MAKE_P(T, J)                                                                   \
+  {                                                                                        \
+    const double d_ = __shfl_sync(0xffffffffu, v[(T) >> 1][T], (J) & 31);                  \
+    if (!(d_ > 0.0) && a == 0) atomicCAS(info, 0, gcol0 + (J) + 1);                        \
+    const double l_ = sqrt(d_);                                                            \
+    const double inv_ = 1.0 / l_;                                                          \
+    _Pragma("unroll") for (int s = 0; s < 4; s++) {                                        \
+      const int row_ = a + 32 * s;                                                         \
+      const double val_ = (row_ == (J)) ? inv_ : v[s][T] * inv_;                           \
+      pbuf[(J) & 1][row_] = val_;                                                          \
+      v[s][T] = (row_ == (J)) ? l_ : val_;                                                 \
+    }                                                                                      \
+    if (a == ((J) & 31)) ldiag[J] = l_;                                                    \
+  }
+  if (b == 0) GPX_MAKE_P(0, 0);
+  __syncthreads();
 #pragma unroll
   for (int t = 0; t < 8; t++) {
     for (int jb = 0; jb < 16; jb++) {
       const int j = t * 16 + jb;
-      if (b == jb) {  // owner warp of column j (slot t); the diagonal element sits in lane j&31, row slot t>>1
-        const double d = __shfl_sync(0xffffffffu, v[t >> 1][t], j & 31);
-        if (!(d > 0.0) && a == 0) atomicCAS(info, 0, gcol0 + j + 1);
-        const double l = sqrt(d);
-        const double inv = 1.0 / l;
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          const int row = a + 32 * s;
-          const double val = (row == j) ? inv : v[s][t] * inv;
-          pbuf[j & 1][row] = val;
-          v[s][t] = (row == j) ? l : val;
-        }
-        if (a == (j & 31)) ldiag[j] = l;
-      }
-      __syncthreads();
       const double* p = pbuf[j & 1];
       double pr[4];
 #pragma unroll
       for (int s = 0; s < 4; s++) pr[s] = p[a + 32 * s];
+      if (jb < 15) {
+        if (b == jb + 1) { GPX_APPLY(t, j); GPX_MAKE_P(t, j + 1); }
+      } else if (t < 7) {
+        if (b == 0) { GPX_APPLY(t + 1, j); GPX_MAKE_P(t + 1, j + 1); }
+      }
 #pragma unroll
       for (int t2 = 0; t2 < 8; t2++) {
         if (t2 < t) continue;
-        if (t2 == t && b <= jb) continue;
-        const int col = b + 16 * t2;
-        const double pc = p[col];
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          const int row = a + 32 * s;
-          if (row >= col || row <= j) v[s][t2] = fma(-pr[s], pc, v[s][t2]);
-        }
+        if (t2 == t && b <= jb + 1) continue;              // columns <= j, and column j+1 (done by its owner above)
+        if (t2 == t + 1 && jb == 15 && b == 0) continue;   // column j+1 when it starts the next slot
+        GPX_APPLY(t2, j);
       }
+      __syncthreads();
     }
   }
+#undef GPX_APPLY
+#undef GPX_MAKE_P
   __syncthreads();
   // outputs
 #pragma unroll
@@ -265,15 +281,18 @@ int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp
 // Replaces lapack.dpotrs (GPy/util/linalg.py:116-125; exact_gaussian_inference.py:60).
 // =================================================================================================================
 __global__ void __launch_bounds__(256) utv_kernel(const double* __restrict__ U, long ld, long n, int P,
-                                                  const double* __restrict__ Y /*[P][ld]*/, double* __restrict__ T) {
+                                                  const double* __restrict__ Y /*[P][ld]*/, double* __restrict__ T,
+                                                  int own_G, int own_g, long own_cols) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long col = (long)blockIdx.x * 8 + warp;
   if (col >= n) return;
+  if (own_G > 1 && ((col / own_cols) % own_G) != own_g) return;   // column block owned by another rank
   const long kend = (col / TILE + 1) * TILE;  // zeros below the diagonal inside the diagonal tile
   const double* u = U + col * ld;
   double acc[MAX_P];
 #pragma unroll
   for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+#pragma unroll 4
   for (long k = lane; k < kend; k += 32) {
     const double x = u[k];
 #pragma unroll
@@ -300,6 +319,7 @@ __global__ void __launch_bounds__(TILE) uv_partial_kernel(const double* __restri
   double acc[MAX_P];
 #pragma unroll
   for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+#pragma unroll 8
   for (long k = kb; k < ke; k++) {
     const double x = U[row + k * ld];
 #pragma unroll
@@ -320,8 +340,99 @@ __global__ void uv_reduce_kernel(const double* __restrict__ part, long ld, int P
   out[q * ld + row] = s;
 }
 
-int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st) {
-  utv_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(U, ld, n, P, Y, T);
+// multi-GPU: a = U t restricted to the column blocks this rank owns; one partial per (row tile, column block)
+__global__ void __launch_bounds__(TILE) uv_partial_blk_kernel(const double* __restrict__ U, long ld, long n, int P,
+                                                              const double* __restrict__ T, long blk, int G, int g,
+                                                              double* __restrict__ part /*[nblk][P][ld]*/) {
+  const long row = (long)blockIdx.x * TILE + threadIdx.x;
+  const long kb = blockIdx.y;
+  double acc[MAX_P];
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+  const long k0 = kb * blk, k1 = k0 + blk;
+  if ((kb % G) == g && k1 > (long)blockIdx.x * TILE) {   // U(row, k) = 0 for k before the row's tile start
+    const long kbeg = k0 > (long)blockIdx.x * TILE ? k0 : (long)blockIdx.x * TILE;
+#pragma unroll 8
+    for (long k = kbeg; k < k1; k++) {
+      const double x = U[row + k * ld];
+#pragma unroll
+      for (int q = 0; q < MAX_P; q++)
+        if (q < P) acc[q] = fma(x, T[(long)q * ld + k], acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++)
+    if (q < P) part[((long)kb * P + q) * ld + row] = acc[q];
+}
+
+int launch_uv_blk(const double* U, long ld, long n, int P, const double* T, long blk, int G, int g, double* part,
+                  double* out, cudaStream_t st) {
+  const int nblk = (int)(n / blk);
+  dim3 grid((unsigned)(n / TILE), nblk);
+  uv_partial_blk_kernel<<<grid, TILE, 0, st>>>(U, ld, n, P, T, blk, G, g, part);
+  GPX_CUDA(cudaGetLastError());
+  uv_reduce_kernel<<<(unsigned)((ld * P + 255) / 256), 256, 0, st>>>(part, ld, P, nblk, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// multi-GPU: after the all-gather of the panel chunks, write block column k of S from the chunks: rows below the
+// diagonal block that this rank owns (L panel) and, on the rank that owns COLUMN block k, all rows above it (U(:,k)).
+__global__ void copyback_kernel(double* __restrict__ S, long ld, const double* __restrict__ Pbuf, long NB, int nbt,
+                                int G, int g, long npr, int k, int nt) {
+  const int r = blockIdx.y;                 // row tile
+  const int R = r / nbt;
+  if (R == k) return;
+  const bool want = (R > k) ? ((R % G) == g) : ((k % G) == g);
+  if (!want) return;
+  const long pos = (long)(R % G) * npr + R / G;
+  const double* src = Pbuf + pos * NB * NB + (long)(r % nbt) * TILE;
+  double* dst = S + (long)r * TILE + (long)k * NB * ld;
+  const int m = threadIdx.x & (TILE - 1);
+  for (long cc = (long)blockIdx.x * 2 + (threadIdx.x >> 7); cc < NB; cc += (long)gridDim.x * 2)
+    dst[m + cc * ld] = src[m + cc * NB];
+}
+
+int launch_copyback(double* S, long ld, const double* Pbuf, long NB, int G, int g, long npr, int k, int nt,
+                    cudaStream_t st) {
+  dim3 grid(32, nt);
+  copyback_kernel<<<grid, 256, 0, st>>>(S, ld, Pbuf, NB, (int)(NB / TILE), G, g, npr, k, nt);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// multi-GPU finalize: raw local sums only (reduced across ranks by the caller): raw[0..nred) gradient partial sums,
+// raw[nred] = log-determinant of the diagonal tiles this rank factored, raw[nred+1] = |T|^2 (T is already global).
+__global__ void __launch_bounds__(256) finalize_raw_kernel(FinalizeParams f) {
+  __shared__ double sh[256];
+  const int tid = threadIdx.x;
+  const int nred = f.nl + 2;
+  for (int t = 0; t < nred + 2; t++) {
+    double s = 0.0;
+    if (t < nred) {
+      for (long i = tid; i < f.ntiles; i += 256) s += f.partials[i * nred + t];
+    } else if (t == nred) {
+      for (long i = tid; i < f.nt; i += 256) s += f.logdet_part[i];
+    } else {
+      for (int q = 0; q < f.P; q++)
+        for (long i = tid; i < f.N; i += 256) { const double x = f.T[(long)q * f.ld + i]; s = fma(x, x, s); }
+    }
+    sh[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) sh[tid] += sh[tid + o]; __syncthreads(); }
+    if (tid == 0) f.res[t] = sh[0];
+    __syncthreads();
+  }
+}
+int launch_finalize_raw(const FinalizeParams& f, cudaStream_t st) {
+  finalize_raw_kernel<<<1, 256, 0, st>>>(f);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st, int own_G,
+               int own_g, long own_cols) {
+  utv_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(U, ld, n, P, Y, T, own_G, own_g, own_cols);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -13,6 +13,7 @@ struct KBuildParams {
   int sym;                             // 1: factor workspace mode (lower tiles, zero upper tiles, identity padding, +diag_add)
   int same;                            // 1: both operands are the same point set -> exact zero distance on the diagonal
   double diag_add;                     // noise + jitter (sym mode)
+  int own_G, own_g, own_blk;           // multi-GPU: only row tiles with ((rt / own_blk) % own_G) == own_g (0 = all)
   KernParams kp;
 };
 
@@ -38,10 +39,16 @@ int launch_kbuild(const KBuildParams& p, int row_tiles, int col_tiles, cudaStrea
 int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
                 cudaStream_t st);
 int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp, double* Tm, cudaStream_t st);
-int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st);
+int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st, int own_G = 0,
+               int own_g = 0, long own_cols = 1);
 int launch_uv(const double* U, long ld, long n, int P, const double* T, int ksplit, double* part, double* out,
               cudaStream_t st);
 int launch_finalize(const FinalizeParams& f, cudaStream_t st);
+int launch_finalize_raw(const FinalizeParams& f, cudaStream_t st);
+int launch_uv_blk(const double* U, long ld, long n, int P, const double* T, long blk, int G, int g, double* part,
+                  double* out, cudaStream_t st);
+int launch_copyback(double* S, long ld, const double* Pbuf, long NB, int G, int g, long npr, int k, int nt,
+                    cudaStream_t st);
 int launch_extract(int which, const double* S, long ld, const double* Ldiag, const double* Kinv, const double* alpha,
                    int P, long N, double* out, cudaStream_t st);
 int launch_transpose_pad(const double* in, long n, int p, long ld, double* out, cudaStream_t st);
