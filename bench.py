@@ -207,6 +207,11 @@ def run_ours(args):
 
     X, Y = synthetic(N, D)
     eng = _ffi.Engine(local)
+    sharded = use_dist and args.mode == "sharded"
+    if sharded:
+        # ONE evaluation spread over all GPUs: block rows dealt block-cyclically, NCCL panel all-gathers (gpx_dist.cu)
+        from gpy_b200 import dist as gdist
+        gdist.init_engine_comm(eng)
     eng.set_data(X, Y)
 
     # ---- device-resident throughput ------------------------------------------------------------------------------
@@ -236,8 +241,8 @@ def run_ours(args):
     if use_dist:
         dist.all_reduce(t_dev_t, op=dist.ReduceOp.MAX)
     t_dev, wall = float(t_dev_t[0]), float(t_dev_t[1])
-    # N>1 (until the sharded factorisation lands in bench): independent replicas, one evaluation stream per GPU
-    value = world * args.steps / t_dev
+    # sharded: all ranks work on the same evaluation (strong scaling); replicas: one independent stream per GPU
+    value = (1 if sharded or world == 1 else world) * args.steps / t_dev
 
     # ---- end to end through the plugin API with host buffers --------------------------------------------------------
     m = gpy_b200.GPRegression(X, Y, gpy_b200.RBF(D, ARD=True), noise_var=0.01, device=local, engine=eng)
@@ -258,7 +263,7 @@ def run_ours(args):
     e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if use_dist:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / float(e2e_t[0])
+    e2e_value = (1 if sharded or world == 1 else world) * e2e_steps / float(e2e_t[0])
 
     if rank == 0:
         peak = eng.measure_fp64_peak()
@@ -279,10 +284,13 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if (world > 1 and not sharded) else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": "GPRegression RBF ARD N=%d D=%d fp64 (BASELINE.json configs[1])" % (N, D),
                        "theta": "theta_bench (variance 1, lengthscale sqrt(D), noise 0.01) +-5% per step",
-                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
+                       "parallelism": "1 GPU" if world == 1 else (
+                           "%d GPUs, one evaluation sharded by block rows (block-cyclic), NCCL panel broadcast + all-gather"
+                           % world if sharded else "%d independent replicas" % world),
                        "l2": "inputs larger than L2: the %.1f GiB workspace is rebuilt and streamed every step"
                              % (N * N * 8 / 2**30),
                        "timing": "CUDA events on the launching stream around each evaluation, max over ranks"},
@@ -318,6 +326,8 @@ def main():
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--d", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
+                    help="N>1: shard ONE evaluation over the GPUs (default) or run independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,7 +16,8 @@ constexpr int KSLAB = 16;        // k-depth of one smem pipeline stage
 constexpr int PITCH = 132;       // smem row pitch in doubles (== 4 mod 16 -> conflict-free DMMA fragment loads)
 constexpr int STAGES = 4;
 constexpr int CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int PRODUCER_WARPS = 4;   // one full warpgroup (setmaxnreg is warpgroup-wide); only its first warp works
+constexpr int GEMM_THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
 constexpr int MAX_D = 64;        // fused gradient epilogue limit on the input dimension
 constexpr int MAX_P = 8;         // fused path limit on the number of output columns
 

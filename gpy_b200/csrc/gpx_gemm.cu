@@ -130,8 +130,11 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   }
   __syncthreads();
 
-  if (warp == CONSUMER_WARPS) {
-    // ================= producer warp: one bulk copy per lane per stage (16 A columns + 16 B columns) =========
+  if (warp >= CONSUMER_WARPS) {
+    // ================= producer warpgroup: hands its registers to the consumers, then warp 8 streams the slabs ====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp != CONSUMER_WARPS) return;
+    // one bulk copy per lane per stage (16 A columns + 16 B columns)
     const bool isA = lane < KSLAB;
     const int kc = lane & (KSLAB - 1);
     const double* src_base = isA ? Aptr : Bptr;
@@ -149,7 +152,8 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
     return;
   }
 
-  // ================= consumer warps ==========================================================================
+  // ================= consumer warps (two warpgroups, 232 registers each after the hand-over) =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps -> 64 x 32 sub-tiles
   const int g = lane >> 2, tg = lane & 3;
   double acc[8][4][2];

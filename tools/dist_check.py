@@ -1,0 +1,38 @@
+"""torchrun --nproc-per-node G tools/dist_check.py [sizes] : distributed evaluation vs oracle (small N) and timing."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from gpy_b200 import _ffi
+from gpy_b200 import dist as gdist
+from oracle import gpy_oracle as o
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = _ffi.Engine(local)
+    gdist.init_engine_comm(eng)
+    sizes = [int(s) for s in sys.argv[1].split(",")] if len(sys.argv) > 1 else [700, 2048, 3000]
+    for N in sizes:
+        for (kind, ARD, D) in [("rbf", True, 8), ("matern52", False, 3)]:
+            X, Y = o.synthetic(N, D, seed=N)
+            var, ls, noise = 1.2, (np.sqrt(D) * np.linspace(0.8, 1.3, D) if ARD else 1.7), 0.02
+            eng.set_data(X, Y)
+            lml, g, jit = eng.exact_eval(kind, ARD, var, ls, noise)
+            t0 = time.time(); lml, g, jit = eng.exact_eval(kind, ARD, var, ls, noise); dt = time.time() - t0
+            if N <= 6000:
+                l0, g0, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, noise)
+                al = eng.get("alpha")
+                msg = "lml abs %.2e grad rel %.2e alpha rel %.2e" % (abs(lml - l0), np.max(np.abs(g - g0) / np.abs(g0)),
+                                                                    np.max(np.abs(al - res["alpha"])) / np.max(np.abs(res["alpha"])))
+            else:
+                msg = "lml %.6f" % lml
+            if rank == 0:
+                print("G=%d N=%6d %-9s ARD=%d  %s  wall %.1f ms (%.2f evals/s)" % (world, N, kind, ARD, msg, dt * 1e3, 1 / dt), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+if __name__ == "__main__":
+    main()
