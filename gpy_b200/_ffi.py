@@ -42,6 +42,7 @@ EXPORTS = {
     "gpx_kern_Kdiag": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int64, _dp]),
     "gpx_kern_grad_full": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64,
                                           _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp]),
+    "gpx_pdinv": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp, _dp, _dp]),
     "gpx_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(GpxStats)]),
     "gpx_total_launches": (ctypes.c_int64, [_vp]),
     "gpx_measure_fp64_peak": (ctypes.c_int, [_vp, _dp]),
@@ -193,6 +194,29 @@ def kern_Kdiag(kind, variance, N):
     out = np.empty(N)
     check(lib().gpx_kern_Kdiag(KIND[kind], float(variance), N, _ptr(out)), "gpx_kern_Kdiag")
     return out
+
+
+def pdinv(A, maxtries=5, want=("Ai", "L", "Li"), engine=None):
+    """GPy.util.linalg.pdinv (linalg.py:193-214) on the device: -> (Ai, L, Li, logdet) (entries not in `want` are None)
+    plus the jitter the jitchol ladder (linalg.py:56-75) had to add. Raises numpy.linalg.LinAlgError like the reference."""
+    A = _f64(A)
+    N = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != N:
+        raise ValueError("A must be square")
+    outs = {k: (np.empty((N, N), order="F") if k in want else None) for k in ("Ai", "L", "Li")}
+    logdet, jit = ctypes.c_double(), ctypes.c_double()
+    h = engine._h if engine is not None else None
+    rc = lib().gpx_pdinv(h, _ptr(np.ascontiguousarray(A)), N, int(maxtries), _ptr(outs["Ai"]), _ptr(outs["L"]), _ptr(outs["Li"]),
+                         ctypes.byref(logdet), ctypes.byref(jit))
+    if rc > 0:
+        raise np.linalg.LinAlgError(lib().gpx_last_error().decode())
+    check(rc, "gpx_pdinv")
+    return outs["Ai"], outs["L"], outs["Li"], logdet.value, jit.value
+
+
+def jitchol(A, maxtries=5, engine=None):
+    """GPy.util.linalg.jitchol (linalg.py:56-75) on the device: lower Cholesky factor, jitter ladder included."""
+    return pdinv(A, maxtries, want=("L",), engine=engine)[1]
 
 
 def kern_grad_full(kind, ARD, variance, lengthscale, X, dL_dK, X2=None):

@@ -677,6 +677,94 @@ int gpx_kern_grad_full(gpx_ctx* c, int kind, int ard, double variance, const dou
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// stand-alone pdinv / jitchol for a caller-supplied symmetric matrix (GPy/util/linalg.py:56-75,193-214)
+// ---------------------------------------------------------------------------------------------------------------
+int gpx_pdinv(gpx_ctx* c, const double* A, int64_t N, int max_tries, double* Ai, double* L, double* Li, double* logdet,
+              double* jitter_used) {
+  if (!A || !logdet) GPX_FAIL("null argument");
+  if (!c) GPX_CHECK(scratch_ctx(&c));
+  if (c->dist) GPX_FAIL("gpx_pdinv is single-GPU");
+  if (N < 1) GPX_FAIL("N must be positive");
+  GPX_CUDA(cudaSetDevice(c->device));
+  // jitchol's diagonal rules need the diagonal of A on the host (N doubles)
+  double dsum = 0.0;
+  bool nonpos = false;
+  for (int64_t i = 0; i < N; i++) { const double d = A[i + i * N]; dsum += d; if (!(d > 0.0)) nonpos = true; }
+  // (re)use the context workspace: allocate like gpx_set_data with a dummy 1-D data set if the shape differs
+  {
+    std::vector<double> zx((size_t)N, 0.0);
+    if (c->N != N || c->D != 1 || c->P != 1 || !c->S) GPX_CHECK(gpx_set_data(c, zx.data(), N, 1, zx.data(), 1));
+  }
+  c->have_eval = false;
+  c->have_kinv = false;
+  cudaStream_t st = c->st;
+  const long ld = c->Npad;
+  GPX_CHECK(ensure_staging(c));
+  GPX_CUDA(cudaMemcpyAsync(c->staging, A, (size_t)N * N * 8, cudaMemcpyHostToDevice, st));
+  Recorder rec{c};
+  double extra = 0.0;
+  int tries = 0, info = 0;
+  const int64_t l0 = c->eval_launches;
+  for (;;) {
+    tries++;
+    GPX_CUDA(cudaMemsetAsync(c->info, 0, sizeof(int), st));
+    if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)ld * ld * 8));
+    GPX_CHECK(launch_load_sym(c->staging, N, c->S, ld, extra, st));
+    c->eval_launches++;
+    GPX_CHECK(run_sweep(c, rec));
+    GPX_CUDA(cudaMemcpyAsync(c->h_info, c->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+    info = *c->h_info;
+    if (info == 0) break;
+    if (nonpos) { gpx::set_error("not pd: non-positive diagonal elements"); c->total_launches += c->eval_launches - l0; return info; }
+    if (tries > max_tries) break;
+    extra = dsum / (double)N * 1e-6 * pow(10.0, tries - 1);     // linalg.py:66-72
+    if (!std::isfinite(extra)) break;
+  }
+  if (jitter_used) *jitter_used = extra;
+  if (info != 0) { gpx::set_error("not positive definite, even with jitter."); c->total_launches += c->eval_launches - l0; return info; }
+  // logdet = 2 sum log diag(L) (linalg.py:208): per-tile partials -> host sum in fixed order
+  {
+    const int nt = (int)(ld / TILE);
+    std::vector<double> parts(nt);
+    GPX_CUDA(cudaMemcpyAsync(parts.data(), c->logdet_part, (size_t)nt * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+    double s = 0.0;
+    for (int i = 0; i < nt; i++) s += parts[i];
+    *logdet = s;
+  }
+  if (Ai) {
+    const long ntl = ld / TILE;
+    GemmParams pl = gemm_defaults();
+    pl.mode = GEMM_LAUUM;
+    pl.A = c->S; pl.lda = ld; pl.B = c->S; pl.ldb = ld; pl.ldc = ld;
+    pl.K = (int)ld; pl.nt = (int)ntl; pl.N = (int)N; pl.P = 1;
+    pl.partials = nullptr; pl.kinv_out = c->Kinv;
+    pl.kp.D = 1;
+    GPX_CHECK(launch_gemm(pl, dim3(1, 1), st));
+    c->eval_launches++;
+    GPX_CHECK(launch_extract(GPX_GET_KINV, c->S, ld, c->Ldiag, c->Kinv, nullptr, 0, N, c->staging, st));
+    c->eval_launches++;
+    GPX_CUDA(cudaMemcpyAsync(Ai, c->staging, (size_t)N * N * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+  }
+  if (L) {
+    GPX_CHECK(launch_extract(GPX_GET_L, c->S, ld, c->Ldiag, nullptr, nullptr, 0, N, c->staging, st));
+    c->eval_launches++;
+    GPX_CUDA(cudaMemcpyAsync(L, c->staging, (size_t)N * N * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+  }
+  if (Li) {
+    GPX_CHECK(launch_extract(GPX_GET_LINV, c->S, ld, c->Ldiag, nullptr, nullptr, 0, N, c->staging, st));
+    c->eval_launches++;
+    GPX_CUDA(cudaMemcpyAsync(Li, c->staging, (size_t)N * N * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+  }
+  c->total_launches += c->eval_launches - l0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // prediction with the factor of the last evaluation (posterior.py:273-302)
 // ---------------------------------------------------------------------------------------------------------------
 int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double* mu, double* var) {

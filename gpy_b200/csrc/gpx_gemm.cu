@@ -218,6 +218,17 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   // work runs as a ROLLED loop: unrolled over the 64 accumulators it was ~160 KB of straight-line code per tile and
   // the kernel stalled on instruction fetch (ncu: stalled_no_instruction ~1.1 per issue, DMMA pipe 83 % vs 93 %).
   decode_tile<MODE>(p, r, c);   // recomputed here so that r, c are not live across the main loop
+  if (p.partials == nullptr) {   // plain K^-1 = U U^T (gpx_pdinv): store the lower tile, no reductions
+    double* ko = p.kinv_out + (long)r * TILE + (long)c * TILE * p.ldc;
+#pragma unroll
+    for (int mb = 0; mb < 8; mb++)
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          ko[wm * 64 + mb * 8 + g + (long)(wn * 32 + nb * 8 + 2 * tg + e) * p.ldc] = acc[mb][nb][e];
+    return;
+  }
   const int D = p.kp.D, P = p.P;
   const int nl = p.kp.ard ? D : 1;
   const int nred = nl + 2;
@@ -246,6 +257,7 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   if (tid < TILE) { sSr[tid] = p.sq[(long)r * TILE + tid]; sSc[tid] = p.sq[(long)c * TILE + tid]; }
 
   const double w = (r > c) ? 2.0 : 1.0;   // strictly-lower tiles stand for their mirror image as well
+  const bool alpha_here = p.k_G <= 1 || p.k_g == 0;
   const int kind = p.kp.kind;
   const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
   const bool ard = p.kp.ard != 0;
@@ -283,7 +295,8 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
         double k, dk;
         k_dk_of_r_unit(kind, rr, k, dk);
         double aa = 0.0;
-        for (int q = 0; q < P; q++) aa = fma(sAr[q * TILE + il], sAc[q * TILE + jl], aa);
+        if (alpha_here)   // multi-GPU: K^-1 is summed over the ranks' k-ranges, the alpha alpha^T term counts once
+          for (int q = 0; q < P; q++) aa = fma(sAr[q * TILE + il], sAc[q * TILE + jl], aa);
         double dl = 0.5 * (aa - (double)P * kinv);
         if (gi >= p.N || gj >= p.N) dl = 0.0;
         gvar = fma(w * k, dl, gvar);

@@ -543,6 +543,25 @@ int launch_extract(int which, const double* S, long ld, const double* Ldiag, con
   return 0;
 }
 
+// gpx_pdinv: dense symmetric A (N x N, ld = N) -> factor workspace (lower tiles + jitter on the diagonal, zero upper
+// tiles, identity padding), and the mean of its diagonal / any non-positive diagonal entry for the jitchol rules.
+__global__ void load_sym_kernel(const double* __restrict__ A, long N, double* __restrict__ S, long ld, double jitter) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long j = blockIdx.y;
+  if (i >= ld) return;
+  double v;
+  if (i >= N || j >= N) v = (i == j) ? 1.0 : 0.0;
+  else if (i / TILE < j / TILE) v = 0.0;
+  else v = A[i + j * N] + ((i == j) ? jitter : 0.0);
+  S[i + j * ld] = v;
+}
+int launch_load_sym(const double* A, long N, double* S, long ld, double jitter, cudaStream_t st) {
+  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)ld);
+  load_sym_kernel<<<grid, 256, 0, st>>>(A, N, S, ld, jitter);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // transpose helpers for host layouts: in [rows][ld_in] (row index slow) -> out[cols... ] generic small kernels
 __global__ void transpose_pad_kernel(const double* __restrict__ in, long n, int p, long ld, double* __restrict__ out) {
   // in: n x p row-major (host Y layout) -> out: [p][ld] (SoA), zero padded

@@ -127,15 +127,11 @@ class ExactGaussianInference(object):
 
     def inference(self, kern, X, likelihood, Y, mean_function=None, Y_metadata=None, K=None, variance=None,
                   Z_tilde=None):
-        if mean_function is not None:
-            raise NotImplementedError("mean functions are outside the accelerated hot path (SURVEY.md §8f)")
-        if K is not None:
-            raise NotImplementedError("precomputed K is outside the accelerated hot path (SURVEY.md §8f)")
-        if not isinstance(kern, Stationary):
-            raise TypeError("gpy_b200.ExactGaussianInference accelerates gpy_b200.kern stationary kernels only")
         if variance is None:
             variance = likelihood.gaussian_variance(Y_metadata)
         noise = float(np.squeeze(np.asarray(variance)))
+        if mean_function is not None or K is not None or not isinstance(kern, Stationary):
+            return self._generic_inference(kern, X, Y, noise, mean_function, K, Z_tilde)
         Xs = kern._slice_X(X)
         Y = np.ascontiguousarray(Y, dtype=np.float64)
         self._bind(Xs, Y)
@@ -149,6 +145,44 @@ class ExactGaussianInference(object):
         dL_dK = DeviceGradient(self.engine, kern._state_key(), grad[0], grad[1:-1], N)
         grad_dict = {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
         return post, lml, grad_dict
+
+
+    def _generic_inference(self, kern, X, Y, noise, mean_function, K, Z_tilde):
+        """exact_gaussian_inference.py:37-74 for the cases the fused call does not cover (mean function, precomputed K,
+        foreign kernel): the N^3 part (jitchol + dpotri, util/linalg.py:193-214) still runs on the device through
+        gpx_pdinv; the O(N^2 P) remainder is NumPy on the host because K arrives as / has to be returned as ndarrays."""
+        m = 0 if mean_function is None else mean_function.f(X)
+        YYT_factor = np.asarray(Y, dtype=np.float64) - m
+        if K is None:
+            K = kern.K(X)
+        Ky = np.array(K, dtype=np.float64, copy=True)
+        Ky[np.diag_indices_from(Ky)] += noise + 1e-8
+        Wi, LW, _, W_logdet, _ = _ffi.pdinv(Ky, maxtries=5, want=("Ai", "L"), engine=self.engine)
+        alpha = np.dot(Wi, YYT_factor)
+        log_marginal = 0.5 * (-YYT_factor.size * np.log(2 * np.pi) - YYT_factor.shape[1] * W_logdet
+                              - np.sum(alpha * YYT_factor))
+        if Z_tilde is not None:
+            log_marginal += Z_tilde
+        dL_dK = 0.5 * (np.dot(alpha, alpha.T) - YYT_factor.shape[1] * Wi)
+        self._data_key = None   # the context workspace was re-used
+        return (HostPosterior(LW, alpha, K), float(log_marginal),
+                {"dL_dK": dL_dK, "dL_dthetaL": float(np.trace(dL_dK)), "dL_dm": alpha})
+
+
+class HostPosterior(object):
+    """posterior.py:21-77,273-302 with host arrays (generic inference path)."""
+
+    def __init__(self, woodbury_chol, woodbury_vector, K):
+        self.woodbury_chol, self.woodbury_vector, self.K = woodbury_chol, woodbury_vector, K
+
+    def _raw_predict(self, kern, Xnew, pred_var, full_cov=False):
+        from scipy.linalg import solve_triangular
+        Kx = kern.K(pred_var, Xnew)
+        mu = np.dot(Kx.T, self.woodbury_vector)
+        tmp = solve_triangular(self.woodbury_chol, Kx, lower=True)
+        if full_cov:
+            return mu, kern.K(Xnew) - np.dot(tmp.T, tmp)
+        return mu, (kern.Kdiag(Xnew) - np.square(tmp).sum(0))[:, None]
 
 
 class _LazyAlpha(object):

@@ -18,8 +18,10 @@ from .param import Logexp, Parameterized
 
 
 class GP(Parameterized):
-    def __init__(self, X, Y, kernel, likelihood, inference_method=None, name="gp", device=0, engine=None):
+    def __init__(self, X, Y, kernel, likelihood, mean_function=None, inference_method=None, name="gp", device=0,
+                 engine=None):
         super(GP, self).__init__(name)
+        self.mean_function = mean_function
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
         assert X.ndim == 2
@@ -43,7 +45,7 @@ class GP(Parameterized):
     # ---- one evaluation: gp.py:269-282 -------------------------------------------------------------------------
     def parameters_changed(self):
         self.posterior, self._log_marginal_likelihood, self.grad_dict = self.inference_method.inference(
-            self.kern, self.X, self.likelihood, self.Y, None, None)
+            self.kern, self.X, self.likelihood, self.Y, self.mean_function, None)
         self.likelihood.update_gradients(self.grad_dict["dL_dthetaL"])
         self.kern.update_gradients_full(self.grad_dict["dL_dK"], self.X)
 
@@ -166,8 +168,11 @@ class GP(Parameterized):
 
     # ---- prediction: gp.py:290-365 --------------------------------------------------------------------------------
     def _raw_predict(self, Xnew, full_cov=False, kern=None):
-        return self.posterior._raw_predict(kern=self.kern if kern is None else kern, Xnew=Xnew, pred_var=self.X,
-                                           full_cov=full_cov)
+        mu, var = self.posterior._raw_predict(kern=self.kern if kern is None else kern, Xnew=Xnew, pred_var=self.X,
+                                              full_cov=full_cov)
+        if self.mean_function is not None:
+            mu = mu + self.mean_function.f(Xnew)   # gp.py:304-305
+        return mu, var
 
     def predict(self, Xnew, full_cov=False, Y_metadata=None, kern=None, likelihood=None, include_likelihood=True):
         mean, var = self._raw_predict(Xnew, full_cov=full_cov, kern=kern)
@@ -186,9 +191,10 @@ class GPRegression(GP):
 
     def __init__(self, X, Y, kernel=None, Y_metadata=None, normalizer=None, noise_var=1., mean_function=None,
                  device=0, engine=None):
-        if normalizer is not None or mean_function is not None:
-            raise NotImplementedError("normalizer / mean_function are outside the accelerated hot path")
+        if normalizer is not None:
+            raise NotImplementedError("normalizer is outside the accelerated hot path (Y is normalised on the host)")
         if kernel is None:
             kernel = RBF(np.asarray(X).shape[1])  # gp_regression.py:31-32
         likelihood = Gaussian(variance=noise_var)  # gp_regression.py:34
-        super(GPRegression, self).__init__(X, Y, kernel, likelihood, name="GP regression", device=device, engine=engine)
+        super(GPRegression, self).__init__(X, Y, kernel, likelihood, mean_function=mean_function, name="GP regression",
+                                           device=device, engine=engine)

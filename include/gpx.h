@@ -85,6 +85,13 @@ int gpx_kern_grad_full(gpx_ctx* ctx, int kind, int ard, double variance, const d
                        int64_t N, const double* X2, int64_t M, int D, const double* dL_dK, double* dvariance,
                        double* dlengthscale);
 
+/* Replaces pdinv / jitchol for a caller-supplied symmetric positive (semi-)definite matrix A (N x N, dense, symmetric so
+ * row- and column-major coincide): GPy/util/linalg.py:193-214 (pdinv -> Ai, L, Li, logdet) and :56-75 (jitchol: first a
+ * plain factorisation; on failure LinAlgError if any diagonal entry is <= 0, else jitter mean(diag)*1e-6*10^k, k <
+ * max_tries). Ai / L / Li may be NULL (not wanted); L, Li are lower, column-major; returns >0 when not PD. */
+int gpx_pdinv(gpx_ctx* ctx, const double* A, int64_t N, int max_tries, double* Ai, double* L, double* Li, double* logdet,
+              double* jitter_used);
+
 /* Measurement hooks (bench.py): device time of the last eval between CUDA events on the launching stream, the number
  * of kernels this library launched since creation, and per-phase accounting of the last eval. */
 typedef struct {

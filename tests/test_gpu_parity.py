@@ -210,3 +210,59 @@ def test_full_size_properties():
     assert abs(lml_p - lml) <= 1e-7
     np.testing.assert_allclose(g_p, g, rtol=1e-8)
     e.close()
+
+
+def test_pdinv_and_jitchol_on_device():
+    """GPy/util/linalg.py:56-75,193-214 as stand-alone device calls (gpx_pdinv); same fixture as
+    GPy/testing/test_linalg.py:8-37: the corrupted matrix needs exactly five rounds of jitter."""
+    from test_oracle import _corrupt
+    A = _corrupt(0)
+    L = _ffi.jitchol(A, maxtries=5)
+    diff = L.dot(L.T) - A
+    np.testing.assert_allclose(diff, np.eye(20) * np.diag(diff).mean(), atol=1e-12)
+    L0, jit0 = o.jitchol(A, maxtries=5)
+    np.testing.assert_allclose(np.diag(diff).mean(), jit0, rtol=1e-6)
+    with pytest.raises(np.linalg.LinAlgError):
+        _ffi.jitchol(A, maxtries=4)
+    Aneg = A.copy()
+    Aneg[3, 3] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        _ffi.jitchol(Aneg)
+    rng = np.random.default_rng(1)
+    for n in (5, 128, 300, 1111):
+        B = rng.standard_normal((n, n + 10))
+        S = B.dot(B.T) + n * np.eye(n)
+        Ai, L, Li, logdet, jit = _ffi.pdinv(S)
+        Ai0, L0, Li0, logdet0 = o.pdinv(S)
+        assert jit == 0.0 and abs(logdet - logdet0) < 1e-9 * abs(logdet0)
+        assert rel(L, L0) < 1e-12 and rel(Li, Li0) < 1e-11 and rel(Ai, Ai0) < 1e-11
+
+
+def test_inference_generic_path_mean_function_and_precomputed_K():
+    """exact_gaussian_inference.py:42-53: mean_function and K= arguments (off the fused path, still on the device for
+    the N^3 part)."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-3, 3, (150, 2))
+    Y = np.sin(X[:, :1]) + 0.3 * X[:, 1:] + 0.05 * rng.standard_normal((150, 1))
+
+    class LinMean(object):
+        def f(self, X):
+            return 0.3 * X[:, 1:2]
+
+    k = gpy_b200.RBF(2, variance=1.2, lengthscale=[1.0, 2.0], ARD=True)
+    lik = gpy_b200.Gaussian(variance=0.05)
+    inf = gpy_b200.ExactGaussianInference()
+    post, lml, gd = inf.inference(k, X, lik, Y, mean_function=LinMean())
+    ko = o.StationaryOracle("rbf", 2, 1.2, [1.0, 2.0], True)
+    res = o.exact_inference(ko, X, Y - 0.3 * X[:, 1:2], 0.05)
+    assert abs(lml - res["log_marginal"]) < 1e-8
+    assert rel(gd["dL_dK"], res["dL_dK"]) < 1e-9 and rel(gd["dL_dm"], res["alpha"]) < 1e-9
+    post2, lml2, gd2 = inf.inference(k, X, lik, Y, K=ko.K(X))
+    res2 = o.exact_inference(ko, X, Y, 0.05)
+    assert abs(lml2 - res2["log_marginal"]) < 1e-8 and rel(post2.woodbury_chol, res2["L"]) < 1e-11
+    m = gpy_b200.GPRegression(X, Y, k, noise_var=0.05, mean_function=LinMean())
+    assert abs(m.log_likelihood() - res["log_marginal"]) < 1e-8
+    mu, var = m.predict(X[:4])
+    mu0, var0 = o.predict(ko, X, res["L"], res["alpha"], X[:4], 0.05)
+    np.testing.assert_allclose(mu, mu0 + 0.3 * X[:4, 1:2], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(var, var0, rtol=1e-7, atol=1e-9)
