@@ -300,13 +300,15 @@ def run_ours(args):
                     "d2h_bytes_per_step": int((nl + 3) * 8), "steps": e2e_steps,
                     "api": "gpy_b200.GPRegression.set_XY/set_theta -> log_likelihood(), gradient (host ndarrays in/out)"},
             "roofline": {"bound": "tensor", "kernel": "gemm_update_kernel (fp64 DMMA trailing update)",
-                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                         "achieved": ach if upd_ms > 0 else None, "peak": peak, "unit": "TFLOP/s",
+                         "frac": ach / peak if (peak and upd_ms > 0) else None,
+                         "note": None if upd_ms > 0 else "per-kernel event accounting is single-GPU; see whole_eval_*",
                          "peak_source": "fp64 DMMA.8x8x4 issue rate measured in this run (gpx_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json holds no fp64 entry",
                          "launches": None, "traffic": None,
                          "share_of_step": upd_ms / (t_dev * 1e3) if t_dev else None,
                          "whole_eval_tflops": float(N) ** 3 * args.steps / t_dev * 1e-12,
-                         "whole_eval_frac": float(N) ** 3 * args.steps / t_dev * 1e-12 / peak if peak else None,
+                         "whole_eval_frac": float(N) ** 3 * args.steps / t_dev * 1e-12 / (peak * (world if sharded else 1)) if peak else None,
                          "lauum_tflops": lau_flops / lau_ms * 1e-9 if lau_ms else None,
                          "kbuild_gbs": kb_bytes / kb_ms * 1e-6 if kb_ms else None},
             "cpu_baseline": cpu,
