@@ -42,6 +42,8 @@ EXPORTS = {
     "gpx_kern_Kdiag": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int64, _dp]),
     "gpx_kern_grad_full": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64,
                                           _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp]),
+    "gpx_kern_grad_X": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64, _dp,
+                                       ctypes.c_int64, ctypes.c_int, _dp, _dp]),
     "gpx_pdinv": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp, _dp, _dp]),
     "gpx_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(GpxStats)]),
     "gpx_total_launches": (ctypes.c_int64, [_vp]),
@@ -161,6 +163,17 @@ class Engine(object):
         check(self._L.gpx_predict(self._h, _ptr(Xnew), M, int(full_cov), _ptr(mu), _ptr(var)), "gpx_predict")
         return mu, (var if full_cov else var[:, None])
 
+    def kern_K_device_only(self, kind, ARD, variance, lengthscale, X, X2=None):
+        """build K(X, X2) on the device without bringing it back; -> (kernel ms, algorithmic GB/s)."""
+        X = _f64(X)
+        N, D = X.shape
+        k, a, ls = _theta(kind, ARD, lengthscale, D)
+        X2c = None if X2 is None else _f64(X2)
+        M = N if X2 is None else X2c.shape[0]
+        check(self._L.gpx_kern_K(self._h, k, a, float(variance), _ptr(ls), _ptr(X), N, _ptr(X2c), M, D, None), "gpx_kern_K")
+        st = self.stats()
+        return st["kbuild_ms"], st["kbuild_bytes"] / st["kbuild_ms"] * 1e-6
+
     def stats(self):
         s = GpxStats()
         check(self._L.gpx_get_stats(self._h, ctypes.byref(s)), "gpx_get_stats")
@@ -193,6 +206,22 @@ def kern_K(kind, ARD, variance, lengthscale, X, X2=None):
 def kern_Kdiag(kind, variance, N):
     out = np.empty(N)
     check(lib().gpx_kern_Kdiag(KIND[kind], float(variance), N, _ptr(out)), "gpx_kern_Kdiag")
+    return out
+
+
+def kern_grad_X(kind, ARD, variance, lengthscale, X, dL_dK, X2=None):
+    """Stationary.gradients_X (stationary.py:245-252) on the device -> N x D."""
+    X = _f64(X)
+    N, D = X.shape
+    k, a, ls = _theta(kind, ARD, lengthscale, D)
+    X2c = None if X2 is None else _f64(X2)
+    M = N if X2 is None else X2c.shape[0]
+    dL_dK = _f64(dL_dK)
+    if dL_dK.shape != (N, M):
+        raise ValueError("dL_dK must be %d x %d" % (N, M))
+    out = np.empty((N, D))
+    check(lib().gpx_kern_grad_X(None, k, a, float(variance), _ptr(ls), _ptr(X), N, _ptr(X2c), M, D, _ptr(dL_dK), _ptr(out)),
+          "gpx_kern_grad_X")
     return out
 
 

@@ -604,7 +604,7 @@ static int upload_points(gpx_ctx* c, const double* X, long n, const KernParams& 
 
 int gpx_kern_K(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* X, int64_t N,
                const double* X2, int64_t M, int D, double* out) {
-  if (!X || !out || !lengthscale) GPX_FAIL("null argument");
+  if (!X || !lengthscale) GPX_FAIL("null argument");
   if (!c) GPX_CHECK(scratch_ctx(&c));
   GPX_CUDA(cudaSetDevice(c->device));
   KernParams kp;
@@ -622,10 +622,22 @@ int gpx_kern_K(gpx_ctx* c, int kind, int ard, double variance, const double* len
   kb.rowsT = pj.xT; kb.ld_rows = pj.ld; kb.sq_rows = pj.sq;
   kb.colsT = p1.xT; kb.ld_cols = p1.ld; kb.sq_cols = p1.sq;
   kb.out = dout; kb.ld = M; kb.nrows = M; kb.ncols = N; kb.sym = 0; kb.same = X2 ? 0 : 1; kb.kp = kp;
-  int rc = launch_kbuild(kb, (int)(pj.ld / TILE), (int)(p1.ld / TILE), c->st);
+  // out == NULL: build on the device only (the result is dropped) and report the kernel time through gpx_get_stats
+  // (kbuild_ms / kbuild_bytes) — used to measure the rectangular K(X, Z) build of the sparse model at full size.
+  cudaEvent_t e0, e1;
+  int rc = ev_get(c, 0, &e0) || ev_get(c, 1, &e1);
+  if (rc == 0) {
+    cudaEventRecord(e0, c->st);
+    rc = launch_kbuild(kb, (int)(pj.ld / TILE), (int)(p1.ld / TILE), c->st);
+    cudaEventRecord(e1, c->st);
+  }
   c->total_launches++;
-  if (rc == 0 && cudaMemcpyAsync(out, dout, (size_t)N * M * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
+  if (rc == 0 && out && cudaMemcpyAsync(out, dout, (size_t)N * M * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
   if (cudaStreamSynchronize(c->st) != cudaSuccess) { gpx::set_error("gpx_kern_K: device failure"); rc = -1; }
+  if (rc == 0) {
+    cudaEventElapsedTime(&c->stats.kbuild_ms, e0, e1);
+    c->stats.kbuild_bytes = 8.0 * (double)N * M + 8.0 * (double)(N + M) * D;
+  }
   cudaFree(dout);
   return rc;
 }
@@ -674,6 +686,41 @@ int gpx_kern_grad_full(gpx_ctx* c, int kind, int ard, double variance, const dou
   *dvariance = tot[0];
   for (int q = 0; q < nl; q++) dlengthscale[q] = -tot[1 + q] / lengthscale[q];
   return 0;
+}
+
+int gpx_kern_grad_X(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* X, int64_t N,
+                    const double* X2, int64_t M, int D, const double* dL_dK, double* grad) {
+  if (!X || !dL_dK || !lengthscale || !grad) GPX_FAIL("null argument");
+  if (!c) GPX_CHECK(scratch_ctx(&c));
+  GPX_CUDA(cudaSetDevice(c->device));
+  KernParams kp;
+  GPX_CHECK(fill_kp(kp, kind, ard, D, variance, lengthscale));
+  if (!X2) M = N;
+  PointSet p1, p2;
+  GPX_CHECK(upload_points(c, X, N, kp, p1));
+  if (X2) GPX_CHECK(upload_points(c, X2, M, kp, p2));
+  PointSet& pj = X2 ? p2 : p1;
+  // m is split into chunks so that ~4 waves of CTAs are in flight; partials are reduced in fixed order
+  const long ntile = (N + TILE - 1) / TILE;
+  int nchunk = (int)std::max<long>(1, std::min<long>((M + 31) / 32, (4 * 148 + ntile - 1) / ntile));
+  const long mchunk = ((M + nchunk - 1) / nchunk + 31) / 32 * 32;
+  nchunk = (int)((M + mchunk - 1) / mchunk);
+  double *dd = nullptr, *dpart = nullptr, *dout = nullptr;
+  GPX_CUDA(cudaMalloc(&dd, (size_t)N * M * 8));
+  GPX_CUDA(cudaMalloc(&dpart, (size_t)nchunk * N * D * 8));
+  GPX_CUDA(cudaMalloc(&dout, (size_t)N * D * 8));
+  GPX_CUDA(cudaMemcpyAsync(dd, dL_dK, (size_t)N * M * 8, cudaMemcpyHostToDevice, c->st));
+  GradFullParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.x1T = p1.xT; gp.ld1 = p1.ld; gp.sq1 = p1.sq; gp.N = N;
+  gp.x2T = pj.xT; gp.ld2 = pj.ld; gp.sq2 = pj.sq; gp.M = M;
+  gp.dL_dK = dd; gp.same = X2 ? 0 : 1; gp.kp = kp;
+  int rc = launch_gradx(gp, nchunk, mchunk, dpart, dout, c->st);
+  c->total_launches += 2;
+  if (rc == 0 && cudaMemcpyAsync(grad, dout, (size_t)N * D * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
+  if (cudaStreamSynchronize(c->st) != cudaSuccess) { gpx::set_error("gpx_kern_grad_X: device failure"); rc = -1; }
+  cudaFree(dd); cudaFree(dpart); cudaFree(dout);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

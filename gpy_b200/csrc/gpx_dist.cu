@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "gpx_common.cuh"
 #include "gpx_ctx.cuh"
@@ -50,6 +51,7 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;   // optional (NCCL >= 2.18)
 };
 NcclApi g_nccl;
 
@@ -75,6 +77,7 @@ int load_nccl() {
   GPX_SYM(AllReduce, "ncclAllReduce")
   GPX_SYM(GetErrorString, "ncclGetErrorString")
 #undef GPX_SYM
+  *(void**)(&g_nccl.CommSplit) = dlsym(g_nccl.handle, "ncclCommSplit");
   return 0;
 }
 }  // namespace
@@ -96,6 +99,9 @@ int load_nccl() {
 
 struct DistState {
   ncclComm_t comm = nullptr;
+  ncclComm_t comm2 = nullptr;  // duplicate communicator for the look-ahead side stream (null: no look-ahead)
+  double* Bc2 = nullptr;       // second broadcast buffer
+  std::vector<cudaEvent_t> ev;
   int rank = 0, G = 1;
   long NB = 0, npr = 0, nblk = 0;
   double* Bc = nullptr;        // NB x NB broadcast buffer (L_kk^-1)
@@ -112,8 +118,9 @@ void dist_free(gpx_ctx* c) {
   if (!c->dist) return;
   DistState* d = c->dist;
   if (d->Bc) cudaFree(d->Bc);
+  if (d->Bc2) cudaFree(d->Bc2);
   if (d->blkpart) cudaFree(d->blkpart);
-  d->Bc = d->blkpart = nullptr;
+  d->Bc = d->Bc2 = d->blkpart = nullptr;
 }
 
 static long dist_pick_nb(const gpx_ctx* c, long N) {
@@ -149,15 +156,16 @@ int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y
     GPX_CUDA(cudaMalloc(&c->dAlpha, (size_t)Npad * P * 8));
     GPX_CUDA(cudaMalloc(&c->dUvPart, (size_t)Npad * P * 8));
     GPX_CUDA(cudaMalloc(&c->S, (size_t)Npad * Npad * 8));
-    GPX_CUDA(cudaMalloc(&c->Pbuf, (size_t)d->G * npr * NB * NB * 8));
+    GPX_CUDA(cudaMalloc(&c->Pbuf, (size_t)2 * d->G * npr * NB * NB * 8));   // double-buffered (look-ahead)
     GPX_CUDA(cudaMalloc(&c->Tm, (size_t)NB * NB * 8));
     GPX_CUDA(cudaMalloc(&d->Bc, (size_t)NB * NB * 8));
+    GPX_CUDA(cudaMalloc(&d->Bc2, (size_t)NB * NB * 8));
     GPX_CUDA(cudaMalloc(&c->Ldiag, (size_t)Npad * TILE * 8));
     GPX_CUDA(cudaMalloc(&c->Dinv, (size_t)Npad * TILE * 8));
     GPX_CUDA(cudaMalloc(&c->logdet_part, (size_t)nt * 8));
     GPX_CUDA(cudaMalloc(&c->partials, (size_t)nt * nt * (MAX_D + 2) * 8));
     GPX_CUDA(cudaMalloc(&d->blkpart, (size_t)nblk * P * Npad * 8));
-    GPX_CUDA(cudaMemsetAsync(c->Pbuf, 0, (size_t)d->G * npr * NB * NB * 8, c->st));
+    GPX_CUDA(cudaMemsetAsync(c->Pbuf, 0, (size_t)2 * d->G * npr * NB * NB * 8, c->st));
   }
   c->N = N;
   c->have_eval = false;
@@ -195,18 +203,43 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
     c->eval_launches++;
   }
   // ---- sweep -----------------------------------------------------------------------------------------------------
+  // Look-ahead (when a second communicator is available): D(k), the broadcast of L_kk^-1, the panel product, the
+  // all-gather and the copy-back of step k run on the high-priority side stream (own NCCL communicator) as soon as
+  // the columns of block k have received update k-1 (U1); the main stream meanwhile finishes U2(k-1).
+  const bool la = c->lookahead && d->comm2 != nullptr && d->nblk > 1;
+  cudaStream_t sm = st, ss = la ? c->st2 : st;
+  ncclComm_t cs = la ? d->comm2 : d->comm;
+  size_t evi = 0;
+  auto next_event = [&](cudaEvent_t* e) -> int {
+    if (d->ev.size() <= evi) {
+      cudaEvent_t x;
+      GPX_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+      d->ev.push_back(x);
+    }
+    *e = d->ev[evi++];
+    return 0;
+  };
+  cudaEvent_t ev;
+  if (la) {
+    GPX_CHECK(next_event(&ev));
+    GPX_CUDA(cudaEventRecord(ev, sm));
+    GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+  }
+  const size_t pstride = (size_t)G * d->npr * NB * NB;
   for (int k = 0; k < (int)d->nblk; k++) {
     const long o = (long)k * NB;
     const int kt0 = k * nbt, kt1 = kt0 + nbt;
     const int root = k % G;
     const long pos_k = (long)(k % G) * d->npr + k / G;
+    double* Pb = c->Pbuf + (size_t)(k & 1) * pstride;
+    double* Bc = (k & 1) ? d->Bc2 : d->Bc;
     if (g == root) {
       double* Sblk = c->S + o + o * ld;
       for (int dd = 0; dd < nbt; dd++) {
         const int gt = kt0 + dd;
         double* tile = Sblk + (long)dd * TILE + (long)dd * TILE * ld;
         GPX_CHECK(launch_base(tile, ld, c->Ldiag + (long)gt * TILE * TILE, c->Dinv + (long)gt * TILE * TILE,
-                              c->logdet_part + gt, c->info, gt * TILE, st));
+                              c->logdet_part + gt, c->info, gt * TILE, ss));
         c->eval_launches++;
         if (nbt > 1) {
           GemmParams pp = gemm_defaults();
@@ -215,53 +248,74 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
           pp.B = c->Dinv + (long)gt * TILE * TILE; pp.ldb = TILE;
           pp.C = Sblk + (long)dd * TILE * ld; pp.ldc = ld;
           pp.K = TILE; pp.nt = nbt; pp.skip0 = dd; pp.skip1 = dd + 1;
-          GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), st));
+          GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), ss));
           c->eval_launches++;
           if (dd + 1 < nbt) {
             GemmParams pu = gemm_defaults();
             pu.mode = GEMM_UPDATE;
             pu.A = Sblk + (long)dd * TILE * ld; pu.lda = ld; pu.B = pu.A; pu.ldb = ld;
             pu.C = Sblk; pu.ldc = ld; pu.K = TILE; pu.nt = nbt; pu.c0 = dd + 1; pu.rlow = dd + 1;
-            GPX_CHECK(launch_gemm(pu, dim3(1, 1), st));
+            GPX_CHECK(launch_gemm(pu, dim3(1, 1), ss));
             c->eval_launches++;
           }
         }
       }
       // U_kk into this rank's chunk of the panel buffer, L_kk^-1 into the broadcast buffer
-      GPX_CHECK(launch_assemble(Sblk, ld, (int)NB, c->Pbuf + pos_k * NB * NB, NB, d->Bc, st));
+      GPX_CHECK(launch_assemble(Sblk, ld, (int)NB, Pb + pos_k * NB * NB, NB, Bc, ss));
       c->eval_launches++;
     }
     if (d->nblk == 1) break;
-    GPX_NCCL(g_nccl.Broadcast(d->Bc, d->Bc, (size_t)NB * NB, ncclDouble, root, d->comm, st));
+    GPX_NCCL(g_nccl.Broadcast(Bc, Bc, (size_t)NB * NB, ncclDouble, root, cs, ss));
     {
       GemmParams pp = gemm_defaults();
       pp.mode = GEMM_PANEL;
       pp.A = c->S + o * ld; pp.lda = ld;
-      pp.B = d->Bc; pp.ldb = NB;
-      pp.C = c->Pbuf; pp.ldc = NB; pp.map_C = 1;
+      pp.B = Bc; pp.ldb = NB;
+      pp.C = Pb; pp.ldc = NB; pp.map_C = 1;
       pp.map_blk = nbt; pp.map_G = G; pp.map_npr = (int)d->npr; pp.map_stride = NB * NB;
       pp.own_G = G; pp.own_g = g; pp.own_blk = nbt;
       pp.K = (int)NB; pp.nt = nt; pp.skip0 = kt0; pp.skip1 = kt1; pp.tri = 1;
-      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), st));
+      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), ss));
       c->eval_launches++;
     }
-    GPX_NCCL(g_nccl.AllGather(c->Pbuf + (size_t)g * d->npr * NB * NB, c->Pbuf, (size_t)d->npr * NB * NB, ncclDouble,
-                              d->comm, st));
-    GPX_CHECK(launch_copyback(c->S, ld, c->Pbuf, NB, G, g, d->npr, k, nt, st));
+    GPX_NCCL(g_nccl.AllGather(Pb + (size_t)g * d->npr * NB * NB, Pb, (size_t)d->npr * NB * NB, ncclDouble, cs, ss));
+    GPX_CHECK(launch_copyback(c->S, ld, Pb, NB, G, g, d->npr, k, nt, ss));
     c->eval_launches++;
-    if (kt1 < nt) {
-      GemmParams pu = gemm_defaults();
-      pu.mode = GEMM_UPDATE;
-      pu.A = c->Pbuf; pu.lda = NB; pu.map_A = 1;
-      pu.B = c->Pbuf; pu.ldb = NB; pu.map_B = 1;
-      pu.map_blk = nbt; pu.map_G = G; pu.map_npr = (int)d->npr; pu.map_stride = NB * NB;
-      pu.own_G = G; pu.own_g = g; pu.own_blk = nbt;
-      pu.C = c->S; pu.ldc = ld;
-      pu.K = (int)NB; pu.nt = nt; pu.c0 = kt1; pu.rlow = kt1;
-      GPX_CHECK(launch_gemm(pu, dim3(1, 1), st));
-      c->eval_launches++;
-      c->stats.update_launches++;
+    if (la) {
+      GPX_CHECK(next_event(&ev));
+      GPX_CUDA(cudaEventRecord(ev, ss));
+      GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
     }
+    if (kt1 < nt) {
+      const int next_nbt = std::min(nbt, nt - kt1);
+      for (int part = 0; part < 2; part++) {
+        const int cbeg = part == 0 ? kt1 : kt1 + next_nbt;
+        const int cend = part == 0 ? kt1 + next_nbt : nt;
+        if (cbeg < cend) {
+          GemmParams pu = gemm_defaults();
+          pu.mode = GEMM_UPDATE;
+          pu.A = Pb; pu.lda = NB; pu.map_A = 1;
+          pu.B = Pb; pu.ldb = NB; pu.map_B = 1;
+          pu.map_blk = nbt; pu.map_G = G; pu.map_npr = (int)d->npr; pu.map_stride = NB * NB;
+          pu.own_G = G; pu.own_g = g; pu.own_blk = nbt;
+          pu.C = c->S; pu.ldc = ld;
+          pu.K = (int)NB; pu.nt = nt; pu.c0 = cbeg; pu.ncols = cend - cbeg; pu.rlow = kt1;
+          GPX_CHECK(launch_gemm(pu, dim3(1, 1), sm));
+          c->eval_launches++;
+          c->stats.update_launches++;
+        }
+        if (part == 0 && la) {
+          GPX_CHECK(next_event(&ev));
+          GPX_CUDA(cudaEventRecord(ev, sm));
+          GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+        }
+      }
+    }
+  }
+  if (la) {
+    GPX_CHECK(next_event(&ev));
+    GPX_CUDA(cudaEventRecord(ev, ss));
+    GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
   }
   // ---- alpha = U (U^T y): owned column blocks, two vector all-reduces ------------------------------------------------
   GPX_CUDA(cudaMemsetAsync(c->dT, 0, (size_t)Npad * c->P * 8, st));
@@ -339,6 +393,9 @@ int gpx_comm_init(gpx_ctx* c, const char id[128], int rank, int nranks) {
   memcpy(uid.internal, id, 128);
   GPX_NCCL(g_nccl.CommInitRank(&d->comm, nranks, uid, rank));
   d->rank = rank; d->G = nranks;
+  if (g_nccl.CommSplit && nranks > 1 && !getenv("GPX_NO_DIST_LOOKAHEAD")) {
+    if (g_nccl.CommSplit(d->comm, 0, rank, &d->comm2, nullptr) != ncclSuccess) d->comm2 = nullptr;
+  }
   GPX_CUDA(cudaMalloc(&d->raw, (MAX_D + 8) * sizeof(double)));
   GPX_CUDA(cudaMallocHost(&d->h_raw, (MAX_D + 8) * sizeof(double)));
   c->Npad = 0;   // force re-allocation in the distributed layout at the next gpx_set_data

@@ -677,6 +677,106 @@ int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStre
 
 
 // =================================================================================================================
+// gradients_X: Stationary.gradients_X (stationary.py:245-252, 348-366 -> stationary_utils.c:1-14 _grad_X):
+//   grad[n,d] = sum_m tmp[n,m] (X[n,d] - X2[m,d]) / l_d^2,  tmp = (1/r) dK_dr dL_dK  (+ its transpose when X2 is None).
+// One CTA = 128 rows n x one m-chunk; dL_dK (N x M row-major) tiles of 128 x 32 go through shared memory so that the
+// global reads are coalesced along m; the points are used in scaled form (x/l), hence the final division by l_d only.
+// Per-chunk partials are reduced in fixed order by gradx_reduce_kernel.
+// =================================================================================================================
+template <int DREG>
+__global__ void __launch_bounds__(TILE) gradx_kernel(GradFullParams p, long mchunk, double* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double (*sdl)[33] = reinterpret_cast<double (*)[33]>(smem_raw);                 // [128][33] dL_dK tile
+  double* sx2 = reinterpret_cast<double*>(smem_raw) + TILE * 33;                    // [D][32] chunk of X2 points (scaled)
+  double* ss2 = sx2 + (size_t)p.kp.D * 32;                // [32]
+  const int D = p.kp.D;
+  const int tid = threadIdx.x;
+  const long n = (long)blockIdx.x * TILE + tid;
+  const long m_beg = (long)blockIdx.y * mchunk;
+  const long m_end = m_beg + mchunk < p.M ? m_beg + mchunk : p.M;
+  double xn[DREG], acc[DREG];
+#pragma unroll
+  for (int q = 0; q < DREG; q++) { xn[q] = (q < D && n < p.N) ? p.x1T[(long)q * p.ld1 + n] : 0.0; acc[q] = 0.0; }
+  const double sn = n < p.N ? p.sq1[n] : 0.0;
+  const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  for (long m0 = m_beg; m0 < m_end; m0 += 32) {
+    __syncthreads();
+    // dL_dK tile rows [n-tile], cols [m0, m0+32): warp w loads rows w, w+4, ... (32 doubles = 256 B per row)
+    for (int rr = tid >> 5; rr < TILE; rr += TILE / 32) {
+      const long gn = (long)blockIdx.x * TILE + rr, gm = m0 + (tid & 31);
+      sdl[rr][tid & 31] = (gn < p.N && gm < m_end) ? p.dL_dK[gn * p.M + gm] : 0.0;
+    }
+    for (int idx = tid; idx < D * 32; idx += TILE) {
+      const int q = idx >> 5, mm = idx & 31;
+      sx2[idx] = (m0 + mm < p.M) ? p.x2T[(long)q * p.ld2 + m0 + mm] : 0.0;
+    }
+    if (tid < 32) ss2[tid] = (m0 + tid < p.M) ? p.sq2[m0 + tid] : 0.0;
+    __syncthreads();
+    if (n < p.N) {
+      const int mlim = (int)((m_end - m0) < 32 ? (m_end - m0) : 32);
+      for (int mm = 0; mm < mlim; mm++) {
+        const long gm = m0 + mm;
+        double dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < DREG; q++)
+          if (q < D) dot = fma(xn[q], sx2[q * 32 + mm], dot);
+        double r2 = sn + ss2[mm] - 2.0 * dot;
+        if (p.same && n == gm) r2 = 0.0;
+        r2 = fmax(r2, 0.0);
+        const double rr = sqrt(r2) * inv_ls;
+        double kk, dk;
+        k_dk_of_r_unit(p.kp.kind, rr, kk, dk);
+        double dl = sdl[tid][mm];
+        if (p.same) dl += p.dL_dK[gm * p.M + n];          // tmp + tmp^T (stationary.py:343-345); coalesced along n
+        const double t = (rr != 0.0) ? variance * dk * dl / rr : 0.0;
+#pragma unroll
+        for (int q = 0; q < DREG; q++)
+          if (q < D) acc[q] = fma(t, xn[q] - sx2[q * 32 + mm], acc[q]);
+      }
+    }
+  }
+  if (n < p.N) {
+#pragma unroll
+    for (int q = 0; q < DREG; q++)
+      if (q < D) part[((long)blockIdx.y * p.N + n) * D + q] = acc[q];
+  }
+}
+
+__global__ void gradx_reduce_kernel(const double* __restrict__ part, long N, int D, int nchunk, KernParams kp,
+                                    double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * D) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunk; c++) s += part[(long)c * N * D + i];
+  const int q = (int)(i % D);
+  // scaled differences: (x - x')/l summed -> divide once more by l (ARD: l_q; iso: the points are unscaled, r carries 1/l)
+  out[i] = kp.ard ? s / kp.ls[q] : s / (kp.ls[0] * kp.ls[0]);
+}
+
+int launch_gradx(const GradFullParams& p, int nchunk, long mchunk, double* part, double* out, cudaStream_t st) {
+  const int D = p.kp.D;
+  const size_t smem = (size_t)(TILE * 33 + D * 32 + 32) * 8;
+  dim3 grid((unsigned)((p.N + TILE - 1) / TILE), nchunk);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int mx = (TILE * 33 + MAX_D * 32 + 32) * 8;
+    GPX_CUDA(cudaFuncSetAttribute(gradx_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    GPX_CUDA(cudaFuncSetAttribute(gradx_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    GPX_CUDA(cudaFuncSetAttribute(gradx_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    GPX_CUDA(cudaFuncSetAttribute(gradx_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    attr_set = true;
+  }
+  if (D <= 8) gradx_kernel<8><<<grid, TILE, smem, st>>>(p, mchunk, part);
+  else if (D <= 16) gradx_kernel<16><<<grid, TILE, smem, st>>>(p, mchunk, part);
+  else if (D <= 32) gradx_kernel<32><<<grid, TILE, smem, st>>>(p, mchunk, part);
+  else gradx_kernel<64><<<grid, TILE, smem, st>>>(p, mchunk, part);
+  GPX_CUDA(cudaGetLastError());
+  gradx_reduce_kernel<<<(unsigned)((p.N * D + 255) / 256), 256, 0, st>>>(part, p.N, D, nchunk, p.kp, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
 // roofline denominator: DMMA.8x8x4 issue rate of this device (8 independent accumulator chains per warp,
 // 8 warps per CTA, 2 CTAs per SM), timed with CUDA events. tools/microbench.cu is the stand-alone version.
 // =================================================================================================================

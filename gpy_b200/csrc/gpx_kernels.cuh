@@ -53,6 +53,7 @@ int launch_extract(int which, const double* S, long ld, const double* Ldiag, con
                    int P, long N, double* out, cudaStream_t st);
 int launch_transpose_pad(const double* in, long n, int p, long ld, double* out, cudaStream_t st);
 int launch_untranspose(const double* in, long n, int p, long ld, double* out, cudaStream_t st);
+int launch_gradx(const GradFullParams& p, int nchunk, long mchunk, double* part, double* out, cudaStream_t st);
 int launch_load_sym(const double* A, long N, double* S, long ld, double jitter, cudaStream_t st);
 int measure_dmma_peak(cudaStream_t st, double* tflops);
 int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStream_t st);

@@ -134,6 +134,22 @@ class Stationary(Kern):
         self.variance.gradient = np.atleast_1d(dv)
         self.lengthscale.gradient = np.atleast_1d(dl)
 
+    def gradients_X(self, dL_dK, X, X2=None):
+        """stationary.py:245-252 -> gpx_kern_grad_X (needed by inducing-point / latent-variable models)."""
+        Xs = self._slice_X(X)
+        X2s = None if X2 is None else self._slice_X(X2)
+        kind, ard, var, ls = self._theta()
+        g = _ffi.kern_grad_X(kind, ard, var, ls, Xs, np.asarray(dL_dK, dtype=np.float64), X2s)
+        if Xs.shape[1] == np.asarray(X).shape[1]:
+            return g
+        full = np.zeros(np.asarray(X).shape)       # kernel_slice_operations.py:138-150: scatter into the full X
+        full[:, self.active_dims] = g
+        return full
+
+    def gradients_X_diag(self, dL_dKdiag, X):
+        """stationary.py:368-369."""
+        return np.zeros(np.asarray(X).shape)
+
     def update_gradients_diag(self, dL_dKdiag, X):
         """stationary.py:182-192."""
         self.variance.gradient = np.atleast_1d(np.sum(dL_dKdiag))

@@ -75,7 +75,8 @@ int gpx_get(gpx_ctx* ctx, int which, double* out_host);
 int gpx_predict(gpx_ctx* ctx, const double* Xnew, int64_t M, int full_cov, double* mu, double* var);
 
 /* Standalone kernel plugin calls (no context needed beyond a device; ctx may be NULL -> device 0 scratch context).
- * Replaces Stationary.K (stationary.py:105-168): out is N x M ROW-major (what Kern.K returns to NumPy callers). */
+ * Replaces Stationary.K (stationary.py:105-168): out is N x M ROW-major (what Kern.K returns to NumPy callers).
+ * out == NULL: build on the device only and report the kernel time via gpx_get_stats (kbuild_ms, kbuild_bytes). */
 int gpx_kern_K(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* X, int64_t N,
                const double* X2 /* NULL -> K(X,X) with exact zero-distance diagonal */, int64_t M, int D, double* out);
 /* Replaces Stationary.Kdiag (stationary.py:170-173). */
@@ -84,6 +85,11 @@ int gpx_kern_Kdiag(int kind, double variance, int64_t N, double* out);
 int gpx_kern_grad_full(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* X,
                        int64_t N, const double* X2, int64_t M, int D, const double* dL_dK, double* dvariance,
                        double* dlengthscale);
+
+/* Replaces Stationary.gradients_X (stationary.py:245-252,348-366 and the OpenMP helper GPy/kern/src/stationary_utils.c:1-14
+ * _grad_X): grad (N x D row-major) = d/dX of sum(dL_dK * K(X, X2)); X2 == NULL is the symmetric case (tmp + tmp^T). */
+int gpx_kern_grad_X(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* X,
+                    int64_t N, const double* X2, int64_t M, int D, const double* dL_dK, double* grad);
 
 /* Replaces pdinv / jitchol for a caller-supplied symmetric positive (semi-)definite matrix A (N x N, dense, symmetric so
  * row- and column-major coincide): GPy/util/linalg.py:193-214 (pdinv -> Ai, L, Li, logdet) and :56-75 (jitchol: first a

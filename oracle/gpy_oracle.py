@@ -290,6 +290,19 @@ class StationaryOracle(object):
             self.lengthscale_gradient = np.atleast_1d(-np.sum(dL_dr * r) / self.lengthscale)
         return self.variance_gradient, self.lengthscale_gradient
 
+    def gradients_X(self, dL_dK, X, X2=None):
+        """stationary.py:245-252 -> _gradients_X_pure (:340-352)."""
+        invdist = inv_dist(X, X2, self.lengthscale, self.ARD)
+        dL_dr = dK_dr(self.kind, self.variance, self._r(X, X2)) * dL_dK
+        tmp = invdist * dL_dr
+        if X2 is None:
+            tmp = tmp + tmp.T
+            X2 = X
+        grad = np.empty(X.shape, dtype=np.float64)
+        for q in range(self.input_dim):
+            np.sum(tmp * (X[:, q][:, None] - X2[:, q][None, :]), axis=1, out=grad[:, q])
+        return grad / self.lengthscale ** 2
+
     def update_gradients_diag(self, dL_dKdiag, X):
         """stationary.py:175-183 (reset-style diag gradient: variance only)."""
         self.variance_gradient = np.sum(dL_dKdiag)

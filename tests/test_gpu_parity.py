@@ -266,3 +266,21 @@ def test_inference_generic_path_mean_function_and_precomputed_K():
     mu0, var0 = o.predict(ko, X, res["L"], res["alpha"], X[:4], 0.05)
     np.testing.assert_allclose(mu, mu0 + 0.3 * X[:4, 1:2], rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(var, var0, rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", o.KINDS)
+@pytest.mark.parametrize("ARD", [False, True])
+def test_gradients_X(kind, ARD):
+    """Stationary.gradients_X (stationary.py:245-252; native helper stationary_utils.c:1-14), fixtures of
+    GPy/testing/test_cython.py:57-81: square (300 x 300) and rectangular (300 x 20) dL_dK."""
+    rng = np.random.default_rng(11)
+    for (n, m, d) in ((300, 20, 10), (257, 131, 3), (40, 700, 5)):
+        X, Z = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+        ls = rng.uniform(0.8, 2.0, d) if ARD else float(rng.uniform(0.8, 2.0))
+        cls = {"rbf": gpy_b200.RBF, "exponential": gpy_b200.Exponential, "matern32": gpy_b200.Matern32,
+               "matern52": gpy_b200.Matern52}[kind]
+        k = cls(d, variance=0.7, lengthscale=ls, ARD=ARD)
+        ko = o.StationaryOracle(kind, d, 0.7, ls, ARD)
+        dKxx, dKxz = rng.standard_normal((n, n)), rng.standard_normal((n, m))
+        np.testing.assert_allclose(k.gradients_X(dKxx, X), ko.gradients_X(dKxx, X), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(k.gradients_X(dKxz, X, Z), ko.gradients_X(dKxz, X, Z), rtol=1e-9, atol=1e-11)

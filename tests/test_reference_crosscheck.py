@@ -73,3 +73,16 @@ def test_reference_native_helper_matches(G):
         g_ref = k._lengthscale_grads_pure(tmp, A, B)
         g_c = o.lengthscale_grads_native(tmp, A, B, np.ones(10), "ref")
         assert np.allclose(g_ref, g_c)
+
+
+def test_oracle_gradients_X_equals_reference(G):
+    rng = np.random.default_rng(2)
+    X, Z = rng.standard_normal((60, 4)), rng.standard_normal((25, 4))
+    for name, kind in (("RBF", "rbf"), ("Matern32", "matern32"), ("Matern52", "matern52"), ("Exponential", "exponential")):
+        for ARD in (False, True):
+            ls = np.array([1.0, 1.5, 2.0, 0.8]) if ARD else 1.3
+            kr = getattr(G, name)(4, variance=0.9, lengthscale=ls, ARD=ARD)
+            ko = o.StationaryOracle(kind, 4, 0.9, ls, ARD)
+            d1, d2 = rng.standard_normal((60, 60)), rng.standard_normal((60, 25))
+            np.testing.assert_allclose(ko.gradients_X(d1, X), kr.gradients_X(d1, X), rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(ko.gradients_X(d2, X, Z), kr.gradients_X(d2, X, Z), rtol=1e-12, atol=1e-14)

@@ -27,6 +27,17 @@ def main():
                 al = eng.get("alpha")
                 msg = "lml abs %.2e grad rel %.2e alpha rel %.2e" % (abs(lml - l0), np.max(np.abs(g - g0) / np.abs(g0)),
                                                                     np.max(np.abs(al - res["alpha"])) / np.max(np.abs(res["alpha"])))
+            elif os.environ.get("GPX_DIST_VERIFY") and kind == "rbf":
+                # parity at sizes the CPU oracle cannot reach: the sharded result against the single-GPU engine
+                msg = "lml %.6f" % lml
+                if rank == 0:
+                    e1 = _ffi.Engine(local)
+                    e1.set_data(X, Y)
+                    l1, g1, _ = e1.exact_eval(kind, ARD, var, ls, noise)
+                    msg += " | vs 1 GPU: lml abs %.2e grad rel %.2e (1-GPU %.1f ms)" % (
+                        abs(lml - l1), np.max(np.abs(g - g1) / np.abs(g1)), e1.stats()["total_ms"])
+                    e1.close()
+                dist.barrier()
             else:
                 msg = "lml %.6f" % lml
             if rank == 0:
