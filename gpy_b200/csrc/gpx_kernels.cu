@@ -43,7 +43,16 @@ int launch_prep_x(const double* X, long N, long ldx, const KernParams& kp, doubl
 // Ky = K + (noise + jitter) I (exact_gaussian_inference.py:55-56) written straight into the factor workspace
 // (lower tiles; upper tiles zero = the initial state of the inverse-factor region; padding = identity).
 // =================================================================================================================
-template <int DREG>
+template <int KIND>
+__device__ __forceinline__ double k_unit(double r) {
+  if (KIND == GPX_RBF) return exp(-0.5 * r * r);
+  if (KIND == GPX_EXPONENTIAL) return exp(-r);
+  if (KIND == GPX_MATERN32) { const double s3 = 1.7320508075688772; return (1.0 + s3 * r) * exp(-s3 * r); }
+  const double s5 = 2.23606797749979;
+  return (1.0 + s5 * r + (5.0 / 3.0) * r * r) * exp(-s5 * r);
+}
+
+template <int DREG, int KIND>
 __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int D = p.kp.D;
@@ -54,13 +63,14 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(sSc + TILE);
 
   const int ct = blockIdx.x, rt = blockIdx.y;
+  if (p.own_G > 1 && ((rt / p.own_blk) % p.own_G) != p.own_g) return;   // block row owned by another rank
   const int tid = threadIdx.x;
   const int il = tid & (TILE - 1), half = tid >> 7;
   const long gi = (long)rt * TILE + il;
   double* outp = p.out + gi + ((long)ct * TILE + half * 64) * p.ld;
 
-  if (p.own_G > 1 && ((rt / p.own_blk) % p.own_G) != p.own_g) return;   // block row owned by another rank
   if (p.sym && rt < ct) {  // strictly-upper tile of the factor workspace: the inverse-factor region starts at zero
+#pragma unroll 8
     for (int j = 0; j < 64; j++) outp[(long)j * p.ld] = 0.0;
     return;
   }
@@ -81,22 +91,35 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
 #pragma unroll
   for (int q = 0; q < DREG; q++) xi[q] = q < D ? sR[q * TILE + il] : 0.0;
   const double si = sSr[il];
-  const int kind = p.kp.kind;
   const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  const double* sCj = sC + half * 64;
+  const double* sScj = sSc + half * 64;
+  // interior tiles (no diagonal, no padding) take the branch-free loop; the tile test is block-uniform
+  const bool edge = (rt == ct && p.same) || ((long)rt * TILE + TILE > p.nrows) || ((long)ct * TILE + TILE > p.ncols);
+  if (!edge) {
+#pragma unroll 4
+    for (int j = 0; j < 64; j++) {
+      double dot = 0.0;
+#pragma unroll
+      for (int q = 0; q < DREG; q++)
+        if (q < D) dot = fma(xi[q], sCj[q * TILE + j], dot);
+      const double r2 = fmax(si + sScj[j] - 2.0 * dot, 0.0);
+      outp[0] = variance * k_unit<KIND>(sqrt(r2) * inv_ls);
+      outp += p.ld;
+    }
+    return;
+  }
   const bool row_valid = gi < p.nrows;
-#pragma unroll 2
   for (int j = 0; j < 64; j++) {
-    const int jl = half * 64 + j;
-    const long gj = (long)ct * TILE + jl;
+    const long gj = (long)ct * TILE + half * 64 + j;
     double dot = 0.0;
 #pragma unroll
     for (int q = 0; q < DREG; q++)
-      if (q < D) dot = fma(xi[q], sC[q * TILE + jl], dot);
-    double r2 = si + sSc[jl] - 2.0 * dot;
+      if (q < D) dot = fma(xi[q], sCj[q * TILE + j], dot);
+    double r2 = si + sScj[j] - 2.0 * dot;
     if (p.same && gi == gj) r2 = 0.0;
     r2 = fmax(r2, 0.0);
-    const double rr = sqrt(r2) * inv_ls;
-    double v = variance * k_of_r_unit(kind, rr);
+    double v = variance * k_unit<KIND>(sqrt(r2) * inv_ls);
     if (p.sym) {
       if (gi == gj) v = v + p.diag_add;
       if (!row_valid || gj >= p.ncols) v = (gi == gj) ? 1.0 : 0.0;
@@ -107,25 +130,38 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
   }
 }
 
+template <int DREG>
+static int launch_kbuild_kind(const KBuildParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+#define GPX_KB(KD)                                                                                              \
+  do {                                                                                                          \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      GPX_CUDA(cudaFuncSetAttribute(kbuild_kernel<DREG, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                    (int)((2 * MAX_D + 2) * TILE * 8 + 16)));                                   \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    kbuild_kernel<DREG, KD><<<grid, 256, smem, st>>>(p);                                                        \
+  } while (0)
+  switch (p.kp.kind) {
+    case GPX_RBF: GPX_KB(GPX_RBF); break;
+    case GPX_EXPONENTIAL: GPX_KB(GPX_EXPONENTIAL); break;
+    case GPX_MATERN32: GPX_KB(GPX_MATERN32); break;
+    default: GPX_KB(GPX_MATERN52); break;
+  }
+#undef GPX_KB
+  return 0;
+}
+
 int launch_kbuild(const KBuildParams& p, int row_tiles, int col_tiles, cudaStream_t st) {
   const int D = p.kp.D;
   const size_t smem = (size_t)(2 * D + 2) * TILE * 8 + 16;
   dim3 grid(col_tiles, row_tiles);
-#define GPX_KB(DR)                                                                                              \
-  do {                                                                                                          \
-    static bool attr_set = false;                                                                               \
-    if (!attr_set) {                                                                                            \
-      GPX_CUDA(cudaFuncSetAttribute(kbuild_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                    (int)((2 * MAX_D + 2) * TILE * 8 + 16)));                                   \
-      attr_set = true;                                                                                          \
-    }                                                                                                           \
-    kbuild_kernel<DR><<<grid, 256, smem, st>>>(p);                                                              \
-  } while (0)
-  if (D <= 8) GPX_KB(8);
-  else if (D <= 16) GPX_KB(16);
-  else if (D <= 32) GPX_KB(32);
-  else GPX_KB(64);
-#undef GPX_KB
+  int rc;
+  if (D <= 8) rc = launch_kbuild_kind<8>(p, grid, smem, st);
+  else if (D <= 16) rc = launch_kbuild_kind<16>(p, grid, smem, st);
+  else if (D <= 32) rc = launch_kbuild_kind<32>(p, grid, smem, st);
+  else rc = launch_kbuild_kind<64>(p, grid, smem, st);
+  if (rc) return rc;
   GPX_CUDA(cudaGetLastError());
   return 0;
 }
