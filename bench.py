@@ -189,6 +189,8 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
@@ -325,7 +327,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--size", "--n", dest="n", type=int, default=16384, help="number of data points N")
     ap.add_argument("--d", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
