@@ -343,113 +343,6 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   }
 }
 
-// =================================================================================================================
-// Persistent variant of the trailing update: one CTA per SM walks the tile schedule round-robin. The mbarrier ring and
-// its slab counters run continuously across tiles, so the producer warp is already streaming the next tile's first
-// k-slabs while the consumers store the finished tile and preload the next C tile; CTA launch / barrier set-up are
-// paid once per launch instead of once per tile (measured fixed cost of the one-tile-per-CTA kernel: ~9 us per tile,
-// 6 % at NB = 1024).
-// =================================================================================================================
-__device__ __forceinline__ bool decode_update_lin(const GemmParams& p, int lin, int& r, int& c) {
-  const int ncols = p.ncols > 0 ? p.ncols : p.nt - p.c0;
-  const int sbcols = (ncols + SB - 1) / SB;
-  const int sb = lin / (SB * SB), t = lin % (SB * SB);
-  const int slot = (sb / sbcols) * SB + t / SB;
-  const int col = (sb % sbcols) * SB + t % SB;
-  if (col >= ncols) return false;
-  c = p.c0 + col;
-  r = slot < p.rlow ? slot : c + (slot - p.rlow);
-  if (r >= p.nt) return false;
-  return p.own_G <= 1 || ((r / p.own_blk) % p.own_G) == p.own_g;
-}
-
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_update_persist_kernel(const GemmParams p, const int total_lin) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + STAGES;
-  double* sA = reinterpret_cast<double*>(smem_raw + BAR_BYTES);
-  double* sB = sA + STAGES * SLAB_DOUBLES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  const int nslab = (p.K / TILE) * (TILE / KSLAB);
-
-  if (warp >= CONSUMER_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp != CONSUMER_WARPS) return;
-    const bool isA = lane < KSLAB;
-    const int kc = lane & (KSLAB - 1);
-    double* dst_base = (isA ? sA : sB) + kc * PITCH;
-    const long ld = isA ? p.lda : p.ldb;
-    uint32_t gs = 0;
-    for (int lin = blockIdx.x; lin < total_lin; lin += gridDim.x) {
-      int r, c;
-      if (!decode_update_lin(p, lin, r, c)) continue;
-      const int rc = isA ? r : c;
-      const double* src_base = (isA ? p.A : p.B) + ((isA ? p.map_A : p.map_B) ? mapped_offset(p, rc) : (long)rc * TILE);
-      for (int it = 0; it < nslab; ++it, ++gs) {
-        const int s = gs % STAGES;
-        const uint32_t n = gs / STAGES;
-        if (gs >= STAGES) mbar_wait(&empty[s], (n & 1) ^ 1);
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], 2 * KSLAB * TILE * 8);
-        __syncwarp();
-        bulk_g2s(dst_base + s * SLAB_DOUBLES, src_base + (long)(it * KSLAB + kc) * ld, TILE * 8, &full[s]);
-      }
-    }
-    return;
-  }
-
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-  const int wm = warp & 1, wn = warp >> 1;
-  const int g = lane >> 2, tg = lane & 3;
-  uint32_t gs = 0;
-  for (int lin = blockIdx.x; lin < total_lin; lin += gridDim.x) {
-    int r, c;
-    if (!decode_update_lin(p, lin, r, c)) continue;
-    double* Ct = p.C + (p.map_C ? mapped_offset(p, r) : (long)r * TILE) + (long)c * TILE * p.ldc + wm * 64 + g +
-                 (long)(wn * 32 + 2 * tg) * p.ldc;
-    double acc[8][4][2];
-#pragma unroll
-    for (int mb = 0; mb < 8; mb++)
-#pragma unroll
-      for (int nb = 0; nb < 4; nb++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) acc[mb][nb][e] = Ct[mb * 8 + (long)(nb * 8 + e) * p.ldc];
-    for (int it = 0; it < nslab; ++it, ++gs) {
-      const int s = gs % STAGES;
-      const uint32_t n = gs / STAGES;
-      mbar_wait(&full[s], n & 1);
-      const double* a = sA + s * SLAB_DOUBLES + wm * 64 + g;
-      const double* b = sB + s * SLAB_DOUBLES + wn * 32 + g;
-#pragma unroll
-      for (int k4 = 0; k4 < KSLAB / 4; k4++) {
-        const int kk = (k4 * 4 + tg) * PITCH;
-        double af[8], bf[4];
-#pragma unroll
-        for (int mb = 0; mb < 8; mb++) af[mb] = -a[kk + mb * 8];
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) bf[nb] = b[kk + nb * 8];
-#pragma unroll
-        for (int mb = 0; mb < 8; mb++)
-#pragma unroll
-          for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-    }
-#pragma unroll
-    for (int mb = 0; mb < 8; mb++)
-#pragma unroll
-      for (int nb = 0; nb < 4; nb++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) Ct[mb * 8 + (long)(nb * 8 + e) * p.ldc] = acc[mb][nb][e];
-  }
-}
-
 // one __global__ entry per mode so that profiles name them apart
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_update_kernel(const GemmParams p) { gemm_nt_body<GEMM_UPDATE>(p); }
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_panel_kernel(const GemmParams p) { gemm_nt_body<GEMM_PANEL>(p); }
@@ -457,7 +350,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_lauum_kernel(const GemmP
 
 int gemm_init() {
   GPX_CUDA(cudaFuncSetAttribute(gemm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
-  GPX_CUDA(cudaFuncSetAttribute(gemm_update_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
   GPX_CUDA(cudaFuncSetAttribute(gemm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PIPE));
   GPX_CUDA(cudaFuncSetAttribute(gemm_lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
   return 0;
@@ -474,21 +366,7 @@ int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t st) {
     grid = dim3((unsigned)(nsr * (nsr + 1) / 2 * SB * SB), 1, 1);
   }
   if (grid.x == 0 || grid.y == 0) return 0;
-  if (p.mode == GEMM_UPDATE) {
-    static int sms = 0;
-    static int persist = -1;
-    if (persist < 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      persist = getenv("GPX_NO_PERSIST") ? 0 : 1;
-    }
-    // persistent walk only pays when every SM gets several tiles; tiny launches keep one tile per CTA
-    if (persist && p.K >= 2 * TILE && (int)grid.x >= 4 * sms)
-      gemm_update_persist_kernel<<<sms, GEMM_THREADS, SMEM_PIPE, st>>>(p, (int)grid.x);
-    else
-      gemm_update_kernel<<<grid, GEMM_THREADS, SMEM_PIPE, st>>>(p);
-  }
+  if (p.mode == GEMM_UPDATE) gemm_update_kernel<<<grid, GEMM_THREADS, SMEM_PIPE, st>>>(p);
   else if (p.mode == GEMM_PANEL) gemm_panel_kernel<<<grid, GEMM_THREADS, SMEM_PIPE, st>>>(p);
   else {
     const int smem = BAR_BYTES + std::max(PIPE_BYTES, epi_bytes(p.kp.D, p.P));
