@@ -1,6 +1,8 @@
 // gpx_kernels.cu — the non-GEMM kernels of the exact-GP path: input scaling, covariance build, the 128x128 base
 // factor-and-invert block, triangular matrix-vector products, block assembly, result extraction, final reduction.
 #include "gpx_common.cuh"
+#include <cstdlib>
+
 #include "gpx_kernels.cuh"
 
 namespace gpx {
@@ -274,9 +276,184 @@ base_sweep_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, d
   }
 }
 
+// =================================================================================================================
+// base block, second generation: the same unified factor-and-invert sweep carried one level further down. The 128x128
+// tile lives in shared memory; it is processed in eight 16-column micro-panels:
+//   (1) ONE WARP factor-and-inverts the 16x16 diagonal micro-block in registers (8 values per lane, shuffles only,
+//       rsqrt on the serial chain, no block barrier inside),
+//   (2) all threads form the micro-panel  P = T(:, panel) W^T  (W = inverse of the micro-block) in place,
+//   (3) all 16 warps apply  T(r,c) -= P_r P_c^T  to the 16x16 micro-tiles c > panel, r in [0..panel] U [c..7] with
+//       DMMA.8x8x4 (fragments straight from shared memory, pitch 132 -> conflict-free).
+// Three block barriers per micro-panel instead of one per column: 24 instead of 128, and the rank-16 updates run on
+// the tensor pipe. Same inputs/outputs as base_sweep_kernel.
+// =================================================================================================================
+constexpr int BP = 132;   // pitch (doubles) of the shared tile, column-major: (row, col) at col*BP + row
+constexpr int MP = 20;    // pitch of the 16x16 micro operand buffers
+
+__global__ void __launch_bounds__(512, 1)
+base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, double* __restrict__ Dinv,
+                    double* __restrict__ logdet_part, int* __restrict__ info, int gcol0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* T = reinterpret_cast<double*>(smem_raw);   // [128][BP]
+  double* Pd = T + TILE * BP;                        // U micro-block of the current panel: (r, k) at k*MP + r
+  double* Wm = Pd + 16 * MP;                         // W = U^T micro-block (lower): (c, k) at k*MP + c
+  double* dinv = Wm + 16 * MP;                       // [128] reciprocal pivots
+  double* ldg = dinv + TILE;                         // [128] pivots
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < TILE * TILE; idx += 512) {
+    const int row = idx & (TILE - 1), col = idx >> 7;
+    T[col * BP + row] = row >= col ? S[row + (long)col * ld] : 0.0;
+  }
+  __syncthreads();
+
+  for (int jp = 0; jp < 8; jp++) {
+    const int c0 = jp * 16;
+    // ---- (1) warp 0: 16x16 diagonal micro-block, register resident ---------------------------------------------
+    if (warp == 0) {
+      const int rr = lane & 15, ch = (lane >> 4) * 8;   // lane owns row rr, columns ch..ch+7 of the micro-block
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = (rr >= ch + q) ? T[(c0 + ch + q) * BP + c0 + rr] : 0.0;
+      double my_inv = 0.0, my_l = 0.0;
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int ob = (j >> 3) * 16;                   // first lane of the half-warp that owns column j
+        const double d = __shfl_sync(0xffffffffu, v[j & 7], ob + j);
+        if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, gcol0 + c0 + j + 1);
+        const double inv = rsqrt(d);
+        const double l = d * inv;
+        const double pown = (rr == j) ? inv : v[j & 7] * inv;      // meaningful on the owner half-warp
+        const double prow = __shfl_sync(0xffffffffu, pown, ob + rr);
+        if ((lane >> 4) == (j >> 3)) v[j & 7] = (rr == j) ? l : pown;
+        if (lane == ob + j) { my_inv = inv; my_l = l; }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const double pcol = __shfl_sync(0xffffffffu, pown, ob + ch + q);
+          const int col = ch + q;
+          if (col > j && (rr >= col || rr <= j)) v[q] = fma(-prow, pcol, v[q]);
+        }
+      }
+      // write back: lower + diagonal (pivots) and strict upper (= U entries) of the micro-block; operand copies
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int col = ch + q;
+        T[(c0 + col) * BP + c0 + rr] = v[q];
+        const double u = rr < col ? v[q] : 0.0;          // U(rr, col) strictly above the diagonal
+        Pd[col * MP + rr] = u;
+        Wm[rr * MP + col] = u;                            // W(col, rr) = U(rr, col); zeros above W's diagonal
+      }
+      // diagonal entries: the lane that produced pivot j is lane (j>>3)*16 + j, i.e. rr == its own column index
+      if (rr >= ch && rr < ch + 8) {
+        // this lane holds (rr, rr); its pivot was computed at j == rr
+        dinv[c0 + rr] = my_inv; ldg[c0 + rr] = my_l;
+        Pd[rr * MP + rr] = my_inv;
+        Wm[rr * MP + rr] = my_inv;
+      }
+    }
+    __syncthreads();
+    // ---- (2) micro-panel: P(r, c) = sum_{k<=c} T(r, c0+k) W(c, k) for rows outside the micro-block, in place --------
+    {
+      const int row = tid >> 2, cq = (tid & 3) * 4;
+      const bool act = row < c0 || row >= c0 + 16;
+      double in[16];
+#pragma unroll
+      for (int kx = 0; kx < 16; kx++) in[kx] = act ? T[(c0 + kx) * BP + row] : 0.0;
+      __syncthreads();
+      if (act) {
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          const int c = cq + cc;
+          double s = 0.0;
+#pragma unroll
+          for (int kx = 0; kx < 16; kx++)
+            if (kx <= c) s = fma(in[kx], Wm[kx * MP + c], s);
+          T[(c0 + c) * BP + row] = s;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (3) micro-tile updates with DMMA --------------------------------------------------------------------------
+    if (jp < 7) {
+      const int g = lane >> 2, tg = lane & 3;
+      const int ncol = 7 - jp;
+      // enumerate (ct, slot): ct = jp+1..7, slot in [0, jp+1 + 8-ct): slot <= jp -> rt = slot, else rt = ct + slot-(jp+1)
+      int lin = 0;
+      for (int ci = 0; ci < ncol; ci++) {
+        const int ct = jp + 1 + ci;
+        const int nslot = jp + 1 + 8 - ct;
+        for (int slot = 0; slot < nslot; slot++, lin++) {
+          if ((lin & 15) != warp) continue;
+          const int rt = slot <= jp ? slot : ct + slot - (jp + 1);
+          const double* Ap = (rt == jp) ? Pd : (T + c0 * BP + rt * 16);
+          const int apitch = (rt == jp) ? MP : BP;
+          const double* Bp = T + c0 * BP + ct * 16;
+          double* Cp = T + (ct * 16) * BP + rt * 16;
+          double c[2][2][2];
+#pragma unroll
+          for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) c[mi][ni][e] = Cp[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) {
+            double af[2], bf[2];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) af[mi] = -Ap[(k4 * 4 + tg) * apitch + mi * 8 + g];
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) bf[ni] = Bp[(k4 * 4 + tg) * BP + ni * 8 + g];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+              for (int ni = 0; ni < 2; ni++) dmma884(c[mi][ni][0], c[mi][ni][1], af[mi], bf[ni]);
+          }
+#pragma unroll
+          for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) Cp[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g] = c[mi][ni][e];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- outputs ----------------------------------------------------------------------------------------------------
+  for (int idx = tid; idx < TILE * TILE; idx += 512) {
+    const int row = idx & (TILE - 1), col = idx >> 7;
+    const double x = T[col * BP + row];
+    if (row > col) {
+      Ldiag[row + col * TILE] = x;
+      S[row + (long)col * ld] = 0.0;
+      Dinv[row + col * TILE] = T[row * BP + col];    // W(row, col) = U(col, row), row > col
+    } else if (row == col) {
+      Ldiag[row + col * TILE] = ldg[row];
+      S[row + (long)col * ld] = dinv[row];
+      Dinv[row + col * TILE] = dinv[row];
+    } else {
+      Ldiag[row + col * TILE] = 0.0;
+      S[row + (long)col * ld] = x;                   // U(row, col)
+      Dinv[row + col * TILE] = 0.0;
+    }
+  }
+  if (tid < 32) {
+    double s = 0.0;
+    for (int j = tid; j < TILE; j += 32) s += log(ldg[j]);
+    s = warp_sum(s);
+    if (tid == 0) *logdet_part = 2.0 * s;
+  }
+}
+
 int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
                 cudaStream_t st) {
-  base_sweep_kernel<<<1, 512, 0, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
+  static int which = -1;
+  constexpr int smem16 = (TILE * BP + 2 * 16 * MP + 2 * TILE) * 8;
+  if (which < 0) {
+    which = getenv("GPX_BASE_V1") ? 1 : 2;
+    GPX_CUDA(cudaFuncSetAttribute(base_sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+  }
+  if (which == 1) base_sweep_kernel<<<1, 512, 0, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
+  else base_sweep16_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }
