@@ -7,7 +7,8 @@ computing requires libgpx.so and a B200.
 from . import _ffi  # noqa: F401
 from ._ffi import Engine, GpxError, kern_K, kern_Kdiag, kern_grad_full  # noqa: F401
 
-from .kern import RBF, Exponential, Matern32, Matern52, Stationary, DeviceGradient  # noqa: F401
+from .kern import (RBF, Exponential, Matern32, Matern52, Stationary, DeviceGradient, Add, Prod, White, Bias,  # noqa: F401
+                   Kern, CombinationKernel)
 from .inference import ExactGaussianInference, Gaussian, PosteriorExact  # noqa: F401
 from .model import GP, GPRegression  # noqa: F401
 

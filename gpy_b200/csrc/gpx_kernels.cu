@@ -308,13 +308,14 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
 
   for (int jp = 0; jp < 8; jp++) {
     const int c0 = jp * 16;
-    // ---- (1) warp 0: 16x16 diagonal micro-block, register resident ---------------------------------------------
+    // ---- (1) warp 0: 16x16 diagonal micro-block; values in registers, pivot vector exchanged through shared memory ---
     if (warp == 0) {
       const int rr = lane & 15, ch = (lane >> 4) * 8;   // lane owns row rr, columns ch..ch+7 of the micro-block
       double v[8];
 #pragma unroll
       for (int q = 0; q < 8; q++) v[q] = (rr >= ch + q) ? T[(c0 + ch + q) * BP + c0 + rr] : 0.0;
       double my_inv = 0.0, my_l = 0.0;
+      double* psh = Pd;                                  // 2 x 16 scratch (Pd is rebuilt after the column loop)
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         const int ob = (j >> 3) * 16;                   // first lane of the half-warp that owns column j
@@ -322,17 +323,22 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
         if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, gcol0 + c0 + j + 1);
         const double inv = rsqrt(d);
         const double l = d * inv;
-        const double pown = (rr == j) ? inv : v[j & 7] * inv;      // meaningful on the owner half-warp
-        const double prow = __shfl_sync(0xffffffffu, pown, ob + rr);
-        if ((lane >> 4) == (j >> 3)) v[j & 7] = (rr == j) ? l : pown;
-        if (lane == ob + j) { my_inv = inv; my_l = l; }
+        double* pj = psh + (j & 1) * 16;
+        if ((lane >> 4) == (j >> 3)) {                  // owner half-warp: finalize column j, publish p
+          const double pown = (rr == j) ? inv : v[j & 7] * inv;
+          pj[rr] = pown;
+          v[j & 7] = (rr == j) ? l : pown;
+          if (rr == j) { my_inv = inv; my_l = l; }
+        }
+        __syncwarp();
+        const double prow = pj[rr];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          const double pcol = __shfl_sync(0xffffffffu, pown, ob + ch + q);
           const int col = ch + q;
-          if (col > j && (rr >= col || rr <= j)) v[q] = fma(-prow, pcol, v[q]);
+          if (col > j && (rr >= col || rr <= j)) v[q] = fma(-prow, pj[col], v[q]);
         }
       }
+      __syncwarp();
       // write back: lower + diagonal (pivots) and strict upper (= U entries) of the micro-block; operand copies
 #pragma unroll
       for (int q = 0; q < 8; q++) {
@@ -342,34 +348,45 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
         Pd[col * MP + rr] = u;
         Wm[rr * MP + col] = u;                            // W(col, rr) = U(rr, col); zeros above W's diagonal
       }
-      // diagonal entries: the lane that produced pivot j is lane (j>>3)*16 + j, i.e. rr == its own column index
-      if (rr >= ch && rr < ch + 8) {
-        // this lane holds (rr, rr); its pivot was computed at j == rr
+      __syncwarp();
+      if (rr >= ch && rr < ch + 8) {                      // this lane produced pivot rr
         dinv[c0 + rr] = my_inv; ldg[c0 + rr] = my_l;
         Pd[rr * MP + rr] = my_inv;
         Wm[rr * MP + rr] = my_inv;
       }
     }
     __syncthreads();
-    // ---- (2) micro-panel: P(r, c) = sum_{k<=c} T(r, c0+k) W(c, k) for rows outside the micro-block, in place --------
-    {
-      const int row = tid >> 2, cq = (tid & 3) * 4;
-      const bool act = row < c0 || row >= c0 + 16;
-      double in[16];
+    // ---- (2) micro-panel with DMMA: P(rows, :) = T(rows, panel) W^T for the 7 row blocks outside the micro-block -----
+    if (warp < 7) {
+      const int g = lane >> 2, tg = lane & 3;
+      const int rt = warp < jp ? warp : warp + 1;        // row micro-block, skipping jp
+      double* Ap = T + c0 * BP + rt * 16;
+      double af[2][4], c[2][2][2];
 #pragma unroll
-      for (int kx = 0; kx < 16; kx++) in[kx] = act ? T[(c0 + kx) * BP + row] : 0.0;
-      __syncthreads();
-      if (act) {
+      for (int mi = 0; mi < 2; mi++)
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-          const int c = cq + cc;
-          double s = 0.0;
+        for (int k4 = 0; k4 < 4; k4++) af[mi][k4] = Ap[(k4 * 4 + tg) * BP + mi * 8 + g];
 #pragma unroll
-          for (int kx = 0; kx < 16; kx++)
-            if (kx <= c) s = fma(in[kx], Wm[kx * MP + c], s);
-          T[(c0 + c) * BP + row] = s;
-        }
+      for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) { c[mi][ni][0] = 0.0; c[mi][ni][1] = 0.0; }
+#pragma unroll
+      for (int k4 = 0; k4 < 4; k4++) {
+        double bf[2];
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) bf[ni] = Wm[(k4 * 4 + tg) * MP + ni * 8 + g];   // B(n = c, k) = W(c, k)
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 2; ni++) dmma884(c[mi][ni][0], c[mi][ni][1], af[mi][k4], bf[ni]);
       }
+      __syncwarp();                                       // every lane has read its A fragments: overwrite in place
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) Ap[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g] = c[mi][ni][e];
     }
     __syncthreads();
     // ---- (3) micro-tile updates with DMMA --------------------------------------------------------------------------

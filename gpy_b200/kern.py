@@ -70,6 +70,26 @@ class Kern(Parameterized):
     def update_gradients_full(self, dL_dK, X, X2=None):
         raise NotImplementedError
 
+    # kern.py:311-360: operator overloading builds combination kernels
+    def __add__(self, other):
+        return self.add(other)
+
+    def add(self, other, name="sum"):
+        assert isinstance(other, Kern), "only kernels can be added to kernels..."
+        return Add([self, other], name=name)
+
+    def __mul__(self, other):
+        return self.prod(other)
+
+    def prod(self, other, name="mul"):
+        assert isinstance(other, Kern), "only kernels can be multiplied to kernels..."
+        return Prod([self, other], name)
+
+    @property
+    def is_fixed(self):
+        ps = self.flattened_parameters()
+        return bool(ps) and all(p.is_fixed for p in ps)
+
 
 class Stationary(Kern):
     """GPy.kern.src.stationary.Stationary (stationary.py:23-243): variance + (ARD) lengthscale, K = K_of_r(r)."""
@@ -191,3 +211,153 @@ class Matern52(Stationary):
 
     def __init__(self, input_dim, variance=1., lengthscale=None, ARD=False, active_dims=None, name="Mat52"):
         super(Matern52, self).__init__(input_dim, variance, lengthscale, ARD, active_dims, name)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# combination / static kernels. The parts' matrices are built on the device; the O(N^2) glue
+# (sums, element-wise products, traces) is NumPy on the host, and a GP with such a kernel runs through the generic
+# inference path (gpx_pdinv for the N^3 part). Mirrors GPy/kern/src/add.py:60-86, prod.py:59-110, static.py:63-140.
+# ----------------------------------------------------------------------------------------------------------------------
+class CombinationKernel(Kern):
+    """GPy.kern.src.kern.CombinationKernel (kern.py:363-451): a kernel made of parts; active dims = union."""
+
+    def __init__(self, kernels, name):
+        assert all(isinstance(p, Kern) for p in kernels)
+        input_dim = int(max(int(np.max(p.active_dims)) for p in kernels) + 1)
+        super(CombinationKernel, self).__init__(input_dim, np.arange(input_dim), name)
+        self.parts = list(kernels)
+        for p in self.parts:
+            self.link_parameter(p)
+
+    def _slice_X(self, X):
+        return np.ascontiguousarray(X, dtype=np.float64)
+
+
+class Add(CombinationKernel):
+    """GPy.kern.Add (add.py:11-86)."""
+
+    def __init__(self, subkerns, name="sum"):
+        flat = []
+        for s in subkerns:                       # add.py:20-27: nested sums are flattened
+            flat.extend(s.parts if isinstance(s, Add) else [s])
+        super(Add, self).__init__(flat, name)
+
+    def K(self, X, X2=None):
+        out = None
+        for p in self.parts:
+            Kp = p.K(X, X2)
+            out = Kp if out is None else out + Kp
+        return out
+
+    def Kdiag(self, X):
+        return sum(p.Kdiag(X) for p in self.parts)
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        dL_dK = np.asarray(dL_dK, dtype=np.float64)
+        for p in self.parts:
+            if not p.is_fixed:
+                p.update_gradients_full(dL_dK, X, X2)
+
+    def update_gradients_diag(self, dL_dKdiag, X):
+        for p in self.parts:
+            p.update_gradients_diag(dL_dKdiag, X)
+
+    def gradients_X(self, dL_dK, X, X2=None):
+        return sum(p.gradients_X(dL_dK, X, X2) for p in self.parts)
+
+
+class Prod(CombinationKernel):
+    """GPy.kern.Prod (prod.py:23-110)."""
+
+    def __init__(self, kernels, name="mul"):
+        flat = []
+        for s in kernels:
+            flat.extend(s.parts if isinstance(s, Prod) else [s])
+        super(Prod, self).__init__(flat, name)
+
+    def K(self, X, X2=None):
+        out = None
+        for p in self.parts:
+            Kp = p.K(X, X2)
+            out = Kp if out is None else out * Kp
+        return out
+
+    def Kdiag(self, X):
+        out = None
+        for p in self.parts:
+            Kp = p.Kdiag(X)
+            out = Kp if out is None else out * Kp
+        return out
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        """prod.py:90-110: each part sees dL_dK times the product of the other parts."""
+        dL_dK = np.asarray(dL_dK, dtype=np.float64)
+        Ks = [p.K(X, X2) for p in self.parts]
+        for i, p in enumerate(self.parts):
+            other = None
+            for j, Kj in enumerate(Ks):
+                if j != i:
+                    other = Kj if other is None else other * Kj
+            p.update_gradients_full(dL_dK * other if other is not None else dL_dK, X, X2)
+
+    def gradients_X(self, dL_dK, X, X2=None):
+        dL_dK = np.asarray(dL_dK, dtype=np.float64)
+        Ks = [p.K(X, X2) for p in self.parts]
+        out = 0.0
+        for i, p in enumerate(self.parts):
+            other = None
+            for j, Kj in enumerate(Ks):
+                if j != i:
+                    other = Kj if other is None else other * Kj
+            out = out + p.gradients_X(dL_dK * other if other is not None else dL_dK, X, X2)
+        return out
+
+
+class Static(Kern):
+    """GPy.kern.src.static.Static (static.py:11-61): a variance parameter, no dependence on X."""
+
+    def __init__(self, input_dim, variance, active_dims, name):
+        super(Static, self).__init__(input_dim, active_dims, name)
+        self.variance = Param("variance", variance)
+        self.link_parameter(self.variance)
+
+    def Kdiag(self, X):
+        ret = np.empty((np.asarray(X).shape[0],), dtype=np.float64)
+        ret[:] = self.variance[0]
+        return ret
+
+    def gradients_X(self, dL_dK, X, X2=None):
+        return np.zeros(np.asarray(X).shape)
+
+    def update_gradients_diag(self, dL_dKdiag, X):
+        self.variance.gradient = np.atleast_1d(np.sum(dL_dKdiag))
+
+
+class White(Static):
+    """GPy.kern.White (static.py:63-99)."""
+
+    def __init__(self, input_dim, variance=1., active_dims=None, name="white"):
+        super(White, self).__init__(input_dim, variance, active_dims, name)
+
+    def K(self, X, X2=None):
+        n = np.asarray(X).shape[0]
+        if X2 is None:
+            return np.eye(n) * self.variance[0]
+        return np.zeros((n, np.asarray(X2).shape[0]))
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        self.variance.gradient = np.atleast_1d(np.trace(np.asarray(dL_dK)) if X2 is None else 0.)
+
+
+class Bias(Static):
+    """GPy.kern.Bias (static.py:142-185)."""
+
+    def __init__(self, input_dim, variance=1., active_dims=None, name="bias"):
+        super(Bias, self).__init__(input_dim, variance, active_dims, name)
+
+    def K(self, X, X2=None):
+        shape = (np.asarray(X).shape[0], np.asarray(X).shape[0] if X2 is None else np.asarray(X2).shape[0])
+        return np.full(shape, self.variance[0], dtype=np.float64)
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        self.variance.gradient = np.atleast_1d(np.asarray(dL_dK).sum())

@@ -284,3 +284,38 @@ def test_gradients_X(kind, ARD):
         dKxx, dKxz = rng.standard_normal((n, n)), rng.standard_normal((n, m))
         np.testing.assert_allclose(k.gradients_X(dKxx, X), ko.gradients_X(dKxx, X), rtol=1e-9, atol=1e-11)
         np.testing.assert_allclose(k.gradients_X(dKxz, X, Z), ko.gradients_X(dKxz, X, Z), rtol=1e-9, atol=1e-11)
+
+
+def test_combination_and_static_kernels():
+    """GPy/kern/src/add.py:60-86, prod.py:59-110, static.py:63-185 through the mirror: K, gradients and a full
+    GPRegression evaluation (generic inference path: device-built parts + gpx_pdinv) against oracle-built references."""
+    rng = np.random.default_rng(8)
+    X = rng.uniform(-3, 3, (120, 3))
+    Y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((120, 1))
+    k1 = gpy_b200.RBF(3, variance=1.1, lengthscale=[1.0, 1.5, 2.0], ARD=True)
+    k2 = gpy_b200.Matern32(2, variance=0.6, lengthscale=1.3, active_dims=[0, 2])
+    o1 = o.StationaryOracle("rbf", 3, 1.1, [1.0, 1.5, 2.0], True)
+    o2 = o.StationaryOracle("matern32", 2, 0.6, 1.3, False)
+    Xs2 = X[:, [0, 2]]
+    ksum = k1 + k2 + gpy_b200.White(3, variance=0.2) + gpy_b200.Bias(3, variance=0.3)
+    Ksum0 = o1.K(X) + o2.K(Xs2) + 0.2 * np.eye(120) + 0.3
+    assert isinstance(ksum, gpy_b200.Add) and len(ksum.parts) == 4
+    assert rel(ksum.K(X), Ksum0) < 1e-13
+    kprod = k1 * k2
+    assert rel(kprod.K(X), o1.K(X) * o2.K(Xs2)) < 1e-13
+    dL = rng.standard_normal((120, 120))
+    kprod.update_gradients_full(dL, X)
+    v1, l1 = o1.update_gradients_full(dL * o2.K(Xs2), X)
+    v2, l2 = o2.update_gradients_full(dL * o1.K(X), Xs2)
+    np.testing.assert_allclose(k1.variance.gradient, v1, rtol=1e-9)
+    np.testing.assert_allclose(k1.lengthscale.gradient, l1, rtol=1e-9)
+    np.testing.assert_allclose(k2.variance.gradient, v2, rtol=1e-9)
+    np.testing.assert_allclose(k2.lengthscale.gradient, l2, rtol=1e-9)
+    # GPRegression with the sum kernel: LML against a direct dense computation, gradient against finite differences
+    m = gpy_b200.GPRegression(X, Y, ksum, noise_var=0.05)
+    Ky = Ksum0 + (0.05 + 1e-8) * np.eye(120)
+    L = np.linalg.cholesky(Ky)
+    alpha = np.linalg.solve(Ky, Y)
+    lml0 = 0.5 * (-120 * o.LOG_2_PI - 2 * np.log(np.diag(L)).sum() - float(Y.T.dot(alpha)))
+    assert abs(m.log_likelihood() - lml0) < 1e-8
+    assert len(m.gradient) == 1 + 3 + 1 + 1 + 1 + 1 + 1 and m.checkgrad()
