@@ -407,3 +407,102 @@ def logexp_gradfactor(f):
     """d theta / d x for theta = log(1+e^x): 1 - exp(-theta)."""
     f = np.asarray(f, dtype=np.float64)
     return np.where(f > 36.0, 1.0, -np.expm1(-f))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# sparse GP regression: GPy/inference/latent_function_inference/var_dtc.py:66-276 (VarDTC, Gaussian likelihood,
+# homoscedastic noise, certain inputs, no mean function) + the gradient wiring of GPy/core/sparse_gp.py:108-119
+# ----------------------------------------------------------------------------------------------------------
+VARDTC_JITTER = 1e-8  # var_dtc.py:24 const_jitter
+
+
+def backsub_both_sides(L, X, transpose="left"):
+    """GPy/util/linalg.py:381-390: L^-T X L^-1 (transpose='left') or L^-1 X L^-T."""
+    if transpose == "left":
+        tmp, _ = dtrtrs(L, X, lower=1, trans=1)
+        return dtrtrs(L, tmp.T, lower=1, trans=1)[0].T
+    tmp, _ = dtrtrs(L, X, lower=1, trans=0)
+    return dtrtrs(L, tmp.T, lower=1, trans=0)[0].T
+
+
+def vardtc_inference(kern, X, Z, noise_variance, Y):
+    """var_dtc.py:66-215. Returns dict(log_marginal, dL_dKmm, dL_dKdiag, dL_dKnm, dL_dthetaL, woodbury_vector,
+    woodbury_inv, Lm, Kmm)."""
+    num_data, output_dim = Y.shape
+    num_inducing = Z.shape[0]
+    precision = 1.0 / np.fmax(noise_variance, VARDTC_JITTER)  # :79-80
+    beta = precision
+    VVT_factor = precision * Y  # :89
+    trYYT = np.einsum("ij,ij->", Y, Y)  # :37
+    Kmm = kern.K(Z).copy()  # :93
+    diag_add(Kmm, VARDTC_JITTER)  # :94
+    Lm, _ = jitchol(Kmm)  # :95
+    psi0 = kern.Kdiag(X)  # :124
+    psi1 = kern.K(X, Z)  # :126
+    tmp = psi1 * np.sqrt(precision)  # :130
+    tmp, _ = dtrtrs(Lm, tmp.T, lower=1)  # :131
+    A = tdot(tmp)  # :132
+    B = np.eye(num_inducing) + A  # :135
+    LB, _ = jitchol(B)  # :136
+    tmp, _ = dtrtrs(Lm, psi1.T, lower=1, trans=0)  # :139
+    _LBi_Lmi_psi1, _ = dtrtrs(LB, tmp, lower=1, trans=0)  # :140
+    _LBi_Lmi_psi1Vf = np.dot(_LBi_Lmi_psi1, VVT_factor)  # :141
+    tmp, _ = dtrtrs(LB, _LBi_Lmi_psi1Vf, lower=1, trans=1)  # :142
+    Cpsi1Vf, _ = dtrtrs(Lm, tmp, lower=1, trans=1)  # :143
+    delit = tdot(_LBi_Lmi_psi1Vf)  # :148
+    data_fit = np.trace(delit)  # :149
+    DBi_plus_BiPBi = backsub_both_sides(LB, output_dim * np.eye(num_inducing) + delit)  # :150
+    delit = -0.5 * DBi_plus_BiPBi  # :152
+    delit += -0.5 * B * output_dim
+    delit += output_dim * np.eye(num_inducing)
+    dL_dKmm = backsub_both_sides(Lm, delit)  # :156
+    # _compute_dL_dpsi (:217-234), homoscedastic / certain inputs
+    dL_dpsi0 = -0.5 * output_dim * (beta * np.ones([num_data, 1])).flatten()
+    dL_dpsi1 = np.dot(VVT_factor, Cpsi1Vf.T)
+    dL_dpsi2_beta = 0.5 * backsub_both_sides(Lm, output_dim * np.eye(num_inducing) - DBi_plus_BiPBi)
+    dL_dpsi2 = beta * dL_dpsi2_beta
+    dL_dpsi1 += 2.0 * np.dot(psi1, dL_dpsi2)
+    # _compute_log_marginal_likelihood (:265-276)
+    lik_1 = -0.5 * num_data * output_dim * (np.log(2.0 * np.pi) - np.log(beta)) - 0.5 * beta * trYYT
+    lik_2 = -0.5 * output_dim * (np.sum(beta * psi0) - np.trace(A))
+    lik_3 = -output_dim * (np.sum(np.log(np.diag(LB))))
+    lik_4 = 0.5 * data_fit
+    log_marginal = lik_1 + lik_2 + lik_3 + lik_4
+    # _compute_dL_dR (:237-263), homoscedastic
+    dL_dR = -0.5 * num_data * output_dim * beta + 0.5 * trYYT * beta ** 2
+    dL_dR += 0.5 * output_dim * (psi0.sum() * beta ** 2 - np.trace(A) * beta)
+    dL_dR += beta * (0.5 * np.sum(A * DBi_plus_BiPBi) - data_fit)
+    # posterior (:201-214)
+    Bi = -dpotri(LB, lower=1)[0]
+    diag_add(Bi, 1)
+    woodbury_inv = backsub_both_sides(Lm, Bi)
+    return dict(log_marginal=float(log_marginal), dL_dKmm=dL_dKmm, dL_dKdiag=dL_dpsi0, dL_dKnm=dL_dpsi1,
+                dL_dthetaL=float(np.sum(dL_dR)), woodbury_vector=Cpsi1Vf, woodbury_inv=woodbury_inv, Lm=Lm, Kmm=Kmm)
+
+
+def sparse_eval(X, Y, Z, kind, ARD, variance, lengthscale, noise_variance):
+    """One SparseGP.parameters_changed() (GPy/core/sparse_gp.py:76-119): returns (log_marginal,
+    grad [kern.variance, kern.lengthscale.., Gaussian_noise.variance], Z.gradient, res)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    kern = StationaryOracle(kind, X.shape[1], variance, lengthscale, ARD)
+    res = vardtc_inference(kern, X, Z, noise_variance, Y)
+    dv0, dl0 = kern.update_gradients_diag(res["dL_dKdiag"], X)  # sparse_gp.py:110
+    dv1, dl1 = kern.update_gradients_full(res["dL_dKnm"], X, Z)  # :112
+    dv2, dl2 = kern.update_gradients_full(res["dL_dKmm"], Z, None)  # :114
+    dvar = dv0 + dv1 + dv2
+    dlen = np.atleast_1d(dl0) + np.atleast_1d(dl1) + np.atleast_1d(dl2)
+    Zgrad = kern.gradients_X(res["dL_dKmm"], Z)  # :117
+    Zgrad = Zgrad + kern.gradients_X(res["dL_dKnm"].T, Z, X)  # :118
+    grad = np.concatenate([[dvar], dlen, [res["dL_dthetaL"]]])
+    return res["log_marginal"], grad, Zgrad, res
+
+
+def sparse_raw_predict(kern, Z, woodbury_vector, woodbury_inv, Xnew):
+    """posterior.py:238-270 (Posterior._raw_predict with woodbury_inv, 2-D): mu = Kx^T wv, var = Kxx - sum(Kx*(Wi Kx))."""
+    Kx = kern.K(Z, Xnew)
+    mu = np.dot(Kx.T, woodbury_vector)
+    Kxx = kern.Kdiag(Xnew)
+    var = (Kxx - np.sum(np.dot(woodbury_inv.T, Kx) * Kx, 0))[:, None]
+    return mu, var

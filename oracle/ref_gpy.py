@@ -83,7 +83,9 @@ def load():
     stat = importlib.import_module("GPy.kern.src.stationary")
     egi = importlib.import_module("GPy.inference.latent_function_inference.exact_gaussian_inference")
     gauss = importlib.import_module("GPy.likelihoods.gaussian")
+    vdtc = importlib.import_module("GPy.inference.latent_function_inference.var_dtc")
     ns = types.SimpleNamespace(
+        VarDTC=vdtc.VarDTC,
         RBF=rbf.RBF, Exponential=stat.Exponential, Matern32=stat.Matern32, Matern52=stat.Matern52,
         ExactGaussianInference=egi.ExactGaussianInference, Gaussian=gauss.Gaussian,
         linalg=sys.modules["GPy.util.linalg"], diag=sys.modules["GPy.util.diag"], stationary=stat,
@@ -116,3 +118,32 @@ def evaluate(G, X, Y, kind, ARD, variance, lengthscale, noise, Xnew=None):
         mu, var = lik.predictive_values(mu, var)                                  # gaussian.py:102-110
         out["mu"], out["var"] = np.asarray(mu), np.asarray(var)
     return out
+
+
+def evaluate_sparse(G, X, Y, Z, kind, ARD, variance, lengthscale, noise):
+    """One SparseGP.parameters_changed() with the reference's own VarDTC / kernel / likelihood objects; the gradient
+    wiring restates GPy/core/sparse_gp.py:108-119 (certain inputs)."""
+    import numpy as np
+    D = X.shape[1]
+    kern = getattr(G, KERNELS[kind])(D, variance=variance, lengthscale=lengthscale, ARD=ARD)
+    lik = G.Gaussian(variance=noise)
+    inf = G.VarDTC(limit=3)
+    post, lml, gd = inf.inference(kern, X, Z, lik, Y)                             # sparse_gp.py:77-80
+
+    def kgrad():
+        return np.concatenate([np.atleast_1d(kern.variance.gradient).reshape(-1),
+                               np.atleast_1d(kern.lengthscale.gradient).reshape(-1) * np.ones(kern.lengthscale.size)])
+
+    lik.update_gradients(gd["dL_dthetaL"])                                         # :84
+    kern.update_gradients_diag(gd["dL_dKdiag"], X)                                 # :110
+    kerngrad = kgrad().copy()
+    kern.update_gradients_full(gd["dL_dKnm"], X, Z)                                # :112
+    kerngrad += kgrad()
+    kern.update_gradients_full(gd["dL_dKmm"], Z, None)                             # :114
+    kerngrad += kgrad()
+    Zgrad = kern.gradients_X(gd["dL_dKmm"], Z)                                     # :117
+    Zgrad = Zgrad + kern.gradients_X(gd["dL_dKnm"].T, Z, X)                        # :118
+    grad = np.concatenate([kerngrad, np.atleast_1d(lik.variance.gradient).reshape(-1)])
+    return dict(lml=float(np.squeeze(lml)), grad=grad, Zgrad=np.asarray(Zgrad), woodbury_vector=np.asarray(post.woodbury_vector),
+                woodbury_inv=np.asarray(post.woodbury_inv), dL_dKmm=np.asarray(gd["dL_dKmm"]),
+                dL_dKnm=np.asarray(gd["dL_dKnm"]))

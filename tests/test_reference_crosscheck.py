@@ -86,3 +86,23 @@ def test_oracle_gradients_X_equals_reference(G):
             d1, d2 = rng.standard_normal((60, 60)), rng.standard_normal((60, 25))
             np.testing.assert_allclose(ko.gradients_X(d1, X), kr.gradients_X(d1, X), rtol=1e-12, atol=1e-14)
             np.testing.assert_allclose(ko.gradients_X(d2, X, Z), kr.gradients_X(d2, X, Z), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern32", "exponential"])
+@pytest.mark.parametrize("ARD", [False, True])
+def test_oracle_vardtc_equals_reference(G, kind, ARD):
+    """Sparse GP regression: oracle.vardtc_inference / sparse_eval against the unmodified
+    GPy/inference/latent_function_inference/var_dtc.py (+ gradient wiring of core/sparse_gp.py:108-119)."""
+    from oracle import ref_gpy
+    X, Y = o.synthetic(300, 3, 4)
+    rng = np.random.default_rng(4)
+    Z = X[rng.permutation(300)[:20]].copy()
+    ls = np.array([1.2, 1.7, 2.1]) if ARD else 1.6
+    r = ref_gpy.evaluate_sparse(G, X, Y, Z, kind, ARD, 1.3, ls, 0.07)
+    lml, g, Zg, res = o.sparse_eval(X, Y, Z, kind, ARD, 1.3, ls, 0.07)
+    assert abs(lml - r["lml"]) <= 1e-9 * abs(r["lml"])
+    np.testing.assert_allclose(g, r["grad"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(Zg, r["Zgrad"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(res["woodbury_vector"], r["woodbury_vector"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(res["woodbury_inv"], r["woodbury_inv"], rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(res["dL_dKnm"], r["dL_dKnm"], rtol=1e-8, atol=1e-12)
