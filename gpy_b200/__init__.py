@@ -11,5 +11,6 @@ from .kern import (RBF, Exponential, Matern32, Matern52, Stationary, DeviceGradi
                    Kern, CombinationKernel)
 from .inference import ExactGaussianInference, Gaussian, PosteriorExact  # noqa: F401
 from .model import GP, GPRegression  # noqa: F401
+from .sparse import SparseGPRegression, VarDTC  # noqa: F401
 
 __version__ = "0.1.0"

@@ -57,7 +57,7 @@ static long pick_nb(const gpx_ctx* c) {
   return std::min<long>(256, c->Npad);
 }
 
-static int fill_kp(KernParams& kp, int kind, int ard, int D, double variance, const double* ls) {
+int gpx::fill_kp(KernParams& kp, int kind, int ard, int D, double variance, const double* ls) {
   if (kind < 0 || kind > 3) GPX_FAIL("unknown kernel kind");
   if (D < 1 || D > MAX_D) GPX_FAIL("input dimension must be in [1, 64]");
   if (!(variance > 0)) GPX_FAIL("variance must be positive");
@@ -109,6 +109,7 @@ int gpx_destroy(gpx_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   dist_free(c);
+  sparse_free(c);
   free_data(c);
   for (auto e : c->ev) cudaEventDestroy(e);
   for (auto e : c->sync_ev) cudaEventDestroy(e);

@@ -135,6 +135,7 @@ struct GemmParams {
   int rlow;     // UPDATE: rows [0, rlow) above the trailing part take part (upper, inverse region)
   int skip0, skip1;  // PANEL: row tiles [skip0, skip1) (the diagonal block) are skipped
   int tri;      // PANEL: B is lower triangular -> k range of output column tile c' is [0, (c'+1)*TILE)
+  int plain;    // PANEL entry used as a general C = A B^T over nt x ncols tiles (super-block schedule); 2 = lower tiles only
   // LAUUM epilogue (fused gradient reductions)
   const double* XsT;    // scaled inputs, SoA [D][ldx]
   const double* sq;     // squared norms of scaled inputs [ldx]

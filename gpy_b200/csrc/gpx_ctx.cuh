@@ -5,6 +5,7 @@
 #include "gpx_common.cuh"
 
 struct DistState;
+struct SparseState;
 
 struct gpx_ctx {
   int device = 0;
@@ -50,6 +51,7 @@ struct gpx_ctx {
   std::vector<cudaEvent_t> ev;
   int profile = 1;
   struct DistState* dist = nullptr;   // multi-GPU state (gpx_dist.cu), null on a single GPU
+  struct SparseState* sparse = nullptr;   // sparse-GP (VarDTC) state (gpx_sparse.cu)
 };
 
 
@@ -60,4 +62,6 @@ GemmParams gemm_defaults();
 int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y, int P);
 int dist_exact_eval(gpx_ctx* c, double extra_jitter);
 void dist_free(gpx_ctx* c);
+void sparse_free(gpx_ctx* c);
+int fill_kp(KernParams& kp, int kind, int ard, int D, double variance, const double* ls);
 }  // namespace gpx

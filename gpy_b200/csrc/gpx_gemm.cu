@@ -88,6 +88,12 @@ __device__ __forceinline__ bool decode_tile(const GemmParams& p, int& r, int& c)
     r = R * SB + t / SB;
     c = C * SB + t % SB;
     return r < p.nt && c <= r;
+  } else if (p.plain) {  // general product: 1-D grid, SB x SB super-blocks over (row tiles nt) x (column tiles ncols)
+    const int sbcols = (p.ncols + SB - 1) / SB;
+    const int sb = blockIdx.x / (SB * SB), t = blockIdx.x % (SB * SB);
+    r = (sb / sbcols) * SB + t / SB;
+    c = (sb % sbcols) * SB + t % SB;
+    return r < p.nt && c < p.ncols && !(p.plain == 2 && r < c);
   } else {  // GEMM_PANEL: 2-D grid (output column tile, row slot); triangular B: longest k-range first
     c = p.tri ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
     const int slot = blockIdx.y;
@@ -361,6 +367,8 @@ int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t st) {
     const int ncols = p.ncols > 0 ? p.ncols : p.nt - p.c0, nslots = p.rlow + (p.nt - p.c0);
     if (ncols <= 0) return 0;
     grid = dim3((unsigned)(((nslots + SB - 1) / SB) * ((ncols + SB - 1) / SB) * SB * SB), 1, 1);
+  } else if (p.mode == GEMM_PANEL && p.plain) {
+    grid = dim3((unsigned)(((p.nt + SB - 1) / SB) * ((p.ncols + SB - 1) / SB) * SB * SB), 1, 1);
   } else if (p.mode == GEMM_LAUUM) {
     const int nsr = (p.nt + SB - 1) / SB;
     grid = dim3((unsigned)(nsr * (nsr + 1) / 2 * SB * SB), 1, 1);

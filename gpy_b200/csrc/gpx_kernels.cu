@@ -773,6 +773,38 @@ int launch_extract(int which, const double* S, long ld, const double* Ldiag, con
   return 0;
 }
 
+// out[p][c] = sum_r A[r + c*ld] * Y[p*ldy + r]  for a tall column-major A (rows x cols): one warp per column
+__global__ void __launch_bounds__(256) col_dot_kernel(const double* __restrict__ A, long ld, long rows, long cols, int P,
+                                                      const double* __restrict__ Y, long ldy, double* __restrict__ out,
+                                                      long ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long col = (long)blockIdx.x * 8 + warp;
+  if (col >= cols) return;
+  const double* a = A + col * ld;
+  double acc[MAX_P];
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+#pragma unroll 4
+  for (long r = lane; r < rows; r += 32) {
+    const double x = a[r];
+#pragma unroll
+    for (int q = 0; q < MAX_P; q++)
+      if (q < P) acc[q] = fma(x, Y[(long)q * ldy + r], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++)
+    if (q < P) {
+      const double s = warp_sum(acc[q]);
+      if (lane == 0) out[(long)q * ldo + col] = s;
+    }
+}
+int launch_col_dot(const double* A, long ld, long rows, long cols, int P, const double* Y, long ldy, double* out, long ldo,
+                   cudaStream_t st) {
+  col_dot_kernel<<<(unsigned)((cols + 7) / 8), 256, 0, st>>>(A, ld, rows, cols, P, Y, ldy, out, ldo);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // gpx_pdinv: dense symmetric A (N x N, ld = N) -> factor workspace (lower tiles + jitter on the diagonal, zero upper
 // tiles, identity padding), and the mean of its diagonal / any non-positive diagonal entry for the jitchol rules.
 __global__ void load_sym_kernel(const double* __restrict__ A, long N, double* __restrict__ S, long ld, double jitter) {
@@ -845,6 +877,7 @@ __global__ void __launch_bounds__(256) grad_full_kernel(GradFullParams p) {
   double gvar = 0.0, giso = 0.0;
   // ARD accumulators live in shared memory per thread column to keep registers bounded: loop q outermost instead
   const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  const long ldd = p.ldd > 0 ? p.ldd : p.M;
   // pass 1: variance + iso lengthscale, and (ARD) nothing cached: recompute per q (D small) — simple and exact
   for (int qq = -1; qq < (p.kp.ard ? D : 0); qq++) {
     double gq = 0.0;
@@ -860,7 +893,8 @@ __global__ void __launch_bounds__(256) grad_full_kernel(GradFullParams p) {
       const double rr = sqrt(r2) * inv_ls;
       double k, dk;
       k_dk_of_r_unit(p.kp.kind, rr, k, dk);
-      const double dl = p.dL_dK[gi * p.M + gj];
+      double dl = p.dL_dK[gi * ldd + gj];
+      for (int cp = 0; cp < p.cP; cp++) dl = fma(p.ci[(long)cp * p.ldci + gi], p.cj[(long)cp * p.ldcj + gj], dl);
       const double G = variance * dk * dl;
       if (qq < 0) {
         gvar = fma(k, dl, gvar);
@@ -929,12 +963,31 @@ __global__ void __launch_bounds__(TILE) gradx_kernel(GradFullParams p, long mchu
   for (int q = 0; q < DREG; q++) { xn[q] = (q < D && n < p.N) ? p.x1T[(long)q * p.ld1 + n] : 0.0; acc[q] = 0.0; }
   const double sn = n < p.N ? p.sq1[n] : 0.0;
   const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  const long ldd = p.ldd > 0 ? p.ldd : p.M;
   for (long m0 = m_beg; m0 < m_end; m0 += 32) {
     __syncthreads();
-    // dL_dK tile rows [n-tile], cols [m0, m0+32): warp w loads rows w, w+4, ... (32 doubles = 256 B per row)
-    for (int rr = tid >> 5; rr < TILE; rr += TILE / 32) {
-      const long gn = (long)blockIdx.x * TILE + rr, gm = m0 + (tid & 31);
-      sdl[rr][tid & 31] = (gn < p.N && gm < m_end) ? p.dL_dK[gn * p.M + gm] : 0.0;
+    if (!p.transposed) {
+      // dL_dK tile rows [n-tile], cols [m0, m0+32): warp w loads rows w, w+4, ... (32 doubles = 256 B per row)
+      for (int rr = tid >> 5; rr < TILE; rr += TILE / 32) {
+        const long gn = (long)blockIdx.x * TILE + rr, gm = m0 + (tid & 31);
+        double dv = 0.0;
+        if (gn < p.N && gm < m_end) {
+          dv = p.dL_dK[gn * ldd + gm];
+          for (int cp = 0; cp < p.cP; cp++) dv = fma(p.ci[(long)cp * p.ldci + gn], p.cj[(long)cp * p.ldcj + gm], dv);
+        }
+        sdl[rr][tid & 31] = dv;
+      }
+    } else {
+      // transposed storage: element (n, m) at dL_dK[m*ldd + n] -> each thread fills its own row, coalesced along n
+      for (int mm = 0; mm < 32; mm++) {
+        const long gm = m0 + mm;
+        double dv = 0.0;
+        if (n < p.N && gm < m_end) {
+          dv = p.dL_dK[gm * ldd + n];
+          for (int cp = 0; cp < p.cP; cp++) dv = fma(p.ci[(long)cp * p.ldci + n], p.cj[(long)cp * p.ldcj + gm], dv);
+        }
+        sdl[tid][mm] = dv;
+      }
     }
     for (int idx = tid; idx < D * 32; idx += TILE) {
       const int q = idx >> 5, mm = idx & 31;
@@ -957,7 +1010,7 @@ __global__ void __launch_bounds__(TILE) gradx_kernel(GradFullParams p, long mchu
         double kk, dk;
         k_dk_of_r_unit(p.kp.kind, rr, kk, dk);
         double dl = sdl[tid][mm];
-        if (p.same) dl += p.dL_dK[gm * p.M + n];          // tmp + tmp^T (stationary.py:343-345); coalesced along n
+        if (p.same) dl += p.dL_dK[gm * ldd + n];            // tmp + tmp^T (stationary.py:343-345); coalesced along n
         const double t = (rr != 0.0) ? variance * dk * dl / rr : 0.0;
 #pragma unroll
         for (int q = 0; q < DREG; q++)

@@ -28,7 +28,11 @@ struct FinalizeParams {
 struct GradFullParams {
   const double* x1T; long ld1; const double* sq1; long N;   // X  (index i, rows of dL_dK)
   const double* x2T; long ld2; const double* sq2; long M;   // X2 (index j, contiguous in dL_dK)
-  const double* dL_dK;                                       // N x M row-major
+  const double* dL_dK;                                       // N x M row-major (row stride ldd, 0 -> M)
+  long ldd;
+  int transposed;                                            // gradx only: element (n, m) is read at dL_dK[m*ldd + n]
+  // optional rank-P correction added on the fly: dL(i, j) += sum_p ci[p*ldci + i] * cj[p*ldcj + j]
+  const double* ci; long ldci; const double* cj; long ldcj; int cP;
   int same;
   double* partials;
   KernParams kp;
@@ -54,6 +58,8 @@ int launch_extract(int which, const double* S, long ld, const double* Ldiag, con
 int launch_transpose_pad(const double* in, long n, int p, long ld, double* out, cudaStream_t st);
 int launch_untranspose(const double* in, long n, int p, long ld, double* out, cudaStream_t st);
 int launch_gradx(const GradFullParams& p, int nchunk, long mchunk, double* part, double* out, cudaStream_t st);
+int launch_col_dot(const double* A, long ld, long rows, long cols, int P, const double* Y, long ldy, double* out, long ldo,
+                   cudaStream_t st);
 int launch_load_sym(const double* A, long N, double* S, long ld, double jitter, cudaStream_t st);
 int measure_dmma_peak(cudaStream_t st, double* tflops);
 int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStream_t st);

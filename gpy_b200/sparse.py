@@ -1,0 +1,251 @@
+"""Host-side mirror of GPy's sparse GP regression (VarDTC), computing the N-dependent work on the B200.
+
+Mirrors:
+    GPy.inference.latent_function_inference.VarDTC.inference   GPy/inference/latent_function_inference/var_dtc.py:66-215
+    GPy.core.SparseGP.parameters_changed / _update_gradients   GPy/core/sparse_gp.py:76-119
+    GPy.models.SparseGPRegression                              GPy/models/sparse_gp_regression.py:33-59
+(Gaussian likelihood, homoscedastic noise, certain inputs, no mean function — BASELINE.json configs[4].)
+
+Split of the work: psi1 = K(X, Z) (8 N M bytes), G = psi1^T psi1, psi1^T Y, dL_dKnm = (beta Y) C^T + 2 psi1 dL_dpsi2 and
+its reductions to kernel / inducing-point gradients all live on the device (gpx_sparse_*: nothing of size N crosses PCIe
+except X and Y once). What is left are M x M objects (M = number of inducing points): two Cholesky factors + inverses
+(gpx_pdinv on the device) and a handful of M x M products / traces, which are NumPy on the host here — the reference does
+them with LAPACK triangular solves; with the explicit triangular inverses returned by the device they become products.
+"""
+import numpy as np
+
+from . import _ffi
+from .inference import Gaussian, _fingerprint
+from .kern import RBF, Stationary
+from .param import Logexp, Param, Parameterized
+
+CONST_JITTER = 1e-8  # var_dtc.py:24
+
+
+class SparsePosterior(object):
+    """Posterior(woodbury_inv, woodbury_vector, K=Kmm, K_chol=Lm) (var_dtc.py:213; posterior.py:238-270)."""
+
+    def __init__(self, woodbury_inv, woodbury_vector, K, K_chol):
+        self.woodbury_inv, self.woodbury_vector, self.K, self.K_chol = woodbury_inv, woodbury_vector, K, K_chol
+
+    def _raw_predict(self, kern, Xnew, pred_var, full_cov=False):
+        """posterior.py:238-270 with pred_var = Z (sparse_gp.py:52-54)."""
+        Kx = kern.K(pred_var, Xnew)
+        mu = np.dot(Kx.T, self.woodbury_vector)
+        if full_cov:
+            return mu, kern.K(Xnew) - np.dot(Kx.T, np.dot(self.woodbury_inv, Kx))
+        return mu, (kern.Kdiag(Xnew) - np.sum(np.dot(self.woodbury_inv.T, Kx) * Kx, 0))[:, None]
+
+
+class VarDTC(object):
+    """Drop-in for GPy's VarDTC: inference(kern, X, Z, likelihood, Y) -> (posterior, log_marginal, grad_dict).
+    `grad_dict['dL_dKnm']` is never materialised (N x M); instead the dict carries the already-reduced contributions
+    `Knm_dvariance`, `Knm_dlengthscale`, `Knm_dZ`, which SparseGP._update_gradients adds (sparse_gp.py:112,118)."""
+
+    const_jitter = CONST_JITTER
+
+    def __init__(self, device=0, engine=None, limit=1):
+        self.device, self._engine, self._data_key = device, engine, None
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = _ffi.Engine(self.device)
+        return self._engine
+
+    def on_optimization_start(self):
+        pass
+
+    def on_optimization_end(self):
+        pass
+
+    def invalidate_data(self):
+        self._data_key = None
+
+    def inference(self, kern, X, Z, likelihood, Y, Y_metadata=None, mean_function=None, precision=None):
+        if mean_function is not None:
+            raise NotImplementedError("sparse GP with a mean function is not on the accelerated path")
+        if not isinstance(kern, Stationary):
+            raise TypeError("gpy_b200.VarDTC accelerates gpy_b200.kern stationary kernels")
+        eng = self.engine
+        Xs = kern._slice_X(X)
+        Zs = kern._slice_X(Z)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        key = (_fingerprint(Xs), _fingerprint(Y))
+        if key != self._data_key:
+            eng.sparse_set_data(Xs, Y)
+            self._data_key = key
+        num_data, output_dim = Y.shape
+        num_inducing = Zs.shape[0]
+        kind, ard, var, ls = kern._theta()
+        if precision is None:
+            precision = 1.0 / np.fmax(float(np.squeeze(np.asarray(likelihood.gaussian_variance(Y_metadata)))),
+                                      self.const_jitter)                                   # var_dtc.py:79-80
+        beta = float(precision)
+        trYYT = float(np.einsum("ij,ij->", Y, Y))                                           # :37,90
+        # ---- device: psi1 statistics ---------------------------------------------------------------------------
+        G, psi1tY = eng.sparse_stats(kind, ard, var, ls, Zs)                                # psi1^T psi1, psi1^T Y
+        psi0_sum = var * num_data                                                           # sum(Kdiag(X)), :124
+        # ---- M x M: Kmm, Lm, Lm^-1 (device) ------------------------------------------------------------------------
+        Kmm = kern.K(Z)
+        Kmm = Kmm + np.eye(num_inducing) * self.const_jitter                                # :93-94
+        _, Lm, Lmi, _, _ = _ffi.pdinv(Kmm, maxtries=5, want=("L", "Li"))                    # :95 jitchol (+ inverse)
+        A = beta * Lmi.dot(G).dot(Lmi.T)                                                    # :130-132
+        B = np.eye(num_inducing) + A                                                        # :135
+        _, LB, LBi, _, _ = _ffi.pdinv(B, maxtries=5, want=("L", "Li"))                      # :136
+        psi1Vf = beta * psi1tY                                                              # psi1^T VVT_factor
+        LBi_Lmi = LBi.dot(Lmi)
+        _LBi_Lmi_psi1Vf = LBi_Lmi.dot(psi1Vf)                                               # :139-141
+        Cpsi1Vf = LBi_Lmi.T.dot(_LBi_Lmi_psi1Vf)                                            # :142-143
+        delit = _LBi_Lmi_psi1Vf.dot(_LBi_Lmi_psi1Vf.T)                                      # :148
+        data_fit = np.trace(delit)                                                          # :149
+        DBi_plus_BiPBi = LBi.T.dot(output_dim * np.eye(num_inducing) + delit).dot(LBi)      # :150 backsub_both_sides
+        delit = -0.5 * DBi_plus_BiPBi - 0.5 * B * output_dim + output_dim * np.eye(num_inducing)   # :152-154
+        dL_dKmm = Lmi.T.dot(delit).dot(Lmi)                                                 # :156
+        dL_dpsi2 = beta * 0.5 * Lmi.T.dot(output_dim * np.eye(num_inducing) - DBi_plus_BiPBi).dot(Lmi)   # :221,231
+        # ---- device: dL_dKnm = VVT C^T + 2 psi1 dL_dpsi2 reduced to parameter / inducing-point gradients -----------
+        W2 = 2.0 * dL_dpsi2
+        W2 = 0.5 * (W2 + W2.T)
+        knm_dvar, knm_dls, knm_dZ = eng.sparse_grads(W2, Cpsi1Vf, beta)
+        # ---- bound and noise gradient (:237-276, homoscedastic) ------------------------------------------------------
+        trA = np.trace(A)
+        lik_1 = -0.5 * num_data * output_dim * (np.log(2.0 * np.pi) - np.log(beta)) - 0.5 * beta * trYYT
+        lik_2 = -0.5 * output_dim * (beta * psi0_sum - trA)
+        lik_3 = -output_dim * np.sum(np.log(np.diag(LB)))
+        lik_4 = 0.5 * data_fit
+        log_marginal = float(lik_1 + lik_2 + lik_3 + lik_4)
+        dL_dR = -0.5 * num_data * output_dim * beta + 0.5 * trYYT * beta ** 2
+        dL_dR += 0.5 * output_dim * (psi0_sum * beta ** 2 - trA * beta)
+        dL_dR += beta * (0.5 * np.sum(A * DBi_plus_BiPBi) - data_fit)
+        # ---- posterior (:201-214) --------------------------------------------------------------------------------
+        Bi = np.eye(num_inducing) - LBi.T.dot(LBi)                                          # -dpotri(LB) + I
+        woodbury_inv = Lmi.T.dot(Bi).dot(Lmi)
+        post = SparsePosterior(woodbury_inv, Cpsi1Vf, Kmm, Lm)
+        grad_dict = {"dL_dKmm": dL_dKmm, "dL_dKdiag_value": -0.5 * output_dim * beta, "num_data": num_data,
+                     "Knm_dvariance": knm_dvar, "Knm_dlengthscale": knm_dls, "Knm_dZ": knm_dZ,
+                     "dL_dthetaL": float(dL_dR)}
+        return post, log_marginal, grad_dict
+
+
+class SparseGPRegression(Parameterized):
+    """GPy.models.SparseGPRegression (sparse_gp_regression.py:33-59) / GPy.core.SparseGP (sparse_gp.py:38-119).
+    Parameter (and gradient) order as in the reference: [inducing inputs, kern.variance, kern.lengthscale, noise]."""
+
+    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, device=0, engine=None, name="sparse_gp"):
+        super(SparseGPRegression, self).__init__(name)
+        X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64)
+        num_data, input_dim = X.shape
+        if kernel is None:
+            kernel = RBF(input_dim)                                            # sparse_gp_regression.py:36-37
+        if Z is None:
+            i = np.random.permutation(num_data)[:min(num_inducing, num_data)]  # :41-43
+            Z = X[i].copy()
+        else:
+            assert Z.shape[1] == input_dim
+        self.X, self.Y = X, Y
+        self.kern = kernel
+        self.likelihood = Gaussian()                                            # :47
+        self.Z = Param("inducing inputs", np.array(Z, dtype=np.float64), transform=None)
+        self.Z.values = np.array(Z, dtype=np.float64)                          # keep the M x D shape
+        self.Z.gradient = np.zeros_like(self.Z.values)
+        self.num_inducing = self.Z.values.shape[0]
+        self.inference_method = VarDTC(device=device, engine=engine)
+        self.link_parameter(self.Z)                                            # sparse_gp.py:61 (index 0)
+        self.link_parameter(self.kern)
+        self.link_parameter(self.likelihood)
+        self.parameters_changed()
+
+    # ---- one evaluation: sparse_gp.py:76-119 ------------------------------------------------------------------------
+    def parameters_changed(self):
+        Z = self.Z.values
+        self.posterior, self._log_marginal_likelihood, gd = self.inference_method.inference(
+            self.kern, self.X, Z, self.likelihood, self.Y)
+        self.grad_dict = gd
+        self.likelihood.update_gradients(gd["dL_dthetaL"])                                     # :84
+        # kern.update_gradients_diag(dL_dKdiag, X) (:110): variance.gradient = sum(dL_dKdiag), lengthscale 0
+        kv = gd["dL_dKdiag_value"] * gd["num_data"]
+        kl = np.zeros(self.kern.lengthscale.size)
+        kv += gd["Knm_dvariance"]                                                                # :112 (device-reduced)
+        kl = kl + gd["Knm_dlengthscale"]
+        self.kern.update_gradients_full(gd["dL_dKmm"], Z, None)                                  # :114
+        self.kern.variance.gradient = np.atleast_1d(self.kern.variance.gradient + kv)
+        self.kern.lengthscale.gradient = np.atleast_1d(self.kern.lengthscale.gradient) + kl
+        self.Z.gradient = self.kern.gradients_X(gd["dL_dKmm"], Z) + gd["Knm_dZ"]                # :117-118
+
+    def log_likelihood(self):
+        return self._log_marginal_likelihood
+
+    def objective_function(self):
+        return -float(self._log_marginal_likelihood)
+
+    # ---- optimizer space: Z unconstrained, the positive parameters through Logexp ---------------------------------------
+    def _flat(self):
+        return [self.Z, self.kern.variance, self.kern.lengthscale, self.likelihood.variance]
+
+    @property
+    def optimizer_array(self):
+        out = [self.Z.values.reshape(-1)]
+        for p in self._flat()[1:]:
+            out.append(Logexp.finv(p.values).reshape(-1))
+        return np.concatenate(out)
+
+    @optimizer_array.setter
+    def optimizer_array(self, x):
+        nz = self.Z.values.size
+        self.Z.values[...] = x[:nz].reshape(self.Z.values.shape)
+        i = nz
+        for p in self._flat()[1:]:
+            p.values[...] = Logexp.f(x[i:i + p.size]).reshape(p.values.shape)
+            i += p.size
+        self.parameters_changed()
+
+    def _grads_transformed(self):
+        g = [np.asarray(self.Z.gradient).reshape(-1)]
+        for p in self._flat()[1:]:
+            g.append(np.asarray(p.gradient, dtype=np.float64).reshape(-1) * Logexp.gradfactor(p.values).reshape(-1))
+        return -np.concatenate(g)
+
+    def optimize(self, max_iters=1000, messages=False):
+        from scipy.optimize import fmin_l_bfgs_b
+        self.n_evals = 0
+
+        def fg(x):
+            self.n_evals += 1
+            self.optimizer_array = x
+            return self.objective_function(), self._grads_transformed()
+
+        x, f, d = fmin_l_bfgs_b(fg, self.optimizer_array, maxfun=max_iters, maxiter=max_iters)
+        self.optimizer_array = x
+        d["n_evals"] = self.n_evals
+        return d
+
+    def checkgrad(self, step=1e-6, tolerance=1e-3, sample=12, seed=0):
+        """finite differences on the kernel / noise parameters and on a random sample of inducing-point coordinates."""
+        x = self.optimizer_array.copy()
+        self.optimizer_array = x
+        g = self._grads_transformed()
+        nz = self.Z.values.size
+        rng = np.random.default_rng(seed)
+        idx = np.concatenate([rng.choice(nz, size=min(sample, nz), replace=False), np.arange(nz, x.size)])
+        ok = True
+        for i in idx:
+            xp, xm = x.copy(), x.copy()
+            xp[i] += step
+            xm[i] -= step
+            self.optimizer_array = xp
+            fp = self.objective_function()
+            self.optimizer_array = xm
+            fm = self.objective_function()
+            num = (fp - fm) / (2 * step)
+            if not (abs(num - g[i]) <= tolerance * max(abs(num), 1e-2)):
+                ok = False
+        self.optimizer_array = x
+        return ok
+
+    def predict(self, Xnew, full_cov=False, include_likelihood=True):
+        """gp.py:290-365 with the sparse posterior (predictive variable = Z)."""
+        mu, var = self.posterior._raw_predict(self.kern, np.asarray(Xnew, dtype=np.float64), self.Z.values, full_cov)
+        if include_likelihood:
+            mu, var = self.likelihood.predictive_values(mu, var, full_cov)
+        return mu, var

@@ -98,6 +98,22 @@ int gpx_kern_grad_X(gpx_ctx* ctx, int kind, int ard, double variance, const doub
 int gpx_pdinv(gpx_ctx* ctx, const double* A, int64_t N, int max_tries, double* Ai, double* L, double* Li, double* logdet,
               double* jitter_used);
 
+/* Sparse GP regression (VarDTC): the N-dependent work of GPy/inference/latent_function_inference/var_dtc.py:66-215 and of
+ * the gradient wiring GPy/core/sparse_gp.py:108-119 (Gaussian likelihood, homoscedastic, certain inputs). psi1 = K(X, Z)
+ * (8 N M bytes) is built and kept in HBM; only M x M / M x P / M x D results cross PCIe.
+ *   gpx_sparse_set_data : X (N x D row-major), Y (N x P row-major) -> HBM (no N x N workspace is allocated).
+ *   gpx_sparse_stats    : G = psi1^T psi1 (M x M, symmetric, fully populated) and psi1^T Y (M x P row-major); with
+ *                         Lm = chol(Kmm): A = beta Lm^-1 G Lm^-T (var_dtc.py:130-132), psi1Vf = beta psi1^T Y (:141).
+ *   gpx_sparse_grads    : dL_dKnm = (beta Y) C^T + psi1 W2 (var_dtc.py:219-234 with C = Cpsi1Vf, W2 = 2 dL_dpsi2,
+ *                         symmetric) is formed on the device and reduced to the kernel-parameter gradients of
+ *                         kern.update_gradients_full(dL_dKnm, X, Z) (sparse_gp.py:112) and to
+ *                         kern.gradients_X(dL_dKnm^T, Z, X) (sparse_gp.py:118; dZ is M x D row-major). */
+int gpx_sparse_set_data(gpx_ctx* ctx, const double* X, int64_t N, int D, const double* Y, int P);
+int gpx_sparse_stats(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                     int64_t M, double* G, double* psi1tY);
+int gpx_sparse_grads(gpx_ctx* ctx, const double* W2, const double* C, double beta, double* dvariance,
+                     double* dlengthscale, double* dZ);
+
 /* Measurement hooks (bench.py): device time of the last eval between CUDA events on the launching stream, the number
  * of kernels this library launched since creation, and per-phase accounting of the last eval. */
 typedef struct {

@@ -319,3 +319,35 @@ def test_combination_and_static_kernels():
     lml0 = 0.5 * (-120 * o.LOG_2_PI - 2 * np.log(np.diag(L)).sum() - float(Y.T.dot(alpha)))
     assert abs(m.log_likelihood() - lml0) < 1e-8
     assert len(m.gradient) == 1 + 3 + 1 + 1 + 1 + 1 + 1 and m.checkgrad()
+
+
+@pytest.mark.parametrize("kind,ARD,N,M,D,P", [("rbf", True, 700, 40, 3, 1), ("matern52", False, 1500, 300, 4, 2),
+                                               ("exponential", True, 2100, 129, 2, 1), ("matern32", True, 600, 600, 5, 1)])
+def test_sparse_gp_vardtc(kind, ARD, N, M, D, P):
+    """Sparse GP regression (VarDTC, GPy/inference/latent_function_inference/var_dtc.py:66-215 + core/sparse_gp.py:108-119)
+    through the mirror: bound, kernel / noise gradients, inducing-point gradients and predictions against the oracle
+    (which is pinned to the unmodified reference VarDTC, tests/test_reference_crosscheck.py)."""
+    rng = np.random.default_rng(N + M)
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.stack([np.sin(X).sum(1) / np.sqrt(D) + 0.1 * rng.standard_normal(N) for _ in range(P)], 1)
+    Z = X[rng.permutation(N)[:M]].copy() + 0.01 * rng.standard_normal((M, D))
+    ls = np.sqrt(D) * rng.uniform(0.7, 1.3, D) if ARD else float(np.sqrt(D) * 0.9)
+    cls = {"rbf": gpy_b200.RBF, "exponential": gpy_b200.Exponential, "matern32": gpy_b200.Matern32,
+           "matern52": gpy_b200.Matern52}[kind]
+    k = cls(D, variance=1.3, lengthscale=ls, ARD=ARD)
+    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z)
+    m.likelihood.variance.values[...] = 0.05
+    m.parameters_changed()
+    lml0, g0, Zg0, res = o.sparse_eval(X, Y, Z, kind, ARD, 1.3, ls, 0.05)
+    assert abs(m.log_likelihood() - lml0) <= 1e-8 * max(1.0, abs(lml0))
+    g = np.concatenate([k.variance.gradient, k.lengthscale.gradient, m.likelihood.variance.gradient])
+    np.testing.assert_allclose(g, g0, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(m.Z.gradient, Zg0, rtol=1e-6, atol=1e-8)
+    Xn = rng.uniform(-3, 3, (11, D))
+    mu, var = m.predict(Xn, include_likelihood=False)
+    ko = o.StationaryOracle(kind, D, 1.3, ls, ARD)
+    mu0, var0 = o.sparse_raw_predict(ko, Z, res["woodbury_vector"], res["woodbury_inv"], Xn)
+    np.testing.assert_allclose(mu, mu0, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(var, var0, rtol=1e-5, atol=1e-8)
+    if N <= 700:
+        assert m.checkgrad()
