@@ -316,7 +316,7 @@ def test_combination_and_static_kernels():
     Ky = Ksum0 + (0.05 + 1e-8) * np.eye(120)
     L = np.linalg.cholesky(Ky)
     alpha = np.linalg.solve(Ky, Y)
-    lml0 = 0.5 * (-120 * o.LOG_2_PI - 2 * np.log(np.diag(L)).sum() - float(Y.T.dot(alpha)))
+    lml0 = 0.5 * (-120 * o.LOG_2_PI - 2 * np.log(np.diag(L)).sum() - float(np.squeeze(Y.T.dot(alpha))))
     assert abs(m.log_likelihood() - lml0) < 1e-8
     assert len(m.gradient) == 1 + 3 + 1 + 1 + 1 + 1 + 1 and m.checkgrad()
 
