@@ -47,6 +47,9 @@ EXPORTS = {
     "gpx_sparse_set_data": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, ctypes.c_int]),
     "gpx_sparse_stats": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64, _dp, _dp]),
     "gpx_sparse_grads": (ctypes.c_int, [_vp, _dp, _dp, ctypes.c_double, _dp, _dp, _dp]),
+    "gpx_sparse_eval": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64,
+                                       ctypes.c_double, _dp, _dp, _dp]),
+    "gpx_sparse_get": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
     "gpx_pdinv": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp, _dp, _dp]),
     "gpx_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(GpxStats)]),
     "gpx_total_launches": (ctypes.c_int64, [_vp]),
@@ -206,6 +209,28 @@ class Engine(object):
         check(self._L.gpx_sparse_grads(self._h, _ptr(W2), _ptr(C), float(beta), ctypes.byref(dv), _ptr(dl), _ptr(dZ)),
               "gpx_sparse_grads")
         return dv.value, dl, dZ
+
+    def sparse_eval(self, kind, ARD, variance, lengthscale, Z, noise_variance):
+        """one whole VarDTC evaluation on the device -> (lml, grad [variance, lengthscale.., noise], dZ (M x D))"""
+        Z = _f64(Z)
+        M = Z.shape[0]
+        k, a, ls = _theta(kind, ARD, lengthscale, self.sD)
+        lml = ctypes.c_double()
+        grad = np.zeros(ls.size + 2)
+        dZ = np.empty((M, self.sD))
+        check(self._L.gpx_sparse_eval(self._h, k, a, float(variance), _ptr(ls), _ptr(Z), M, float(noise_variance),
+                                      ctypes.byref(lml), _ptr(grad), _ptr(dZ)), "gpx_sparse_eval")
+        self.sM, self._snl = M, ls.size
+        self.sparse_serial = getattr(self, "sparse_serial", 0) + 1
+        return lml.value, grad, dZ
+
+    SPARSE_GET = {"woodbury_vector": 0, "woodbury_inv": 1, "Kmm": 2, "Lm": 3}
+
+    def sparse_get(self, what):
+        which = self.SPARSE_GET[what]
+        out = np.empty((self.sM, self.sP)) if which == 0 else np.empty((self.sM, self.sM), order="F")
+        check(self._L.gpx_sparse_get(self._h, which, _ptr(out)), "gpx_sparse_get")
+        return out
 
     def stats(self):
         s = GpxStats()

@@ -727,18 +727,13 @@ int gpx_kern_grad_X(gpx_ctx* c, int kind, int ard, double variance, const double
 // ---------------------------------------------------------------------------------------------------------------
 // stand-alone pdinv / jitchol for a caller-supplied symmetric matrix (GPy/util/linalg.py:56-75,193-214)
 // ---------------------------------------------------------------------------------------------------------------
-int gpx_pdinv(gpx_ctx* c, const double* A, int64_t N, int max_tries, double* Ai, double* L, double* Li, double* logdet,
-              double* jitter_used) {
-  if (!A || !logdet) GPX_FAIL("null argument");
-  if (!c) GPX_CHECK(scratch_ctx(&c));
-  if (c->dist) GPX_FAIL("gpx_pdinv is single-GPU");
-  if (N < 1) GPX_FAIL("N must be positive");
-  GPX_CUDA(cudaSetDevice(c->device));
-  // jitchol's diagonal rules need the diagonal of A on the host (N doubles)
-  double dsum = 0.0;
-  bool nonpos = false;
-  for (int64_t i = 0; i < N; i++) { const double d = A[i + i * N]; dsum += d; if (!(d > 0.0)) nonpos = true; }
-  // (re)use the context workspace: allocate like gpx_set_data with a dummy 1-D data set if the shape differs
+}  // extern "C"
+
+// Factor-and-invert a dense symmetric matrix that already lives on the device (dA, leading dimension lda, order N) into
+// the workspace of context c (lower = L, upper = U = L^-T), with jitchol's ladder (GPy/util/linalg.py:56-75):
+// jitter0 is always added; on failure mean(diag)*1e-6*10^k. Returns 0, or the failing minor (>0) / an error (<0).
+int gpx::factor_device(gpx_ctx* c, const double* dA, long lda, long N, double jitter0, int max_tries, double* logdet,
+                       double* jitter_used) {
   {
     std::vector<double> zx((size_t)N, 0.0);
     if (c->N != N || c->D != 1 || c->P != 1 || !c->S) GPX_CHECK(gpx_set_data(c, zx.data(), N, 1, zx.data(), 1));
@@ -747,8 +742,6 @@ int gpx_pdinv(gpx_ctx* c, const double* A, int64_t N, int max_tries, double* Ai,
   c->have_kinv = false;
   cudaStream_t st = c->st;
   const long ld = c->Npad;
-  GPX_CHECK(ensure_staging(c));
-  GPX_CUDA(cudaMemcpyAsync(c->staging, A, (size_t)N * N * 8, cudaMemcpyHostToDevice, st));
   Recorder rec{c};
   double extra = 0.0;
   int tries = 0, info = 0;
@@ -756,23 +749,29 @@ int gpx_pdinv(gpx_ctx* c, const double* A, int64_t N, int max_tries, double* Ai,
   for (;;) {
     tries++;
     GPX_CUDA(cudaMemsetAsync(c->info, 0, sizeof(int), st));
-    if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)ld * ld * 8));
-    GPX_CHECK(launch_load_sym(c->staging, N, c->S, ld, extra, st));
+    GPX_CHECK(launch_load_sym(dA, lda, N, c->S, ld, jitter0 + extra, st));
     c->eval_launches++;
     GPX_CHECK(run_sweep(c, rec));
     GPX_CUDA(cudaMemcpyAsync(c->h_info, c->info, sizeof(int), cudaMemcpyDeviceToHost, st));
     GPX_CUDA(cudaStreamSynchronize(st));
     info = *c->h_info;
     if (info == 0) break;
+    // jitchol's rules need the diagonal: fetch it only on this (rare) path
+    std::vector<double> dg((size_t)N);
+    GPX_CUDA(cudaMemcpy2DAsync(dg.data(), 8, dA, (size_t)(lda + 1) * 8, 8, (size_t)N, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+    double dsum = 0.0;
+    bool nonpos = false;
+    for (long i = 0; i < N; i++) { dsum += dg[i] + jitter0; if (!(dg[i] + jitter0 > 0.0)) nonpos = true; }
     if (nonpos) { gpx::set_error("not pd: non-positive diagonal elements"); c->total_launches += c->eval_launches - l0; return info; }
     if (tries > max_tries) break;
     extra = dsum / (double)N * 1e-6 * pow(10.0, tries - 1);     // linalg.py:66-72
     if (!std::isfinite(extra)) break;
   }
+  c->total_launches += c->eval_launches - l0;
   if (jitter_used) *jitter_used = extra;
-  if (info != 0) { gpx::set_error("not positive definite, even with jitter."); c->total_launches += c->eval_launches - l0; return info; }
-  // logdet = 2 sum log diag(L) (linalg.py:208): per-tile partials -> host sum in fixed order
-  {
+  if (info != 0) { gpx::set_error("not positive definite, even with jitter."); return info; }
+  if (logdet) {   // 2 sum log diag(L) (linalg.py:208): per-tile partials summed in fixed order
     const int nt = (int)(ld / TILE);
     std::vector<double> parts(nt);
     GPX_CUDA(cudaMemcpyAsync(parts.data(), c->logdet_part, (size_t)nt * 8, cudaMemcpyDeviceToHost, st));
@@ -781,6 +780,35 @@ int gpx_pdinv(gpx_ctx* c, const double* A, int64_t N, int max_tries, double* Ai,
     for (int i = 0; i < nt; i++) s += parts[i];
     *logdet = s;
   }
+  return 0;
+}
+
+extern "C" {
+
+int gpx_pdinv(gpx_ctx* c, const double* A, int64_t N, int max_tries, double* Ai, double* L, double* Li, double* logdet,
+              double* jitter_used) {
+  if (!A || !logdet) GPX_FAIL("null argument");
+  if (!c) GPX_CHECK(scratch_ctx(&c));
+  if (c->dist) GPX_FAIL("gpx_pdinv is single-GPU");
+  if (N < 1) GPX_FAIL("N must be positive");
+  GPX_CUDA(cudaSetDevice(c->device));
+  {
+    std::vector<double> zx((size_t)N, 0.0);
+    if (c->N != N || c->D != 1 || c->P != 1 || !c->S) GPX_CHECK(gpx_set_data(c, zx.data(), N, 1, zx.data(), 1));
+  }
+  cudaStream_t st = c->st;
+  const long ld = c->Npad;
+  GPX_CHECK(ensure_staging(c));
+  GPX_CUDA(cudaMemcpyAsync(c->staging, A, (size_t)N * N * 8, cudaMemcpyHostToDevice, st));
+  if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)ld * ld * 8));
+  // the factorisation reads the staged copy; the staging buffer is reused for the results afterwards
+  double* dA = c->Kinv;   // park A in the K^-1 buffer (same size class) so that staging stays free for extraction
+  GPX_CUDA(cudaMemcpyAsync(dA, c->staging, (size_t)N * N * 8, cudaMemcpyDeviceToDevice, st));
+  {
+    const int rc = factor_device(c, dA, N, N, 0.0, max_tries, logdet, jitter_used);
+    if (rc != 0) return rc;
+  }
+  const int64_t l0 = c->eval_launches;
   if (Ai) {
     const long ntl = ld / TILE;
     GemmParams pl = gemm_defaults();

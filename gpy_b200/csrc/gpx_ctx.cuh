@@ -63,5 +63,7 @@ int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y
 int dist_exact_eval(gpx_ctx* c, double extra_jitter);
 void dist_free(gpx_ctx* c);
 void sparse_free(gpx_ctx* c);
+int factor_device(gpx_ctx* c, const double* dA, long lda, long N, double jitter0, int max_tries, double* logdet,
+                  double* jitter_used);
 int fill_kp(KernParams& kp, int kind, int ard, int D, double variance, const double* ls);
 }  // namespace gpx

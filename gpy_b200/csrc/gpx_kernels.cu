@@ -807,19 +807,20 @@ int launch_col_dot(const double* A, long ld, long rows, long cols, int P, const 
 
 // gpx_pdinv: dense symmetric A (N x N, ld = N) -> factor workspace (lower tiles + jitter on the diagonal, zero upper
 // tiles, identity padding), and the mean of its diagonal / any non-positive diagonal entry for the jitchol rules.
-__global__ void load_sym_kernel(const double* __restrict__ A, long N, double* __restrict__ S, long ld, double jitter) {
+__global__ void load_sym_kernel(const double* __restrict__ A, long lda, long N, double* __restrict__ S, long ld,
+                                double jitter) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long j = blockIdx.y;
   if (i >= ld) return;
   double v;
   if (i >= N || j >= N) v = (i == j) ? 1.0 : 0.0;
   else if (i / TILE < j / TILE) v = 0.0;
-  else v = A[i + j * N] + ((i == j) ? jitter : 0.0);
+  else v = A[i + j * lda] + ((i == j) ? jitter : 0.0);
   S[i + j * ld] = v;
 }
-int launch_load_sym(const double* A, long N, double* S, long ld, double jitter, cudaStream_t st) {
+int launch_load_sym(const double* A, long lda, long N, double* S, long ld, double jitter, cudaStream_t st) {
   dim3 grid((unsigned)((ld + 255) / 256), (unsigned)ld);
-  load_sym_kernel<<<grid, 256, 0, st>>>(A, N, S, ld, jitter);
+  load_sym_kernel<<<grid, 256, 0, st>>>(A, lda, N, S, ld, jitter);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

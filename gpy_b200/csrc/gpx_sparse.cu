@@ -19,6 +19,8 @@
 
 using namespace gpx;
 
+static int knm_grads_device(gpx_ctx* c, double beta, double* dvariance, double* dlengthscale, double* dZ);
+
 #define GPX_CHECK(x)            \
   do {                          \
     int rc__ = (x);             \
@@ -42,19 +44,32 @@ struct SparseState {
   double *part = nullptr; size_t part_cap = 0;
   KernParams kp{};
   bool have_stats = false;
+  // full-device evaluation (gpx_sparse_eval)
+  gpx_ctx *cK = nullptr, *cB = nullptr;             // child contexts holding the factors of Kmm and of B = I + A
+  double *mm[10] = {nullptr};                        // Mpad x Mpad work matrices
+  double *vec = nullptr;                             // [8][P][Mpad] small vectors
+  double *red = nullptr; double *h_red = nullptr;    // scalar reductions
+  double trYYT = 0.0;
+  bool have_eval = false;
+  double noise = 0.0;
 };
 
 namespace {
 void free_m(SparseState* s) {
-  double** ptrs[] = {&s->Z, &s->ZsT, &s->sqZ, &s->Kuf, &s->Kfu, &s->dLt, &s->Gm, &s->W2, &s->Cm};
+  double** ptrs[] = {&s->Z, &s->ZsT, &s->sqZ, &s->Kuf, &s->Kfu, &s->dLt, &s->Gm, &s->W2, &s->Cm, &s->vec};
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  for (auto& p : s->mm) { if (p) cudaFree(p); p = nullptr; }
+  s->have_eval = false;
   s->M = s->Mpad = 0;
   s->have_stats = false;
 }
 void free_all(SparseState* s) {
   free_m(s);
-  double** ptrs[] = {&s->X, &s->XsT, &s->sqX, &s->Y, &s->Yb, &s->part};
+  double** ptrs[] = {&s->X, &s->XsT, &s->sqX, &s->Y, &s->Yb, &s->part, &s->red};
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (s->h_red) { cudaFreeHost(s->h_red); s->h_red = nullptr; }
+  if (s->cK) { gpx_destroy(s->cK); s->cK = nullptr; }
+  if (s->cB) { gpx_destroy(s->cB); s->cB = nullptr; }
   s->part_cap = 0;
   s->N = s->Npad = 0;
 }
@@ -69,6 +84,52 @@ int ensure_part(SparseState* s, size_t bytes) {
 __global__ void scale_kernel(const double* __restrict__ in, double a, long n, double* __restrict__ out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a * in[i];
+}
+// out = a X + b Y + cdiag I + d sum_p u_p u_p^T   (n x n, leading dimension ld; X, Y, U may be null)
+__global__ void combine_kernel(double* __restrict__ out, long ld, long n, double a, const double* __restrict__ X, double b,
+                               const double* __restrict__ Y, double cdiag, double d, const double* __restrict__ U, long ldu,
+                               int P) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= n) return;
+  double v = 0.0;
+  if (X) v += a * X[i + j * ld];
+  if (Y) v += b * Y[i + j * ld];
+  if (i == j) v += cdiag;
+  if (U)
+    for (int q = 0; q < P; q++) v = fma(d * U[(long)q * ldu + i], U[(long)q * ldu + j], v);
+  out[i + j * ld] = v;
+}
+// lower tiles of a symmetric matrix were computed: mirror them into the upper tiles
+__global__ void mirror_tiles_kernel(double* __restrict__ A, long ld, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= n || i / TILE >= j / TILE) return;
+  A[i + j * ld] = A[j + i * ld];
+}
+__global__ void transpose_kernel(const double* __restrict__ in, long ld, long n, double* __restrict__ out) {
+  __shared__ double t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+  for (int k = ty; k < 32; k += 8) t[k][tx] = in[(by + tx) + (long)(bx + k) * ld];      // t[col][row]
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) out[(bx + tx) + (long)(by + k) * ld] = t[tx][k];     // out(col, row)
+}
+// r[0] = trace(A), r[1] = sum(A .* B) over n x n; single CTA partial sums reduced in fixed order
+__global__ void __launch_bounds__(256) trace_dot_kernel(const double* __restrict__ A, const double* __restrict__ B, long ld,
+                                                         long n, double* __restrict__ r) {
+  __shared__ double sh[2][256];
+  double tr = 0.0, dt = 0.0;
+  for (long j = blockIdx.x; j < n; j += gridDim.x)
+    for (long i = threadIdx.x; i < n; i += 256) {
+      const double a = A[i + j * ld];
+      dt = fma(a, B[i + j * ld], dt);
+      if (i == j) tr += a;
+    }
+  sh[0][threadIdx.x] = tr; sh[1][threadIdx.x] = dt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { r[2 * blockIdx.x] = sh[0][0]; r[2 * blockIdx.x + 1] = sh[1][0]; }
 }
 }  // namespace
 
@@ -102,6 +163,12 @@ int gpx_sparse_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const dou
   }
   s->N = N;
   s->have_stats = false;
+  s->have_eval = false;
+  {   // trYYT = sum(Y .* Y) (var_dtc.py:37,90)
+    double t = 0.0;
+    for (int64_t i = 0; i < N * (int64_t)P; i++) t += Y[i] * Y[i];
+    s->trYYT = t;
+  }
   GPX_CUDA(cudaMemcpyAsync(s->X, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, c->st));
   GPX_CUDA(cudaMemcpyAsync(s->Yb, Y, (size_t)N * P * 8, cudaMemcpyHostToDevice, c->st));
   GPX_CHECK(launch_transpose_pad(s->Yb, N, P, Npad, s->Y, c->st));
@@ -110,12 +177,11 @@ int gpx_sparse_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const dou
   return 0;
 }
 
-int gpx_sparse_stats(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
-                     int64_t M, double* G, double* psi1tY) {
-  if (!c || !c->sparse || !c->sparse->X) GPX_FAIL("gpx_sparse_set_data has not been called");
-  if (!Z || !G || !psi1tY || !lengthscale) GPX_FAIL("null argument");
-  if (M < 1) GPX_FAIL("M must be positive");
-  GPX_CUDA(cudaSetDevice(c->device));
+}  // extern "C"
+
+// psi1 in both layouts, G = psi1^T psi1 (lower tiles of Gm) and psi1^T Y (Cm), all left on the device
+static int stats_device(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                        int64_t M) {
   SparseState* s = c->sparse;
   cudaStream_t st = c->st;
   GPX_CHECK(fill_kp(s->kp, kind, ard, s->D, variance, lengthscale));
@@ -160,8 +226,25 @@ int gpx_sparse_stats(gpx_ctx* c, int kind, int ard, double variance, const doubl
     pg.K = (int)Npad; pg.nt = mt; pg.ncols = mt;
     GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
   }
+  GPX_CUDA(cudaMemsetAsync(s->Cm, 0, (size_t)Mpad * s->P * 8, st));
   GPX_CHECK(launch_col_dot(s->Kfu, Npad, N, M, s->P, s->Y, Npad, s->Cm, Mpad, st));
   c->total_launches += 6;
+  s->have_stats = true;
+  return 0;
+}
+
+extern "C" {
+
+int gpx_sparse_stats(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                     int64_t M, double* G, double* psi1tY) {
+  if (!c || !c->sparse || !c->sparse->X) GPX_FAIL("gpx_sparse_set_data has not been called");
+  if (!Z || !G || !psi1tY || !lengthscale) GPX_FAIL("null argument");
+  if (M < 1) GPX_FAIL("M must be positive");
+  GPX_CUDA(cudaSetDevice(c->device));
+  GPX_CHECK(stats_device(c, kind, ard, variance, lengthscale, Z, M));
+  SparseState* s = c->sparse;
+  cudaStream_t st = c->st;
+  const long Mpad = s->Mpad;
   std::vector<double> hG((size_t)Mpad * Mpad), hC((size_t)Mpad * s->P);
   GPX_CUDA(cudaMemcpyAsync(hG.data(), s->Gm, hG.size() * 8, cudaMemcpyDeviceToHost, st));
   GPX_CUDA(cudaMemcpyAsync(hC.data(), s->Cm, hC.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -173,7 +256,6 @@ int gpx_sparse_stats(gpx_ctx* c, int kind, int ard, double variance, const doubl
     }
   for (long i = 0; i < M; i++)
     for (int q = 0; q < s->P; q++) psi1tY[i * s->P + q] = hC[(size_t)q * Mpad + i];
-  s->have_stats = true;
   return 0;
 }
 
@@ -184,15 +266,32 @@ int gpx_sparse_grads(gpx_ctx* c, const double* W2, const double* Cmat, double be
   GPX_CUDA(cudaSetDevice(c->device));
   SparseState* s = c->sparse;
   cudaStream_t st = c->st;
-  const long M = s->M, Mpad = s->Mpad, N = s->N, Npad = s->Npad;
-  const int D = s->D, P = s->P;
-  const int mt = (int)(Mpad / TILE), ntl = (int)(Npad / TILE);
+  const long M = s->M, Mpad = s->Mpad;
+  const int P = s->P;
   GPX_CUDA(cudaMemsetAsync(s->W2, 0, (size_t)Mpad * Mpad * 8, st));
   GPX_CUDA(cudaMemcpy2DAsync(s->W2, Mpad * 8, W2, M * 8, (size_t)M * 8, M, cudaMemcpyHostToDevice, st));
   std::vector<double> hC((size_t)Mpad * P, 0.0);
   for (long i = 0; i < M; i++)
     for (int q = 0; q < P; q++) hC[(size_t)q * Mpad + i] = Cmat[i * P + q];
   GPX_CUDA(cudaMemcpyAsync(s->Cm, hC.data(), hC.size() * 8, cudaMemcpyHostToDevice, st));
+  GPX_CUDA(cudaStreamSynchronize(st));   // hC is a local
+  {
+    const int rc = knm_grads_device(c, beta, dvariance, dlengthscale, dZ);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// dL_dKnm^T = W2 psi1^T (+ rank-P term on the fly) reduced to kernel-parameter gradients and dL/dZ; W2 (device, s->W2)
+// and C (device, s->Cm as [P][Mpad]) must be in place. Results on the host.
+static int knm_grads_device(gpx_ctx* c, double beta, double* dvariance, double* dlengthscale, double* dZ) {
+  SparseState* s = c->sparse;
+  cudaStream_t st = c->st;
+  const long M = s->M, Mpad = s->Mpad, N = s->N, Npad = s->Npad;
+  const int D = s->D, P = s->P;
+  const int mt = (int)(Mpad / TILE), ntl = (int)(Npad / TILE);
   scale_kernel<<<(unsigned)((Npad * P + 255) / 256), 256, 0, st>>>(s->Y, beta, Npad * P, s->Yb);
   GPX_CUDA(cudaGetLastError());
   // dLt = W2 * psi1^T  (M x N), W2 symmetric
@@ -239,6 +338,254 @@ int gpx_sparse_grads(gpx_ctx* c, const double* W2, const double* Cmat, double be
   GPX_CUDA(cudaMemcpyAsync(dZ, dout, (size_t)M * D * 8, cudaMemcpyDeviceToHost, st));
   GPX_CUDA(cudaStreamSynchronize(st));
   c->total_launches += 5;
+  return 0;
+}
+
+// =================================================================================================================
+// Full-device VarDTC evaluation: var_dtc.py:66-215 + sparse_gp.py:108-119 with every M x M product on the DMMA GEMM.
+// All products are written as X Y^T (the kernel's native NT form) over column-major operands:
+//   Lm, Um = Lm^-T from the factor-and-invert sweep of Kmm + 1e-8 I;  Lmi = Um^T
+//   A = beta (Lmi G) Lmi^T;  B = I + A -> LB, UB;  Q = LBi Um^T (= LBi Lmi);  v = Q psi1Vf;  C = Q^T v;  w = UB v
+//   B^-1 = UB UB^T;  DBi = P B^-1 + w w^T;  dL_dKmm = Um (..) Um^T;  dL_dpsi2 = beta/2 Um (P I - DBi) Um^T
+// =================================================================================================================
+static int mm_nt(gpx_ctx* c, const double* A, const double* B, double* C, long Mpad, int plain = 1) {
+  GemmParams pg = gemm_defaults();
+  pg.mode = GEMM_PANEL; pg.plain = plain;
+  pg.A = A; pg.lda = Mpad; pg.B = B; pg.ldb = Mpad; pg.C = C; pg.ldc = Mpad;
+  pg.K = (int)Mpad; pg.nt = (int)(Mpad / TILE); pg.ncols = (int)(Mpad / TILE);
+  c->total_launches++;
+  return launch_gemm(pg, dim3(1, 1), c->st);
+}
+static int combine(gpx_ctx* c, double* out, long Mpad, long n, double a, const double* X, double b, const double* Y,
+                   double cdiag, double d = 0.0, const double* U = nullptr, int P = 0) {
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  combine_kernel<<<grid, 256, 0, c->st>>>(out, Mpad, n, a, X, b, Y, cdiag, d, U, Mpad, P);
+  GPX_CUDA(cudaGetLastError());
+  c->total_launches++;
+  return 0;
+}
+
+extern "C" {
+
+int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z, int64_t M,
+                    double noise, double* lml, double* grad, double* dZ) {
+  if (!c || !c->sparse || !c->sparse->X) GPX_FAIL("gpx_sparse_set_data has not been called");
+  if (!Z || !lml || !grad || !dZ || !lengthscale) GPX_FAIL("null argument");
+  if (M < 1) GPX_FAIL("M must be positive");
+  GPX_CUDA(cudaSetDevice(c->device));
+  SparseState* s = c->sparse;
+  cudaStream_t st = c->st;
+  s->have_eval = false;
+  GPX_CHECK(stats_device(c, kind, ard, variance, lengthscale, Z, M));
+  const long Mpad = s->Mpad, N = s->N;
+  const int D = s->D, P = s->P, mt = (int)(Mpad / TILE);
+  const int nl = s->kp.ard ? D : 1;
+  if (!s->mm[0]) {
+    for (auto& p : s->mm) GPX_CUDA(cudaMalloc(&p, (size_t)Mpad * Mpad * 8));
+    GPX_CUDA(cudaMalloc(&s->vec, (size_t)8 * P * Mpad * 8));
+  }
+  if (!s->red) {
+    GPX_CUDA(cudaMalloc(&s->red, 4096 * 8));
+    GPX_CUDA(cudaMallocHost(&s->h_red, 4096 * 8));
+  }
+  if (!s->cK) { GPX_CHECK(gpx_create(c->device, &s->cK)); GPX_CHECK(gpx_create(c->device, &s->cB)); }
+  double *Kd = s->mm[0], *Um = s->mm[1], *Lmi = s->mm[2], *T = s->mm[3], *Ar = s->mm[4], *Bd = s->mm[5], *UB = s->mm[6],
+         *LBi = s->mm[7], *DB = s->mm[8], *E = s->mm[9];
+  double *xv = s->vec, *vv = xv + (size_t)P * Mpad, *Cv = vv + (size_t)P * Mpad, *wv = Cv + (size_t)P * Mpad;
+  const double beta = 1.0 / std::max(noise, 1e-8);                                       // var_dtc.py:79-80
+  s->noise = noise;
+  // G: mirror the computed lower tiles
+  {
+    dim3 grid((unsigned)((Mpad + 255) / 256), (unsigned)Mpad);
+    mirror_tiles_kernel<<<grid, 256, 0, st>>>(s->Gm, Mpad, Mpad);
+    GPX_CUDA(cudaGetLastError());
+  }
+  // Kmm (dense, zero padded), factor-and-invert with const_jitter (var_dtc.py:93-95)
+  GPX_CUDA(cudaMemsetAsync(Kd, 0, (size_t)Mpad * Mpad * 8, st));
+  {
+    KBuildParams kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.kp = s->kp; kb.sym = 0; kb.same = 1;
+    kb.rowsT = s->ZsT; kb.ld_rows = Mpad; kb.sq_rows = s->sqZ; kb.colsT = s->ZsT; kb.ld_cols = Mpad; kb.sq_cols = s->sqZ;
+    kb.out = Kd; kb.ld = Mpad; kb.nrows = M; kb.ncols = M;
+    GPX_CHECK(launch_kbuild(kb, mt, mt, st));
+  }
+  GPX_CUDA(cudaStreamSynchronize(st));
+  {
+    const int rc = factor_device(s->cK, Kd, Mpad, M, 1e-8, 5, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  if (s->cK->Npad != Mpad) GPX_FAIL("internal: child workspace size");
+  GPX_CHECK(launch_assemble(s->cK->S, Mpad, (int)Mpad, Um, Mpad, Lmi, s->cK->st));      // Um (clean upper), Lmi = Um^T
+  GPX_CUDA(cudaStreamSynchronize(s->cK->st));
+  // A_raw = (Lmi G) Lmi^T ;  B = I + beta A_raw
+  GPX_CHECK(mm_nt(c, Lmi, s->Gm, T, Mpad));
+  GPX_CHECK(mm_nt(c, T, Lmi, Ar, Mpad));
+  GPX_CHECK(combine(c, Bd, Mpad, Mpad, beta, Ar, 0.0, nullptr, 1.0));
+  GPX_CUDA(cudaStreamSynchronize(st));
+  double logdetB = 0.0;
+  {
+    const int rc = factor_device(s->cB, Bd, Mpad, M, 0.0, 5, &logdetB, nullptr);
+    if (rc) return rc;
+  }
+  GPX_CHECK(launch_assemble(s->cB->S, Mpad, (int)Mpad, UB, Mpad, LBi, s->cB->st));
+  GPX_CUDA(cudaStreamSynchronize(s->cB->st));
+  // Q = LBi Lmi = LBi Um^T  (into T), Qt = Q^T (into E)
+  GPX_CHECK(mm_nt(c, LBi, Um, T, Mpad));
+  {
+    dim3 grid((unsigned)(Mpad / 32), (unsigned)(Mpad / 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(T, Mpad, Mpad, E);
+    GPX_CUDA(cudaGetLastError());
+  }
+  // x = beta psi1^T Y ; v = Q x ; C = Q^T v ; w = UB v = LBi^T v
+  scale_kernel<<<(unsigned)((Mpad * P + 255) / 256), 256, 0, st>>>(s->Cm, beta, Mpad * P, xv);
+  GPX_CUDA(cudaGetLastError());
+  GPX_CHECK(launch_col_dot(E, Mpad, Mpad, Mpad, P, xv, Mpad, vv, Mpad, st));            // v = (Qt)^T x = Q x
+  GPX_CHECK(launch_col_dot(T, Mpad, Mpad, Mpad, P, vv, Mpad, Cv, Mpad, st));            // C = Q^T v
+  GPX_CHECK(launch_col_dot(LBi, Mpad, Mpad, Mpad, P, vv, Mpad, wv, Mpad, st));          // w = LBi^T v
+  // Binv = UB UB^T (lower tiles, mirrored) ; DBi = P Binv + w w^T
+  GPX_CHECK(mm_nt(c, UB, UB, DB, Mpad, 2));
+  {
+    dim3 grid((unsigned)((Mpad + 255) / 256), (unsigned)Mpad);
+    mirror_tiles_kernel<<<grid, 256, 0, st>>>(DB, Mpad, Mpad);
+    GPX_CUDA(cudaGetLastError());
+  }
+  GPX_CHECK(combine(c, DB, Mpad, Mpad, (double)P, DB, 0.0, nullptr, 0.0, 1.0, wv, P));
+  // scalars: trace(A_raw), sum(A_raw .* DBi), |v|^2
+  const int RB = 64;
+  trace_dot_kernel<<<RB, 256, 0, st>>>(Ar, DB, Mpad, M, s->red);
+  GPX_CUDA(cudaGetLastError());
+  GPX_CUDA(cudaMemcpyAsync(s->h_red, s->red, 2 * RB * 8, cudaMemcpyDeviceToHost, st));
+  std::vector<double> hv((size_t)P * Mpad);
+  GPX_CUDA(cudaMemcpyAsync(hv.data(), vv, hv.size() * 8, cudaMemcpyDeviceToHost, st));
+  // dL_dKmm = Um (-0.5 DBi - 0.5 P B + P I) Um^T   (var_dtc.py:152-156)
+  GPX_CHECK(combine(c, E, Mpad, Mpad, -0.5, DB, -0.5 * P, Bd, (double)P));
+  GPX_CHECK(mm_nt(c, Um, E, T, Mpad));
+  GPX_CHECK(mm_nt(c, T, Um, Kd, Mpad));                                                  // Kd now holds dL_dKmm
+  // W2 = 2 dL_dpsi2 = beta Um (P I - DBi) Um^T     (var_dtc.py:221,231-233)
+  GPX_CHECK(combine(c, E, Mpad, Mpad, -1.0, DB, 0.0, nullptr, (double)P));
+  GPX_CHECK(mm_nt(c, Um, E, T, Mpad));
+  GPX_CHECK(mm_nt(c, T, Um, E, Mpad));
+  GPX_CHECK(combine(c, s->W2, Mpad, Mpad, beta, E, 0.0, nullptr, 0.0));
+  // Knm part: needs C in s->Cm
+  GPX_CUDA(cudaMemcpyAsync(s->Cm, Cv, (size_t)P * Mpad * 8, cudaMemcpyDeviceToDevice, st));
+  double dv_knm = 0.0;
+  std::vector<double> dl_knm(nl, 0.0);
+  GPX_CHECK(knm_grads_device(c, beta, &dv_knm, dl_knm.data(), dZ));                     // dZ <- Knm part
+  // Kmm part: kern.update_gradients_full(dL_dKmm, Z) and kern.gradients_X(dL_dKmm, Z)  (sparse_gp.py:114,117)
+  const int nred = nl + 1;
+  GradFullParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.x1T = s->ZsT; gp.ld1 = Mpad; gp.sq1 = s->sqZ; gp.N = M;
+  gp.x2T = s->ZsT; gp.ld2 = Mpad; gp.sq2 = s->sqZ; gp.M = M;
+  gp.dL_dK = Kd; gp.ldd = Mpad; gp.same = 1; gp.partials = s->part; gp.kp = s->kp;
+  GPX_CHECK(launch_grad_full(gp, mt, mt, st));
+  std::vector<double> hp((size_t)mt * mt * nred);
+  GPX_CUDA(cudaMemcpyAsync(hp.data(), s->part, hp.size() * 8, cudaMemcpyDeviceToHost, st));
+  GPX_CUDA(cudaStreamSynchronize(st));
+  double dv_kmm = 0.0;
+  std::vector<double> dl_kmm(nl, 0.0);
+  {
+    std::vector<double> tot(nred, 0.0);
+    for (size_t t = 0; t < (size_t)mt * mt; t++)
+      for (int q = 0; q < nred; q++) tot[q] += hp[t * nred + q];
+    dv_kmm = tot[0];
+    for (int q = 0; q < nl; q++) dl_kmm[q] = -tot[1 + q] / s->kp.ls[q];
+  }
+  {
+    const int nchunk = (int)std::max<long>(1, std::min<long>((M + 31) / 32, (4 * 148 + mt - 1) / mt));
+    const long mchunk = ((M + nchunk - 1) / nchunk + 31) / 32 * 32;
+    const int nch = (int)((M + mchunk - 1) / mchunk);
+    GPX_CHECK(ensure_part(s, (size_t)(nch + 1) * M * D * 8));
+    GradFullParams gx = gp;
+    gx.partials = nullptr;
+    double* dout = s->part + (size_t)nch * M * D;
+    GPX_CHECK(launch_gradx(gx, nch, mchunk, s->part, dout, st));
+    std::vector<double> hz((size_t)M * D);
+    GPX_CUDA(cudaMemcpyAsync(hz.data(), dout, hz.size() * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < hz.size(); i++) dZ[i] += hz[i];
+  }
+  c->total_launches += 8;
+  // ---- scalars on the host (var_dtc.py:237-276, homoscedastic) -----------------------------------------------------
+  double trAr = 0.0, sumAD = 0.0, data_fit = 0.0;
+  for (int b = 0; b < RB; b++) { trAr += s->h_red[2 * b]; sumAD += s->h_red[2 * b + 1]; }
+  for (int q = 0; q < P; q++)
+    for (long i = 0; i < M; i++) data_fit += hv[(size_t)q * Mpad + i] * hv[(size_t)q * Mpad + i];
+  const double trA = beta * trAr, sumADB = beta * sumAD;
+  const double psi0_sum = variance * (double)N;
+  const double nd = (double)N, od = (double)P;
+  const double log2pi = 1.8378770664093453;
+  const double lik_1 = -0.5 * nd * od * (log2pi - log(beta)) - 0.5 * beta * s->trYYT;
+  const double lik_2 = -0.5 * od * (beta * psi0_sum - trA);
+  const double lik_3 = -od * 0.5 * logdetB;
+  const double lik_4 = 0.5 * data_fit;
+  *lml = lik_1 + lik_2 + lik_3 + lik_4;
+  double dL_dR = -0.5 * nd * od * beta + 0.5 * s->trYYT * beta * beta;
+  dL_dR += 0.5 * od * (psi0_sum * beta * beta - trA * beta);
+  dL_dR += beta * (0.5 * sumADB - data_fit);
+  // d beta / d noise is folded by the reference into dL_dR (gradient wrt the noise VARIANCE): exact_inference_gradients
+  // sums dL_dR as is (var_dtc.py:176, gaussian.py:78-79)
+  const double dvar_diag = -0.5 * od * beta * nd;                                          // update_gradients_diag (:110)
+  grad[0] = dvar_diag + dv_knm + dv_kmm;
+  for (int q = 0; q < nl; q++) grad[1 + q] = dl_knm[q] + dl_kmm[q];
+  grad[1 + nl] = dL_dR;
+  s->have_eval = true;
+  return 0;
+}
+
+/* which: 0 woodbury_vector (M x P row-major), 1 woodbury_inv (M x M), 2 Kmm (+1e-8 I), 3 Lm (lower, col-major) */
+int gpx_sparse_get(gpx_ctx* c, int which, double* out) {
+  if (!c || !c->sparse || !c->sparse->have_eval || !out) GPX_FAIL("no sparse evaluation to fetch from");
+  GPX_CUDA(cudaSetDevice(c->device));
+  SparseState* s = c->sparse;
+  cudaStream_t st = c->st;
+  const long M = s->M, Mpad = s->Mpad;
+  const int P = s->P;
+  if (which == 0) {
+    std::vector<double> h((size_t)P * Mpad);
+    GPX_CUDA(cudaMemcpyAsync(h.data(), s->Cm, h.size() * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaStreamSynchronize(st));
+    for (long i = 0; i < M; i++)
+      for (int q = 0; q < P; q++) out[i * P + q] = h[(size_t)q * Mpad + i];
+    return 0;
+  }
+  double* src = nullptr;
+  if (which == 1) {   // woodbury_inv = Um (I - B^-1) Um^T   (var_dtc.py:207-210); B^-1 = (DBi - w w^T) / P is rebuilt
+    double *Um = s->mm[1], *UB = s->mm[6], *T = s->mm[3], *E = s->mm[9], *DB = s->mm[8];
+    GPX_CHECK(mm_nt(c, UB, UB, DB, Mpad, 2));
+    dim3 grid((unsigned)((Mpad + 255) / 256), (unsigned)Mpad);
+    mirror_tiles_kernel<<<grid, 256, 0, st>>>(DB, Mpad, Mpad);
+    GPX_CUDA(cudaGetLastError());
+    GPX_CHECK(combine(c, E, Mpad, Mpad, -1.0, DB, 0.0, nullptr, 1.0));
+    GPX_CHECK(mm_nt(c, Um, E, T, Mpad));
+    GPX_CHECK(mm_nt(c, T, Um, E, Mpad));
+    src = E;
+  } else if (which == 2 || which == 3) {
+    // Kmm / Lm from the child context's factor: rebuild Kmm by the kernel build, Lm by extraction
+    if (which == 2) {
+      double* Kd = s->mm[3];
+      GPX_CUDA(cudaMemsetAsync(Kd, 0, (size_t)Mpad * Mpad * 8, st));
+      KBuildParams kb;
+      memset(&kb, 0, sizeof(kb));
+      kb.kp = s->kp; kb.sym = 0; kb.same = 1;
+      kb.rowsT = s->ZsT; kb.ld_rows = Mpad; kb.sq_rows = s->sqZ; kb.colsT = s->ZsT; kb.ld_cols = Mpad; kb.sq_cols = s->sqZ;
+      kb.out = Kd; kb.ld = Mpad; kb.nrows = M; kb.ncols = M;
+      GPX_CHECK(launch_kbuild(kb, (int)(Mpad / TILE), (int)(Mpad / TILE), st));
+      GPX_CHECK(combine(c, Kd, Mpad, M, 1.0, Kd, 0.0, nullptr, 1e-8));
+      src = Kd;
+    } else {
+      double* Ld = s->mm[3];
+      GPX_CUDA(cudaStreamSynchronize(st));
+      GPX_CHECK(launch_extract(GPX_GET_L, s->cK->S, Mpad, s->cK->Ldiag, nullptr, nullptr, 0, Mpad, Ld, s->cK->st));
+      GPX_CUDA(cudaStreamSynchronize(s->cK->st));
+      src = Ld;
+    }
+  } else {
+    GPX_FAIL("unknown gpx_sparse_get selector");
+  }
+  GPX_CUDA(cudaMemcpy2DAsync(out, M * 8, src, Mpad * 8, (size_t)M * 8, M, cudaMemcpyDeviceToHost, st));
+  GPX_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -6,11 +6,13 @@ Mirrors:
     GPy.models.SparseGPRegression                              GPy/models/sparse_gp_regression.py:33-59
 (Gaussian likelihood, homoscedastic noise, certain inputs, no mean function — BASELINE.json configs[4].)
 
-Split of the work: psi1 = K(X, Z) (8 N M bytes), G = psi1^T psi1, psi1^T Y, dL_dKnm = (beta Y) C^T + 2 psi1 dL_dpsi2 and
-its reductions to kernel / inducing-point gradients all live on the device (gpx_sparse_*: nothing of size N crosses PCIe
-except X and Y once). What is left are M x M objects (M = number of inducing points): two Cholesky factors + inverses
-(gpx_pdinv on the device) and a handful of M x M products / traces, which are NumPy on the host here — the reference does
-them with LAPACK triangular solves; with the explicit triangular inverses returned by the device they become products.
+Default (`VarDTC(device_algebra=True)`): ONE call, gpx_sparse_eval, does the whole evaluation on the device — psi1 =
+K(X, Z), G = psi1^T psi1, psi1^T Y, the two M x M factor-and-invert sweeps (Kmm, B = I + A), every M x M product, dL_dKnm
+= (beta Y) C^T + 2 psi1 dL_dpsi2 and all reductions to kernel / inducing-point / noise gradients. Only X, Y (once), Z and
+theta go in; the bound, 2 + nl gradient entries and dZ (M x D) come back; the posterior is fetched lazily.
+
+`device_algebra=False` keeps the split formulation (gpx_sparse_stats / gpx_pdinv / gpx_sparse_grads with the M x M
+products in NumPy between them): same numbers, used by the tests to cross-check the fused path step by step.
 """
 import numpy as np
 
@@ -37,6 +39,32 @@ class SparsePosterior(object):
         return mu, (kern.Kdiag(Xnew) - np.sum(np.dot(self.woodbury_inv.T, Kx) * Kx, 0))[:, None]
 
 
+class LazySparsePosterior(object):
+    """Posterior of the last gpx_sparse_eval; its arrays are produced on the device on first touch (var_dtc.py:201-214)."""
+
+    def __init__(self, engine):
+        self._eng, self._serial, self._c = engine, engine.sparse_serial, {}
+
+    def _get(self, what):
+        if what not in self._c:
+            if self._eng.sparse_serial != self._serial:
+                raise RuntimeError("stale sparse posterior: the engine has evaluated other parameters since")
+            self._c[what] = self._eng.sparse_get(what)
+        return self._c[what]
+
+    woodbury_vector = property(lambda self: self._get("woodbury_vector"))
+    woodbury_inv = property(lambda self: self._get("woodbury_inv"))
+    K = property(lambda self: self._get("Kmm"))
+    K_chol = property(lambda self: self._get("Lm"))
+
+    def materialise(self):
+        for w in ("woodbury_vector", "woodbury_inv"):
+            self._get(w)
+        return self
+
+    _raw_predict = SparsePosterior._raw_predict
+
+
 class VarDTC(object):
     """Drop-in for GPy's VarDTC: inference(kern, X, Z, likelihood, Y) -> (posterior, log_marginal, grad_dict).
     `grad_dict['dL_dKnm']` is never materialised (N x M); instead the dict carries the already-reduced contributions
@@ -44,8 +72,9 @@ class VarDTC(object):
 
     const_jitter = CONST_JITTER
 
-    def __init__(self, device=0, engine=None, limit=1):
+    def __init__(self, device=0, engine=None, limit=1, device_algebra=True):
         self.device, self._engine, self._data_key = device, engine, None
+        self.device_algebra = device_algebra
 
     @property
     def engine(self):
@@ -78,10 +107,17 @@ class VarDTC(object):
         num_data, output_dim = Y.shape
         num_inducing = Zs.shape[0]
         kind, ard, var, ls = kern._theta()
+        noise_var = None
         if precision is None:
+            noise_var = float(np.squeeze(np.asarray(likelihood.gaussian_variance(Y_metadata))))
             precision = 1.0 / np.fmax(float(np.squeeze(np.asarray(likelihood.gaussian_variance(Y_metadata)))),
                                       self.const_jitter)                                   # var_dtc.py:79-80
         beta = float(precision)
+        if self.device_algebra:
+            lml, grad, dZ = eng.sparse_eval(kind, ard, var, ls, Zs, noise_var if noise_var is not None else 1.0 / beta)
+            post = LazySparsePosterior(eng)
+            return post, float(lml), {"dvariance": grad[0], "dlengthscale": grad[1:-1], "dZ": dZ,
+                                      "dL_dthetaL": float(grad[-1]), "num_data": num_data}
         trYYT = float(np.einsum("ij,ij->", Y, Y))                                           # :37,90
         # ---- device: psi1 statistics ---------------------------------------------------------------------------
         G, psi1tY = eng.sparse_stats(kind, ard, var, ls, Zs)                                # psi1^T psi1, psi1^T Y
@@ -131,7 +167,8 @@ class SparseGPRegression(Parameterized):
     """GPy.models.SparseGPRegression (sparse_gp_regression.py:33-59) / GPy.core.SparseGP (sparse_gp.py:38-119).
     Parameter (and gradient) order as in the reference: [inducing inputs, kern.variance, kern.lengthscale, noise]."""
 
-    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, device=0, engine=None, name="sparse_gp"):
+    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, device=0, engine=None, name="sparse_gp",
+                 device_algebra=True):
         super(SparseGPRegression, self).__init__(name)
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
@@ -150,7 +187,7 @@ class SparseGPRegression(Parameterized):
         self.Z.values = np.array(Z, dtype=np.float64)                          # keep the M x D shape
         self.Z.gradient = np.zeros_like(self.Z.values)
         self.num_inducing = self.Z.values.shape[0]
-        self.inference_method = VarDTC(device=device, engine=engine)
+        self.inference_method = VarDTC(device=device, engine=engine, device_algebra=device_algebra)
         self.link_parameter(self.Z)                                            # sparse_gp.py:61 (index 0)
         self.link_parameter(self.kern)
         self.link_parameter(self.likelihood)
@@ -163,6 +200,11 @@ class SparseGPRegression(Parameterized):
             self.kern, self.X, Z, self.likelihood, self.Y)
         self.grad_dict = gd
         self.likelihood.update_gradients(gd["dL_dthetaL"])                                     # :84
+        if "dZ" in gd:                                      # fused device evaluation: gradients already reduced
+            self.kern.variance.gradient = np.atleast_1d(gd["dvariance"])
+            self.kern.lengthscale.gradient = np.atleast_1d(gd["dlengthscale"])
+            self.Z.gradient = gd["dZ"]
+            return
         # kern.update_gradients_diag(dL_dKdiag, X) (:110): variance.gradient = sum(dL_dKdiag), lengthscale 0
         kv = gd["dL_dKdiag_value"] * gd["num_data"]
         kl = np.zeros(self.kern.lengthscale.size)

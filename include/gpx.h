@@ -114,6 +114,17 @@ int gpx_sparse_stats(gpx_ctx* ctx, int kind, int ard, double variance, const dou
 int gpx_sparse_grads(gpx_ctx* ctx, const double* W2, const double* C, double beta, double* dvariance,
                      double* dlengthscale, double* dZ);
 
+/* One whole VarDTC evaluation on the device: VarDTC.inference (var_dtc.py:66-215, Gaussian homoscedastic noise, certain
+ * inputs, no mean function) + SparseGP._update_gradients (core/sparse_gp.py:108-119) + Gaussian.update_gradients
+ * (likelihoods/gaussian.py:78-79). Kmm + 1e-8 I and B = I + A are factored-and-inverted by the same sweep as the exact
+ * path (jitchol ladder, util/linalg.py:56-75); every M x M product of :130-156,:201-233 is a DMMA GEMM; only the
+ * scalars, dZ (M x D row-major) and the (1 + nl + 1) gradient entries [variance, lengthscale.., noise variance] return.
+ *   gpx_sparse_get: posterior pieces of the last evaluation (var_dtc.py:201-214): 0 woodbury_vector (M x P row-major),
+ *                   1 woodbury_inv (M x M), 2 Kmm (+ const_jitter on the diagonal), 3 Lm (lower, column-major). */
+int gpx_sparse_eval(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                    int64_t M, double noise_variance, double* lml, double* grad, double* dZ);
+int gpx_sparse_get(gpx_ctx* ctx, int which, double* out);
+
 /* Measurement hooks (bench.py): device time of the last eval between CUDA events on the launching stream, the number
  * of kernels this library launched since creation, and per-phase accounting of the last eval. */
 typedef struct {

@@ -11,14 +11,15 @@ def main():
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
     M = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
     D = int(sys.argv[3]) if len(sys.argv) > 3 else 16
-    cpu = len(sys.argv) > 4 and sys.argv[4] == "cpu"
+    cpu = "cpu" in sys.argv[4:]
     rng = np.random.default_rng(0)
     X = rng.uniform(-3, 3, (N, D))
     Y = np.sin(X).sum(1, keepdims=True) / np.sqrt(D) + 0.1 * rng.standard_normal((N, 1))
     Z = X[rng.permutation(N)[:M]].copy()
     k = gpy_b200.RBF(D, variance=1.0, lengthscale=np.full(D, np.sqrt(D)), ARD=True)
     t0 = time.time()
-    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z)
+    split = "split" in sys.argv[4:]
+    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z, device_algebra=not split)
     t_first = time.time() - t0
     eng = m.inference_method.engine
     times = []
@@ -33,7 +34,8 @@ def main():
     out = {"config": "SparseGPRegression RBF ARD N=%d M=%d D=%d" % (N, M, D), "first_eval_incl_alloc_s": t_first,
            "eval_wall_s": float(np.median(times)), "evals_per_s": 1.0 / float(np.median(times)),
            "device_stats_call_s": t_stats, "device_grads_call_s": t_grads,
-           "host_MxM_algebra_s": float(np.median(times)) - t_stats - t_grads,
+           "mode": "split (host M x M algebra)" if split else "fused device evaluation (gpx_sparse_eval)",
+           "MxM_algebra_s": float(np.median(times)) - t_stats - t_grads,
            "flops_stats": 2.0 * N * M * M / 2, "flops_grads": 2.0 * N * M * M, "lml": m.log_likelihood(),
            "grad_kern_variance": float(k.variance.gradient[0])}
     if cpu:
