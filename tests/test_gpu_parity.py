@@ -359,4 +359,4 @@ def test_sparse_gp_vardtc(kind, ARD, N, M, D, P, device_algebra):
     np.testing.assert_allclose(mu, mu0, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(var, var0, rtol=1e-5, atol=1e-8)
     if N <= 700:
-        assert m.checkgrad()
+        assert m.checkgrad(step=1e-5)   # 1e-6 drowns the O(1e-2) inducing-point gradients in fp64 round-off of the bound
