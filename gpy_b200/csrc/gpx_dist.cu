@@ -123,6 +123,18 @@ void dist_free(gpx_ctx* c) {
   d->Bc = d->Bc2 = d->blkpart = nullptr;
 }
 
+int dist_world(const gpx_ctx* c, int* rank, int* nranks) {
+  if (c->dist && c->dist->comm) { *rank = c->dist->rank; *nranks = c->dist->G; }
+  else { *rank = 0; *nranks = 1; }
+  return 0;
+}
+
+int dist_allreduce_sum(gpx_ctx* c, double* buf, size_t count, cudaStream_t st) {
+  if (!c->dist || !c->dist->comm || c->dist->G <= 1) return 0;
+  GPX_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, c->dist->comm, st));
+  return 0;
+}
+
 static long dist_pick_nb(const gpx_ctx* c, long N) {
   if (c->NB > 0) return c->NB;
   const char* e = getenv("GPX_NB");

@@ -33,7 +33,8 @@ static int knm_grads_device(gpx_ctx* c, double beta, double* dvariance, double* 
   } while (0)
 
 struct SparseState {
-  long N = 0, Npad = 0, M = 0, Mpad = 0;
+  long N = 0, Npad = 0, M = 0, Mpad = 0;   // N: rows held by THIS rank (all of them on one GPU)
+  long Ntot = 0;                           // rows over all ranks (var_dtc.py num_data)
   int D = 0, P = 0;
   double *X = nullptr, *XsT = nullptr, *sqX = nullptr, *Y = nullptr, *Yb = nullptr;   // Y: [P][Npad]
   double *Z = nullptr, *ZsT = nullptr, *sqZ = nullptr;
@@ -49,6 +50,7 @@ struct SparseState {
   double *mm[10] = {nullptr};                        // Mpad x Mpad work matrices
   double *vec = nullptr;                             // [8][P][Mpad] small vectors
   double *red = nullptr; double *h_red = nullptr;    // scalar reductions
+  double *gsum = nullptr;                            // [1 + nl + M*D] gradient pieces summed over ranks
   double trYYT = 0.0;
   bool have_eval = false;
   double noise = 0.0;
@@ -56,7 +58,7 @@ struct SparseState {
 
 namespace {
 void free_m(SparseState* s) {
-  double** ptrs[] = {&s->Z, &s->ZsT, &s->sqZ, &s->Kuf, &s->Kfu, &s->dLt, &s->Gm, &s->W2, &s->Cm, &s->vec};
+  double** ptrs[] = {&s->Z, &s->ZsT, &s->sqZ, &s->Kuf, &s->Kfu, &s->dLt, &s->Gm, &s->W2, &s->Cm, &s->vec, &s->gsum};
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   for (auto& p : s->mm) { if (p) cudaFree(p); p = nullptr; }
   s->have_eval = false;
@@ -164,10 +166,26 @@ int gpx_sparse_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const dou
   s->N = N;
   s->have_stats = false;
   s->have_eval = false;
-  {   // trYYT = sum(Y .* Y) (var_dtc.py:37,90)
+  {   // trYYT = sum(Y .* Y) (var_dtc.py:37,90); with row shards: summed over the ranks, like num_data
     double t = 0.0;
     for (int64_t i = 0; i < N * (int64_t)P; i++) t += Y[i] * Y[i];
     s->trYYT = t;
+    s->Ntot = N;
+    int rank = 0, G = 1;
+    dist_world(c, &rank, &G);
+    if (G > 1) {
+      if (!s->red) {
+        GPX_CUDA(cudaMalloc(&s->red, 4096 * 8));
+        GPX_CUDA(cudaMallocHost(&s->h_red, 4096 * 8));
+      }
+      s->h_red[0] = (double)N; s->h_red[1] = t;
+      GPX_CUDA(cudaMemcpyAsync(s->red, s->h_red, 16, cudaMemcpyHostToDevice, c->st));
+      GPX_CHECK(dist_allreduce_sum(c, s->red, 2, c->st));
+      GPX_CUDA(cudaMemcpyAsync(s->h_red, s->red, 16, cudaMemcpyDeviceToHost, c->st));
+      GPX_CUDA(cudaStreamSynchronize(c->st));
+      s->Ntot = (long)llround(s->h_red[0]);
+      s->trYYT = s->h_red[1];
+    }
   }
   GPX_CUDA(cudaMemcpyAsync(s->X, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, c->st));
   GPX_CUDA(cudaMemcpyAsync(s->Yb, Y, (size_t)N * P * 8, cudaMemcpyHostToDevice, c->st));
@@ -199,6 +217,8 @@ static int stats_device(gpx_ctx* c, int kind, int ard, double variance, const do
     GPX_CUDA(cudaMalloc(&s->Gm, (size_t)Mpad * Mpad * 8));
     GPX_CUDA(cudaMalloc(&s->W2, (size_t)Mpad * Mpad * 8));
     GPX_CUDA(cudaMalloc(&s->Cm, (size_t)Mpad * s->P * 8));
+    GPX_CUDA(cudaMalloc(&s->gsum, (size_t)(MAX_D + 2 + Mpad * s->D) * 8));
+    GPX_CUDA(cudaMemsetAsync(s->Gm, 0, (size_t)Mpad * Mpad * 8, st));
     GPX_CUDA(cudaMemsetAsync(s->Kuf, 0, (size_t)Mpad * Npad * 8, st));   // padding stays zero: only valid entries
     GPX_CUDA(cudaMemsetAsync(s->Kfu, 0, (size_t)Mpad * Npad * 8, st));   // are ever written
   }
@@ -228,6 +248,10 @@ static int stats_device(gpx_ctx* c, int kind, int ard, double variance, const do
   }
   GPX_CUDA(cudaMemsetAsync(s->Cm, 0, (size_t)Mpad * s->P * 8, st));
   GPX_CHECK(launch_col_dot(s->Kfu, Npad, N, M, s->P, s->Y, Npad, s->Cm, Mpad, st));
+  // row shards: the psi statistics are sums over data points -> one M x M and one M x P all-reduce
+  // (the pattern of var_dtc_parallel.py:113-131 with NCCL instead of mpi4py)
+  GPX_CHECK(dist_allreduce_sum(c, s->Gm, (size_t)Mpad * Mpad, st));
+  GPX_CHECK(dist_allreduce_sum(c, s->Cm, (size_t)Mpad * s->P, st));
   c->total_launches += 6;
   s->have_stats = true;
   return 0;
@@ -240,6 +264,11 @@ int gpx_sparse_stats(gpx_ctx* c, int kind, int ard, double variance, const doubl
   if (!c || !c->sparse || !c->sparse->X) GPX_FAIL("gpx_sparse_set_data has not been called");
   if (!Z || !G || !psi1tY || !lengthscale) GPX_FAIL("null argument");
   if (M < 1) GPX_FAIL("M must be positive");
+  {
+    int rank = 0, G_ = 1;
+    dist_world(c, &rank, &G_);
+    if (G_ > 1) GPX_FAIL("the split sparse calls are single-GPU; use gpx_sparse_eval with row shards");
+  }
   GPX_CUDA(cudaSetDevice(c->device));
   GPX_CHECK(stats_device(c, kind, ard, variance, lengthscale, Z, M));
   SparseState* s = c->sparse;
@@ -377,7 +406,7 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   cudaStream_t st = c->st;
   s->have_eval = false;
   GPX_CHECK(stats_device(c, kind, ard, variance, lengthscale, Z, M));
-  const long Mpad = s->Mpad, N = s->N;
+  const long Mpad = s->Mpad, N = s->Ntot;
   const int D = s->D, P = s->P, mt = (int)(Mpad / TILE);
   const int nl = s->kp.ard ? D : 1;
   if (!s->mm[0]) {
@@ -472,6 +501,23 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   double dv_knm = 0.0;
   std::vector<double> dl_knm(nl, 0.0);
   GPX_CHECK(knm_grads_device(c, beta, &dv_knm, dl_knm.data(), dZ));                     // dZ <- Knm part
+  {
+    int rank = 0, G = 1;
+    dist_world(c, &rank, &G);
+    if (G > 1) {   // sums over this rank's data points -> totals
+      std::vector<double> h((size_t)1 + nl + (size_t)M * D);
+      h[0] = dv_knm;
+      for (int q = 0; q < nl; q++) h[1 + q] = dl_knm[q];
+      memcpy(h.data() + 1 + nl, dZ, (size_t)M * D * 8);
+      GPX_CUDA(cudaMemcpyAsync(s->gsum, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+      GPX_CHECK(dist_allreduce_sum(c, s->gsum, h.size(), st));
+      GPX_CUDA(cudaMemcpyAsync(h.data(), s->gsum, h.size() * 8, cudaMemcpyDeviceToHost, st));
+      GPX_CUDA(cudaStreamSynchronize(st));
+      dv_knm = h[0];
+      for (int q = 0; q < nl; q++) dl_knm[q] = h[1 + q];
+      memcpy(dZ, h.data() + 1 + nl, (size_t)M * D * 8);
+    }
+  }
   // Kmm part: kern.update_gradients_full(dL_dKmm, Z) and kern.gradients_X(dL_dKmm, Z)  (sparse_gp.py:114,117)
   const int nred = nl + 1;
   GradFullParams gp;

@@ -27,6 +27,13 @@ def block_layout(N, NB, G):
     return Npad, nblk, -(-nblk // G)
 
 
+def shard_rows(N, rank, G):
+    """contiguous row shard of rank `rank` for the row-sharded sparse model (the first N mod G ranks get one more row)."""
+    base, extra = divmod(N, G)
+    lo = rank * base + min(rank, extra)
+    return slice(lo, lo + base + (1 if rank < extra else 0))
+
+
 def exchange_unique_id(make_id, group=None):
     """rank 0 calls make_id() -> 128 bytes; everybody gets them (works on gloo and nccl process groups)."""
     import torch

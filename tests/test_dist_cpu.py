@@ -126,3 +126,89 @@ def test_two_rank_gloo_sweep():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _sparse_worker(rank, world, port, q):
+    """Row-sharded VarDTC as gpx_sparse_eval runs it with a communicator: each rank holds N/world data rows, the psi
+    statistics (psi1^T psi1, psi1^T Y, num_data, trYYT) are all-reduced, every rank repeats the M x M algebra, the
+    Knm gradient pieces are all-reduced. Checked against the oracle on the whole data set."""
+    import torch
+    import torch.distributed as dist
+    from oracle import gpy_oracle as o
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, M, D, P = 403, 37, 3, 2
+        rng = np.random.default_rng(5)
+        X = rng.uniform(-3, 3, (N, D))
+        Y = np.stack([np.sin(X).sum(1) + 0.1 * rng.standard_normal(N) for _ in range(P)], 1)
+        Z = X[rng.permutation(N)[:M]] + 0.01 * rng.standard_normal((M, D))
+        ls, var, noise = np.array([1.1, 1.6, 2.0]), 1.3, 0.07
+        lml0, g0, Zg0, res0 = o.sparse_eval(X, Y, Z, "matern52", True, var, ls, noise)
+        rows = gdist.shard_rows(N, rank, world)
+        Xl, Yl = X[rows], Y[rows]
+        kern = o.StationaryOracle("matern52", D, var, ls, True)
+        beta = 1.0 / max(noise, 1e-8)
+
+        def allsum(a):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).copy())
+            dist.all_reduce(t)
+            return t.numpy()
+
+        psi1 = kern.K(Xl, Z)
+        G = allsum(psi1.T @ psi1)
+        pY = allsum(psi1.T @ Yl)
+        ntot, trYYT = allsum(np.array([float(Xl.shape[0]), float((Yl * Yl).sum())]))
+        assert int(round(ntot)) == N
+        # replicated M x M algebra, in the product form of gpx_sparse.cu
+        Kmm = kern.K(Z) + 1e-8 * np.eye(M)
+        Lm = np.linalg.cholesky(Kmm); Lmi = np.linalg.inv(Lm); Um = Lmi.T
+        Ar = Lmi @ G @ Lmi.T
+        B = np.eye(M) + beta * Ar
+        LB = np.linalg.cholesky(B); LBi = np.linalg.inv(LB); UB = LBi.T
+        Q = LBi @ Lmi
+        v = Q @ (beta * pY); C = Q.T @ v; w = UB @ v
+        DBi = P * (UB @ UB.T) + w @ w.T
+        dKmm = Um @ (-0.5 * DBi - 0.5 * P * B + P * np.eye(M)) @ Um.T
+        W2 = beta * Um @ (P * np.eye(M) - DBi) @ Um.T
+        data_fit, trA, sumADB = float((v * v).sum()), beta * np.trace(Ar), beta * float((Ar * DBi).sum())
+        psi0_sum = var * ntot
+        lml = (-0.5 * ntot * P * (np.log(2 * np.pi) - np.log(beta)) - 0.5 * beta * trYYT
+               - 0.5 * P * (beta * psi0_sum - trA) - P * np.log(np.diag(LB)).sum() + 0.5 * data_fit)
+        dR = (-0.5 * ntot * P * beta + 0.5 * trYYT * beta ** 2 + 0.5 * P * (psi0_sum * beta ** 2 - trA * beta)
+              + beta * (0.5 * sumADB - data_fit))
+        # local Knm pieces -> all-reduce
+        dKnm = (beta * Yl) @ C.T + psi1 @ W2
+        dv1, dl1 = kern.update_gradients_full(dKnm, Xl, Z)
+        dZ1 = kern.gradients_X(dKnm.T, Z, Xl)
+        pieces = allsum(np.concatenate([[dv1], np.atleast_1d(dl1), dZ1.ravel()]))
+        dv2, dl2 = kern.update_gradients_full(dKmm, Z, None)
+        dvar = -0.5 * P * beta * ntot + pieces[0] + dv2
+        dlen = pieces[1:1 + D] + np.atleast_1d(dl2)
+        Zg = pieces[1 + D:].reshape(M, D) + kern.gradients_X(dKmm, Z)
+        g = np.concatenate([[dvar], dlen, [dR]])
+        assert abs(lml - lml0) < 1e-8 * max(1.0, abs(lml0))
+        np.testing.assert_allclose(g, g0, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(Zg, Zg0, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(C, res0["woodbury_vector"], rtol=1e-6, atol=1e-8)
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sparse_row_shards():
+    import torch.multiprocessing as mp
+    assert [gdist.shard_rows(10, r, 3) for r in range(3)] == [slice(0, 4), slice(4, 7), slice(7, 10)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
