@@ -72,6 +72,20 @@ def test_block_size_does_not_change_the_answer(nb):
     e.close()
 
 
+def test_metric_size_n4096_against_oracle():
+    """N=4096, D=8 (the smallest size of the BASELINE.json metric): LML, gradient and alpha against the oracle."""
+    X, Y = o.synthetic(4096, 8, seed=3)
+    var, ls, noise = o.theta_bench(8, True)
+    lml0, g0, res = o.eval_lml_grad(X, Y, "matern32", True, var, ls, noise)
+    e = _ffi.Engine(0)
+    e.set_data(X, Y)
+    lml, g, _ = e.exact_eval("matern32", True, var, ls, noise)
+    assert abs(lml - lml0) <= LML_ATOL
+    np.testing.assert_allclose(g, g0, rtol=GRAD_RTOL)
+    assert rel(e.get("alpha"), res["alpha"]) < 1e-9
+    e.close()
+
+
 def test_multiple_outputs_and_large_D(eng):
     rng = np.random.default_rng(0)
     X = rng.uniform(-3, 3, (400, 64))
