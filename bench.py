@@ -255,11 +255,15 @@ def run_ours(args):
         m.set_theta(*theta_for_step(D, -1 - w))
     barrier()
     t0 = time.perf_counter()
+    e2e_dev_ms, e2e_setxy_ms = [], []
     for s in range(e2e_steps):
+        ts = time.perf_counter()
         m.set_XY(X.copy(), Y.copy())           # fresh host buffers: forces the host->device copy of the inputs
+        e2e_setxy_ms.append((time.perf_counter() - ts) * 1e3)
         m.set_theta(*theta_for_step(D, s))     # -> parameters_changed(): inference + kernel gradients
         ll = m.log_likelihood()
         g = m.gradient
+        e2e_dev_ms.append(eng.stats()["total_ms"])
     barrier()
     e2e_wall = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
@@ -300,6 +304,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + (D + 2) * 8),
                     "d2h_bytes_per_step": int((nl + 3) * 8), "steps": e2e_steps,
+                    "device_ms_per_step": float(np.mean(e2e_dev_ms)), "set_XY_host_ms_per_step": float(np.mean(e2e_setxy_ms)),
                     "api": "gpy_b200.GPRegression.set_XY/set_theta -> log_likelihood(), gradient (host ndarrays in/out)"},
             "roofline": {"bound": "tensor", "kernel": "gemm_update_kernel (fp64 DMMA trailing update)",
                          "achieved": ach if upd_ms > 0 else None, "peak": peak, "unit": "TFLOP/s",

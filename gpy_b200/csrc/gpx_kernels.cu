@@ -290,14 +290,103 @@ base_sweep_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, d
 constexpr int BP = 132;   // pitch (doubles) of the shared tile, column-major: (row, col) at col*BP + row
 constexpr int MP = 20;    // pitch of the 16x16 micro operand buffers
 
+// (1) one warp: factor-and-invert the 16x16 diagonal micro-block at (c0, c0); values in registers (8 per lane), the
+// pivot column is exchanged through a 2 x 16 shared scratch. Writes the micro-block back (lower = L, strict upper = U),
+// the operand copies Pd = U micro-block ((r,k) at k*MP+r) and Wm = U^T ((c,k) at k*MP+c), and the pivots.
+__device__ __forceinline__ void micro_diag(double* T, int c0, double* Pd, double* Wm, double* psh, double* dinv,
+                                           double* ldg, int* info, int gcol0, int lane) {
+  const int rr = lane & 15, ch = (lane >> 4) * 8;   // lane owns row rr, columns ch..ch+7 of the micro-block
+  double v[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) v[q] = (rr >= ch + q) ? T[(c0 + ch + q) * BP + c0 + rr] : 0.0;
+  double my_inv = 0.0, my_l = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int ob = (j >> 3) * 16;                   // first lane of the half-warp that owns column j
+    const double d = __shfl_sync(0xffffffffu, v[j & 7], ob + j);
+    if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, gcol0 + c0 + j + 1);
+    const double inv = rsqrt(d);
+    const double l = d * inv;
+    double* pj = psh + (j & 1) * 16;
+    if ((lane >> 4) == (j >> 3)) {                  // owner half-warp: finalize column j, publish p
+      const double pown = (rr == j) ? inv : v[j & 7] * inv;
+      pj[rr] = pown;
+      v[j & 7] = (rr == j) ? l : pown;
+      if (rr == j) { my_inv = inv; my_l = l; }
+    }
+    __syncwarp();
+    const double prow = pj[rr];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int col = ch + q;
+      if (col > j && (rr >= col || rr <= j)) v[q] = fma(-prow, pj[col], v[q]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const int col = ch + q;
+    T[(c0 + col) * BP + c0 + rr] = v[q];
+    const double u = rr < col ? v[q] : 0.0;          // U(rr, col) strictly above the diagonal
+    Pd[col * MP + rr] = u;
+    Wm[rr * MP + col] = u;                            // W(col, rr) = U(rr, col); zeros above W's diagonal
+  }
+  __syncwarp();
+  if (rr >= ch && rr < ch + 8) {                      // this lane produced pivot rr
+    dinv[c0 + rr] = my_inv; ldg[c0 + rr] = my_l;
+    Pd[rr * MP + rr] = my_inv;
+    Wm[rr * MP + rr] = my_inv;
+  }
+}
+
+// (3) one 16 x (8*NI) piece of a micro-tile update  T(rt, ct) -= P_rt P_ct^T  (k-depth 16) with DMMA.8x8x4
+template <int NI>
+__device__ __forceinline__ void micro_update(double* T, int c0, int jp, int rt, int ct, int n0, const double* Pd,
+                                             int lane) {
+  const int g = lane >> 2, tg = lane & 3;
+  const double* Ap = (rt == jp) ? Pd : (T + c0 * BP + rt * 16);
+  const int apitch = (rt == jp) ? MP : BP;
+  const double* Bp = T + c0 * BP + ct * 16 + n0;
+  double* Cp = T + (ct * 16 + n0) * BP + rt * 16;
+  double c[2][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) c[mi][ni][e] = Cp[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; k4++) {
+    double af[2], bf[NI];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) af[mi] = -Ap[(k4 * 4 + tg) * apitch + mi * 8 + g];
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++) bf[ni] = Bp[(k4 * 4 + tg) * BP + ni * 8 + g];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) dmma884(c[mi][ni][0], c[mi][ni][1], af[mi], bf[ni]);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) Cp[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g] = c[mi][ni][e];
+}
+
+// Schedule per micro-panel jp (look-ahead inside the tile): panel(jp) | update of column block jp+1 by all warps |
+// warp 0 factors micro-block jp+1 WHILE warps 1..15 update the column blocks > jp+1. The serial chain is therefore
+// micro_diag + panel + one column block, the rest of the rank-16 update hides behind the next micro_diag.
 __global__ void __launch_bounds__(512, 1)
 base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, double* __restrict__ Dinv,
                     double* __restrict__ logdet_part, int* __restrict__ info, int gcol0) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* T = reinterpret_cast<double*>(smem_raw);   // [128][BP]
-  double* Pd = T + TILE * BP;                        // U micro-block of the current panel: (r, k) at k*MP + r
-  double* Wm = Pd + 16 * MP;                         // W = U^T micro-block (lower): (c, k) at k*MP + c
-  double* dinv = Wm + 16 * MP;                       // [128] reciprocal pivots
+  double* PdB = T + TILE * BP;                       // 2 x U micro-block of a panel: (r, k) at k*MP + r
+  double* WmB = PdB + 2 * 16 * MP;                   // 2 x W = U^T micro-block (lower): (c, k) at k*MP + c
+  double* psh = WmB + 2 * 16 * MP;                   // 2 x 16 pivot-column scratch of micro_diag
+  double* dinv = psh + 32;                           // [128] reciprocal pivots
   double* ldg = dinv + TILE;                         // [128] pivots
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int idx = tid; idx < TILE * TILE; idx += 512) {
@@ -305,57 +394,13 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
     T[col * BP + row] = row >= col ? S[row + (long)col * ld] : 0.0;
   }
   __syncthreads();
+  if (warp == 0) micro_diag(T, 0, PdB, WmB, psh, dinv, ldg, info, gcol0, lane);
+  __syncthreads();
 
   for (int jp = 0; jp < 8; jp++) {
     const int c0 = jp * 16;
-    // ---- (1) warp 0: 16x16 diagonal micro-block; values in registers, pivot vector exchanged through shared memory ---
-    if (warp == 0) {
-      const int rr = lane & 15, ch = (lane >> 4) * 8;   // lane owns row rr, columns ch..ch+7 of the micro-block
-      double v[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) v[q] = (rr >= ch + q) ? T[(c0 + ch + q) * BP + c0 + rr] : 0.0;
-      double my_inv = 0.0, my_l = 0.0;
-      double* psh = Pd;                                  // 2 x 16 scratch (Pd is rebuilt after the column loop)
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int ob = (j >> 3) * 16;                   // first lane of the half-warp that owns column j
-        const double d = __shfl_sync(0xffffffffu, v[j & 7], ob + j);
-        if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, gcol0 + c0 + j + 1);
-        const double inv = rsqrt(d);
-        const double l = d * inv;
-        double* pj = psh + (j & 1) * 16;
-        if ((lane >> 4) == (j >> 3)) {                  // owner half-warp: finalize column j, publish p
-          const double pown = (rr == j) ? inv : v[j & 7] * inv;
-          pj[rr] = pown;
-          v[j & 7] = (rr == j) ? l : pown;
-          if (rr == j) { my_inv = inv; my_l = l; }
-        }
-        __syncwarp();
-        const double prow = pj[rr];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int col = ch + q;
-          if (col > j && (rr >= col || rr <= j)) v[q] = fma(-prow, pj[col], v[q]);
-        }
-      }
-      __syncwarp();
-      // write back: lower + diagonal (pivots) and strict upper (= U entries) of the micro-block; operand copies
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int col = ch + q;
-        T[(c0 + col) * BP + c0 + rr] = v[q];
-        const double u = rr < col ? v[q] : 0.0;          // U(rr, col) strictly above the diagonal
-        Pd[col * MP + rr] = u;
-        Wm[rr * MP + col] = u;                            // W(col, rr) = U(rr, col); zeros above W's diagonal
-      }
-      __syncwarp();
-      if (rr >= ch && rr < ch + 8) {                      // this lane produced pivot rr
-        dinv[c0 + rr] = my_inv; ldg[c0 + rr] = my_l;
-        Pd[rr * MP + rr] = my_inv;
-        Wm[rr * MP + rr] = my_inv;
-      }
-    }
-    __syncthreads();
+    double* Pd = PdB + (jp & 1) * 16 * MP;
+    double* Wm = WmB + (jp & 1) * 16 * MP;
     // ---- (2) micro-panel with DMMA: P(rows, :) = T(rows, panel) W^T for the 7 row blocks outside the micro-block -----
     if (warp < 7) {
       const int g = lane >> 2, tg = lane & 3;
@@ -389,47 +434,22 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
           for (int e = 0; e < 2; e++) Ap[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g] = c[mi][ni][e];
     }
     __syncthreads();
-    // ---- (3) micro-tile updates with DMMA --------------------------------------------------------------------------
-    if (jp < 7) {
-      const int g = lane >> 2, tg = lane & 3;
-      const int ncol = 7 - jp;
-      // enumerate (ct, slot): ct = jp+1..7, slot in [0, jp+1 + 8-ct): slot <= jp -> rt = slot, else rt = ct + slot-(jp+1)
+    if (jp == 7) break;
+    // ---- (3a) column block jp+1 (8 micro-tiles, rows 0..7), two warps per micro-tile ---------------------------------
+    micro_update<1>(T, c0, jp, warp >> 1, jp + 1, (warp & 1) * 8, Pd, lane);
+    __syncthreads();
+    // ---- (1') warp 0: next diagonal micro-block  ||  (3b) warps 1..15: column blocks jp+2..7 -------------------------
+    if (warp == 0) {
+      micro_diag(T, c0 + 16, PdB + ((jp + 1) & 1) * 16 * MP, WmB + ((jp + 1) & 1) * 16 * MP, psh, dinv, ldg, info, gcol0,
+                 lane);
+    } else {
       int lin = 0;
-      for (int ci = 0; ci < ncol; ci++) {
-        const int ct = jp + 1 + ci;
-        const int nslot = jp + 1 + 8 - ct;
+      for (int ct = jp + 2; ct < 8; ct++) {
+        const int nslot = jp + 1 + 8 - ct;   // rows [0..jp] and [ct..7]
         for (int slot = 0; slot < nslot; slot++, lin++) {
-          if ((lin & 15) != warp) continue;
+          if (lin % 15 != warp - 1) continue;
           const int rt = slot <= jp ? slot : ct + slot - (jp + 1);
-          const double* Ap = (rt == jp) ? Pd : (T + c0 * BP + rt * 16);
-          const int apitch = (rt == jp) ? MP : BP;
-          const double* Bp = T + c0 * BP + ct * 16;
-          double* Cp = T + (ct * 16) * BP + rt * 16;
-          double c[2][2][2];
-#pragma unroll
-          for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-            for (int ni = 0; ni < 2; ni++)
-#pragma unroll
-              for (int e = 0; e < 2; e++) c[mi][ni][e] = Cp[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g];
-#pragma unroll
-          for (int k4 = 0; k4 < 4; k4++) {
-            double af[2], bf[2];
-#pragma unroll
-            for (int mi = 0; mi < 2; mi++) af[mi] = -Ap[(k4 * 4 + tg) * apitch + mi * 8 + g];
-#pragma unroll
-            for (int ni = 0; ni < 2; ni++) bf[ni] = Bp[(k4 * 4 + tg) * BP + ni * 8 + g];
-#pragma unroll
-            for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-              for (int ni = 0; ni < 2; ni++) dmma884(c[mi][ni][0], c[mi][ni][1], af[mi], bf[ni]);
-          }
-#pragma unroll
-          for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-            for (int ni = 0; ni < 2; ni++)
-#pragma unroll
-              for (int e = 0; e < 2; e++) Cp[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g] = c[mi][ni][e];
+          micro_update<2>(T, c0, jp, rt, ct, 0, Pd, lane);
         }
       }
     }
@@ -439,18 +459,19 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
   for (int idx = tid; idx < TILE * TILE; idx += 512) {
     const int row = idx & (TILE - 1), col = idx >> 7;
     const double x = T[col * BP + row];
-    if (row > col) {
-      Ldiag[row + col * TILE] = x;
-      S[row + (long)col * ld] = 0.0;
-      Dinv[row + col * TILE] = T[row * BP + col];    // W(row, col) = U(col, row), row > col
-    } else if (row == col) {
-      Ldiag[row + col * TILE] = ldg[row];
-      S[row + (long)col * ld] = dinv[row];
-      Dinv[row + col * TILE] = dinv[row];
-    } else {
-      Ldiag[row + col * TILE] = 0.0;
-      S[row + (long)col * ld] = x;                   // U(row, col)
-      Dinv[row + col * TILE] = 0.0;
+    Ldiag[row + col * TILE] = row > col ? x : (row == col ? ldg[row] : 0.0);
+    S[row + (long)col * ld] = row > col ? 0.0 : (row == col ? dinv[row] : x);   // U(row, col) above the diagonal
+  }
+  // Dinv = W = U^T needs T read transposed: lanes take consecutive rows and a column that rotates with lane/4, which
+  // spreads the 32 shared-memory reads over all banks (a plain column walk is a 16-way conflict) while every group of
+  // four lanes still writes one full 32-byte sector of Dinv.
+  for (int blk = warp; blk < 64; blk += 16) {
+    const int row = (blk & 3) * 32 + lane, cbase = (blk >> 2) * 8;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const int col = cbase + (((lane >> 2) + it) & 7);
+      const double v = row > col ? T[row * BP + col] : (row == col ? dinv[row] : 0.0);   // W(row, col) = U(col, row)
+      Dinv[row + col * TILE] = v;
     }
   }
   if (tid < 32) {
@@ -464,7 +485,7 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
 int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
                 cudaStream_t st) {
   static int which = -1;
-  constexpr int smem16 = (TILE * BP + 2 * 16 * MP + 2 * TILE) * 8;
+  constexpr int smem16 = (TILE * BP + 4 * 16 * MP + 32 + 2 * TILE) * 8;
   if (which < 0) {
     which = getenv("GPX_BASE_V1") ? 1 : 2;
     GPX_CUDA(cudaFuncSetAttribute(base_sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
