@@ -846,8 +846,13 @@ int gpx_pdinv(gpx_ctx* c, const double* A, int64_t N, int max_tries, double* Ai,
 int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double* mu, double* var) {
   if (!c || !Xnew || !mu || !var) GPX_FAIL("null argument");
   if (!c->have_eval) GPX_FAIL("no successful gpx_exact_eval to predict from");
-  if (c->dist) GPX_FAIL("gpx_predict is single-GPU in this version");
   if (M < 1) GPX_FAIL("empty Xnew");
+  // sharded factor: U = L^-T is column-distributed (block columns dealt round-robin), X / Y / alpha are replicated.
+  // Every rank forms K(X, Xnew) and the mean; the variance term sum_i (U^T Kx)_i^2 splits over the owned columns and is
+  // all-reduced. All ranks must call gpx_predict together (it contains a collective).
+  int drank = 0, dG = 1;
+  dist_world(c, &drank, &dG);
+  const long dNB = dist_block(c);
   GPX_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->st;
   const long ld = c->Npad, N = c->N;
@@ -858,6 +863,7 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   GPX_CUDA(cudaMalloc(&Kx, (size_t)pn.ld * ld * 8));
   GPX_CUDA(cudaMalloc(&Tx, (size_t)pn.ld * ld * 8));
   GPX_CUDA(cudaMemsetAsync(Kx, 0, (size_t)pn.ld * ld * 8, st));
+  if (dG > 1) GPX_CUDA(cudaMemsetAsync(Tx, 0, (size_t)pn.ld * ld * 8, st));   // columns of other ranks stay zero
   KBuildParams kb;
   memset(&kb, 0, sizeof(kb));
   kb.rowsT = c->dXsT; kb.ld_rows = ld; kb.sq_rows = c->dsq;
@@ -868,7 +874,8 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   // tmp = L^-1 Kx = U^T Kx, MAX_P columns per pass
   for (long m0 = 0; rc == 0 && m0 < M; m0 += MAX_P) {
     const int pc = (int)std::min<long>(MAX_P, M - m0);
-    rc = launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st);
+    rc = dG > 1 ? launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st, dG, drank, dNB)
+                : launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st);
     c->total_launches++;
   }
   std::vector<double> hK, hT;
@@ -880,6 +887,31 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   std::vector<double> hA((size_t)c->P * ld);
   if (rc == 0 && cudaMemcpyAsync(hA.data(), c->dAlpha, hA.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
   if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
+  // sums over the training index of this rank's part, completed over the ranks below
+  std::vector<double> ssq(full_cov ? (size_t)M * M : (size_t)M, 0.0);
+  if (rc == 0) {
+    if (!full_cov) {
+      for (long m = 0; m < M; m++) {
+        double s = 0.0;
+        for (long i = 0; i < N; i++) s += hT[m * ld + i] * hT[m * ld + i];
+        ssq[m] = s;
+      }
+    } else {
+      for (long a = 0; a < M; a++)
+        for (long b = 0; b < M; b++) {
+          double s = 0.0;
+          for (long i = 0; i < N; i++) s += hT[a * ld + i] * hT[b * ld + i];
+          ssq[a + b * M] = s;
+        }
+    }
+    if (dG > 1) {
+      if ((size_t)pn.ld * ld < ssq.size()) { gpx::set_error("gpx_predict: internal buffer size"); rc = -2; }
+      if (rc == 0 && cudaMemcpyAsync(Kx, ssq.data(), ssq.size() * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+      if (rc == 0) rc = dist_allreduce_sum(c, Kx, ssq.size(), st);
+      if (rc == 0 && cudaMemcpyAsync(ssq.data(), Kx, ssq.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+      if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
+    }
+  }
   cudaFree(Kx); cudaFree(Tx);
   if (rc) return rc;
   // small host epilogue: mu = Kx^T alpha, var = Kdiag - colsum(tmp^2) (or Kxx - tmp^T tmp)
@@ -890,11 +922,7 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
       mu[m * c->P + q] = s;
     }
   if (!full_cov) {
-    for (long m = 0; m < M; m++) {
-      double s = 0.0;
-      for (long i = 0; i < N; i++) s += hT[m * ld + i] * hT[m * ld + i];
-      var[m] = c->kp.variance - s;
-    }
+    for (long m = 0; m < M; m++) var[m] = c->kp.variance - ssq[m];
   } else {
     std::vector<double> kxx((size_t)M * M);
     double lsv[MAX_D];
@@ -902,11 +930,7 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
     rc = gpx_kern_K(c, c->kp.kind, c->kp.ard, c->kp.variance, lsv, Xnew, M, nullptr, M, c->D, kxx.data());
     if (rc) return rc;
     for (long a = 0; a < M; a++)
-      for (long b = 0; b < M; b++) {
-        double s = 0.0;
-        for (long i = 0; i < N; i++) s += hT[a * ld + i] * hT[b * ld + i];
-        var[a + b * M] = kxx[a * M + b] - s;
-      }
+      for (long b = 0; b < M; b++) var[a + b * M] = kxx[a * M + b] - ssq[a + b * M];
   }
   return 0;
 }

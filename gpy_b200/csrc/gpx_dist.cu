@@ -123,6 +123,8 @@ void dist_free(gpx_ctx* c) {
   d->Bc = d->Bc2 = d->blkpart = nullptr;
 }
 
+long dist_block(const gpx_ctx* c) { return c->dist ? c->dist->NB : 0; }
+
 int dist_world(const gpx_ctx* c, int* rank, int* nranks) {
   if (c->dist && c->dist->comm) { *rank = c->dist->rank; *nranks = c->dist->G; }
   else { *rank = 0; *nranks = 1; }

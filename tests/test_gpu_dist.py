@@ -25,6 +25,7 @@ def test_two_gpu_sharded_evaluation_matches_oracle():
         lml_abs = float(f[f.index("abs") + 1])
         grad_rel = float(f[f.index("grad") + 2])
         assert lml_abs <= 1e-8 and grad_rel <= 1e-6, l
+        assert float(f[f.index("predict") + 1]) <= 1e-7, l
 
 
 def test_two_gpu_row_sharded_sparse_matches_oracle():
