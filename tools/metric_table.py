@@ -8,11 +8,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from gpy_b200 import _ffi
 from oracle import gpy_oracle as o
-from bench import synthetic, theta_for_step
+from bench import synthetic, theta_for_step, ensure_oracle_native
 
 D = 8
 sizes = [int(s) for s in sys.argv[1].split(",")] if len(sys.argv) > 1 else [512, 4096, 16384, 65536]
 cpu_sizes = [int(s) for s in sys.argv[2].split(",")] if len(sys.argv) > 2 else [512, 4096]
+native = ensure_oracle_native()
 eng = _ffi.Engine(0)
 peak = eng.measure_fp64_peak()
 rows = []
@@ -31,7 +32,7 @@ for N in sizes:
         for s in range(4):
             th = theta_for_step(D, s)
             t0 = time.perf_counter()
-            l0, g0, _ = o.eval_lml_grad(X, Y, "rbf", True, *th, native=True)
+            l0, g0, _ = o.eval_lml_grad(X, Y, "rbf", True, *th, native=native)
             cs.append(time.perf_counter() - t0)
         row.update({"cpu_s_per_eval": float(np.median(cs[1:])), "cpu_evals_per_s": 1.0 / float(np.median(cs[1:])),
                     "parity_lml_abs": abs(l0 - lml), "parity_grad_rel_max": float(np.max(np.abs(g - g0) / np.abs(g0)))})
