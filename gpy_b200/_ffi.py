@@ -35,6 +35,8 @@ EXPORTS = {
     "gpx_set_data": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, ctypes.c_int]),
     "gpx_exact_eval": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_int, _dp, _dp, _dp]),
+    "gpx_exact_eval_het": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_double,
+                                          ctypes.c_int, _dp, _dp, _dp, _dp]),
     "gpx_get": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
     "gpx_predict": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp]),
     "gpx_kern_K": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64, _dp,
@@ -152,6 +154,21 @@ class Engine(object):
                                     ctypes.byref(lml), _ptr(grad), ctypes.byref(jit))
         check(rc, "gpx_exact_eval")
         return lml.value, grad, jit.value
+
+    def exact_eval_het(self, kind, ARD, variance, lengthscale, noise_variances, jitter=1e-8, max_tries=5):
+        """one noise variance per data point -> (log_marginal, gradient[variance, lengthscale.., sum], dnoise (N,), jitter)"""
+        k, a, ls = _theta(kind, ARD, lengthscale, self.D)
+        nv = _f64(np.asarray(noise_variances).reshape(-1))
+        if nv.size != self.N:
+            raise ValueError("need one noise variance per data point")
+        lml = ctypes.c_double()
+        jit = ctypes.c_double()
+        grad = np.zeros(ls.size + 2)
+        dnoise = np.zeros(self.N)
+        rc = self._L.gpx_exact_eval_het(self._h, k, a, float(variance), _ptr(ls), _ptr(nv), float(jitter), int(max_tries),
+                                        ctypes.byref(lml), _ptr(grad), _ptr(dnoise), ctypes.byref(jit))
+        check(rc, "gpx_exact_eval_het")
+        return lml.value, grad, dnoise, jit.value
 
     def get(self, which):
         if which == "alpha":

@@ -115,6 +115,8 @@ int gpx_destroy(gpx_ctx* c) {
   for (auto e : c->sync_ev) cudaEventDestroy(e);
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->res) cudaFree(c->res);
+  if (c->dNoiseVec) cudaFree(c->dNoiseVec);
+  if (c->dDnoise) cudaFree(c->dDnoise);
   if (c->info) cudaFree(c->info);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_info) cudaFreeHost(c->h_info);
@@ -374,6 +376,7 @@ static int run_lauum(gpx_ctx* c, double* kinv_out, Recorder* rec) {
   pl.N = (int)c->N; pl.P = c->P;
   pl.partials = c->partials;
   pl.kinv_out = kinv_out;
+  pl.dnoise_out = (c->het && rec) ? c->dDnoise : nullptr;
   pl.kp = c->kp;
   double flops = 0;
   for (int r = 0; r < nt; r++) flops += (double)(r + 1) * 2.0 * TILE * TILE * (double)(c->Npad - (long)r * TILE);
@@ -401,7 +404,8 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     kb.out = c->S; kb.ld = ld;
     kb.nrows = c->N; kb.ncols = c->N;
     kb.sym = 1; kb.same = 1;
-    kb.diag_add = (c->noise + c->jitter) + extra_jitter;
+    kb.diag_add = ((c->het ? 0.0 : c->noise) + c->jitter) + extra_jitter;
+    kb.diag_vec = c->het ? c->dNoiseVec : nullptr;
     kb.kp = c->kp;
     const int h = rec.begin(PH_KBUILD);
     GPX_CHECK(launch_kbuild(kb, nt, nt, st));
@@ -439,13 +443,31 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
 
 extern "C" {
 
-int gpx_exact_eval(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, double noise,
-                   double jitter, int max_tries, double* lml, double* grad, double* jitter_used) {
+}  // extern "C"
+
+// noise_vec == nullptr: homoscedastic (`noise`); else N per-point variances (`noise` = their mean, used by the ladder)
+static int exact_eval_impl(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, double noise,
+                           const double* noise_vec, double jitter, int max_tries, double* lml, double* grad,
+                           double* dnoise, double* jitter_used) {
   if (!c || !lengthscale || !lml || !grad) GPX_FAIL("null argument");
   if (!c->S) GPX_FAIL("gpx_set_data has not been called");
   if (!(noise >= 0)) GPX_FAIL("noise variance must be non-negative");
   GPX_CUDA(cudaSetDevice(c->device));
   GPX_CHECK(fill_kp(c->kp, kind, ard, c->D, variance, lengthscale));
+  c->het = noise_vec != nullptr;
+  if (c->het) {
+    if (c->dist) GPX_FAIL("heteroscedastic evaluation is single-GPU");
+    if (!dnoise) GPX_FAIL("null argument");
+    if (c->het_cap < c->Npad) {
+      if (c->dNoiseVec) cudaFree(c->dNoiseVec);
+      if (c->dDnoise) cudaFree(c->dDnoise);
+      c->dNoiseVec = c->dDnoise = nullptr;
+      GPX_CUDA(cudaMalloc(&c->dNoiseVec, (size_t)c->Npad * 8));
+      GPX_CUDA(cudaMalloc(&c->dDnoise, (size_t)c->Npad * 8));
+      c->het_cap = c->Npad;
+    }
+    GPX_CUDA(cudaMemcpyAsync(c->dNoiseVec, noise_vec, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->st));
+  }
   c->noise = noise;
   c->jitter = jitter;
   c->have_eval = false;
@@ -503,8 +525,34 @@ int gpx_exact_eval(gpx_ctx* c, int kind, int ard, double variance, const double*
   }
   *lml = c->h_res[0];
   for (int q = 0; q < nl + 2; q++) grad[q] = c->h_res[1 + q];
+  if (c->het) {
+    GPX_CUDA(cudaMemcpyAsync(dnoise, c->dDnoise, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->st));
+    GPX_CUDA(cudaStreamSynchronize(c->st));
+  }
   c->have_eval = true;
   return 0;
+}
+
+extern "C" {
+
+int gpx_exact_eval(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, double noise,
+                   double jitter, int max_tries, double* lml, double* grad, double* jitter_used) {
+  return exact_eval_impl(c, kind, ard, variance, lengthscale, noise, nullptr, jitter, max_tries, lml, grad, nullptr,
+                         jitter_used);
+}
+
+int gpx_exact_eval_het(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale,
+                       const double* noise_variances, double jitter, int max_tries, double* lml, double* grad,
+                       double* dnoise, double* jitter_used) {
+  if (!c || !noise_variances) GPX_FAIL("null argument");
+  double mean = 0.0;
+  for (int64_t i = 0; i < c->N; i++) {
+    if (!(noise_variances[i] >= 0)) GPX_FAIL("noise variances must be non-negative");
+    mean += noise_variances[i];
+  }
+  mean /= (double)std::max<int64_t>(c->N, 1);
+  return exact_eval_impl(c, kind, ard, variance, lengthscale, mean, noise_variances, jitter, max_tries, lml, grad, dnoise,
+                         jitter_used);
 }
 
 int gpx_measure_fp64_peak(gpx_ctx* c, double* tflops) {

@@ -153,6 +153,7 @@ struct GemmParams {
   int own_G, own_g, own_blk;   // UPDATE / PANEL: a tile is processed iff ((r / own_blk) % own_G) == own_g
   int k_G, k_g, k_blk;         // LAUUM: only k-tiles inside column blocks kb == k_g (mod k_G), k_blk tiles per block
   KernParams kp;
+  double* dnoise_out;   // LAUUM epilogue, optional: diag(dL_dK)_i per data point (heteroscedastic noise gradients)
 };
 
 int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t st);

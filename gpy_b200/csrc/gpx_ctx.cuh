@@ -44,6 +44,9 @@ struct gpx_ctx {
   bool have_kinv = false;
   gpx::KernParams kp{};
   double noise = 0, jitter = 0, jitter_extra = 0;
+  // heteroscedastic evaluation (gpx_exact_eval_het): per-point noise variances in, diag(dL_dK) out
+  bool het = false;
+  double* dNoiseVec = nullptr; double* dDnoise = nullptr; long het_cap = 0;
   // accounting
   gpx_stats stats{};
   int64_t total_launches = 0;

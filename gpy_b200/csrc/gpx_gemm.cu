@@ -307,7 +307,10 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
         double dl = 0.5 * (aa - (double)P * kinv);
         if (gi >= p.N || gj >= p.N) dl = 0.0;
         gvar = fma(w * k, dl, gvar);
-        if (gi == gj) gnoise += dl;
+        if (gi == gj) {
+          gnoise += dl;
+          if (p.dnoise_out && gi < p.N) p.dnoise_out[gi] = dl;
+        }
         const double G = variance * dk * dl;
         if (ard) {
           st[e * sthr] = (rr != 0.0) ? w * G / rr : 0.0;   // stationary.py:205,225-232: 1/r with 1/0 := 0

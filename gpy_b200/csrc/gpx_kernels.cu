@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
     r2 = fmax(r2, 0.0);
     double v = variance * k_unit<KIND>(sqrt(r2) * inv_ls);
     if (p.sym) {
-      if (gi == gj) v = v + p.diag_add;
+      if (gi == gj) v = v + p.diag_add + ((p.diag_vec && row_valid) ? p.diag_vec[gi] : 0.0);
       if (!row_valid || gj >= p.ncols) v = (gi == gj) ? 1.0 : 0.0;
       outp[(long)j * p.ld] = v;
     } else if (row_valid && gj < p.ncols) {

@@ -13,6 +13,7 @@ struct KBuildParams {
   int sym;                             // 1: factor workspace mode (lower tiles, zero upper tiles, identity padding, +diag_add)
   int same;                            // 1: both operands are the same point set -> exact zero distance on the diagonal
   double diag_add;                     // noise + jitter (sym mode)
+  const double* diag_vec;              // optional per-point noise variances added on the diagonal as well (sym mode)
   int own_G, own_g, own_blk;           // multi-GPU: only row tiles with ((rt / own_blk) % own_G) == own_g (0 = all)
   KernParams kp;
 };

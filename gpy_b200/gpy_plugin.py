@@ -94,7 +94,9 @@ def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi)
                                                                          Y_metadata, K, variance, Z_tilde)
             if variance is None:
                 variance = likelihood.gaussian_variance(Y_metadata)
-            noise = float(np.squeeze(np.asarray(variance)))
+            nvec = np.asarray(variance, dtype=np.float64).reshape(-1)
+            het = nvec.size > 1                      # HeteroscedasticGaussian (likelihoods/gaussian.py:347-362)
+            noise = None if het else float(nvec[0])
             Xs = np.ascontiguousarray(kern._slice_X(X)[0] if _returns_tuple(kern, X) else kern._slice_X(X),
                                       dtype=np.float64)
             Yc = np.ascontiguousarray(Y, dtype=np.float64)
@@ -103,13 +105,18 @@ def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi)
                 self.engine.set_data(Xs, Yc)
                 self._data_key = key
             k, ard, var, ls = kern._gpx_theta()
-            lml, grad, _ = self.engine.exact_eval(k, ard, var, ls, noise, jitter=1e-8, max_tries=5)
+            if het:
+                lml, grad, dnoise, _ = self.engine.exact_eval_het(k, ard, var, ls, nvec, jitter=1e-8, max_tries=5)
+                dL_dthetaL = likelihood.exact_inference_gradients(dnoise, Y_metadata)   # gaussian.py:358-359
+            else:
+                lml, grad, _ = self.engine.exact_eval(k, ard, var, ls, noise, jitter=1e-8, max_tries=5)
+                dL_dthetaL = grad[-1]
             if Z_tilde is not None:
                 lml += Z_tilde
             post = PosteriorExact(self.engine, Yc.shape[0], Yc.shape[1])
             dlen = grad[1:-1] if ard else grad[1]
             dL_dK = DeviceGradient(self.engine, kern._gpx_state_key(), grad[0], dlen, Yc.shape[0])
-            return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
+            return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": dL_dthetaL, "dL_dm": _LazyAlpha(post)}
 
     B200ExactGaussianInference.__name__ = B200ExactGaussianInference.__qualname__ = "ExactGaussianInference"
     return types.SimpleNamespace(ExactGaussianInference=B200ExactGaussianInference, **kernels)

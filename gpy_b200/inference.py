@@ -39,6 +39,29 @@ class Gaussian(Parameterized):
         return mu, var
 
 
+class HeteroscedasticGaussian(Gaussian):
+    """GPy.likelihoods.HeteroscedasticGaussian (gaussian.py:347-377): one noise variance per output index."""
+
+    def __init__(self, Y_metadata, variance=1., name="het_Gauss"):
+        idx = np.asarray(Y_metadata["output_index"])
+        super(HeteroscedasticGaussian, self).__init__(np.ones(idx.shape[0]) * variance, name)   # gaussian.py:356
+
+    def gaussian_variance(self, Y_metadata=None):
+        return self.variance.values[np.asarray(Y_metadata["output_index"]).flatten()]            # gaussian.py:361-362
+
+    def exact_inference_gradients(self, dL_dKdiag, Y_metadata=None):
+        return np.asarray(dL_dKdiag)[np.asarray(Y_metadata["output_index"]).flatten()]            # gaussian.py:358-359
+
+    def update_gradients(self, grad):
+        self.variance.gradient = np.asarray(grad, dtype=np.float64).reshape(-1)
+
+    def predictive_values(self, mu, var, full_cov=False, Y_metadata=None):
+        _s = self.gaussian_variance(Y_metadata)                                                  # gaussian.py:364-373
+        if full_cov:
+            return mu, var + np.eye(var.shape[0]) * _s
+        return mu, var + _s.reshape(-1, 1)
+
+
 class PosteriorExact(object):
     """Posterior whose big members live in HBM and are fetched lazily (posterior.py:21-77 constructor contract:
     woodbury_chol = L, woodbury_vector = alpha, K = noise-free kernel matrix)."""
@@ -132,13 +155,26 @@ class ExactGaussianInference(object):
                   Z_tilde=None):
         if variance is None:
             variance = likelihood.gaussian_variance(Y_metadata)
-        noise = float(np.squeeze(np.asarray(variance)))
+        nvec = np.asarray(variance, dtype=np.float64).reshape(-1)
+        het = nvec.size > 1                          # HeteroscedasticGaussian: a vector reaches diag.add (:55-56)
+        noise = nvec if het else float(nvec[0])
         if mean_function is not None or K is not None or not isinstance(kern, Stationary):
-            return self._generic_inference(kern, X, Y, noise, mean_function, K, Z_tilde)
+            return self._generic_inference(kern, X, Y, noise, mean_function, K, Z_tilde, likelihood, Y_metadata)
         Xs = kern._slice_X(X)
         Y = np.ascontiguousarray(Y, dtype=np.float64)
         self._bind(Xs, Y)
         kind, ard, var, ls = kern._theta()
+        if het:
+            if nvec.size != Y.shape[0]:
+                raise ValueError("heteroscedastic noise needs one variance per data point")
+            lml, grad, dnoise, _ = self.engine.exact_eval_het(kind, ard, var, ls, nvec, jitter=1e-8, max_tries=5)
+            if Z_tilde is not None:
+                lml += Z_tilde
+            N, P = Y.shape
+            post = PosteriorExact(self.engine, N, P)
+            dL_dK = DeviceGradient(self.engine, kern._state_key(), grad[0], grad[1:-1], N)
+            dL_dthetaL = likelihood.exact_inference_gradients(dnoise, Y_metadata)              # :72 with gaussian.py:358
+            return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": dL_dthetaL, "dL_dm": _LazyAlpha(post)}
         # exact_gaussian_inference.py:56: +1e-8 on the diagonal, always; jitchol ladder of 5 (util/linalg.py:56)
         lml, grad, _ = self.engine.exact_eval(kind, ard, var, ls, noise, jitter=1e-8, max_tries=5)
         if Z_tilde is not None:
@@ -150,7 +186,7 @@ class ExactGaussianInference(object):
         return post, lml, grad_dict
 
 
-    def _generic_inference(self, kern, X, Y, noise, mean_function, K, Z_tilde):
+    def _generic_inference(self, kern, X, Y, noise, mean_function, K, Z_tilde, likelihood=None, Y_metadata=None):
         """exact_gaussian_inference.py:37-74 for the cases the fused call does not cover (mean function, precomputed K,
         foreign kernel): the N^3 part (jitchol + dpotri, util/linalg.py:193-214) still runs on the device through
         gpx_pdinv; the O(N^2 P) remainder is NumPy on the host because K arrives as / has to be returned as ndarrays."""
@@ -159,7 +195,7 @@ class ExactGaussianInference(object):
         if K is None:
             K = kern.K(X)
         Ky = np.array(K, dtype=np.float64, copy=True)
-        Ky[np.diag_indices_from(Ky)] += noise + 1e-8
+        Ky[np.diag_indices_from(Ky)] += np.asarray(noise) + 1e-8
         Wi, LW, _, W_logdet, _ = _ffi.pdinv(Ky, maxtries=5, want=("Ai", "L"), engine=self.engine)
         alpha = np.dot(Wi, YYT_factor)
         log_marginal = 0.5 * (-YYT_factor.size * np.log(2 * np.pi) - YYT_factor.shape[1] * W_logdet
@@ -168,8 +204,12 @@ class ExactGaussianInference(object):
             log_marginal += Z_tilde
         dL_dK = 0.5 * (np.dot(alpha, alpha.T) - YYT_factor.shape[1] * Wi)
         self._data_key = None   # the context workspace was re-used
+        if np.ndim(noise) > 0 and likelihood is not None:
+            dL_dthetaL = likelihood.exact_inference_gradients(np.diag(dL_dK), Y_metadata)
+        else:
+            dL_dthetaL = float(np.trace(dL_dK))
         return (HostPosterior(LW, alpha, K), float(log_marginal),
-                {"dL_dK": dL_dK, "dL_dthetaL": float(np.trace(dL_dK)), "dL_dm": alpha})
+                {"dL_dK": dL_dK, "dL_dthetaL": dL_dthetaL, "dL_dm": alpha})
 
 
 class HostPosterior(object):

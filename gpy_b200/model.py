@@ -12,16 +12,17 @@ paramz are importable, use the real GPy model with the plugin classes of gpy_b20
 """
 import numpy as np
 
-from .inference import ExactGaussianInference, Gaussian
+from .inference import ExactGaussianInference, Gaussian, HeteroscedasticGaussian
 from .kern import RBF
 from .param import Logexp, Parameterized
 
 
 class GP(Parameterized):
     def __init__(self, X, Y, kernel, likelihood, mean_function=None, inference_method=None, name="gp", device=0,
-                 engine=None):
+                 engine=None, Y_metadata=None):
         super(GP, self).__init__(name)
         self.mean_function = mean_function
+        self.Y_metadata = Y_metadata
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
         assert X.ndim == 2
@@ -45,7 +46,7 @@ class GP(Parameterized):
     # ---- one evaluation: gp.py:269-282 -------------------------------------------------------------------------
     def parameters_changed(self):
         self.posterior, self._log_marginal_likelihood, self.grad_dict = self.inference_method.inference(
-            self.kern, self.X, self.likelihood, self.Y, self.mean_function, None)
+            self.kern, self.X, self.likelihood, self.Y, self.mean_function, self.Y_metadata)
         self.likelihood.update_gradients(self.grad_dict["dL_dthetaL"])
         self.kern.update_gradients_full(self.grad_dict["dL_dK"], self.X)
 
@@ -184,6 +185,24 @@ class GP(Parameterized):
 
     def predict_noiseless(self, Xnew, full_cov=False, Y_metadata=None, kern=None):
         return self.predict(Xnew, full_cov, Y_metadata, kern, None, False)
+
+
+class GPHeteroscedasticRegression(GP):
+    """GPy.models.GPHeteroscedasticRegression (gp_heteroscedastic_regression.py:10-37): one Gaussian noise variance per
+    data point (HeteroscedasticGaussian), exact inference; "does not make inference on the noise outside the training
+    set", so predict() needs Y_metadata for the new points (or include_likelihood=False)."""
+
+    def __init__(self, X, Y, kernel=None, Y_metadata=None, device=0, engine=None):
+        Ny = np.asarray(Y).shape[0]
+        if Y_metadata is None:
+            Y_metadata = {"output_index": np.arange(Ny)[:, None]}          # :26-27
+        else:
+            assert Y_metadata["output_index"].shape[0] == Ny
+        if kernel is None:
+            kernel = RBF(np.asarray(X).shape[1])                             # :31-32
+        likelihood = HeteroscedasticGaussian(Y_metadata)                      # :35
+        super(GPHeteroscedasticRegression, self).__init__(X, Y, kernel, likelihood, name="gp_het", device=device,
+                                                          engine=engine, Y_metadata=Y_metadata)
 
 
 class GPRegression(GP):

@@ -65,6 +65,15 @@ int gpx_set_data(gpx_ctx* ctx, const double* X, int64_t N, int D, const double* 
 int gpx_exact_eval(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, double noise,
                    double jitter, int max_tries, double* lml, double* grad, double* jitter_used);
 
+/* The same evaluation with one noise variance PER DATA POINT (HeteroscedasticGaussian, GPy/likelihoods/gaussian.py:347-362;
+ * GPy/models/gp_heteroscedastic_regression.py:10-37): Ky = K + diag(noise_variances + jitter)
+ * (exact_gaussian_inference.py:55-56 with a vector `variance`), and dL_dthetaL = diag(dL_dK) per point
+ * (gaussian.py:358-359 applied to exact_gaussian_inference.py:72) written to dnoise (N doubles) by the fused K^-1
+ * epilogue. grad keeps the layout of gpx_exact_eval; its last entry is the sum of dnoise. Single-GPU. */
+int gpx_exact_eval_het(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale,
+                       const double* noise_variances, double jitter, int max_tries, double* lml, double* grad,
+                       double* dnoise, double* jitter_used);
+
 /* Lazy device->host fetch of N^2 / N*P results of the last gpx_exact_eval (Posterior / grad_dict consumers:
  * GPy/inference/latent_function_inference/posterior.py:21-77; exact_gaussian_inference.py:74). */
 int gpx_get(gpx_ctx* ctx, int which, double* out_host);

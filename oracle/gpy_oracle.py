@@ -326,9 +326,14 @@ def exact_inference(kern, X, Y, noise_variance, K=None):
     alpha, _ = dpotrs(LW, YYT_factor, lower=1)  # :60
     log_marginal = 0.5 * (-Y.size * LOG_2_PI - Y.shape[1] * W_logdet - np.sum(alpha * YYT_factor))  # :62
     dL_dK = 0.5 * (tdot(alpha) - Y.shape[1] * Wi)  # :70
-    dL_dthetaL = np.sum(np.diag(dL_dK))  # :72 -> likelihoods/gaussian.py:78-79
+    if np.ndim(noise_variance) > 0 and np.size(noise_variance) > 1:
+        # HeteroscedasticGaussian with output_index = arange(N) (likelihoods/gaussian.py:356-362,
+        # models/gp_heteroscedastic_regression.py:26-27): `variance` reaching :56 is the N-vector, :72 keeps the diagonal
+        dL_dthetaL = np.diag(dL_dK).copy()  # gaussian.py:358-359
+    else:
+        dL_dthetaL = float(np.sum(np.diag(dL_dK)))  # :72 -> likelihoods/gaussian.py:78-79
     return dict(L=LW, alpha=alpha, K=K, Wi=Wi, logdet=W_logdet, log_marginal=float(log_marginal), dL_dK=dL_dK,
-                dL_dthetaL=float(dL_dthetaL), dL_dm=alpha)
+                dL_dthetaL=dL_dthetaL, dL_dm=alpha)
 
 
 def eval_lml_grad(X, Y, kind, ARD, variance, lengthscale, noise_variance, native=None):
@@ -346,7 +351,7 @@ def eval_lml_grad(X, Y, kind, ARD, variance, lengthscale, noise_variance, native
         dvar, dlen = kern.update_gradients_full(res["dL_dK"], X)  # gp.py:280
     finally:
         NATIVE_LINALG = prev
-    grad = np.concatenate([[dvar], np.atleast_1d(dlen), [res["dL_dthetaL"]]])
+    grad = np.concatenate([[dvar], np.atleast_1d(dlen), np.atleast_1d(res["dL_dthetaL"])])
     return res["log_marginal"], grad, res
 
 

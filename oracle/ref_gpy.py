@@ -88,6 +88,7 @@ def load():
         VarDTC=vdtc.VarDTC,
         RBF=rbf.RBF, Exponential=stat.Exponential, Matern32=stat.Matern32, Matern52=stat.Matern52,
         ExactGaussianInference=egi.ExactGaussianInference, Gaussian=gauss.Gaussian,
+        HeteroscedasticGaussian=gauss.HeteroscedasticGaussian,
         linalg=sys.modules["GPy.util.linalg"], diag=sys.modules["GPy.util.diag"], stationary=stat,
         __version__=open(os.path.join(REF, "GPy", "__version__.py")).read().split('"')[1])
     _loaded = ns
@@ -118,6 +119,25 @@ def evaluate(G, X, Y, kind, ARD, variance, lengthscale, noise, Xnew=None):
         mu, var = lik.predictive_values(mu, var)                                  # gaussian.py:102-110
         out["mu"], out["var"] = np.asarray(mu), np.asarray(var)
     return out
+
+
+def evaluate_het(G, X, Y, kind, ARD, variance, lengthscale, noise_vec):
+    """GPHeteroscedasticRegression's evaluation (models/gp_heteroscedastic_regression.py:22-37 + core/gp.py:278-280) with
+    the reference's own HeteroscedasticGaussian / ExactGaussianInference / kernel objects."""
+    import numpy as np
+    N, D = X.shape
+    Y_metadata = {"output_index": np.arange(N)[:, None]}                          # gp_heteroscedastic_regression.py:26-27
+    kern = getattr(G, KERNELS[kind])(D, variance=variance, lengthscale=lengthscale, ARD=ARD)
+    lik = G.HeteroscedasticGaussian(Y_metadata)
+    lik.variance[:] = np.asarray(noise_vec).reshape(lik.variance.shape)
+    inf = G.ExactGaussianInference()
+    posterior, lml, grad_dict = inf.inference(kern, X, lik, Y, None, Y_metadata)  # gp.py:278
+    lik.update_gradients(grad_dict["dL_dthetaL"])                                  # gp.py:279
+    kern.update_gradients_full(grad_dict["dL_dK"], X)                              # gp.py:280
+    grad = np.concatenate([np.atleast_1d(kern.variance.gradient).reshape(-1),
+                           np.atleast_1d(kern.lengthscale.gradient).reshape(-1),
+                           np.asarray(lik.variance.gradient).reshape(-1)])
+    return dict(lml=float(lml), grad=grad, alpha=np.asarray(posterior.woodbury_vector))
 
 
 def evaluate_sparse(G, X, Y, Z, kind, ARD, variance, lengthscale, noise):

@@ -374,3 +374,55 @@ def test_sparse_gp_vardtc(kind, ARD, N, M, D, P, device_algebra):
     np.testing.assert_allclose(var, var0, rtol=1e-5, atol=1e-8)
     if N <= 700:
         assert m.checkgrad(step=1e-5)   # 1e-6 drowns the O(1e-2) inducing-point gradients in fp64 round-off of the bound
+
+
+@pytest.mark.parametrize("kind,ARD,N,D,P", [("rbf", True, 300, 3, 1), ("matern52", False, 700, 2, 2), ("exponential", True, 129, 4, 1)])
+def test_heteroscedastic_noise(kind, ARD, N, D, P):
+    """One noise variance per data point (HeteroscedasticGaussian, likelihoods/gaussian.py:347-362): gpx_exact_eval_het
+    against the oracle (pinned to the reference's own objects in tests/test_reference_crosscheck.py): LML, kernel
+    gradients, the N per-point noise gradients diag(dL_dK), alpha."""
+    rng = np.random.default_rng(N)
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.stack([np.sin(X).sum(1) + 0.2 * rng.standard_normal(N) for _ in range(P)], 1)
+    ls = rng.uniform(0.8, 2.0, D) if ARD else 1.3
+    nv = rng.uniform(0.01, 0.3, N)
+    lml0, g0, res = o.eval_lml_grad(X, Y, kind, ARD, 1.4, ls, nv)
+    e = _ffi.Engine(0)
+    e.set_data(X, Y)
+    lml, g, dn, _ = e.exact_eval_het(kind, ARD, 1.4, ls, nv)
+    nl = D if ARD else 1
+    assert abs(lml - lml0) <= LML_ATOL
+    np.testing.assert_allclose(g[:1 + nl], g0[:1 + nl], rtol=GRAD_RTOL, atol=1e-9)
+    np.testing.assert_allclose(dn, g0[1 + nl:], rtol=GRAD_RTOL, atol=1e-9)
+    assert abs(g[-1] - dn.sum()) <= 1e-9 * max(1.0, np.abs(dn).sum())
+    assert rel(e.get("alpha"), res["alpha"]) < 1e-9
+    # the homoscedastic call on the same context afterwards is unaffected
+    lml1, g1, _ = e.exact_eval(kind, ARD, 1.4, ls, 0.1)
+    lml2, g2, _ = o.eval_lml_grad(X, Y, kind, ARD, 1.4, ls, 0.1)
+    assert abs(lml1 - lml2) <= LML_ATOL
+    np.testing.assert_allclose(g1, g2, rtol=GRAD_RTOL, atol=1e-9)
+    e.close()
+
+
+def test_heteroscedastic_model():
+    """gpy_b200.GPHeteroscedasticRegression (models/gp_heteroscedastic_regression.py:10-37): parameter vector
+    [variance, lengthscale, N noise variances], gradient check, prediction with Y_metadata."""
+    rng = np.random.default_rng(5)
+    N = 40
+    X = rng.uniform(-3, 3, (N, 1))
+    Y = np.sin(X) + rng.standard_normal((N, 1)) * (0.05 + 0.2 * (X > 0))
+    m = gpy_b200.GPHeteroscedasticRegression(X, Y, gpy_b200.Matern32(1, lengthscale=1.2))
+    m.likelihood.variance.values[...] = rng.uniform(0.02, 0.2, N)
+    m.parameters_changed()
+    assert len(m.gradient) == 1 + 1 + N
+    lml0, g0, res = o.eval_lml_grad(X, Y, "matern32", False, 1.0, 1.2, m.likelihood.variance.values.copy())
+    assert abs(m.log_likelihood() - lml0) <= LML_ATOL
+    np.testing.assert_allclose(m.gradient, g0, rtol=GRAD_RTOL, atol=1e-9)
+    assert m.checkgrad(step=1e-5)
+    Xn = rng.uniform(-3, 3, (5, 1))
+    mu, var = m.predict(Xn, Y_metadata={"output_index": np.arange(5)[:, None]})
+    mu0, var0 = o.raw_predict(o.StationaryOracle("matern32", 1, 1.0, 1.2, False), X, res["L"], res["alpha"], Xn)
+    np.testing.assert_allclose(mu, mu0, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, var0 + m.likelihood.variance.values[:5].reshape(-1, 1), rtol=1e-7, atol=1e-10)
+    d = m.optimize(max_iters=15)
+    assert np.isfinite(m.log_likelihood()) and m.log_likelihood() >= lml0 - 1e-6

@@ -106,3 +106,22 @@ def test_oracle_vardtc_equals_reference(G, kind, ARD):
     np.testing.assert_allclose(res["woodbury_vector"], r["woodbury_vector"], rtol=1e-8, atol=1e-12)
     np.testing.assert_allclose(res["woodbury_inv"], r["woodbury_inv"], rtol=1e-7, atol=1e-10)
     np.testing.assert_allclose(res["dL_dKnm"], r["dL_dKnm"], rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,ARD", [("rbf", True), ("matern32", False)])
+def test_oracle_heteroscedastic_equals_reference(G, kind, ARD):
+    """One noise variance per data point: oracle restatement against the reference's HeteroscedasticGaussian +
+    ExactGaussianInference objects (likelihoods/gaussian.py:347-362, models/gp_heteroscedastic_regression.py:22-37)."""
+    from oracle import ref_gpy
+    for (N, D, seed) in ((70, 2, 3), (211, 5, 4)):
+        X, Y = o.synthetic(N, D, seed)
+        rng = np.random.default_rng(seed)
+        ls = rng.uniform(0.8, 2.5, D) if ARD else float(rng.uniform(0.8, 2.5))
+        var = float(rng.uniform(0.5, 2))
+        nv = rng.uniform(0.01, 0.3, N)
+        r = ref_gpy.evaluate_het(G, X, Y, kind, ARD, var, ls, nv)
+        lml, g, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, nv)
+        assert g.size == r["grad"].size == 1 + (D if ARD else 1) + N
+        assert abs(r["lml"] - lml) <= 1e-10 * max(1.0, abs(lml))
+        np.testing.assert_allclose(g, r["grad"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(res["alpha"], r["alpha"], rtol=1e-10, atol=1e-12)
