@@ -874,6 +874,9 @@ int launch_untranspose(const double* in, long n, int p, long ld, double* out, cu
 // (stationary.py:193-243) for K(X, X2), dL_dK row-major N x M. One CTA per (128 x 128) tile, thread-mapped index is
 // the X2 point (contiguous in the row-major dL_dK), per-tile partials reduced by finalize-style fixed order on host.
 // =================================================================================================================
+// ONE pass over the tile: every element's K, dK/dr and dL_dK are formed once; the ARD lengthscale sums live in DREG
+// registers per thread (the first version re-derived the element D+1 times, once per lengthscale).
+template <int DREG>
 __global__ void __launch_bounds__(256) grad_full_kernel(GradFullParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int D = p.kp.D;
@@ -893,50 +896,62 @@ __global__ void __launch_bounds__(256) grad_full_kernel(GradFullParams p) {
   __syncthreads();
   const int jl = tid & (TILE - 1), half = tid >> 7;
   const long gj = (long)jt * TILE + jl;
-  const int nl = p.kp.ard ? D : 1;
+  const bool ard = p.kp.ard != 0;
+  const int nl = ard ? D : 1;
   const int nred = nl + 1;
   const int warp = tid >> 5, lane = tid & 31;
   double gvar = 0.0, giso = 0.0;
-  // ARD accumulators live in shared memory per thread column to keep registers bounded: loop q outermost instead
+  double gq[DREG], xj[DREG];
+#pragma unroll
+  for (int q = 0; q < DREG; q++) { gq[q] = 0.0; xj[q] = q < D ? sR[q * TILE + jl] : 0.0; }
+  const double sj = sSr[jl];
   const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
   const long ldd = p.ldd > 0 ? p.ldd : p.M;
-  // pass 1: variance + iso lengthscale, and (ARD) nothing cached: recompute per q (D small) — simple and exact
-  for (int qq = -1; qq < (p.kp.ard ? D : 0); qq++) {
-    double gq = 0.0;
+  const int kind = p.kp.kind;
+  if (gj < p.M) {
     for (int ii = 0; ii < 64; ii++) {
       const int il = half * 64 + ii;
       const long gi = (long)it * TILE + il;
-      if (gi >= p.N || gj >= p.M) continue;
+      if (gi >= p.N) break;
       double dot = 0.0;
-      for (int q = 0; q < D; q++) dot = fma(sR[q * TILE + jl], sC[q * TILE + il], dot);
-      double r2 = sSr[jl] + sSc[il] - 2.0 * dot;
+#pragma unroll
+      for (int q = 0; q < DREG; q++)
+        if (q < D) dot = fma(xj[q], sC[q * TILE + il], dot);
+      double r2 = sj + sSc[il] - 2.0 * dot;
       if (p.same && gi == gj) r2 = 0.0;
       r2 = fmax(r2, 0.0);
       const double rr = sqrt(r2) * inv_ls;
       double k, dk;
-      k_dk_of_r_unit(p.kp.kind, rr, k, dk);
+      k_dk_of_r_unit(kind, rr, k, dk);
       double dl = p.dL_dK[gi * ldd + gj];
       for (int cp = 0; cp < p.cP; cp++) dl = fma(p.ci[(long)cp * p.ldci + gi], p.cj[(long)cp * p.ldcj + gj], dl);
       const double G = variance * dk * dl;
-      if (qq < 0) {
-        gvar = fma(k, dl, gvar);
-        giso = fma(G, rr, giso);
+      gvar = fma(k, dl, gvar);
+      if (ard) {
+        const double tmpv = (rr != 0.0) ? G / rr : 0.0;       // stationary.py:205,225-232: 1/r with 1/0 := 0
+#pragma unroll
+        for (int q = 0; q < DREG; q++)
+          if (q < D) {
+            const double df = xj[q] - sC[q * TILE + il];
+            gq[q] = fma(tmpv, df * df, gq[q]);
+          }
       } else {
-        const double tmpv = (rr != 0.0) ? G / rr : 0.0;
-        const double df = sR[qq * TILE + jl] - sC[qq * TILE + il];
-        gq = fma(tmpv, df * df, gq);
+        giso = fma(G, rr, giso);
       }
-    }
-    if (qq >= 0) {
-      gq = warp_sum(gq);
-      if (lane == 0) sRed[warp * nred + 1 + qq] = gq;
     }
   }
   gvar = warp_sum(gvar);
-  giso = warp_sum(giso);
-  if (lane == 0) {
-    sRed[warp * nred + 0] = gvar;
-    if (!p.kp.ard) sRed[warp * nred + 1] = giso;
+  if (lane == 0) sRed[warp * nred + 0] = gvar;
+  if (ard) {
+#pragma unroll
+    for (int q = 0; q < DREG; q++)
+      if (q < D) {
+        const double sq_ = warp_sum(gq[q]);
+        if (lane == 0) sRed[warp * nred + 1 + q] = sq_;
+      }
+  } else {
+    giso = warp_sum(giso);
+    if (lane == 0) sRed[warp * nred + 1] = giso;
   }
   __syncthreads();
   if (tid < nred) {
@@ -946,19 +961,27 @@ __global__ void __launch_bounds__(256) grad_full_kernel(GradFullParams p) {
   }
 }
 
-int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStream_t st) {
-  const int D = p.kp.D;
-  const size_t smem = (size_t)(2 * D + 2) * TILE * 8 + 8 * (MAX_D + 2) * 8;
+template <int DREG>
+static int launch_grad_full_t(const GradFullParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    GPX_CUDA(cudaFuncSetAttribute(grad_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GPX_CUDA(cudaFuncSetAttribute(grad_full_kernel<DREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((2 * MAX_D + 2) * TILE * 8 + 8 * (MAX_D + 2) * 8)));
     attr_set = true;
   }
-  dim3 grid(tiles_j, tiles_i);
-  grad_full_kernel<<<grid, 256, smem, st>>>(p);
+  grad_full_kernel<DREG><<<grid, 256, smem, st>>>(p);
   GPX_CUDA(cudaGetLastError());
   return 0;
+}
+
+int launch_grad_full(const GradFullParams& p, int tiles_j, int tiles_i, cudaStream_t st) {
+  const int D = p.kp.D;
+  const size_t smem = (size_t)(2 * D + 2) * TILE * 8 + 8 * (MAX_D + 2) * 8;
+  dim3 grid(tiles_j, tiles_i);
+  if (D <= 8) return launch_grad_full_t<8>(p, grid, smem, st);
+  if (D <= 16) return launch_grad_full_t<16>(p, grid, smem, st);
+  if (D <= 32) return launch_grad_full_t<32>(p, grid, smem, st);
+  return launch_grad_full_t<64>(p, grid, smem, st);
 }
 
 
