@@ -68,5 +68,34 @@ def main():
         print("%-28s lml %.10f source %s" % (name, lml, source))
 
 
+HET_CASES = [("het_matern32_ard_n150_d3", "matern32", True, 150, 3, 11), ("het_rbf_iso_n260_d2", "rbf", False, 260, 2, 12)]
+
+
+def main_het():
+    """tests/golden/het/*.npz: one noise variance per data point (GPHeteroscedasticRegression), produced by the
+    reference's own HeteroscedasticGaussian + ExactGaussianInference objects when importable."""
+    GPy = try_reference()
+    os.makedirs(os.path.join(HERE, "het"), exist_ok=True)
+    for name, kind, ARD, N, D, seed in HET_CASES:
+        X, Y = o.synthetic(N, D, seed)
+        rng = np.random.default_rng(100 + seed)
+        var = float(rng.uniform(0.5, 2.0))
+        ls = np.sqrt(D) * rng.uniform(0.6, 1.5, D) if ARD else float(np.sqrt(D) * rng.uniform(0.6, 1.5))
+        nv = rng.uniform(0.005, 0.3, N)
+        lml, grad, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, nv)
+        alpha, source = res["alpha"], "oracle"
+        if GPy is not None:
+            from oracle import ref_gpy
+            r = ref_gpy.evaluate_het(GPy, X, Y, kind, ARD, var, ls, nv)
+            assert abs(r["lml"] - lml) <= 1e-9 * max(1, abs(lml)), (name, r["lml"], lml)
+            np.testing.assert_allclose(r["grad"], grad, rtol=1e-8, atol=1e-10, err_msg=name)
+            lml, grad, alpha = r["lml"], r["grad"], r["alpha"]
+            source = "GPy %s (unmodified /root/reference via oracle/paramz_shim)" % GPy.__version__
+        np.savez_compressed(os.path.join(HERE, "het", name + ".npz"), X=X, Y=Y, kind=kind, ARD=ARD, variance=var,
+                            lengthscale=ls, noise_variances=nv, lml=lml, grad=grad, alpha=alpha, source=source)
+        print("%-28s lml %.10f source %s" % (name, lml, source))
+
+
 if __name__ == "__main__":
     main()
+    main_het()

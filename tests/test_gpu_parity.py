@@ -404,6 +404,23 @@ def test_heteroscedastic_noise(kind, ARD, N, D, P):
     e.close()
 
 
+def test_heteroscedastic_golden_fixtures(eng):
+    """tests/golden/het/*.npz: numbers produced by the reference's own HeteroscedasticGaussian + ExactGaussianInference."""
+    gdir = os.path.join(os.path.dirname(__file__), "golden", "het")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".npz"))
+    assert files
+    for fn in files:
+        z = np.load(os.path.join(gdir, fn))
+        kind, ARD = str(z["kind"]), bool(z["ARD"])
+        ls = z["lengthscale"] if ARD else float(z["lengthscale"])
+        eng.set_data(z["X"], z["Y"])
+        lml, g, dn, _ = eng.exact_eval_het(kind, ARD, float(z["variance"]), ls, z["noise_variances"])
+        nk = z["grad"].size - z["noise_variances"].size
+        assert abs(lml - float(z["lml"])) <= LML_ATOL, fn
+        np.testing.assert_allclose(np.concatenate([g[:nk], dn]), z["grad"], rtol=GRAD_RTOL, atol=1e-9, err_msg=fn)
+        assert rel(eng.get("alpha"), z["alpha"]) < 1e-8, fn
+
+
 def test_heteroscedastic_model():
     """gpy_b200.GPHeteroscedasticRegression (models/gp_heteroscedastic_regression.py:10-37): parameter vector
     [variance, lengthscale, N noise variances], gradient check, prediction with Y_metadata."""

@@ -125,3 +125,27 @@ def test_oracle_heteroscedastic_equals_reference(G, kind, ARD):
         assert abs(r["lml"] - lml) <= 1e-10 * max(1.0, abs(lml))
         np.testing.assert_allclose(g, r["grad"], rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(res["alpha"], r["alpha"], rtol=1e-10, atol=1e-12)
+
+
+def test_mirror_heteroscedastic_likelihood_matches_reference_class(G):
+    """gpy_b200.inference.HeteroscedasticGaussian (host mirror) against the reference class: variance lookup, gradient
+    routing and predictive values for the same Y_metadata (likelihoods/gaussian.py:347-373)."""
+    from gpy_b200.inference import HeteroscedasticGaussian
+    rng = np.random.default_rng(0)
+    N = 17
+    md = {"output_index": np.arange(N)[:, None]}
+    ref = G.HeteroscedasticGaussian(md)
+    mir = HeteroscedasticGaussian(md)
+    nv = rng.uniform(0.1, 1.0, N)
+    ref.variance[:] = nv.reshape(ref.variance.shape)
+    mir.variance.values[...] = nv
+    sub = {"output_index": np.array([3, 0, 11])[:, None]}
+    np.testing.assert_array_equal(np.asarray(ref.gaussian_variance(sub)).reshape(-1), mir.gaussian_variance(sub).reshape(-1))
+    dd = rng.standard_normal(N)
+    np.testing.assert_array_equal(np.asarray(ref.exact_inference_gradients(dd, md)).reshape(-1),
+                                  np.asarray(mir.exact_inference_gradients(dd, md)).reshape(-1))
+    mu, var = rng.standard_normal((3, 1)), rng.uniform(0.1, 1, (3, 1))
+    m0, v0 = ref.predictive_values(mu.copy(), var.copy(), False, sub)
+    m1, v1 = mir.predictive_values(mu.copy(), var.copy(), False, sub)
+    np.testing.assert_allclose(np.asarray(v0).reshape(-1), np.asarray(v1).reshape(-1), rtol=0, atol=0)
+    np.testing.assert_array_equal(m0, m1)
