@@ -96,6 +96,38 @@ def main_het():
         print("%-28s lml %.10f source %s" % (name, lml, source))
 
 
+SPARSE_CASES = [("sparse_rbf_ard_n400_m50_d3", "rbf", True, 400, 50, 3, 21), ("sparse_matern52_iso_n333_m129_d2", "matern52", False, 333, 129, 2, 22)]
+
+
+def main_sparse():
+    """tests/golden/sparse/*.npz: SparseGPRegression (VarDTC) bound, gradients and inducing-input gradients produced by
+    the reference's own VarDTC + kernel + Gaussian objects (gradient wiring of core/sparse_gp.py:108-119)."""
+    GPy = try_reference()
+    os.makedirs(os.path.join(HERE, "sparse"), exist_ok=True)
+    for name, kind, ARD, N, M, D, seed in SPARSE_CASES:
+        rng = np.random.default_rng(100 + seed)
+        X = rng.uniform(-3, 3, (N, D))
+        Y = np.sin(X).sum(1, keepdims=True) / np.sqrt(D) + 0.1 * rng.standard_normal((N, 1))
+        Z = X[rng.permutation(N)[:M]].copy() + 0.01 * rng.standard_normal((M, D))
+        var = float(rng.uniform(0.5, 2.0))
+        ls = np.sqrt(D) * rng.uniform(0.6, 1.5, D) if ARD else float(np.sqrt(D) * rng.uniform(0.6, 1.5))
+        noise = float(rng.uniform(0.01, 0.1))
+        lml, grad, Zg, res = o.sparse_eval(X, Y, Z, kind, ARD, var, ls, noise)
+        wv, source = res["woodbury_vector"], "oracle"
+        if GPy is not None:
+            from oracle import ref_gpy
+            r = ref_gpy.evaluate_sparse(GPy, X, Y, Z, kind, ARD, var, ls, noise)
+            assert abs(r["lml"] - lml) <= 1e-8 * max(1, abs(lml)), (name, r["lml"], lml)
+            np.testing.assert_allclose(r["grad"], grad, rtol=1e-6, atol=1e-8, err_msg=name)
+            np.testing.assert_allclose(r["Zgrad"], Zg, rtol=1e-6, atol=1e-8, err_msg=name)
+            lml, grad, Zg, wv = r["lml"], r["grad"], r["Zgrad"], r["woodbury_vector"]
+            source = "GPy %s (unmodified /root/reference via oracle/paramz_shim)" % GPy.__version__
+        np.savez_compressed(os.path.join(HERE, "sparse", name + ".npz"), X=X, Y=Y, Z=Z, kind=kind, ARD=ARD, variance=var,
+                            lengthscale=ls, noise=noise, lml=lml, grad=grad, Zgrad=Zg, woodbury_vector=wv, source=source)
+        print("%-36s lml %.10f source %s" % (name, lml, source))
+
+
 if __name__ == "__main__":
     main()
     main_het()
+    main_sparse()

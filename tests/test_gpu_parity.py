@@ -404,6 +404,29 @@ def test_heteroscedastic_noise(kind, ARD, N, D, P):
     e.close()
 
 
+def test_sparse_golden_fixtures():
+    """tests/golden/sparse/*.npz: bound, gradients and inducing-input gradients produced by the reference's own VarDTC."""
+    gdir = os.path.join(os.path.dirname(__file__), "golden", "sparse")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".npz"))
+    assert files
+    for fn in files:
+        z = np.load(os.path.join(gdir, fn))
+        kind, ARD, D = str(z["kind"]), bool(z["ARD"]), z["X"].shape[1]
+        ls = z["lengthscale"] if ARD else float(z["lengthscale"])
+        cls = {"rbf": gpy_b200.RBF, "exponential": gpy_b200.Exponential, "matern32": gpy_b200.Matern32,
+               "matern52": gpy_b200.Matern52}[kind]
+        k = cls(D, variance=float(z["variance"]), lengthscale=ls, ARD=ARD)
+        m = gpy_b200.SparseGPRegression(z["X"], z["Y"], kernel=k, Z=z["Z"])
+        m.likelihood.variance.values[...] = float(z["noise"])
+        m.parameters_changed()
+        lml0 = float(z["lml"])
+        assert abs(m.log_likelihood() - lml0) <= 1e-8 * max(1.0, abs(lml0)), fn
+        g = np.concatenate([k.variance.gradient, k.lengthscale.gradient, m.likelihood.variance.gradient])
+        np.testing.assert_allclose(g, z["grad"], rtol=1e-6, atol=1e-8, err_msg=fn)
+        np.testing.assert_allclose(m.Z.gradient, z["Zgrad"], rtol=1e-6, atol=1e-8, err_msg=fn)
+        np.testing.assert_allclose(m.posterior.woodbury_vector, z["woodbury_vector"], rtol=1e-6, atol=1e-7, err_msg=fn)
+
+
 def test_heteroscedastic_golden_fixtures(eng):
     """tests/golden/het/*.npz: numbers produced by the reference's own HeteroscedasticGaussian + ExactGaussianInference."""
     gdir = os.path.join(os.path.dirname(__file__), "golden", "het")
