@@ -47,8 +47,6 @@ EXPORTS = {
     "gpx_kern_grad_X": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64, _dp,
                                        ctypes.c_int64, ctypes.c_int, _dp, _dp]),
     "gpx_sparse_set_data": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, ctypes.c_int]),
-    "gpx_sparse_stats": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64, _dp, _dp]),
-    "gpx_sparse_grads": (ctypes.c_int, [_vp, _dp, _dp, ctypes.c_double, _dp, _dp, _dp]),
     "gpx_sparse_eval": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64,
                                        ctypes.c_double, _dp, _dp, _dp]),
     "gpx_sparse_get": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
@@ -203,29 +201,6 @@ class Engine(object):
         self.sN, self.sD = X.shape
         self.sP = Y.shape[1]
         check(self._L.gpx_sparse_set_data(self._h, _ptr(X), self.sN, self.sD, _ptr(Y), self.sP), "gpx_sparse_set_data")
-
-    def sparse_stats(self, kind, ARD, variance, lengthscale, Z):
-        """-> (G = psi1^T psi1 (M x M), psi1^T Y (M x P))"""
-        Z = _f64(Z)
-        M = Z.shape[0]
-        k, a, ls = _theta(kind, ARD, lengthscale, self.sD)
-        G = np.empty((M, M), order="F")
-        pY = np.empty((M, self.sP))
-        check(self._L.gpx_sparse_stats(self._h, k, a, float(variance), _ptr(ls), _ptr(Z), M, _ptr(G), _ptr(pY)),
-              "gpx_sparse_stats")
-        self.sM, self._snl = M, ls.size
-        return G, pY
-
-    def sparse_grads(self, W2, C, beta):
-        """-> (d variance, d lengthscale, dZ) of the dL_dKnm = (beta Y) C^T + psi1 W2 term"""
-        W2 = np.asfortranarray(_f64(W2))
-        C = _f64(C)
-        dv = ctypes.c_double()
-        dl = np.zeros(self._snl)
-        dZ = np.empty((self.sM, self.sD))
-        check(self._L.gpx_sparse_grads(self._h, _ptr(W2), _ptr(C), float(beta), ctypes.byref(dv), _ptr(dl), _ptr(dZ)),
-              "gpx_sparse_grads")
-        return dv.value, dl, dZ
 
     def sparse_eval(self, kind, ARD, variance, lengthscale, Z, noise_variance):
         """one whole VarDTC evaluation on the device -> (lml, grad [variance, lengthscale.., noise], dZ (M x D))"""

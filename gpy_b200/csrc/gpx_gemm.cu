@@ -122,7 +122,7 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   } else if (MODE == GEMM_LAUUM) {
     nkt = kseq_init(p, r, kq);
   } else {
-    nkt = p.tri ? (c + 1) : p.K / TILE;
+    nkt = p.tri == 1 ? (c + 1) : (p.tri == 2 ? (r + 1) : p.K / TILE);   // tri 1: B lower triangular, 2: A lower triangular
   }
   const double* Aptr = p.A + (p.map_A ? mapped_offset(p, r) : (long)r * TILE);
   const double* Bptr = p.B + (p.map_B ? mapped_offset(p, c) : (long)c * TILE);

@@ -591,6 +591,39 @@ __global__ void uv_reduce_kernel(const double* __restrict__ part, long ld, int P
   out[q * ld + row] = s;
 }
 
+// general tall-skinny product out[q][row] = sum_c A[row + c*lda] * Y[q*ldy + c] (A: rows x ncols column-major, rows a multiple
+// of 128): thread per row (coalesced along rows), the column range split over blockIdx.y, partials reduced in fixed order
+__global__ void __launch_bounds__(TILE) row_dot_partial_kernel(const double* __restrict__ A, long lda, long ncols, int P,
+                                                               const double* __restrict__ Y, long ldy, int nsplit, long ldo,
+                                                               double* __restrict__ part /*[nsplit][P][ldo]*/) {
+  const long row = (long)blockIdx.x * TILE + threadIdx.x;
+  const long chunk = ((ncols + nsplit - 1) / nsplit + 7) / 8 * 8;
+  const long cb = (long)blockIdx.y * chunk;
+  const long ce = cb + chunk < ncols ? cb + chunk : ncols;
+  double acc[MAX_P];
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+#pragma unroll 8
+  for (long c = cb; c < ce; c++) {
+    const double x = A[row + c * lda];
+#pragma unroll
+    for (int q = 0; q < MAX_P; q++)
+      if (q < P) acc[q] = fma(x, Y[(long)q * ldy + c], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++)
+    if (q < P) part[((long)blockIdx.y * P + q) * ldo + row] = acc[q];
+}
+int launch_row_dot(const double* A, long lda, long rows_pad, long ncols, int P, const double* Y, long ldy, int nsplit,
+                   double* part, double* out, cudaStream_t st) {
+  dim3 grid((unsigned)(rows_pad / TILE), nsplit);
+  row_dot_partial_kernel<<<grid, TILE, 0, st>>>(A, lda, ncols, P, Y, ldy, nsplit, rows_pad, part);
+  GPX_CUDA(cudaGetLastError());
+  uv_reduce_kernel<<<(unsigned)((rows_pad * P + 255) / 256), 256, 0, st>>>(part, rows_pad, P, nsplit, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // multi-GPU: a = U t restricted to the column blocks this rank owns; one partial per (row tile, column block)
 __global__ void __launch_bounds__(TILE) uv_partial_blk_kernel(const double* __restrict__ U, long ld, long n, int P,
                                                               const double* __restrict__ T, long blk, int G, int g,

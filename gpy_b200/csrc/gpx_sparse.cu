@@ -1,14 +1,14 @@
-// gpx_sparse.cu — the N-dependent work of sparse GP regression (VarDTC) on the device.
+// gpx_sparse.cu — sparse GP regression (VarDTC) as one device evaluation.
 //
 // Reference: GPy/inference/latent_function_inference/var_dtc.py:66-215 with the gradient wiring of
-// GPy/core/sparse_gp.py:108-119 (Gaussian likelihood, homoscedastic noise, certain inputs). Everything that scales with
-// the number of data points N stays in HBM and never crosses PCIe:
-//   gpx_sparse_stats : psi1 = K(X, Z) in both layouts (8 N M bytes each), G = psi1^T psi1 (M x M, DMMA GEMM with
-//                      k-depth N) and psi1^T Y (M x P)            -> var_dtc.py:126-132,139-141 (A, psi1Vf need only these)
-//   gpx_sparse_grads : dL_dKnm^T = W2 psi1^T + C (beta Y)^T (M x N, never materialised on the host) reduced straight to
-//                      d/d(variance, lengthscale) and dL/dZ       -> var_dtc.py:219-234, sparse_gp.py:112,118
-// The M x M algebra in between (two Choleskys, back-substitutions; var_dtc.py:135-156) is driven from the host mirror
-// (gpy_b200/sparse.py) through gpx_pdinv and small host products: it does not depend on N.
+// GPy/core/sparse_gp.py:108-119 (Gaussian likelihood, homoscedastic noise, certain inputs). Everything stays in HBM:
+//   psi1 = K(X, Z) in both layouts (8 N M bytes each)                                         var_dtc.py:126
+//   Kmm + jitter -> Lm, Lm^-1 (factor-and-invert sweep)                                        :93-95
+//   tmp = Lm^-1 psi1^T (M x N, triangular product), A = beta tmp tmp^T, t = tmp Y              :130-132,139
+//   B = I + A -> LB, LB^-1; v, C, DBi, dL_dKmm, dL_dpsi2 as M x M DMMA GEMMs                   :135-156,217-233
+//   dL_dKnm^T = W2 psi1^T + C (beta Y)^T (M x N, never materialised on the host) reduced straight to
+//   d/d(variance, lengthscale) and dL/dZ                                                       sparse_gp.py:112,118
+// With a communicator the data rows are sharded: A, t and the Knm gradient pieces are all-reduced (var_dtc_parallel.py).
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -44,7 +44,6 @@ struct SparseState {
   double *Gm = nullptr, *W2 = nullptr, *Cm = nullptr;   // Mpad x Mpad, Mpad x Mpad, [P][Mpad]
   double *part = nullptr; size_t part_cap = 0;
   KernParams kp{};
-  bool have_stats = false;
   // full-device evaluation (gpx_sparse_eval)
   gpx_ctx *cK = nullptr, *cB = nullptr;             // child contexts holding the factors of Kmm and of B = I + A
   double *mm[10] = {nullptr};                        // Mpad x Mpad work matrices
@@ -63,7 +62,6 @@ void free_m(SparseState* s) {
   for (auto& p : s->mm) { if (p) cudaFree(p); p = nullptr; }
   s->have_eval = false;
   s->M = s->Mpad = 0;
-  s->have_stats = false;
 }
 void free_all(SparseState* s) {
   free_m(s);
@@ -106,13 +104,6 @@ __global__ void mirror_tiles_kernel(double* __restrict__ A, long ld, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= n || i / TILE >= j / TILE) return;
   A[i + j * ld] = A[j + i * ld];
-}
-__global__ void transpose_kernel(const double* __restrict__ in, long ld, long n, double* __restrict__ out) {
-  __shared__ double t[32][33];
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
-  for (int k = ty; k < 32; k += 8) t[k][tx] = in[(by + tx) + (long)(bx + k) * ld];      // t[col][row]
-  __syncthreads();
-  for (int k = ty; k < 32; k += 8) out[(bx + tx) + (long)(by + k) * ld] = t[tx][k];     // out(col, row)
 }
 // r[0] = trace(A), r[1] = sum(A .* B) over n x n; single CTA partial sums reduced in fixed order
 __global__ void __launch_bounds__(256) trace_dot_kernel(const double* __restrict__ A, const double* __restrict__ B, long ld,
@@ -164,7 +155,6 @@ int gpx_sparse_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const dou
     GPX_CUDA(cudaMalloc(&s->Yb, (size_t)Npad * P * 8));
   }
   s->N = N;
-  s->have_stats = false;
   s->have_eval = false;
   {   // trYYT = sum(Y .* Y) (var_dtc.py:37,90); with row shards: summed over the ranks, like num_data
     double t = 0.0;
@@ -197,9 +187,9 @@ int gpx_sparse_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const dou
 
 }  // extern "C"
 
-// psi1 in both layouts, G = psi1^T psi1 (lower tiles of Gm) and psi1^T Y (Cm), all left on the device
-static int stats_device(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
-                        int64_t M) {
+// psi1 = K(X, Z) in both layouts (Kuf: M x N, Kfu: N x M), left on the device
+static int psi_device(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                      int64_t M) {
   SparseState* s = c->sparse;
   cudaStream_t st = c->st;
   GPX_CHECK(fill_kp(s->kp, kind, ard, s->D, variance, lengthscale));
@@ -238,80 +228,9 @@ static int stats_device(gpx_ctx* c, int kind, int ard, double variance, const do
   kb.rowsT = s->XsT; kb.ld_rows = Npad; kb.sq_rows = s->sqX; kb.colsT = s->ZsT; kb.ld_cols = Mpad; kb.sq_cols = s->sqZ;
   kb.out = s->Kfu; kb.ld = Npad; kb.nrows = N; kb.ncols = M;
   GPX_CHECK(launch_kbuild(kb, ntl, mt, st));
-  // G = psi1^T psi1 (lower tiles), k-depth = Npad
-  {
-    GemmParams pg = gemm_defaults();
-    pg.mode = GEMM_PANEL; pg.plain = 2;
-    pg.A = s->Kuf; pg.lda = Mpad; pg.B = s->Kuf; pg.ldb = Mpad; pg.C = s->Gm; pg.ldc = Mpad;
-    pg.K = (int)Npad; pg.nt = mt; pg.ncols = mt;
-    GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
-  }
-  GPX_CUDA(cudaMemsetAsync(s->Cm, 0, (size_t)Mpad * s->P * 8, st));
-  GPX_CHECK(launch_col_dot(s->Kfu, Npad, N, M, s->P, s->Y, Npad, s->Cm, Mpad, st));
-  // row shards: the psi statistics are sums over data points -> one M x M and one M x P all-reduce
-  // (the pattern of var_dtc_parallel.py:113-131 with NCCL instead of mpi4py)
-  GPX_CHECK(dist_allreduce_sum(c, s->Gm, (size_t)Mpad * Mpad, st));
-  GPX_CHECK(dist_allreduce_sum(c, s->Cm, (size_t)Mpad * s->P, st));
-  c->total_launches += 6;
-  s->have_stats = true;
+  c->total_launches += 4;
   return 0;
 }
-
-extern "C" {
-
-int gpx_sparse_stats(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
-                     int64_t M, double* G, double* psi1tY) {
-  if (!c || !c->sparse || !c->sparse->X) GPX_FAIL("gpx_sparse_set_data has not been called");
-  if (!Z || !G || !psi1tY || !lengthscale) GPX_FAIL("null argument");
-  if (M < 1) GPX_FAIL("M must be positive");
-  {
-    int rank = 0, G_ = 1;
-    dist_world(c, &rank, &G_);
-    if (G_ > 1) GPX_FAIL("the split sparse calls are single-GPU; use gpx_sparse_eval with row shards");
-  }
-  GPX_CUDA(cudaSetDevice(c->device));
-  GPX_CHECK(stats_device(c, kind, ard, variance, lengthscale, Z, M));
-  SparseState* s = c->sparse;
-  cudaStream_t st = c->st;
-  const long Mpad = s->Mpad;
-  std::vector<double> hG((size_t)Mpad * Mpad), hC((size_t)Mpad * s->P);
-  GPX_CUDA(cudaMemcpyAsync(hG.data(), s->Gm, hG.size() * 8, cudaMemcpyDeviceToHost, st));
-  GPX_CUDA(cudaMemcpyAsync(hC.data(), s->Cm, hC.size() * 8, cudaMemcpyDeviceToHost, st));
-  GPX_CUDA(cudaStreamSynchronize(st));
-  for (long j = 0; j < M; j++)
-    for (long i = 0; i < M; i++) {
-      const long ti = i / TILE, tj = j / TILE;
-      G[i + j * M] = (ti >= tj) ? hG[i + j * Mpad] : hG[j + i * Mpad];   // lower tiles were computed: mirror
-    }
-  for (long i = 0; i < M; i++)
-    for (int q = 0; q < s->P; q++) psi1tY[i * s->P + q] = hC[(size_t)q * Mpad + i];
-  return 0;
-}
-
-int gpx_sparse_grads(gpx_ctx* c, const double* W2, const double* Cmat, double beta, double* dvariance,
-                     double* dlengthscale, double* dZ) {
-  if (!c || !c->sparse || !c->sparse->have_stats) GPX_FAIL("gpx_sparse_stats has not been called");
-  if (!W2 || !Cmat || !dvariance || !dlengthscale || !dZ) GPX_FAIL("null argument");
-  GPX_CUDA(cudaSetDevice(c->device));
-  SparseState* s = c->sparse;
-  cudaStream_t st = c->st;
-  const long M = s->M, Mpad = s->Mpad;
-  const int P = s->P;
-  GPX_CUDA(cudaMemsetAsync(s->W2, 0, (size_t)Mpad * Mpad * 8, st));
-  GPX_CUDA(cudaMemcpy2DAsync(s->W2, Mpad * 8, W2, M * 8, (size_t)M * 8, M, cudaMemcpyHostToDevice, st));
-  std::vector<double> hC((size_t)Mpad * P, 0.0);
-  for (long i = 0; i < M; i++)
-    for (int q = 0; q < P; q++) hC[(size_t)q * Mpad + i] = Cmat[i * P + q];
-  GPX_CUDA(cudaMemcpyAsync(s->Cm, hC.data(), hC.size() * 8, cudaMemcpyHostToDevice, st));
-  GPX_CUDA(cudaStreamSynchronize(st));   // hC is a local
-  {
-    const int rc = knm_grads_device(c, beta, dvariance, dlengthscale, dZ);
-    if (rc) return rc;
-  }
-  return 0;
-}
-
-}  // extern "C"
 
 // dL_dKnm^T = W2 psi1^T (+ rank-P term on the fly) reduced to kernel-parameter gradients and dL/dZ; W2 (device, s->W2)
 // and C (device, s->Cm as [P][Mpad]) must be in place. Results on the host.
@@ -405,13 +324,14 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   SparseState* s = c->sparse;
   cudaStream_t st = c->st;
   s->have_eval = false;
-  GPX_CHECK(stats_device(c, kind, ard, variance, lengthscale, Z, M));
-  const long Mpad = s->Mpad, N = s->Ntot;
-  const int D = s->D, P = s->P, mt = (int)(Mpad / TILE);
+  GPX_CHECK(psi_device(c, kind, ard, variance, lengthscale, Z, M));
+  const long Mpad = s->Mpad, N = s->Ntot, Npad = s->Npad;
+  const int D = s->D, P = s->P, mt = (int)(Mpad / TILE), ntl = (int)(Npad / TILE);
   const int nl = s->kp.ard ? D : 1;
+  constexpr int RSPLIT = 64;
   if (!s->mm[0]) {
     for (auto& p : s->mm) GPX_CUDA(cudaMalloc(&p, (size_t)Mpad * Mpad * 8));
-    GPX_CUDA(cudaMalloc(&s->vec, (size_t)8 * P * Mpad * 8));
+    GPX_CUDA(cudaMalloc(&s->vec, (size_t)(8 + RSPLIT) * P * Mpad * 8));
   }
   if (!s->red) {
     GPX_CUDA(cudaMalloc(&s->red, 4096 * 8));
@@ -420,15 +340,10 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   if (!s->cK) { GPX_CHECK(gpx_create(c->device, &s->cK)); GPX_CHECK(gpx_create(c->device, &s->cB)); }
   double *Kd = s->mm[0], *Um = s->mm[1], *Lmi = s->mm[2], *T = s->mm[3], *Ar = s->mm[4], *Bd = s->mm[5], *UB = s->mm[6],
          *LBi = s->mm[7], *DB = s->mm[8], *E = s->mm[9];
-  double *xv = s->vec, *vv = xv + (size_t)P * Mpad, *Cv = vv + (size_t)P * Mpad, *wv = Cv + (size_t)P * Mpad;
+  double *tv = s->vec, *vv = tv + (size_t)P * Mpad, *Cv = vv + (size_t)P * Mpad, *wv = Cv + (size_t)P * Mpad,
+         *xv = wv + (size_t)P * Mpad, *rpart = s->vec + (size_t)8 * P * Mpad;
   const double beta = 1.0 / std::max(noise, 1e-8);                                       // var_dtc.py:79-80
   s->noise = noise;
-  // G: mirror the computed lower tiles
-  {
-    dim3 grid((unsigned)((Mpad + 255) / 256), (unsigned)Mpad);
-    mirror_tiles_kernel<<<grid, 256, 0, st>>>(s->Gm, Mpad, Mpad);
-    GPX_CUDA(cudaGetLastError());
-  }
   // Kmm (dense, zero padded), factor-and-invert with const_jitter (var_dtc.py:93-95)
   GPX_CUDA(cudaMemsetAsync(Kd, 0, (size_t)Mpad * Mpad * 8, st));
   {
@@ -447,9 +362,36 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   if (s->cK->Npad != Mpad) GPX_FAIL("internal: child workspace size");
   GPX_CHECK(launch_assemble(s->cK->S, Mpad, (int)Mpad, Um, Mpad, Lmi, s->cK->st));      // Um (clean upper), Lmi = Um^T
   GPX_CUDA(cudaStreamSynchronize(s->cK->st));
-  // A_raw = (Lmi G) Lmi^T ;  B = I + beta A_raw
-  GPX_CHECK(mm_nt(c, Lmi, s->Gm, T, Mpad));
-  GPX_CHECK(mm_nt(c, T, Lmi, Ar, Mpad));
+  // tmp = Lm^-1 psi1^T (M x N; var_dtc.py:131,139 dtrtrs) as a product with the triangular inverse, k-range <= row tile.
+  // A = tmp tmp^T is then formed from O(1) entries. (Forming G = psi1^T psi1 first and sandwiching it, Lm^-1 G Lm^-T,
+  // saves 2 M^2 N flops but cancels ~cond(Kmm) digits: measured 1e-4 instead of 1e-8 on dL/dZ at cond(Kmm) = 2e8.)
+  double* Tuf = s->dLt;   // the dL_dKnm^T buffer is free until knm_grads_device
+  {
+    GemmParams pg = gemm_defaults();
+    pg.mode = GEMM_PANEL; pg.plain = 1; pg.tri = 2;
+    pg.A = Lmi; pg.lda = Mpad; pg.B = s->Kfu; pg.ldb = Npad; pg.C = Tuf; pg.ldc = Mpad;
+    pg.K = (int)Mpad; pg.nt = mt; pg.ncols = ntl;
+    GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
+  }
+  {
+    GemmParams pg = gemm_defaults();   // A_raw = tmp tmp^T (lower tiles), k-depth = Npad
+    pg.mode = GEMM_PANEL; pg.plain = 2;
+    pg.A = Tuf; pg.lda = Mpad; pg.B = Tuf; pg.ldb = Mpad; pg.C = Ar; pg.ldc = Mpad;
+    pg.K = (int)Npad; pg.nt = mt; pg.ncols = mt;
+    GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
+  }
+  GPX_CHECK(launch_row_dot(Tuf, Mpad, Mpad, s->N, P, s->Y, Npad, RSPLIT, rpart, tv, st));   // t = tmp Y  ([P][Mpad])
+  // row shards: A_raw and t are sums over data points -> one M x M and one M x P all-reduce
+  // (the pattern of var_dtc_parallel.py:113-131 with NCCL instead of mpi4py)
+  GPX_CHECK(dist_allreduce_sum(c, Ar, (size_t)Mpad * Mpad, st));
+  GPX_CHECK(dist_allreduce_sum(c, tv, (size_t)Mpad * P, st));
+  {
+    dim3 grid((unsigned)((Mpad + 255) / 256), (unsigned)Mpad);
+    mirror_tiles_kernel<<<grid, 256, 0, st>>>(Ar, Mpad, Mpad);
+    GPX_CUDA(cudaGetLastError());
+  }
+  c->total_launches += 6;
+  // B = I + beta A_raw  (var_dtc.py:135-136)
   GPX_CHECK(combine(c, Bd, Mpad, Mpad, beta, Ar, 0.0, nullptr, 1.0));
   GPX_CUDA(cudaStreamSynchronize(st));
   double logdetB = 0.0;
@@ -459,19 +401,12 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   }
   GPX_CHECK(launch_assemble(s->cB->S, Mpad, (int)Mpad, UB, Mpad, LBi, s->cB->st));
   GPX_CUDA(cudaStreamSynchronize(s->cB->st));
-  // Q = LBi Lmi = LBi Um^T  (into T), Qt = Q^T (into E)
-  GPX_CHECK(mm_nt(c, LBi, Um, T, Mpad));
-  {
-    dim3 grid((unsigned)(Mpad / 32), (unsigned)(Mpad / 32)), block(32, 8);
-    transpose_kernel<<<grid, block, 0, st>>>(T, Mpad, Mpad, E);
-    GPX_CUDA(cudaGetLastError());
-  }
-  // x = beta psi1^T Y ; v = Q x ; C = Q^T v ; w = UB v = LBi^T v
-  scale_kernel<<<(unsigned)((Mpad * P + 255) / 256), 256, 0, st>>>(s->Cm, beta, Mpad * P, xv);
+  // v = LB^-1 (beta t) (:139-141) ; w = LB^-T v ; C = Lm^-T w (:142-143)   [col_dot(A, y) = A^T y]
+  scale_kernel<<<(unsigned)((Mpad * P + 255) / 256), 256, 0, st>>>(tv, beta, Mpad * P, xv);
   GPX_CUDA(cudaGetLastError());
-  GPX_CHECK(launch_col_dot(E, Mpad, Mpad, Mpad, P, xv, Mpad, vv, Mpad, st));            // v = (Qt)^T x = Q x
-  GPX_CHECK(launch_col_dot(T, Mpad, Mpad, Mpad, P, vv, Mpad, Cv, Mpad, st));            // C = Q^T v
+  GPX_CHECK(launch_col_dot(UB, Mpad, Mpad, Mpad, P, xv, Mpad, vv, Mpad, st));           // v = UB^T x = LBi x
   GPX_CHECK(launch_col_dot(LBi, Mpad, Mpad, Mpad, P, vv, Mpad, wv, Mpad, st));          // w = LBi^T v
+  GPX_CHECK(launch_col_dot(Lmi, Mpad, Mpad, Mpad, P, wv, Mpad, Cv, Mpad, st));          // C = Lmi^T w
   // Binv = UB UB^T (lower tiles, mirrored) ; DBi = P Binv + w w^T
   GPX_CHECK(mm_nt(c, UB, UB, DB, Mpad, 2));
   {

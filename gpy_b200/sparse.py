@@ -6,13 +6,11 @@ Mirrors:
     GPy.models.SparseGPRegression                              GPy/models/sparse_gp_regression.py:33-59
 (Gaussian likelihood, homoscedastic noise, certain inputs, no mean function — BASELINE.json configs[4].)
 
-Default (`VarDTC(device_algebra=True)`): ONE call, gpx_sparse_eval, does the whole evaluation on the device — psi1 =
-K(X, Z), G = psi1^T psi1, psi1^T Y, the two M x M factor-and-invert sweeps (Kmm, B = I + A), every M x M product, dL_dKnm
-= (beta Y) C^T + 2 psi1 dL_dpsi2 and all reductions to kernel / inducing-point / noise gradients. Only X, Y (once), Z and
-theta go in; the bound, 2 + nl gradient entries and dZ (M x D) come back; the posterior is fetched lazily.
-
-`device_algebra=False` keeps the split formulation (gpx_sparse_stats / gpx_pdinv / gpx_sparse_grads with the M x M
-products in NumPy between them): same numbers, used by the tests to cross-check the fused path step by step.
+ONE call, gpx_sparse_eval, does the whole evaluation on the device — psi1 = K(X, Z), tmp = Lm^-1 psi1^T, A = beta tmp
+tmp^T, the two M x M factor-and-invert sweeps (Kmm, B = I + A), every M x M product, dL_dKnm = (beta Y) C^T + 2 psi1
+dL_dpsi2 and all reductions to kernel / inducing-point / noise gradients. Only X, Y (once), Z and theta go in; the
+bound, 2 + nl gradient entries and dZ (M x D) come back; the posterior is fetched lazily (gpx_sparse_get). With an engine
+attached to a NCCL communicator, X and Y are this rank's rows (gpy_b200.dist.shard_rows).
 """
 import numpy as np
 
@@ -72,9 +70,8 @@ class VarDTC(object):
 
     const_jitter = CONST_JITTER
 
-    def __init__(self, device=0, engine=None, limit=1, device_algebra=True):
+    def __init__(self, device=0, engine=None, limit=1):
         self.device, self._engine, self._data_key = device, engine, None
-        self.device_algebra = device_algebra
 
     @property
     def engine(self):
@@ -113,62 +110,17 @@ class VarDTC(object):
             precision = 1.0 / np.fmax(float(np.squeeze(np.asarray(likelihood.gaussian_variance(Y_metadata)))),
                                       self.const_jitter)                                   # var_dtc.py:79-80
         beta = float(precision)
-        if self.device_algebra:
-            lml, grad, dZ = eng.sparse_eval(kind, ard, var, ls, Zs, noise_var if noise_var is not None else 1.0 / beta)
-            post = LazySparsePosterior(eng)
-            return post, float(lml), {"dvariance": grad[0], "dlengthscale": grad[1:-1], "dZ": dZ,
-                                      "dL_dthetaL": float(grad[-1]), "num_data": num_data}
-        trYYT = float(np.einsum("ij,ij->", Y, Y))                                           # :37,90
-        # ---- device: psi1 statistics ---------------------------------------------------------------------------
-        G, psi1tY = eng.sparse_stats(kind, ard, var, ls, Zs)                                # psi1^T psi1, psi1^T Y
-        psi0_sum = var * num_data                                                           # sum(Kdiag(X)), :124
-        # ---- M x M: Kmm, Lm, Lm^-1 (device) ------------------------------------------------------------------------
-        Kmm = kern.K(Z)
-        Kmm = Kmm + np.eye(num_inducing) * self.const_jitter                                # :93-94
-        _, Lm, Lmi, _, _ = _ffi.pdinv(Kmm, maxtries=5, want=("L", "Li"))                    # :95 jitchol (+ inverse)
-        A = beta * Lmi.dot(G).dot(Lmi.T)                                                    # :130-132
-        B = np.eye(num_inducing) + A                                                        # :135
-        _, LB, LBi, _, _ = _ffi.pdinv(B, maxtries=5, want=("L", "Li"))                      # :136
-        psi1Vf = beta * psi1tY                                                              # psi1^T VVT_factor
-        LBi_Lmi = LBi.dot(Lmi)
-        _LBi_Lmi_psi1Vf = LBi_Lmi.dot(psi1Vf)                                               # :139-141
-        Cpsi1Vf = LBi_Lmi.T.dot(_LBi_Lmi_psi1Vf)                                            # :142-143
-        delit = _LBi_Lmi_psi1Vf.dot(_LBi_Lmi_psi1Vf.T)                                      # :148
-        data_fit = np.trace(delit)                                                          # :149
-        DBi_plus_BiPBi = LBi.T.dot(output_dim * np.eye(num_inducing) + delit).dot(LBi)      # :150 backsub_both_sides
-        delit = -0.5 * DBi_plus_BiPBi - 0.5 * B * output_dim + output_dim * np.eye(num_inducing)   # :152-154
-        dL_dKmm = Lmi.T.dot(delit).dot(Lmi)                                                 # :156
-        dL_dpsi2 = beta * 0.5 * Lmi.T.dot(output_dim * np.eye(num_inducing) - DBi_plus_BiPBi).dot(Lmi)   # :221,231
-        # ---- device: dL_dKnm = VVT C^T + 2 psi1 dL_dpsi2 reduced to parameter / inducing-point gradients -----------
-        W2 = 2.0 * dL_dpsi2
-        W2 = 0.5 * (W2 + W2.T)
-        knm_dvar, knm_dls, knm_dZ = eng.sparse_grads(W2, Cpsi1Vf, beta)
-        # ---- bound and noise gradient (:237-276, homoscedastic) ------------------------------------------------------
-        trA = np.trace(A)
-        lik_1 = -0.5 * num_data * output_dim * (np.log(2.0 * np.pi) - np.log(beta)) - 0.5 * beta * trYYT
-        lik_2 = -0.5 * output_dim * (beta * psi0_sum - trA)
-        lik_3 = -output_dim * np.sum(np.log(np.diag(LB)))
-        lik_4 = 0.5 * data_fit
-        log_marginal = float(lik_1 + lik_2 + lik_3 + lik_4)
-        dL_dR = -0.5 * num_data * output_dim * beta + 0.5 * trYYT * beta ** 2
-        dL_dR += 0.5 * output_dim * (psi0_sum * beta ** 2 - trA * beta)
-        dL_dR += beta * (0.5 * np.sum(A * DBi_plus_BiPBi) - data_fit)
-        # ---- posterior (:201-214) --------------------------------------------------------------------------------
-        Bi = np.eye(num_inducing) - LBi.T.dot(LBi)                                          # -dpotri(LB) + I
-        woodbury_inv = Lmi.T.dot(Bi).dot(Lmi)
-        post = SparsePosterior(woodbury_inv, Cpsi1Vf, Kmm, Lm)
-        grad_dict = {"dL_dKmm": dL_dKmm, "dL_dKdiag_value": -0.5 * output_dim * beta, "num_data": num_data,
-                     "Knm_dvariance": knm_dvar, "Knm_dlengthscale": knm_dls, "Knm_dZ": knm_dZ,
-                     "dL_dthetaL": float(dL_dR)}
-        return post, log_marginal, grad_dict
+        lml, grad, dZ = eng.sparse_eval(kind, ard, var, ls, Zs, noise_var if noise_var is not None else 1.0 / beta)
+        post = LazySparsePosterior(eng)
+        return post, float(lml), {"dvariance": grad[0], "dlengthscale": grad[1:-1], "dZ": dZ,
+                                  "dL_dthetaL": float(grad[-1]), "num_data": num_data}
 
 
 class SparseGPRegression(Parameterized):
     """GPy.models.SparseGPRegression (sparse_gp_regression.py:33-59) / GPy.core.SparseGP (sparse_gp.py:38-119).
     Parameter (and gradient) order as in the reference: [inducing inputs, kern.variance, kern.lengthscale, noise]."""
 
-    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, device=0, engine=None, name="sparse_gp",
-                 device_algebra=True):
+    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, device=0, engine=None, name="sparse_gp"):
         super(SparseGPRegression, self).__init__(name)
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
@@ -187,7 +139,7 @@ class SparseGPRegression(Parameterized):
         self.Z.values = np.array(Z, dtype=np.float64)                          # keep the M x D shape
         self.Z.gradient = np.zeros_like(self.Z.values)
         self.num_inducing = self.Z.values.shape[0]
-        self.inference_method = VarDTC(device=device, engine=engine, device_algebra=device_algebra)
+        self.inference_method = VarDTC(device=device, engine=engine)
         self.link_parameter(self.Z)                                            # sparse_gp.py:61 (index 0)
         self.link_parameter(self.kern)
         self.link_parameter(self.likelihood)
@@ -200,20 +152,9 @@ class SparseGPRegression(Parameterized):
             self.kern, self.X, Z, self.likelihood, self.Y)
         self.grad_dict = gd
         self.likelihood.update_gradients(gd["dL_dthetaL"])                                     # :84
-        if "dZ" in gd:                                      # fused device evaluation: gradients already reduced
-            self.kern.variance.gradient = np.atleast_1d(gd["dvariance"])
-            self.kern.lengthscale.gradient = np.atleast_1d(gd["dlengthscale"])
-            self.Z.gradient = gd["dZ"]
-            return
-        # kern.update_gradients_diag(dL_dKdiag, X) (:110): variance.gradient = sum(dL_dKdiag), lengthscale 0
-        kv = gd["dL_dKdiag_value"] * gd["num_data"]
-        kl = np.zeros(self.kern.lengthscale.size)
-        kv += gd["Knm_dvariance"]                                                                # :112 (device-reduced)
-        kl = kl + gd["Knm_dlengthscale"]
-        self.kern.update_gradients_full(gd["dL_dKmm"], Z, None)                                  # :114
-        self.kern.variance.gradient = np.atleast_1d(self.kern.variance.gradient + kv)
-        self.kern.lengthscale.gradient = np.atleast_1d(self.kern.lengthscale.gradient) + kl
-        self.Z.gradient = self.kern.gradients_X(gd["dL_dKmm"], Z) + gd["Knm_dZ"]                # :117-118
+        self.kern.variance.gradient = np.atleast_1d(gd["dvariance"])          # :110-114 summed on the device
+        self.kern.lengthscale.gradient = np.atleast_1d(gd["dlengthscale"])
+        self.Z.gradient = gd["dZ"]                                             # :117-118
 
     def log_likelihood(self):
         return self._log_marginal_likelihood

@@ -111,23 +111,16 @@ int gpx_pdinv(gpx_ctx* ctx, const double* A, int64_t N, int max_tries, double* A
  * the gradient wiring GPy/core/sparse_gp.py:108-119 (Gaussian likelihood, homoscedastic, certain inputs). psi1 = K(X, Z)
  * (8 N M bytes) is built and kept in HBM; only M x M / M x P / M x D results cross PCIe.
  *   gpx_sparse_set_data : X (N x D row-major), Y (N x P row-major) -> HBM (no N x N workspace is allocated).
- *   gpx_sparse_stats    : G = psi1^T psi1 (M x M, symmetric, fully populated) and psi1^T Y (M x P row-major); with
- *                         Lm = chol(Kmm): A = beta Lm^-1 G Lm^-T (var_dtc.py:130-132), psi1Vf = beta psi1^T Y (:141).
- *   gpx_sparse_grads    : dL_dKnm = (beta Y) C^T + psi1 W2 (var_dtc.py:219-234 with C = Cpsi1Vf, W2 = 2 dL_dpsi2,
- *                         symmetric) is formed on the device and reduced to the kernel-parameter gradients of
- *                         kern.update_gradients_full(dL_dKnm, X, Z) (sparse_gp.py:112) and to
- *                         kern.gradients_X(dL_dKnm^T, Z, X) (sparse_gp.py:118; dZ is M x D row-major). */
+ */
 int gpx_sparse_set_data(gpx_ctx* ctx, const double* X, int64_t N, int D, const double* Y, int P);
-int gpx_sparse_stats(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* Z,
-                     int64_t M, double* G, double* psi1tY);
-int gpx_sparse_grads(gpx_ctx* ctx, const double* W2, const double* C, double beta, double* dvariance,
-                     double* dlengthscale, double* dZ);
-
 /* One whole VarDTC evaluation on the device: VarDTC.inference (var_dtc.py:66-215, Gaussian homoscedastic noise, certain
  * inputs, no mean function) + SparseGP._update_gradients (core/sparse_gp.py:108-119) + Gaussian.update_gradients
  * (likelihoods/gaussian.py:78-79). Kmm + 1e-8 I and B = I + A are factored-and-inverted by the same sweep as the exact
  * path (jitchol ladder, util/linalg.py:56-75); every M x M product of :130-156,:201-233 is a DMMA GEMM; only the
  * scalars, dZ (M x D row-major) and the (1 + nl + 1) gradient entries [variance, lengthscale.., noise variance] return.
+ * A = beta (Lm^-1 psi1^T)(Lm^-1 psi1^T)^T is formed from tmp = Lm^-1 psi1^T like the reference does (:130-132), not by
+ * sandwiching psi1^T psi1, which loses ~cond(Kmm) digits. With a communicator attached (gpx_comm_init) X, Y are THIS
+ * rank's rows and A, tmp Y and the Knm gradient pieces are all-reduced (var_dtc_parallel.py:113-131).
  *   gpx_sparse_get: posterior pieces of the last evaluation (var_dtc.py:201-214): 0 woodbury_vector (M x P row-major),
  *                   1 woodbury_inv (M x M), 2 Kmm (+ const_jitter on the diagonal), 3 Lm (lower, column-major). */
 int gpx_sparse_eval(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* Z,

@@ -129,9 +129,9 @@ def test_two_rank_gloo_sweep():
 
 
 def _sparse_worker(rank, world, port, q):
-    """Row-sharded VarDTC as gpx_sparse_eval runs it with a communicator: each rank holds N/world data rows, the psi
-    statistics (psi1^T psi1, psi1^T Y, num_data, trYYT) are all-reduced, every rank repeats the M x M algebra, the
-    Knm gradient pieces are all-reduced. Checked against the oracle on the whole data set."""
+    """Row-sharded VarDTC as gpx_sparse_eval runs it with a communicator: each rank holds N/world data rows; num_data,
+    trYYT, A = tmp tmp^T and tmp Y (tmp = Lm^-1 psi1^T of the local rows) are all-reduced, every rank repeats the M x M
+    algebra, the Knm gradient pieces are all-reduced. Checked against the oracle on the whole data set."""
     import torch
     import torch.distributed as dist
     from oracle import gpy_oracle as o
@@ -156,18 +156,18 @@ def _sparse_worker(rank, world, port, q):
             return t.numpy()
 
         psi1 = kern.K(Xl, Z)
-        G = allsum(psi1.T @ psi1)
-        pY = allsum(psi1.T @ Yl)
         ntot, trYYT = allsum(np.array([float(Xl.shape[0]), float((Yl * Yl).sum())]))
         assert int(round(ntot)) == N
-        # replicated M x M algebra, in the product form of gpx_sparse.cu
+        # replicated M x M algebra, in the product form of gpx_sparse.cu; the N-dependent pieces are formed from
+        # tmp = Lm^-1 psi1^T of this rank's rows and all-reduced
         Kmm = kern.K(Z) + 1e-8 * np.eye(M)
         Lm = np.linalg.cholesky(Kmm); Lmi = np.linalg.inv(Lm); Um = Lmi.T
-        Ar = Lmi @ G @ Lmi.T
+        tmp = Lmi @ psi1.T
+        Ar = allsum(tmp @ tmp.T)
+        t = allsum(tmp @ Yl)
         B = np.eye(M) + beta * Ar
         LB = np.linalg.cholesky(B); LBi = np.linalg.inv(LB); UB = LBi.T
-        Q = LBi @ Lmi
-        v = Q @ (beta * pY); C = Q.T @ v; w = UB @ v
+        v = LBi @ (beta * t); w = UB @ v; C = Um @ w
         DBi = P * (UB @ UB.T) + w @ w.T
         dKmm = Um @ (-0.5 * DBi - 0.5 * P * B + P * np.eye(M)) @ Um.T
         W2 = beta * Um @ (P * np.eye(M) - DBi) @ Um.T

@@ -337,8 +337,7 @@ def test_combination_and_static_kernels():
 
 @pytest.mark.parametrize("kind,ARD,N,M,D,P", [("rbf", True, 700, 40, 3, 1), ("matern52", False, 1500, 300, 4, 2),
                                                ("exponential", True, 2100, 129, 2, 1), ("matern32", True, 600, 600, 5, 1)])
-@pytest.mark.parametrize("device_algebra", [True, False])
-def test_sparse_gp_vardtc(kind, ARD, N, M, D, P, device_algebra):
+def test_sparse_gp_vardtc(kind, ARD, N, M, D, P):
     """Sparse GP regression (VarDTC, GPy/inference/latent_function_inference/var_dtc.py:66-215 + core/sparse_gp.py:108-119)
     through the mirror: bound, kernel / noise gradients, inducing-point gradients and predictions against the oracle
     (which is pinned to the unmodified reference VarDTC, tests/test_reference_crosscheck.py)."""
@@ -350,18 +349,17 @@ def test_sparse_gp_vardtc(kind, ARD, N, M, D, P, device_algebra):
     cls = {"rbf": gpy_b200.RBF, "exponential": gpy_b200.Exponential, "matern32": gpy_b200.Matern32,
            "matern52": gpy_b200.Matern52}[kind]
     k = cls(D, variance=1.3, lengthscale=ls, ARD=ARD)
-    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z, device_algebra=device_algebra)
+    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z)
     m.likelihood.variance.values[...] = 0.05
     m.parameters_changed()
     lml0, g0, Zg0, res = o.sparse_eval(X, Y, Z, kind, ARD, 1.3, ls, 0.05)
     np.testing.assert_allclose(m.posterior.woodbury_vector, res["woodbury_vector"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(m.posterior.woodbury_inv, res["woodbury_inv"], rtol=1e-4,
                                atol=1e-6 * np.abs(res["woodbury_inv"]).max())
-    if device_algebra:
-        Kmm0 = o.StationaryOracle(kind, D, 1.3, ls, ARD).K(Z) + 1e-8 * np.eye(M)
-        np.testing.assert_allclose(m.posterior.K, Kmm0, rtol=1e-12, atol=1e-12)
-        Lm = np.tril(m.posterior.K_chol)
-        np.testing.assert_allclose(Lm.dot(Lm.T), Kmm0, rtol=1e-9, atol=1e-10)
+    Kmm0 = o.StationaryOracle(kind, D, 1.3, ls, ARD).K(Z) + 1e-8 * np.eye(M)
+    np.testing.assert_allclose(m.posterior.K, Kmm0, rtol=1e-12, atol=1e-12)
+    Lm = np.tril(m.posterior.K_chol)
+    np.testing.assert_allclose(Lm.dot(Lm.T), Kmm0, rtol=1e-9, atol=1e-10)
     assert abs(m.log_likelihood() - lml0) <= 1e-8 * max(1.0, abs(lml0))
     g = np.concatenate([k.variance.gradient, k.lengthscale.gradient, m.likelihood.variance.gradient])
     np.testing.assert_allclose(g, g0, rtol=1e-6, atol=1e-8)

@@ -18,25 +18,18 @@ def main():
     Z = X[rng.permutation(N)[:M]].copy()
     k = gpy_b200.RBF(D, variance=1.0, lengthscale=np.full(D, np.sqrt(D)), ARD=True)
     t0 = time.time()
-    split = "split" in sys.argv[4:]
-    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z, device_algebra=not split)
+    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z)
     t_first = time.time() - t0
     eng = m.inference_method.engine
     times = []
     for rep in range(3):
         m.likelihood.variance.values[...] = 0.05 * (1 + 0.01 * rep)
         t0 = time.time(); m.parameters_changed(); times.append(time.time() - t0)
-    # split: time the two device calls alone
-    kind, ard, var, ls = k._theta()
-    t0 = time.time(); G, pY = eng.sparse_stats(kind, ard, var, ls, Z); t_stats = time.time() - t0
-    W2 = np.eye(M) * 1e-3; C = np.zeros((M, 1))
-    t0 = time.time(); eng.sparse_grads(W2, C, 20.0); t_grads = time.time() - t0
     out = {"config": "SparseGPRegression RBF ARD N=%d M=%d D=%d" % (N, M, D), "first_eval_incl_alloc_s": t_first,
            "eval_wall_s": float(np.median(times)), "evals_per_s": 1.0 / float(np.median(times)),
-           "device_stats_call_s": t_stats, "device_grads_call_s": t_grads,
-           "mode": "split (host M x M algebra)" if split else "fused device evaluation (gpx_sparse_eval)",
-           "MxM_algebra_s": float(np.median(times)) - t_stats - t_grads,
-           "flops_stats": 2.0 * N * M * M / 2, "flops_grads": 2.0 * N * M * M, "lml": m.log_likelihood(),
+           "mode": "fused device evaluation (gpx_sparse_eval)",
+           "flops_NM2": {"tmp = Lm^-1 psi1^T (triangular)": 1.0 * N * M * M, "A = tmp tmp^T (lower)": 1.0 * N * M * M,
+                         "dL_dKnm^T = W2 psi1^T": 2.0 * N * M * M}, "lml": m.log_likelihood(),
            "grad_kern_variance": float(k.variance.gradient[0])}
     if cpu:
         from oracle import gpy_oracle as o
