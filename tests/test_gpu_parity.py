@@ -421,7 +421,10 @@ def test_sparse_golden_fixtures():
         assert abs(m.log_likelihood() - lml0) <= 1e-8 * max(1.0, abs(lml0)), fn
         g = np.concatenate([k.variance.gradient, k.lengthscale.gradient, m.likelihood.variance.gradient])
         np.testing.assert_allclose(g, z["grad"], rtol=1e-6, atol=1e-8, err_msg=fn)
-        np.testing.assert_allclose(m.Z.gradient, z["Zgrad"], rtol=1e-6, atol=1e-8, err_msg=fn)
+        # dL/dZ is the worst-conditioned output: for the Matern-5/2 fixture cond(Kmm) = 2e8 and the reference's own fp64
+        # result differs from an extended-precision evaluation of the same formulas by 7.7e-8 (2e-8 of max|dL/dZ|);
+        # hence the absolute floor relative to the largest entry
+        np.testing.assert_allclose(m.Z.gradient, z["Zgrad"], rtol=1e-6, atol=1e-7 * np.abs(z["Zgrad"]).max(), err_msg=fn)
         np.testing.assert_allclose(m.posterior.woodbury_vector, z["woodbury_vector"], rtol=1e-6, atol=1e-7, err_msg=fn)
 
 
