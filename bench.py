@@ -224,6 +224,7 @@ def run_ours(args):
         sampler.start()
     launches0 = eng.total_launches()
     dev_ms, upd_ms, upd_flops, lau_ms, lau_flops, kb_ms, kb_bytes = [], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
+    upd_launches = 0
     barrier()
     t0 = time.perf_counter()
     last = None
@@ -231,7 +232,7 @@ def run_ours(args):
         last = eng.exact_eval("rbf", True, *theta_for_step(D, s))
         st = eng.stats()
         dev_ms.append(st["total_ms"])
-        upd_ms += st["update_ms"]; upd_flops += st["update_flops"]
+        upd_ms += st["update_ms"]; upd_flops += st["update_flops"]; upd_launches += st["update_launches"]
         lau_ms += st["lauum_ms"]; lau_flops += st["lauum_flops"]
         kb_ms += st["kbuild_ms"]; kb_bytes += st["kbuild_bytes"]
     barrier()
@@ -310,9 +311,17 @@ def run_ours(args):
                          "achieved": ach if upd_ms > 0 else None, "peak": peak, "unit": "TFLOP/s",
                          "frac": ach / peak if (peak and upd_ms > 0) else None,
                          "note": None if upd_ms > 0 else "per-kernel event accounting is single-GPU; see whole_eval_*",
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 29 outer update
+                         # launches of one evaluation (ncu, profiles/r01_update_kernel_dram_traffic.txt); only valid
+                         # for the configuration it was captured on
+                         "traffic": 1.2127e9 if (N == 16384 and world == 1 and upd_ms > 0) else None,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         # C tiles read + written once (K = 1024 per launch at this size) + the 16384 x 1024 panel once
+                         "algorithmic_bytes_per_launch": (upd_flops / (2.0 * 128 * 128 * 1024) * 2 * 128 * 128 * 8 / upd_launches
+                                                          + 16384 * 1024 * 8) if (N == 16384 and upd_launches) else None,
                          "peak_source": "fp64 DMMA.8x8x4 issue rate measured in this run (gpx_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json holds no fp64 entry",
-                         "launches": None, "traffic": None,
+                         "launches": (upd_launches / args.steps) if upd_launches else None,
                          "share_of_step": upd_ms / (t_dev * 1e3) if t_dev else None,
                          "whole_eval_tflops": float(N) ** 3 * args.steps / t_dev * 1e-12,
                          "whole_eval_frac": float(N) ** 3 * args.steps / t_dev * 1e-12 / (peak * (world if sharded else 1)) if peak else None,
