@@ -926,6 +926,26 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
                 : launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st);
     c->total_launches++;
   }
+  if (!full_cov) {
+    // diagonal variance: everything reduces on the device; only M (P + 1) doubles come back
+    double* red = nullptr;   // [P][M] means, then [M] sums of squares
+    if (rc == 0 && cudaMalloc(&red, (size_t)(c->P + 1) * M * 8) != cudaSuccess) { gpx::set_error("gpx_predict: out of memory"); rc = -1; }
+    if (rc == 0) rc = launch_col_dot(Kx, ld, N, M, c->P, c->dAlpha, ld, red, M, st);              // mu = Kx^T alpha
+    if (rc == 0) rc = launch_col_sqnorm(Tx, ld, c->Npad, M, red + (size_t)c->P * M, st);          // sum_i tmp_i^2
+    if (rc == 0 && dG > 1) rc = dist_allreduce_sum(c, red + (size_t)c->P * M, (size_t)M, st);
+    c->total_launches += 2;
+    std::vector<double> h((size_t)(c->P + 1) * M);
+    if (rc == 0 && cudaMemcpyAsync(h.data(), red, h.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
+    cudaFree(Kx); cudaFree(Tx);
+    if (red) cudaFree(red);
+    if (rc) return rc;
+    for (long m = 0; m < M; m++) {
+      for (int q = 0; q < c->P; q++) mu[m * c->P + q] = h[(size_t)q * M + m];
+      var[m] = c->kp.variance - h[(size_t)c->P * M + m];
+    }
+    return 0;
+  }
   std::vector<double> hK, hT;
   if (rc == 0) {
     hK.resize((size_t)M * ld); hT.resize((size_t)M * ld);
@@ -936,22 +956,14 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   if (rc == 0 && cudaMemcpyAsync(hA.data(), c->dAlpha, hA.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
   if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
   // sums over the training index of this rank's part, completed over the ranks below
-  std::vector<double> ssq(full_cov ? (size_t)M * M : (size_t)M, 0.0);
+  std::vector<double> ssq((size_t)M * M, 0.0);
   if (rc == 0) {
-    if (!full_cov) {
-      for (long m = 0; m < M; m++) {
+    for (long a = 0; a < M; a++)
+      for (long b = 0; b < M; b++) {
         double s = 0.0;
-        for (long i = 0; i < N; i++) s += hT[m * ld + i] * hT[m * ld + i];
-        ssq[m] = s;
+        for (long i = 0; i < N; i++) s += hT[a * ld + i] * hT[b * ld + i];
+        ssq[a + b * M] = s;
       }
-    } else {
-      for (long a = 0; a < M; a++)
-        for (long b = 0; b < M; b++) {
-          double s = 0.0;
-          for (long i = 0; i < N; i++) s += hT[a * ld + i] * hT[b * ld + i];
-          ssq[a + b * M] = s;
-        }
-    }
     if (dG > 1) {
       if ((size_t)pn.ld * ld < ssq.size()) { gpx::set_error("gpx_predict: internal buffer size"); rc = -2; }
       if (rc == 0 && cudaMemcpyAsync(Kx, ssq.data(), ssq.size() * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
@@ -962,24 +974,20 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   }
   cudaFree(Kx); cudaFree(Tx);
   if (rc) return rc;
-  // small host epilogue: mu = Kx^T alpha, var = Kdiag - colsum(tmp^2) (or Kxx - tmp^T tmp)
+  // full covariance (small M): host epilogue mu = Kx^T alpha, var = Kxx - tmp^T tmp
   for (long m = 0; m < M; m++)
     for (int q = 0; q < c->P; q++) {
       double s = 0.0;
       for (long i = 0; i < N; i++) s += hK[m * ld + i] * hA[(size_t)q * ld + i];
       mu[m * c->P + q] = s;
     }
-  if (!full_cov) {
-    for (long m = 0; m < M; m++) var[m] = c->kp.variance - ssq[m];
-  } else {
-    std::vector<double> kxx((size_t)M * M);
-    double lsv[MAX_D];
-    for (int q = 0; q < MAX_D; q++) lsv[q] = c->kp.ls[q];
-    rc = gpx_kern_K(c, c->kp.kind, c->kp.ard, c->kp.variance, lsv, Xnew, M, nullptr, M, c->D, kxx.data());
-    if (rc) return rc;
-    for (long a = 0; a < M; a++)
-      for (long b = 0; b < M; b++) var[a + b * M] = kxx[a * M + b] - ssq[a + b * M];
-  }
+  std::vector<double> kxx((size_t)M * M);
+  double lsv[MAX_D];
+  for (int q = 0; q < MAX_D; q++) lsv[q] = c->kp.ls[q];
+  rc = gpx_kern_K(c, c->kp.kind, c->kp.ard, c->kp.variance, lsv, Xnew, M, nullptr, M, c->D, kxx.data());
+  if (rc) return rc;
+  for (long a = 0; a < M; a++)
+    for (long b = 0; b < M; b++) var[a + b * M] = kxx[a * M + b] - ssq[a + b * M];
   return 0;
 }
 

@@ -852,6 +852,24 @@ __global__ void __launch_bounds__(256) col_dot_kernel(const double* __restrict__
       if (lane == 0) out[(long)q * ldo + col] = s;
     }
 }
+// out[c] = sum_r A[r + c*ld]^2 : squared column norms of a tall column-major matrix, one warp per column
+__global__ void __launch_bounds__(256) col_sqnorm_kernel(const double* __restrict__ A, long ld, long rows, long cols,
+                                                         double* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long col = (long)blockIdx.x * 8 + warp;
+  if (col >= cols) return;
+  const double* a = A + col * ld;
+  double acc = 0.0;
+#pragma unroll 4
+  for (long r = lane; r < rows; r += 32) acc = fma(a[r], a[r], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[col] = acc;
+}
+int launch_col_sqnorm(const double* A, long ld, long rows, long cols, double* out, cudaStream_t st) {
+  col_sqnorm_kernel<<<(unsigned)((cols + 7) / 8), 256, 0, st>>>(A, ld, rows, cols, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
 int launch_col_dot(const double* A, long ld, long rows, long cols, int P, const double* Y, long ldy, double* out, long ldo,
                    cudaStream_t st) {
   col_dot_kernel<<<(unsigned)((cols + 7) / 8), 256, 0, st>>>(A, ld, rows, cols, P, Y, ldy, out, ldo);

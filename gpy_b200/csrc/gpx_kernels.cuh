@@ -61,6 +61,7 @@ int launch_untranspose(const double* in, long n, int p, long ld, double* out, cu
 int launch_gradx(const GradFullParams& p, int nchunk, long mchunk, double* part, double* out, cudaStream_t st);
 int launch_col_dot(const double* A, long ld, long rows, long cols, int P, const double* Y, long ldy, double* out, long ldo,
                    cudaStream_t st);
+int launch_col_sqnorm(const double* A, long ld, long rows, long cols, double* out, cudaStream_t st);
 int launch_row_dot(const double* A, long lda, long rows_pad, long ncols, int P, const double* Y, long ldy, int nsplit,
                    double* part, double* out, cudaStream_t st);
 int launch_load_sym(const double* A, long lda, long N, double* S, long ld, double jitter, cudaStream_t st);
