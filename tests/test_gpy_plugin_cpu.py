@@ -29,6 +29,13 @@ class FakeEngine(object):
         lml, g, self.res = o.eval_lml_grad(self.X, self.Y, kind, ARD, variance, lengthscale, noise)
         return lml, g, 0.0
 
+    def exact_eval_het(self, kind, ARD, variance, lengthscale, noise_variances, jitter=1e-8, max_tries=5):
+        self.calls.append("exact_eval_het")
+        lml, g, self.res = o.eval_lml_grad(self.X, self.Y, kind, ARD, variance, lengthscale, np.asarray(noise_variances))
+        nk = g.size - self.X.shape[0]
+        dn = g[nk:]
+        return lml, np.concatenate([g[:nk], [dn.sum()]]), dn, 0.0
+
     def get(self, which):
         return {"L": self.res["L"], "alpha": self.res["alpha"], "Kinv": self.res["Wi"], "dL_dK": self.res["dL_dK"],
                 "K": self.res["K"]}[which]
@@ -111,3 +118,31 @@ def test_unsupported_cases_fall_back_to_stock_method(setup):
     Kpre = plug.K(X)
     post, lml2, gd = inf.inference(plug, X, G.Gaussian(variance=0.1), Y, K=Kpre)   # precomputed K -> stock
     assert abs(lml - lml2) < 1e-10 and inf._engine is None
+
+
+def test_plugin_heteroscedastic_likelihood_equals_stock_reference(setup):
+    """The reference's own HeteroscedasticGaussian (likelihoods/gaussian.py:347-362) through the plugin inference: the
+    vector `variance` is routed to the per-point entry (gpx_exact_eval_het) and dL_dthetaL comes back through the
+    likelihood's own exact_inference_gradients — equal to the stock ExactGaussianInference with the stock kernel."""
+    G, B = setup
+    N = 60
+    X, Y = o.synthetic(N, 3, 7)
+    md = {"output_index": np.arange(N)[:, None]}
+    nv = np.random.default_rng(2).uniform(0.02, 0.3, N)
+    stock, plug = G.Matern32(3, variance=1.2, lengthscale=1.6), B.Matern32(3, variance=1.2, lengthscale=1.6)
+    lik_s, lik_p = G.HeteroscedasticGaussian(md), G.HeteroscedasticGaussian(md)
+    lik_s.variance[:] = nv.reshape(lik_s.variance.shape)
+    lik_p.variance[:] = nv.reshape(lik_p.variance.shape)
+    inf_s, inf_p = G.ExactGaussianInference(), B.ExactGaussianInference()
+    post_s, lml_s, gd_s = inf_s.inference(stock, X, lik_s, Y, None, md)
+    post_p, lml_p, gd_p = inf_p.inference(plug, X, lik_p, Y, None, md)
+    assert inf_p.engine.calls == ["set_data", "exact_eval_het"]
+    assert abs(lml_s - lml_p) < 1e-10
+    np.testing.assert_allclose(np.asarray(gd_p["dL_dthetaL"]).reshape(-1), np.asarray(gd_s["dL_dthetaL"]).reshape(-1), rtol=1e-9,
+                               atol=1e-12)
+    lik_s.update_gradients(gd_s["dL_dthetaL"]); lik_p.update_gradients(gd_p["dL_dthetaL"])
+    np.testing.assert_allclose(np.asarray(lik_p.variance.gradient).reshape(-1), np.asarray(lik_s.variance.gradient).reshape(-1),
+                               rtol=1e-9, atol=1e-12)
+    stock.update_gradients_full(gd_s["dL_dK"], X); plug.update_gradients_full(gd_p["dL_dK"], X)
+    np.testing.assert_allclose(plug.variance.gradient, stock.variance.gradient, rtol=1e-10)
+    np.testing.assert_allclose(plug.lengthscale.gradient, stock.lengthscale.gradient, rtol=1e-10)
