@@ -35,6 +35,7 @@ static int knm_grads_device(gpx_ctx* c, double beta, double* dvariance, double* 
 struct SparseState {
   long N = 0, Npad = 0, M = 0, Mpad = 0;   // N: rows held by THIS rank (all of them on one GPU)
   long Ntot = 0;                           // rows over all ranks (var_dtc.py num_data)
+  long Nw = 0, Mw = 0;                     // extents of psi1 written last time (a smaller N or M must re-zero the padding)
   int D = 0, P = 0;
   double *X = nullptr, *XsT = nullptr, *sqX = nullptr, *Y = nullptr, *Yb = nullptr;   // Y: [P][Npad]
   double *Z = nullptr, *ZsT = nullptr, *sqZ = nullptr;
@@ -62,6 +63,7 @@ void free_m(SparseState* s) {
   for (auto& p : s->mm) { if (p) cudaFree(p); p = nullptr; }
   s->have_eval = false;
   s->M = s->Mpad = 0;
+  s->Nw = s->Mw = 0;
 }
 void free_all(SparseState* s) {
   free_m(s);
@@ -213,6 +215,11 @@ static int psi_device(gpx_ctx* c, int kind, int ard, double variance, const doub
     GPX_CUDA(cudaMemsetAsync(s->Kfu, 0, (size_t)Mpad * Npad * 8, st));   // are ever written
   }
   s->M = M;
+  if (N < s->Nw || M < s->Mw) {   // fewer points than last time inside the same padded extents: stale entries must go
+    GPX_CUDA(cudaMemsetAsync(s->Kuf, 0, (size_t)Mpad * Npad * 8, st));
+    GPX_CUDA(cudaMemsetAsync(s->Kfu, 0, (size_t)Mpad * Npad * 8, st));
+  }
+  s->Nw = N; s->Mw = M;
   GPX_CUDA(cudaMemcpyAsync(s->Z, Z, (size_t)M * s->D * 8, cudaMemcpyHostToDevice, st));
   GPX_CHECK(launch_prep_x(s->X, N, Npad, s->kp, s->XsT, s->sqX, st));
   GPX_CHECK(launch_prep_x(s->Z, M, Mpad, s->kp, s->ZsT, s->sqZ, st));

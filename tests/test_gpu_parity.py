@@ -467,3 +467,22 @@ def test_heteroscedastic_model():
     np.testing.assert_allclose(var, var0 + m.likelihood.variance.values[:5].reshape(-1, 1), rtol=1e-7, atol=1e-10)
     d = m.optimize(max_iters=15)
     assert np.isfinite(m.log_likelihood()) and m.log_likelihood() >= lml0 - 1e-6
+
+
+def test_sparse_engine_reuse_with_fewer_points():
+    """The same context evaluated first with (N, M) = (700, 130) and then with (690, 129): same padded extents, so the
+    psi1 buffers must be re-zeroed beyond the new N and M (stale entries would enter the k-ranges of the GEMMs)."""
+    rng = np.random.default_rng(9)
+    e = _ffi.Engine(0)
+    for (N, M) in ((700, 130), (690, 129), (700, 130)):
+        X = rng.uniform(-3, 3, (N, 3))
+        Y = np.sin(X).sum(1, keepdims=True) + 0.1 * rng.standard_normal((N, 1))
+        Z = X[rng.permutation(N)[:M]].copy() + 0.01 * rng.standard_normal((M, 3))
+        ls = np.array([1.4, 1.9, 2.2])
+        e.sparse_set_data(X, Y)
+        lml, g, dZ = e.sparse_eval("matern32", True, 1.1, ls, Z, 0.06)
+        lml0, g0, Zg0, _ = o.sparse_eval(X, Y, Z, "matern32", True, 1.1, ls, 0.06)
+        assert abs(lml - lml0) <= 1e-8 * max(1.0, abs(lml0)), (N, M)
+        np.testing.assert_allclose(g, g0, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(dZ, Zg0, rtol=1e-6, atol=1e-7 * np.abs(Zg0).max())
+    e.close()
