@@ -142,26 +142,6 @@ def test_kernel_plugin_calls(kind, ARD):
             np.testing.assert_allclose(k.lengthscale.gradient, l0, rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("d", [20, 40, 64])
-def test_kernel_gradient_reductions_large_input_dimension(d):
-    """update_gradients_full / gradients_X with 16 < D <= 64 (the register-resident ARD sums are instantiated for 8, 16, 32
-    and 64 dimensions; the fused evaluation is covered at D=64 by test_multiple_outputs_and_large_D)."""
-    rng = np.random.default_rng(d)
-    n, m = 150, 70
-    X, X2 = rng.standard_normal((n, d)), rng.standard_normal((m, d))
-    ls = np.sqrt(d) * rng.uniform(0.8, 1.6, d)
-    k = gpy_b200.Matern52(d, variance=0.9, lengthscale=ls, ARD=True)
-    ko = o.StationaryOracle("matern52", d, 0.9, ls, True)
-    for XX2, shape in ((None, (n, n)), (X2, (n, m))):
-        dL = rng.standard_normal(shape)
-        k.update_gradients_full(dL, X, XX2)
-        v0, l0 = ko.update_gradients_full(dL, X, XX2)
-        np.testing.assert_allclose(k.variance.gradient, v0, rtol=1e-10)
-        np.testing.assert_allclose(k.lengthscale.gradient, l0, rtol=1e-9, atol=1e-12)
-        gx = k.gradients_X(dL, X, XX2)
-        np.testing.assert_allclose(gx, ko.gradients_X(dL, X, XX2), rtol=1e-9, atol=1e-12)
-
-
 def test_jitter_ladder_and_failure(eng):
     """jitchol semantics (GPy/util/linalg.py:56-75; test_linalg.py:20-37): duplicated inputs with zero noise are
     singular -> the ladder adds mean(diag)*1e-6*10^k; the result equals the oracle run with the same ladder."""
@@ -506,3 +486,23 @@ def test_sparse_engine_reuse_with_fewer_points():
         np.testing.assert_allclose(g, g0, rtol=1e-6, atol=1e-8)
         np.testing.assert_allclose(dZ, Zg0, rtol=1e-6, atol=1e-7 * np.abs(Zg0).max())
     e.close()
+
+
+@pytest.mark.parametrize("d", [20, 40, 64])
+def test_kernel_gradient_reductions_large_input_dimension(d):
+    """update_gradients_full / gradients_X with 16 < D <= 64 (the register-resident ARD sums are instantiated for 8, 16, 32
+    and 64 dimensions; the fused evaluation is covered at D=64 by test_multiple_outputs_and_large_D)."""
+    rng = np.random.default_rng(d)
+    n, m = 150, 70
+    X, X2 = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    ls = np.sqrt(d) * rng.uniform(0.8, 1.6, d)
+    k = gpy_b200.Matern52(d, variance=0.9, lengthscale=ls, ARD=True)
+    ko = o.StationaryOracle("matern52", d, 0.9, ls, True)
+    for XX2, shape in ((None, (n, n)), (X2, (n, m))):
+        dL = rng.standard_normal(shape)
+        k.update_gradients_full(dL, X, XX2)
+        v0, l0 = ko.update_gradients_full(dL, X, XX2)
+        np.testing.assert_allclose(k.variance.gradient, v0, rtol=1e-10)
+        np.testing.assert_allclose(k.lengthscale.gradient, l0, rtol=1e-9, atol=1e-12)
+        gx = k.gradients_X(dL, X, XX2)
+        np.testing.assert_allclose(gx, ko.gradients_X(dL, X, XX2), rtol=1e-9, atol=1e-12)
