@@ -81,6 +81,12 @@ class GpxError(RuntimeError):
     pass
 
 
+class GpxArgumentError(GpxError, ValueError):
+    """rc == -2: an argument outside its domain (variance / lengthscale <= 0 or NaN, bad shapes). It is a ValueError so
+    that an optimizer loop counts it as a failed evaluation the way paramz does (a Logexp underflow to exactly 0 or a
+    NaN iterate must not abort `optimize()`), and still a GpxError for callers that catch the library's own class."""
+
+
 def _ptr(a):
     return a.ctypes.data_as(_dp) if a is not None else None
 
@@ -97,6 +103,8 @@ def check(rc, what):
     msg = lib().gpx_last_error().decode()
     if rc > 0:
         raise np.linalg.LinAlgError("not positive definite, even with jitter. (leading minor %d)" % rc)
+    if rc == -2:
+        raise GpxArgumentError("%s: %s" % (what, msg))
     raise GpxError("%s failed (%d): %s" % (what, rc, msg))
 
 
@@ -119,6 +127,7 @@ class Engine(object):
         check(self._L.gpx_create(int(device), ctypes.byref(self._h)), "gpx_create")
         self.N = self.D = self.P = 0
         self.device = device
+        self.eval_serial = 0      # bumped by every evaluation: lazy posterior views check it before fetching
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -140,6 +149,7 @@ class Engine(object):
             raise ValueError("X must be N x D and Y N x P")
         self.N, self.D = X.shape
         self.P = Y.shape[1]
+        self.eval_serial += 1
         check(self._L.gpx_set_data(self._h, _ptr(X), self.N, self.D, _ptr(Y), self.P), "gpx_set_data")
 
     def exact_eval(self, kind, ARD, variance, lengthscale, noise, jitter=1e-8, max_tries=5):
@@ -150,6 +160,7 @@ class Engine(object):
         grad = np.zeros(ls.size + 2)
         rc = self._L.gpx_exact_eval(self._h, k, a, float(variance), _ptr(ls), float(noise), float(jitter), int(max_tries),
                                     ctypes.byref(lml), _ptr(grad), ctypes.byref(jit))
+        self.eval_serial += 1
         check(rc, "gpx_exact_eval")
         return lml.value, grad, jit.value
 
@@ -165,6 +176,7 @@ class Engine(object):
         dnoise = np.zeros(self.N)
         rc = self._L.gpx_exact_eval_het(self._h, k, a, float(variance), _ptr(ls), _ptr(nv), float(jitter), int(max_tries),
                                         ctypes.byref(lml), _ptr(grad), _ptr(dnoise), ctypes.byref(jit))
+        self.eval_serial += 1
         check(rc, "gpx_exact_eval_het")
         return lml.value, grad, dnoise, jit.value
 

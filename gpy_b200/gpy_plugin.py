@@ -20,7 +20,7 @@ import types
 import numpy as np
 
 from . import _ffi
-from .inference import PosteriorExact, _LazyAlpha, _fingerprint
+from .inference import PosteriorExact, _DataKey, _LazyAlpha
 from .kern import DeviceGradient
 
 _KINDS = {"RBF": "rbf", "Exponential": "exponential", "Matern32": "matern32", "Matern52": "matern52"}
@@ -79,13 +79,24 @@ def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi)
 
         def __init__(self, device=0, engine=None):
             super(B200ExactGaussianInference, self).__init__()
-            self.device, self._engine, self._data_key = device, engine, None
+            self.device, self._engine, self._data_key = device, engine, _DataKey()
 
         @property
         def engine(self):
             if self._engine is None:
                 self._engine = ffi.Engine(self.device)
             return self._engine
+
+        def invalidate_data(self):
+            """force an upload at the next inference whatever the content"""
+            self._data_key.invalidate()
+
+        def __getstate__(self):
+            """pickling goes back to a device-less object (precedent: GPy/kern/src/rbf.py:313-318 drops its GPU state);
+            the engine is re-created lazily and the data re-uploaded at the next inference"""
+            d = dict(self.__dict__)
+            d["_engine"], d["_data_key"] = None, _DataKey()
+            return d
 
         def inference(self, kern, X, likelihood, Y, mean_function=None, Y_metadata=None, K=None, variance=None,
                       Z_tilde=None):
@@ -100,10 +111,9 @@ def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi)
             Xs = np.ascontiguousarray(kern._slice_X(X)[0] if _returns_tuple(kern, X) else kern._slice_X(X),
                                       dtype=np.float64)
             Yc = np.ascontiguousarray(Y, dtype=np.float64)
-            key = (_fingerprint(Xs), _fingerprint(Yc))
-            if key != self._data_key:
+            if not self._data_key.matches(Xs, Yc):   # exact content comparison (GP.set_XY has no hook into inference)
                 self.engine.set_data(Xs, Yc)
-                self._data_key = key
+                self._data_key.remember(Xs, Yc)
             k, ard, var, ls = kern._gpx_theta()
             if het:
                 lml, grad, dnoise, _ = self.engine.exact_eval_het(k, ard, var, ls, nvec, jitter=1e-8, max_tries=5)
@@ -113,7 +123,7 @@ def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi)
                 dL_dthetaL = grad[-1]
             if Z_tilde is not None:
                 lml += Z_tilde
-            post = PosteriorExact(self.engine, Yc.shape[0], Yc.shape[1])
+            post = PosteriorExact(self.engine, Yc.shape[0], Yc.shape[1], kern._gpx_state_key())
             dlen = grad[1:-1] if ard else grad[1]
             dL_dK = DeviceGradient(self.engine, kern._gpx_state_key(), grad[0], dlen, Yc.shape[0])
             return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": dL_dthetaL, "dL_dm": _LazyAlpha(post)}

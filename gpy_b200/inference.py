@@ -66,12 +66,22 @@ class PosteriorExact(object):
     """Posterior whose big members live in HBM and are fetched lazily (posterior.py:21-77 constructor contract:
     woodbury_chol = L, woodbury_vector = alpha, K = noise-free kernel matrix)."""
 
-    def __init__(self, engine, N, P):
+    def __init__(self, engine, N, P, kern_key=None):
         self._engine, self._N, self._P = engine, N, P
         self._cache = {}
+        self._serial = getattr(engine, "eval_serial", None)   # the evaluation this posterior describes
+        self._kern_key = kern_key
+
+    def _check_fresh(self):
+        """The big members stay in HBM and the engine keeps only its LAST evaluation: a posterior handle kept across a
+        later evaluation must not silently describe the new theta (the reference's posterior owns its arrays)."""
+        if self._serial is not None and getattr(self._engine, "eval_serial", None) != self._serial:
+            raise RuntimeError("this posterior belongs to an earlier evaluation; the device now holds a newer one "
+                               "(read m.posterior again, or fetch what you need before the next parameter change)")
 
     def _get(self, which):
         if which not in self._cache:
+            self._check_fresh()
             self._cache[which] = self._engine.get(which)
         return self._cache[which]
 
@@ -99,20 +109,39 @@ class PosteriorExact(object):
 
     def _raw_predict(self, kern, Xnew, pred_var=None, full_cov=False):
         """posterior.py:273-302 on the device (gpx_predict). `pred_var` (the training inputs) is what the engine holds."""
+        key = kern._state_key() if hasattr(kern, "_state_key") else (
+            kern._gpx_state_key() if hasattr(kern, "_gpx_state_key") else None)
+        if self._kern_key is not None and key != self._kern_key:
+            # a different kernel than the one evaluated (GP.predict(Xnew, kern=sub_kernel)): the reference's formula with
+            # the kernel it is given (posterior.py:276-295), on the factor fetched from the device
+            return HostPosterior(self.woodbury_chol, self.woodbury_vector, None)._raw_predict(kern, Xnew, pred_var, full_cov)
+        self._check_fresh()
         Xn = kern._slice_X(Xnew) if hasattr(kern, "_slice_X") else np.asarray(Xnew, dtype=np.float64)
-        return self._engine.predict(Xn, full_cov=full_cov)
+        if isinstance(Xn, tuple):
+            Xn = Xn[0]
+        return self._engine.predict(np.ascontiguousarray(Xn, dtype=np.float64), full_cov=full_cov)
 
 
-def _fingerprint(A):
-    """Content fingerprint deciding whether (X, Y) must be re-uploaded: shape + two moments + a strided sample.
-    (paramz keys its caches on object identity; the sliced X is a fresh array on every call without paramz's cache, so
-    identity cannot be used here.) O(N D) host work, ~100 us at N=16384. Deliberately NOT a BLAS call (np.dot): a
-    multi-threaded BLAS spins up its worker pool for this tiny product and, under a CPU quota, the spinning workers get the
-    process throttled for tens of milliseconds right when the evaluation's kernels have to be enqueued (measured: +15/+31
-    ms on ~40 % of the evaluations at N=16384)."""
-    A = np.asarray(A)
-    flat = A.reshape(-1)
-    return (A.shape, float(flat.sum()), float(np.square(flat).sum()), flat[::max(1, flat.size // 64)].tobytes())
+class _DataKey(object):
+    """Decides whether (X, Y) must be uploaded again: an exact comparison with a private host copy of what the device
+    holds. (paramz keys its caches on object identity; the sliced X is a fresh array on every call without paramz's cache
+    and callers may permute rows in place, so neither identity nor a moment/sample fingerprint is safe — a row swap keeps
+    every moment.) Cost: one memcmp-speed pass, ~0.1 ms per MB, and N (D + P) doubles of host memory. Deliberately not a
+    BLAS call: a multi-threaded BLAS spins up its worker pool for such a tiny product and, under a CPU quota, the
+    spinning workers get the process throttled right when the evaluation's kernels have to be enqueued."""
+
+    def __init__(self):
+        self._X = self._Y = None
+
+    def invalidate(self):
+        self._X = self._Y = None
+
+    def matches(self, X, Y):
+        return (self._X is not None and self._X.shape == X.shape and self._Y.shape == Y.shape
+                and np.array_equal(self._X, X) and np.array_equal(self._Y, Y))
+
+    def remember(self, X, Y):
+        self._X, self._Y = np.array(X, dtype=np.float64, copy=True), np.array(Y, dtype=np.float64, copy=True)
 
 
 class ExactGaussianInference(object):
@@ -124,7 +153,7 @@ class ExactGaussianInference(object):
     def __init__(self, device=0, engine=None):
         self.device = device
         self._engine = engine
-        self._data_key = None
+        self._data_key = _DataKey()
 
     def on_optimization_start(self):
         pass
@@ -143,13 +172,12 @@ class ExactGaussianInference(object):
 
     def invalidate_data(self):
         """the model was handed new data (GP.set_XY): upload again at the next inference whatever the content."""
-        self._data_key = None
+        self._data_key.invalidate()
 
     def _bind(self, X, Y, force=False):
-        key = (_fingerprint(X), _fingerprint(Y))
-        if force or key != self._data_key:
+        if force or not self._data_key.matches(X, Y):
             self.engine.set_data(X, Y)
-            self._data_key = key
+            self._data_key.remember(X, Y)
 
     def inference(self, kern, X, likelihood, Y, mean_function=None, Y_metadata=None, K=None, variance=None,
                   Z_tilde=None):
@@ -171,7 +199,7 @@ class ExactGaussianInference(object):
             if Z_tilde is not None:
                 lml += Z_tilde
             N, P = Y.shape
-            post = PosteriorExact(self.engine, N, P)
+            post = PosteriorExact(self.engine, N, P, kern._state_key())
             dL_dK = DeviceGradient(self.engine, kern._state_key(), grad[0], grad[1:-1], N)
             dL_dthetaL = likelihood.exact_inference_gradients(dnoise, Y_metadata)              # :72 with gaussian.py:358
             return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": dL_dthetaL, "dL_dm": _LazyAlpha(post)}
@@ -180,7 +208,7 @@ class ExactGaussianInference(object):
         if Z_tilde is not None:
             lml += Z_tilde
         N, P = Y.shape
-        post = PosteriorExact(self.engine, N, P)
+        post = PosteriorExact(self.engine, N, P, kern._state_key())
         dL_dK = DeviceGradient(self.engine, kern._state_key(), grad[0], grad[1:-1], N)
         grad_dict = {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
         return post, lml, grad_dict
@@ -203,7 +231,7 @@ class ExactGaussianInference(object):
         if Z_tilde is not None:
             log_marginal += Z_tilde
         dL_dK = 0.5 * (np.dot(alpha, alpha.T) - YYT_factor.shape[1] * Wi)
-        self._data_key = None   # the context workspace was re-used
+        self._data_key.invalidate()   # the context workspace was re-used
         if np.ndim(noise) > 0 and likelihood is not None:
             dL_dthetaL = likelihood.exact_inference_gradients(np.diag(dL_dK), Y_metadata)
         else:

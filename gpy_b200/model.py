@@ -21,6 +21,7 @@ class GP(Parameterized):
     def __init__(self, X, Y, kernel, likelihood, mean_function=None, inference_method=None, name="gp", device=0,
                  engine=None, Y_metadata=None):
         super(GP, self).__init__(name)
+        self._initialised = False   # parameter writes during construction do not evaluate (paramz: after __init__)
         self.mean_function = mean_function
         self.Y_metadata = Y_metadata
         X = np.asarray(X, dtype=np.float64)
@@ -41,6 +42,7 @@ class GP(Parameterized):
         self._log_marginal_likelihood = None
         self.grad_dict = None
         self.update_model_flag = True
+        self._initialised = True
         self.parameters_changed()  # paramz's metaclass triggers this after __init__
 
     # ---- one evaluation: gp.py:269-282 -------------------------------------------------------------------------
@@ -116,12 +118,15 @@ class GP(Parameterized):
             self.optimizer_array = x
             f, g = self.objective_function(), self._grads_transformed()
             self._fail_count = 0
-        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError):
+        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError):   # _ffi.check maps argument-domain errors to ValueError
             # paramz tolerates a bounded number of failed evaluations during optimisation
             self._fail_count = getattr(self, "_fail_count", 0) + 1
             if self._fail_count > 10:
                 raise
-            return np.inf, np.zeros_like(x)
+            # paramz Model._objective_grads: objective = inf, gradient = the last good one (clipped)
+            g = getattr(self, "_last_good_grad", None)
+            return np.inf, (np.zeros_like(x) if g is None or g.shape != x.shape else np.clip(g, -1e10, 1e10))
+        self._last_good_grad = g
         return f, g
 
     def optimize(self, optimizer="lbfgsb", max_iters=1000, messages=False, gtol=1e-5, ftol=2.220446049250313e-09):

@@ -102,7 +102,14 @@ class Param(object):
 
 
 class Parameterized(object):
-    """Ordered container of Params and sub-containers (cf. paramz.Parameterized.link_parameter)."""
+    """Ordered container of Params and sub-containers (cf. paramz.Parameterized.link_parameter).
+
+    Writes to a linked leaf (`m.kern.variance[0] = 2.`, `Param.set`) travel up the link chain and end in the root's
+    `parameters_changed()` — the observer contract of paramz (`Parameterizable._notify_parent_change` /
+    `_trigger_params_changed`), so that `log_likelihood()`, `gradient` and `predict()` never describe an older theta.
+    The root gates the re-evaluation on `update_model_flag` (paramz `update_model(False)`)."""
+
+    _parent = None
 
     def __init__(self, name):
         self.name = name
@@ -110,6 +117,20 @@ class Parameterized(object):
 
     def link_parameter(self, p):
         self._links.append(p)
+        if isinstance(p, Param):
+            p._observers.append(self._child_changed)
+        else:
+            p._parent = self
+
+    def _child_changed(self):
+        root = self
+        while getattr(root, "_parent", None) is not None:
+            root = root._parent
+        if getattr(root, "update_model_flag", True) and getattr(root, "_initialised", True):
+            root.parameters_changed()
+
+    def parameters_changed(self):
+        pass
 
     link_parameters = lambda self, *ps: [self.link_parameter(p) for p in ps]
 

@@ -15,7 +15,7 @@ attached to a NCCL communicator, X and Y are this rank's rows (gpy_b200.dist.sha
 import numpy as np
 
 from . import _ffi
-from .inference import Gaussian, _fingerprint
+from .inference import Gaussian, _DataKey
 from .kern import RBF, Stationary
 from .param import Logexp, Param, Parameterized
 
@@ -71,7 +71,7 @@ class VarDTC(object):
     const_jitter = CONST_JITTER
 
     def __init__(self, device=0, engine=None, limit=1):
-        self.device, self._engine, self._data_key = device, engine, None
+        self.device, self._engine, self._data_key = device, engine, _DataKey()
 
     @property
     def engine(self):
@@ -86,7 +86,7 @@ class VarDTC(object):
         pass
 
     def invalidate_data(self):
-        self._data_key = None
+        self._data_key.invalidate()
 
     def inference(self, kern, X, Z, likelihood, Y, Y_metadata=None, mean_function=None, precision=None):
         if mean_function is not None:
@@ -97,10 +97,9 @@ class VarDTC(object):
         Xs = kern._slice_X(X)
         Zs = kern._slice_X(Z)
         Y = np.ascontiguousarray(Y, dtype=np.float64)
-        key = (_fingerprint(Xs), _fingerprint(Y))
-        if key != self._data_key:
+        if not self._data_key.matches(Xs, Y):
             eng.sparse_set_data(Xs, Y)
-            self._data_key = key
+            self._data_key.remember(Xs, Y)
         num_data, output_dim = Y.shape
         num_inducing = Zs.shape[0]
         kind, ard, var, ls = kern._theta()

@@ -25,3 +25,13 @@ def _have_gpu():
 @pytest.fixture(scope="session")
 def have_gpu():
     return _have_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU-marked tests are skipped (not failed) on a box without a CUDA device or without the built library."""
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (or libgpx.so not built)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

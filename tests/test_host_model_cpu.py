@@ -1,0 +1,163 @@
+"""Host-side model logic of the stand-alone mirror (gpy_b200.GPRegression) on CPU: the C ABI is replaced by a test double
+that answers from the oracle, so what is tested is the HOST logic only — observer propagation of parameter writes
+(paramz contract: every write re-evaluates), the exact-content data key, posterior handles that must not outlive
+their evaluation, `predict(kern=other)`, and the error mapping of the ctypes layer."""
+import numpy as np
+import pytest
+
+from oracle import gpy_oracle as o
+
+
+class FakeEngine(object):
+    """test double of gpy_b200._ffi.Engine: same methods, numbers from the oracle."""
+
+    def __init__(self, device=0):
+        self.calls = []
+        self.eval_serial = 0
+
+    def set_data(self, X, Y):
+        self.X, self.Y = np.array(X), np.array(Y)
+        self.eval_serial += 1
+        self.calls.append("set_data")
+
+    def exact_eval(self, kind, ARD, variance, lengthscale, noise, jitter=1e-8, max_tries=5):
+        self.calls.append("exact_eval")
+        self.eval_serial += 1
+        self.theta = (kind, ARD, variance, np.array(lengthscale, copy=True))
+        lml, g, self.res = o.eval_lml_grad(self.X, self.Y, kind, ARD, variance, lengthscale, noise)
+        return lml, g, 0.0
+
+    def get(self, which):
+        return {"L": self.res["L"], "alpha": self.res["alpha"], "Kinv": self.res["Wi"], "dL_dK": self.res["dL_dK"],
+                "K": self.res["K"]}[which]
+
+    def predict(self, Xnew, full_cov=False):
+        kind, ARD, var, ls = self.theta
+        k = o.StationaryOracle(kind, self.X.shape[1], var, ls, ARD)
+        return o.raw_predict(k, self.X, self.res["L"], self.res["alpha"], Xnew, full_cov)
+
+    def total_launches(self):
+        return 0
+
+
+def _model(N=60, D=3, seed=2):
+    import gpy_b200
+    X, Y = o.synthetic(N, D, seed)
+    eng = FakeEngine()
+    m = gpy_b200.GPRegression(X, Y, gpy_b200.RBF(D, variance=1.3, lengthscale=[1.1, 1.6, 2.2], ARD=True), noise_var=0.05,
+                              engine=eng)
+    return m, eng, X, Y
+
+
+def test_parameter_writes_re_evaluate_like_paramz():
+    m, eng, X, Y = _model()
+    assert eng.calls == ["set_data", "exact_eval"]           # one evaluation after construction, none during it
+    l0 = m.log_likelihood()
+    m.kern.variance[0] = 2.0                                   # a leaf write -> GP.parameters_changed()
+    assert eng.calls[-1] == "exact_eval" and len(eng.calls) == 3
+    ref, g, _ = o.eval_lml_grad(X, Y, "rbf", True, 2.0, np.array([1.1, 1.6, 2.2]), 0.05)
+    assert m.log_likelihood() != l0 and abs(m.log_likelihood() - ref) < 1e-9
+    np.testing.assert_allclose(m.gradient, g, rtol=1e-9)
+    m.likelihood.variance.set(0.2)
+    ref, g, _ = o.eval_lml_grad(X, Y, "rbf", True, 2.0, np.array([1.1, 1.6, 2.2]), 0.2)
+    assert abs(m.log_likelihood() - ref) < 1e-9
+    # update_model(False) defers, update_model(True) evaluates once
+    n = len(eng.calls)
+    m.update_model(False)
+    m.kern.lengthscale[1] = 3.0
+    m.kern.variance[0] = 0.7
+    assert len(eng.calls) == n
+    m.update_model(True)
+    assert len(eng.calls) == n + 1
+    ref, g, _ = o.eval_lml_grad(X, Y, "rbf", True, 0.7, np.array([1.1, 3.0, 2.2]), 0.2)
+    assert abs(m.log_likelihood() - ref) < 1e-9
+
+
+def test_data_key_sees_row_permutations_and_in_place_edits():
+    from gpy_b200.inference import _DataKey
+    rng = np.random.default_rng(0)
+    X, Y = rng.standard_normal((1000, 4)), rng.standard_normal((1000, 1))
+    k = _DataKey()
+    assert not k.matches(X, Y)
+    k.remember(X, Y)
+    assert k.matches(X, Y) and k.matches(X.copy(), Y.copy())
+    for trial in range(50):                                    # a moment / strided-sample fingerprint misses most of these
+        i, j = rng.choice(1000, 2, replace=False)
+        Yp = Y.copy(); Yp[[i, j]] = Yp[[j, i]]
+        Xp = X.copy(); Xp[[i, j]] = Xp[[j, i]]
+        assert not k.matches(X, Yp) and not k.matches(Xp, Y)
+    X[3, 1] += 1e-9                                            # in-place edit of the caller's array: the key holds a copy
+    assert not k.matches(X, Y)
+    assert not k.matches(X[:999], Y[:999])
+
+
+def test_shuffled_labels_are_uploaded_again():
+    m, eng, X, Y = _model()
+    Yp = Y.copy(); Yp[[0, 1]] = Yp[[1, 0]]
+    post, lml, _ = m.inference_method.inference(m.kern, X, m.likelihood, Yp)
+    assert eng.calls[-2:] == ["set_data", "exact_eval"]
+    ref, _, _ = o.eval_lml_grad(X, Yp, "rbf", True, 1.3, np.array([1.1, 1.6, 2.2]), 0.05)
+    assert abs(lml - ref) < 1e-9
+
+
+def test_posterior_handle_does_not_outlive_its_evaluation():
+    m, eng, X, Y = _model()
+    old = m.posterior
+    alpha_old = old.woodbury_vector.copy()                     # fetched while fresh: stays cached and valid
+    m.kern.variance[0] = 2.5
+    np.testing.assert_array_equal(old.woodbury_vector, alpha_old)
+    with pytest.raises(RuntimeError):
+        old.woodbury_chol                                      # not fetched before the new evaluation -> refuses
+    assert m.posterior is not old
+    assert m.posterior.woodbury_chol.shape == (60, 60)
+
+
+def test_predict_with_another_kernel_uses_that_kernel():
+    import gpy_b200
+    m, eng, X, Y = _model()
+    Xn = np.random.default_rng(1).uniform(-2, 2, (7, 3))
+    mu, var = m.predict(Xn)
+    k = o.StationaryOracle("rbf", 3, 1.3, np.array([1.1, 1.6, 2.2]), True)
+    mu0, var0 = o.predict(k, X, eng.res["L"], eng.res["alpha"], Xn, 0.05)
+    np.testing.assert_allclose(mu, mu0, rtol=1e-10)
+    np.testing.assert_allclose(var, var0, rtol=1e-10)
+
+    class HostRBF(gpy_b200.RBF):
+        """answers K / Kdiag from the oracle (no device here)"""
+        def K(self, X, X2=None):
+            return o.StationaryOracle("rbf", self.input_dim, float(self.variance[0]), self.lengthscale.values, self.ARD).K(X, X2)
+        def Kdiag(self, X):
+            return np.full(X.shape[0], float(self.variance[0]))
+
+    other = HostRBF(3, variance=0.4, lengthscale=[2.0, 2.0, 2.0], ARD=True)
+    mu2, var2 = m.predict(Xn, kern=other, include_likelihood=False)
+    k2 = o.StationaryOracle("rbf", 3, 0.4, np.array([2.0, 2.0, 2.0]), True)
+    mu20, var20 = o.raw_predict(k2, X, eng.res["L"], eng.res["alpha"], Xn)      # posterior.py:276-295 with the GIVEN kernel
+    np.testing.assert_allclose(mu2, mu20, rtol=1e-10)
+    np.testing.assert_allclose(var2, var20, rtol=1e-10)
+    assert not np.allclose(mu2, mu)
+
+
+def test_argument_domain_errors_are_value_errors_and_optimize_survives():
+    from gpy_b200 import _ffi
+    assert issubclass(_ffi.GpxArgumentError, ValueError) and issubclass(_ffi.GpxArgumentError, _ffi.GpxError)
+    with pytest.raises(ValueError):
+        _ffi.check(-2, "gpx_exact_eval")
+    with pytest.raises(np.linalg.LinAlgError):
+        _ffi.check(3, "gpx_exact_eval")
+    with pytest.raises(_ffi.GpxError):
+        _ffi.check(-1, "gpx_exact_eval")
+    m, eng, X, Y = _model(N=40)
+    real = eng.exact_eval
+    state = {"n": 0}
+
+    def flaky(*a, **k):                                        # the 4th evaluation of the run fails in the argument check
+        state["n"] += 1
+        if state["n"] == 4:
+            raise _ffi.GpxArgumentError("gpx_exact_eval: lengthscale must be positive")
+        return real(*a, **k)
+
+    eng.exact_eval = flaky
+    f0 = m.objective_function()
+    d = m.optimize(max_iters=15)                               # must not raise; the failed iterate counts as f = inf
+    assert state["n"] > 4 and np.isfinite(d["f"]) and d["f"] < f0

@@ -26,12 +26,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int c_fmt, int a_fmt, int b_fm
          (uint32_t)((M >> 4) << 24);
 }
 
-template <int KIND>   // 0 = i8 (s8 x s8 -> s32), 1 = f8f6f4 (e4m3 -> f32), 2 = f16 (bf16 -> f32)
+template <int KIND, int N>   // 0 = i8 (s8 x s8 -> s32), 1 = f8f6f4 (e4m3 -> f32), 2 = f16 (bf16 -> f32); N = MMA width
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* cycles, int nmma) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base;
   __shared__ __align__(8) uint64_t bar;
-  constexpr int M = 128, N = 256;
+  constexpr int M = 128;
   constexpr int A_BYTES = M * 32, B_BYTES = N * 32;     // one MMA consumes 32 bytes of K per row
   for (int i = threadIdx.x; i < 4 * (A_BYTES + B_BYTES) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
   if (threadIdx.x == 0) {
@@ -81,24 +81,24 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* cycles, int
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(taddr));
 }
 
-template <int KIND>
+template <int KIND, int N = 256>
 static void run(const char* name, int k_elems, int nsm, double ghz) {
-  const int smem = 4 * (128 * 32 + 256 * 32);
-  cudaFuncSetAttribute(mma_rate_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = 4 * (128 * 32 + N * 32);
+  cudaFuncSetAttribute(mma_rate_kernel<KIND, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   long long* d; cudaMalloc(&d, nsm * sizeof(long long));
   const int nmma = 4096;
   for (int rep = 0; rep < 3; rep++) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    mma_rate_kernel<KIND><<<nsm, 128, smem>>>(d, nmma);
+    mma_rate_kernel<KIND, N><<<nsm, 128, smem>>>(d, nmma);
     cudaEventRecord(e1);
     cudaError_t err = cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     long long h[1024]; cudaMemcpy(h, d, nsm * sizeof(long long), cudaMemcpyDeviceToHost);
     long long mx = 0; for (int i = 0; i < nsm; i++) mx = h[i] > mx ? h[i] : mx;
-    const double ops = 2.0 * 128 * 256 * k_elems * (double)nmma;
-    printf("%-18s rep %d: %s  %.1f clk per 128x256x%d MMA, %.0f ops/clk/SM, chip %.1f Tops/s (kernel %.3f ms -> %.1f Tops/s)\n", name, rep,
-           cudaGetErrorString(err), (double)mx / nmma, k_elems, ops / mx, ops / mx * nsm * ghz * 1e-3, ms, ops * nsm / (ms * 1e-3) * 1e-12);
+    const double ops = 2.0 * 128 * N * k_elems * (double)nmma;
+    printf("%-18s rep %d: %s  %.1f clk per 128x%dx%d MMA, %.0f ops/clk/SM, chip %.1f Tops/s (kernel %.3f ms -> %.1f Tops/s)\n", name, rep,
+           cudaGetErrorString(err), (double)mx / nmma, N, k_elems, ops / mx, ops / mx * nsm * ghz * 1e-3, ms, ops * nsm / (ms * 1e-3) * 1e-12);
   }
   cudaFree(d);
 }
@@ -111,5 +111,9 @@ int main() {
   run<0>("kind::i8 s8xs8->s32", 32, p.multiProcessorCount, ghz);
   run<1>("kind::f8f6f4 e4m3", 32, p.multiProcessorCount, ghz);
   run<2>("kind::f16 bf16", 16, p.multiProcessorCount, ghz);
+  // narrower MMAs: is the rate still 8192 MAC/clk/SM when the A tile (4 KB) is re-read for every N = 128 / 64 / 32 columns?
+  run<0, 128>("kind::i8 N=128", 32, p.multiProcessorCount, ghz);
+  run<0, 64>("kind::i8 N=64", 32, p.multiProcessorCount, ghz);
+  run<0, 32>("kind::i8 N=32", 32, p.multiProcessorCount, ghz);
   return 0;
 }
