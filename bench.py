@@ -189,8 +189,9 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line on stdout: NCCL's own lines (version banner, INFO/INIT when NCCL_DEBUG asks for them)
+    # are routed to stderr, not silenced — NCCL_DEBUG itself is left exactly as the caller set it
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
@@ -272,6 +273,24 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = (1 if sharded or world == 1 else world) * e2e_steps / float(e2e_t[0])
 
+    # ---- parity carried by the bench line itself when N > 1 (the driver's SCALE run has no other parity evidence) ---------
+    parity_multi = None
+    if sharded:
+        th_last = theta_for_step(D, args.steps - 1)
+        lml_s, grad_s, _ = eng.exact_eval("rbf", True, *th_last)      # collective: every rank takes part
+        if rank == 0:
+            e1 = _ffi.Engine(local)                                  # the single-GPU engine on the same device, same theta
+            e1.set_data(X, Y)
+            lml_1, grad_1, _ = e1.exact_eval("rbf", True, *th_last)
+            e1.close()
+            parity_multi = {"parity_vs_1gpu": {"lml_abs": abs(lml_s - lml_1),
+                                               "grad_rel_max": float(np.max(np.abs(grad_s - grad_1) / np.abs(grad_1)))}}
+            if N <= 4096:
+                _, lml_c, grad_c = cpu_eval_timed(N, D, args.steps - 1, ensure_oracle_native())
+                parity_multi["parity_vs_oracle"] = {"lml_abs": abs(lml_s - lml_c),
+                                                    "grad_rel_max": float(np.max(np.abs(grad_s - grad_c) / np.abs(grad_c)))}
+        barrier()
+
     if rank == 0:
         peak = eng.measure_fp64_peak()
         ach = upd_flops / upd_ms * 1e-9 if upd_ms > 0 else 0.0
@@ -330,6 +349,8 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if parity_multi:
+            line.update(parity_multi)
         print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()

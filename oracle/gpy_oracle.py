@@ -414,6 +414,34 @@ def logexp_gradfactor(f):
     return np.where(f > 36.0, 1.0, -np.expm1(-f))
 
 
+def optimize_lbfgsb(X, Y, kind, ARD, variance, lengthscale, noise_variance, max_iters=1000, gtol=1e-5,
+                    ftol=2.220446049250313e-09):
+    """The optimisation loop of GP.optimize (GPy/core/gp.py:663-684 -> paramz Model.optimize, default 'lbfgsb' =
+    scipy.optimize.fmin_l_bfgs_b) on this oracle's objective: minimise -LML (model.py:97-109) over the Logexp-transformed
+    [variance, lengthscale.., noise] (stationary.py:78-79, gaussian.py:43), gradient chain-ruled through d theta/d x
+    (model.py:111-128 + paramz _transform_gradients). paramz itself is absent, so the trajectory is *parity unpinned*
+    (SURVEY.md §8c ii); this restatement gives the device path a CPU run of the same loop to compare final values with.
+    -> (lml_final, theta_final [variance, lengthscale.., noise], n_evals, lml_initial)"""
+    from scipy.optimize import fmin_l_bfgs_b
+    D = X.shape[1]
+    nl = D if ARD else 1
+    th0 = np.concatenate([[variance], np.atleast_1d(np.asarray(lengthscale, dtype=np.float64)).reshape(-1), [noise_variance]])
+    count = {"n": 0, "first": None}
+
+    def fg(x):
+        th = logexp_f(x)
+        ls = th[1:1 + nl] if ARD else float(th[1])
+        lml, g, _ = eval_lml_grad(X, Y, kind, ARD, float(th[0]), ls, float(th[-1]))
+        count["n"] += 1
+        if count["first"] is None:
+            count["first"] = lml
+        return -lml, -g * logexp_gradfactor(th)
+
+    x, f, d = fmin_l_bfgs_b(fg, logexp_finv(th0), maxfun=max_iters, maxiter=max_iters, pgtol=gtol,
+                            factr=ftol / np.finfo(float).eps)
+    return -f, logexp_f(x), count["n"], count["first"]
+
+
 # ----------------------------------------------------------------------------------------------------------
 # sparse GP regression: GPy/inference/latent_function_inference/var_dtc.py:66-276 (VarDTC, Gaussian likelihood,
 # homoscedastic noise, certain inputs, no mean function) + the gradient wiring of GPy/core/sparse_gp.py:108-119
