@@ -46,6 +46,12 @@ static void free_data(gpx_ctx* c) {
   c->staging_cap = 0;
   c->have_eval = false;
   c->have_kinv = false;
+  oz_planes_free(c->ozp[0]);
+  oz_planes_free(c->ozp[1]);
+  if (c->oz_tiles) cudaFree(c->oz_tiles);
+  c->oz_tiles = nullptr;
+  c->oz_steps.clear();
+  c->oz_ready = false;
 }
 
 static long pick_nb(const gpx_ctx* c) {
@@ -100,6 +106,8 @@ int gpx_create(int device, gpx_ctx** out) {
   GPX_CUDA(cudaMallocHost(&c->h_res, (MAX_D + 8) * sizeof(double)));
   GPX_CUDA(cudaMallocHost(&c->h_info, sizeof(int)));
   GPX_CHECK(gemm_init());
+  GPX_CHECK(oz_init());
+  GPX_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   *out = c;
   return 0;
 }
@@ -139,6 +147,13 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "profile")) { c->profile = (int)value; return 0; }
+  if (!strcmp(name, "ozaki")) { c->ozaki = value < 0 ? -1 : (value ? 1 : 0); return 0; }
+  if (!strcmp(name, "oz_dig_up")) {
+    if (value < 4 || value > OZ_S) GPX_FAIL("oz_dig_up must be in [4, 8]");
+    c->oz_dig_up = (int)value;
+    return 0;
+  }
+  if (!strcmp(name, "oz_ctas")) { c->oz_ctas = (int)std::max<int64_t>(0, value); return 0; }
   if (!strcmp(name, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
   GPX_FAIL("unknown option");
 }
@@ -244,6 +259,71 @@ static int sync_event(gpx_ctx* c, size_t idx, cudaEvent_t* out) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05 / Ozaki path: tile lists and buffers for (Npad, NB)
+// ---------------------------------------------------------------------------------------------------------------
+static bool oz_wanted(const gpx_ctx* c) {
+  if (c->dist) return false;
+  int on = c->ozaki;
+  if (on < 0) { const char* e = getenv("GPX_OZAKI"); on = e ? atoi(e) : 1; }
+  if (!on) return false;
+  const long NB = pick_nb(c);
+  return c->Npad >= 2 * NB && NB % OZ_KC == 0;   // a single-block matrix has no panel: it stays on the DMMA path
+}
+
+// tiles in bands of 8 row tiles x 16 column tiles (64 wide): the ~148 tiles in flight share 8 A panels and 16 B panels in L2
+template <class Valid, class Emit>
+static void oz_banded(const std::vector<int>& rows, int c64_beg, int c64_end, Valid valid, Emit emit) {
+  for (size_t b = 0; b < rows.size(); b += 8)
+    for (int cc = c64_beg; cc < c64_end; cc += 16)
+      for (size_t i = b; i < std::min(rows.size(), b + 8); i++)
+        for (int c64 = cc; c64 < std::min(c64_end, cc + 16); c64++)
+          if (valid(rows[i], c64 / 2)) emit(rows[i], c64);
+}
+
+static int oz_prepare(gpx_ctx* c) {
+  if (c->oz_ready) return 0;
+  const long Npad = c->Npad, NB = pick_nb(c);
+  const int nt = (int)(Npad / TILE);
+  if (nt >= 4096) GPX_FAIL("matrix too large for the tile encoding");
+  GPX_CHECK(oz_planes_alloc(c->ozp[0], Npad, NB));
+  GPX_CHECK(oz_planes_alloc(c->ozp[1], Npad, NB));
+  if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)Npad * Npad * 8));
+  std::vector<uint32_t> tiles;
+  c->oz_steps.clear();
+  for (long o = 0; o < Npad; o += NB) {
+    const long nb = std::min(NB, Npad - o);
+    const int kt0 = (int)(o / TILE), kt1 = kt0 + (int)(nb / TILE);
+    const int next_nbt = kt1 < nt ? (int)(std::min(NB, Npad - (o + nb)) / TILE) : 0;
+    gpx_ctx::OzStep st;
+    auto emit_update = [&](int cbeg, int cend) {   // S(r, c) -= P_r P_c^T, c in [cbeg, cend), r in [0, kt1) U [c, nt)
+      std::vector<int> rows;
+      for (int r = 0; r < kt1; r++) rows.push_back(r);
+      for (int r = cbeg; r < nt; r++) rows.push_back(r);
+      oz_banded(rows, 2 * cbeg, 2 * cend, [&](int r, int cc) { return r < kt1 || cc <= r; },
+                [&](int r, int c64) { tiles.push_back(oz_tile(r, c64, OZ_UPDATE, r < kt1 ? 1 : 0)); });
+    };
+    st.u1_off = (int)tiles.size();
+    if (kt1 < nt) emit_update(kt1, kt1 + next_nbt);
+    st.u1_n = (int)tiles.size() - st.u1_off;
+    st.u2_off = (int)tiles.size();
+    if (kt1 + next_nbt < nt) emit_update(kt1 + next_nbt, nt);
+    st.u2_upd = (int)tiles.size() - st.u2_off;
+    {   // K^-1(r, c) (+)= P_r P_c^T for c <= r < kt1: rows of block k see their first contribution at this step
+      std::vector<int> rows;
+      for (int r = 0; r < kt1; r++) rows.push_back(r);
+      oz_banded(rows, 0, 2 * kt1, [&](int r, int cc) { return cc <= r; },
+                [&](int r, int c64) { tiles.push_back(oz_tile(r, c64, r >= kt0 ? OZ_LAUUM_SET : OZ_LAUUM_ACC, 1)); });
+    }
+    st.u2_n = (int)tiles.size() - st.u2_off;
+    c->oz_steps.push_back(st);
+  }
+  GPX_CUDA(cudaMalloc(&c->oz_tiles, tiles.size() * sizeof(uint32_t)));
+  GPX_CUDA(cudaMemcpy(c->oz_tiles, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  c->oz_ready = true;
+  return 0;
+}
+
 // Step k of the sweep (block column k of width nb):
 //   D(k)  inner sweep of the diagonal block (128 columns at a time) + assemble of U_kk / Linv_kk      [side stream]
 //   Pn(k) panel GEMM  P = S(:,block k) Linv_kk^T -> Pbuf[k&1], copied back into S                     [side stream]
@@ -251,7 +331,9 @@ static int sync_event(gpx_ctx* c, size_t idx, cudaEvent_t* out) {
 //   U2(k) trailing update of the remaining columns                                                      [main stream]
 // Look-ahead: D(k+1), Pn(k+1) only need U1(k), so they run on the high-priority side stream while U2(k) keeps the
 // machine busy; U1(k+1) waits for Pn(k+1). Without look-ahead everything is issued on the main stream.
-static int run_sweep(gpx_ctx* c, Recorder& rec) {
+// oz: 0 = DMMA updates; 1 = trailing update on tcgen05 (Ozaki split); 2 = that + K^-1 = U U^T accumulated into c->Kinv
+// panel by panel inside the same launches (the panel's digit planes serve both)
+static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
   const long ld = c->Npad, Npad = c->Npad;
   const int nt = (int)(Npad / TILE);
   const long NB = pick_nb(c);
@@ -318,13 +400,42 @@ static int run_sweep(gpx_ctx* c, Recorder& rec) {
     if (kt1 < nt)
       GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8,
                                  (size_t)(Npad - o - nb) * 8, nb, cudaMemcpyDeviceToDevice, ss));
+    if (oz) {   // digit planes + row exponents of this panel (all rows: U block column | U_kk | Cholesky panel)
+      GPX_CHECK(launch_oz_split(Pb, Npad, nb, c->ozp[kblk & 1], ss));
+      c->eval_launches++;
+    }
     if (la) {
       GPX_CHECK(sync_event(c, evi++, &ev));
       GPX_CUDA(cudaEventRecord(ev, ss));
       GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
     }
     // ---- trailing update: S(r,c) -= P_r P_c^T for c >= kt1, r in [0,kt1) U [c,nt), split U1 | U2 ---------------
-    if (kt1 < nt) {
+    if (oz) {
+      const gpx_ctx::OzStep& os = c->oz_steps[kblk];
+      const OzPlanes& pl = c->ozp[kblk & 1];
+      for (int part = 0; part < 2; part++) {
+        const int off = part == 0 ? os.u1_off : os.u2_off;
+        const int ntl = part == 0 ? os.u1_n : (oz >= 2 ? os.u2_n : os.u2_upd);
+        if (ntl > 0) {
+          OzParams op;
+          memset(&op, 0, sizeof(op));
+          op.tiles = c->oz_tiles + off; op.ntiles = ntl; op.nkc = (int)(nb / OZ_KC);
+          op.scale = pl.scale; op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
+          op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up;
+          const double flops = (double)ntl * 2.0 * OZ_TM * OZ_TN * (double)nb;
+          const int h = rec.begin(PH_UPDATE, flops);
+          GPX_CHECK(launch_oz_gemm(pl, op, c->oz_ctas > 0 ? c->oz_ctas : c->num_sms, sm));
+          rec.end(h);
+          c->eval_launches++;
+          c->stats.update_launches++;
+        }
+        if (part == 0 && la && kt1 < nt) {
+          GPX_CHECK(sync_event(c, evi++, &ev));
+          GPX_CUDA(cudaEventRecord(ev, sm));
+          GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+        }
+      }
+    } else if (kt1 < nt) {
       const int next_nbt = (int)(std::min(NB, Npad - (o + nb)) / TILE);
       for (int part = 0; part < 2; part++) {
         const int cbeg = part == 0 ? kt1 : kt1 + next_nbt;
@@ -412,9 +523,12 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     rec.end(h);
     c->eval_launches++;
   }
+  const bool oz = oz_wanted(c);
+  if (oz) GPX_CHECK(oz_prepare(c));
+  c->oz_last = oz;
   {
     const int h = rec.begin(PH_SWEEP);
-    GPX_CHECK(run_sweep(c, rec));
+    GPX_CHECK(run_sweep(c, rec, oz ? 2 : 0));
     rec.end(h);
   }
   {
@@ -424,7 +538,24 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     rec.end(h);
     c->eval_launches += 3;
   }
-  GPX_CHECK(run_lauum(c, nullptr, &rec));
+  if (oz) {
+    // K^-1 was accumulated panel by panel inside the sweep (tcgen05): reduce dL_dK -> gradients from the stored tiles
+    GPX_CUDA(cudaMemsetAsync(c->partials, 0, (size_t)nt * nt * (nl + 2) * 8, st));
+    GradKinvParams gk;
+    memset(&gk, 0, sizeof(gk));
+    gk.Kinv = c->Kinv; gk.ld = ld;
+    gk.XsT = c->dXsT; gk.sq = c->dsq; gk.alpha = c->dAlpha; gk.ldx = c->Npad;
+    gk.N = c->N; gk.P = c->P; gk.nt = nt;
+    gk.partials = c->partials;
+    gk.dnoise_out = c->het ? c->dDnoise : nullptr;
+    gk.kp = c->kp;
+    const int h = rec.begin(PH_LAUUM, 0.0);
+    GPX_CHECK(launch_grad_kinv(gk, st));
+    rec.end(h);
+    c->eval_launches++;
+  } else {
+    GPX_CHECK(run_lauum(c, nullptr, &rec));
+  }
   {
     FinalizeParams f;
     memset(&f, 0, sizeof(f));
@@ -530,6 +661,7 @@ static int exact_eval_impl(gpx_ctx* c, int kind, int ard, double variance, const
     GPX_CUDA(cudaStreamSynchronize(c->st));
   }
   c->have_eval = true;
+  c->have_kinv = c->oz_last;   // the Ozaki path leaves K^-1 (lower tiles) in c->Kinv
   return 0;
 }
 

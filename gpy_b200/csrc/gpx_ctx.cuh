@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "gpx_common.cuh"
+#include "gpx_ozaki.cuh"
 
 struct DistState;
 struct SparseState;
@@ -53,6 +54,17 @@ struct gpx_ctx {
   int64_t eval_launches = 0;
   std::vector<cudaEvent_t> ev;
   int profile = 1;
+  // ---- tcgen05 / Ozaki path (gpx_ozaki.cu): trailing update and K^-1 on the INT8 tensor cores ------------------------
+  int ozaki = -1;              // option "ozaki": -1 = default (env GPX_OZAKI, else on), 0 = DMMA only, 1 = on where applicable
+  int oz_dig_up = gpx::OZ_S;   // digits per operand for the inverse-part / K^-1 tiles (option "oz_dig_up")
+  int oz_ctas = 0;             // CTAs of the persistent GEMM (0 = one per SM)
+  int num_sms = 148;
+  bool oz_ready = false;       // planes, K^-1 buffer and tile lists allocated for (Npad, NB)
+  gpx::OzPlanes ozp[2];        // digit planes of the current / next panel (look-ahead double buffer)
+  uint32_t* oz_tiles = nullptr;
+  struct OzStep { int u1_off, u1_n, u2_off, u2_n, u2_upd; };   // U2 list: u2_upd update tiles, then the K^-1 tiles
+  std::vector<OzStep> oz_steps;
+  bool oz_last = false;        // the last evaluation went through the Ozaki path (K^-1 already stored)
   struct DistState* dist = nullptr;   // multi-GPU state (gpx_dist.cu), null on a single GPU
   struct SparseState* sparse = nullptr;   // sparse-GP (VarDTC) state (gpx_sparse.cu)
 };

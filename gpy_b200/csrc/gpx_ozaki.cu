@@ -1,0 +1,449 @@
+// gpx_ozaki.cu — the trailing update and K^-1 = U U^T of the factor-and-invert sweep on the 5th-generation tensor cores.
+//
+// tcgen05.mma has no f64 kind, so fp64-grade products are formed by an Ozaki split on kind::i8 (exact s32 accumulation):
+//   every row of a panel P (rows x K) is scaled by a power of two to (-1, 1) and cut into 8 signed 7-bit digits (int8 planes),
+//   P_r P_c^T = sum_{s+t <= 7} 2^(e_r + e_c - 7 (s+t+2)) D_s(r) D_t(c)^T; the 36 digit-pair products of a 32-deep k-chunk are
+//   36 tcgen05.mma (128 x 64 x 32) accumulated per exponent group g = s + t in its own 64 TMEM columns (8 groups = all 512
+//   columns of the SM), |digit product sum| <= 127^2 * K * 8 < 2^31 for K <= 16384; the epilogue converts the groups to
+//   fp64, sums them smallest first, rescales by the row/column exponents and applies the result to the fp64 target tile.
+// Replaces the same reference work as the DMMA GEMM of gpx_gemm.cu: LAPACK dpotrf / dtrtri / dpotri behind
+// GPy/util/linalg.py:58,142,209-212 (see DESIGN.md §5 for the digit budget against the 1e-8 / 1e-6 tolerances).
+//
+// Kernel anatomy (one CTA per SM, persistent over a tile list): warp 0 = TMA producer (cp.async.bulk.tensor, 4-D tensor map
+// over the pre-tiled digit planes, 4-stage mbarrier ring of 32-deep k-chunks), warp 1 = MMA issuer (one thread, tcgen05.mma
+// from shared-memory descriptors, tcgen05.commit frees the stage / publishes the accumulators), warps 2..9 = epilogue
+// (tcgen05.ld, one TMEM lane quarter x 32 columns each).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "gpx_common.cuh"
+#include "gpx_ozaki.cuh"
+
+namespace gpx {
+
+constexpr int OZ_STAGES = 4;
+constexpr int OZ_A_BYTES = OZ_TM * OZ_KC;                         // 4096: one digit plane of the A tile, one k-chunk
+constexpr int OZ_B_BYTES = OZ_TN * OZ_KC;                         // 2048
+constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_BYTES + OZ_B_BYTES);  // 49152
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_THREADS = (2 + OZ_EPI_WARPS) * 32;               // 320
+constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + 1024 + 256;  // ring + alignment slack + barriers
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX helpers (tcgen05 / TMA tensor copies); mbarrier helpers come from gpx_common.cuh
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// shared-memory matrix descriptor: no swizzle, K-major, core matrices 8 rows x 16 B; LBO = 128 B between the two core matrices
+// along K, SBO = 256 B between 8-row groups (layout pinned by tools/tcgen05_i8_check.cu on the hardware)
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N at bit 17 (units of 8), M at bit 24 (units of 16)
+__host__ __device__ constexpr uint32_t oz_idesc(int M, int N) {
+  return (uint32_t)(2 << 4) | (uint32_t)(1 << 7) | (uint32_t)(1 << 10) | (uint32_t)((N >> 3) << 17) | (uint32_t)((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+               "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. digit split: row exponents + 8 signed 7-bit digit planes of a panel, written in the tiled image of gpx_ozaki.cuh
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SPLIT_ROWS = 64;
+// nkc = k-chunks of the plane LAYOUT (strides), nkc_used <= nkc = k-chunks actually present in this panel (a short last block)
+__global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict__ P, long ld, long rows, int nkc, int nkc_used,
+                                                      int8_t* __restrict__ planes, double* __restrict__ scale) {
+  __shared__ double smax[4][SPLIT_ROWS];
+  __shared__ double sinv[SPLIT_ROWS];
+  const int tid = threadIdx.x, rl = tid & (SPLIT_ROWS - 1), part = tid >> 6;
+  const long row = (long)blockIdx.x * SPLIT_ROWS + rl;
+  const long K = (long)nkc_used * OZ_KC;
+  const double* prow = P + row;
+  double amax = 0.0;
+  for (long k = part; k < K; k += 4) amax = fmax(amax, fabs(prow[k * ld]));
+  smax[part][rl] = amax;
+  __syncthreads();
+  if (part == 0) {
+    amax = fmax(fmax(smax[0][rl], smax[1][rl]), fmax(smax[2][rl], smax[3][rl]));
+    double inv = 0.0, sc = 0.0;
+    if (amax >= 1e-290 && amax <= 1e290) {   // rows of zeros (padding) and non-finite rows get all-zero digits
+      int e = 0;
+      frexp(amax, &e);                        // amax = m 2^e, m in [0.5, 1): |x| 2^-e < 1 for the whole row
+      inv = ldexp(1.0, -e);
+      sc = ldexp(1.0, e - 7);                 // value = 2^e sum_s d_s 2^(-7 (s+1)); the 2^-7 of both operands folded in here
+    }
+    sinv[rl] = inv;
+    scale[row] = sc;
+  }
+  __syncthreads();
+  const double inv = sinv[rl];
+  const long ngrp = rows / 8;
+  for (int u = part; u < nkc_used * 2; u += 4) {   // unit = 16 consecutive k of one row = one 16-byte line of a core matrix
+    const int kc = u >> 1, half = u & 1;
+    uint32_t w[OZ_S][4];
+#pragma unroll
+    for (int s = 0; s < OZ_S; s++) { w[s][0] = 0; w[s][1] = 0; w[s][2] = 0; w[s][3] = 0; }
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      double x = prow[((long)kc * OZ_KC + half * 16 + kk) * ld] * inv;   // exact (power of two), |x| < 1
+#pragma unroll
+      for (int s = 0; s < OZ_S; s++) {
+        x *= 128.0;                              // exact
+        const int d = __double2int_rz(x);        // |d| <= 127
+        x -= (double)d;                          // exact, same sign, |x| < 1
+        w[s][kk >> 2] |= ((uint32_t)d & 0xffu) << (8 * (kk & 3));
+      }
+    }
+    int8_t* base = planes + ((long)kc * ngrp + row / 8) * 256 + half * 128 + (row % 8) * 16;
+#pragma unroll
+    for (int s = 0; s < OZ_S; s++)
+      *reinterpret_cast<uint4*>(base + (long)s * nkc * ngrp * 256) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+  }
+}
+
+int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t st) {
+  if (K % OZ_KC || K / OZ_KC > pl.nkc) { set_error("launch_oz_split: bad panel width"); return -2; }
+  oz_split_kernel<<<(unsigned)(pl.rows / SPLIT_ROWS), 256, 0, st>>>(P, ld, pl.rows, pl.nkc, (int)(K / OZ_KC), pl.planes, pl.scale);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. the GEMM
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzParams p) {
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + OZ_STAGES * OZ_STAGE_BYTES);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < OZ_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, OZ_EPI_WARPS);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {   // the MMA warp owns the TMEM allocation: all 512 columns (8 exponent groups x 64)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = *tmem_slot;
+  const int nkc = p.nkc;
+
+  if (warp == 0) {
+    // ================= TMA producer ==============================================================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x) {
+        const uint32_t t = p.tiles[ti];
+        const int r = t & 0xfff, c64 = (t >> 12) & 0x1fff;
+        const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+        for (int kc = 0; kc < nkc; kc++, it++) {
+          const int st = it % OZ_STAGES;
+          mbar_wait(&empty[st], ((it / OZ_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[st], (uint32_t)nd * (OZ_A_BYTES + OZ_B_BYTES));
+          unsigned char* dst = ring + st * OZ_STAGE_BYTES;
+          for (int s = 0; s < nd; s++) {
+            tma_load_4d(dst + s * OZ_A_BYTES, &mapA, 0, r * (OZ_TM / 8), kc, s, &full[st]);
+            tma_load_4d(dst + OZ_S * OZ_A_BYTES + s * OZ_B_BYTES, &mapB, 0, c64 * (OZ_TN / 8), kc, s, &full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) ======================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = oz_idesc(OZ_TM, OZ_TN);
+      uint32_t it = 0, tl = 0;
+      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, tl++) {
+        const uint32_t t = p.tiles[ti];
+        const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+        mbar_wait(tmem_empty, (tl & 1) ^ 1);     // the epilogue has read the previous tile out of TMEM
+        tc_fence_after();
+        for (int kc = 0; kc < nkc; kc++, it++) {
+          const int st = it % OZ_STAGES;
+          mbar_wait(&full[st], (it / OZ_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(ring + st * OZ_STAGE_BYTES), b0 = a0 + OZ_S * OZ_A_BYTES;
+          for (int g = 0; g < nd; g++) {          // exponent group g = s + t accumulates in TMEM columns [64 g, 64 g + 64)
+            const uint32_t dcol = taddr + (uint32_t)(g * OZ_TN);
+            for (int s = 0; s <= g; s++)
+              umma_i8(dcol, oz_desc(a0 + s * OZ_A_BYTES), oz_desc(b0 + (g - s) * OZ_B_BYTES), idesc, (kc > 0 || s > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);                // the stage may be refilled once these MMAs have read it
+        }
+        umma_commit(tmem_full);                   // accumulators of this tile complete
+      }
+    }
+  } else {
+    // ================= epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ====================
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    uint32_t tl = 0;
+    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, tl++) {
+      const uint32_t t = p.tiles[ti];
+      const int r = t & 0xfff, c64 = (t >> 12) & 0x1fff, kind = (t >> 25) & 3;
+      const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+      mbar_wait(tmem_full, tl & 1);
+      tc_fence_after();
+      double acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc[j] = 0.0;
+      for (int g = nd - 1; g >= 0; g--) {         // smallest magnitude first
+        uint32_t v[32];
+        tmem_ld32(taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * OZ_TN + h * 32), v);
+        const double sc = __longlong_as_double((long long)(1023 - 7 * g) << 52);   // 2^(-7 g)
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] = fma((double)(int32_t)v[j], sc, acc[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);     // TMEM may be overwritten by the next tile's MMAs
+      const long gi = (long)r * OZ_TM + q * 32 + lane;
+      const long gj0 = (long)c64 * OZ_TN + h * 32;
+      const double si = p.scale[gi];
+      if (kind == OZ_UPDATE) {
+        double* C = p.S + gi + gj0 * p.lds;
+#pragma unroll
+        for (int j = 0; j < 32; j++) C[(long)j * p.lds] -= acc[j] * (si * __ldg(p.scale + gj0 + j));
+      } else {
+        double* C = p.Kinv + gi + gj0 * p.ldk;
+        if (kind == OZ_LAUUM_ACC) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) C[(long)j * p.ldk] += acc[j] * (si * __ldg(p.scale + gj0 + j));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) C[(long)j * p.ldk] = acc[j] * (si * __ldg(p.scale + gj0 + j));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int oz_init() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GPX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return -1; }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  GPX_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+  return 0;
+}
+
+static int oz_make_map(CUtensorMap* map, const OzPlanes& pl, int box_rows) {
+  const cuuint64_t ngrp = (cuuint64_t)(pl.rows / 8);
+  cuuint64_t dims[4] = {256, ngrp, (cuuint64_t)pl.nkc, (cuuint64_t)OZ_S};
+  cuuint64_t strides[3] = {256, ngrp * 256, (cuuint64_t)pl.nkc * ngrp * 256};
+  cuuint32_t box[4] = {256, (cuuint32_t)(box_rows / 8), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, pl.planes, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"); return -1; }
+  return 0;
+}
+
+int oz_planes_alloc(OzPlanes& pl, long rows, long K) {
+  if (rows % OZ_TM || K % OZ_KC) { set_error("oz_planes_alloc: rows % 128 or K % 32"); return -2; }
+  pl.rows = rows;
+  pl.nkc = (int)(K / OZ_KC);
+  GPX_CUDA(cudaMalloc(&pl.planes, (size_t)OZ_S * rows * K));
+  GPX_CUDA(cudaMalloc(&pl.scale, (size_t)rows * 8));
+  if (oz_make_map(&pl.mapA, pl, OZ_TM) || oz_make_map(&pl.mapB, pl, OZ_TN)) return -1;
+  return 0;
+}
+
+void oz_planes_free(OzPlanes& pl) {
+  if (pl.planes) cudaFree(pl.planes);
+  if (pl.scale) cudaFree(pl.scale);
+  pl.planes = nullptr; pl.scale = nullptr; pl.rows = 0; pl.nkc = 0;
+}
+
+int launch_oz_gemm(const OzPlanes& pl, const OzParams& p, int max_ctas, cudaStream_t st) {
+  if (p.ntiles <= 0) return 0;
+  const int grid = std::min(p.ntiles, std::max(1, max_ctas));
+  oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(pl.mapA, pl.mapB, p);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. gradient reductions from the stored K^-1 (same sums as the fused LAUUM epilogue of gpx_gemm.cu):
+//    dL_dK = 1/2 (alpha alpha^T - P K^-1)  (exact_gaussian_inference.py:70), tr -> noise (:72, gaussian.py:78-79),
+//    sum K o dL_dK / variance (stationary.py:199), ARD / iso lengthscale sums (:202-213, 225-243). One CTA per lower
+//    128 x 128 tile; the thread-mapped index is the ROW (contiguous in the column-major K^-1), 64 columns per thread.
+// ---------------------------------------------------------------------------------------------------------------
+template <int DREG>
+__global__ void __launch_bounds__(256) grad_kinv_kernel(GradKinvParams p) {
+  extern __shared__ __align__(128) unsigned char gk_smem[];
+  const int D = p.kp.D, P = p.P;
+  double* sXc = reinterpret_cast<double*>(gk_smem);   // [D][128] column points
+  double* sSc = sXc + (size_t)D * TILE;               // [128]
+  double* sAc = sSc + TILE;                           // [P][128]
+  double* sRed = sAc + (size_t)P * TILE;              // [8 warps][nred]
+  // lower tiles only: blockIdx.x enumerates (r, c), c <= r
+  int r = (int)((sqrtf(8.f * (float)blockIdx.x + 1.f) - 1.f) * 0.5f);
+  while (r * (r + 1) / 2 > (int)blockIdx.x) --r;
+  while ((r + 1) * (r + 2) / 2 <= (int)blockIdx.x) ++r;
+  const int c = blockIdx.x - r * (r + 1) / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < D * TILE; idx += 256) sXc[idx] = p.XsT[(long)(idx / TILE) * p.ldx + (long)c * TILE + idx % TILE];
+  for (int idx = tid; idx < P * TILE; idx += 256) sAc[idx] = p.alpha[(long)(idx / TILE) * p.ldx + (long)c * TILE + idx % TILE];
+  if (tid < TILE) sSc[tid] = p.sq[(long)c * TILE + tid];
+  __syncthreads();
+  const int il = tid & (TILE - 1), half = tid >> 7;
+  const long gi = (long)r * TILE + il;
+  const bool ard = p.kp.ard != 0;
+  const int nl = ard ? D : 1, nred = nl + 2;
+  double xi[DREG], gq[DREG], ai[MAX_P];
+#pragma unroll
+  for (int q = 0; q < DREG; q++) { gq[q] = 0.0; xi[q] = q < D ? p.XsT[(long)q * p.ldx + gi] : 0.0; }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) ai[q] = q < P ? p.alpha[(long)q * p.ldx + gi] : 0.0;
+  const double si = p.sq[gi];
+  const double w = (r > c) ? 2.0 : 1.0;               // strictly-lower tiles stand for their mirror image as well
+  const double variance = p.kp.variance, inv_ls = p.kp.inv_ls_iso;
+  const int kind = p.kp.kind;
+  double gvar = 0.0, giso = 0.0, gnoise = 0.0;
+  const double* kcol = p.Kinv + gi + ((long)c * TILE + half * 64) * p.ld;
+  if (gi < p.N) {
+    for (int jj = 0; jj < 64; jj++) {
+      const int jl = half * 64 + jj;
+      const long gj = (long)c * TILE + jl;
+      if (gj >= p.N) break;
+      const double kinv = kcol[(long)jj * p.ld];
+      double dot = 0.0;
+#pragma unroll
+      for (int q = 0; q < DREG; q++)
+        if (q < D) dot = fma(xi[q], sXc[q * TILE + jl], dot);
+      double r2 = si + sSc[jl] - 2.0 * dot;
+      if (gi == gj) r2 = 0.0;
+      r2 = fmax(r2, 0.0);
+      const double rr = sqrt(r2) * inv_ls;
+      double k, dk;
+      k_dk_of_r_unit(kind, rr, k, dk);
+      double aa = 0.0;
+#pragma unroll
+      for (int q = 0; q < MAX_P; q++)
+        if (q < P) aa = fma(ai[q], sAc[q * TILE + jl], aa);
+      const double dl = 0.5 * (aa - (double)P * kinv);
+      gvar = fma(w * k, dl, gvar);
+      if (gi == gj) {
+        gnoise += dl;
+        if (p.dnoise_out) p.dnoise_out[gi] = dl;
+      }
+      const double G = variance * dk * dl;
+      if (ard) {
+        const double tmpv = (rr != 0.0) ? w * G / rr : 0.0;     // stationary.py:205,225-232: 1/r with 1/0 := 0
+#pragma unroll
+        for (int q = 0; q < DREG; q++)
+          if (q < D) {
+            const double df = xi[q] - sXc[q * TILE + jl];
+            gq[q] = fma(tmpv, df * df, gq[q]);
+          }
+      } else {
+        giso = fma(w * G, rr, giso);
+      }
+    }
+  }
+  gvar = warp_sum(gvar);
+  gnoise = warp_sum(gnoise);
+  if (lane == 0) { sRed[warp * nred] = gvar; sRed[warp * nred + nred - 1] = gnoise; }
+  if (ard) {
+#pragma unroll
+    for (int q = 0; q < DREG; q++)
+      if (q < D) {
+        const double s = warp_sum(gq[q]);
+        if (lane == 0) sRed[warp * nred + 1 + q] = s;
+      }
+  } else {
+    giso = warp_sum(giso);
+    if (lane == 0) sRed[warp * nred + 1] = giso;
+  }
+  __syncthreads();
+  if (tid < nred) {
+    double s = 0.0;
+#pragma unroll
+    for (int wdx = 0; wdx < 8; wdx++) s += sRed[wdx * nred + tid];
+    p.partials[((long)r * p.nt + c) * nred + tid] = s;
+  }
+}
+
+template <int DREG>
+static int launch_grad_kinv_t(const GradKinvParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPX_CUDA(cudaFuncSetAttribute(grad_kinv_kernel<DREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((MAX_D + 1 + MAX_P) * TILE * 8 + 8 * (MAX_D + 2) * 8)));
+    attr_set = true;
+  }
+  grad_kinv_kernel<DREG><<<grid, 256, smem, st>>>(p);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_grad_kinv(const GradKinvParams& p, cudaStream_t st) {
+  const int D = p.kp.D;
+  const size_t smem = (size_t)(D + 1 + p.P) * TILE * 8 + 8 * (MAX_D + 2) * 8;
+  const unsigned grid = (unsigned)(p.nt * (p.nt + 1) / 2);
+  if (D <= 8) return launch_grad_kinv_t<8>(p, grid, smem, st);
+  if (D <= 16) return launch_grad_kinv_t<16>(p, grid, smem, st);
+  if (D <= 32) return launch_grad_kinv_t<32>(p, grid, smem, st);
+  return launch_grad_kinv_t<64>(p, grid, smem, st);
+}
+
+}  // namespace gpx

@@ -1,0 +1,64 @@
+// gpx_ozaki.cuh — fp64-grade GEMM on the INT8 tensor path (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed): internal API.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+#include "gpx_common.cuh"
+
+struct gpx_ctx;
+
+namespace gpx {
+
+constexpr int OZ_S = 8;         // signed 7-bit digit planes per fp64 operand (56 bits >= the 53-bit significand)
+constexpr int OZ_TM = 128;      // output tile rows   (= MMA M, one TMEM lane per row)
+constexpr int OZ_TN = 64;       // output tile columns (= MMA N; 8 exponent groups x 64 columns = all 512 TMEM columns)
+constexpr int OZ_KC = 32;       // k-depth of one tcgen05.mma kind::i8 (32 bytes of K)
+
+// Digit planes of one panel (rows x K, K = nkc * 32), stored so that every (plane, k-chunk, 8-row group) is one 256-byte
+// block in exactly the shared-memory image tcgen05 reads (no-swizzle K-major core matrices: two 8 x 16 B core matrices per
+// block). A tile of R rows of one (plane, k-chunk) is therefore R*32 contiguous bytes = one TMA box {256, R/8, 1, 1}.
+//   byte offset of digit s of element (row i, column k):
+//     (((s * nkc + k/32) * (rows/8) + i/8) * 256) + ((k%32)/16)*128 + (i%8)*16 + k%16
+struct OzPlanes {
+  int8_t* planes = nullptr;     // [S][nkc][rows/8][256]
+  double* scale = nullptr;      // [rows]: 2^(e_i - 7), e_i = exponent of the row maximum over the K columns of the panel
+  long rows = 0;
+  int nkc = 0;
+  CUtensorMap mapA, mapB;       // the same tensor with a 128-row and a 64-row box
+};
+
+// one output tile: bits 0-11 row tile (128 rows), 12-24 column tile (64 columns), 25-26 kind, 27 inverse-part tile
+enum OzKind { OZ_UPDATE = 0, OZ_LAUUM_ACC = 1, OZ_LAUUM_SET = 2 };
+inline uint32_t oz_tile(int r, int c64, int kind, int upper) {
+  return (uint32_t)r | ((uint32_t)c64 << 12) | ((uint32_t)kind << 25) | ((uint32_t)upper << 27);
+}
+
+struct OzParams {
+  const uint32_t* tiles;   // device tile list of this launch
+  int ntiles;
+  int nkc;                 // K / 32
+  const double* scale;     // row scales of the panel (shared by both operands: C (op)= P_r P_c^T)
+  double* S; long lds;     // OZ_UPDATE target:      S(r, c)    -= P_r P_c^T
+  double* Kinv; long ldk;  // OZ_LAUUM_* target:     Kinv(r, c) (+)= P_r P_c^T   (lower tiles)
+  int dig_lo, dig_up;      // digits per operand for Cholesky-part tiles / inverse-part tiles (<= OZ_S)
+};
+
+int oz_init();                                                          // driver entry point + kernel attributes
+int oz_planes_alloc(OzPlanes& pl, long rows, long K);                    // buffers + tensor maps
+void oz_planes_free(OzPlanes& pl);
+int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t st);   // P: rows x K column-major, K <= layout
+int launch_oz_gemm(const OzPlanes& pl, const OzParams& p, int max_ctas, cudaStream_t st);
+
+// gradient reductions from a stored K^-1 (lower 128 x 128 tiles, column-major, leading dimension ld): same partial sums as
+// the fused epilogue of gemm_lauum_kernel, consumed by finalize_kernel
+struct GradKinvParams {
+  const double* Kinv; long ld;
+  const double* XsT; const double* sq; const double* alpha; long ldx;
+  long N; int P; int nt;
+  double* partials;        // [nt*nt][nl+2], zeroed by the caller
+  double* dnoise_out;      // optional diag(dL_dK)
+  KernParams kp;
+};
+int launch_grad_kinv(const GradKinvParams& p, cudaStream_t st);
+
+}  // namespace gpx

@@ -21,6 +21,60 @@ class Parameterized(Parameterizable, metaclass=ParametersChangedMeta):
         super(Parameterized, self).__init__(name=name)
         self.parameters = []
         self._in_init_ = True
+        self._update_on_ = True
+
+    # ---- observer contract (eager): parameter writes below this node end in the ROOT's parameters_changed() ----------
+    def _trigger_params_changed(self):
+        if getattr(self, "_in_init_", False) or not getattr(self, "_update_on_", True):
+            return
+        self.parameters_changed()
+
+    def update_model(self, updates=None):
+        """paramz Parameterizable.update_model: False defers re-evaluation while several things are written"""
+        if updates is None:
+            return self._update_on_
+        was = self._update_on_
+        self._update_on_ = bool(updates)
+        if updates and not was:
+            self._trigger_params_changed()
+
+    @property
+    def is_fixed(self):
+        ps = self.flattened_parameters()
+        return bool(ps) and all(p.is_fixed for p in ps)
+
+    def fix(self, *a, **kw):
+        for p in self.flattened_parameters():
+            p._fixed_ = True
+
+    def unfix(self):
+        for p in self.flattened_parameters():
+            p._fixed_ = False
+
+    @property
+    def optimizer_array(self):
+        """free parameters in the optimizer's (transformed) space, link order"""
+        out = []
+        for p in self.flattened_parameters():
+            if p.is_fixed:
+                continue
+            v = np.asarray(p, dtype=np.float64).reshape(-1)
+            c = p.default_constraint
+            out.append(v if c is None else c.finv(v))
+        return np.concatenate(out) if out else np.zeros(0)
+
+    @optimizer_array.setter
+    def optimizer_array(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        i = 0
+        for p in self.flattened_parameters():
+            if p.is_fixed:
+                continue
+            v = x[i:i + p.size]
+            i += p.size
+            c = p.default_constraint
+            np.ndarray.__setitem__(p, Ellipsis, (v if c is None else c.f(v)).reshape(p.shape))   # silent write ...
+        self._trigger_params_changed()                                                            # ... ONE evaluation
 
     def link_parameter(self, p, index=None):
         self.parameters.append(p) if index is None else self.parameters.insert(index, p)

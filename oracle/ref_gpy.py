@@ -95,6 +95,50 @@ def load():
     return ns
 
 
+_models = None
+
+
+def load_models():
+    """-> namespace with the reference's own GP, GPRegression and Model classes: GPy/core/model.py, GPy/core/gp.py and
+    GPy/models/gp_regression.py executed verbatim on top of `load()`. GPy/core/__init__.py and
+    GPy/models/__init__.py are NOT executed (they import every model family); the names gp.py takes from sibling packages
+    (`kern.Kern`, `kern.RBF`, `likelihoods.Gaussian/Likelihood/MixedNoise`) are set on the stub packages from the
+    reference's own modules. Not the reference's code: `expectation_propagation.EP` is replaced by a class that raises
+    (gp.py:100 only reaches it for non-Gaussian likelihoods, outside this path)."""
+    global _models
+    if _models is not None:
+        return _models
+    G = load()
+    kern_pkg, lik_pkg = sys.modules["GPy.kern"], sys.modules["GPy.likelihoods"]
+    kmod = importlib.import_module("GPy.kern.src.kern")
+    kern_pkg.Kern = kmod.Kern
+    for n in ("RBF", "Exponential", "Matern32", "Matern52"):
+        setattr(kern_pkg, n, getattr(G, n))
+    lmod = importlib.import_module("GPy.likelihoods.likelihood")
+    lik_pkg.Likelihood = lmod.Likelihood
+    lik_pkg.Gaussian, lik_pkg.HeteroscedasticGaussian = G.Gaussian, G.HeteroscedasticGaussian
+    lik_pkg.MixedNoise = importlib.import_module("GPy.likelihoods.mixed_noise").MixedNoise
+    ep = types.ModuleType("GPy.inference.latent_function_inference.expectation_propagation")
+
+    class EP(object):
+        def __init__(self, *a, **kw):
+            raise NotImplementedError("expectation propagation is outside the exact-GP path (test stand-in)")
+
+    ep.EP = EP
+    sys.modules[ep.__name__] = ep
+    sys.modules["GPy.inference.latent_function_inference"].expectation_propagation = ep
+    sys.modules["GPy.inference.latent_function_inference"].exact_gaussian_inference = sys.modules[
+        "GPy.inference.latent_function_inference.exact_gaussian_inference"]
+    model = importlib.import_module("GPy.core.model")
+    sys.modules["GPy.core"].Model = model.Model
+    gp = importlib.import_module("GPy.core.gp")
+    sys.modules["GPy.core"].GP = gp.GP
+    _stub("GPy.models", "GPy/models")
+    reg = importlib.import_module("GPy.models.gp_regression")
+    _models = types.SimpleNamespace(GP=gp.GP, GPRegression=reg.GPRegression, Model=model.Model, G=G)
+    return _models
+
+
 KERNELS = {"rbf": "RBF", "exponential": "Exponential", "matern32": "Matern32", "matern52": "Matern52"}
 
 

@@ -26,8 +26,15 @@ class FakeEngine(object):
 
     def exact_eval(self, kind, ARD, variance, lengthscale, noise, jitter=1e-8, max_tries=5):
         self.calls.append("exact_eval")
+        self.eval_serial = getattr(self, "eval_serial", 0) + 1
+        self.theta = (kind, ARD, variance, np.array(lengthscale, copy=True))
         lml, g, self.res = o.eval_lml_grad(self.X, self.Y, kind, ARD, variance, lengthscale, noise)
         return lml, g, 0.0
+
+    def predict(self, Xnew, full_cov=False):
+        kind, ARD, var, ls = self.theta
+        k = o.StationaryOracle(kind, self.X.shape[1], var, ls if ARD else float(np.atleast_1d(ls)[0]), ARD)
+        return o.raw_predict(k, self.X, self.res["L"], self.res["alpha"], Xnew, full_cov)
 
     def exact_eval_het(self, kind, ARD, variance, lengthscale, noise_variances, jitter=1e-8, max_tries=5):
         self.calls.append("exact_eval_het")
