@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgpx.so")
 
-KIND = {"rbf": 0, "exponential": 1, "matern32": 2, "matern52": 3}
+KIND = {"rbf": 0, "exponential": 1, "matern32": 2, "matern52": 3, "white": 4, "bias": 5}
 GET = {"L": 0, "alpha": 1, "Kinv": 2, "dL_dK": 3, "K": 4, "Linv": 5}
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -25,6 +25,12 @@ class GpxStats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class GpxKernPart(ctypes.Structure):
+    """gpx_kern_part of include/gpx.h: one factor of a composite kernel."""
+    _fields_ = [("kind", ctypes.c_int), ("ard", ctypes.c_int), ("term", ctypes.c_int), ("ndims", ctypes.c_int),
+                ("dims", ctypes.POINTER(ctypes.c_int)), ("variance", ctypes.c_double), ("lengthscale", _dp)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "gpx_last_error": (ctypes.c_char_p, []),
@@ -37,6 +43,8 @@ EXPORTS = {
                                       ctypes.c_double, ctypes.c_int, _dp, _dp, _dp]),
     "gpx_exact_eval_het": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_double,
                                           ctypes.c_int, _dp, _dp, _dp, _dp]),
+    "gpx_exact_eval_multi": (ctypes.c_int, [_vp, ctypes.POINTER(GpxKernPart), ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                            ctypes.c_int, _dp, _dp, _dp]),
     "gpx_get": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
     "gpx_predict": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp]),
     "gpx_kern_K": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64, _dp,
@@ -179,6 +187,30 @@ class Engine(object):
         self.eval_serial += 1
         check(rc, "gpx_exact_eval_het")
         return lml.value, grad, dnoise, jit.value
+
+    def exact_eval_multi(self, parts, noise, jitter=1e-8, max_tries=5):
+        """composite kernel: parts = [(kind, ARD, term, dims, variance, lengthscale)], ordered by term ->
+        (log_marginal, gradient [per part: variance, lengthscale.. (none for white / bias); then noise], extra_jitter)"""
+        arr = (GpxKernPart * len(parts))()
+        keep, ngrad = [], 1
+        for i, (kind, ard, term, dims, variance, lengthscale) in enumerate(parts):
+            static = kind in ("white", "bias")
+            d = np.ascontiguousarray([] if static else dims, dtype=np.int32)
+            ls = np.ascontiguousarray([1.0] if static else np.atleast_1d(lengthscale), dtype=np.float64).reshape(-1)
+            if not static and ls.size != (d.size if ard else 1):
+                raise ValueError("part %d: lengthscale does not match its active dims" % i)
+            keep += [d, ls]
+            arr[i].kind, arr[i].ard, arr[i].term, arr[i].ndims = KIND[kind], int(bool(ard)), int(term), int(d.size)
+            arr[i].dims = d.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+            arr[i].variance, arr[i].lengthscale = float(variance), _ptr(ls)
+            ngrad += 1 + (0 if static else ls.size)
+        lml, jit = ctypes.c_double(), ctypes.c_double()
+        grad = np.zeros(ngrad)
+        rc = self._L.gpx_exact_eval_multi(self._h, arr, len(parts), float(noise), float(jitter), int(max_tries),
+                                          ctypes.byref(lml), _ptr(grad), ctypes.byref(jit))
+        self.eval_serial += 1
+        check(rc, "gpx_exact_eval_multi")
+        return lml.value, grad, jit.value
 
     def get(self, which):
         if which == "alpha":

@@ -46,6 +46,8 @@ static void free_data(gpx_ctx* c) {
   c->staging_cap = 0;
   c->have_eval = false;
   c->have_kinv = false;
+  for (double** mp : {&c->mXsT, &c->msq, &c->mpartials}) { if (*mp) cudaFree(*mp); *mp = nullptr; }
+  c->m_cap = 0;
   oz_planes_free(c->ozp[0]);
   oz_planes_free(c->ozp[1]);
   if (c->oz_tiles) cudaFree(c->oz_tiles);
@@ -101,9 +103,9 @@ int gpx_create(int device, gpx_ctx** out) {
   GPX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   GPX_CUDA(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio_lo));
   GPX_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_hi));
-  GPX_CUDA(cudaMalloc(&c->res, (MAX_D + 8) * sizeof(double)));
+  GPX_CUDA(cudaMalloc(&c->res, (MAX_D + 2 * MAX_PARTS + 8) * sizeof(double)));
   GPX_CUDA(cudaMalloc(&c->info, sizeof(int)));
-  GPX_CUDA(cudaMallocHost(&c->h_res, (MAX_D + 8) * sizeof(double)));
+  GPX_CUDA(cudaMallocHost(&c->h_res, (MAX_D + 2 * MAX_PARTS + 8) * sizeof(double)));
   GPX_CUDA(cudaMallocHost(&c->h_info, sizeof(int)));
   GPX_CHECK(gemm_init());
   GPX_CHECK(oz_init());
@@ -472,7 +474,8 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
   return 0;
 }
 
-static int run_lauum(gpx_ctx* c, double* kinv_out, Recorder* rec) {
+// plain: store K^-1 (lower tiles) only, no gradient reductions (composite kernels reduce from the stored matrix)
+static int run_lauum(gpx_ctx* c, double* kinv_out, Recorder* rec, bool plain = false) {
   const long ld = c->Npad;
   const int nt = (int)(c->Npad / TILE);
   const int nl = c->kp.ard ? c->D : 1;
@@ -485,10 +488,11 @@ static int run_lauum(gpx_ctx* c, double* kinv_out, Recorder* rec) {
   pl.K = (int)c->Npad; pl.nt = nt;
   pl.XsT = c->dXsT; pl.sq = c->dsq; pl.alpha = c->dAlpha; pl.ldx = c->Npad;
   pl.N = (int)c->N; pl.P = c->P;
-  pl.partials = c->partials;
+  pl.partials = plain ? nullptr : c->partials;
   pl.kinv_out = kinv_out;
-  pl.dnoise_out = (c->het && rec) ? c->dDnoise : nullptr;
+  pl.dnoise_out = (c->het && rec && !plain) ? c->dDnoise : nullptr;
   pl.kp = c->kp;
+  if (plain) { pl.kp.D = 1; pl.P = 1; }
   double flops = 0;
   for (int r = 0; r < nt; r++) flops += (double)(r + 1) * 2.0 * TILE * TILE * (double)(c->Npad - (long)r * TILE);
   int h = rec ? rec->begin(PH_LAUUM, flops) : -1;
@@ -504,6 +508,28 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
   const int nt = (int)(c->Npad / TILE);
   const int nl = c->kp.ard ? c->D : 1;
   GPX_CUDA(cudaMemsetAsync(c->info, 0, sizeof(int), st));
+  if (c->multi) {
+    if (c->m_cap != c->Npad) {
+      for (double** mp : {&c->mXsT, &c->msq, &c->mpartials}) { if (*mp) cudaFree(*mp); *mp = nullptr; }
+      GPX_CUDA(cudaMalloc(&c->mXsT, (size_t)MAX_D * c->Npad * 8));
+      GPX_CUDA(cudaMalloc(&c->msq, (size_t)MAX_PARTS * c->Npad * 8));
+      GPX_CUDA(cudaMalloc(&c->mpartials, (size_t)MAX_PARTS * nt * nt * (MAX_D + 2) * 8));
+      c->m_cap = c->Npad;
+    }
+    GPX_CHECK(launch_prep_multi(c->dX, c->N, c->D, c->Npad, c->mk, c->mXsT, c->msq, st));
+    c->eval_launches++;
+    KBuildMultiParams kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.rowsT = c->mXsT; kb.ld_rows = c->Npad; kb.sq_rows = c->msq;
+    kb.colsT = c->mXsT; kb.ld_cols = c->Npad; kb.sq_cols = c->msq;
+    kb.out = c->S; kb.ld = ld; kb.nrows = c->N; kb.ncols = c->N; kb.sym = 1; kb.same = 1;
+    kb.diag_add = (c->noise + c->jitter) + extra_jitter;
+    kb.mk = c->mk;
+    const int h = rec.begin(PH_KBUILD);
+    GPX_CHECK(launch_kbuild_multi(kb, nt, nt, st));
+    rec.end(h);
+    c->eval_launches++;
+  } else {
   GPX_CHECK(launch_prep_x(c->dX, c->N, c->Npad, c->kp, c->dXsT, c->dsq, st));
   c->eval_launches++;
   {
@@ -523,6 +549,7 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     rec.end(h);
     c->eval_launches++;
   }
+  }
   const bool oz = oz_wanted(c);
   if (oz) GPX_CHECK(oz_prepare(c));
   c->oz_last = oz;
@@ -537,6 +564,37 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     GPX_CHECK(launch_uv(c->S, ld, c->Npad, c->P, c->dT, KSPLIT, c->dUvPart, c->dAlpha, st));
     rec.end(h);
     c->eval_launches += 3;
+  }
+  if (c->multi) {
+    // composite kernel: K^-1 stored (by the sweep on the tcgen05 path, else by a plain LAUUM), then one reduction pass per part
+    if (!oz) {
+      if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)ld * ld * 8));
+      GPX_CHECK(run_lauum(c, c->Kinv, &rec, true));
+    }
+    FinalizeMultiParams fm;
+    memset(&fm, 0, sizeof(fm));
+    const int h = rec.begin(PH_LAUUM, 0.0);
+    for (int q = 0; q < c->mk.nparts; q++) {
+      double* part = c->mpartials + (size_t)q * nt * nt * (MAX_D + 2);
+      const int nred = std::max(1, part_nl(c->mk.part[q])) + 2;
+      GPX_CUDA(cudaMemsetAsync(part, 0, (size_t)nt * nt * nred * 8, st));
+      GradKinvMultiParams gm;
+      memset(&gm, 0, sizeof(gm));
+      gm.Kinv = c->Kinv; gm.ld = ld; gm.XsT = c->mXsT; gm.sq = c->msq; gm.ldx = c->Npad; gm.alpha = c->dAlpha;
+      gm.N = c->N; gm.P = c->P; gm.nt = nt; gm.part = q; gm.want_noise = q == 0; gm.partials = part; gm.mk = c->mk;
+      GPX_CHECK(launch_grad_kinv_multi(gm, st));
+      c->eval_launches++;
+      fm.partials[q] = part;
+    }
+    rec.end(h);
+    fm.ntiles = (long)nt * nt; fm.logdet_part = c->logdet_part; fm.nt = nt;
+    fm.T = c->dT; fm.ld = ld; fm.N = c->N; fm.P = c->P; fm.mk = c->mk; fm.res = c->res;
+    GPX_CHECK(launch_finalize_multi(fm, st));
+    c->eval_launches++;
+    GPX_CUDA(cudaMemcpyAsync(c->h_res, c->res, (MAX_D + 2 * MAX_PARTS + 8) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaMemcpyAsync(c->h_info, c->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    c->oz_last = true;   // K^-1 is stored either way
+    return 0;
   }
   if (oz) {
     // K^-1 was accumulated panel by panel inside the sweep (tcgen05): reduce dL_dK -> gradients from the stored tiles
@@ -577,13 +635,55 @@ extern "C" {
 }  // extern "C"
 
 // noise_vec == nullptr: homoscedastic (`noise`); else N per-point variances (`noise` = their mean, used by the ladder)
+static int fill_multi(gpx_ctx* c, const gpx_kern_part* parts, int nparts, double* kdiag_total) {
+  if (!parts || nparts < 1 || nparts > MAX_PARTS) GPX_FAIL("number of kernel parts must be in [1, 8]");
+  MultiKern& mk = c->mk;
+  memset(&mk, 0, sizeof(mk));
+  mk.nparts = nparts;
+  int off = 0;
+  double total = 0.0, prod = 1.0;
+  for (int p = 0; p < nparts; p++) {
+    const gpx_kern_part& in = parts[p];
+    PartDev& pd = mk.part[p];
+    if (in.kind < 0 || in.kind > GPX_BIAS) GPX_FAIL("unknown kernel kind");
+    if (!(in.variance > 0)) GPX_FAIL("variance must be positive");
+    if (p > 0 && in.term < parts[p - 1].term) GPX_FAIL("kernel parts must be ordered by term");
+    const bool stat = in.kind >= GPX_WHITE;
+    if (!stat && (in.ndims < 1 || !in.dims || !in.lengthscale)) GPX_FAIL("a stationary part needs active dims and a lengthscale");
+    pd.kind = in.kind; pd.ard = (!stat && in.ard) ? 1 : 0; pd.term = in.term; pd.D = stat ? 0 : in.ndims; pd.xoff = off;
+    pd.variance = in.variance; pd.inv_ls_iso = 1.0;
+    if (off + pd.D > MAX_D) GPX_FAIL("the parts' active dims add up to more than 64");
+    for (int q = 0; q < pd.D; q++) {
+      if (in.dims[q] < 0 || in.dims[q] >= c->D) GPX_FAIL("active dim outside the data");
+      const double l = in.lengthscale[pd.ard ? q : 0];
+      if (!(l > 0)) GPX_FAIL("lengthscale must be positive");
+      mk.dims[off + q] = in.dims[q];
+      mk.ls[off + q] = l;
+    }
+    if (!stat && !pd.ard) pd.inv_ls_iso = 1.0 / in.lengthscale[0];
+    off += pd.D;
+    if (p > 0 && in.term != parts[p - 1].term) { total += prod; prod = 1.0; }
+    prod *= in.variance;                      // every kind has Kdiag = variance (stationary.py:170-173, static.py:30-33)
+  }
+  total += prod;
+  mk.sumD = off;
+  *kdiag_total = total;
+  return 0;
+}
+
 static int exact_eval_impl(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, double noise,
                            const double* noise_vec, double jitter, int max_tries, double* lml, double* grad,
-                           double* dnoise, double* jitter_used) {
-  if (!c || !lengthscale || !lml || !grad) GPX_FAIL("null argument");
+                           double* dnoise, double* jitter_used, const gpx_kern_part* parts = nullptr, int nparts = 0) {
+  if (!c || !lml || !grad || (!parts && !lengthscale)) GPX_FAIL("null argument");
   if (!c->S) GPX_FAIL("gpx_set_data has not been called");
   if (!(noise >= 0)) GPX_FAIL("noise variance must be non-negative");
   GPX_CUDA(cudaSetDevice(c->device));
+  c->multi = parts != nullptr;
+  if (c->multi) {
+    if (c->dist) GPX_FAIL("composite kernels are single-GPU");
+    GPX_CHECK(fill_multi(c, parts, nparts, &variance));     // `variance` = Kdiag of the composite kernel (jitter ladder)
+    c->kp.variance = variance;
+  } else
   GPX_CHECK(fill_kp(c->kp, kind, ard, c->D, variance, lengthscale));
   c->het = noise_vec != nullptr;
   if (c->het) {
@@ -655,6 +755,12 @@ static int exact_eval_impl(gpx_ctx* c, int kind, int ard, double variance, const
     return info;
   }
   *lml = c->h_res[0];
+  if (c->multi) {
+    int n = 0;
+    for (int p = 0; p < c->mk.nparts; p++) n += 1 + part_nl(c->mk.part[p]);
+    for (int q = 0; q < n; q++) grad[q] = c->h_res[4 + q];
+    grad[n] = c->h_res[3];
+  } else
   for (int q = 0; q < nl + 2; q++) grad[q] = c->h_res[1 + q];
   if (c->het) {
     GPX_CUDA(cudaMemcpyAsync(dnoise, c->dDnoise, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->st));
@@ -671,6 +777,13 @@ int gpx_exact_eval(gpx_ctx* c, int kind, int ard, double variance, const double*
                    double jitter, int max_tries, double* lml, double* grad, double* jitter_used) {
   return exact_eval_impl(c, kind, ard, variance, lengthscale, noise, nullptr, jitter, max_tries, lml, grad, nullptr,
                          jitter_used);
+}
+
+int gpx_exact_eval_multi(gpx_ctx* c, const gpx_kern_part* parts, int nparts, double noise, double jitter, int max_tries,
+                         double* lml, double* grad, double* jitter_used) {
+  if (!parts) GPX_FAIL("null argument");
+  return exact_eval_impl(c, 0, 0, 1.0, nullptr, noise, nullptr, jitter, max_tries, lml, grad, nullptr, jitter_used, parts,
+                         nparts);
 }
 
 int gpx_exact_eval_het(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale,
@@ -722,7 +835,14 @@ int gpx_get(gpx_ctx* c, int which, double* out) {
     return 0;
   }
   GPX_CHECK(ensure_staging(c));
-  if (which == GPX_GET_K) {
+  if (which == GPX_GET_K && c->multi) {
+    KBuildMultiParams kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.rowsT = c->mXsT; kb.ld_rows = ld; kb.sq_rows = c->msq; kb.colsT = c->mXsT; kb.ld_cols = ld; kb.sq_cols = c->msq;
+    kb.out = c->staging; kb.ld = N; kb.nrows = N; kb.ncols = N; kb.sym = 0; kb.same = 1; kb.mk = c->mk;
+    GPX_CHECK(launch_kbuild_multi(kb, (int)(ld / TILE), (int)(ld / TILE), st));
+    c->total_launches++;
+  } else if (which == GPX_GET_K) {
     KBuildParams kb;
     memset(&kb, 0, sizeof(kb));
     kb.rowsT = c->dXsT; kb.ld_rows = ld; kb.colsT = c->dXsT; kb.ld_cols = ld;
@@ -1037,6 +1157,15 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   cudaStream_t st = c->st;
   const long ld = c->Npad, N = c->N;
   PointSet pn;
+  if (c->multi) {   // composite kernel: stacked per-part scaled coordinates of the new points
+    pn.n = M; pn.ld = (M + TILE - 1) / TILE * TILE;
+    GPX_CUDA(cudaMalloc(&pn.raw, (size_t)M * c->D * 8));
+    GPX_CUDA(cudaMalloc(&pn.xT, (size_t)pn.ld * std::max(1, c->mk.sumD) * 8));
+    GPX_CUDA(cudaMalloc(&pn.sq, (size_t)pn.ld * c->mk.nparts * 8));
+    GPX_CUDA(cudaMemcpyAsync(pn.raw, Xnew, (size_t)M * c->D * 8, cudaMemcpyHostToDevice, st));
+    GPX_CHECK(launch_prep_multi(pn.raw, M, c->D, pn.ld, c->mk, pn.xT, pn.sq, st));
+    c->total_launches++;
+  } else
   GPX_CHECK(upload_points(c, Xnew, M, c->kp, pn));
   // Kx as [M][ld] (each new point one zero-padded column of length ld): thread-mapped operand = training points
   double* Kx = nullptr; double* Tx = nullptr;
@@ -1049,7 +1178,15 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   kb.rowsT = c->dXsT; kb.ld_rows = ld; kb.sq_rows = c->dsq;
   kb.colsT = pn.xT; kb.ld_cols = pn.ld; kb.sq_cols = pn.sq;
   kb.out = Kx; kb.ld = ld; kb.nrows = N; kb.ncols = M; kb.sym = 0; kb.same = 0; kb.kp = c->kp;
-  int rc = launch_kbuild(kb, (int)(ld / TILE), (int)(pn.ld / TILE), st);
+  int rc;
+  if (c->multi) {
+    KBuildMultiParams km;
+    memset(&km, 0, sizeof(km));
+    km.rowsT = c->mXsT; km.ld_rows = ld; km.sq_rows = c->msq; km.colsT = pn.xT; km.ld_cols = pn.ld; km.sq_cols = pn.sq;
+    km.out = Kx; km.ld = ld; km.nrows = N; km.ncols = M; km.sym = 0; km.same = 0; km.mk = c->mk;
+    rc = launch_kbuild_multi(km, (int)(ld / TILE), (int)(pn.ld / TILE), st);
+  } else
+  rc = launch_kbuild(kb, (int)(ld / TILE), (int)(pn.ld / TILE), st);
   c->total_launches++;
   // tmp = L^-1 Kx = U^T Kx, MAX_P columns per pass
   for (long m0 = 0; rc == 0 && m0 < M; m0 += MAX_P) {
@@ -1116,6 +1253,26 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   std::vector<double> kxx((size_t)M * M);
   double lsv[MAX_D];
   for (int q = 0; q < MAX_D; q++) lsv[q] = c->kp.ls[q];
+  if (c->multi) {   // K(Xnew, Xnew) of the composite kernel, built on the device
+    PointSet pm;
+    pm.n = M; pm.ld = (M + TILE - 1) / TILE * TILE;
+    double* dk = nullptr;
+    GPX_CUDA(cudaMalloc(&pm.raw, (size_t)M * c->D * 8));
+    GPX_CUDA(cudaMalloc(&pm.xT, (size_t)pm.ld * std::max(1, c->mk.sumD) * 8));
+    GPX_CUDA(cudaMalloc(&pm.sq, (size_t)pm.ld * c->mk.nparts * 8));
+    GPX_CUDA(cudaMalloc(&dk, (size_t)M * M * 8));
+    GPX_CUDA(cudaMemcpyAsync(pm.raw, Xnew, (size_t)M * c->D * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_prep_multi(pm.raw, M, c->D, pm.ld, c->mk, pm.xT, pm.sq, st);
+    KBuildMultiParams km;
+    memset(&km, 0, sizeof(km));
+    km.rowsT = pm.xT; km.ld_rows = pm.ld; km.sq_rows = pm.sq; km.colsT = pm.xT; km.ld_cols = pm.ld; km.sq_cols = pm.sq;
+    km.out = dk; km.ld = M; km.nrows = M; km.ncols = M; km.sym = 0; km.same = 1; km.mk = c->mk;
+    if (rc == 0) rc = launch_kbuild_multi(km, (int)(pm.ld / TILE), (int)(pm.ld / TILE), st);
+    c->total_launches += 2;
+    if (rc == 0 && cudaMemcpyAsync(kxx.data(), dk, (size_t)M * M * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
+    cudaFree(dk);
+  } else
   rc = gpx_kern_K(c, c->kp.kind, c->kp.ard, c->kp.variance, lsv, Xnew, M, nullptr, M, c->D, kxx.data());
   if (rc) return rc;
   for (long a = 0; a < M; a++)

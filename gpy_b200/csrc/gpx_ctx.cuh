@@ -4,6 +4,7 @@
 
 #include "gpx_common.cuh"
 #include "gpx_ozaki.cuh"
+#include "gpx_multi.cuh"
 
 struct DistState;
 struct SparseState;
@@ -65,6 +66,13 @@ struct gpx_ctx {
   struct OzStep { int u1_off, u1_n, u2_off, u2_n, u2_upd; };   // U2 list: u2_upd update tiles, then the K^-1 tiles
   std::vector<OzStep> oz_steps;
   bool oz_last = false;        // the last evaluation went through the Ozaki path (K^-1 already stored)
+  // ---- composite kernels (gpx_multi.cu): the last evaluation used gpx_exact_eval_multi --------------------------------
+  bool multi = false;
+  gpx::MultiKern mk{};
+  double* mXsT = nullptr;      // [sumD][Npad] stacked scaled inputs of the parts
+  double* msq = nullptr;       // [nparts][Npad]
+  double* mpartials = nullptr; // [MAX_PARTS][nt*nt][MAX_D+2]
+  long m_cap = 0;              // Npad the three buffers were sized for
   struct DistState* dist = nullptr;   // multi-GPU state (gpx_dist.cu), null on a single GPU
   struct SparseState* sparse = nullptr;   // sparse-GP (VarDTC) state (gpx_sparse.cu)
 };

@@ -10,7 +10,7 @@ Mirrors (same names, argument meaning, return structure and error behaviour):
 import numpy as np
 
 from . import _ffi
-from .kern import DeviceGradient, Stationary
+from .kern import (DeviceGradient, Stationary, White, Bias, composite_state_key, flatten_parts, part_descriptor)
 from .param import Param, Parameterized
 
 
@@ -110,7 +110,7 @@ class PosteriorExact(object):
     def _raw_predict(self, kern, Xnew, pred_var=None, full_cov=False):
         """posterior.py:273-302 on the device (gpx_predict). `pred_var` (the training inputs) is what the engine holds."""
         key = kern._state_key() if hasattr(kern, "_state_key") else (
-            kern._gpx_state_key() if hasattr(kern, "_gpx_state_key") else None)
+            kern._gpx_state_key() if hasattr(kern, "_gpx_state_key") else composite_state_key(kern))
         if self._kern_key is not None and key != self._kern_key:
             # a different kernel than the one evaluated (GP.predict(Xnew, kern=sub_kernel)): the reference's formula with
             # the kernel it is given (posterior.py:276-295), on the factor fetched from the device
@@ -186,6 +186,10 @@ class ExactGaussianInference(object):
         nvec = np.asarray(variance, dtype=np.float64).reshape(-1)
         het = nvec.size > 1                          # HeteroscedasticGaussian: a vector reaches diag.add (:55-56)
         noise = nvec if het else float(nvec[0])
+        if mean_function is None and K is None and not het and not isinstance(kern, Stationary):
+            parts = flatten_parts(kern)
+            if parts is not None:
+                return self._composite_inference(kern, parts, X, Y, noise, Z_tilde)
         if mean_function is not None or K is not None or not isinstance(kern, Stationary):
             return self._generic_inference(kern, X, Y, noise, mean_function, K, Z_tilde, likelihood, Y_metadata)
         Xs = kern._slice_X(X)
@@ -213,6 +217,27 @@ class ExactGaussianInference(object):
         grad_dict = {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
         return post, lml, grad_dict
 
+
+    def _composite_inference(self, kern, parts, X, Y, noise, Z_tilde):
+        """Sum / product kernels (add.py, prod.py, static.py) on the fused device path: ONE gpx_exact_eval_multi per
+        evaluation; the data stay resident, nothing of size N^2 crosses PCIe."""
+        Xc = np.ascontiguousarray(kern._slice_X(X), dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        self._bind(Xc, Y)
+        desc = [part_descriptor(leaf, term) for (leaf, term) in parts]
+        lml, grad, _ = self.engine.exact_eval_multi(desc, noise, jitter=1e-8, max_tries=5)
+        if Z_tilde is not None:
+            lml += Z_tilde
+        part_grads, i = [], 0
+        for (leaf, _) in parts:
+            n = 1 + (leaf.lengthscale.size if isinstance(leaf, Stationary) else 0)
+            part_grads.append(grad[i:i + n])
+            i += n
+        N, P = Y.shape
+        key = composite_state_key(kern)
+        post = PosteriorExact(self.engine, N, P, key)
+        dL_dK = DeviceGradient(self.engine, key, None, None, N, part_grads=part_grads)
+        return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
 
     def _generic_inference(self, kern, X, Y, noise, mean_function, K, Z_tilde, likelihood=None, Y_metadata=None):
         """exact_gaussian_inference.py:37-74 for the cases the fused call does not cover (mean function, precomputed K,

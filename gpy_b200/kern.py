@@ -21,9 +21,10 @@ class DeviceGradient(object):
     the kernel's parameter gradients; this handle carries them (keyed by the kernel state they were computed for)
     and only materialises the matrix (2 GiB at N=16384) if somebody treats it as an ndarray."""
 
-    def __init__(self, engine, key, dvariance, dlengthscale, N):
+    def __init__(self, engine, key, dvariance, dlengthscale, N, part_grads=None):
         self._engine, self._key = engine, key
         self.dvariance, self.dlengthscale = dvariance, dlengthscale
+        self.part_grads = part_grads          # composite kernels: one [variance, lengthscale..] array per flattened part
         self.shape = (N, N)
         self.ndim = 2
         self.dtype = np.dtype(np.float64)
@@ -214,10 +215,69 @@ class Matern52(Stationary):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# combination / static kernels. The parts' matrices are built on the device; the O(N^2) glue
-# (sums, element-wise products, traces) is NumPy on the host, and a GP with such a kernel runs through the generic
-# inference path (gpx_pdinv for the N^3 part). Mirrors GPy/kern/src/add.py:60-86, prod.py:59-110, static.py:63-140.
+# combination / static kernels. Mirrors GPy/kern/src/add.py:60-99, prod.py:59-68,377-396,
+# static.py:63-185. A GP whose kernel is a sum of products of stationary / White / Bias leaves is evaluated by ONE device
+# call (gpx_exact_eval_multi: the K-build multiplies / adds the parts in registers, every part's gradient is reduced from
+# the stored K^-1 with the other factors of its term recomputed on the fly); `flatten_parts` is the translation.
+# The stand-alone K / update_gradients_full methods below (foreign dL_dK, nested structures the flattening does not cover)
+# build the parts' matrices on the device and do the O(N^2) glue in NumPy on the host.
 # ----------------------------------------------------------------------------------------------------------------------
+def flatten_parts(kern):
+    """-> list of (leaf kernel, term index) for a kernel that is a leaf, a product of leaves, or a sum of those; None for
+    anything else (e.g. a product containing a sum), which then takes the generic inference path."""
+    def leaf(k):
+        return isinstance(k, (Stationary, White, Bias))
+
+    def product(k, term):
+        if leaf(k):
+            return [(k, term)]
+        if isinstance(k, Prod) and all(leaf(q) for q in k.parts):
+            return [(q, term) for q in k.parts]
+        return None
+
+    if isinstance(kern, Add):
+        out = []
+        for t, part in enumerate(kern.parts):
+            fl = product(part, t)
+            if fl is None:
+                return None
+            out.extend(fl)
+        return out
+    return product(kern, 0)
+
+
+def part_descriptor(leaf, term):
+    """(kind, ARD, term, dims, variance, lengthscale) of one leaf for Engine.exact_eval_multi"""
+    if isinstance(leaf, White):
+        return ("white", False, term, [], float(leaf.variance[0]), None)
+    if isinstance(leaf, Bias):
+        return ("bias", False, term, [], float(leaf.variance[0]), None)
+    kind, ard, var, ls = leaf._theta()
+    return (kind, ard, term, leaf.active_dims.tolist(), var, ls)
+
+
+def composite_state_key(kern):
+    fl = flatten_parts(kern)
+    if fl is None:
+        return None
+    return tuple((t, type(k).__name__, float(k.variance[0]),
+                  tuple(k.lengthscale.values.tolist()) if isinstance(k, Stationary) else (),
+                  tuple(k.active_dims.tolist())) for (k, t) in fl)
+
+
+def scatter_part_gradients(kern, dL_dK):
+    """hand the per-part gradients of a fused composite evaluation to the leaves (what Add / Prod.update_gradients_full do
+    with a dense dL_dK); -> False if the handle does not belong to this kernel state"""
+    if not (isinstance(dL_dK, DeviceGradient) and dL_dK.part_grads is not None and dL_dK.matches(composite_state_key(kern))):
+        return False
+    for (leaf, _), g in zip(flatten_parts(kern), dL_dK.part_grads):
+        leaf.variance.gradient = np.atleast_1d(g[0])
+        if isinstance(leaf, Stationary):
+            leaf.lengthscale.gradient = np.atleast_1d(g[1:]).copy()
+    return True
+
+
+
 class CombinationKernel(Kern):
     """GPy.kern.src.kern.CombinationKernel (kern.py:363-451): a kernel made of parts; active dims = union."""
 
@@ -253,6 +313,8 @@ class Add(CombinationKernel):
         return sum(p.Kdiag(X) for p in self.parts)
 
     def update_gradients_full(self, dL_dK, X, X2=None):
+        if X2 is None and scatter_part_gradients(self, dL_dK):
+            return
         dL_dK = np.asarray(dL_dK, dtype=np.float64)
         for p in self.parts:
             if not p.is_fixed:
@@ -290,7 +352,9 @@ class Prod(CombinationKernel):
         return out
 
     def update_gradients_full(self, dL_dK, X, X2=None):
-        """prod.py:90-110: each part sees dL_dK times the product of the other parts."""
+        """prod.py:377-385: each part sees dL_dK times the product of the other parts."""
+        if X2 is None and scatter_part_gradients(self, dL_dK):
+            return
         dL_dK = np.asarray(dL_dK, dtype=np.float64)
         Ks = [p.K(X, X2) for p in self.parts]
         for i, p in enumerate(self.parts):

@@ -28,7 +28,8 @@ extern "C" {
 
 typedef struct gpx_ctx gpx_ctx;
 
-enum { GPX_RBF = 0, GPX_EXPONENTIAL = 1, GPX_MATERN32 = 2, GPX_MATERN52 = 3 };
+enum { GPX_RBF = 0, GPX_EXPONENTIAL = 1, GPX_MATERN32 = 2, GPX_MATERN52 = 3,
+       GPX_WHITE = 4, GPX_BIAS = 5 /* static parts of a composite kernel only (GPy/kern/src/static.py:63-99,142-185) */ };
 
 /* gpx_get selectors */
 enum {
@@ -73,6 +74,27 @@ int gpx_exact_eval(gpx_ctx* ctx, int kind, int ard, double variance, const doubl
 int gpx_exact_eval_het(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale,
                        const double* noise_variances, double jitter, int max_tries, double* lml, double* grad,
                        double* dnoise, double* jitter_used);
+
+/* Composite kernels on the fused path: K = sum over terms of products of parts (GPy/kern/src/add.py:60-99 Add.K /
+ * update_gradients_full; prod.py:59-68,377-396 Prod.K, where every factor's gradient sees dL_dK times the other factors;
+ * static.py:63-99 White, :142-185 Bias). Each part is a stationary kernel on its own active dims (column indices into
+ * the X of gpx_set_data; kernel_slice_operations.py:59-79), a White or a Bias kernel. Parts with the same `term` are
+ * multiplied, terms are summed; parts must be ordered by term. The whole evaluation runs on the device like
+ * gpx_exact_eval (K-build, factor-and-invert sweep, K^-1, one gradient-reduction pass per part over the stored K^-1).
+ *   grad: out, concatenation over the parts in the given order of [d/d variance, d/d lengthscale (1 or ndims; none for
+ *         White / Bias)], then d/d noise — the order paramz gives Add/Prod parameters (kern.py:363-451 link order).
+ * gpx_get / gpx_predict afterwards use the composite kernel. Single-GPU. */
+typedef struct {
+  int kind;                  /* GPX_RBF .. GPX_MATERN52, GPX_WHITE, GPX_BIAS */
+  int ard;                   /* stationary kinds: 0 -> lengthscale points at 1 double, 1 -> at ndims doubles */
+  int term;                  /* additive term this factor belongs to */
+  int ndims;                 /* number of active dims (0 for White / Bias) */
+  const int* dims;           /* column indices into X, ndims entries */
+  double variance;
+  const double* lengthscale;
+} gpx_kern_part;
+int gpx_exact_eval_multi(gpx_ctx* ctx, const gpx_kern_part* parts, int nparts, double noise, double jitter, int max_tries,
+                         double* lml, double* grad, double* jitter_used);
 
 /* Lazy device->host fetch of N^2 / N*P results of the last gpx_exact_eval (Posterior / grad_dict consumers:
  * GPy/inference/latent_function_inference/posterior.py:21-77; exact_gaussian_inference.py:74). */
@@ -148,13 +170,15 @@ int64_t gpx_total_launches(gpx_ctx* ctx);
 /* Roofline denominator measured on this device: fp64 tensor (DMMA.8x8x4) issue rate in TFLOP/s, CUDA-event timed. */
 int gpx_measure_fp64_peak(gpx_ctx* ctx, double* tflops);
 
-/* Tunables (block sizes etc.), mainly for tests: name in {"nb", "lookahead", "profile"}. */
+/* Tunables (block sizes etc.), mainly for tests: name in {"nb", "lookahead", "profile", "ozaki" (0 = fp64 DMMA only,
+ * 1 = trailing update and K^-1 on the tcgen05 int8 path where applicable, -1 = default), "oz_dig_up" (digits per operand
+ * for the inverse-part tiles, 4..8), "oz_ctas" (CTAs of the persistent tcgen05 GEMM, 0 = one per SM)}. */
 int gpx_set_option(gpx_ctx* ctx, const char* name, int64_t value);
 
 /* Multi-GPU (one process per GPU). The caller obtains a 128-byte NCCL unique id on rank 0 (gpx_comm_unique_id),
  * ships it to the other ranks with its own plumbing (torch.distributed broadcast), and every rank calls
  * gpx_comm_init. Afterwards gpx_set_data / gpx_exact_eval are collective: block rows are dealt block-cyclically
- * to the ranks, panels are broadcast with ncclBroadcast over NVLink, scalars all-reduced. */
+ * to the ranks, the inverted diagonal block is broadcast and the panel all-gathered (NCCL over NVLink), scalars all-reduced. */
 int gpx_comm_unique_id(char id_out[128]);
 int gpx_comm_init(gpx_ctx* ctx, const char id[128], int rank, int nranks);
 

@@ -414,6 +414,91 @@ def logexp_gradfactor(f):
     return np.where(f > 36.0, 1.0, -np.expm1(-f))
 
 
+# ----------------------------------------------------------------------------------------------------------
+# composite kernels: GPy/kern/src/add.py:60-99, prod.py:59-68,377-396, static.py:63-99 (White), :142-185 (Bias), with
+# active_dims slicing of every part (kernel_slice_operations.py:59-79)
+# ----------------------------------------------------------------------------------------------------------
+class StaticOracle(object):
+    """White (static.py:63-99) / Bias (static.py:142-185)."""
+
+    def __init__(self, kind, variance):
+        self.kind, self.variance = kind, float(variance)
+
+    def K(self, X, X2=None):
+        n = X.shape[0]
+        if self.kind == "white":
+            return np.eye(n) * self.variance if X2 is None else np.zeros((n, X2.shape[0]))     # static.py:75-79
+        return np.full((n, n if X2 is None else X2.shape[0]), self.variance, dtype=np.float64)   # static.py:155-157
+
+    def Kdiag(self, X):
+        return np.full(X.shape[0], self.variance)                                                # static.py:30-33
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        if self.kind == "white":
+            return (np.trace(dL_dK) if X2 is None else 0.0), np.zeros(0)                          # static.py:88-92
+        return dL_dK.sum(), np.zeros(0)                                                           # static.py:172-173
+
+
+def composite_parts(parts):
+    """parts: list of dicts(kind, term, dims, variance, [lengthscale, ARD]) -> list of (oracle kernel, dims, term)."""
+    out = []
+    for p in parts:
+        if p["kind"] in ("white", "bias"):
+            out.append((StaticOracle(p["kind"], p["variance"]), None, p["term"]))
+        else:
+            out.append((StationaryOracle(p["kind"], len(p["dims"]), p["variance"], p["lengthscale"], p.get("ARD", False)),
+                        np.asarray(p["dims"]), p["term"]))
+    return out
+
+
+def _slice(X, dims):
+    return X if dims is None else np.ascontiguousarray(X[:, dims])
+
+
+def composite_K(kparts, X, X2=None):
+    """Add.K over the terms (add.py:60-74) of Prod.K over the factors (prod.py:59-68)."""
+    terms = {}
+    for (k, dims, t) in kparts:
+        Kp = k.K(_slice(X, dims), None if X2 is None else _slice(X2, dims))
+        terms[t] = Kp if t not in terms else terms[t] * Kp
+    return sum(terms[t] for t in sorted(terms))
+
+
+def composite_Kdiag(kparts, X):
+    terms = {}
+    for (k, dims, t) in kparts:
+        Kd = k.Kdiag(_slice(X, dims))
+        terms[t] = Kd if t not in terms else terms[t] * Kd
+    return sum(terms[t] for t in sorted(terms))
+
+
+def composite_eval_lml_grad(X, Y, parts, noise_variance):
+    """One GP.parameters_changed() with a composite kernel: -> (lml, grad [per part: variance, lengthscale.. ; noise], res).
+    Add.update_gradients_full hands dL_dK to every term (add.py:76-77); inside a product each factor sees dL_dK times the
+    other factors' K (prod.py:377-385)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    kparts = composite_parts(parts)
+    K = composite_K(kparts, X)
+    Ky = K.copy()
+    diag_add(Ky, noise_variance + 1e-8)
+    Wi, LW, LWi, W_logdet = pdinv(Ky)
+    alpha, _ = dpotrs(LW, Y, lower=1)
+    lml = 0.5 * (-Y.size * np.log(2 * np.pi) - Y.shape[1] * W_logdet - np.sum(alpha * Y))
+    dL_dK = 0.5 * (tdot(alpha) - Y.shape[1] * Wi)
+    grad = []
+    for i, (k, dims, t) in enumerate(kparts):
+        other = None
+        for j, (k2, dims2, t2) in enumerate(kparts):
+            if j != i and t2 == t:
+                Kj = k2.K(_slice(X, dims2))
+                other = Kj if other is None else other * Kj
+        dv, dl = k.update_gradients_full(dL_dK if other is None else dL_dK * other, _slice(X, dims), None)
+        grad.append(np.concatenate([[dv], np.atleast_1d(dl).reshape(-1)]))
+    grad.append([np.trace(dL_dK)])
+    return float(lml), np.concatenate(grad), dict(L=LW, alpha=alpha, K=K, Wi=Wi, dL_dK=dL_dK, kparts=kparts)
+
+
 def optimize_lbfgsb(X, Y, kind, ARD, variance, lengthscale, noise_variance, max_iters=1000, gtol=1e-5,
                     ftol=2.220446049250313e-09):
     """The optimisation loop of GP.optimize (GPy/core/gp.py:663-684 -> paramz Model.optimize, default 'lbfgsb' =

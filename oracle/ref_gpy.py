@@ -139,6 +139,27 @@ def load_models():
     return _models
 
 
+_comb = None
+
+
+def load_combination():
+    """-> namespace with the reference's own Add, Prod, White, Bias (GPy/kern/src/add.py, prod.py, static.py verbatim).
+    Add.__init__ imports RBF / Linear / Bias / White from the GPy.kern package (add.py:34): the names are set on the stub
+    package from the reference's own modules."""
+    global _comb
+    if _comb is not None:
+        return _comb
+    G = load()
+    kern_pkg = sys.modules["GPy.kern"]
+    static = importlib.import_module("GPy.kern.src.static")
+    linear = importlib.import_module("GPy.kern.src.linear")
+    kern_pkg.RBF, kern_pkg.Linear, kern_pkg.Bias, kern_pkg.White = G.RBF, linear.Linear, static.Bias, static.White
+    add = importlib.import_module("GPy.kern.src.add")
+    prod = importlib.import_module("GPy.kern.src.prod")
+    _comb = types.SimpleNamespace(Add=add.Add, Prod=prod.Prod, White=static.White, Bias=static.Bias, G=G)
+    return _comb
+
+
 KERNELS = {"rbf": "RBF", "exponential": "Exponential", "matern32": "Matern32", "matern52": "Matern52"}
 
 

@@ -547,3 +547,76 @@ def test_kernel_gradient_reductions_large_input_dimension(d):
         np.testing.assert_allclose(k.lengthscale.gradient, l0, rtol=1e-9, atol=1e-12)
         gx = k.gradients_X(dL, X, XX2)
         np.testing.assert_allclose(gx, ko.gradients_X(dL, X, XX2), rtol=1e-9, atol=1e-12)
+
+
+def _composite_case(D=5):
+    k = gpy_b200.Add([gpy_b200.Prod([gpy_b200.RBF(2, variance=1.2, lengthscale=[1.0, 2.0], ARD=True, active_dims=[0, 1]),
+                                     gpy_b200.Matern32(2, variance=0.8, lengthscale=1.5, active_dims=[2, 3])]),
+                      gpy_b200.Matern52(D, variance=0.5, lengthscale=np.linspace(1.5, 2.5, D), ARD=True),
+                      gpy_b200.Exponential(1, variance=0.3, lengthscale=2.0, active_dims=[4]),
+                      gpy_b200.White(D, variance=0.05), gpy_b200.Bias(D, variance=0.3)])
+    parts = [dict(kind="rbf", term=0, dims=[0, 1], variance=1.2, lengthscale=np.array([1.0, 2.0]), ARD=True),
+             dict(kind="matern32", term=0, dims=[2, 3], variance=0.8, lengthscale=1.5, ARD=False),
+             dict(kind="matern52", term=1, dims=list(range(D)), variance=0.5, lengthscale=np.linspace(1.5, 2.5, D), ARD=True),
+             dict(kind="exponential", term=2, dims=[4], variance=0.3, lengthscale=2.0, ARD=False),
+             dict(kind="white", term=3, dims=None, variance=0.05), dict(kind="bias", term=4, dims=None, variance=0.3)]
+    return k, parts
+
+
+@pytest.mark.parametrize("N", [150, 700, 1300])
+def test_composite_kernels_on_the_fused_device_path(N):
+    """Sum / product / White / Bias kernels (add.py:60-99, prod.py:59-68,377-396, static.py:63-185) through
+    gpx_exact_eval_multi: LML, every part's gradient, alpha, K and predictions against the oracle; N = 700 / 1300 take the
+    tcgen05 sweep with the stored K^-1, N = 150 the DMMA sweep + plain LAUUM."""
+    D = 5
+    X, Y = o.synthetic(N, D, seed=N)
+    k, parts = _composite_case(D)
+    m = gpy_b200.GPRegression(X, Y, k, noise_var=0.04)
+    lml0, g0, res = o.composite_eval_lml_grad(X, Y, parts, 0.04)
+    assert abs(m.log_likelihood() - lml0) <= LML_ATOL
+    np.testing.assert_allclose(m.gradient, g0, rtol=GRAD_RTOL, atol=1e-9)
+    assert rel(m.posterior.woodbury_vector, res["alpha"]) < 1e-9
+    if N <= 700:
+        assert rel(m.posterior.K, res["K"]) < 1e-12
+        assert rel(m.posterior.woodbury_chol, res["L"]) < 1e-10
+    Xn = np.random.default_rng(N).uniform(-3, 3, (9, D))
+    Kx = o.composite_K(res["kparts"], X, Xn)
+    tmp = o.dtrtrs(res["L"], Kx, lower=1)[0]
+    mu, var = m.predict(Xn, include_likelihood=False)
+    np.testing.assert_allclose(mu, Kx.T @ res["alpha"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var[:, 0], o.composite_Kdiag(res["kparts"], Xn) - np.square(tmp).sum(0), rtol=1e-7, atol=1e-9)
+    mu2, cov = m.predict(Xn, full_cov=True, include_likelihood=False)
+    np.testing.assert_allclose(cov, o.composite_K(res["kparts"], Xn) - tmp.T @ tmp, rtol=1e-7, atol=1e-9)
+    if N == 150:
+        assert m.checkgrad()
+        f0 = m.objective_function()
+        m.optimize(max_iters=10)
+        assert m.objective_function() < f0
+    # a single-kernel evaluation on the same context afterwards is unaffected
+    eng = m.inference_method.engine
+    lml1, g1, _ = eng.exact_eval("rbf", False, 1.1, 1.7, 0.05)
+    lml2, g2, _ = o.eval_lml_grad(X, Y, "rbf", False, 1.1, 1.7, 0.05)
+    assert abs(lml1 - lml2) <= LML_ATOL
+    np.testing.assert_allclose(g1, g2, rtol=GRAD_RTOL, atol=1e-9)
+
+
+@pytest.mark.parametrize("oz", [0, 1])
+def test_tensor_path_selection_gives_the_same_answer(oz):
+    """option ozaki = 0 (fp64 DMMA GEMMs) and 1 (tcgen05 kind::i8 digit-split GEMMs) both meet the tolerances against the
+    oracle, on a size with several panels, a non-multiple-of-block tail and P = 2 outputs."""
+    rng = np.random.default_rng(3)
+    N, D = 1700, 6
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.stack([np.sin(X).sum(1) / np.sqrt(D) + 0.1 * rng.standard_normal(N) for _ in range(2)], 1)
+    var, ls, noise = 1.3, np.sqrt(D) * np.linspace(0.8, 1.4, D), 0.02
+    lml0, g0, res = o.eval_lml_grad(X, Y, "matern52", True, var, ls, noise)
+    e = _ffi.Engine(0)
+    e.set_option("ozaki", oz)
+    e.set_data(X, Y)
+    lml, g, _ = e.exact_eval("matern52", True, var, ls, noise)
+    assert abs(lml - lml0) <= LML_ATOL
+    np.testing.assert_allclose(g, g0, rtol=GRAD_RTOL, atol=1e-9)
+    assert rel(e.get("alpha"), res["alpha"]) < 1e-9
+    assert rel(e.get("Kinv"), res["Wi"]) < 1e-8
+    assert rel(e.get("L"), res["L"]) < 1e-10
+    e.close()

@@ -168,3 +168,43 @@ def test_cited_reference_locations_exist():
             assert last <= n, (m.group(0), n)
             seen += 1
     assert seen >= 20
+
+
+def test_composite_oracle_equals_reference_add_prod_static():
+    """oracle.composite_* (restating add.py:60-99, prod.py:59-68,377-396, static.py:63-185) against the reference's own
+    Add / Prod / White / Bias objects: K, Kdiag and every parameter gradient for a foreign dL_dK."""
+    from oracle import ref_gpy
+    C = ref_gpy.load_combination()
+    G, add, prod, static = C.G, C, C, C
+    rng = np.random.default_rng(5)
+    N, D = 40, 5
+    X = rng.uniform(-2, 2, (N, D))
+    X2 = rng.uniform(-2, 2, (17, D))
+    k_rbf = G.RBF(2, variance=1.2, lengthscale=[1.0, 2.0], ARD=True, active_dims=[0, 1])
+    k_m32 = G.Matern32(2, variance=0.8, lengthscale=1.5, active_dims=[2, 3])
+    k_m52 = G.Matern52(D, variance=0.5, lengthscale=np.linspace(1.5, 2.5, D), ARD=True)
+    k_w, k_b = static.White(D, variance=0.05), static.Bias(D, variance=0.3)
+    kern = add.Add([prod.Prod([k_rbf, k_m32]), k_m52, k_w, k_b])
+    parts = [dict(kind="rbf", term=0, dims=[0, 1], variance=1.2, lengthscale=np.array([1.0, 2.0]), ARD=True),
+             dict(kind="matern32", term=0, dims=[2, 3], variance=0.8, lengthscale=1.5, ARD=False),
+             dict(kind="matern52", term=1, dims=list(range(D)), variance=0.5, lengthscale=np.linspace(1.5, 2.5, D), ARD=True),
+             dict(kind="white", term=2, dims=None, variance=0.05), dict(kind="bias", term=3, dims=None, variance=0.3)]
+    kp = o.composite_parts(parts)
+    np.testing.assert_allclose(o.composite_K(kp, X), kern.K(X), rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(o.composite_K(kp, X, X2), kern.K(X, X2), rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(o.composite_Kdiag(kp, X), kern.Kdiag(X), rtol=1e-14)
+    # gradients: one evaluation through the reference's own inference + Add/Prod.update_gradients_full
+    Y = np.sin(X).sum(1, keepdims=True) + 0.1 * rng.standard_normal((N, 1))
+    lik = G.Gaussian(variance=0.1)
+    post, lml, gd = G.ExactGaussianInference().inference(kern, X, lik, Y)
+    kern.update_gradients_full(gd["dL_dK"], X)
+    k_rbf, k_m32 = kern.parts[0].parts            # Prod copies its factors (prod.py:36-41): read the linked copies
+    k_m52, k_w, k_b = kern.parts[1:]
+    ref_grad = np.concatenate([np.atleast_1d(k_rbf.variance.gradient), np.atleast_1d(k_rbf.lengthscale.gradient).reshape(-1),
+                               np.atleast_1d(k_m32.variance.gradient), np.atleast_1d(k_m32.lengthscale.gradient).reshape(-1),
+                               np.atleast_1d(k_m52.variance.gradient), np.atleast_1d(k_m52.lengthscale.gradient).reshape(-1),
+                               np.atleast_1d(k_w.variance.gradient), np.atleast_1d(k_b.variance.gradient),
+                               np.atleast_1d(gd["dL_dthetaL"])])
+    lml0, g0, _ = o.composite_eval_lml_grad(X, Y, parts, 0.1)
+    assert abs(lml0 - float(lml)) < 1e-10
+    np.testing.assert_allclose(g0, ref_grad, rtol=1e-10, atol=1e-12)
