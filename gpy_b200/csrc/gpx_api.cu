@@ -156,6 +156,7 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "oz_ctas")) { c->oz_ctas = (int)std::max<int64_t>(0, value); return 0; }
+  if (!strcmp(name, "oz_dbg")) { c->oz_dbg = (int)value; return 0; }
   if (!strcmp(name, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
   GPX_FAIL("unknown option");
 }
@@ -423,7 +424,7 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
           memset(&op, 0, sizeof(op));
           op.tiles = c->oz_tiles + off; op.ntiles = ntl; op.nkc = (int)(nb / OZ_KC);
           op.scale = pl.scale; op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
-          op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up;
+          op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg;
           const double flops = (double)ntl * 2.0 * OZ_TM * OZ_TN * (double)nb;
           const int h = rec.begin(PH_UPDATE, flops);
           GPX_CHECK(launch_oz_gemm(pl, op, c->oz_ctas > 0 ? c->oz_ctas : c->num_sms, sm));

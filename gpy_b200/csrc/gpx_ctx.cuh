@@ -59,6 +59,7 @@ struct gpx_ctx {
   int ozaki = -1;              // option "ozaki": -1 = default (env GPX_OZAKI, else on), 0 = DMMA only, 1 = on where applicable
   int oz_dig_up = gpx::OZ_S;   // digits per operand for the inverse-part / K^-1 tiles (option "oz_dig_up")
   int oz_ctas = 0;             // CTAs of the persistent GEMM (0 = one per SM)
+  int oz_dbg = 0;              // measurement-only kernel variants (OzParams::dbg)
   int num_sms = 148;
   bool oz_ready = false;       // planes, K^-1 buffer and tile lists allocated for (Npad, NB)
   gpx::OzPlanes ozp[2];        // digit planes of the current / next panel (look-ahead double buffer)

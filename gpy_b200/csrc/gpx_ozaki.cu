@@ -183,6 +183,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kc = 0; kc < nkc; kc++, it++) {
           const int st = it % OZ_STAGES;
           mbar_wait(&empty[st], ((it / OZ_STAGES) & 1) ^ 1);
+          if (p.dbg & 2) { mbar_arrive(&full[st]); continue; }
           mbar_arrive_expect_tx(&full[st], (uint32_t)nd * (OZ_A_BYTES + OZ_B_BYTES));
           unsigned char* dst = ring + st * OZ_STAGE_BYTES;
           for (int s = 0; s < nd; s++) {
@@ -207,7 +208,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(&full[st], (it / OZ_STAGES) & 1);
           tc_fence_after();
           const uint32_t a0 = smem_u32(ring + st * OZ_STAGE_BYTES), b0 = a0 + OZ_S * OZ_A_BYTES;
-          for (int g = 0; g < nd; g++) {          // exponent group g = s + t accumulates in TMEM columns [64 g, 64 g + 64)
+          for (int g = 0; g < ((p.dbg & 1) ? 0 : nd); g++) {   // exponent group g = s + t accumulates in TMEM columns [64 g, 64 g + 64)
             const uint32_t dcol = taddr + (uint32_t)(g * OZ_TN);
             for (int s = 0; s <= g; s++)
               umma_i8(dcol, oz_desc(a0 + s * OZ_A_BYTES), oz_desc(b0 + (g - s) * OZ_B_BYTES), idesc, (kc > 0 || s > 0) ? 1u : 0u);
@@ -230,7 +231,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       double acc[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) acc[j] = 0.0;
-      for (int g = nd - 1; g >= 0; g--) {         // smallest magnitude first
+      for (int g = ((p.dbg & 4) ? 0 : nd) - 1; g >= 0; g--) {         // smallest magnitude first
         uint32_t v[32];
         tmem_ld32(taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * OZ_TN + h * 32), v);
         const double sc = __longlong_as_double((long long)(1023 - 7 * g) << 52);   // 2^(-7 g)
@@ -240,6 +241,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);     // TMEM may be overwritten by the next tile's MMAs
+      if (p.dbg & 4) continue;
       const long gi = (long)r * OZ_TM + q * 32 + lane;
       const long gj0 = (long)c64 * OZ_TN + h * 32;
       const double si = p.scale[gi];

@@ -41,6 +41,7 @@ struct OzParams {
   double* S; long lds;     // OZ_UPDATE target:      S(r, c)    -= P_r P_c^T
   double* Kinv; long ldk;  // OZ_LAUUM_* target:     Kinv(r, c) (+)= P_r P_c^T   (lower tiles)
   int dig_lo, dig_up;      // digits per operand for Cholesky-part tiles / inverse-part tiles (<= OZ_S)
+  int dbg;                 // measurement only (results invalid): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work
 };
 
 int oz_init();                                                          // driver entry point + kernel attributes

@@ -67,11 +67,73 @@ def _make_kernel(base, kind, ffi):
     return B200Kernel
 
 
-def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi):
-    """Build the plugin classes on top of the given GPy base classes."""
+def _make_combination(base, is_prod):
+    """Add / Prod over GPy's own class: K, Kdiag, gradients_X ... stay the reference's; update_gradients_full recognises the
+    handle of a fused composite evaluation and hands every leaf the gradient the device already reduced for it (the stock
+    methods would build every factor's N x N matrix on the host: add.py:76-77, prod.py:377-385)."""
+
+    class B200Combination(base):
+        def update_gradients_full(self, dL_dK, X, X2=None):
+            if isinstance(dL_dK, DeviceGradient) and X2 is None and dL_dK.part_grads is not None \
+                    and dL_dK.matches(_composite_key(self)):
+                for (leaf, _), g in zip(_flatten(self), dL_dK.part_grads):
+                    leaf.variance.gradient = g[0]
+                    if hasattr(leaf, "lengthscale"):
+                        leaf.lengthscale.gradient = g[1:] if leaf.ARD else g[1]
+                return
+            return super(B200Combination, self).update_gradients_full(np.asarray(dL_dK, dtype=np.float64), X, X2)
+
+    B200Combination.__name__ = B200Combination.__qualname__ = base.__name__
+    B200Combination._gpx_is_prod = is_prod
+    return B200Combination
+
+
+def _is_leaf(k):
+    return hasattr(k, "_gpx_kind") or type(k).__name__ in ("White", "Bias")
+
+
+def _flatten(kern):
+    """GPy kernel object -> [(leaf, term)] when it is a leaf, a product of leaves or a sum of those; else None"""
+    def product(k, term):
+        if _is_leaf(k):
+            return [(k, term)]
+        if getattr(k, "_gpx_is_prod", None) is True and all(_is_leaf(q) for q in k.parts):
+            return [(q, term) for q in k.parts]
+        return None
+
+    if getattr(kern, "_gpx_is_prod", None) is False:
+        out = []
+        for t, part in enumerate(kern.parts):
+            fl = product(part, t)
+            if fl is None:
+                return None
+            out.extend(fl)
+        return out
+    return product(kern, 0)
+
+
+def _leaf_descriptor(leaf, term):
+    var = float(np.asarray(leaf.variance).reshape(-1)[0])
+    if not hasattr(leaf, "_gpx_kind"):
+        return (type(leaf).__name__.lower(), False, term, [], var, None)
+    kind, ard, var, ls = leaf._gpx_theta()
+    return (kind, ard, term, np.atleast_1d(leaf.active_dims).astype(int).tolist(), var, ls)
+
+
+def _composite_key(kern):
+    fl = _flatten(kern)
+    if fl is None:
+        return None
+    return tuple((t,) + tuple(repr(x) for x in _leaf_descriptor(leaf, t)) for (leaf, t) in fl)
+
+
+def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi, Add=None, Prod=None):
+    """Build the plugin classes on top of the given GPy base classes (Add / Prod optional: composite kernels)."""
     kernels = {n: _make_kernel(b, _KINDS[n], ffi) for n, b in
                (("RBF", RBF), ("Exponential", Exponential), ("Matern32", Matern32), ("Matern52", Matern52))}
     kernel_types = tuple(kernels.values())
+    if Add is not None and Prod is not None:
+        kernels["Add"], kernels["Prod"] = _make_combination(Add, False), _make_combination(Prod, True)
 
     class B200ExactGaussianInference(ExactGaussianInference):
         """GPy.inference.latent_function_inference.ExactGaussianInference with the fused device evaluation; anything the
@@ -100,13 +162,39 @@ def make(RBF, Exponential, Matern32, Matern52, ExactGaussianInference, ffi=_ffi)
 
         def inference(self, kern, X, likelihood, Y, mean_function=None, Y_metadata=None, K=None, variance=None,
                       Z_tilde=None):
-            if mean_function is not None or K is not None or not isinstance(kern, kernel_types):
+            parts = None
+            if mean_function is None and K is None and not isinstance(kern, kernel_types):
+                parts = _flatten(kern) if hasattr(kern, "_gpx_is_prod") else None
+            if parts is None and (mean_function is not None or K is not None or not isinstance(kern, kernel_types)):
                 return super(B200ExactGaussianInference, self).inference(kern, X, likelihood, Y, mean_function,
                                                                          Y_metadata, K, variance, Z_tilde)
             if variance is None:
                 variance = likelihood.gaussian_variance(Y_metadata)
             nvec = np.asarray(variance, dtype=np.float64).reshape(-1)
             het = nvec.size > 1                      # HeteroscedasticGaussian (likelihoods/gaussian.py:347-362)
+            if parts is not None:
+                if het:
+                    return super(B200ExactGaussianInference, self).inference(kern, X, likelihood, Y, mean_function,
+                                                                             Y_metadata, K, variance, Z_tilde)
+                # sum / product kernel (add.py, prod.py, static.py): ONE gpx_exact_eval_multi, data resident
+                Xc = np.ascontiguousarray(X, dtype=np.float64)
+                Yc = np.ascontiguousarray(Y, dtype=np.float64)
+                if not self._data_key.matches(Xc, Yc):
+                    self.engine.set_data(Xc, Yc)
+                    self._data_key.remember(Xc, Yc)
+                lml, grad, _ = self.engine.exact_eval_multi([_leaf_descriptor(l, t) for (l, t) in parts], float(nvec[0]),
+                                                            jitter=1e-8, max_tries=5)
+                if Z_tilde is not None:
+                    lml += Z_tilde
+                pg, i = [], 0
+                for (leaf, _) in parts:
+                    n = 1 + (np.asarray(leaf.lengthscale).size if hasattr(leaf, "lengthscale") else 0)
+                    pg.append(grad[i:i + n])
+                    i += n
+                key = _composite_key(kern)
+                post = PosteriorExact(self.engine, Yc.shape[0], Yc.shape[1], key)
+                dL_dK = DeviceGradient(self.engine, key, None, None, Yc.shape[0], part_grads=pg)
+                return post, lml, {"dL_dK": dL_dK, "dL_dthetaL": grad[-1], "dL_dm": _LazyAlpha(post)}
             noise = None if het else float(nvec[0])
             Xs = np.ascontiguousarray(kern._slice_X(X)[0] if _returns_tuple(kern, X) else kern._slice_X(X),
                                       dtype=np.float64)
@@ -142,4 +230,5 @@ def load():
     """Plugin classes over an installed GPy."""
     import GPy
     from GPy.inference.latent_function_inference import ExactGaussianInference
-    return make(GPy.kern.RBF, GPy.kern.Exponential, GPy.kern.Matern32, GPy.kern.Matern52, ExactGaussianInference)
+    return make(GPy.kern.RBF, GPy.kern.Exponential, GPy.kern.Matern32, GPy.kern.Matern52, ExactGaussianInference,
+                Add=GPy.kern.Add, Prod=GPy.kern.Prod)

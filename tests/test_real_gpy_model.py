@@ -73,3 +73,38 @@ def test_stock_gpregression_optimizes_through_the_plugin_gpu():
     M, G, B = _plugin()
     for (kname, ARD, D, N) in (("RBF", True, 8, 1500), ("Matern52", False, 32, 900)):
         _run_pair(M, G, B, N, D, kname, ARD, 40)
+
+
+def test_stock_gpregression_with_a_sum_product_kernel_through_the_plugin_cpu():
+    """GPy's own Add / Prod (add.py, prod.py) over plugin leaves + the reference's White / Bias, inside the reference's own
+    GPRegression: the plugin inference flattens the kernel and makes ONE engine call per evaluation; the stock model class
+    distributes the gradients through (plugin) Add / Prod.update_gradients_full; same numbers as the all-stock model."""
+    from test_host_model_cpu import FakeEngine as MultiFakeEngine
+    from test_gpy_plugin_cpu import fake_ffi
+    from oracle import ref_gpy
+    from gpy_b200 import gpy_plugin
+    M = ref_gpy.load_models()
+    C = ref_gpy.load_combination()
+    G = M.G
+    ffi = fake_ffi()
+    ffi.Engine = MultiFakeEngine
+    B = gpy_plugin.make(G.RBF, G.Exponential, G.Matern32, G.Matern52, G.ExactGaussianInference, ffi=ffi, Add=C.Add, Prod=C.Prod)
+    X, Y = o.synthetic(90, 4, seed=6)
+
+    def build(K, Add, Prod):
+        return Add([Prod([K.RBF(2, variance=1.2, lengthscale=[1.0, 2.0], ARD=True, active_dims=[0, 1]),
+                          K.Matern32(2, variance=0.8, lengthscale=1.5, active_dims=[2, 3])]),
+                    K.Matern52(4, variance=0.5, lengthscale=2.0), C.White(4, variance=0.05), C.Bias(4, variance=0.3)])
+
+    stock = M.GPRegression(X, Y, build(G, C.Add, C.Prod), noise_var=0.1)
+    plug = M.GPRegression(X, Y, build(B, B.Add, B.Prod), noise_var=0.1)
+    plug.inference_method = B.ExactGaussianInference()
+    plug.parameters_changed()
+    eng = plug.inference_method.engine
+    assert eng.calls == ["set_data", "exact_eval_multi"]
+    assert abs(plug.log_likelihood() - stock.log_likelihood()) < 1e-9
+    np.testing.assert_allclose(plug.gradient, stock.gradient, rtol=1e-8, atol=1e-10)
+    plug.optimize(max_iters=15)
+    stock.optimize(max_iters=15)
+    assert abs(plug.log_likelihood() - stock.log_likelihood()) <= 1e-5 * max(1.0, abs(stock.log_likelihood()))
+    assert eng.calls.count("set_data") == 1 and "exact_eval" not in eng.calls

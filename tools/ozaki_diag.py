@@ -1,0 +1,31 @@
+"""Timing diagnosis of the tcgen05 GEMM (measurement only): which role bounds it. Runs the N=16384 evaluation with the
+measurement variants of oz_gemm_kernel (oz_dbg: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work; results invalid)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from gpy_b200 import _ffi
+
+def synthetic(N, D, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.sin(X).sum(1, keepdims=True) / np.sqrt(D) + 0.1 * rng.standard_normal((N, 1))
+    return X, Y
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+X, Y = synthetic(N, 8)
+th = ("rbf", True, 1.0, np.full(8, np.sqrt(8)), 0.01)
+e = _ffi.Engine(0)
+e.set_data(X, Y)
+for (dbg, ctas, la, dig, label) in [(0, 0, 1, 8, "full"), (0, 0, 0, 8, "full, no look-ahead"), (4, 0, 0, 8, "no epilogue"), (2, 0, 0, 8, "no TMA"),
+                              (6, 0, 0, 8, "no TMA, no epilogue (MMA issue only)"), (1, 0, 0, 8, "no MMA"), (5, 0, 0, 8, "TMA only"),
+                              (0, 132, 1, 8, "132 CTAs"), (0, 296, 1, 8, "296 CTAs (non-persistent-like)"), (0, 0, 1, 6, "inverse part 6 digits"),
+                              (0, 0, 1, 4, "inverse part 4 digits")]:
+    e.set_option("oz_dbg", dbg); e.set_option("oz_ctas", ctas); e.set_option("lookahead", la); e.set_option("oz_dig_up", dig)
+    for rep in range(2):
+        try:
+            e.exact_eval(*th, max_tries=0)
+        except Exception as ex:      # the measurement variants produce garbage: a not-PD report is expected
+            pass
+    st = e.stats()
+    print("%-40s total %7.2f ms  sweep %7.2f  update(sum of launches) %7.2f  grad %5.2f  tries %d" % (
+        label, st["total_ms"], st["sweep_ms"], st["update_ms"], st["lauum_ms"], st["tries"]), flush=True)
