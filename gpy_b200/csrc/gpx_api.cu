@@ -52,6 +52,7 @@ static void free_data(gpx_ctx* c) {
   oz_planes_free(c->ozp[1]);
   if (c->oz_tiles) cudaFree(c->oz_tiles);
   c->oz_tiles = nullptr;
+  for (double** mp : {&c->dYres, &c->dTfw}) { if (*mp) cudaFree(*mp); *mp = nullptr; }
   c->oz_steps.clear();
   c->oz_ready = false;
 }
@@ -292,6 +293,8 @@ static int oz_prepare(gpx_ctx* c) {
   GPX_CHECK(oz_planes_alloc(c->ozp[0], Npad, NB));
   GPX_CHECK(oz_planes_alloc(c->ozp[1], Npad, NB));
   if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)Npad * Npad * 8));
+  GPX_CUDA(cudaMalloc(&c->dYres, (size_t)MAX_P * Npad * 8));
+  GPX_CUDA(cudaMalloc(&c->dTfw, (size_t)MAX_P * Npad * 8));
   std::vector<uint32_t> tiles;
   c->oz_steps.clear();
   for (long o = 0; o < Npad; o += NB) {
@@ -350,6 +353,8 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
     GPX_CUDA(cudaEventRecord(ev, sm));
     GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
   }
+  if (oz >= 2)   // forward substitution t = L^-1 y rides along on the side stream (see fw_block_kernel)
+    GPX_CUDA(cudaMemcpyAsync(c->dYres, c->dY, (size_t)c->P * Npad * 8, cudaMemcpyDeviceToDevice, ss));
   int kblk = 0;
   for (long o = 0; o < Npad; o += NB, kblk++) {
     const long nb = std::min(NB, Npad - o);
@@ -411,6 +416,11 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
       GPX_CHECK(sync_event(c, evi++, &ev));
       GPX_CUDA(cudaEventRecord(ev, ss));
       GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
+    }
+    if (oz >= 2) {   // after the hand-over to the main stream: overlaps U1(k); the panel buffer is not reused before step k+2
+      GPX_CHECK(launch_fw_block(c->Tm, (int)nb, c->dYres + o, Npad, c->P, c->dTfw + o, ss));
+      GPX_CHECK(launch_fw_panel(Pb + (o + nb), Npad, Npad - o - nb, (int)nb, c->dTfw + o, Npad, c->P, c->dYres + (o + nb), ss));
+      c->eval_launches += 2;
     }
     // ---- trailing update: S(r,c) -= P_r P_c^T for c >= kt1, r in [0,kt1) U [c,nt), split U1 | U2 ---------------
     if (oz) {
@@ -589,7 +599,7 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     }
     rec.end(h);
     fm.ntiles = (long)nt * nt; fm.logdet_part = c->logdet_part; fm.nt = nt;
-    fm.T = c->dT; fm.ld = ld; fm.N = c->N; fm.P = c->P; fm.mk = c->mk; fm.res = c->res;
+    fm.T = oz ? c->dTfw : c->dT; fm.ld = ld; fm.N = c->N; fm.P = c->P; fm.mk = c->mk; fm.res = c->res;
     GPX_CHECK(launch_finalize_multi(fm, st));
     c->eval_launches++;
     GPX_CUDA(cudaMemcpyAsync(c->h_res, c->res, (MAX_D + 2 * MAX_PARTS + 8) * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -620,7 +630,7 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     memset(&f, 0, sizeof(f));
     f.partials = c->partials; f.ntiles = (long)nt * nt; f.nl = nl;
     f.logdet_part = c->logdet_part; f.nt = nt;
-    f.T = c->dT; f.ld = ld; f.N = c->N; f.P = c->P;
+    f.T = oz ? c->dTfw : c->dT; f.ld = ld; f.N = c->N; f.P = c->P;
     f.kp = c->kp;
     f.res = c->res;
     GPX_CHECK(launch_finalize(f, st));

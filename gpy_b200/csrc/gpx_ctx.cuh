@@ -64,6 +64,8 @@ struct gpx_ctx {
   bool oz_ready = false;       // planes, K^-1 buffer and tile lists allocated for (Npad, NB)
   gpx::OzPlanes ozp[2];        // digit planes of the current / next panel (look-ahead double buffer)
   uint32_t* oz_tiles = nullptr;
+  double* dYres = nullptr;     // [P][Npad] running right-hand side of the forward substitution carried along the sweep
+  double* dTfw = nullptr;      // [P][Npad] t = L^-1 y from that substitution (quadratic form of the LML)
   struct OzStep { int u1_off, u1_n, u2_off, u2_n, u2_upd; };   // U2 list: u2_upd update tiles, then the K^-1 tiles
   std::vector<OzStep> oz_steps;
   bool oz_last = false;        // the last evaluation went through the Ozaki path (K^-1 already stored)

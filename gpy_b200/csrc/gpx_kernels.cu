@@ -526,6 +526,65 @@ int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp
 }
 
 // =================================================================================================================
+// forward substitution t = L^-1 y carried along the sweep, block by block (the quadratic form y^T Ky^-1 y = |t|^2 of the
+// log marginal likelihood, exact_gaussian_inference.py:60-62, then rests on the CHOLESKY part of the factorisation only):
+//   fw_block : t_k = Linv_kk yres_k                    (Linv_kk = Tm, nb x nb lower triangular, column-major)
+//   fw_panel : yres(rows below) -= L(rows below, k) t_k   (the panel rows below the diagonal block)
+// =================================================================================================================
+__global__ void __launch_bounds__(TILE) fw_block_kernel(const double* __restrict__ Tm, int nb, const double* __restrict__ yres,
+                                                        long ld, int P, double* __restrict__ t) {
+  const int i = blockIdx.x * TILE + threadIdx.x;   // row inside the block
+  if (i >= nb) return;
+  double acc[MAX_P];
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+  const int jend = (i / 32 + 1) * 32 < nb ? (i / 32 + 1) * 32 : nb;   // zeros right of the diagonal: warp-uniform bound
+  for (int j = 0; j < jend; j++) {
+    const double a = Tm[i + (long)j * nb];
+#pragma unroll
+    for (int q = 0; q < MAX_P; q++)
+      if (q < P) acc[q] = fma(a, yres[(long)q * ld + j], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++)
+    if (q < P) t[(long)q * ld + i] = acc[q];
+}
+
+__global__ void __launch_bounds__(TILE) fw_panel_kernel(const double* __restrict__ Pb, long ldp, long rows, int nb,
+                                                        const double* __restrict__ t, long ld, int P,
+                                                        double* __restrict__ yres) {
+  const long r = (long)blockIdx.x * TILE + threadIdx.x;
+  if (r >= rows) return;
+  double acc[MAX_P];
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
+#pragma unroll 4
+  for (int c = 0; c < nb; c++) {
+    const double a = Pb[r + (long)c * ldp];
+#pragma unroll
+    for (int q = 0; q < MAX_P; q++)
+      if (q < P) acc[q] = fma(a, t[(long)q * ld + c], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < MAX_P; q++)
+    if (q < P) yres[(long)q * ld + r] -= acc[q];
+}
+
+int launch_fw_block(const double* Tm, int nb, const double* yres, long ld, int P, double* t, cudaStream_t st) {
+  fw_block_kernel<<<(unsigned)((nb + TILE - 1) / TILE), TILE, 0, st>>>(Tm, nb, yres, ld, P, t);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_fw_panel(const double* Pb, long ldp, long rows, int nb, const double* t, long ld, int P, double* yres,
+                    cudaStream_t st) {
+  if (rows <= 0) return 0;
+  fw_panel_kernel<<<(unsigned)((rows + TILE - 1) / TILE), TILE, 0, st>>>(Pb, ldp, rows, nb, t, ld, P, yres);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================================
 // triangular matrix-vector products with U = L^-T (upper, column-major, diagonal tiles included):
 //   t = U^T y  (= L^-1 y)      one warp per column, coalesced column walk
 //   a = U t    (= Ky^-1 y)     thread per row, k-range split over blockIdx.y, partials reduced in fixed order

@@ -44,6 +44,9 @@ int launch_kbuild(const KBuildParams& p, int row_tiles, int col_tiles, cudaStrea
 int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
                 cudaStream_t st);
 int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp, double* Tm, cudaStream_t st);
+int launch_fw_block(const double* Tm, int nb, const double* yres, long ld, int P, double* t, cudaStream_t st);
+int launch_fw_panel(const double* Pb, long ldp, long rows, int nb, const double* t, long ld, int P, double* yres,
+                    cudaStream_t st);
 int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st, int own_G = 0,
                int own_g = 0, long own_cols = 1);
 int launch_uv(const double* U, long ld, long n, int P, const double* T, int ksplit, double* part, double* out,

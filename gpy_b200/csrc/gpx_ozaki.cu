@@ -142,6 +142,24 @@ int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t
 // ---------------------------------------------------------------------------------------------------------------
 // 2. the GEMM
 // ---------------------------------------------------------------------------------------------------------------
+// one 32-deep k-chunk: the ND (ND + 1) / 2 digit-pair products, exponent group g = s + t in TMEM columns [64 g, 64 g + 64).
+// a_lo = low descriptor word (address field) of digit plane 0 of the A tile in this stage; the B planes follow the 8 A planes.
+template <int ND>
+__device__ __forceinline__ void oz_issue_chunk(uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
+  constexpr uint32_t idesc = oz_idesc(OZ_TM, OZ_TN);
+  constexpr uint64_t hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);   // LBO, SBO, version
+  const uint32_t b_lo = a_lo + (uint32_t)((OZ_S * OZ_A_BYTES) >> 4);
+#pragma unroll
+  for (int g = 0; g < ND; g++) {
+#pragma unroll
+    for (int s = 0; s <= g; s++) {
+      const uint64_t da = hi | (uint64_t)(a_lo + (uint32_t)(s * (OZ_A_BYTES >> 4)));
+      const uint64_t db = hi | (uint64_t)(b_lo + (uint32_t)((g - s) * (OZ_B_BYTES >> 4)));
+      umma_i8(taddr + (uint32_t)(g * OZ_TN), da, db, idesc, s > 0 ? 1u : acc0);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzParams p) {
   extern __shared__ unsigned char oz_smem_raw[];
@@ -173,31 +191,34 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int nkc = p.nkc;
 
   if (warp == 0) {
-    // ================= TMA producer ==============================================================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x) {
-        const uint32_t t = p.tiles[ti];
-        const int r = t & 0xfff, c64 = (t >> 12) & 0x1fff;
-        const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
-        for (int kc = 0; kc < nkc; kc++, it++) {
-          const int st = it % OZ_STAGES;
-          mbar_wait(&empty[st], ((it / OZ_STAGES) & 1) ^ 1);
-          if (p.dbg & 2) { mbar_arrive(&full[st]); continue; }
-          mbar_arrive_expect_tx(&full[st], (uint32_t)nd * (OZ_A_BYTES + OZ_B_BYTES));
-          unsigned char* dst = ring + st * OZ_STAGE_BYTES;
-          for (int s = 0; s < nd; s++) {
-            tma_load_4d(dst + s * OZ_A_BYTES, &mapA, 0, r * (OZ_TM / 8), kc, s, &full[st]);
-            tma_load_4d(dst + OZ_S * OZ_A_BYTES + s * OZ_B_BYTES, &mapB, 0, c64 * (OZ_TN / 8), kc, s, &full[st]);
-          }
+    // ================= TMA producer: lane s < nd loads digit plane s of both operands ================================
+    uint32_t it = 0;
+    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x) {
+      const uint32_t t = p.tiles[ti];
+      const int r = t & 0xfff, c64 = (t >> 12) & 0x1fff;
+      const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+      for (int kc = 0; kc < nkc; kc++, it++) {
+        const int st = it % OZ_STAGES;
+        mbar_wait(&empty[st], ((it / OZ_STAGES) & 1) ^ 1);
+        if (p.dbg & 2) { if (lane == 0) mbar_arrive(&full[st]); continue; }
+        // complete_tx of a copy may precede the expect_tx below: the phase cannot complete before lane 0's arrival
+        unsigned char* dst = ring + st * OZ_STAGE_BYTES;
+        if (lane < nd) {
+          tma_load_4d(dst + lane * OZ_A_BYTES, &mapA, 0, r * (OZ_TM / 8), kc, lane, &full[st]);
+          tma_load_4d(dst + OZ_S * OZ_A_BYTES + lane * OZ_B_BYTES, &mapB, 0, c64 * (OZ_TN / 8), kc, lane, &full[st]);
         }
+        if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)nd * (OZ_A_BYTES + OZ_B_BYTES));
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) ======================================================================
+    // The issue loop must sustain one tcgen05.mma per ~48 clk from ONE thread: descriptors are not rebuilt per instruction
+    // (the first version spent ~100 clk of uniform-datapath arithmetic per MMA and ran at half the shared-memory bound);
+    // the low descriptor word of plane s is the stage's base word + s * (plane bytes >> 4), the 36 instructions of a
+    // k-chunk are straight-line code (template on the digit count).
     if (lane == 0) {
-      constexpr uint32_t idesc = oz_idesc(OZ_TM, OZ_TN);
       uint32_t it = 0, tl = 0;
+      const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, tl++) {
         const uint32_t t = p.tiles[ti];
         const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
@@ -207,11 +228,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int st = it % OZ_STAGES;
           mbar_wait(&full[st], (it / OZ_STAGES) & 1);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(ring + st * OZ_STAGE_BYTES), b0 = a0 + OZ_S * OZ_A_BYTES;
-          for (int g = 0; g < ((p.dbg & 1) ? 0 : nd); g++) {   // exponent group g = s + t accumulates in TMEM columns [64 g, 64 g + 64)
-            const uint32_t dcol = taddr + (uint32_t)(g * OZ_TN);
-            for (int s = 0; s <= g; s++)
-              umma_i8(dcol, oz_desc(a0 + s * OZ_A_BYTES), oz_desc(b0 + (g - s) * OZ_B_BYTES), idesc, (kc > 0 || s > 0) ? 1u : 0u);
+          if (!(p.dbg & 1)) {
+            const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ_STAGE_BYTES >> 4);
+            const uint32_t acc0 = kc > 0 ? 1u : 0u;
+            switch (nd) {
+              case 8: oz_issue_chunk<8>(taddr, a_lo, acc0); break;
+              case 7: oz_issue_chunk<7>(taddr, a_lo, acc0); break;
+              case 6: oz_issue_chunk<6>(taddr, a_lo, acc0); break;
+              case 5: oz_issue_chunk<5>(taddr, a_lo, acc0); break;
+              default: oz_issue_chunk<4>(taddr, a_lo, acc0); break;
+            }
           }
           umma_commit(&empty[st]);                // the stage may be refilled once these MMAs have read it
         }
