@@ -19,7 +19,8 @@ class GpxStats(ctypes.Structure):
     _fields_ = [("total_ms", ctypes.c_float), ("kbuild_ms", ctypes.c_float), ("sweep_ms", ctypes.c_float),
                 ("update_ms", ctypes.c_float), ("lauum_ms", ctypes.c_float), ("solve_ms", ctypes.c_float),
                 ("update_flops", ctypes.c_double), ("lauum_flops", ctypes.c_double), ("kbuild_bytes", ctypes.c_double),
-                ("launches", ctypes.c_int64), ("update_launches", ctypes.c_int32), ("tries", ctypes.c_int32)]
+                ("launches", ctypes.c_int64), ("update_launches", ctypes.c_int32), ("tries", ctypes.c_int32),
+                ("update_int8_ops", ctypes.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -158,6 +158,7 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
   }
   if (!strcmp(name, "oz_ctas")) { c->oz_ctas = (int)std::max<int64_t>(0, value); return 0; }
   if (!strcmp(name, "oz_dbg")) { c->oz_dbg = (int)value; return 0; }
+  if (!strcmp(name, "oz_tpc")) { c->oz_tpc = (int)std::max<int64_t>(0, value); return 0; }
   if (!strcmp(name, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
   GPX_FAIL("unknown option");
 }
@@ -312,9 +313,12 @@ static int oz_prepare(gpx_ctx* c) {
     st.u1_off = (int)tiles.size();
     if (kt1 < nt) emit_update(kt1, kt1 + next_nbt);
     st.u1_n = (int)tiles.size() - st.u1_off;
+    auto count_up = [&](int off, int n) { int u = 0; for (int i = off; i < off + n; i++) u += (tiles[i] >> 27) & 1; return u; };
+    st.u1_up = count_up(st.u1_off, st.u1_n);
     st.u2_off = (int)tiles.size();
     if (kt1 + next_nbt < nt) emit_update(kt1 + next_nbt, nt);
     st.u2_upd = (int)tiles.size() - st.u2_off;
+    st.u2_upd_up = count_up(st.u2_off, st.u2_upd);
     {   // K^-1(r, c) (+)= P_r P_c^T for c <= r < kt1: rows of block k see their first contribution at this step
       std::vector<int> rows;
       for (int r = 0; r < kt1; r++) rows.push_back(r);
@@ -322,6 +326,7 @@ static int oz_prepare(gpx_ctx* c) {
                 [&](int r, int c64) { tiles.push_back(oz_tile(r, c64, r >= kt0 ? OZ_LAUUM_SET : OZ_LAUUM_ACC, 1)); });
     }
     st.u2_n = (int)tiles.size() - st.u2_off;
+    st.u2_up = count_up(st.u2_off, st.u2_n);
     c->oz_steps.push_back(st);
   }
   GPX_CUDA(cudaMalloc(&c->oz_tiles, tiles.size() * sizeof(uint32_t)));
@@ -403,11 +408,17 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
       GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), ss));
       c->eval_launches++;
     }
-    if (o > 0)
-      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, Pb, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, ss));
-    if (kt1 < nt)
-      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8,
-                                 (size_t)(Npad - o - nb) * 8, nb, cudaMemcpyDeviceToDevice, ss));
+    auto copy_back = [&]() -> int {   // the panel rows take their final place in S (U block column above, L panel below)
+      if (o > 0)
+        GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, Pb, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, ss));
+      if (kt1 < nt)
+        GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8,
+                                   (size_t)(Npad - o - nb) * 8, nb, cudaMemcpyDeviceToDevice, ss));
+      return 0;
+    };
+    // DMMA updates read the panel from Pb, tcgen05 updates from the digit planes: either way nothing on the main stream
+    // reads block column k of S, so on the tcgen05 path the copy-back leaves the critical chain (after the hand-over)
+    if (!oz) GPX_CHECK(copy_back());
     if (oz) {   // digit planes + row exponents of this panel (all rows: U block column | U_kk | Cholesky panel)
       GPX_CHECK(launch_oz_split(Pb, Npad, nb, c->ozp[kblk & 1], ss));
       c->eval_launches++;
@@ -417,6 +428,7 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
       GPX_CUDA(cudaEventRecord(ev, ss));
       GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
     }
+    if (oz) GPX_CHECK(copy_back());
     if (oz >= 2) {   // after the hand-over to the main stream: overlaps U1(k); the panel buffer is not reused before step k+2
       GPX_CHECK(launch_fw_block(c->Tm, (int)nb, c->dYres + o, Npad, c->P, c->dTfw + o, ss));
       GPX_CHECK(launch_fw_panel(Pb + (o + nb), Npad, Npad - o - nb, (int)nb, c->dTfw + o, Npad, c->P, c->dYres + (o + nb), ss));
@@ -435,9 +447,14 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
           op.tiles = c->oz_tiles + off; op.ntiles = ntl; op.nkc = (int)(nb / OZ_KC);
           op.scale = pl.scale; op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
           op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg;
+          op.tpc = c->oz_ctas > 0 ? (ntl + c->oz_ctas - 1) / c->oz_ctas : c->oz_tpc;
           const double flops = (double)ntl * 2.0 * OZ_TM * OZ_TN * (double)nb;
+          const int nup = part == 0 ? os.u1_up : (oz >= 2 ? os.u2_up : os.u2_upd_up);
+          const int du = c->oz_dig_up;
+          c->stats.update_int8_ops += ((double)nup * (du * (du + 1) / 2) + (double)(ntl - nup) * (OZ_S * (OZ_S + 1) / 2)) * 2.0 *
+                                      OZ_TM * OZ_TN * (double)nb;
           const int h = rec.begin(PH_UPDATE, flops);
-          GPX_CHECK(launch_oz_gemm(pl, op, c->oz_ctas > 0 ? c->oz_ctas : c->num_sms, sm));
+          GPX_CHECK(launch_oz_gemm(pl, op, c->num_sms, sm));
           rec.end(h);
           c->eval_launches++;
           c->stats.update_launches++;

@@ -58,7 +58,8 @@ struct gpx_ctx {
   // ---- tcgen05 / Ozaki path (gpx_ozaki.cu): trailing update and K^-1 on the INT8 tensor cores ------------------------
   int ozaki = -1;              // option "ozaki": -1 = default (env GPX_OZAKI, else on), 0 = DMMA only, 1 = on where applicable
   int oz_dig_up = gpx::OZ_S;   // digits per operand for the inverse-part / K^-1 tiles (option "oz_dig_up")
-  int oz_ctas = 0;             // CTAs of the persistent GEMM (0 = one per SM)
+  int oz_ctas = 0;             // option "oz_ctas": >0 = that many CTAs sharing the tile list evenly (persistent-style); 0 = default chunking
+  int oz_tpc = 0;              // option "oz_tpc": consecutive tiles per CTA (0 = default 4)
   int oz_dbg = 0;              // measurement-only kernel variants (OzParams::dbg)
   int num_sms = 148;
   bool oz_ready = false;       // planes, K^-1 buffer and tile lists allocated for (Npad, NB)
@@ -66,7 +67,7 @@ struct gpx_ctx {
   uint32_t* oz_tiles = nullptr;
   double* dYres = nullptr;     // [P][Npad] running right-hand side of the forward substitution carried along the sweep
   double* dTfw = nullptr;      // [P][Npad] t = L^-1 y from that substitution (quadratic form of the LML)
-  struct OzStep { int u1_off, u1_n, u2_off, u2_n, u2_upd; };   // U2 list: u2_upd update tiles, then the K^-1 tiles
+  struct OzStep { int u1_off, u1_n, u2_off, u2_n, u2_upd, u1_up, u2_up, u2_upd_up; };   // U2 list: u2_upd update tiles, then the K^-1 tiles; *_up = inverse-part tiles among them
   std::vector<OzStep> oz_steps;
   bool oz_last = false;        // the last evaluation went through the Ozaki path (K^-1 already stored)
   // ---- composite kernels (gpx_multi.cu): the last evaluation used gpx_exact_eval_multi --------------------------------

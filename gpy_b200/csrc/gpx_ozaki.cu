@@ -189,11 +189,15 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after();
   const uint32_t taddr = *tmem_slot;
   const int nkc = p.nkc;
+  // a CTA owns p.tpc CONSECUTIVE tiles of the list (neighbours in the banded order share operand panels in L2) and then
+  // retires: SM slots come free every few tiles, so the high-priority side stream of the sweep (diagonal block, panel of the
+  // next step) gets onto the machine while this launch is still running — a fully persistent grid would shut it out
+  const int ti_beg = blockIdx.x * p.tpc, ti_end = min(p.ntiles, ti_beg + p.tpc);
 
   if (warp == 0) {
     // ================= TMA producer: lane s < nd loads digit plane s of both operands ================================
     uint32_t it = 0;
-    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x) {
+    for (int ti = ti_beg; ti < ti_end; ti++) {
       const uint32_t t = p.tiles[ti];
       const int r = t & 0xfff, c64 = (t >> 12) & 0x1fff;
       const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
@@ -219,7 +223,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       uint32_t it = 0, tl = 0;
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
-      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, tl++) {
+      for (int ti = ti_beg; ti < ti_end; ti++, tl++) {
         const uint32_t t = p.tiles[ti];
         const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
         mbar_wait(tmem_empty, (tl & 1) ^ 1);     // the epilogue has read the previous tile out of TMEM
@@ -248,7 +252,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ================= epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ====================
     const int q = warp & 3, h = (warp - 2) >> 2;
     uint32_t tl = 0;
-    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, tl++) {
+    for (int ti = ti_beg; ti < ti_end; ti++, tl++) {
       const uint32_t t = p.tiles[ti];
       const int r = t & 0xfff, c64 = (t >> 12) & 0x1fff, kind = (t >> 25) & 3;
       const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
@@ -341,9 +345,11 @@ void oz_planes_free(OzPlanes& pl) {
   pl.planes = nullptr; pl.scale = nullptr; pl.rows = 0; pl.nkc = 0;
 }
 
-int launch_oz_gemm(const OzPlanes& pl, const OzParams& p, int max_ctas, cudaStream_t st) {
-  if (p.ntiles <= 0) return 0;
-  const int grid = std::min(p.ntiles, std::max(1, max_ctas));
+int launch_oz_gemm(const OzPlanes& pl, const OzParams& p_in, int num_sms, cudaStream_t st) {
+  if (p_in.ntiles <= 0) return 0;
+  OzParams p = p_in;
+  if (p.tpc <= 0) p.tpc = std::max(1, std::min(4, p.ntiles / std::max(1, num_sms)));   // default: 4 tiles per CTA when there is enough work
+  const int grid = (p.ntiles + p.tpc - 1) / p.tpc;
   oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(pl.mapA, pl.mapB, p);
   GPX_CUDA(cudaGetLastError());
   return 0;

@@ -41,6 +41,7 @@ struct OzParams {
   double* S; long lds;     // OZ_UPDATE target:      S(r, c)    -= P_r P_c^T
   double* Kinv; long ldk;  // OZ_LAUUM_* target:     Kinv(r, c) (+)= P_r P_c^T   (lower tiles)
   int dig_lo, dig_up;      // digits per operand for Cholesky-part tiles / inverse-part tiles (<= OZ_S)
+  int tpc;                 // consecutive tiles per CTA (0 = default)
   int dbg;                 // measurement only (results invalid): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work
 };
 
@@ -48,7 +49,7 @@ int oz_init();                                                          // drive
 int oz_planes_alloc(OzPlanes& pl, long rows, long K);                    // buffers + tensor maps
 void oz_planes_free(OzPlanes& pl);
 int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t st);   // P: rows x K column-major, K <= layout
-int launch_oz_gemm(const OzPlanes& pl, const OzParams& p, int max_ctas, cudaStream_t st);
+int launch_oz_gemm(const OzPlanes& pl, const OzParams& p, int num_sms, cudaStream_t st);
 
 // gradient reductions from a stored K^-1 (lower 128 x 128 tiles, column-major, leading dimension ld): same partial sums as
 // the fused epilogue of gemm_lauum_kernel, consumed by finalize_kernel

@@ -164,6 +164,12 @@ class ExactGaussianInference(object):
     def to_dict(self):
         return {"class": "gpy_b200.inference.ExactGaussianInference", "name": "ExactGaussianInference"}
 
+    def __getstate__(self):
+        """pickle without the device handle (precedent: GPy/kern/src/rbf.py:313-318); re-created lazily after loading"""
+        d = dict(self.__dict__)
+        d["_engine"], d["_data_key"] = None, _DataKey()
+        return d
+
     @property
     def engine(self):
         if self._engine is None:

@@ -17,9 +17,38 @@ from .kern import RBF
 from .param import Logexp, Parameterized
 
 
+class Standardize(object):
+    """GPy.util.normalizer.Standardize (normalizer.py:85-113): per-output mean / standard deviation of Y; O(N P) host work,
+    the device sees the normalised targets."""
+
+    def __init__(self):
+        self.mean = None
+
+    def scale_by(self, Y):
+        Y = np.ma.masked_invalid(Y, copy=False)
+        self.mean = Y.mean(0).view(np.ndarray)
+        self.std = Y.std(0).view(np.ndarray)
+        self.std[np.where(self.std == 0)] = 1.                      # normalizer.py:93-96
+
+    def scaled(self):
+        return self.mean is not None
+
+    def normalize(self, Y):
+        return (Y - self.mean) / self.std
+
+    def inverse_mean(self, X):
+        return (X * self.std) + self.mean
+
+    def inverse_variance(self, var):
+        return var * (self.std ** 2)
+
+    def inverse_covariance(self, covariance):
+        return covariance[..., np.newaxis] * (self.std ** 2)
+
+
 class GP(Parameterized):
     def __init__(self, X, Y, kernel, likelihood, mean_function=None, inference_method=None, name="gp", device=0,
-                 engine=None, Y_metadata=None):
+                 engine=None, Y_metadata=None, normalizer=False):
         super(GP, self).__init__(name)
         self._initialised = False   # parameter writes during construction do not evaluate (paramz: after __init__)
         self.mean_function = mean_function
@@ -29,6 +58,9 @@ class GP(Parameterized):
         assert X.ndim == 2
         assert Y.ndim == 2 and Y.shape[0] == X.shape[0]  # gp.py:42-66
         self.X, self.Y = X, Y
+        # gp.py:49-66: normalizer True -> Standardize, False / None -> none, else a _Norm-like object
+        self.normalizer = Standardize() if normalizer is True else (None if normalizer in (False, None) else normalizer)
+        self._normalize_Y()
         self.num_data, self.input_dim = X.shape
         self.output_dim = Y.shape[1]
         self.kern, self.likelihood = kernel, likelihood
@@ -45,10 +77,24 @@ class GP(Parameterized):
         self._initialised = True
         self.parameters_changed()  # paramz's metaclass triggers this after __init__
 
+    def _normalize_Y(self):
+        if self.normalizer is not None:
+            self.normalizer.scale_by(self.Y)
+            self.Y_normalized = np.ascontiguousarray(self.normalizer.normalize(self.Y), dtype=np.float64)
+        else:
+            self.Y_normalized = self.Y
+
+    def __getstate__(self):
+        """pickling returns a device-less model (precedent: GPy/kern/src/rbf.py:313-318 drops its GPU state): the engine
+        handle is dropped, the inference object re-creates it lazily and uploads the data at the next evaluation"""
+        d = dict(self.__dict__)
+        d["posterior"] = None
+        return d
+
     # ---- one evaluation: gp.py:269-282 -------------------------------------------------------------------------
     def parameters_changed(self):
         self.posterior, self._log_marginal_likelihood, self.grad_dict = self.inference_method.inference(
-            self.kern, self.X, self.likelihood, self.Y, self.mean_function, self.Y_metadata)
+            self.kern, self.X, self.likelihood, self.Y_normalized, self.mean_function, self.Y_metadata)
         self.likelihood.update_gradients(self.grad_dict["dL_dthetaL"])
         self.kern.update_gradients_full(self.grad_dict["dL_dK"], self.X)
 
@@ -63,6 +109,7 @@ class GP(Parameterized):
             self.X = np.asarray(X, dtype=np.float64)
         if Y is not None:
             self.Y = np.asarray(Y, dtype=np.float64)
+            self._normalize_Y()                                     # gp.py:224-226
         self.num_data = self.X.shape[0]
         if hasattr(self.inference_method, "invalidate_data"):
             self.inference_method.invalidate_data()
@@ -186,6 +233,12 @@ class GP(Parameterized):
             if likelihood is None:
                 likelihood = self.likelihood
             mean, var = likelihood.predictive_values(mean, var, full_cov, Y_metadata=Y_metadata)
+        if self.normalizer is not None:                             # gp.py:355-363
+            mean = self.normalizer.inverse_mean(mean)
+            if full_cov and mean.shape[1] > 1:
+                var = self.normalizer.inverse_covariance(var)
+            else:
+                var = self.normalizer.inverse_variance(var)
         return mean, var
 
     def predict_noiseless(self, Xnew, full_cov=False, Y_metadata=None, kern=None):
@@ -215,10 +268,9 @@ class GPRegression(GP):
 
     def __init__(self, X, Y, kernel=None, Y_metadata=None, normalizer=None, noise_var=1., mean_function=None,
                  device=0, engine=None):
-        if normalizer is not None:
-            raise NotImplementedError("normalizer is outside the accelerated hot path (Y is normalised on the host)")
         if kernel is None:
             kernel = RBF(np.asarray(X).shape[1])  # gp_regression.py:31-32
         likelihood = Gaussian(variance=noise_var)  # gp_regression.py:34
         super(GPRegression, self).__init__(X, Y, kernel, likelihood, mean_function=mean_function, name="GP regression",
-                                           device=device, engine=engine)
+                                           device=device, engine=engine, Y_metadata=Y_metadata,
+                                           normalizer=False if normalizer is None else normalizer)

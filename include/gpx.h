@@ -155,8 +155,9 @@ typedef struct {
   float total_ms;       /* whole eval, H2D of theta .. D2H of (lml, grad) */
   float kbuild_ms;      /* covariance build kernel */
   float sweep_ms;       /* blocked factor-and-invert sweep (all launches) */
-  float update_ms;      /* sum over the outer trailing-update GEMM launches (dominant kernel) */
-  float lauum_ms;       /* K^-1 = U U^T + fused gradient epilogue */
+  float update_ms;      /* sum over the outer trailing-update GEMM launches (dominant kernel); on the tcgen05 path these launches
+                           also accumulate K^-1 = U U^T */
+  float lauum_ms;       /* DMMA path: K^-1 = U U^T + fused gradient epilogue; tcgen05 path: gradient reductions from the stored K^-1 */
   float solve_ms;       /* alpha / quadratic form */
   double update_flops;  /* algorithmic flops executed by the outer trailing-update launches */
   double lauum_flops;
@@ -164,6 +165,8 @@ typedef struct {
   int64_t launches;     /* kernels launched by the last eval */
   int32_t update_launches;
   int32_t tries;        /* factorisation attempts (1 = no jitter ladder) */
+  double update_int8_ops; /* tcgen05 path: int8 multiply-add operations (2 per MAC) issued by the update / K^-1 launches, summed
+                             over the digit pairs actually computed; 0 on the DMMA path */
 } gpx_stats;
 int gpx_get_stats(gpx_ctx* ctx, gpx_stats* out);
 int64_t gpx_total_launches(gpx_ctx* ctx);

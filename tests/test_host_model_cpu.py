@@ -207,3 +207,31 @@ def test_sum_and_product_kernels_take_the_fused_composite_path():
     k2 = gpy_b200.Prod([gpy_b200.Add([gpy_b200.RBF(4), gpy_b200.Bias(4)]), gpy_b200.Matern32(4)])
     from gpy_b200.kern import flatten_parts
     assert flatten_parts(k2) is None and flatten_parts(k) is not None and len(flatten_parts(k)) == 5
+
+
+def test_normalizer_and_pickle_round_trip():
+    """normalizer=True -> Standardize (gp.py:49-66,355-363; normalizer.py:85-113): the engine sees the standardised Y, the
+    predictions come back in the units of Y. Pickling drops the device handle (rbf.py:313-318 precedent) and the copy
+    evaluates again after loading."""
+    import pickle
+    import gpy_b200
+    X, Y = o.synthetic(50, 2, 4)
+    Y = 3.0 + 5.0 * Y
+    eng = FakeEngine()
+    m = gpy_b200.GPRegression(X, Y, gpy_b200.RBF(2, lengthscale=1.4), noise_var=0.1, normalizer=True, engine=eng)
+    Yn = (Y - Y.mean(0)) / Y.std(0)
+    np.testing.assert_allclose(eng.Y, Yn, rtol=1e-14)
+    lml0, g0, res = o.eval_lml_grad(X, Yn, "rbf", False, 1.0, 1.4, 0.1)
+    assert abs(m.log_likelihood() - lml0) < 1e-9
+    Xn = np.random.default_rng(0).uniform(-2, 2, (4, 2))
+    mu, var = m.predict(Xn)
+    k = o.StationaryOracle("rbf", 2, 1.0, 1.4, False)
+    mu0, var0 = o.predict(k, X, res["L"], res["alpha"], Xn, 0.1)
+    np.testing.assert_allclose(mu, mu0 * Y.std(0) + Y.mean(0), rtol=1e-10)
+    np.testing.assert_allclose(var, var0 * Y.std(0) ** 2, rtol=1e-10)
+    blob = pickle.dumps(m)
+    m2 = pickle.loads(blob)
+    assert m2.inference_method._engine is None and m2.posterior is None
+    m2.inference_method._engine = FakeEngine()           # stands for the lazily re-created device context
+    m2.parameters_changed()
+    assert abs(m2.log_likelihood() - lml0) < 1e-9 and m2.inference_method._engine.calls == ["set_data", "exact_eval"]
