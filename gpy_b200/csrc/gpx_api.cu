@@ -270,10 +270,16 @@ static int sync_event(gpx_ctx* c, size_t idx, cudaEvent_t* out) {
 static bool oz_wanted(const gpx_ctx* c) {
   if (c->dist) return false;
   int on = c->ozaki;
-  if (on < 0) { const char* e = getenv("GPX_OZAKI"); on = e ? atoi(e) : 1; }
+  bool forced = on > 0;
+  if (on < 0) { const char* e = getenv("GPX_OZAKI"); on = e ? atoi(e) : 1; forced = e != nullptr && on > 0; }
   if (!on) return false;
   const long NB = pick_nb(c);
-  return c->Npad >= 2 * NB && NB % OZ_KC == 0;   // a single-block matrix has no panel: it stays on the DMMA path
+  // Default: from Npad = 8192 on. Below that the evaluation is bound by the serial diagonal-block chain, not by the GEMMs,
+  // and the extra launches of the digit split cost more than the faster tiles save (measured: 0.82x at N = 4096, 1.5x at
+  // 16384). An explicit request (option "ozaki" = 1 / GPX_OZAKI=1) applies wherever there are at least two panels:
+  // a single-block matrix has no panel and stays on the DMMA path.
+  if (!forced && c->Npad < 8192) return false;
+  return c->Npad >= 2 * NB && NB % OZ_KC == 0;
 }
 
 // tiles in bands of 8 row tiles x 16 column tiles (64 wide): the ~148 tiles in flight share 8 A panels and 16 B panels in L2

@@ -57,7 +57,8 @@ struct gpx_ctx {
   int profile = 1;
   // ---- tcgen05 / Ozaki path (gpx_ozaki.cu): trailing update and K^-1 on the INT8 tensor cores ------------------------
   int ozaki = -1;              // option "ozaki": -1 = default (env GPX_OZAKI, else on), 0 = DMMA only, 1 = on where applicable
-  int oz_dig_up = gpx::OZ_S;   // digits per operand for the inverse-part / K^-1 tiles (option "oz_dig_up")
+  int oz_dig_up = 7;           // digits per operand for the inverse-part / K^-1 tiles, which feed only the gradients
+                               // (option "oz_dig_up"; 7 -> 28 digit pairs instead of 36, gradient error ~6e-10 at N = 16384)
   int oz_ctas = 0;             // option "oz_ctas": >0 = that many CTAs sharing the tile list evenly (persistent-style); 0 = default chunking
   int oz_tpc = 0;              // option "oz_tpc": consecutive tiles per CTA (0 = default 4)
   int oz_dbg = 0;              // measurement-only kernel variants (OzParams::dbg)

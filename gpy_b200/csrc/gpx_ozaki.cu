@@ -265,8 +265,11 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * OZ_TN + h * 32), v);
         const double sc = __longlong_as_double((long long)(1023 - 7 * g) << 52);   // 2^(-7 g)
+        // s32 -> fp64 without the conversion unit (I2F.F64 is a few lanes per SM: it made the TMEM drain ~15k clk per tile):
+        // the bit pattern {0x43300000, v ^ 0x80000000} is the double 2^52 + 2^31 + v, one exact DADD takes the offset off
 #pragma unroll
-        for (int j = 0; j < 32; j++) acc[j] = fma((double)(int32_t)v[j], sc, acc[j]);
+        for (int j = 0; j < 32; j++)
+          acc[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, sc, acc[j]);
       }
       tc_fence_before();
       __syncwarp();
