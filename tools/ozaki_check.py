@@ -37,8 +37,8 @@ def main():
         for oz in (0, 1, 7, 6):
             e = _ffi.Engine(0)
             e.set_option("ozaki", 1 if oz else 0)
-            if oz > 1:
-                e.set_option("oz_dig_up", oz)         # digits per operand of the inverse-part / K^-1 tiles
+            if oz >= 1:
+                e.set_option("oz_dig_up", 8 if oz == 1 else oz)   # digits per operand of the inverse-part / K^-1 tiles
             e.set_data(X, Y)
             e.exact_eval(kind, ARD, var, ls, noise)           # warm-up (allocations, tile lists)
             lml, g, jit = e.exact_eval(kind, ARD, var, ls, noise)
