@@ -1225,8 +1225,10 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   // tmp = L^-1 Kx = U^T Kx, MAX_P columns per pass
   for (long m0 = 0; rc == 0 && m0 < M; m0 += MAX_P) {
     const int pc = (int)std::min<long>(MAX_P, M - m0);
-    rc = dG > 1 ? launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st, dG, drank, dNB)
-                : launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st);
+    long ldu = ld;
+    const double* Ud = c->dist ? dist_U(c, &ldu) : nullptr;   // sharded: the column-owned U storage (local column slots)
+    rc = Ud ? launch_utv(Ud, ldu, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st, dG, drank, dNB, 1)
+            : launch_utv(c->S, ld, c->Npad, pc, Kx + m0 * ld, Tx + m0 * ld, st);
     c->total_launches++;
   }
   if (!full_cov) {

@@ -152,9 +152,18 @@ struct GemmParams {
   int map_blk, map_G, map_npr; long map_stride;
   int own_G, own_g, own_blk;   // UPDATE / PANEL: a tile is processed iff ((r / own_blk) % own_G) == own_g
   int k_G, k_g, k_blk;         // LAUUM: only k-tiles inside column blocks kb == k_g (mod k_G), k_blk tiles per block
+  // memory-distributed layout: a rank stores only the block rows it owns (row tile r at local tile loc_tile(r, own_G,
+  // own_blk)) and, for U = L^-T, only the column blocks it owns (k-tile kt at local tile loc_tile(kt, k_G, k_blk))
+  int loc_A, loc_C;            // PANEL: A rows / UPDATE: C rows are local
+  int k_local;                 // LAUUM: the k index of A and B is local
   KernParams kp;
   double* dnoise_out;   // LAUUM epilogue, optional: diag(dL_dK)_i per data point (heteroscedastic noise gradients)
 };
+
+// local tile index of an OWNED global tile t under a block-cyclic deal of blocks of `blk` tiles over G ranks
+__host__ __device__ __forceinline__ long loc_tile(int t, int G, int blk) {
+  return G <= 1 ? (long)t : (long)((t / blk) / G) * blk + t % blk;
+}
 
 int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t st);
 size_t gemm_smem_bytes();

@@ -90,7 +90,8 @@ GemmParams gemm_defaults();
 int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y, int P);
 int dist_exact_eval(gpx_ctx* c, double extra_jitter);
 void dist_free(gpx_ctx* c);
-long dist_block(const gpx_ctx* c);                                             // NB of the sharded layout (0: none)
+long dist_block(const gpx_ctx* c);
+const double* dist_U(const gpx_ctx* c, long* ld);                               // sharded: column-owned U storage                                             // NB of the sharded layout (0: none)
 int dist_world(const gpx_ctx* c, int* rank, int* nranks);                       // (0, 1) without a communicator
 int dist_allreduce_sum(gpx_ctx* c, double* buf, size_t count, cudaStream_t st);   // in place, on stream st
 void sparse_free(gpx_ctx* c);

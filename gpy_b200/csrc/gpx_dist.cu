@@ -108,6 +108,11 @@ struct DistState {
   double* raw = nullptr;       // device: raw sums for the scalar all-reduce
   double* h_raw = nullptr;     // pinned
   double* blkpart = nullptr;   // [nblk][P][Npad] partials of alpha
+  // memory-distributed layout: c->S is the ROW-owned workspace SL (ldl = npr * NB rows x Npad columns: the block rows of
+  // the trailing matrix / L / inverse region this rank updates), SU the COLUMN-owned final U = L^-T (Npad rows x npr * NB
+  // columns: column block k at local slot k / G). Together 2 Npad^2 / G doubles per rank instead of Npad^2.
+  double* SU = nullptr;
+  long ldl = 0;
 };
 
 using namespace gpx;
@@ -120,10 +125,18 @@ void dist_free(gpx_ctx* c) {
   if (d->Bc) cudaFree(d->Bc);
   if (d->Bc2) cudaFree(d->Bc2);
   if (d->blkpart) cudaFree(d->blkpart);
-  d->Bc = d->Bc2 = d->blkpart = nullptr;
+  if (d->SU) cudaFree(d->SU);
+  d->Bc = d->Bc2 = d->blkpart = d->SU = nullptr;
 }
 
 long dist_block(const gpx_ctx* c) { return c->dist ? c->dist->NB : 0; }
+
+// the column-owned U = L^-T storage of a sharded context (predict): Npad x (npr NB), leading dimension Npad
+const double* dist_U(const gpx_ctx* c, long* ld) {
+  if (!c->dist || !c->dist->SU) return nullptr;
+  *ld = c->Npad;
+  return c->dist->SU;
+}
 
 int dist_world(const gpx_ctx* c, int* rank, int* nranks) {
   if (c->dist && c->dist->comm) { *rank = c->dist->rank; *nranks = c->dist->G; }
@@ -169,7 +182,10 @@ int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y
     GPX_CUDA(cudaMalloc(&c->dT, (size_t)Npad * P * 8));
     GPX_CUDA(cudaMalloc(&c->dAlpha, (size_t)Npad * P * 8));
     GPX_CUDA(cudaMalloc(&c->dUvPart, (size_t)Npad * P * 8));
-    GPX_CUDA(cudaMalloc(&c->S, (size_t)Npad * Npad * 8));
+    d->ldl = npr * NB;
+    GPX_CUDA(cudaMalloc(&c->S, (size_t)d->ldl * Npad * 8));       // owned block rows only
+    GPX_CUDA(cudaMalloc(&d->SU, (size_t)Npad * d->ldl * 8));      // owned column blocks of U only
+    GPX_CUDA(cudaMemsetAsync(d->SU, 0, (size_t)Npad * d->ldl * 8, c->st));
     GPX_CUDA(cudaMalloc(&c->Pbuf, (size_t)2 * d->G * npr * NB * NB * 8));   // double-buffered (look-ahead)
     GPX_CUDA(cudaMalloc(&c->Tm, (size_t)NB * NB * 8));
     GPX_CUDA(cudaMalloc(&d->Bc, (size_t)NB * NB * 8));
@@ -196,7 +212,7 @@ int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y
 int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
   DistState* d = c->dist;
   cudaStream_t st = c->st;
-  const long ld = c->Npad, Npad = c->Npad, NB = d->NB;
+  const long ld = d->ldl, Npad = c->Npad, NB = d->NB;   // ld: leading dimension of the row-owned workspace
   const int nt = (int)(Npad / TILE), nbt = (int)(NB / TILE);
   const int G = d->G, g = d->rank;
   const int nl = c->kp.ard ? c->D : 1, nred = nl + 2;
@@ -211,7 +227,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
     kb.sq_rows = c->dsq; kb.sq_cols = c->dsq;
     kb.out = c->S; kb.ld = ld; kb.nrows = c->N; kb.ncols = c->N; kb.sym = 1; kb.same = 1;
     kb.diag_add = (c->noise + c->jitter) + extra_jitter;
-    kb.own_G = G; kb.own_g = g; kb.own_blk = nbt;
+    kb.own_G = G; kb.own_g = g; kb.own_blk = nbt; kb.loc_rows = 1;
     kb.kp = c->kp;
     GPX_CHECK(launch_kbuild(kb, nt, nt, st));
     c->eval_launches++;
@@ -248,7 +264,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
     double* Pb = c->Pbuf + (size_t)(k & 1) * pstride;
     double* Bc = (k & 1) ? d->Bc2 : d->Bc;
     if (g == root) {
-      double* Sblk = c->S + o + o * ld;
+      double* Sblk = c->S + (long)(k / G) * NB + o * ld;   // the diagonal block inside the owner's local rows
       for (int dd = 0; dd < nbt; dd++) {
         const int gt = kt0 + dd;
         double* tile = Sblk + (long)dd * TILE + (long)dd * TILE * ld;
@@ -283,7 +299,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
     {
       GemmParams pp = gemm_defaults();
       pp.mode = GEMM_PANEL;
-      pp.A = c->S + o * ld; pp.lda = ld;
+      pp.A = c->S + o * ld; pp.lda = ld; pp.loc_A = 1;
       pp.B = Bc; pp.ldb = NB;
       pp.C = Pb; pp.ldc = NB; pp.map_C = 1;
       pp.map_blk = nbt; pp.map_G = G; pp.map_npr = (int)d->npr; pp.map_stride = NB * NB;
@@ -293,7 +309,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
       c->eval_launches++;
     }
     GPX_NCCL(g_nccl.AllGather(Pb + (size_t)g * d->npr * NB * NB, Pb, (size_t)d->npr * NB * NB, ncclDouble, cs, ss));
-    GPX_CHECK(launch_copyback(c->S, ld, Pb, NB, G, g, d->npr, k, nt, ss));
+    GPX_CHECK(launch_copyback(c->S, ld, d->SU, Npad, Pb, NB, G, g, d->npr, k, nt, ss));
     c->eval_launches++;
     if (la) {
       GPX_CHECK(next_event(&ev));
@@ -312,7 +328,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
           pu.B = Pb; pu.ldb = NB; pu.map_B = 1;
           pu.map_blk = nbt; pu.map_G = G; pu.map_npr = (int)d->npr; pu.map_stride = NB * NB;
           pu.own_G = G; pu.own_g = g; pu.own_blk = nbt;
-          pu.C = c->S; pu.ldc = ld;
+          pu.C = c->S; pu.ldc = ld; pu.loc_C = 1;
           pu.K = (int)NB; pu.nt = nt; pu.c0 = cbeg; pu.ncols = cend - cbeg; pu.rlow = kt1;
           GPX_CHECK(launch_gemm(pu, dim3(1, 1), sm));
           c->eval_launches++;
@@ -333,9 +349,9 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
   }
   // ---- alpha = U (U^T y): owned column blocks, two vector all-reduces ------------------------------------------------
   GPX_CUDA(cudaMemsetAsync(c->dT, 0, (size_t)Npad * c->P * 8, st));
-  GPX_CHECK(launch_utv(c->S, ld, Npad, c->P, c->dY, c->dT, st, G, g, NB));
+  GPX_CHECK(launch_utv(d->SU, Npad, Npad, c->P, c->dY, c->dT, st, G, g, NB, 1));
   GPX_NCCL(g_nccl.AllReduce(c->dT, c->dT, (size_t)Npad * c->P, ncclDouble, ncclSum, d->comm, st));
-  GPX_CHECK(launch_uv_blk(c->S, ld, Npad, c->P, c->dT, NB, G, g, d->blkpart, c->dAlpha, st));
+  GPX_CHECK(launch_uv_blk(d->SU, Npad, Npad, c->P, c->dT, NB, G, g, d->blkpart, c->dAlpha, st, 1));
   GPX_NCCL(g_nccl.AllReduce(c->dAlpha, c->dAlpha, (size_t)Npad * c->P, ncclDouble, ncclSum, d->comm, st));
   c->eval_launches += 3;
   // ---- K^-1 = U U^T over the owned k-range with the fused gradient epilogue ------------------------------------------
@@ -343,7 +359,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
   {
     GemmParams pl = gemm_defaults();
     pl.mode = GEMM_LAUUM;
-    pl.A = c->S; pl.lda = ld; pl.B = c->S; pl.ldb = ld; pl.C = nullptr; pl.ldc = ld;
+    pl.A = d->SU; pl.lda = Npad; pl.B = d->SU; pl.ldb = Npad; pl.C = nullptr; pl.ldc = Npad; pl.k_local = 1;
     pl.K = (int)Npad; pl.nt = nt;
     pl.XsT = c->dXsT; pl.sq = c->dsq; pl.alpha = c->dAlpha; pl.ldx = Npad;
     pl.N = (int)c->N; pl.P = c->P; pl.partials = c->partials; pl.kinv_out = nullptr;
@@ -357,7 +373,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
     memset(&f, 0, sizeof(f));
     f.partials = c->partials; f.ntiles = (long)nt * nt; f.nl = nl;
     f.logdet_part = c->logdet_part; f.nt = nt;
-    f.T = c->dT; f.ld = ld; f.N = c->N; f.P = c->P; f.kp = c->kp; f.res = d->raw;
+    f.T = c->dT; f.ld = Npad; f.N = c->N; f.P = c->P; f.kp = c->kp; f.res = d->raw;
     GPX_CHECK(launch_finalize_raw(f, st));
     c->eval_launches++;
   }

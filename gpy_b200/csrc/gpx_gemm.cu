@@ -124,7 +124,7 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   } else {
     nkt = p.tri == 1 ? (c + 1) : (p.tri == 2 ? (r + 1) : p.K / TILE);   // tri 1: B lower triangular, 2: A lower triangular
   }
-  const double* Aptr = p.A + (p.map_A ? mapped_offset(p, r) : (long)r * TILE);
+  const double* Aptr = p.A + (p.map_A ? mapped_offset(p, r) : (p.loc_A ? loc_tile(r, p.own_G, p.own_blk) : (long)r) * TILE);
   const double* Bptr = p.B + (p.map_B ? mapped_offset(p, c) : (long)c * TILE);
   const long lda = p.lda, ldb = p.ldb;
   const int nslab = nkt * (TILE / KSLAB);
@@ -153,7 +153,9 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
       if (it >= STAGES) mbar_wait(&empty[s], (n & 1) ^ 1);
       if (lane == 0) mbar_arrive_expect_tx(&full[s], 2 * KSLAB * TILE * 8);
       __syncwarp();
-      const long k = (long)(MODE == GEMM_LAUUM ? kseq_tile(p, kq, it >> 3) : (it >> 3)) * TILE + (it & 7) * KSLAB + kc;
+      long kt = MODE == GEMM_LAUUM ? kseq_tile(p, kq, it >> 3) : (it >> 3);
+      if (MODE == GEMM_LAUUM && p.k_local) kt = loc_tile((int)kt, p.k_G, p.k_blk);
+      const long k = kt * TILE + (it & 7) * KSLAB + kc;
       bulk_g2s(dst_base + s * SLAB_DOUBLES, src_base + k * ld, TILE * 8, &full[s]);
     }
     return;
@@ -167,7 +169,8 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   if (MODE == GEMM_UPDATE) {
     // C -= A B^T  ==  C + (-A) B^T : the accumulators start from the old C tile (loads overlap the pipeline fill),
     // the A fragments are negated on the way in, and the epilogue is store-only.
-    const double* Ct = p.C + (p.map_C ? mapped_offset(p, r) : (long)r * TILE) + (long)c * TILE * p.ldc;
+    const double* Ct = p.C + (p.map_C ? mapped_offset(p, r) : (p.loc_C ? loc_tile(r, p.own_G, p.own_blk) : (long)r) * TILE) +
+                       (long)c * TILE * p.ldc;
 #pragma unroll
     for (int mb = 0; mb < 8; mb++)
 #pragma unroll
@@ -208,7 +211,8 @@ __device__ __forceinline__ void gemm_nt_body(const GemmParams& p) {
   // ================= epilogues ===============================================================================
   if (MODE != GEMM_LAUUM) {
     decode_tile<MODE>(p, r, c);
-    double* Ct = p.C + (p.map_C ? mapped_offset(p, r) : (long)r * TILE) + (long)c * TILE * p.ldc;
+    double* Ct = p.C + (p.map_C ? mapped_offset(p, r) : (p.loc_C ? loc_tile(r, p.own_G, p.own_blk) : (long)r) * TILE) +
+                 (long)c * TILE * p.ldc;
 #pragma unroll
     for (int mb = 0; mb < 8; mb++) {
       const int i = wm * 64 + mb * 8 + g;

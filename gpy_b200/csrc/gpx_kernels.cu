@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
   const int tid = threadIdx.x;
   const int il = tid & (TILE - 1), half = tid >> 7;
   const long gi = (long)rt * TILE + il;
-  double* outp = p.out + gi + ((long)ct * TILE + half * 64) * p.ld;
+  double* outp = p.out + (p.loc_rows ? loc_tile(rt, p.own_G, p.own_blk) * TILE + il : gi) + ((long)ct * TILE + half * 64) * p.ld;
 
   if (p.sym && rt < ct) {  // strictly-upper tile of the factor workspace: the inverse-factor region starts at zero
 #pragma unroll 8
@@ -592,13 +592,15 @@ int launch_fw_panel(const double* Pb, long ldp, long rows, int nb, const double*
 // =================================================================================================================
 __global__ void __launch_bounds__(256) utv_kernel(const double* __restrict__ U, long ld, long n, int P,
                                                   const double* __restrict__ Y /*[P][ld]*/, double* __restrict__ T,
-                                                  int own_G, int own_g, long own_cols) {
+                                                  int own_G, int own_g, long own_cols, int local_cols) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long col = (long)blockIdx.x * 8 + warp;
   if (col >= n) return;
   if (own_G > 1 && ((col / own_cols) % own_G) != own_g) return;   // column block owned by another rank
   const long kend = (col / TILE + 1) * TILE;  // zeros below the diagonal inside the diagonal tile
-  const double* u = U + col * ld;
+  // memory-distributed layout: U holds only the owned column blocks, block kb at local slot kb / G
+  const long lcol = (local_cols && own_G > 1) ? ((col / own_cols) / own_G) * own_cols + col % own_cols : col;
+  const double* u = U + lcol * ld;
   double acc[MAX_P];
 #pragma unroll
   for (int q = 0; q < MAX_P; q++) acc[q] = 0.0;
@@ -686,7 +688,8 @@ int launch_row_dot(const double* A, long lda, long rows_pad, long ncols, int P, 
 // multi-GPU: a = U t restricted to the column blocks this rank owns; one partial per (row tile, column block)
 __global__ void __launch_bounds__(TILE) uv_partial_blk_kernel(const double* __restrict__ U, long ld, long n, int P,
                                                               const double* __restrict__ T, long blk, int G, int g,
-                                                              double* __restrict__ part /*[nblk][P][ld]*/) {
+                                                              double* __restrict__ part /*[nblk][P][ld]*/, int local_cols,
+                                                              long ldp) {
   const long row = (long)blockIdx.x * TILE + threadIdx.x;
   const long kb = blockIdx.y;
   double acc[MAX_P];
@@ -695,51 +698,56 @@ __global__ void __launch_bounds__(TILE) uv_partial_blk_kernel(const double* __re
   const long k0 = kb * blk, k1 = k0 + blk;
   if ((kb % G) == g && k1 > (long)blockIdx.x * TILE) {   // U(row, k) = 0 for k before the row's tile start
     const long kbeg = k0 > (long)blockIdx.x * TILE ? k0 : (long)blockIdx.x * TILE;
+    const long koff = local_cols ? (kb / G) * blk - k0 : 0;   // owned column block kb sits at local slot kb / G
 #pragma unroll 8
     for (long k = kbeg; k < k1; k++) {
-      const double x = U[row + k * ld];
+      const double x = U[row + (k + koff) * ld];
 #pragma unroll
       for (int q = 0; q < MAX_P; q++)
-        if (q < P) acc[q] = fma(x, T[(long)q * ld + k], acc[q]);
+        if (q < P) acc[q] = fma(x, T[(long)q * ldp + k], acc[q]);
     }
   }
 #pragma unroll
   for (int q = 0; q < MAX_P; q++)
-    if (q < P) part[((long)kb * P + q) * ld + row] = acc[q];
+    if (q < P) part[((long)kb * P + q) * ldp + row] = acc[q];
 }
 
 int launch_uv_blk(const double* U, long ld, long n, int P, const double* T, long blk, int G, int g, double* part,
-                  double* out, cudaStream_t st) {
+                  double* out, cudaStream_t st, int local_cols) {
   const int nblk = (int)(n / blk);
   dim3 grid((unsigned)(n / TILE), nblk);
-  uv_partial_blk_kernel<<<grid, TILE, 0, st>>>(U, ld, n, P, T, blk, G, g, part);
+  uv_partial_blk_kernel<<<grid, TILE, 0, st>>>(U, ld, n, P, T, blk, G, g, part, local_cols, ld);
   GPX_CUDA(cudaGetLastError());
   uv_reduce_kernel<<<(unsigned)((ld * P + 255) / 256), 256, 0, st>>>(part, ld, P, nblk, out);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }
 
-// multi-GPU: after the all-gather of the panel chunks, write block column k of S from the chunks: rows below the
-// diagonal block that this rank owns (L panel) and, on the rank that owns COLUMN block k, all rows above it (U(:,k)).
-__global__ void copyback_kernel(double* __restrict__ S, long ld, const double* __restrict__ Pbuf, long NB, int nbt,
-                                int G, int g, long npr, int k, int nt) {
+// multi-GPU (memory-distributed layout): after the all-gather of the panel chunks every rank files its share of block
+// column k: the rows BELOW the diagonal block that it owns go into its row-owned workspace SL (the L panel), and the rank
+// that owns COLUMN block k stores all rows up to and including the diagonal block (= U(:, k), with U_kk from the owner's
+// chunk) in its column-owned U storage SU, at local column slot k / G.
+__global__ void copyback_kernel(double* __restrict__ SL, long ldl, double* __restrict__ SU, long ldu,
+                                const double* __restrict__ Pbuf, long NB, int nbt, int G, int g, long npr, int k, int nt) {
   const int r = blockIdx.y;                 // row tile
   const int R = r / nbt;
-  if (R == k) return;
-  const bool want = (R > k) ? ((R % G) == g) : ((k % G) == g);
+  const bool below = R > k;
+  const bool want = below ? ((R % G) == g) : ((k % G) == g);
   if (!want) return;
   const long pos = (long)(R % G) * npr + R / G;
   const double* src = Pbuf + pos * NB * NB + (long)(r % nbt) * TILE;
-  double* dst = S + (long)r * TILE + (long)k * NB * ld;
+  double* dst = below ? SL + loc_tile(r, G, nbt) * TILE + (long)k * NB * ldl
+                      : SU + (long)r * TILE + (long)(k / G) * NB * ldu;
+  const long ldd = below ? ldl : ldu;
   const int m = threadIdx.x & (TILE - 1);
   for (long cc = (long)blockIdx.x * 2 + (threadIdx.x >> 7); cc < NB; cc += (long)gridDim.x * 2)
-    dst[m + cc * ld] = src[m + cc * NB];
+    dst[m + cc * ldd] = src[m + cc * NB];
 }
 
-int launch_copyback(double* S, long ld, const double* Pbuf, long NB, int G, int g, long npr, int k, int nt,
-                    cudaStream_t st) {
-  dim3 grid(32, nt);
-  copyback_kernel<<<grid, 256, 0, st>>>(S, ld, Pbuf, NB, (int)(NB / TILE), G, g, npr, k, nt);
+int launch_copyback(double* SL, long ldl, double* SU, long ldu, const double* Pbuf, long NB, int G, int g, long npr, int k,
+                    int nt, cudaStream_t st) {
+  dim3 grid(8, nt);
+  copyback_kernel<<<grid, 256, 0, st>>>(SL, ldl, SU, ldu, Pbuf, NB, (int)(NB / TILE), G, g, npr, k, nt);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }
@@ -774,8 +782,8 @@ int launch_finalize_raw(const FinalizeParams& f, cudaStream_t st) {
 }
 
 int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st, int own_G,
-               int own_g, long own_cols) {
-  utv_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(U, ld, n, P, Y, T, own_G, own_g, own_cols);
+               int own_g, long own_cols, int local_cols) {
+  utv_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(U, ld, n, P, Y, T, own_G, own_g, own_cols, local_cols);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

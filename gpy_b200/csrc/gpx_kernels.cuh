@@ -15,6 +15,7 @@ struct KBuildParams {
   double diag_add;                     // noise + jitter (sym mode)
   const double* diag_vec;              // optional per-point noise variances added on the diagonal as well (sym mode)
   int own_G, own_g, own_blk;           // multi-GPU: only row tiles with ((rt / own_blk) % own_G) == own_g (0 = all)
+  int loc_rows;                        // multi-GPU: `out` holds only the owned block rows (row tile rt at loc_tile(rt, ..))
   KernParams kp;
 };
 
@@ -48,15 +49,15 @@ int launch_fw_block(const double* Tm, int nb, const double* yres, long ld, int P
 int launch_fw_panel(const double* Pb, long ldp, long rows, int nb, const double* t, long ld, int P, double* yres,
                     cudaStream_t st);
 int launch_utv(const double* U, long ld, long n, int P, const double* Y, double* T, cudaStream_t st, int own_G = 0,
-               int own_g = 0, long own_cols = 1);
+               int own_g = 0, long own_cols = 1, int local_cols = 0);
 int launch_uv(const double* U, long ld, long n, int P, const double* T, int ksplit, double* part, double* out,
               cudaStream_t st);
 int launch_finalize(const FinalizeParams& f, cudaStream_t st);
 int launch_finalize_raw(const FinalizeParams& f, cudaStream_t st);
 int launch_uv_blk(const double* U, long ld, long n, int P, const double* T, long blk, int G, int g, double* part,
-                  double* out, cudaStream_t st);
-int launch_copyback(double* S, long ld, const double* Pbuf, long NB, int G, int g, long npr, int k, int nt,
-                    cudaStream_t st);
+                  double* out, cudaStream_t st, int local_cols = 0);
+int launch_copyback(double* SL, long ldl, double* SU, long ldu, const double* Pbuf, long NB, int G, int g, long npr, int k,
+                    int nt, cudaStream_t st);
 int launch_extract(int which, const double* S, long ld, const double* Ldiag, const double* Kinv, const double* alpha,
                    int P, long N, double* out, cudaStream_t st);
 int launch_transpose_pad(const double* in, long n, int p, long ld, double* out, cudaStream_t st);

@@ -20,6 +20,12 @@ def chunk_position(R, G, npr):
     return (R % G) * npr + R // G
 
 
+def local_slot(R, G):
+    """memory-distributed layout (gpx_dist.cu): a rank stores only what it owns; its block row R (R mod G == rank) is its
+    local block row R div G of the row-owned workspace, and column block R of U = L^-T its local column block R div G."""
+    return R // G
+
+
 def block_layout(N, NB, G):
     """(Npad, nblk, npr): the matrix is padded to whole NB-blocks, npr = chunks per rank."""
     Npad = -(-N // NB) * NB

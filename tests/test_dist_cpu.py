@@ -1,5 +1,6 @@
 """CPU tests (gloo, world_size 2) of the multi-GPU host-side logic: the unique-id exchange over torch.distributed, the
-block-cyclic layout helpers, and a NumPy re-enactment of the distributed sweep of gpx_dist.cu in which each rank only
+block-cyclic layout helpers, and a NumPy re-enactment of the distributed sweep of gpx_dist.cu in its MEMORY-DISTRIBUTED
+layout (every rank stores only its block rows of the workspace and its column blocks of U), in which each rank only
 touches the block rows it owns and the all-gather / broadcast / all-reduce steps go through gloo."""
 import os
 import socket
@@ -48,42 +49,47 @@ def _worker(rank, world, port, q):
         nblk = n // NB
         npr = -(-nblk // world)
         own = lambda R: R % world == rank
-        S = np.zeros((n, n))
-        for R in range(nblk):                                         # owned block rows only
+        # memory-distributed storage, as in gpx_dist.cu: SL = the OWNED block rows only (local block row R // G), all columns;
+        # SU = the OWNED column blocks of U = L^-T only (local column block k // G), all rows. Nothing of size n x n per rank.
+        SL = np.zeros((npr * NB, n))
+        SU = np.zeros((n, npr * NB))
+        rows = lambda R: slice(gdist.local_slot(R, world) * NB, (gdist.local_slot(R, world) + 1) * NB)
+        for R in range(nblk):
             if own(R):
-                S[R * NB:(R + 1) * NB] = np.tril(K)[R * NB:(R + 1) * NB]
+                SL[rows(R)] = np.tril(K)[R * NB:(R + 1) * NB]
         P = np.zeros((world * npr, NB, NB))
         for k in range(nblk):
             sl = slice(k * NB, (k + 1) * NB)
             Bc = np.zeros((NB, NB))
             if own(k):
-                L = np.linalg.cholesky(S[sl, sl] + np.tril(S[sl, sl], -1).T)
+                D = SL[rows(k), sl]
+                L = np.linalg.cholesky(D + np.tril(D, -1).T)
                 Li = np.linalg.inv(L)
-                S[sl, sl] = np.tril(L, -1) + np.triu(Li.T)           # diag: lower L (strict) | upper U_kk incl. diagonal
+                SL[rows(k), sl] = np.tril(L, -1) + np.triu(Li.T)      # diag: lower L (strict) | upper U_kk incl. diagonal
                 Ldiag = np.diag(L).copy()
                 Bc[:] = Li
-                P[gdist.chunk_position(k, world, npr)] = Li.T
+                P[gdist.chunk_position(k, world, npr)] = Li.T         # assemble: U_kk into the owner's chunk
                 logdet_local = 2 * np.log(Ldiag).sum()
             else:
                 logdet_local = 0.0
             t = torch.from_numpy(Bc); dist.broadcast(t, src=k % world); Bc = t.numpy()
             for R in range(nblk):
                 if R != k and own(R):
-                    P[gdist.chunk_position(R, world, npr)] = S[R * NB:(R + 1) * NB, sl] @ Bc.T
+                    P[gdist.chunk_position(R, world, npr)] = SL[rows(R), sl] @ Bc.T
             mine = torch.from_numpy(P[rank * npr:(rank + 1) * npr].copy())
             outs = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(outs, mine)
             P = np.concatenate([o_.numpy() for o_ in outs])
             chunk = lambda R: P[gdist.chunk_position(R, world, npr)]
-            for R in range(nblk):                                     # copy-back rules of copyback_kernel
-                if R == k:
-                    continue
-                if (R > k and own(R)) or (R < k and k % world == rank):
-                    S[R * NB:(R + 1) * NB, sl] = chunk(R)
+            for R in range(nblk):                                     # filing rules of copyback_kernel
+                if R > k and own(R):
+                    SL[rows(R), sl] = chunk(R)                        # L panel rows -> row-owned workspace
+                if R <= k and k % world == rank:                      # U(:, k) incl. U_kk -> column-owned storage
+                    SU[R * NB:(R + 1) * NB, rows(k)] = np.triu(chunk(R)) if R == k else chunk(R)
             for c in range(k + 1, nblk):                              # owned rows: [0..k] (inverse region) and [c..] (SYRK)
                 for R in list(range(0, k + 1)) + list(range(c, nblk)):
                     if own(R):
-                        S[R * NB:(R + 1) * NB, c * NB:(c + 1) * NB] -= chunk(R) @ chunk(c).T
+                        SL[rows(R), c * NB:(c + 1) * NB] -= chunk(R) @ chunk(c).T
             if k == 0:
                 ld_acc = 0.0
             ld_acc += logdet_local
@@ -93,12 +99,9 @@ def _worker(rank, world, port, q):
         for k in range(nblk):
             if k % world != rank:
                 continue
-            sl = slice(k * NB, (k + 1) * NB)
-            Ucol = np.zeros((n, NB))
-            Ucol[:k * NB] = S[:k * NB, sl]
-            Ucol[sl] = np.triu(S[sl, sl])
+            Ucol = SU[:, rows(k)]
             Kinv_part += Ucol @ Ucol.T
-            tvec[sl] = Ucol.T @ y
+            tvec[k * NB:(k + 1) * NB] = Ucol.T @ y
         tt = torch.from_numpy(tvec); dist.all_reduce(tt); tvec = tt.numpy()
         kk = torch.from_numpy(Kinv_part); dist.all_reduce(kk)
         ldt = torch.tensor([ld_acc]); dist.all_reduce(ldt)
