@@ -10,8 +10,10 @@ SURVEY.md §8(d) (BASELINE.json configs[1]: N=16384, D=8, fp64, 1xB200).
 `value`  : evaluations/s with X, Y resident in HBM (theta in, (LML, grad) out each step), device-timed.
 `e2e`    : the same metric through the reference-facing plugin API (gpy_b200.GPRegression over the C ABI) with HOST
            buffers: every step copies X and Y host->device and reads (LML, grad) back, inside the timed region.
-`roofline`: dominant kernel = the trailing-update DMMA GEMM; achieved = its algorithmic flops / its CUDA-event time,
-           measured live over the timed steps; peak = fp64 DMMA issue rate measured in the same run.
+`roofline`: dominant kernel = the digit-split int8 GEMM on the tcgen05 tensor cores (trailing update + K^-1); achieved = the
+           int8 tensor operations it issues / its CUDA-event time, measured live over the timed steps; peak = 2 x the
+           measured dense bf16 rate (MEASURED_PEAKS.json). On the fp64 DMMA path (option ozaki = 0, multi-GPU) the kernel
+           is the DMMA GEMM and the peak the DMMA issue rate measured in the same run.
 `cpu_baseline` / `--impl reference`: the reference's own CPU operation sequence (oracle/gpy_oracle.py: same LAPACK/BLAS
            calls incl. the wasted dtrtri, two exp passes, the serial ARD loop compiled from C) on this box's cores.
 """
@@ -102,6 +104,17 @@ class ClockSampler(object):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "power_w_max": float(np.max(power)),
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    """dense bf16 TFLOP/s (sustained) measured by the driver on this pool (MEASURED_PEAKS.json), else the fallback of
+    B200_PROFILING.md (1.4 PFLOP/s sustained) -> (value, source)"""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        return float(mp.get("bf16_tflops_sustained") or mp["bf16_tflops"]), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        return 1400.0, "B200_PROFILING.md fallback (1.4 PFLOP/s sustained bf16)"
 
 
 def dist_env():
@@ -224,7 +237,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = eng.total_launches()
-    dev_ms, upd_ms, upd_flops, lau_ms, lau_flops, kb_ms, kb_bytes = [], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
+    dev_ms, upd_ms, upd_flops, lau_ms, lau_flops, kb_ms, kb_bytes, upd_i8 = [], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
     upd_launches = 0
     barrier()
     t0 = time.perf_counter()
@@ -236,6 +249,7 @@ def run_ours(args):
         upd_ms += st["update_ms"]; upd_flops += st["update_flops"]; upd_launches += st["update_launches"]
         lau_ms += st["lauum_ms"]; lau_flops += st["lauum_flops"]
         kb_ms += st["kbuild_ms"]; kb_bytes += st["kbuild_bytes"]
+        upd_i8 += st.get("update_int8_ops", 0.0)
     barrier()
     wall = time.perf_counter() - t0
     launches = eng.total_launches() - launches0
@@ -293,7 +307,6 @@ def run_ours(args):
 
     if rank == 0:
         peak = eng.measure_fp64_peak()
-        ach = upd_flops / upd_ms * 1e-9 if upd_ms > 0 else 0.0
         cpu = None
         if world == 1 and not args.no_cpu:
             native = ensure_oracle_native()
@@ -307,6 +320,42 @@ def run_ours(args):
                    "parity_vs_gpu": {"lml_abs": abs(lml_c - lml_g),
                                      "grad_rel_max": float(np.max(np.abs(grad_c - grad_g) / np.abs(grad_c)))}}
         nl = D
+        whole = {"whole_eval_tflops_fp64": float(N) ** 3 * args.steps / t_dev * 1e-12,
+                 "whole_eval_frac_of_dmma_peak": float(N) ** 3 * args.steps / t_dev * 1e-12 / (peak * (world if sharded else 1)) if peak else None,
+                 "dmma_peak_tflops": peak,
+                 "kbuild_gbs": kb_bytes / kb_ms * 1e-6 if kb_ms else None,
+                 "share_of_step": upd_ms / (t_dev * 1e3) if t_dev else None,
+                 "launches": (upd_launches / args.steps) if upd_launches else None}
+        if upd_i8 > 0 and upd_ms > 0:
+            # tcgen05 path: the dominant kernel is the int8 digit-split GEMM (trailing update + K^-1 in the same launches).
+            # achieved = int8 tensor operations actually issued (2 per MAC, summed over the digit pairs computed: 36 per
+            # fp64 product with 8 digits, 28 with 7) / CUDA-event time of those launches; peak = 2 x the measured dense bf16
+            # rate of MEASURED_PEAKS.json (kind::i8 issues at exactly twice the kind::f16 rate on this part:
+            # profiles/r02_microbench_tcgen05_i8_width_sweep.txt), the sustained figure because the kernel is timed inside a
+            # long step.
+            mp, src = measured_peaks()
+            i8_peak = 2.0 * mp
+            ach = upd_i8 / upd_ms * 1e-9
+            roofline = {"bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma kind::i8 digit-split GEMM: trailing update + K^-1)",
+                        "achieved": ach, "peak": i8_peak, "unit": "TFLOP/s", "frac": ach / i8_peak,
+                        "unit_note": "int8 tensor operations (2 per multiply-add), not floating point",
+                        "peak_source": "2 x bf16_tflops_sustained of %s" % src,
+                        "fp64_equivalent_tflops": upd_flops / upd_ms * 1e-9,
+                        "algorithmic_flops_per_step": upd_flops / args.steps,
+                        "traffic": None,
+                        "traffic_note": "per-launch DRAM traffic differs launch to launch (16 panels); see profiles/ for the ncu capture",
+                        "grad_from_kinv_ms_per_step": lau_ms / args.steps}
+        else:
+            ach = upd_flops / upd_ms * 1e-9 if upd_ms > 0 else 0.0
+            roofline = {"bound": "tensor", "kernel": "gemm_update_kernel (fp64 DMMA trailing update)",
+                        "achieved": ach if upd_ms > 0 else None, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak if (peak and upd_ms > 0) else None,
+                        "note": None if upd_ms > 0 else "per-kernel event accounting is single-GPU; see whole_eval_*",
+                        "traffic": None,
+                        "peak_source": "fp64 DMMA.8x8x4 issue rate measured in this run (gpx_measure_fp64_peak); "
+                                       "MEASURED_PEAKS.json holds no fp64 entry",
+                        "lauum_tflops": lau_flops / lau_ms * 1e-9 if lau_ms else None}
+        roofline.update(whole)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
@@ -326,26 +375,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int((nl + 3) * 8), "steps": e2e_steps,
                     "device_ms_per_step": float(np.mean(e2e_dev_ms)), "set_XY_host_ms_per_step": float(np.mean(e2e_setxy_ms)),
                     "api": "gpy_b200.GPRegression.set_XY/set_theta -> log_likelihood(), gradient (host ndarrays in/out)"},
-            "roofline": {"bound": "tensor", "kernel": "gemm_update_kernel (fp64 DMMA trailing update)",
-                         "achieved": ach if upd_ms > 0 else None, "peak": peak, "unit": "TFLOP/s",
-                         "frac": ach / peak if (peak and upd_ms > 0) else None,
-                         "note": None if upd_ms > 0 else "per-kernel event accounting is single-GPU; see whole_eval_*",
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 29 outer update
-                         # launches of one evaluation (ncu, profiles/r01_update_kernel_dram_traffic.txt); only valid
-                         # for the configuration it was captured on
-                         "traffic": 1.2127e9 if (N == 16384 and world == 1 and upd_ms > 0) else None,
-                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                         # C tiles read + written once (K = 1024 per launch at this size) + the 16384 x 1024 panel once
-                         "algorithmic_bytes_per_launch": (upd_flops / (2.0 * 128 * 128 * 1024) * 2 * 128 * 128 * 8 / upd_launches
-                                                          + 16384 * 1024 * 8) if (N == 16384 and upd_launches) else None,
-                         "peak_source": "fp64 DMMA.8x8x4 issue rate measured in this run (gpx_measure_fp64_peak); "
-                                        "MEASURED_PEAKS.json holds no fp64 entry",
-                         "launches": (upd_launches / args.steps) if upd_launches else None,
-                         "share_of_step": upd_ms / (t_dev * 1e3) if t_dev else None,
-                         "whole_eval_tflops": float(N) ** 3 * args.steps / t_dev * 1e-12,
-                         "whole_eval_frac": float(N) ** 3 * args.steps / t_dev * 1e-12 / (peak * (world if sharded else 1)) if peak else None,
-                         "lauum_tflops": lau_flops / lau_ms * 1e-9 if lau_ms else None,
-                         "kbuild_gbs": kb_bytes / kb_ms * 1e-6 if kb_ms else None},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

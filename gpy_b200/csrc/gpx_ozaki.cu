@@ -43,6 +43,17 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
+// mbarrier wait with back-off: the polling loop of a waiting warp takes issue slots from the one thread that feeds the tensor
+// core, so the roles that wait for long (epilogue: a whole tile; producer: a free stage) sleep between polls
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -144,13 +155,13 @@ int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t
 // ---------------------------------------------------------------------------------------------------------------
 // one 32-deep k-chunk: the ND (ND + 1) / 2 digit-pair products, exponent group g = s + t in TMEM columns [64 g, 64 g + 64).
 // a_lo = low descriptor word (address field) of digit plane 0 of the A tile in this stage; the B planes follow the 8 A planes.
-template <int ND>
-__device__ __forceinline__ void oz_issue_chunk(uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
+template <int ND, int G_BEG, int G_END>
+__device__ __forceinline__ void oz_issue_groups(uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
   constexpr uint32_t idesc = oz_idesc(OZ_TM, OZ_TN);
   constexpr uint64_t hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);   // LBO, SBO, version
   const uint32_t b_lo = a_lo + (uint32_t)((OZ_S * OZ_A_BYTES) >> 4);
 #pragma unroll
-  for (int g = 0; g < ND; g++) {
+  for (int g = G_BEG; g < G_END; g++) {
 #pragma unroll
     for (int s = 0; s <= g; s++) {
       const uint64_t da = hi | (uint64_t)(a_lo + (uint32_t)(s * (OZ_A_BYTES >> 4)));
@@ -203,7 +214,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
       for (int kc = 0; kc < nkc; kc++, it++) {
         const int st = it % OZ_STAGES;
-        mbar_wait(&empty[st], ((it / OZ_STAGES) & 1) ^ 1);
+        if (p.dbg & 16) mbar_wait(&empty[st], ((it / OZ_STAGES) & 1) ^ 1);
+        else mbar_wait_backoff(&empty[st], ((it / OZ_STAGES) & 1) ^ 1, 64);
         if (p.dbg & 2) { if (lane == 0) mbar_arrive(&full[st]); continue; }
         // complete_tx of a copy may precede the expect_tx below: the phase cannot complete before lane 0's arrival
         unsigned char* dst = ring + st * OZ_STAGE_BYTES;
@@ -222,6 +234,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // k-chunk are straight-line code (template on the digit count).
     if (lane == 0) {
       uint32_t it = 0, tl = 0;
+      bool primed = false;
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
       for (int ti = ti_beg; ti < ti_end; ti++, tl++) {
         const uint32_t t = p.tiles[ti];
@@ -230,18 +243,34 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_after();
         for (int kc = 0; kc < nkc; kc++, it++) {
           const int st = it % OZ_STAGES;
-          mbar_wait(&full[st], (it / OZ_STAGES) & 1);
-          tc_fence_after();
-          if (!(p.dbg & 1)) {
-            const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ_STAGE_BYTES >> 4);
-            const uint32_t acc0 = kc > 0 ? 1u : 0u;
-            switch (nd) {
-              case 8: oz_issue_chunk<8>(taddr, a_lo, acc0); break;
-              case 7: oz_issue_chunk<7>(taddr, a_lo, acc0); break;
-              case 6: oz_issue_chunk<6>(taddr, a_lo, acc0); break;
-              case 5: oz_issue_chunk<5>(taddr, a_lo, acc0); break;
-              default: oz_issue_chunk<4>(taddr, a_lo, acc0); break;
-            }
+          if (!primed) {                          // very first chunk of this CTA; afterwards the wait is done one chunk ahead
+            mbar_wait(&full[st], (it / OZ_STAGES) & 1);
+            tc_fence_after();
+            primed = true;
+          }
+          const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ_STAGE_BYTES >> 4);
+          const uint32_t acc0 = kc > 0 ? 1u : 0u;
+          const bool mma = !(p.dbg & 1);
+          // first part of the chunk's MMAs: they sit in the tensor-core queue while this thread checks the NEXT stage, so
+          // the barrier round trip (try_wait + fence, several hundred clk) no longer opens a gap between two chunks
+          if (mma) switch (nd) {
+            case 8: oz_issue_groups<8, 0, 6>(taddr, a_lo, acc0); break;
+            case 7: oz_issue_groups<7, 0, 5>(taddr, a_lo, acc0); break;
+            case 6: oz_issue_groups<6, 0, 4>(taddr, a_lo, acc0); break;
+            case 5: oz_issue_groups<5, 0, 3>(taddr, a_lo, acc0); break;
+            default: oz_issue_groups<4, 0, 2>(taddr, a_lo, acc0); break;
+          }
+          if (kc + 1 < nkc || ti + 1 < ti_end) {
+            const uint32_t itn = it + 1;
+            mbar_wait(&full[itn % OZ_STAGES], (itn / OZ_STAGES) & 1);
+            tc_fence_after();
+          }
+          if (mma) switch (nd) {
+            case 8: oz_issue_groups<8, 6, 8>(taddr, a_lo, acc0); break;
+            case 7: oz_issue_groups<7, 5, 7>(taddr, a_lo, acc0); break;
+            case 6: oz_issue_groups<6, 4, 6>(taddr, a_lo, acc0); break;
+            case 5: oz_issue_groups<5, 3, 5>(taddr, a_lo, acc0); break;
+            default: oz_issue_groups<4, 2, 4>(taddr, a_lo, acc0); break;
           }
           umma_commit(&empty[st]);                // the stage may be refilled once these MMAs have read it
         }
@@ -256,7 +285,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t t = p.tiles[ti];
       const int r = t & 0xfff, c64 = (t >> 12) & 0x1fff, kind = (t >> 25) & 3;
       const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
-      mbar_wait(tmem_full, tl & 1);
+      if (p.dbg & 8) mbar_wait(tmem_full, tl & 1);
+      else mbar_wait_backoff(tmem_full, tl & 1, 128);
       tc_fence_after();
       double acc[32];
 #pragma unroll

@@ -42,7 +42,8 @@ struct OzParams {
   double* Kinv; long ldk;  // OZ_LAUUM_* target:     Kinv(r, c) (+)= P_r P_c^T   (lower tiles)
   int dig_lo, dig_up;      // digits per operand for Cholesky-part tiles / inverse-part tiles (<= OZ_S)
   int tpc;                 // consecutive tiles per CTA (0 = default)
-  int dbg;                 // measurement only (results invalid): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work
+  int dbg;                 // measurement only: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work (results invalid);
+                           // 8 / 16 = epilogue / producer wait WITHOUT back-off (results valid)
 };
 
 int oz_init();                                                          // driver entry point + kernel attributes
