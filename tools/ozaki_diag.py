@@ -16,11 +16,14 @@ X, Y = synthetic(N, 8)
 th = ("rbf", True, 1.0, np.full(8, np.sqrt(8)), 0.01)
 e = _ffi.Engine(0)
 e.set_data(X, Y)
-for (dbg, ctas, la, dig, label) in [(0, 0, 1, 8, "full"), (0, 0, 0, 8, "full, no look-ahead"), (4, 0, 0, 8, "no epilogue"), (2, 0, 0, 8, "no TMA"),
+CASES = [(0, 0, 1, 8, "full"), (0, 0, 0, 8, "full, no look-ahead"), (4, 0, 0, 8, "no epilogue"), (2, 0, 0, 8, "no TMA"),
                               (6, 0, 0, 8, "no TMA, no epilogue (MMA issue only)"), (1, 0, 0, 8, "no MMA"), (5, 0, 0, 8, "TMA only"),
                               (8, 0, 0, 8, "no look-ahead, epilogue polls without back-off"), (24, 0, 0, 8, "no look-ahead, epilogue + producer poll without back-off"), (0, 132, 1, 8, "132 CTAs"), (0, 296, 1, 8, "296 CTAs (non-persistent-like)"), (0, 0, 1, 7, "inverse part 7 digits"), (0, 0, 1, 6, "inverse part 6 digits"),
-                              (0, 0, 1, 4, "inverse part 4 digits")]:
-    e.set_option("oz_dbg", dbg); e.set_option("oz_ctas", ctas); e.set_option("lookahead", la); e.set_option("oz_dig_up", dig)
+                              (0, 0, 1, 4, "inverse part 4 digits")]
+CASES += [(0, -t, 1, 7, "7 digits, %d tiles per CTA" % t) for t in (1, 2, 8, 16)]
+for (dbg, ctas, la, dig, label) in CASES:
+    e.set_option("oz_dbg", dbg); e.set_option("oz_ctas", max(ctas, 0)); e.set_option("oz_tpc", max(-ctas, 0))
+    e.set_option("lookahead", la); e.set_option("oz_dig_up", dig)
     for rep in range(2):
         try:
             e.exact_eval(*th, max_tries=0)
