@@ -386,6 +386,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# --workload sparse: BASELINE.json configs[4] (SparseGPRegression RBF N=262144 M=4096 D=16), one VarDTC evaluation per step
+# ------------------------------------------------------------------------------------------------------------------
+def run_sparse(args):
+    """One step = one SparseGP.parameters_changed() (GPy/core/sparse_gp.py:76-119: VarDTC bound + all gradients incl. dZ)
+    through gpy_b200.SparseGPRegression over the C ABI. value = device-resident evaluations/s (X, Y in HBM; Z and theta
+    in, bound and gradients out), e2e = the same with X, Y re-uploaded from the host every step."""
+    import torch
+    rank, world, local = dist_env()
+    if world > 1 and rank != 0:
+        return                                   # replicas only: the driver's line comes from rank 0 (row sharding: tools/)
+    torch.cuda.set_device(local)
+    import gpy_b200
+    N, M, D = args.n if args.n != 16384 else 262144, args.m, args.d if args.d != 8 else 16
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.sin(X).sum(1, keepdims=True) / np.sqrt(D) + 0.1 * rng.standard_normal((N, 1))
+    Z = X[rng.permutation(N)[:M]].copy()         # sparse_gp_regression.py:41-43: a random subset of the inputs
+    ls0 = np.full(D, np.sqrt(D))
+    k = gpy_b200.RBF(D, variance=1.0, lengthscale=ls0, ARD=True)
+    m = gpy_b200.SparseGPRegression(X, Y, kernel=k, Z=Z, device=local)
+    eng = m.inference_method.engine
+
+    def step(i, reupload):
+        r = np.random.default_rng(2000 + i)
+        if reupload:
+            m.inference_method.invalidate_data()
+        k.variance.values[...] = 1.0 * (1 + 0.05 * r.uniform(-1, 1))
+        k.lengthscale.values[...] = ls0 * (1 + 0.05 * r.uniform(-1, 1, D))
+        m.likelihood.variance.values[...] = 0.05 * (1 + 0.05 * r.uniform(-1, 1))
+        m.parameters_changed()
+        return m.log_likelihood()
+
+    for w in range(args.warmup):
+        step(-1 - w, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.total_launches()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, False)
+    torch.cuda.synchronize()
+    t_res = time.perf_counter() - t0
+    launches = eng.total_launches() - l0
+    clocks = sampler.stop()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, True)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    flops = 4.0 * N * M * M + 20.0 * M ** 3       # DESIGN.md §7b: tmp, A, dL_dKnm over N M^2 + the M x M algebra
+    peak = eng.measure_fp64_peak()
+    ach = flops * args.steps / t_res * 1e-12
+    cpu = None
+    if not args.no_cpu:
+        from oracle import gpy_oracle as o
+        Ns = min(N, 16384)                         # bounded sample: the first Ns rows, same Z / theta (CPU work is ~ linear in N)
+        ts = time.perf_counter()
+        o.sparse_eval(X[:Ns], Y[:Ns], Z, "rbf", True, 1.0, ls0, 0.05)
+        dt = time.perf_counter() - ts
+        threads, _ = cpu_threads()
+        cpu = {"value": 1.0 / (dt * N / Ns), "unit": "evals/s", "cores": threads, "kind": "port",
+               "sample": "oracle VarDTC (var_dtc.py:66-276 restated) on the first %d of %d rows, same Z and theta: %.1f s, "
+                         "scaled by N/Ns (the N-dependent work is linear in N)" % (Ns, N, dt), "seconds_sample": dt}
+    line = {"metric": "SparseGPRegression VarDTC bound+gradient evals/sec (fp64) at N=%d M=%d D=%d" % (N, M, D),
+            "value": args.steps / t_res, "unit": "evals/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "SparseGPRegression RBF ARD N=%d M=%d D=%d (BASELINE.json configs[4])" % (N, M, D),
+                       "l2": "inputs larger than L2: psi1 = K(X, Z) is %.1f GB and is rebuilt every step" % (8.0 * N * M / 1e9),
+                       "timing": "host clock around K steps with a device synchronize on both sides (one process)"},
+            "gpu_launches": int(launches),
+            "e2e": {"value": args.steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + Z.nbytes),
+                    "d2h_bytes_per_step": int((D + 3 + M * D) * 8),
+                    "api": "gpy_b200.SparseGPRegression.parameters_changed() with the data re-uploaded every step"},
+            "roofline": {"bound": "tensor", "kernel": "gemm_panel_kernel (fp64 DMMA, the three N M^2 products)", "achieved": ach,
+                         "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
+                         "algorithmic_flops_per_step": flops,
+                         "peak_source": "fp64 DMMA issue rate measured in this run"},
+            "cpu_baseline": cpu, "clocks": clocks, "lml_last": float(m.log_likelihood())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -395,11 +480,16 @@ def main():
     ap.add_argument("--size", "--n", dest="n", type=int, default=16384, help="number of data points N")
     ap.add_argument("--d", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="exact", choices=["exact", "sparse"],
+                    help="exact = BASELINE.json configs[1] (the metric); sparse = configs[4] (VarDTC, N=262144 M=4096 D=16)")
+    ap.add_argument("--m", type=int, default=4096, help="inducing points (sparse workload)")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: shard ONE evaluation over the GPUs (default) or run independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sparse":
+        run_sparse(args)
     else:
         run_ours(args)
 

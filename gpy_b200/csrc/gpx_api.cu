@@ -55,6 +55,7 @@ static void free_data(gpx_ctx* c) {
   for (double** mp : {&c->dYres, &c->dTfw}) { if (*mp) cudaFree(*mp); *mp = nullptr; }
   c->oz_steps.clear();
   c->oz_ready = false;
+  c->oz_lists_ready = false;
 }
 
 static long pick_nb(const gpx_ctx* c) {
@@ -159,6 +160,18 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "oz_ctas")) { c->oz_ctas = (int)std::max<int64_t>(0, value); return 0; }
   if (!strcmp(name, "oz_dbg")) { c->oz_dbg = (int)value; return 0; }
   if (!strcmp(name, "oz_tpc")) { c->oz_tpc = (int)std::max<int64_t>(0, value); return 0; }
+  if (!strcmp(name, "oz_wide")) {
+    if ((value ? 1 : 0) != c->oz_wide && c->oz_ready) {   // the tile lists are per tile shape: rebuild at the next evaluation
+      GPX_CUDA(cudaSetDevice(c->device));
+      GPX_CUDA(cudaStreamSynchronize(c->st));
+      if (c->oz_tiles) cudaFree(c->oz_tiles);
+      c->oz_tiles = nullptr;
+      c->oz_steps.clear();
+      c->oz_lists_ready = false;
+    }
+    c->oz_wide = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(name, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
   GPX_FAIL("unknown option");
 }
@@ -283,25 +296,31 @@ static bool oz_wanted(const gpx_ctx* c) {
 }
 
 // tiles in bands of 8 row tiles x 16 column tiles (64 wide): the ~148 tiles in flight share 8 A panels and 16 B panels in L2
+// (column tiles: cw per 128 columns — two 64-wide tiles for the one-pass kernel, one 128-wide tile for the two-pass kernel)
 template <class Valid, class Emit>
-static void oz_banded(const std::vector<int>& rows, int c64_beg, int c64_end, Valid valid, Emit emit) {
+static void oz_banded(const std::vector<int>& rows, int ct_beg, int ct_end, int cw, Valid valid, Emit emit) {
   for (size_t b = 0; b < rows.size(); b += 8)
-    for (int cc = c64_beg; cc < c64_end; cc += 16)
+    for (int cc = ct_beg; cc < ct_end; cc += 8 * cw)
       for (size_t i = b; i < std::min(rows.size(), b + 8); i++)
-        for (int c64 = cc; c64 < std::min(c64_end, cc + 16); c64++)
-          if (valid(rows[i], c64 / 2)) emit(rows[i], c64);
+        for (int ct = cc; ct < std::min(ct_end, cc + 8 * cw); ct++)
+          if (valid(rows[i], ct / cw)) emit(rows[i], ct);
 }
 
 static int oz_prepare(gpx_ctx* c) {
-  if (c->oz_ready) return 0;
   const long Npad = c->Npad, NB = pick_nb(c);
   const int nt = (int)(Npad / TILE);
   if (nt >= 4096) GPX_FAIL("matrix too large for the tile encoding");
-  GPX_CHECK(oz_planes_alloc(c->ozp[0], Npad, NB));
-  GPX_CHECK(oz_planes_alloc(c->ozp[1], Npad, NB));
-  if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)Npad * Npad * 8));
-  GPX_CUDA(cudaMalloc(&c->dYres, (size_t)MAX_P * Npad * 8));
-  GPX_CUDA(cudaMalloc(&c->dTfw, (size_t)MAX_P * Npad * 8));
+  if (!c->oz_ready) {
+    GPX_CHECK(oz_planes_alloc(c->ozp[0], Npad, NB));
+    GPX_CHECK(oz_planes_alloc(c->ozp[1], Npad, NB));
+    if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)Npad * Npad * 8));
+    GPX_CUDA(cudaMalloc(&c->dYres, (size_t)MAX_P * Npad * 8));
+    GPX_CUDA(cudaMalloc(&c->dTfw, (size_t)MAX_P * Npad * 8));
+    c->oz_ready = true;
+    c->oz_lists_ready = false;
+  }
+  if (c->oz_lists_ready) return 0;
+  const int cw = c->oz_wide ? 1 : 2;   // column tiles per 128 columns: one 128-wide tile or two 64-wide tiles
   std::vector<uint32_t> tiles;
   c->oz_steps.clear();
   for (long o = 0; o < Npad; o += NB) {
@@ -313,8 +332,8 @@ static int oz_prepare(gpx_ctx* c) {
       std::vector<int> rows;
       for (int r = 0; r < kt1; r++) rows.push_back(r);
       for (int r = cbeg; r < nt; r++) rows.push_back(r);
-      oz_banded(rows, 2 * cbeg, 2 * cend, [&](int r, int cc) { return r < kt1 || cc <= r; },
-                [&](int r, int c64) { tiles.push_back(oz_tile(r, c64, OZ_UPDATE, r < kt1 ? 1 : 0)); });
+      oz_banded(rows, cw * cbeg, cw * cend, cw, [&](int r, int cc) { return r < kt1 || cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, r < kt1 ? 1 : 0)); });
     };
     st.u1_off = (int)tiles.size();
     if (kt1 < nt) emit_update(kt1, kt1 + next_nbt);
@@ -328,8 +347,8 @@ static int oz_prepare(gpx_ctx* c) {
     {   // K^-1(r, c) (+)= P_r P_c^T for c <= r < kt1: rows of block k see their first contribution at this step
       std::vector<int> rows;
       for (int r = 0; r < kt1; r++) rows.push_back(r);
-      oz_banded(rows, 0, 2 * kt1, [&](int r, int cc) { return cc <= r; },
-                [&](int r, int c64) { tiles.push_back(oz_tile(r, c64, r >= kt0 ? OZ_LAUUM_SET : OZ_LAUUM_ACC, 1)); });
+      oz_banded(rows, 0, cw * kt1, cw, [&](int r, int cc) { return cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, r >= kt0 ? OZ_LAUUM_SET : OZ_LAUUM_ACC, 1)); });
     }
     st.u2_n = (int)tiles.size() - st.u2_off;
     st.u2_up = count_up(st.u2_off, st.u2_n);
@@ -337,7 +356,7 @@ static int oz_prepare(gpx_ctx* c) {
   }
   GPX_CUDA(cudaMalloc(&c->oz_tiles, tiles.size() * sizeof(uint32_t)));
   GPX_CUDA(cudaMemcpy(c->oz_tiles, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  c->oz_ready = true;
+  c->oz_lists_ready = true;
   return 0;
 }
 
@@ -452,13 +471,14 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
           memset(&op, 0, sizeof(op));
           op.tiles = c->oz_tiles + off; op.ntiles = ntl; op.nkc = (int)(nb / OZ_KC);
           op.scale = pl.scale; op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
-          op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg;
+          op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg; op.wide = c->oz_wide;
           op.tpc = c->oz_ctas > 0 ? (ntl + c->oz_ctas - 1) / c->oz_ctas : c->oz_tpc;
-          const double flops = (double)ntl * 2.0 * OZ_TM * OZ_TN * (double)nb;
+          const int tn = c->oz_wide ? 2 * OZ_TN : OZ_TN;
+          const double flops = (double)ntl * 2.0 * OZ_TM * tn * (double)nb;
           const int nup = part == 0 ? os.u1_up : (oz >= 2 ? os.u2_up : os.u2_upd_up);
           const int du = c->oz_dig_up;
           c->stats.update_int8_ops += ((double)nup * (du * (du + 1) / 2) + (double)(ntl - nup) * (OZ_S * (OZ_S + 1) / 2)) * 2.0 *
-                                      OZ_TM * OZ_TN * (double)nb;
+                                      OZ_TM * tn * (double)nb;
           const int h = rec.begin(PH_UPDATE, flops);
           GPX_CHECK(launch_oz_gemm(pl, op, c->num_sms, sm));
           rec.end(h);

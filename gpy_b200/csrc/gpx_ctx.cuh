@@ -62,8 +62,10 @@ struct gpx_ctx {
   int oz_ctas = 0;             // option "oz_ctas": >0 = that many CTAs sharing the tile list evenly (persistent-style); 0 = default chunking
   int oz_tpc = 0;              // option "oz_tpc": consecutive tiles per CTA (0 = default 4)
   int oz_dbg = 0;              // measurement-only kernel variants (OzParams::dbg)
+  int oz_wide = 0;             // option "oz_wide": 1 = two-pass kernel with 128 x 128 tiles, 0 = one-pass kernel with 128 x 64 tiles
   int num_sms = 148;
-  bool oz_ready = false;       // planes, K^-1 buffer and tile lists allocated for (Npad, NB)
+  bool oz_ready = false;       // planes and K^-1 buffer allocated for (Npad, NB)
+  bool oz_lists_ready = false; // tile lists built for (Npad, NB, oz_wide)
   gpx::OzPlanes ozp[2];        // digit planes of the current / next panel (look-ahead double buffer)
   uint32_t* oz_tiles = nullptr;
   double* dYres = nullptr;     // [P][Npad] running right-hand side of the forward substitution carried along the sweep

@@ -330,6 +330,203 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// 2b. the two-pass variant: 128 x 128 output tiles, tcgen05.mma 128 x 128 x 32.
+// At N = 64 the tensor core re-reads the 4 KB A plane for every 2 KB B plane and the 128 B/clk shared-memory read port
+// caps it at 2/3 of its rate (48 clk instead of 32 per MMA, tools/microbench_ozaki_pattern.cu); at N = 128 it runs at the
+// full 8192 MAC/clk. Eight exponent groups x 128 columns do not fit the 512 TMEM columns, so a tile is computed in two
+// passes over K: first the low-order groups 4..7 (26 digit pairs, all planes), drained into fp64 registers, then the
+// high-order groups 0..3 (10 pairs, planes 0..3 only). Operand traffic per output element is 1.5x that of the one-pass
+// kernel (24 instead of 16 plane-tile loads per 128 x 128 x 32), the MMA time 2/3.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int OZ2_TN = 128;
+constexpr int OZ2_STAGES = 3;
+constexpr int OZ2_PLANE = OZ_TM * OZ_KC;                          // 4096 bytes: one digit plane of a 128-row tile, one k-chunk
+constexpr int OZ2_STAGE_BYTES = 2 * OZ_S * OZ2_PLANE;             // 65536: up to 8 A planes + 8 B planes
+constexpr int OZ2_SMEM = OZ2_STAGES * OZ2_STAGE_BYTES + 1024 + 256;
+
+// groups [G_BEG, G_END) of one k-chunk; group g accumulates in TMEM columns [(g - G_BASE) * 128, +128)
+template <int G_BEG, int G_END, int G_BASE>
+__device__ __forceinline__ void oz2_issue_groups(uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
+  constexpr uint32_t idesc = oz_idesc(OZ_TM, OZ2_TN);
+  constexpr uint64_t hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+  const uint32_t b_lo = a_lo + (uint32_t)((OZ_S * OZ2_PLANE) >> 4);
+#pragma unroll
+  for (int g = G_BEG; g < G_END; g++) {
+#pragma unroll
+    for (int s = 0; s <= g; s++) {
+      const uint64_t da = hi | (uint64_t)(a_lo + (uint32_t)(s * (OZ2_PLANE >> 4)));
+      const uint64_t db = hi | (uint64_t)(b_lo + (uint32_t)((g - s) * (OZ2_PLANE >> 4)));
+      umma_i8(taddr + (uint32_t)((g - G_BASE) * OZ2_TN), da, db, idesc, s > 0 ? 1u : acc0);
+    }
+  }
+}
+// one k-chunk of a pass in two parts (the caller checks the next stage's barrier in between)
+template <int PART>
+__device__ __forceinline__ void oz2_issue_pass(bool low, int nd, uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
+  if (low) {   // groups 4 .. nd-1
+    if (PART == 0) {
+      switch (nd) {
+        case 8: oz2_issue_groups<4, 7, 4>(taddr, a_lo, acc0); break;
+        case 7: oz2_issue_groups<4, 6, 4>(taddr, a_lo, acc0); break;
+        case 6: oz2_issue_groups<4, 5, 4>(taddr, a_lo, acc0); break;
+        default: break;
+      }
+    } else {
+      switch (nd) {
+        case 8: oz2_issue_groups<7, 8, 4>(taddr, a_lo, acc0); break;
+        case 7: oz2_issue_groups<6, 7, 4>(taddr, a_lo, acc0); break;
+        case 6: oz2_issue_groups<5, 6, 4>(taddr, a_lo, acc0); break;
+        default: oz2_issue_groups<4, 5, 4>(taddr, a_lo, acc0); break;   // nd == 5
+      }
+    }
+  } else {     // groups 0 .. 3 (nd >= 4 always)
+    if (PART == 0) oz2_issue_groups<0, 3, 0>(taddr, a_lo, acc0);
+    else oz2_issue_groups<3, 4, 0>(taddr, a_lo, acc0);
+  }
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + OZ2_STAGES * OZ2_STAGE_BYTES);
+  uint64_t* empty = full + OZ2_STAGES;
+  uint64_t* tmem_full = empty + OZ2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < OZ2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, OZ_EPI_WARPS);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapA);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = *tmem_slot;
+  const int nkc = p.nkc;
+  const int ti_beg = blockIdx.x * p.tpc, ti_end = min(p.ntiles, ti_beg + p.tpc);
+
+  if (warp == 0) {
+    // ================= TMA producer =================================================================================
+    uint32_t it = 0;
+    for (int ti = ti_beg; ti < ti_end; ti++) {
+      const uint32_t t = p.tiles[ti];
+      const int r = t & 0xfff, c = (t >> 12) & 0x1fff;
+      const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+      for (int pass = nd > 4 ? 0 : 1; pass < 2; pass++) {
+        const int npl = pass == 0 ? nd : 4;        // low-order groups need every plane, groups 0..3 only planes 0..3
+        for (int kc = 0; kc < nkc; kc++, it++) {
+          const int st = it % OZ2_STAGES;
+          mbar_wait_backoff(&empty[st], ((it / OZ2_STAGES) & 1) ^ 1, 64);
+          if (p.dbg & 2) { if (lane == 0) mbar_arrive(&full[st]); continue; }
+          unsigned char* dst = ring + st * OZ2_STAGE_BYTES;
+          if (lane < npl) {
+            tma_load_4d(dst + lane * OZ2_PLANE, &mapA, 0, r * (OZ_TM / 8), kc, lane, &full[st]);
+            tma_load_4d(dst + (OZ_S + lane) * OZ2_PLANE, &mapA, 0, c * (OZ2_TN / 8), kc, lane, &full[st]);
+          }
+          if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)npl * 2 * OZ2_PLANE);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) ======================================================================
+    if (lane == 0) {
+      uint32_t it = 0, hs = 0;
+      bool primed = false;
+      const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
+      const bool mma = !(p.dbg & 1);
+      for (int ti = ti_beg; ti < ti_end; ti++) {
+        const uint32_t t = p.tiles[ti];
+        const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+        for (int pass = nd > 4 ? 0 : 1; pass < 2; pass++, hs++) {
+          mbar_wait(tmem_empty, (hs & 1) ^ 1);   // the epilogue has drained the previous pass out of TMEM
+          tc_fence_after();
+          for (int kc = 0; kc < nkc; kc++, it++) {
+            const int st = it % OZ2_STAGES;
+            if (!primed) {
+              mbar_wait(&full[st], (it / OZ2_STAGES) & 1);
+              tc_fence_after();
+              primed = true;
+            }
+            const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ2_STAGE_BYTES >> 4);
+            const uint32_t acc0 = kc > 0 ? 1u : 0u;
+            if (mma) oz2_issue_pass<0>(pass == 0, nd, taddr, a_lo, acc0);
+            if (kc + 1 < nkc || pass == 0 || ti + 1 < ti_end) {   // next stage's barrier, hidden behind the queued MMAs
+              const uint32_t itn = it + 1;
+              mbar_wait(&full[itn % OZ2_STAGES], (itn / OZ2_STAGES) & 1);
+              tc_fence_after();
+            }
+            if (mma) oz2_issue_pass<1>(pass == 0, nd, taddr, a_lo, acc0);
+            umma_commit(&empty[st]);
+          }
+          umma_commit(tmem_full);
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps: TMEM lane quarter = warp % 4, 64 of the 128 columns each =======================
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    uint32_t hs = 0;
+    for (int ti = ti_beg; ti < ti_end; ti++) {
+      const uint32_t t = p.tiles[ti];
+      const int r = t & 0xfff, c = (t >> 12) & 0x1fff, kind = (t >> 25) & 3;
+      const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+      double acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; j++) acc[j] = 0.0;
+      for (int pass = nd > 4 ? 0 : 1; pass < 2; pass++, hs++) {
+        mbar_wait_backoff(tmem_full, hs & 1, 128);
+        tc_fence_after();
+        const int gbase = pass == 0 ? 4 : 0, gtop = pass == 0 ? nd : 4;
+        for (int g = ((p.dbg & 4) ? gbase : gtop) - 1; g >= gbase; g--) {   // smallest magnitude first (pass 0 before pass 1)
+          const double sc = __longlong_as_double((long long)(1023 - 7 * g) << 52);   // 2^(-7 g)
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - gbase) * OZ2_TN + h * 64 + half * 32), v);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              acc[half * 32 + j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, sc, acc[half * 32 + j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+      }
+      if (p.dbg & 4) continue;
+      const long gi = (long)r * OZ_TM + q * 32 + lane;
+      const long gj0 = (long)c * OZ2_TN + h * 64;
+      const double si = p.scale[gi];
+      if (kind == OZ_UPDATE) {
+        double* C = p.S + gi + gj0 * p.lds;
+#pragma unroll
+        for (int j = 0; j < 64; j++) C[(long)j * p.lds] -= acc[j] * (si * __ldg(p.scale + gj0 + j));
+      } else {
+        double* C = p.Kinv + gi + gj0 * p.ldk;
+        if (kind == OZ_LAUUM_ACC) {
+#pragma unroll
+          for (int j = 0; j < 64; j++) C[(long)j * p.ldk] += acc[j] * (si * __ldg(p.scale + gj0 + j));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; j++) C[(long)j * p.ldk] = acc[j] * (si * __ldg(p.scale + gj0 + j));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -346,6 +543,7 @@ int oz_init() {
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   GPX_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+  GPX_CUDA(cudaFuncSetAttribute(oz_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM));
   return 0;
 }
 
@@ -383,7 +581,8 @@ int launch_oz_gemm(const OzPlanes& pl, const OzParams& p_in, int num_sms, cudaSt
   OzParams p = p_in;
   if (p.tpc <= 0) p.tpc = std::max(1, std::min(4, p.ntiles / std::max(1, num_sms)));   // default: 4 tiles per CTA when there is enough work
   const int grid = (p.ntiles + p.tpc - 1) / p.tpc;
-  oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(pl.mapA, pl.mapB, p);
+  if (p.wide) oz_gemm2_kernel<<<grid, OZ_THREADS, OZ2_SMEM, st>>>(pl.mapA, p);
+  else oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(pl.mapA, pl.mapB, p);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -42,6 +42,7 @@ struct OzParams {
   double* Kinv; long ldk;  // OZ_LAUUM_* target:     Kinv(r, c) (+)= P_r P_c^T   (lower tiles)
   int dig_lo, dig_up;      // digits per operand for Cholesky-part tiles / inverse-part tiles (<= OZ_S)
   int tpc;                 // consecutive tiles per CTA (0 = default)
+  int wide;                // 1: 128 x 128 tiles (two-pass kernel, column tile index in 128-column units), 0: 128 x 64 tiles
   int dbg;                 // measurement only: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work (results invalid);
                            // 8 / 16 = epilogue / producer wait WITHOUT back-off (results valid)
 };
