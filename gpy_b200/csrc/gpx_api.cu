@@ -877,8 +877,13 @@ static int ensure_staging(gpx_ctx* c) {
 int gpx_get(gpx_ctx* c, int which, double* out) {
   if (!c || !out) GPX_FAIL("null argument");
   if (!c->have_eval) GPX_FAIL("no successful gpx_exact_eval to fetch results from");
-  if (c->dist && which != GPX_GET_ALPHA) GPX_FAIL("only alpha can be fetched in multi-GPU mode (the factor is distributed)");
   GPX_CUDA(cudaSetDevice(c->device));
+  if (c->dist && which == GPX_GET_L) {   // collective: every rank calls it and receives the whole factor
+    memset(out, 0, (size_t)c->N * c->N * 8);
+    return dist_get_L(c, out);
+  }
+  if (c->dist && which != GPX_GET_ALPHA)
+    GPX_FAIL("sharded mode: alpha and L (collective) can be fetched; K^-1 / dL_dK / K stay distributed or are rebuilt by the caller");
   cudaStream_t st = c->st;
   const long N = c->N, ld = c->Npad;
   if (which == GPX_GET_ALPHA) {

@@ -92,6 +92,7 @@ GemmParams gemm_defaults();
 int dist_set_data(gpx_ctx* c, const double* X, int64_t N, int D, const double* Y, int P);
 int dist_exact_eval(gpx_ctx* c, double extra_jitter);
 void dist_free(gpx_ctx* c);
+int dist_get_L(gpx_ctx* c, double* out);                                       // collective: sharded woodbury_chol
 long dist_block(const gpx_ctx* c);
 const double* dist_U(const gpx_ctx* c, long* ld);                               // sharded: column-owned U storage                                             // NB of the sharded layout (0: none)
 int dist_world(const gpx_ctx* c, int* rank, int* nranks);                       // (0, 1) without a communicator

@@ -129,6 +129,36 @@ void dist_free(gpx_ctx* c) {
   d->Bc = d->Bc2 = d->blkpart = d->SU = nullptr;
 }
 
+// Collective gpx_get(GPX_GET_L) on a sharded factor (Posterior.woodbury_chol, posterior.py:21-77): block row by block row the
+// owner extracts its rows of L into a staging block, broadcasts it, and every rank copies it into its own host matrix
+// (N x N column-major). N x NB doubles of device staging; nothing of size N^2 on any device.
+int dist_get_L(gpx_ctx* c, double* out) {
+  DistState* d = c->dist;
+  const long N = c->N, Npad = c->Npad, NB = d->NB;
+  cudaStream_t st = c->st;
+  double* stage = nullptr;
+  GPX_CUDA(cudaMalloc(&stage, (size_t)NB * Npad * 8));
+  int rc = 0;
+  for (long R = 0; R < d->nblk && rc == 0; R++) {
+    const long grow0 = R * NB;
+    if (grow0 >= N) break;
+    const long ncols = std::min(N, grow0 + NB);            // L is lower triangular: columns beyond the block row are zero
+    if (R % d->G == d->rank)
+      rc = launch_extract_L_rows(c->S, d->ldl, (R / d->G) * NB, c->Ldiag, grow0, NB, ncols, stage, st);
+    if (rc == 0 && g_nccl.Broadcast(stage, stage, (size_t)NB * ncols, ncclDouble, (int)(R % d->G), d->comm, st) != ncclSuccess) {
+      gpx::set_error("ncclBroadcast failed in the sharded gpx_get");
+      rc = -1;
+    }
+    const long nrows = std::min(NB, N - grow0);
+    if (rc == 0 && cudaMemcpy2DAsync(out + grow0, (size_t)N * 8, stage, (size_t)NB * 8, (size_t)nrows * 8, (size_t)ncols,
+                                     cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = -1;   // the staging block is reused by the next block row
+  }
+  cudaFree(stage);
+  c->total_launches += (d->nblk + d->G - 1) / d->G;
+  return rc;
+}
+
 long dist_block(const gpx_ctx* c) { return c->dist ? c->dist->NB : 0; }
 
 // the column-owned U = L^-T storage of a sharded context (predict): Npad x (npr NB), leading dimension Npad

@@ -886,6 +886,28 @@ __global__ void extract_kernel(int which, const double* __restrict__ S, long ld,
   out[i + j * N] = v;
 }
 
+// sharded factor: rows [R NB, (R+1) NB) of L out of the OWNER's row-owned workspace (local row offset lrow0) into a dense
+// NB x ncols staging block (leading dimension NB): strict block-lower straight from the workspace, diagonal tiles from Ldiag
+__global__ void extract_L_rows_kernel(const double* __restrict__ SL, long ldl, long lrow0, const double* __restrict__ Ldiag,
+                                      long grow0, long NB, long ncols, double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // row inside the block row
+  const long j = blockIdx.y;                                     // global column
+  if (i >= NB || j >= ncols) return;
+  const long gi = grow0 + i, ti = gi / TILE, tj = j / TILE;
+  double v = 0.0;
+  if (ti > tj) v = SL[lrow0 + i + j * ldl];
+  else if (ti == tj) v = Ldiag[ti * TILE * TILE + (gi % TILE) + (j % TILE) * TILE];
+  out[i + j * NB] = v;
+}
+
+int launch_extract_L_rows(const double* SL, long ldl, long lrow0, const double* Ldiag, long grow0, long NB, long ncols,
+                          double* out, cudaStream_t st) {
+  dim3 grid((unsigned)((NB + 127) / 128), (unsigned)ncols);
+  extract_L_rows_kernel<<<grid, 128, 0, st>>>(SL, ldl, lrow0, Ldiag, grow0, NB, ncols, out);
+  GPX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_extract(int which, const double* S, long ld, const double* Ldiag, const double* Kinv, const double* alpha,
                    int P, long N, double* out, cudaStream_t st) {
   dim3 grid((unsigned)((N + 255) / 256), (unsigned)N);

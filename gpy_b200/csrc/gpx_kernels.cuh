@@ -58,6 +58,8 @@ int launch_uv_blk(const double* U, long ld, long n, int P, const double* T, long
                   double* out, cudaStream_t st, int local_cols = 0);
 int launch_copyback(double* SL, long ldl, double* SU, long ldu, const double* Pbuf, long NB, int G, int g, long npr, int k,
                     int nt, cudaStream_t st);
+int launch_extract_L_rows(const double* SL, long ldl, long lrow0, const double* Ldiag, long grow0, long NB, long ncols,
+                          double* out, cudaStream_t st);
 int launch_extract(int which, const double* S, long ld, const double* Ldiag, const double* Kinv, const double* alpha,
                    int P, long N, double* out, cudaStream_t st);
 int launch_transpose_pad(const double* in, long n, int p, long ld, double* out, cudaStream_t st);

@@ -26,6 +26,7 @@ def test_two_gpu_sharded_evaluation_matches_oracle():
         grad_rel = float(f[f.index("grad") + 2])
         assert lml_abs <= 1e-8 and grad_rel <= 1e-6, l
         assert float(f[f.index("predict") + 1]) <= 1e-7, l
+        assert float(f[f.index("L") + 2]) <= 1e-10, l          # the sharded woodbury_chol, gathered collectively
 
 
 def test_two_gpu_row_sharded_sparse_matches_oracle():

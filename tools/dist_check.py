@@ -25,6 +25,8 @@ def main():
             if N <= 6000:
                 l0, g0, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, noise)
                 al = eng.get("alpha")
+                Lsh = eng.get("L")                  # collective: the sharded factor gathered block row by block row
+                lerr = np.max(np.abs(Lsh - res["L"])) / np.max(np.abs(res["L"]))
                 # sharded prediction (collective): mean from the replicated alpha, variance all-reduced over the ranks
                 Xn = np.random.default_rng(N).uniform(-3, 3, (9, D))
                 ko = o.StationaryOracle(kind, D, var, ls, ARD)
@@ -33,9 +35,9 @@ def main():
                 mu0f, c0f = o.raw_predict(ko, X, res["L"], res["alpha"], Xn, full_cov=True)
                 mu2, c2 = eng.predict(Xn, full_cov=True)
                 perr = max(np.max(np.abs(mu1 - mu0)), np.max(np.abs(np.ravel(v1) - np.ravel(v0))), np.max(np.abs(c2 - c0f)))
-                msg = "lml abs %.2e grad rel %.2e alpha rel %.2e predict %.2e" % (
+                msg = "lml abs %.2e grad rel %.2e alpha rel %.2e predict %.2e L rel %.2e" % (
                     abs(lml - l0), np.max(np.abs(g - g0) / np.abs(g0)),
-                    np.max(np.abs(al - res["alpha"])) / np.max(np.abs(res["alpha"])), perr)
+                    np.max(np.abs(al - res["alpha"])) / np.max(np.abs(res["alpha"])), perr, lerr)
             elif os.environ.get("GPX_DIST_VERIFY") and kind == "rbf":
                 # parity at sizes the CPU oracle cannot reach: the sharded result against the single-GPU engine
                 msg = "lml %.6f" % lml
