@@ -160,6 +160,8 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "oz_ctas")) { c->oz_ctas = (int)std::max<int64_t>(0, value); return 0; }
   if (!strcmp(name, "oz_dbg")) { c->oz_dbg = (int)value; return 0; }
   if (!strcmp(name, "oz_tpc")) { c->oz_tpc = (int)std::max<int64_t>(0, value); return 0; }
+  if (!strcmp(name, "oz_sched")) { c->oz_sched = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "oz_reserve")) { c->oz_reserve = (int)std::max<int64_t>(0, std::min<int64_t>(value, 64)); return 0; }
   if (!strcmp(name, "oz_wide")) {
     if ((value ? 1 : 0) != c->oz_wide && c->oz_ready) {   // the tile lists are per tile shape: rebuild at the next evaluation
       GPX_CUDA(cudaSetDevice(c->device));
@@ -420,8 +422,18 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
       }
     }
     if (nbt == nt) break;  // single block: done
+    // tcgen05 schedule (option "oz_sched", default): the persistent U2(k-1) leaves a few SMs free, on which the serial
+    // diagonal-block chain D(k) runs meanwhile (side stream); the panel GEMM Pn(k), which needs the whole machine for half a
+    // millisecond, is queued on the MAIN stream behind U2(k-1) instead of fighting it for SM slots.
+    const bool sched2 = oz && la && c->oz_sched;
+    cudaStream_t sp = sched2 ? sm : ss;   // stream of assemble / panel / split
+    if (sched2) {
+      GPX_CHECK(sync_event(c, evi++, &ev));
+      GPX_CUDA(cudaEventRecord(ev, ss));
+      GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
+    }
     // ---- Pn(k): P = S(:, block) * Linv_kk^T; rows of the diagonal block get U_kk ------------------------------
-    GPX_CHECK(launch_assemble(Sblk, ld, (int)nb, Pb + o, Npad, c->Tm, ss));
+    GPX_CHECK(launch_assemble(Sblk, ld, (int)nb, Pb + o, Npad, c->Tm, sp));
     c->eval_launches++;
     {
       GemmParams pp = gemm_defaults();
@@ -430,7 +442,7 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
       pp.B = c->Tm; pp.ldb = nb;
       pp.C = Pb; pp.ldc = Npad;
       pp.K = (int)nb; pp.nt = nt; pp.skip0 = kt0; pp.skip1 = kt1; pp.tri = 1;
-      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), ss));
+      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt), sp));
       c->eval_launches++;
     }
     auto copy_back = [&]() -> int {   // the panel rows take their final place in S (U block column above, L panel below)
@@ -445,10 +457,14 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
     // reads block column k of S, so on the tcgen05 path the copy-back leaves the critical chain (after the hand-over)
     if (!oz) GPX_CHECK(copy_back());
     if (oz) {   // digit planes + row exponents of this panel (all rows: U block column | U_kk | Cholesky panel)
-      GPX_CHECK(launch_oz_split(Pb, Npad, nb, c->ozp[kblk & 1], ss));
+      GPX_CHECK(launch_oz_split(Pb, Npad, nb, c->ozp[kblk & 1], sp));
       c->eval_launches++;
     }
-    if (la) {
+    if (sched2) {          // the side stream (copy-back, forward substitution, later D(k+1)) continues after the panel
+      GPX_CHECK(sync_event(c, evi++, &ev));
+      GPX_CUDA(cudaEventRecord(ev, sm));
+      GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+    } else if (la) {
       GPX_CHECK(sync_event(c, evi++, &ev));
       GPX_CUDA(cudaEventRecord(ev, ss));
       GPX_CUDA(cudaStreamWaitEvent(sm, ev, 0));
@@ -473,6 +489,11 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
           op.scale = pl.scale; op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
           op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg; op.wide = c->oz_wide;
           op.tpc = c->oz_ctas > 0 ? (ntl + c->oz_ctas - 1) / c->oz_ctas : c->oz_tpc;
+          if (sched2 && c->oz_ctas <= 0 && c->oz_tpc <= 0) {
+            // persistent: U1 on every SM (nothing else can run before it is done), U2 on all but the reserved SMs
+            const int ctas = std::max(1, c->num_sms - (part == 1 ? c->oz_reserve : 0));
+            op.tpc = (ntl + ctas - 1) / ctas;
+          }
           const int tn = c->oz_wide ? 2 * OZ_TN : OZ_TN;
           const double flops = (double)ntl * 2.0 * OZ_TM * tn * (double)nb;
           const int nup = part == 0 ? os.u1_up : (oz >= 2 ? os.u2_up : os.u2_upd_up);

@@ -25,9 +25,13 @@ CASES += [(1000 + d, c, l, g, "WIDE " + lab) for (d, c, l, g, lab) in CASES if l
     "full", "full, no look-ahead", "no epilogue", "no TMA", "no TMA, no epilogue (MMA issue only)", "no MMA", "TMA only",
     "inverse part 7 digits", "inverse part 6 digits", "7 digits, 2 tiles per CTA", "7 digits, 8 tiles per CTA",
     "no look-ahead, next-stage wait between MMA parts", "MMA issue only, next-stage wait between MMA parts")]
+CASES += [(3000 + r, 0, 1, 7, "WIDE 7 digits, panel on the main stream, %d SMs reserved" % r) for r in (0, 2, 4, 8, 16)]
+CASES += [(2000, 0, 1, 7, "narrow 7 digits, panel on the main stream, 4 SMs reserved")]
 for (dbg, ctas, la, dig, label) in CASES:
-    e.set_option("oz_wide", 1 if dbg >= 1000 else 0)
-    dbg = dbg % 1000
+    e.set_option("oz_wide", 1 if (1000 <= dbg < 2000 or dbg >= 3000) else 0)
+    e.set_option("oz_sched", 1 if dbg >= 2000 else 0)
+    e.set_option("oz_reserve", dbg - 3000 if dbg >= 3000 else 4)
+    dbg = dbg % 1000 if dbg < 2000 else 0
     e.set_option("oz_dbg", dbg); e.set_option("oz_ctas", max(ctas, 0)); e.set_option("oz_tpc", max(-ctas, 0))
     e.set_option("lookahead", la); e.set_option("oz_dig_up", dig)
     for rep in range(2):
