@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 
@@ -59,6 +60,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -227,14 +233,15 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) ======================================================================
+    // ================= MMA issuer ====================================================================================
     // The issue loop must sustain one tcgen05.mma per ~48 clk from ONE thread: descriptors are not rebuilt per instruction
     // (the first version spent ~100 clk of uniform-datapath arithmetic per MMA and ran at half the shared-memory bound);
     // the low descriptor word of plane s is the stage's base word + s * (plane bytes >> 4), the 36 instructions of a
-    // k-chunk are straight-line code (template on the digit count).
-    if (lane == 0) {
+    // k-chunk are straight-line code (template on the digit count). The whole warp executes the loop convergently and an
+    // elected lane issues: inside an `if (lane == 0)` region the compiler can lose track of warp-uniformity and then
+    // feeds every MMA operand through R2UR from vector registers (measured: 1.3x slower issue).
+    {   // the WHOLE warp runs the (warp-uniform) control flow; one elected lane issues MMAs and commits
       uint32_t it = 0, tl = 0;
-      bool primed = false;
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
       for (int ti = ti_beg; ti < ti_end; ti++, tl++) {
         const uint32_t t = p.tiles[ti];
@@ -243,39 +250,24 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_after();
         for (int kc = 0; kc < nkc; kc++, it++) {
           const int st = it % OZ_STAGES;
-          const bool ahead = (p.dbg & 32) != 0;   // experimental: check the NEXT stage between two parts of the chunk's MMAs
-          if (!ahead || !primed) {
-            mbar_wait(&full[st], (it / OZ_STAGES) & 1);
-            tc_fence_after();
-            primed = true;
-          }
+          mbar_wait(&full[st], (it / OZ_STAGES) & 1);
+          tc_fence_after();
           const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ_STAGE_BYTES >> 4);
           const uint32_t acc0 = kc > 0 ? 1u : 0u;
-          const bool mma = !(p.dbg & 1);
-          // first part of the chunk's MMAs: they sit in the tensor-core queue while this thread checks the NEXT stage, so
-          // the barrier round trip (try_wait + fence, several hundred clk) no longer opens a gap between two chunks
-          if (mma) switch (nd) {
-            case 8: oz_issue_groups<8, 0, 6>(taddr, a_lo, acc0); break;
-            case 7: oz_issue_groups<7, 0, 5>(taddr, a_lo, acc0); break;
-            case 6: oz_issue_groups<6, 0, 4>(taddr, a_lo, acc0); break;
-            case 5: oz_issue_groups<5, 0, 3>(taddr, a_lo, acc0); break;
-            default: oz_issue_groups<4, 0, 2>(taddr, a_lo, acc0); break;
+          if (elect_one()) {
+            if (!(p.dbg & 1)) {
+              if (nd == 8) oz_issue_groups<8, 0, 8>(taddr, a_lo, acc0);
+              else if (nd == 7) oz_issue_groups<7, 0, 7>(taddr, a_lo, acc0);
+              else if (nd == 6) oz_issue_groups<6, 0, 6>(taddr, a_lo, acc0);
+              else if (nd == 5) oz_issue_groups<5, 0, 5>(taddr, a_lo, acc0);
+              else oz_issue_groups<4, 0, 4>(taddr, a_lo, acc0);
+            }
+            umma_commit(&empty[st]);              // the stage may be refilled once these MMAs have read it
           }
-          if (ahead && (kc + 1 < nkc || ti + 1 < ti_end)) {
-            const uint32_t itn = it + 1;
-            mbar_wait(&full[itn % OZ_STAGES], (itn / OZ_STAGES) & 1);
-            tc_fence_after();
-          }
-          if (mma) switch (nd) {
-            case 8: oz_issue_groups<8, 6, 8>(taddr, a_lo, acc0); break;
-            case 7: oz_issue_groups<7, 5, 7>(taddr, a_lo, acc0); break;
-            case 6: oz_issue_groups<6, 4, 6>(taddr, a_lo, acc0); break;
-            case 5: oz_issue_groups<5, 3, 5>(taddr, a_lo, acc0); break;
-            default: oz_issue_groups<4, 2, 4>(taddr, a_lo, acc0); break;
-          }
-          umma_commit(&empty[st]);                // the stage may be refilled once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(tmem_full);                   // accumulators of this tile complete
+        if (elect_one()) umma_commit(tmem_full);  // accumulators of this tile complete
+        __syncwarp();
       }
     }
   } else {
@@ -361,31 +353,6 @@ __device__ __forceinline__ void oz2_issue_groups(uint32_t taddr, uint32_t a_lo, 
     }
   }
 }
-// one k-chunk of a pass in two parts (the caller checks the next stage's barrier in between)
-template <int PART>
-__device__ __forceinline__ void oz2_issue_pass(bool low, int nd, uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
-  if (low) {   // groups 4 .. nd-1
-    if (PART == 0) {
-      switch (nd) {
-        case 8: oz2_issue_groups<4, 7, 4>(taddr, a_lo, acc0); break;
-        case 7: oz2_issue_groups<4, 6, 4>(taddr, a_lo, acc0); break;
-        case 6: oz2_issue_groups<4, 5, 4>(taddr, a_lo, acc0); break;
-        default: break;
-      }
-    } else {
-      switch (nd) {
-        case 8: oz2_issue_groups<7, 8, 4>(taddr, a_lo, acc0); break;
-        case 7: oz2_issue_groups<6, 7, 4>(taddr, a_lo, acc0); break;
-        case 6: oz2_issue_groups<5, 6, 4>(taddr, a_lo, acc0); break;
-        default: oz2_issue_groups<4, 5, 4>(taddr, a_lo, acc0); break;   // nd == 5
-      }
-    }
-  } else {     // groups 0 .. 3 (nd >= 4 always)
-    if (PART == 0) oz2_issue_groups<0, 3, 0>(taddr, a_lo, acc0);
-    else oz2_issue_groups<3, 4, 0>(taddr, a_lo, acc0);
-  }
-}
-
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
   extern __shared__ unsigned char oz_smem_raw[];
@@ -421,8 +388,8 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
     for (int ti = ti_beg; ti < ti_end; ti++) {
       const uint32_t t = p.tiles[ti];
       const int r = t & 0xfff, c = (t >> 12) & 0x1fff;
-      const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
-      for (int pass = nd > 4 ? 0 : 1; pass < 2; pass++) {
+      const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;   // >= 5 here: both passes always run, so that the stage
+      for (int pass = 0; pass < 2; pass++) {                    // counter stays warp-uniform (descriptors in uniform registers)
         const int npl = pass == 0 ? nd : 4;        // low-order groups need every plane, groups 0..3 only planes 0..3
         for (int kc = 0; kc < nkc; kc++, it++) {
           const int st = it % OZ2_STAGES;
@@ -439,38 +406,43 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
     }
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) ======================================================================
-    if (lane == 0) {
-      uint32_t it = 0, hs = 0;
-      bool primed = false;
+    {   // the WHOLE warp runs the (warp-uniform) control flow; one elected lane issues MMAs and commits
+      uint32_t hs = 0, ph = 0;
+      int st = 0;
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
-      const bool mma = !(p.dbg & 1);
       for (int ti = ti_beg; ti < ti_end; ti++) {
         const uint32_t t = p.tiles[ti];
         const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
-        for (int pass = nd > 4 ? 0 : 1; pass < 2; pass++, hs++) {
+        // the two passes are two copies of the loop (compile-time pass): with a run-time pass variable selecting the MMA
+        // block the compiler keeps the descriptors in vector registers (R2UR per operand, ~1.3x slower issue)
+        auto run_pass = [&](auto pass_tag) {
+          constexpr int pass = decltype(pass_tag)::value;
           mbar_wait(tmem_empty, (hs & 1) ^ 1);   // the epilogue has drained the previous pass out of TMEM
           tc_fence_after();
-          for (int kc = 0; kc < nkc; kc++, it++) {
-            const int st = it % OZ2_STAGES;
-            const bool ahead = (p.dbg & 32) != 0;
-            if (!ahead || !primed) {
-              mbar_wait(&full[st], (it / OZ2_STAGES) & 1);
-              tc_fence_after();
-              primed = true;
-            }
+          for (int kc = 0; kc < nkc; kc++) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
             const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ2_STAGE_BYTES >> 4);
             const uint32_t acc0 = kc > 0 ? 1u : 0u;
-            if (mma) oz2_issue_pass<0>(pass == 0, nd, taddr, a_lo, acc0);
-            if (ahead && (kc + 1 < nkc || pass == 0 || ti + 1 < ti_end)) {   // next stage's barrier, behind the queued MMAs
-              const uint32_t itn = it + 1;
-              mbar_wait(&full[itn % OZ2_STAGES], (itn / OZ2_STAGES) & 1);
-              tc_fence_after();
+            if (elect_one()) {
+              if (!(p.dbg & 1)) {
+                if (pass == 1) oz2_issue_groups<0, 4, 0>(taddr, a_lo, acc0);          // groups 0 .. 3
+                else if (nd == 8) oz2_issue_groups<4, 8, 4>(taddr, a_lo, acc0);       // low-order groups 4 .. nd-1
+                else if (nd == 7) oz2_issue_groups<4, 7, 4>(taddr, a_lo, acc0);
+                else if (nd == 6) oz2_issue_groups<4, 6, 4>(taddr, a_lo, acc0);
+                else oz2_issue_groups<4, 5, 4>(taddr, a_lo, acc0);
+              }
+              umma_commit(&empty[st]);
             }
-            if (mma) oz2_issue_pass<1>(pass == 0, nd, taddr, a_lo, acc0);
-            umma_commit(&empty[st]);
+            __syncwarp();
+            if (++st == OZ2_STAGES) { st = 0; ph ^= 1; }
           }
-          umma_commit(tmem_full);
-        }
+          if (elect_one()) umma_commit(tmem_full);
+          __syncwarp();
+          hs++;
+        };
+        run_pass(std::integral_constant<int, 0>{});
+        run_pass(std::integral_constant<int, 1>{});
       }
     }
   } else {
@@ -484,7 +456,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
       double acc[64];
 #pragma unroll
       for (int j = 0; j < 64; j++) acc[j] = 0.0;
-      for (int pass = nd > 4 ? 0 : 1; pass < 2; pass++, hs++) {
+      for (int pass = 0; pass < 2; pass++, hs++) {
         mbar_wait_backoff(tmem_full, hs & 1, 128);
         tc_fence_after();
         const int gbase = pass == 0 ? 4 : 0, gtop = pass == 0 ? nd : 4;
@@ -584,6 +556,7 @@ int launch_oz_gemm(const OzPlanes& pl, const OzParams& p_in, int num_sms, cudaSt
   // default: 8 narrow / 4 wide tiles per CTA when there is enough work (measured: 1 -> 2 -> 4 -> 8 tiles per CTA = 118 / 104 / 98 / 91 ms)
   if (p.tpc <= 0) p.tpc = std::max(1, std::min(p.wide ? 4 : 8, p.ntiles / std::max(1, num_sms)));
   const int grid = (p.ntiles + p.tpc - 1) / p.tpc;
+  if (p.wide && (p.dig_lo < 5 || p.dig_up < 5)) { set_error("the two-pass kernel needs at least 5 digits"); return -2; }
   if (p.wide) oz_gemm2_kernel<<<grid, OZ_THREADS, OZ2_SMEM, st>>>(pl.mapA, p);
   else oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(pl.mapA, pl.mapB, p);
   GPX_CUDA(cudaGetLastError());

@@ -44,8 +44,7 @@ struct OzParams {
   int tpc;                 // consecutive tiles per CTA (0 = default)
   int wide;                // 1: 128 x 128 tiles (two-pass kernel, column tile index in 128-column units), 0: 128 x 64 tiles
   int dbg;                 // measurement only: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work (results invalid);
-                           // 8 / 16 = epilogue / producer wait WITHOUT back-off, 32 = next-stage wait between two parts of a
-                           // chunk's MMAs (results valid)
+                           // 8 / 16 = epilogue / producer wait WITHOUT back-off (results valid)
 };
 
 int oz_init();                                                          // driver entry point + kernel attributes

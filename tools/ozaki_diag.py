@@ -18,13 +18,12 @@ e = _ffi.Engine(0)
 e.set_data(X, Y)
 CASES = [(0, 0, 1, 8, "full"), (0, 0, 0, 8, "full, no look-ahead"), (4, 0, 0, 8, "no epilogue"), (2, 0, 0, 8, "no TMA"),
                               (6, 0, 0, 8, "no TMA, no epilogue (MMA issue only)"), (1, 0, 0, 8, "no MMA"), (5, 0, 0, 8, "TMA only"),
-                              (32, 0, 0, 8, "no look-ahead, next-stage wait between MMA parts"), (38, 0, 0, 8, "MMA issue only, next-stage wait between MMA parts"), (0, 132, 1, 8, "132 CTAs"), (0, 296, 1, 8, "296 CTAs (non-persistent-like)"), (0, 0, 1, 7, "inverse part 7 digits"), (0, 0, 1, 6, "inverse part 6 digits"),
+                               (0, 132, 1, 8, "132 CTAs"), (0, 296, 1, 8, "296 CTAs (non-persistent-like)"), (0, 0, 1, 7, "inverse part 7 digits"), (0, 0, 1, 6, "inverse part 6 digits"),
                               (0, 0, 1, 4, "inverse part 4 digits")]
 CASES += [(0, -t, 1, 7, "7 digits, %d tiles per CTA" % t) for t in (1, 2, 8, 16)]
 CASES += [(1000 + d, c, l, g, "WIDE " + lab) for (d, c, l, g, lab) in CASES if lab in (
     "full", "full, no look-ahead", "no epilogue", "no TMA", "no TMA, no epilogue (MMA issue only)", "no MMA", "TMA only",
-    "inverse part 7 digits", "inverse part 6 digits", "7 digits, 2 tiles per CTA", "7 digits, 8 tiles per CTA",
-    "no look-ahead, next-stage wait between MMA parts", "MMA issue only, next-stage wait between MMA parts")]
+    "inverse part 7 digits", "inverse part 6 digits", "7 digits, 2 tiles per CTA", "7 digits, 8 tiles per CTA")]
 CASES += [(3000 + r, 0, 1, 7, "WIDE 7 digits, panel on the main stream, %d SMs reserved" % r) for r in (0, 2, 4, 8, 16)]
 CASES += [(2000, 0, 1, 7, "narrow 7 digits, panel on the main stream, 4 SMs reserved")]
 for (dbg, ctas, la, dig, label) in CASES:
