@@ -62,7 +62,7 @@ struct gpx_ctx {
   int oz_ctas = 0;             // option "oz_ctas": >0 = that many CTAs sharing the tile list evenly (persistent-style); 0 = default chunking
   int oz_tpc = 0;              // option "oz_tpc": consecutive tiles per CTA (0 = default 4)
   int oz_dbg = 0;              // measurement-only kernel variants (OzParams::dbg)
-  int oz_sched = 1;            // option "oz_sched": 1 = panel GEMM on the main stream + persistent U2 leaving oz_reserve SMs to the
+  int oz_sched = 0;            // option "oz_sched": 1 = panel GEMM on the main stream + persistent U2 leaving oz_reserve SMs to the
                                // diagonal-block chain; 0 = everything of step k+1 on the side stream, U launches in chunks of tiles
   int oz_reserve = 4;          // SMs left free by the persistent U2 launch for the side stream
   int oz_wide = 1;             // option "oz_wide": 1 = two-pass kernel with 128 x 128 tiles, 0 = one-pass kernel with 128 x 64 tiles

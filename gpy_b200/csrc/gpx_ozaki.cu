@@ -156,6 +156,27 @@ int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t
   return 0;
 }
 
+// apply one thread's row of an output tile to the fp64 target: NCOL columns, leading dimension ld. The loads of a group of 8
+// columns are all issued before the first store: written as `C[j * ld] -= ...` the compiler must assume that a store may
+// alias the next load (ld is a run-time value) and serialises 64 global round trips per thread (~20 us per tile, measured).
+template <int NCOL>
+__device__ __forceinline__ void oz_apply_row(double* __restrict__ C, long ld, const double (&acc)[NCOL], double si,
+                                             const double* __restrict__ scol, int kind) {
+#pragma unroll
+  for (int j0 = 0; j0 < NCOL; j0 += 8) {
+    double old[8];
+    if (kind != OZ_LAUUM_SET) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) old[j] = C[(long)(j0 + j) * ld];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const double v = acc[j0 + j] * (si * __ldg(scol + j0 + j));
+      C[(long)(j0 + j) * ld] = kind == OZ_UPDATE ? old[j] - v : (kind == OZ_LAUUM_ACC ? old[j] + v : v);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 2. the GEMM
 // ---------------------------------------------------------------------------------------------------------------
@@ -301,20 +322,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const long gi = (long)r * OZ_TM + q * 32 + lane;
       const long gj0 = (long)c64 * OZ_TN + h * 32;
       const double si = p.scale[gi];
-      if (kind == OZ_UPDATE) {
-        double* C = p.S + gi + gj0 * p.lds;
-#pragma unroll
-        for (int j = 0; j < 32; j++) C[(long)j * p.lds] -= acc[j] * (si * __ldg(p.scale + gj0 + j));
-      } else {
-        double* C = p.Kinv + gi + gj0 * p.ldk;
-        if (kind == OZ_LAUUM_ACC) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) C[(long)j * p.ldk] += acc[j] * (si * __ldg(p.scale + gj0 + j));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++) C[(long)j * p.ldk] = acc[j] * (si * __ldg(p.scale + gj0 + j));
-        }
-      }
+      if (kind == OZ_UPDATE) oz_apply_row<32>(p.S + gi + gj0 * p.lds, p.lds, acc, si, p.scale + gj0, kind);
+      else oz_apply_row<32>(p.Kinv + gi + gj0 * p.ldk, p.ldk, acc, si, p.scale + gj0, kind);
     }
   }
   tc_fence_before();
@@ -336,6 +345,7 @@ constexpr int OZ2_STAGES = 3;
 constexpr int OZ2_PLANE = OZ_TM * OZ_KC;                          // 4096 bytes: one digit plane of a 128-row tile, one k-chunk
 constexpr int OZ2_STAGE_BYTES = 2 * OZ_S * OZ2_PLANE;             // 65536: up to 8 A planes + 8 B planes
 constexpr int OZ2_SMEM = OZ2_STAGES * OZ2_STAGE_BYTES + 1024 + 256;
+constexpr int OZ2_THREADS = 384;                                   // three warpgroups (setmaxnreg works per warpgroup)
 
 // groups [G_BEG, G_END) of one k-chunk; group g accumulates in TMEM columns [(g - G_BASE) * 128, +128)
 template <int G_BEG, int G_END, int G_BASE>
@@ -353,7 +363,10 @@ __device__ __forceinline__ void oz2_issue_groups(uint32_t taddr, uint32_t a_lo, 
     }
   }
 }
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+// Warp roles: warps 0..7 = epilogue (TMEM lane quarter = warp % 4, column half = warp / 4; two warpgroups that raise their
+// register budget to 224 with setmaxnreg: 64 fp64 accumulators per thread live across the two passes), warp 8 = TMA
+// producer, warp 9 = MMA issuer, warps 10-11 idle (the third warpgroup hands its registers over: 56 each).
+__global__ void __launch_bounds__(OZ2_THREADS, 1)
 oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
   extern __shared__ unsigned char oz_smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -371,7 +384,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
     fence_mbar_init();
     tma_prefetch_desc(&mapA);
   }
-  if (warp == 1) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -382,7 +395,9 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
   const int nkc = p.nkc;
   const int ti_beg = blockIdx.x * p.tpc, ti_end = min(p.ntiles, ti_beg + p.tpc);
 
-  if (warp == 0) {
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 8) {
     // ================= TMA producer =================================================================================
     uint32_t it = 0;
     for (int ti = ti_beg; ti < ti_end; ti++) {
@@ -404,7 +419,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ================= MMA issuer (one thread) ======================================================================
     {   // the WHOLE warp runs the (warp-uniform) control flow; one elected lane issues MMAs and commits
       uint32_t hs = 0, ph = 0;
@@ -445,9 +460,11 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
         run_pass(std::integral_constant<int, 1>{});
       }
     }
+  }
   } else {
     // ================= epilogue warps: TMEM lane quarter = warp % 4, 64 of the 128 columns each =======================
-    const int q = warp & 3, h = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int q = warp & 3, h = warp >> 2;
     uint32_t hs = 0;
     for (int ti = ti_beg; ti < ti_end; ti++) {
       const uint32_t t = p.tiles[ti];
@@ -479,25 +496,13 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
       const long gi = (long)r * OZ_TM + q * 32 + lane;
       const long gj0 = (long)c * OZ2_TN + h * 64;
       const double si = p.scale[gi];
-      if (kind == OZ_UPDATE) {
-        double* C = p.S + gi + gj0 * p.lds;
-#pragma unroll
-        for (int j = 0; j < 64; j++) C[(long)j * p.lds] -= acc[j] * (si * __ldg(p.scale + gj0 + j));
-      } else {
-        double* C = p.Kinv + gi + gj0 * p.ldk;
-        if (kind == OZ_LAUUM_ACC) {
-#pragma unroll
-          for (int j = 0; j < 64; j++) C[(long)j * p.ldk] += acc[j] * (si * __ldg(p.scale + gj0 + j));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 64; j++) C[(long)j * p.ldk] = acc[j] * (si * __ldg(p.scale + gj0 + j));
-        }
-      }
+      if (kind == OZ_UPDATE) oz_apply_row<64>(p.S + gi + gj0 * p.lds, p.lds, acc, si, p.scale + gj0, kind);
+      else oz_apply_row<64>(p.Kinv + gi + gj0 * p.ldk, p.ldk, acc, si, p.scale + gj0, kind);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr));
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -557,7 +562,7 @@ int launch_oz_gemm(const OzPlanes& pl, const OzParams& p_in, int num_sms, cudaSt
   if (p.tpc <= 0) p.tpc = std::max(1, std::min(p.wide ? 4 : 8, p.ntiles / std::max(1, num_sms)));
   const int grid = (p.ntiles + p.tpc - 1) / p.tpc;
   if (p.wide && (p.dig_lo < 5 || p.dig_up < 5)) { set_error("the two-pass kernel needs at least 5 digits"); return -2; }
-  if (p.wide) oz_gemm2_kernel<<<grid, OZ_THREADS, OZ2_SMEM, st>>>(pl.mapA, p);
+  if (p.wide) oz_gemm2_kernel<<<grid, OZ2_THREADS, OZ2_SMEM, st>>>(pl.mapA, p);
   else oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(pl.mapA, pl.mapB, p);
   GPX_CUDA(cudaGetLastError());
   return 0;
