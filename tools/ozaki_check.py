@@ -34,8 +34,8 @@ def main():
             lml0, g0, res = o.eval_lml_grad(X, Y, kind, ARD, var, ls, noise)
             ref = (lml0, g0, res, time.time() - t0)
         out = {}
-        variants = [("fp64 DMMA", dict(ozaki=0)), ("tcgen05 8/8 digits", dict(ozaki=1, oz_dig_up=8)),
-                    ("tcgen05 8/7 digits", dict(ozaki=1, oz_dig_up=7)), ("tcgen05 8/6 digits", dict(ozaki=1, oz_dig_up=6)),
+        variants = [("fp64 DMMA", dict(ozaki=0)), ("tcgen05 narrow 8/8", dict(ozaki=1, oz_dig_up=8, oz_wide=0)),
+                    ("tcgen05 narrow 8/7", dict(ozaki=1, oz_dig_up=7, oz_wide=0)), ("tcgen05 narrow 8/6", dict(ozaki=1, oz_dig_up=6, oz_wide=0)),
                     ("tcgen05 wide 8/8", dict(ozaki=1, oz_dig_up=8, oz_wide=1)), ("tcgen05 wide 8/7", dict(ozaki=1, oz_dig_up=7, oz_wide=1)),
                     ("tcgen05 wide 8/5", dict(ozaki=1, oz_dig_up=5, oz_wide=1))]
         for name, opts in variants:

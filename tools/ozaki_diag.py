@@ -26,6 +26,7 @@ CASES += [(1000 + d, c, l, g, "WIDE " + lab) for (d, c, l, g, lab) in CASES if l
     "inverse part 7 digits", "inverse part 6 digits", "7 digits, 2 tiles per CTA", "7 digits, 8 tiles per CTA")]
 CASES += [(3000 + r, 0, 1, 7, "WIDE 7 digits, panel on the main stream, %d SMs reserved" % r) for r in (0, 2, 4, 8, 16)]
 CASES += [(2000, 0, 1, 7, "narrow 7 digits, panel on the main stream, 4 SMs reserved")]
+NB_CASES = [(nb, t) for nb in (512, 2048) for t in (0, 8)]
 for (dbg, ctas, la, dig, label) in CASES:
     e.set_option("oz_wide", 1 if (1000 <= dbg < 2000 or dbg >= 3000) else 0)
     e.set_option("oz_sched", 1 if dbg >= 2000 else 0)
@@ -41,3 +42,14 @@ for (dbg, ctas, la, dig, label) in CASES:
     st = e.stats()
     print("%-40s total %7.2f ms  sweep %7.2f  update(sum of launches) %7.2f  grad %5.2f  tries %d" % (
         label, st["total_ms"], st["sweep_ms"], st["update_ms"], st["lauum_ms"], st["tries"]), flush=True)
+
+for (nb, tpc) in NB_CASES:      # a fresh context per block size (the panel buffers are sized by it)
+    e2 = _ffi.Engine(0)
+    e2.set_option("nb", nb); e2.set_option("oz_tpc", tpc); e2.set_option("oz_dig_up", 7)
+    e2.set_data(X, Y)
+    for rep in range(2):
+        e2.exact_eval(*th)
+    st = e2.stats()
+    print("%-40s total %7.2f ms  sweep %7.2f  update(sum of launches) %7.2f  grad %5.2f" % (
+        "WIDE 7 digits, NB = %d, tpc %d" % (nb, tpc), st["total_ms"], st["sweep_ms"], st["update_ms"], st["lauum_ms"]), flush=True)
+    e2.close()
