@@ -161,6 +161,7 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "oz_dbg")) { c->oz_dbg = (int)value; return 0; }
   if (!strcmp(name, "oz_tpc")) { c->oz_tpc = (int)std::max<int64_t>(0, value); return 0; }
   if (!strcmp(name, "oz_sched")) { c->oz_sched = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "oz_u0")) { c->oz_u0 = value ? 1 : 0; return 0; }
   if (!strcmp(name, "oz_reserve")) { c->oz_reserve = (int)std::max<int64_t>(0, std::min<int64_t>(value, 64)); return 0; }
   if (!strcmp(name, "oz_wide")) {
     if ((value ? 1 : 0) != c->oz_wide && c->oz_ready) {   // the tile lists are per tile shape: rebuild at the next evaluation
@@ -337,10 +338,27 @@ static int oz_prepare(gpx_ctx* c) {
       oz_banded(rows, cw * cbeg, cw * cend, cw, [&](int r, int cc) { return r < kt1 || cc <= r; },
                 [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, r < kt1 ? 1 : 0)); });
     };
-    st.u1_off = (int)tiles.size();
-    if (kt1 < nt) emit_update(kt1, kt1 + next_nbt);
-    st.u1_n = (int)tiles.size() - st.u1_off;
     auto count_up = [&](int off, int n) { int u = 0; for (int i = off; i < off + n; i++) u += (tiles[i] >> 27) & 1; return u; };
+    // U0: the tiles of the NEXT diagonal block (rows and columns of block k+1): all that D(k+1) waits for
+    st.u0_off = (int)tiles.size();
+    if (kt1 < nt) {
+      std::vector<int> rows;
+      for (int r = kt1; r < kt1 + next_nbt; r++) rows.push_back(r);
+      oz_banded(rows, cw * kt1, cw * (kt1 + next_nbt), cw, [&](int r, int cc) { return cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, 0)); });
+    }
+    st.u0_n = (int)tiles.size() - st.u0_off;
+    st.u0_up = 0;
+    // U1: the rest of block column k+1 (rows above the block and below it)
+    st.u1_off = (int)tiles.size();
+    if (kt1 < nt) {
+      std::vector<int> rows;
+      for (int r = 0; r < kt1; r++) rows.push_back(r);
+      for (int r = kt1 + next_nbt; r < nt; r++) rows.push_back(r);
+      oz_banded(rows, cw * kt1, cw * (kt1 + next_nbt), cw, [&](int r, int cc) { return r < kt1 || cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, r < kt1 ? 1 : 0)); });
+    }
+    st.u1_n = (int)tiles.size() - st.u1_off;
     st.u1_up = count_up(st.u1_off, st.u1_n);
     st.u2_off = (int)tiles.size();
     if (kt1 + next_nbt < nt) emit_update(kt1 + next_nbt, nt);
@@ -379,7 +397,8 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
   cudaStream_t sm = c->st;
   cudaStream_t ss = la ? c->st2 : c->st;
   size_t evi = 0;
-  cudaEvent_t ev;
+  cudaEvent_t ev, u1_done = nullptr;
+  bool u1_pending = false;
   if (la) {  // side stream starts after everything queued so far on the main stream (K build)
     GPX_CHECK(sync_event(c, evi++, &ev));
     GPX_CUDA(cudaEventRecord(ev, sm));
@@ -425,6 +444,10 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
     // tcgen05 schedule (option "oz_sched", default): the persistent U2(k-1) leaves a few SMs free, on which the serial
     // diagonal-block chain D(k) runs meanwhile (side stream); the panel GEMM Pn(k), which needs the whole machine for half a
     // millisecond, is queued on the MAIN stream behind U2(k-1) instead of fighting it for SM slots.
+    if (u1_pending) {   // (oz_u0) the panel of this step needs ALL of its block column updated, not only the diagonal block
+      GPX_CUDA(cudaStreamWaitEvent(ss, u1_done, 0));
+      u1_pending = false;
+    }
     const bool sched2 = oz && la && c->oz_sched;
     cudaStream_t sp = sched2 ? sm : ss;   // stream of assemble / panel / split
     if (sched2) {
@@ -479,9 +502,12 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
     if (oz) {
       const gpx_ctx::OzStep& os = c->oz_steps[kblk];
       const OzPlanes& pl = c->ozp[kblk & 1];
-      for (int part = 0; part < 2; part++) {
-        const int off = part == 0 ? os.u1_off : os.u2_off;
-        const int ntl = part == 0 ? os.u1_n : (oz >= 2 ? os.u2_n : os.u2_upd);
+      // U0 (next diagonal block) | U1 (rest of block column k+1) | U2 (everything else + K^-1 tiles). With option oz_u0 = 0
+      // U0 and U1 are one launch (their lists are adjacent).
+      const bool u0 = c->oz_u0 && la && os.u0_n > 0;
+      for (int part = u0 ? -1 : 0; part < 2; part++) {
+        const int off = part < 0 ? os.u0_off : (part == 0 ? (u0 ? os.u1_off : os.u0_off) : os.u2_off);
+        const int ntl = part < 0 ? os.u0_n : (part == 0 ? (u0 ? os.u1_n : os.u0_n + os.u1_n) : (oz >= 2 ? os.u2_n : os.u2_upd));
         if (ntl > 0) {
           OzParams op;
           memset(&op, 0, sizeof(op));
@@ -491,12 +517,12 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
           op.tpc = c->oz_ctas > 0 ? (ntl + c->oz_ctas - 1) / c->oz_ctas : c->oz_tpc;
           if (sched2 && c->oz_ctas <= 0 && c->oz_tpc <= 0) {
             // persistent: U1 on every SM (nothing else can run before it is done), U2 on all but the reserved SMs
-            const int ctas = std::max(1, c->num_sms - (part == 1 ? c->oz_reserve : 0));
+            const int ctas = std::max(1, c->num_sms - (part == 1 ? c->oz_reserve : 0));   // (part <= 0: every SM)
             op.tpc = (ntl + ctas - 1) / ctas;
           }
           const int tn = c->oz_wide ? 2 * OZ_TN : OZ_TN;
           const double flops = (double)ntl * 2.0 * OZ_TM * tn * (double)nb;
-          const int nup = part == 0 ? os.u1_up : (oz >= 2 ? os.u2_up : os.u2_upd_up);
+          const int nup = part < 0 ? 0 : (part == 0 ? os.u1_up : (oz >= 2 ? os.u2_up : os.u2_upd_up));
           const int du = c->oz_dig_up;
           c->stats.update_int8_ops += ((double)nup * (du * (du + 1) / 2) + (double)(ntl - nup) * (OZ_S * (OZ_S + 1) / 2)) * 2.0 *
                                       OZ_TM * tn * (double)nb;
@@ -506,10 +532,15 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
           c->eval_launches++;
           c->stats.update_launches++;
         }
-        if (part == 0 && la && kt1 < nt) {
+        if (la && kt1 < nt && part == (u0 ? -1 : 0)) {   // the next diagonal block is final: D(k+1) may start on the side stream
           GPX_CHECK(sync_event(c, evi++, &ev));
           GPX_CUDA(cudaEventRecord(ev, sm));
           GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+        }
+        if (u0 && part == 0 && kt1 < nt) {               // block column k+1 is final: the panel GEMM of step k+1 may read it
+          GPX_CHECK(sync_event(c, evi++, &u1_done));
+          GPX_CUDA(cudaEventRecord(u1_done, sm));
+          u1_pending = true;
         }
       }
     } else if (kt1 < nt) {

@@ -62,6 +62,8 @@ struct gpx_ctx {
   int oz_ctas = 0;             // option "oz_ctas": >0 = that many CTAs sharing the tile list evenly (persistent-style); 0 = default chunking
   int oz_tpc = 0;              // option "oz_tpc": consecutive tiles per CTA (0 = default 4)
   int oz_dbg = 0;              // measurement-only kernel variants (OzParams::dbg)
+  int oz_u0 = 1;               // option "oz_u0": update the NEXT diagonal block first (own small launch) so that its factorisation starts
+                               // before the rest of block column k+1 is updated
   int oz_sched = 0;            // option "oz_sched": 1 = panel GEMM on the main stream + persistent U2 leaving oz_reserve SMs to the
                                // diagonal-block chain; 0 = everything of step k+1 on the side stream, U launches in chunks of tiles
   int oz_reserve = 4;          // SMs left free by the persistent U2 launch for the side stream
@@ -73,7 +75,7 @@ struct gpx_ctx {
   uint32_t* oz_tiles = nullptr;
   double* dYres = nullptr;     // [P][Npad] running right-hand side of the forward substitution carried along the sweep
   double* dTfw = nullptr;      // [P][Npad] t = L^-1 y from that substitution (quadratic form of the LML)
-  struct OzStep { int u1_off, u1_n, u2_off, u2_n, u2_upd, u1_up, u2_up, u2_upd_up; };   // U2 list: u2_upd update tiles, then the K^-1 tiles; *_up = inverse-part tiles among them
+  struct OzStep { int u0_off, u0_n, u1_off, u1_n, u2_off, u2_n, u2_upd, u0_up, u1_up, u2_up, u2_upd_up; };   // U0: the next diagonal block only   // U2 list: u2_upd update tiles, then the K^-1 tiles; *_up = inverse-part tiles among them
   std::vector<OzStep> oz_steps;
   bool oz_last = false;        // the last evaluation went through the Ozaki path (K^-1 already stored)
   // ---- composite kernels (gpx_multi.cu): the last evaluation used gpx_exact_eval_multi --------------------------------

@@ -26,8 +26,14 @@ CASES += [(1000 + d, c, l, g, "WIDE " + lab) for (d, c, l, g, lab) in CASES if l
     "inverse part 7 digits", "inverse part 6 digits", "7 digits, 2 tiles per CTA", "7 digits, 8 tiles per CTA")]
 CASES += [(3000 + r, 0, 1, 7, "WIDE 7 digits, panel on the main stream, %d SMs reserved" % r) for r in (0, 2, 4, 8, 16)]
 CASES += [(2000, 0, 1, 7, "narrow 7 digits, panel on the main stream, 4 SMs reserved")]
-NB_CASES = [(nb, t) for nb in (512, 2048) for t in (0, 8)]
+NB_CASES = []
+CASES = [c for c in CASES if c[4].startswith("WIDE") and "panel on the main" not in c[4] and "tiles per CTA" not in c[4]]
+CASES += [(4000, 0, 1, 7, "WIDE 7 digits, without the U0 launch"), (1000, 0, 1, 7, "WIDE 7 digits, with the U0 launch (default)"),
+          (4000, 0, 1, 8, "WIDE 8 digits, without the U0 launch"), (1000, 0, 1, 8, "WIDE 8 digits, with the U0 launch (default)")]
 for (dbg, ctas, la, dig, label) in CASES:
+    e.set_option("oz_u0", 0 if dbg == 4000 else 1)
+    if dbg == 4000:
+        dbg = 1000
     e.set_option("oz_wide", 1 if (1000 <= dbg < 2000 or dbg >= 3000) else 0)
     e.set_option("oz_sched", 1 if dbg >= 2000 else 0)
     e.set_option("oz_reserve", dbg - 3000 if dbg >= 3000 else 4)
