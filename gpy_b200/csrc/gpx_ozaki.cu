@@ -408,7 +408,8 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
         const int npl = pass == 0 ? nd : 4;        // low-order groups need every plane, groups 0..3 only planes 0..3
         for (int kc = 0; kc < nkc; kc++, it++) {
           const int st = it % OZ2_STAGES;
-          mbar_wait_backoff(&empty[st], ((it / OZ2_STAGES) & 1) ^ 1, 64);
+          if (p.dbg & 16) mbar_wait(&empty[st], ((it / OZ2_STAGES) & 1) ^ 1);
+          else mbar_wait_backoff(&empty[st], ((it / OZ2_STAGES) & 1) ^ 1, 64);
           if (p.dbg & 2) { if (lane == 0) mbar_arrive(&full[st]); continue; }
           unsigned char* dst = ring + st * OZ2_STAGE_BYTES;
           if (lane < npl) {
@@ -474,7 +475,8 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
 #pragma unroll
       for (int j = 0; j < 64; j++) acc[j] = 0.0;
       for (int pass = 0; pass < 2; pass++, hs++) {
-        mbar_wait_backoff(tmem_full, hs & 1, 128);
+        if (p.dbg & 8) mbar_wait(tmem_full, hs & 1);
+        else mbar_wait_backoff(tmem_full, hs & 1, 128);
         tc_fence_after();
         const int gbase = pass == 0 ? 4 : 0, gtop = pass == 0 ? nd : 4;
         for (int g = ((p.dbg & 4) ? gbase : gtop) - 1; g >= gbase; g--) {   // smallest magnitude first (pass 0 before pass 1)

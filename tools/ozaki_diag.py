@@ -28,7 +28,8 @@ CASES += [(3000 + r, 0, 1, 7, "WIDE 7 digits, panel on the main stream, %d SMs r
 CASES += [(2000, 0, 1, 7, "narrow 7 digits, panel on the main stream, 4 SMs reserved")]
 NB_CASES = []
 CASES = [c for c in CASES if c[4].startswith("WIDE") and "panel on the main" not in c[4] and "tiles per CTA" not in c[4]]
-CASES += [(4000, 0, 1, 7, "WIDE 7 digits, without the U0 launch"), (1000, 0, 1, 7, "WIDE 7 digits, with the U0 launch (default)"),
+CASES += [(1008, 0, 0, 8, "WIDE no look-ahead, epilogue polls without back-off"), (1024, 0, 0, 8, "WIDE no look-ahead, epilogue + producer poll without back-off"),
+          (4000, 0, 1, 7, "WIDE 7 digits, without the U0 launch"), (1000, 0, 1, 7, "WIDE 7 digits, with the U0 launch (default)"),
           (4000, 0, 1, 8, "WIDE 8 digits, without the U0 launch"), (1000, 0, 1, 8, "WIDE 8 digits, with the U0 launch (default)")]
 for (dbg, ctas, la, dig, label) in CASES:
     e.set_option("oz_u0", 0 if dbg == 4000 else 1)
