@@ -336,10 +336,15 @@ def run_ours(args):
             mp, src = measured_peaks()
             i8_peak = 2.0 * mp
             ach = upd_i8 / upd_ms * 1e-9
-            roofline = {"bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma kind::i8 digit-split GEMM: trailing update + K^-1)",
+            roofline = {"bound": "tensor", "kernel": "oz_gemm2_kernel (tcgen05.mma kind::i8 digit-split GEMM, 128x128x32 MMAs in two "
+                                                      "passes: trailing update + K^-1)",
                         "achieved": ach, "peak": i8_peak, "unit": "TFLOP/s", "frac": ach / i8_peak,
                         "unit_note": "int8 tensor operations (2 per multiply-add), not floating point",
                         "peak_source": "2 x bf16_tflops_sustained of %s" % src,
+                        # for context: the kind::i8 ISSUE rate of this part (8192 MAC/clk/SM, tools/microbench_tcgen05.cu) at the
+                        # SM clock sampled during this run; cuBLAS bf16 itself reaches ~0.73 of the corresponding bf16 issue rate
+                        "frac_of_i8_issue_rate": ach / (2 * 8192 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e-6)
+                        if clocks and clocks.get("sm_mhz") else None,
                         "fp64_equivalent_tflops": upd_flops / upd_ms * 1e-9,
                         "algorithmic_flops_per_step": upd_flops / args.steps,
                         "traffic": None,

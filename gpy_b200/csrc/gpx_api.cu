@@ -286,15 +286,11 @@ static int sync_event(gpx_ctx* c, size_t idx, cudaEvent_t* out) {
 static bool oz_wanted(const gpx_ctx* c) {
   if (c->dist) return false;
   int on = c->ozaki;
-  bool forced = on > 0;
-  if (on < 0) { const char* e = getenv("GPX_OZAKI"); on = e ? atoi(e) : 1; forced = e != nullptr && on > 0; }
+  if (on < 0) { const char* e = getenv("GPX_OZAKI"); on = e ? atoi(e) : 1; }
   if (!on) return false;
   const long NB = pick_nb(c);
-  // Default: from Npad = 8192 on. Below that the evaluation is bound by the serial diagonal-block chain, not by the GEMMs,
-  // and the extra launches of the digit split cost more than the faster tiles save (measured: 0.82x at N = 4096, 1.5x at
-  // 16384). An explicit request (option "ozaki" = 1 / GPX_OZAKI=1) applies wherever there are at least two panels:
-  // a single-block matrix has no panel and stays on the DMMA path.
-  if (!forced && c->Npad < 8192) return false;
+  // wherever there are at least two panels (measured faster than the DMMA path from N = 700 up: 0.97 vs 1.03 ms at 700,
+  // 5.3 vs 5.9 ms at 4096, 64 vs 142 ms at 16384); a single-block matrix has no panel and stays on the DMMA path
   return c->Npad >= 2 * NB && NB % OZ_KC == 0;
 }
 

@@ -572,7 +572,7 @@ def test_composite_kernels_on_the_fused_device_path(N):
     X, Y = o.synthetic(N, D, seed=N)
     k, parts = _composite_case(D)
     eng = _ffi.Engine(0)
-    eng.set_option("ozaki", 1 if N >= 700 else 0)     # below N = 8192 the tcgen05 path is opt-in
+    eng.set_option("ozaki", 1 if N >= 700 else 0)     # N = 150: one panel only, DMMA path with the plain K^-1 store
     m = gpy_b200.GPRegression(X, Y, k, noise_var=0.04, engine=eng)
     lml0, g0, res = o.composite_eval_lml_grad(X, Y, parts, 0.04)
     assert abs(m.log_likelihood() - lml0) <= LML_ATOL
