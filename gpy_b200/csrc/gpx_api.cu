@@ -294,17 +294,6 @@ static bool oz_wanted(const gpx_ctx* c) {
   return c->Npad >= 2 * NB && NB % OZ_KC == 0;
 }
 
-// tiles in bands of 8 row tiles x 16 column tiles (64 wide): the ~148 tiles in flight share 8 A panels and 16 B panels in L2
-// (column tiles: cw per 128 columns — two 64-wide tiles for the one-pass kernel, one 128-wide tile for the two-pass kernel)
-template <class Valid, class Emit>
-static void oz_banded(const std::vector<int>& rows, int ct_beg, int ct_end, int cw, Valid valid, Emit emit) {
-  for (size_t b = 0; b < rows.size(); b += 8)
-    for (int cc = ct_beg; cc < ct_end; cc += 8 * cw)
-      for (size_t i = b; i < std::min(rows.size(), b + 8); i++)
-        for (int ct = cc; ct < std::min(ct_end, cc + 8 * cw); ct++)
-          if (valid(rows[i], ct / cw)) emit(rows[i], ct);
-}
-
 static int oz_prepare(gpx_ctx* c) {
   const long Npad = c->Npad, NB = pick_nb(c);
   const int nt = (int)(Npad / TILE);
@@ -319,57 +308,8 @@ static int oz_prepare(gpx_ctx* c) {
     c->oz_lists_ready = false;
   }
   if (c->oz_lists_ready) return 0;
-  const int cw = c->oz_wide ? 1 : 2;   // column tiles per 128 columns: one 128-wide tile or two 64-wide tiles
   std::vector<uint32_t> tiles;
-  c->oz_steps.clear();
-  for (long o = 0; o < Npad; o += NB) {
-    const long nb = std::min(NB, Npad - o);
-    const int kt0 = (int)(o / TILE), kt1 = kt0 + (int)(nb / TILE);
-    const int next_nbt = kt1 < nt ? (int)(std::min(NB, Npad - (o + nb)) / TILE) : 0;
-    gpx_ctx::OzStep st;
-    auto emit_update = [&](int cbeg, int cend) {   // S(r, c) -= P_r P_c^T, c in [cbeg, cend), r in [0, kt1) U [c, nt)
-      std::vector<int> rows;
-      for (int r = 0; r < kt1; r++) rows.push_back(r);
-      for (int r = cbeg; r < nt; r++) rows.push_back(r);
-      oz_banded(rows, cw * cbeg, cw * cend, cw, [&](int r, int cc) { return r < kt1 || cc <= r; },
-                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, r < kt1 ? 1 : 0)); });
-    };
-    auto count_up = [&](int off, int n) { int u = 0; for (int i = off; i < off + n; i++) u += (tiles[i] >> 27) & 1; return u; };
-    // U0: the tiles of the NEXT diagonal block (rows and columns of block k+1): all that D(k+1) waits for
-    st.u0_off = (int)tiles.size();
-    if (kt1 < nt) {
-      std::vector<int> rows;
-      for (int r = kt1; r < kt1 + next_nbt; r++) rows.push_back(r);
-      oz_banded(rows, cw * kt1, cw * (kt1 + next_nbt), cw, [&](int r, int cc) { return cc <= r; },
-                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, 0)); });
-    }
-    st.u0_n = (int)tiles.size() - st.u0_off;
-    st.u0_up = 0;
-    // U1: the rest of block column k+1 (rows above the block and below it)
-    st.u1_off = (int)tiles.size();
-    if (kt1 < nt) {
-      std::vector<int> rows;
-      for (int r = 0; r < kt1; r++) rows.push_back(r);
-      for (int r = kt1 + next_nbt; r < nt; r++) rows.push_back(r);
-      oz_banded(rows, cw * kt1, cw * (kt1 + next_nbt), cw, [&](int r, int cc) { return r < kt1 || cc <= r; },
-                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, r < kt1 ? 1 : 0)); });
-    }
-    st.u1_n = (int)tiles.size() - st.u1_off;
-    st.u1_up = count_up(st.u1_off, st.u1_n);
-    st.u2_off = (int)tiles.size();
-    if (kt1 + next_nbt < nt) emit_update(kt1 + next_nbt, nt);
-    st.u2_upd = (int)tiles.size() - st.u2_off;
-    st.u2_upd_up = count_up(st.u2_off, st.u2_upd);
-    {   // K^-1(r, c) (+)= P_r P_c^T for c <= r < kt1: rows of block k see their first contribution at this step
-      std::vector<int> rows;
-      for (int r = 0; r < kt1; r++) rows.push_back(r);
-      oz_banded(rows, 0, cw * kt1, cw, [&](int r, int cc) { return cc <= r; },
-                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, r >= kt0 ? OZ_LAUUM_SET : OZ_LAUUM_ACC, 1)); });
-    }
-    st.u2_n = (int)tiles.size() - st.u2_off;
-    st.u2_up = count_up(st.u2_off, st.u2_n);
-    c->oz_steps.push_back(st);
-  }
+  oz_build_lists(Npad, NB, c->oz_wide ? 1 : 2, 1, 0, tiles, c->oz_steps);
   GPX_CUDA(cudaMalloc(&c->oz_tiles, tiles.size() * sizeof(uint32_t)));
   GPX_CUDA(cudaMemcpy(c->oz_tiles, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   c->oz_lists_ready = true;

@@ -75,7 +75,7 @@ struct gpx_ctx {
   uint32_t* oz_tiles = nullptr;
   double* dYres = nullptr;     // [P][Npad] running right-hand side of the forward substitution carried along the sweep
   double* dTfw = nullptr;      // [P][Npad] t = L^-1 y from that substitution (quadratic form of the LML)
-  struct OzStep { int u0_off, u0_n, u1_off, u1_n, u2_off, u2_n, u2_upd, u0_up, u1_up, u2_up, u2_upd_up; };   // U0: the next diagonal block only   // U2 list: u2_upd update tiles, then the K^-1 tiles; *_up = inverse-part tiles among them
+  using OzStep = gpx::OzStep;
   std::vector<OzStep> oz_steps;
   bool oz_last = false;        // the last evaluation went through the Ozaki path (K^-1 already stored)
   // ---- composite kernels (gpx_multi.cu): the last evaluation used gpx_exact_eval_multi --------------------------------

@@ -24,6 +24,9 @@
 #include "gpx_common.cuh"
 #include "gpx_ozaki.cuh"
 
+#include <algorithm>
+#include <vector>
+
 namespace gpx {
 
 constexpr int OZ_STAGES = 4;
@@ -347,20 +350,41 @@ constexpr int OZ2_STAGE_BYTES = 2 * OZ_S * OZ2_PLANE;             // 65536: up t
 constexpr int OZ2_SMEM = OZ2_STAGES * OZ2_STAGE_BYTES + 1024 + 256;
 constexpr int OZ2_THREADS = 384;                                   // three warpgroups (setmaxnreg works per warpgroup)
 
-// groups [G_BEG, G_END) of one k-chunk; group g accumulates in TMEM columns [(g - G_BASE) * 128, +128)
-template <int G_BEG, int G_END, int G_BASE>
-__device__ __forceinline__ void oz2_issue_groups(uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
+// groups [G_BEG, G_END) of one k-chunk, highest group first; group g accumulates in TMEM columns [(g - G_BASE) * 128, +128)
+template <int G, int G_BASE>
+__device__ __forceinline__ void oz2_issue_group(uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
   constexpr uint32_t idesc = oz_idesc(OZ_TM, OZ2_TN);
   constexpr uint64_t hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
   const uint32_t b_lo = a_lo + (uint32_t)((OZ_S * OZ2_PLANE) >> 4);
 #pragma unroll
-  for (int g = G_BEG; g < G_END; g++) {
-#pragma unroll
-    for (int s = 0; s <= g; s++) {
-      const uint64_t da = hi | (uint64_t)(a_lo + (uint32_t)(s * (OZ2_PLANE >> 4)));
-      const uint64_t db = hi | (uint64_t)(b_lo + (uint32_t)((g - s) * (OZ2_PLANE >> 4)));
-      umma_i8(taddr + (uint32_t)((g - G_BASE) * OZ2_TN), da, db, idesc, s > 0 ? 1u : acc0);
+  for (int s = 0; s <= G; s++) {
+    const uint64_t da = hi | (uint64_t)(a_lo + (uint32_t)(s * (OZ2_PLANE >> 4)));
+    const uint64_t db = hi | (uint64_t)(b_lo + (uint32_t)((G - s) * (OZ2_PLANE >> 4)));
+    umma_i8(taddr + (uint32_t)((G - G_BASE) * OZ2_TN), da, db, idesc, s > 0 ? 1u : acc0);
+  }
+}
+template <int G_BEG, int G_END, int G_BASE>
+__device__ __forceinline__ void oz2_issue_groups(uint32_t taddr, uint32_t a_lo, uint32_t acc0) {
+  if constexpr (G_END > G_BEG) {
+    oz2_issue_group<G_END - 1, G_BASE>(taddr, a_lo, acc0);
+    oz2_issue_groups<G_BEG, G_END - 1, G_BASE>(taddr, a_lo, acc0);
+  }
+}
+// First k-chunk of a pass: the accumulator of group g (TMEM slot g - G_BASE) is overwritten as soon as the epilogue has drained
+// THAT slot of the previous pass (it drains the slots in the same descending order), not the whole TMEM: the tensor core waits
+// for one slot's drain (~670 clk) instead of four. Bit s of usebits is the parity of the number of passes that used slot s (the mbarrier phase to wait for).
+template <int G_BEG, int G_END, int G_BASE>
+__device__ __forceinline__ void oz2_first_chunk(uint32_t taddr, uint32_t a_lo, uint64_t* tmem_empty, uint32_t& usebits, bool issue) {
+  if constexpr (G_END > G_BEG) {
+    constexpr int slot = G_END - 1 - G_BASE;
+    mbar_wait(&tmem_empty[slot], ((usebits >> slot) & 1u) ^ 1u);
+    usebits ^= 1u << slot;
+    tc_fence_after();
+    if (elect_one()) {
+      if (issue) oz2_issue_group<G_END - 1, G_BASE>(taddr, a_lo, 0u);
     }
+    __syncwarp();
+    oz2_first_chunk<G_BEG, G_END - 1, G_BASE>(taddr, a_lo, tmem_empty, usebits, issue);
   }
 }
 // Warp roles: warps 0..7 = epilogue (TMEM lane quarter = warp % 4, column half = warp / 4; two warpgroups that raise their
@@ -373,14 +397,15 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + OZ2_STAGES * OZ2_STAGE_BYTES);
   uint64_t* empty = full + OZ2_STAGES;
   uint64_t* tmem_full = empty + OZ2_STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* tmem_empty = tmem_full + 1;                    // one per TMEM slot (128 accumulator columns)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < OZ2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, OZ_EPI_WARPS);
+#pragma unroll
+    for (int s = 0; s < 4; s++) mbar_init(&tmem_empty[s], OZ_EPI_WARPS);
     fence_mbar_init();
     tma_prefetch_desc(&mapA);
   }
@@ -423,9 +448,11 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
   } else if (warp == 9) {
     // ================= MMA issuer (one thread) ======================================================================
     {   // the WHOLE warp runs the (warp-uniform) control flow; one elected lane issues MMAs and commits
-      uint32_t hs = 0, ph = 0;
+      uint32_t ph = 0;
+      uint32_t usebits = 0u;
       int st = 0;
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
+      const bool issue = !(p.dbg & 1);
       for (int ti = ti_beg; ti < ti_end; ti++) {
         const uint32_t t = p.tiles[ti];
         const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
@@ -433,20 +460,24 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
         // block the compiler keeps the descriptors in vector registers (R2UR per operand, ~1.3x slower issue)
         auto run_pass = [&](auto pass_tag) {
           constexpr int pass = decltype(pass_tag)::value;
-          mbar_wait(tmem_empty, (hs & 1) ^ 1);   // the epilogue has drained the previous pass out of TMEM
-          tc_fence_after();
           for (int kc = 0; kc < nkc; kc++) {
             mbar_wait(&full[st], ph);
             tc_fence_after();
             const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ2_STAGE_BYTES >> 4);
-            const uint32_t acc0 = kc > 0 ? 1u : 0u;
-            if (elect_one()) {
-              if (!(p.dbg & 1)) {
-                if (pass == 1) oz2_issue_groups<0, 4, 0>(taddr, a_lo, acc0);          // groups 0 .. 3
-                else if (nd == 8) oz2_issue_groups<4, 8, 4>(taddr, a_lo, acc0);       // low-order groups 4 .. nd-1
-                else if (nd == 7) oz2_issue_groups<4, 7, 4>(taddr, a_lo, acc0);
-                else if (nd == 6) oz2_issue_groups<4, 6, 4>(taddr, a_lo, acc0);
-                else oz2_issue_groups<4, 5, 4>(taddr, a_lo, acc0);
+            if (kc == 0) {   // slot by slot behind the epilogue's drain of the previous pass
+              if (pass == 1) oz2_first_chunk<0, 4, 0>(taddr, a_lo, tmem_empty, usebits, issue);
+              else if (nd == 8) oz2_first_chunk<4, 8, 4>(taddr, a_lo, tmem_empty, usebits, issue);
+              else if (nd == 7) oz2_first_chunk<4, 7, 4>(taddr, a_lo, tmem_empty, usebits, issue);
+              else if (nd == 6) oz2_first_chunk<4, 6, 4>(taddr, a_lo, tmem_empty, usebits, issue);
+              else oz2_first_chunk<4, 5, 4>(taddr, a_lo, tmem_empty, usebits, issue);
+              if (elect_one()) umma_commit(&empty[st]);
+            } else if (elect_one()) {
+              if (issue) {
+                if (pass == 1) oz2_issue_groups<0, 4, 0>(taddr, a_lo, 1u);          // groups 0 .. 3
+                else if (nd == 8) oz2_issue_groups<4, 8, 4>(taddr, a_lo, 1u);       // low-order groups 4 .. nd-1
+                else if (nd == 7) oz2_issue_groups<4, 7, 4>(taddr, a_lo, 1u);
+                else if (nd == 6) oz2_issue_groups<4, 6, 4>(taddr, a_lo, 1u);
+                else oz2_issue_groups<4, 5, 4>(taddr, a_lo, 1u);
               }
               umma_commit(&empty[st]);
             }
@@ -455,7 +486,6 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
           }
           if (elect_one()) umma_commit(tmem_full);
           __syncwarp();
-          hs++;
         };
         run_pass(std::integral_constant<int, 0>{});
         run_pass(std::integral_constant<int, 1>{});
@@ -479,20 +509,31 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
         else mbar_wait_backoff(tmem_full, hs & 1, 128);
         tc_fence_after();
         const int gbase = pass == 0 ? 4 : 0, gtop = pass == 0 ? nd : 4;
-        for (int g = ((p.dbg & 4) ? gbase : gtop) - 1; g >= gbase; g--) {   // smallest magnitude first (pass 0 before pass 1)
+        for (int g = gtop - 1; g >= gbase; g--) {   // smallest magnitude first (pass 0 before pass 1)
           const double sc = __longlong_as_double((long long)(1023 - 7 * g) << 52);   // 2^(-7 g)
-#pragma unroll
-          for (int half = 0; half < 2; half++) {
-            uint32_t v[32];
-            tmem_ld32(taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - gbase) * OZ2_TN + h * 64 + half * 32), v);
+          uint32_t v0[32], v1[32];
+          if (!(p.dbg & 4)) {
+            const uint32_t ta = taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - gbase) * OZ2_TN + h * 64);
+            tmem_ld32(ta, v0);
+            tmem_ld32(ta + 32, v1);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 32)) mbar_arrive(&tmem_empty[g - gbase]);   // this slot may take the next pass's MMAs: the fp64 sum follows
+          if (!(p.dbg & 4)) {
 #pragma unroll
             for (int j = 0; j < 32; j++)
-              acc[half * 32 + j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, sc, acc[half * 32 + j]);
+              acc[j] = fma(__hiloint2double(0x43300000, (int)(v0[j] ^ 0x80000000u)) - 4503601774854144.0, sc, acc[j]);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              acc[32 + j] = fma(__hiloint2double(0x43300000, (int)(v1[j] ^ 0x80000000u)) - 4503601774854144.0, sc, acc[32 + j]);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);
+        if (p.dbg & 32) {   // measurement: release the whole TMEM only after the full drain (the behaviour before the per-slot barriers)
+          __syncwarp();
+          if (lane == 0)
+            for (int g = gtop - 1; g >= gbase; g--) mbar_arrive(&tmem_empty[g - gbase]);
+        }
       }
       if (p.dbg & 4) continue;
       const long gi = (long)r * OZ_TM + q * 32 + lane;
@@ -505,6 +546,77 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile lists of the sweep (host): per panel step the launches U0 | U1 | U2 (+ the K^-1 tiles of the step)
+// ---------------------------------------------------------------------------------------------------------------
+// tiles in bands of 8 row tiles x 16 column tiles (64 wide): the ~148 tiles in flight share 8 A panels and 16 B panels in L2
+// (column tiles: cw per 128 columns - two 64-wide tiles for the one-pass kernel, one 128-wide tile for the two-pass kernel)
+template <class Valid, class Emit>
+static void oz_banded(const std::vector<int>& rows, int ct_beg, int ct_end, int cw, Valid valid, Emit emit) {
+  for (size_t b = 0; b < rows.size(); b += 8)
+    for (int cc = ct_beg; cc < ct_end; cc += 8 * cw)
+      for (size_t i = b; i < std::min(rows.size(), b + 8); i++)
+        for (int ct = cc; ct < std::min(ct_end, cc + 8 * cw); ct++)
+          if (valid(rows[i], ct / cw)) emit(rows[i], ct);
+}
+
+// own_G > 1 (memory-distributed multi-GPU sweep): only the row tiles of the block rows this rank owns (block-cyclic over the
+// panels of NB rows, like the DMMA update of gpx_dist.cu) are listed; every tile of the matrix is in exactly one rank's list.
+void oz_build_lists(long Npad, long NB, int cw, int own_G, int own_g, std::vector<uint32_t>& tiles, std::vector<OzStep>& steps) {
+  const int nt = (int)(Npad / TILE), nbt_full = (int)(NB / TILE);
+  auto mine = [&](int r) { return own_G <= 1 || ((r / nbt_full) % own_G) == own_g; };
+  tiles.clear();
+  steps.clear();
+  for (long o = 0; o < Npad; o += NB) {
+    const long nb = std::min(NB, Npad - o);
+    const int kt0 = (int)(o / TILE), kt1 = kt0 + (int)(nb / TILE);
+    const int next_nbt = kt1 < nt ? (int)(std::min(NB, Npad - (o + nb)) / TILE) : 0;
+    OzStep st;
+    auto emit_update = [&](int cbeg, int cend) {   // S(r, c) -= P_r P_c^T, c in [cbeg, cend), r in [0, kt1) U [c, nt)
+      std::vector<int> rows;
+      for (int r = 0; r < kt1; r++) if (mine(r)) rows.push_back(r);
+      for (int r = cbeg; r < nt; r++) if (mine(r)) rows.push_back(r);
+      oz_banded(rows, cw * cbeg, cw * cend, cw, [&](int r, int cc) { return r < kt1 || cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, r < kt1 ? 1 : 0)); });
+    };
+    auto count_up = [&](int off, int n) { int u = 0; for (int i = off; i < off + n; i++) u += (tiles[i] >> 27) & 1; return u; };
+    // U0: the tiles of the NEXT diagonal block (rows and columns of block k+1): all that D(k+1) waits for
+    st.u0_off = (int)tiles.size();
+    if (kt1 < nt) {
+      std::vector<int> rows;
+      for (int r = kt1; r < kt1 + next_nbt; r++) if (mine(r)) rows.push_back(r);
+      oz_banded(rows, cw * kt1, cw * (kt1 + next_nbt), cw, [&](int r, int cc) { return cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, 0)); });
+    }
+    st.u0_n = (int)tiles.size() - st.u0_off;
+    st.u0_up = 0;
+    // U1: the rest of block column k+1 (rows above the block and below it)
+    st.u1_off = (int)tiles.size();
+    if (kt1 < nt) {
+      std::vector<int> rows;
+      for (int r = 0; r < kt1; r++) if (mine(r)) rows.push_back(r);
+      for (int r = kt1 + next_nbt; r < nt; r++) if (mine(r)) rows.push_back(r);
+      oz_banded(rows, cw * kt1, cw * (kt1 + next_nbt), cw, [&](int r, int cc) { return r < kt1 || cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, OZ_UPDATE, r < kt1 ? 1 : 0)); });
+    }
+    st.u1_n = (int)tiles.size() - st.u1_off;
+    st.u1_up = count_up(st.u1_off, st.u1_n);
+    st.u2_off = (int)tiles.size();
+    if (kt1 + next_nbt < nt) emit_update(kt1 + next_nbt, nt);
+    st.u2_upd = (int)tiles.size() - st.u2_off;
+    st.u2_upd_up = count_up(st.u2_off, st.u2_upd);
+    {   // K^-1(r, c) (+)= P_r P_c^T for c <= r < kt1: rows of block k see their first contribution at this step
+      std::vector<int> rows;
+      for (int r = 0; r < kt1; r++) if (mine(r)) rows.push_back(r);
+      oz_banded(rows, 0, cw * kt1, cw, [&](int r, int cc) { return cc <= r; },
+                [&](int r, int ct) { tiles.push_back(oz_tile(r, ct, r >= kt0 ? OZ_LAUUM_SET : OZ_LAUUM_ACC, 1)); });
+    }
+    st.u2_n = (int)tiles.size() - st.u2_off;
+    st.u2_up = count_up(st.u2_off, st.u2_n);
+    steps.push_back(st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

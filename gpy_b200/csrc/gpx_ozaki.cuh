@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "gpx_common.cuh"
 
 struct gpx_ctx;
@@ -44,8 +46,13 @@ struct OzParams {
   int tpc;                 // consecutive tiles per CTA (0 = default)
   int wide;                // 1: 128 x 128 tiles (two-pass kernel, column tile index in 128-column units), 0: 128 x 64 tiles
   int dbg;                 // measurement only: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work (results invalid);
-                           // 8 / 16 = epilogue / producer wait WITHOUT back-off (results valid)
+                           // 8 / 16 = epilogue / producer wait WITHOUT back-off, 32 = TMEM released per pass, not per slot (results valid)
 };
+
+// one panel step of the sweep: offsets into the tile list. U0: the next diagonal block only; U1: the rest of block column k+1;
+// U2 list: u2_upd update tiles, then the K^-1 tiles; *_up = inverse-part tiles among them
+struct OzStep { int u0_off, u0_n, u1_off, u1_n, u2_off, u2_n, u2_upd, u0_up, u1_up, u2_up, u2_upd_up; };
+void oz_build_lists(long Npad, long NB, int cw, int own_G, int own_g, std::vector<uint32_t>& tiles, std::vector<OzStep>& steps);
 
 int oz_init();                                                          // driver entry point + kernel attributes
 int oz_planes_alloc(OzPlanes& pl, long rows, long K);                    // buffers + tensor maps
