@@ -9,7 +9,8 @@ from ._ffi import Engine, GpxError, kern_K, kern_Kdiag, kern_grad_full  # noqa: 
 
 from .kern import (RBF, Exponential, Matern32, Matern52, Stationary, DeviceGradient, Add, Prod, White, Bias,  # noqa: F401
                    Kern, CombinationKernel)
-from .inference import ExactGaussianInference, Gaussian, PosteriorExact  # noqa: F401
+from .inference import (ExactGaussianInference, Gaussian, HeteroscedasticGaussian, MixedNoise,  # noqa: F401
+                        PosteriorExact)
 from .model import GP, GPHeteroscedasticRegression, GPRegression  # noqa: F401
 from .sparse import SparseGPRegression, VarDTC  # noqa: F401
 

@@ -16,6 +16,7 @@
 #include "gpx_common.cuh"
 #include "gpx_kernels.cuh"
 #include "gpx_ctx.cuh"
+#include "gpx_fine.cuh"
 
 namespace gpx {
 static thread_local std::string g_err;
@@ -62,9 +63,12 @@ static long pick_nb(const gpx_ctx* c) {
   if (c->NB > 0) return std::min<long>(c->NB, c->Npad);
   const char* e = getenv("GPX_NB");
   if (e && atol(e) >= TILE && atol(e) % TILE == 0) return std::min<long>(atol(e), c->Npad);
-  if (c->Npad >= 8192) return 1024;
+  // measured with the chain schedule (profiles/r02s2_chain_ab.txt): N = 16384: 1024 (66.8 ms; 512: 76.3, 2048: 73.4);
+  // N = 8192: 512 (12.65 vs 13.15 ms); N = 4096: 512 (3.27; 256: 3.80, 1024: 3.76); N = 512: one block (0.467 vs 0.506 ms)
+  if (c->Npad > 8192) return 1024;
   if (c->Npad >= 2048) return 512;
-  return std::min<long>(256, c->Npad);
+  if (c->Npad <= 512) return c->Npad;
+  return 256;
 }
 
 int gpx::fill_kp(KernParams& kp, int kind, int ard, int D, double variance, const double* ls) {
@@ -105,12 +109,15 @@ int gpx_create(int device, gpx_ctx** out) {
   GPX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   GPX_CUDA(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio_lo));
   GPX_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_hi));
+  // between the two: the big panel GEMM on st3 must not hold back the small launches of the diagonal-block chain on st2
+  GPX_CUDA(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, prio_hi < prio_lo - 1 ? prio_hi + 1 : prio_hi));
   GPX_CUDA(cudaMalloc(&c->res, (MAX_D + 2 * MAX_PARTS + 8) * sizeof(double)));
   GPX_CUDA(cudaMalloc(&c->info, sizeof(int)));
   GPX_CUDA(cudaMallocHost(&c->h_res, (MAX_D + 2 * MAX_PARTS + 8) * sizeof(double)));
   GPX_CUDA(cudaMallocHost(&c->h_info, sizeof(int)));
   GPX_CHECK(gemm_init());
   GPX_CHECK(oz_init());
+  GPX_CHECK(fine_init());
   GPX_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   *out = c;
   return 0;
@@ -126,6 +133,8 @@ int gpx_destroy(gpx_ctx* c) {
   for (auto e : c->ev) cudaEventDestroy(e);
   for (auto e : c->sync_ev) cudaEventDestroy(e);
   if (c->st2) cudaStreamDestroy(c->st2);
+  if (c->st3) cudaStreamDestroy(c->st3);
+  if (c->ev_kfirst) cudaEventDestroy(c->ev_kfirst);
   if (c->res) cudaFree(c->res);
   if (c->dNoiseVec) cudaFree(c->dNoiseVec);
   if (c->dDnoise) cudaFree(c->dDnoise);
@@ -176,6 +185,10 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "base")) { set_base_version((int)std::max<int64_t>(0, std::min<int64_t>(value, 4))); return 0; }
+  if (!strcmp(name, "base_prof")) return set_base_prof((int)value);
+  if (!strcmp(name, "fine")) { c->fine = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "chain")) { c->chain = value ? 1 : 0; return 0; }
   GPX_FAIL("unknown option");
 }
 
@@ -325,11 +338,14 @@ static int oz_prepare(gpx_ctx* c) {
 // machine busy; U1(k+1) waits for Pn(k+1). Without look-ahead everything is issued on the main stream.
 // oz: 0 = DMMA updates; 1 = trailing update on tcgen05 (Ozaki split); 2 = that + K^-1 = U U^T accumulated into c->Kinv
 // panel by panel inside the same launches (the panel's digit planes serve both)
+static int run_sweep_chain(gpx_ctx* c, Recorder& rec);
+
 static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
   const long ld = c->Npad, Npad = c->Npad;
   const int nt = (int)(Npad / TILE);
   const long NB = pick_nb(c);
   const bool la = c->lookahead && NB < Npad;
+  if (oz >= 2 && la && c->chain && !c->oz_sched) return run_sweep_chain(c, rec);
   cudaStream_t sm = c->st;
   cudaStream_t ss = la ? c->st2 : c->st;
   size_t evi = 0;
@@ -349,33 +365,7 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
     double* Sblk = c->S + o + o * ld;
     double* Pb = c->Pbuf + (size_t)(kblk & 1) * Npad * NB;
     // ---- D(k): inner sweep of the nb x nb diagonal block ------------------------------------------------------
-    for (int d = 0; d < nbt; d++) {
-      const int g = kt0 + d;
-      double* tile = Sblk + (long)d * TILE + (long)d * TILE * ld;
-      GPX_CHECK(launch_base(tile, ld, c->Ldiag + (long)g * TILE * TILE, c->Dinv + (long)g * TILE * TILE,
-                            c->logdet_part + g, c->info, g * TILE, ss));
-      c->eval_launches++;
-      if (nbt > 1) {
-        GemmParams pp = gemm_defaults();
-        pp.mode = GEMM_PANEL;
-        pp.A = Sblk + (long)d * TILE * ld; pp.lda = ld;
-        pp.B = c->Dinv + (long)g * TILE * TILE; pp.ldb = TILE;
-        pp.C = Sblk + (long)d * TILE * ld; pp.ldc = ld;      // in place: one k-tile deep, tile-local dependence only
-        pp.K = TILE; pp.nt = nbt; pp.skip0 = d; pp.skip1 = d + 1; pp.tri = 0;
-        GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), ss));
-        c->eval_launches++;
-        if (d + 1 < nbt) {
-          GemmParams pu = gemm_defaults();
-          pu.mode = GEMM_UPDATE;
-          pu.A = Sblk + (long)d * TILE * ld; pu.lda = ld;
-          pu.B = pu.A; pu.ldb = ld;
-          pu.C = Sblk; pu.ldc = ld;
-          pu.K = TILE; pu.nt = nbt; pu.c0 = d + 1; pu.rlow = d + 1;
-          GPX_CHECK(launch_gemm(pu, dim3(1, 1), ss));
-          c->eval_launches++;
-        }
-      }
-    }
+    GPX_CHECK(diag_block_sweep(c, Sblk, ld, nbt, kt0, ss));
     if (nbt == nt) break;  // single block: done
     // tcgen05 schedule (option "oz_sched", default): the persistent U2(k-1) leaves a few SMs free, on which the serial
     // diagonal-block chain D(k) runs meanwhile (side stream); the panel GEMM Pn(k), which needs the whole machine for half a
@@ -516,6 +506,132 @@ static int run_sweep(gpx_ctx* c, Recorder& rec, int oz = 0) {
   return 0;
 }
 
+// The tcgen05 sweep with the serial chain on its own stream (option "chain", default). Per step k:
+//   side stream  ss : D(k) -> assemble -> Pc(k): panel rows of block k+1 (fine DMMA tiles) -> U0d(k): diagonal block k+1 -= Pc Pc^T
+//                     (fine DMMA tiles, fp64 operands straight from the panel buffer) -> D(k+1) ...
+//   third stream s3 : Pr(k): the other panel rows -> digit split of the whole panel -> copy-back -> forward substitution
+//   main stream  sm : U1(k): rest of block column k+1 -> U2(k): everything else + the K^-1 tiles          (tcgen05)
+// Dependences across streams (events):  Pc(k), Pr(k) read block column k: after U1(k-1);  U0d(k) touches tiles that U2(k-1)
+// updates: after U2(k-1);  split(k) after Pc(k);  U1(k) after split(k);  assemble(k+1) overwrites Tm and, with Pc/Pr(k+1), the
+// panel buffer of step k-1: after the forward-substitution block of step k on s3 (s3 runs in order, so everything of step
+// k-1 there is done as well);  the digit planes of step k are those of step k-2: split(k) is behind Pr(k), which waits for
+// U1(k-1), which is behind U2(k-2) on the main stream.
+// What the next diagonal block waits for is therefore D(k) + two small launches instead of D(k) + full panel + split + a
+// tcgen05 launch, and the main stream never waits for a diagonal block unless the trailing update is shorter than D.
+static int run_sweep_chain(gpx_ctx* c, Recorder& rec) {
+  const long ld = c->Npad, Npad = c->Npad;
+  const int nt = (int)(Npad / TILE);
+  const long NB = pick_nb(c);
+  cudaStream_t sm = c->st, ss = c->st2, s3 = c->st3;
+  size_t evi = 0;
+  cudaEvent_t ev, ev_u1 = nullptr, ev_u2 = nullptr, ev_fw = nullptr;
+  auto link = [&](cudaStream_t from, cudaStream_t to, cudaEvent_t* keep) -> int {   // `to` continues after what `from` holds now
+    cudaEvent_t e;
+    GPX_CHECK(sync_event(c, evi++, &e));
+    GPX_CUDA(cudaEventRecord(e, from));
+    if (to) GPX_CUDA(cudaStreamWaitEvent(to, e, 0));
+    if (keep) *keep = e;
+    return 0;
+  };
+  GPX_CHECK(link(sm, s3, &ev));                      // K build (all of it); it also stands in for "U1(-1)": block column 0 is final
+  if (c->kfirst_valid) GPX_CUDA(cudaStreamWaitEvent(ss, c->ev_kfirst, 0));   // D(0) needs the first block row only
+  else GPX_CUDA(cudaStreamWaitEvent(ss, ev, 0));
+  ev_u1 = ev;
+  GPX_CUDA(cudaMemcpyAsync(c->dYres, c->dY, (size_t)c->P * Npad * 8, cudaMemcpyDeviceToDevice, s3));
+  int kblk = 0;
+  for (long o = 0; o < Npad; o += NB, kblk++) {
+    const long nb = std::min(NB, Npad - o);
+    const int nbt = (int)(nb / TILE), kt0 = (int)(o / TILE), kt1 = kt0 + nbt;
+    const int next_nbt = kt1 < nt ? (int)(std::min(NB, Npad - (o + nb)) / TILE) : 0;
+    double* Sblk = c->S + o + o * ld;
+    double* Pb = c->Pbuf + (size_t)(kblk & 1) * Npad * NB;
+    const gpx_ctx::OzStep& os = c->oz_steps[kblk];
+    const OzPlanes& pl = c->ozp[kblk & 1];
+    // ---- ss: D(k), assemble ------------------------------------------------------------------------------------------
+    GPX_CHECK(diag_block_sweep(c, Sblk, ld, nbt, kt0, ss));
+    if (ev_fw) GPX_CUDA(cudaStreamWaitEvent(ss, ev_fw, 0));
+    GPX_CHECK(launch_assemble(Sblk, ld, (int)nb, Pb + o, Npad, c->Tm, ss));
+    c->eval_launches++;
+    cudaEvent_t ev_asm, ev_pc = nullptr;
+    GPX_CHECK(link(ss, s3, &ev_asm));
+    if (ev_u1) { GPX_CUDA(cudaStreamWaitEvent(ss, ev_u1, 0)); GPX_CUDA(cudaStreamWaitEvent(s3, ev_u1, 0)); }
+    // ---- ss: Pc(k), U0d(k) -------------------------------------------------------------------------------------------
+    if (next_nbt > 0) {
+      FineParams pc{};
+      pc.mode = FINE_PANEL;
+      pc.A = c->S + o * ld; pc.lda = ld;
+      pc.B = c->Tm; pc.ldb = nb;
+      pc.C = Pb; pc.ldc = Npad;
+      pc.K = (int)nb; pc.r0 = kt1; pc.nr = next_nbt; pc.nc = nbt; pc.tri = 1;
+      GPX_CHECK(launch_fine(pc, ss));
+      c->eval_launches++;
+      GPX_CHECK(link(ss, nullptr, &ev_pc));
+      if (ev_u2) GPX_CUDA(cudaStreamWaitEvent(ss, ev_u2, 0));
+      FineParams pu{};
+      pu.mode = FINE_UPDATE;
+      pu.A = Pb; pu.lda = Npad;
+      pu.B = Pb; pu.ldb = Npad;
+      pu.C = c->S; pu.ldc = ld;
+      pu.K = (int)nb; pu.nt = kt1 + next_nbt; pu.c0 = kt1; pu.ncols = next_nbt; pu.rlow = 0;
+      GPX_CHECK(launch_fine(pu, ss));
+      c->eval_launches++;
+    }
+    // ---- s3: Pr(k), split, copy-back, forward substitution --------------------------------------------------------------
+    if (nt - nbt - next_nbt > 0) {
+      GemmParams pp = gemm_defaults();
+      pp.mode = GEMM_PANEL;
+      pp.A = c->S + o * ld; pp.lda = ld;
+      pp.B = c->Tm; pp.ldb = nb;
+      pp.C = Pb; pp.ldc = Npad;
+      pp.K = (int)nb; pp.nt = nt; pp.skip0 = kt0; pp.skip1 = kt1 + next_nbt; pp.tri = 1;
+      GPX_CHECK(launch_gemm(pp, dim3(nbt, nt - nbt - next_nbt), s3));
+      c->eval_launches++;
+    }
+    if (ev_pc) GPX_CUDA(cudaStreamWaitEvent(s3, ev_pc, 0));
+    GPX_CHECK(launch_oz_split(Pb, Npad, nb, c->ozp[kblk & 1], s3));
+    c->eval_launches++;
+    GPX_CHECK(link(s3, sm, nullptr));
+    if (o > 0)
+      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, Pb, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, s3));
+    if (kt1 < nt)
+      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8, (size_t)(Npad - o - nb) * 8, nb,
+                                 cudaMemcpyDeviceToDevice, s3));
+    GPX_CHECK(launch_fw_block(c->Tm, (int)nb, c->dYres + o, Npad, c->P, c->dTfw + o, s3));
+    c->eval_launches++;
+    GPX_CHECK(link(s3, nullptr, &ev_fw));
+    GPX_CHECK(launch_fw_panel(Pb + (o + nb), Npad, Npad - o - nb, (int)nb, c->dTfw + o, Npad, c->P, c->dYres + (o + nb), s3));
+    c->eval_launches++;
+    // ---- sm: U1(k), U2(k) on the tcgen05 tensor cores ---------------------------------------------------------------------
+    for (int part = 0; part < 2; part++) {
+      const int off = part == 0 ? os.u1_off : os.u2_off;
+      const int ntl = part == 0 ? os.u1_n : os.u2_n;
+      if (ntl > 0) {
+        OzParams op;
+        memset(&op, 0, sizeof(op));
+        op.tiles = c->oz_tiles + off; op.ntiles = ntl; op.nkc = (int)(nb / OZ_KC);
+        op.scale = pl.scale; op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
+        op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg; op.wide = c->oz_wide;
+        op.tpc = c->oz_ctas > 0 ? (ntl + c->oz_ctas - 1) / c->oz_ctas : c->oz_tpc;
+        const int tn = c->oz_wide ? 2 * OZ_TN : OZ_TN;
+        const double flops = (double)ntl * 2.0 * OZ_TM * tn * (double)nb;
+        const int nup = part == 0 ? os.u1_up : os.u2_up;
+        const int du = c->oz_dig_up;
+        c->stats.update_int8_ops += ((double)nup * (du * (du + 1) / 2) + (double)(ntl - nup) * (OZ_S * (OZ_S + 1) / 2)) * 2.0 *
+                                    OZ_TM * tn * (double)nb;
+        const int h = rec.begin(PH_UPDATE, flops);
+        GPX_CHECK(launch_oz_gemm(pl, op, c->num_sms, sm));
+        rec.end(h);
+        c->eval_launches++;
+        c->stats.update_launches++;
+      }
+      GPX_CHECK(link(sm, nullptr, part == 0 ? &ev_u1 : &ev_u2));
+    }
+  }
+  GPX_CHECK(link(ss, sm, nullptr));
+  GPX_CHECK(link(s3, sm, nullptr));
+  return 0;
+}
+
 // plain: store K^-1 (lower tiles) only, no gradient reductions (composite kernels reduce from the stored matrix)
 static int run_lauum(gpx_ctx* c, double* kinv_out, Recorder* rec, bool plain = false) {
   const long ld = c->Npad;
@@ -587,7 +703,21 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     kb.diag_vec = c->het ? c->dNoiseVec : nullptr;
     kb.kp = c->kp;
     const int h = rec.begin(PH_KBUILD);
-    GPX_CHECK(launch_kbuild(kb, nt, nt, st));
+    // chain schedule: the first block row goes first and is announced by an event, so that the factorisation of the first
+    // diagonal block runs beside the rest of the covariance build
+    const int nbt0 = (int)(pick_nb(c) / TILE);
+    c->kfirst_valid = false;
+    if (oz_wanted(c) && c->lookahead && c->chain && !c->oz_sched && nbt0 < nt) {
+      GPX_CHECK(launch_kbuild(kb, nbt0, nt, st));
+      if (!c->ev_kfirst) GPX_CUDA(cudaEventCreateWithFlags(&c->ev_kfirst, cudaEventDisableTiming));
+      GPX_CUDA(cudaEventRecord(c->ev_kfirst, st));
+      c->kfirst_valid = true;
+      kb.rt0 = nbt0;
+      GPX_CHECK(launch_kbuild(kb, nt - nbt0, nt, st));
+      c->eval_launches++;
+    } else {
+      GPX_CHECK(launch_kbuild(kb, nt, nt, st));
+    }
     rec.end(h);
     c->eval_launches++;
   }
@@ -602,10 +732,11 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
   }
   {
     const int h = rec.begin(PH_SOLVE);
-    GPX_CHECK(launch_utv(c->S, ld, c->Npad, c->P, c->dY, c->dT, st));
-    GPX_CHECK(launch_uv(c->S, ld, c->Npad, c->P, c->dT, KSPLIT, c->dUvPart, c->dAlpha, st));
+    // alpha = U (U^T y). On the tcgen05 path t = L^-1 y = U^T y came along with the sweep (forward substitution): one mat-vec
+    if (!oz) GPX_CHECK(launch_utv(c->S, ld, c->Npad, c->P, c->dY, c->dT, st));
+    GPX_CHECK(launch_uv(c->S, ld, c->Npad, c->P, oz ? c->dTfw : c->dT, KSPLIT, c->dUvPart, c->dAlpha, st));
     rec.end(h);
-    c->eval_launches += 3;
+    c->eval_launches += oz ? 2 : 3;
   }
   if (c->multi) {
     // composite kernel: K^-1 stored (by the sweep on the tcgen05 path, else by a plain LAUUM), then one reduction pass per part

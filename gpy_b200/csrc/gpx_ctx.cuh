@@ -13,7 +13,14 @@ struct gpx_ctx {
   int device = 0;
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;   // high-priority side stream: diagonal-block work + panel of the NEXT step (look-ahead)
+  cudaStream_t st3 = nullptr;   // high-priority third stream (option "chain"): rest of the panel, digit split, copy-back, forward
+                                // substitution -- everything of step k that the NEXT diagonal block does not wait for
+  cudaEvent_t ev_kfirst = nullptr;   // chain schedule: the first block row of the covariance build is done (D(0) may start)
+  bool kfirst_valid = false;
   int lookahead = 1;
+  int fine = 1;                 // option "fine": 64 x 64-tile DMMA kernels in the diagonal-block chain (gpx_fine.cu); 0 = 128 x 128 tiles
+  int chain = 1;                // option "chain": tcgen05 path: the chain D(k) -> panel rows of block k+1 -> update of diagonal block k+1
+                                // (fp64 DMMA, fine tiles) -> D(k+1) runs alone on the side stream; 0 = round-2 schedule
   std::vector<cudaEvent_t> sync_ev;
   // data
   long N = 0, Npad = 0;

@@ -28,6 +28,7 @@
 
 #include "gpx_common.cuh"
 #include "gpx_ctx.cuh"
+#include "gpx_fine.cuh"
 #include "gpx_kernels.cuh"
 
 // ---- minimal NCCL surface (types as in nccl.h 2.x) ---------------------------------------------------------------
@@ -295,31 +296,7 @@ int dist_exact_eval(gpx_ctx* c, double extra_jitter) {
     double* Bc = (k & 1) ? d->Bc2 : d->Bc;
     if (g == root) {
       double* Sblk = c->S + (long)(k / G) * NB + o * ld;   // the diagonal block inside the owner's local rows
-      for (int dd = 0; dd < nbt; dd++) {
-        const int gt = kt0 + dd;
-        double* tile = Sblk + (long)dd * TILE + (long)dd * TILE * ld;
-        GPX_CHECK(launch_base(tile, ld, c->Ldiag + (long)gt * TILE * TILE, c->Dinv + (long)gt * TILE * TILE,
-                              c->logdet_part + gt, c->info, gt * TILE, ss));
-        c->eval_launches++;
-        if (nbt > 1) {
-          GemmParams pp = gemm_defaults();
-          pp.mode = GEMM_PANEL;
-          pp.A = Sblk + (long)dd * TILE * ld; pp.lda = ld;
-          pp.B = c->Dinv + (long)gt * TILE * TILE; pp.ldb = TILE;
-          pp.C = Sblk + (long)dd * TILE * ld; pp.ldc = ld;
-          pp.K = TILE; pp.nt = nbt; pp.skip0 = dd; pp.skip1 = dd + 1;
-          GPX_CHECK(launch_gemm(pp, dim3(1, nbt - 1), ss));
-          c->eval_launches++;
-          if (dd + 1 < nbt) {
-            GemmParams pu = gemm_defaults();
-            pu.mode = GEMM_UPDATE;
-            pu.A = Sblk + (long)dd * TILE * ld; pu.lda = ld; pu.B = pu.A; pu.ldb = ld;
-            pu.C = Sblk; pu.ldc = ld; pu.K = TILE; pu.nt = nbt; pu.c0 = dd + 1; pu.rlow = dd + 1;
-            GPX_CHECK(launch_gemm(pu, dim3(1, 1), ss));
-            c->eval_launches++;
-          }
-        }
-      }
+      GPX_CHECK(diag_block_sweep(c, Sblk, ld, nbt, kt0, ss));
       // U_kk into this rank's chunk of the panel buffer, L_kk^-1 into the broadcast buffer
       GPX_CHECK(launch_assemble(Sblk, ld, (int)NB, Pb + pos_k * NB * NB, NB, Bc, ss));
       c->eval_launches++;

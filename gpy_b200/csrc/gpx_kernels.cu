@@ -3,6 +3,8 @@
 #include "gpx_common.cuh"
 #include <cstdlib>
 
+#include <cstdio>
+
 #include "gpx_kernels.cuh"
 
 namespace gpx {
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KBuildParams p) {
   double* sSc = sSr + TILE;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sSc + TILE);
 
-  const int ct = blockIdx.x, rt = blockIdx.y;
+  const int ct = blockIdx.x, rt = p.rt0 + blockIdx.y;
   if (p.own_G > 1 && ((rt / p.own_blk) % p.own_G) != p.own_g) return;   // block row owned by another rank
   const int tid = threadIdx.x;
   const int il = tid & (TILE - 1), half = tid >> 7;
@@ -482,16 +484,477 @@ base_sweep16_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag,
   }
 }
 
+// =================================================================================================================
+// base block, third generation (default). Same algorithm and outputs as base_sweep16_kernel; what changed is the serial part:
+//   * micro_diag_row: lane r of the chain warp holds ROW r of the 16 x 16 micro-block (both half-warps mirror each other), so a
+//     lane scales its own pivot-column entry without any exchange, and the NEXT pivot  d_{j+1} = v(j+1,j+1) - p_{j+1}^2  is
+//     formed locally in lane j+1 before the column is published: the serial chain per column is shuffle -> reciprocal square
+//     root -> multiply -> fused multiply-add, and the publish / read-back of the column through shared memory runs beside it.
+//     The reciprocal square root is MUFU.RSQ64H + one third-order correction (branch-free, ~1 ulp; the library rsqrt has a
+//     special-case branch that splits the basic block the scheduler can interleave).
+//   * the tile comes in by bulk async copies (lower part only, one copy per column, one mbarrier) instead of a load loop;
+//   * a column block is final as soon as its micro-panel is done: warps 1..15 stream it out (Ldiag, U into the workspace tile,
+//     the rows of L^-1) while warp 0 is busy with the next micro-block; only the last column block is written at the end.
+// =================================================================================================================
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // relative error ~2^-22
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);                          // 1 - x y^2
+  const double c = fma(0.375, e, 0.5);
+  const double ye = y * e;
+  return fma(ye, c, y);                                      // y (1 + e/2 + 3 e^2/8): error O(e^3)
+}
+
+__device__ __forceinline__ void micro_diag_row(double* T, int c0, double* Pd, double* Wm, double* psh, double* dinv,
+                                               double* ldg, int* info, int gcol0, int lane) {
+  const int rr = lane & 15;
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) v[q] = (rr >= q) ? T[(c0 + q) * BP + c0 + rr] : 0.0;
+  double my_inv = 0.0, my_l = 0.0;
+  double d = __shfl_sync(0xffffffffu, v[0], 0);
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, gcol0 + c0 + j + 1);
+    const double inv = rsqrt_fast(d);
+    const double l = d * inv;
+    const double p = (rr == j) ? inv : v[j] * inv;
+    if (rr == j) { my_inv = inv; my_l = l; }
+    v[j] = (rr == j) ? l : p;
+    if (j < 15) {                                     // next pivot, formed where it lives (lane j+1 owns row j+1)
+      const double dn = fma(-p, p, v[j + 1]);
+      d = __shfl_sync(0xffffffffu, dn, j + 1);
+    }
+    double* pj = psh + (j & 1) * 16;
+    pj[rr] = p;
+    __syncwarp();
+    const bool up = rr <= j;
+#pragma unroll
+    for (int col = j + 1; col < 16; col++)
+      if (up || rr >= col) v[col] = fma(-p, pj[col], v[col]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int col = 0; col < 16; col++) {
+    T[(c0 + col) * BP + c0 + rr] = v[col];
+    const double u = rr < col ? v[col] : (rr == col ? my_inv : 0.0);   // U(rr, col), reciprocal pivot on the diagonal
+    Pd[col * MP + rr] = u;
+    Wm[rr * MP + col] = u;                                               // W(col, rr) = U(rr, col)
+  }
+  if (lane < 16) { dinv[c0 + rr] = my_inv; ldg[c0 + rr] = my_l; }
+}
+
+// stream out the finished column block cb (16 columns): Ldiag and U columns, and rows [16cb, 16cb+16) of Dinv = L^-1 = U^T
+__device__ __forceinline__ void base_out_block(const double* T, const double* dinv, const double* ldg, int cb, int t, int nthr,
+                                               double* __restrict__ S, long ld, double* __restrict__ Ldiag,
+                                               double* __restrict__ Dinv) {
+  const int c0 = cb * 16;
+  for (int idx = t; idx < 16 * TILE; idx += nthr) {
+    const int row = idx & (TILE - 1), col = c0 + (idx >> 7);
+    const double x = T[col * BP + row];
+    Ldiag[row + col * TILE] = row > col ? x : (row == col ? ldg[row] : 0.0);
+    S[row + (long)col * ld] = row > col ? 0.0 : (row == col ? dinv[row] : x);
+  }
+  for (int idx = t; idx < 16 * TILE; idx += nthr) {
+    const int row = c0 + (idx & 15), col = idx >> 4;                     // W(row, col) = U(col, row): column `row` of T
+    Dinv[row + col * TILE] = row > col ? T[row * BP + col] : (row == col ? dinv[row] : 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(512, 1)
+base_sweep3_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, double* __restrict__ Dinv,
+                   double* __restrict__ logdet_part, int* __restrict__ info, int gcol0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* T = reinterpret_cast<double*>(smem_raw);   // [128][BP]
+  double* PdB = T + TILE * BP;
+  double* WmB = PdB + 2 * 16 * MP;
+  double* psh = WmB + 2 * 16 * MP;
+  double* dinv = psh + 32;
+  double* ldg = dinv + TILE;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ldg + TILE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  // the inverse region starts from zero; column c is copied from row (c & ~1) down (16-byte granularity of the bulk copy)
+  for (int idx = tid; idx < TILE * TILE; idx += 512) {
+    const int row = idx & (TILE - 1), col = idx >> 7;
+    if (row < (col & ~1)) T[col * BP + row] = 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) mbar_arrive_expect_tx(bar, 8320 * 8);   // sum over columns of (128 - (c & ~1)) doubles
+  __syncthreads();
+  if (tid < TILE) {
+    const int r0 = tid & ~1;
+    bulk_g2s(T + tid * BP + r0, S + r0 + (long)tid * ld, (TILE - r0) * 8, bar);
+  }
+  mbar_wait(bar, 0);
+  if (tid < TILE && (tid & 1)) T[tid * BP + tid - 1] = 0.0;   // the one element above the diagonal that came along
+  __syncthreads();
+  if (warp == 0) micro_diag_row(T, 0, PdB, WmB, psh, dinv, ldg, info, gcol0, lane);
+  __syncthreads();
+
+  for (int jp = 0; jp < 8; jp++) {
+    const int c0 = jp * 16;
+    double* Pd = PdB + (jp & 1) * 16 * MP;
+    double* Wm = WmB + (jp & 1) * 16 * MP;
+    // ---- micro-panel with DMMA: P(rows, :) = T(rows, panel) W^T for the 7 row blocks outside the micro-block -------------
+    if (warp < 7) {
+      const int g = lane >> 2, tg = lane & 3;
+      const int rt = warp < jp ? warp : warp + 1;
+      double* Ap = T + c0 * BP + rt * 16;
+      double af[2][4], c[2][2][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) af[mi][k4] = Ap[(k4 * 4 + tg) * BP + mi * 8 + g];
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) { c[mi][ni][0] = 0.0; c[mi][ni][1] = 0.0; }
+#pragma unroll
+      for (int k4 = 0; k4 < 4; k4++) {
+        double bf[2];
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) bf[ni] = Wm[(k4 * 4 + tg) * MP + ni * 8 + g];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 2; ni++) dmma884(c[mi][ni][0], c[mi][ni][1], af[mi][k4], bf[ni]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) Ap[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g] = c[mi][ni][e];
+    }
+    __syncthreads();
+    if (jp == 7) break;
+    // ---- column block jp+1 (8 micro-tiles, rows 0..7), two warps per micro-tile ------------------------------------------
+    micro_update<1>(T, c0, jp, warp >> 1, jp + 1, (warp & 1) * 8, Pd, lane);
+    __syncthreads();
+    // ---- warp 0: next diagonal micro-block  ||  warps 1..15: column blocks jp+2..7, then column block jp goes out --------
+    if (warp == 0) {
+      micro_diag_row(T, c0 + 16, PdB + ((jp + 1) & 1) * 16 * MP, WmB + ((jp + 1) & 1) * 16 * MP, psh, dinv, ldg, info, gcol0,
+                     lane);
+    } else {
+      int lin = 0;
+      for (int ct = jp + 2; ct < 8; ct++) {
+        const int nslot = jp + 1 + 8 - ct;
+        for (int slot = 0; slot < nslot; slot++, lin++) {
+          if (lin % 15 != warp - 1) continue;
+          const int rt = slot <= jp ? slot : ct + slot - (jp + 1);
+          micro_update<2>(T, c0, jp, rt, ct, 0, Pd, lane);
+        }
+      }
+      base_out_block(T, dinv, ldg, jp, tid - 32, 480, S, ld, Ldiag, Dinv);
+    }
+    __syncthreads();
+  }
+  base_out_block(T, dinv, ldg, 7, tid, 512, S, ld, Ldiag, Dinv);
+  if (tid < 32) {
+    double s = 0.0;
+    for (int j = tid; j < TILE; j += 32) s += log(ldg[j]);
+    s = warp_sum(s);
+    if (tid == 0) *logdet_part = 2.0 * s;
+  }
+}
+
+// =================================================================================================================
+// base block, fourth generation (default): the chain warp RUNS AHEAD of the other fifteen.
+// The serial part of a 128 x 128 factor-and-invert is the chain of the eight 16 x 16 diagonal micro-blocks. In generations 2/3
+// every micro-block waited for two block-wide phases (micro-panel, update of the next column block) with a barrier each. Here
+// warp 0 does, by itself, the only pieces of those phases the next micro-block needs -- P(jp+1, jp) = T(jp+1, jp) W^T and
+// T(jp+1, jp+1) -= P P^T, 32 DMMAs -- and goes straight on to micro-block jp+1, while warps 1..15 do the rest of the
+// micro-panel and of the rank-16 update of step jp and stream the finished column block out. Producer / consumer hand-overs
+// through named barriers (bar.arrive / bar.sync, two of each kind alternating by step parity):
+//   A[jp&1]: warp 0 -> bulk : W(jp), U micro-block and P(jp+1, jp) are in shared memory
+//   D[jp&1]: bulk -> warp 0 : the rank-16 update of step jp is done (warp 0 needs it before it touches row block jp+2)
+//   barrier 7: bulk only, between its micro-panel and its update.
+// micro_diag_row2: the pivot chain per column is multiply -> fused multiply-add -> shuffle -> MUFU.RSQ64H + 4 dependent fp64
+// operations; p_j(j+1), which the next column needs from lane j+1, travels by shuffle, the rest of the column through
+// shared memory (vector loads issued together, off the chain).
+// =================================================================================================================
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void micro_diag_row2(double* T, int c0, double* Pd, double* Wm, double* psh, double* dinv,
+                                                double* ldg, int* info, int gcol0, int lane) {
+  const int rr = lane & 15;
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) v[q] = (rr >= q) ? T[(c0 + q) * BP + c0 + rr] : 0.0;
+  double my_inv = 0.0, my_l = 0.0;
+  int badcol = -1;
+  double d = __shfl_sync(0xffffffffu, v[0], 0);
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    if (!(d > 0.0) && badcol < 0) badcol = j;
+    const double inv = rsqrt_fast(d);
+    const double l = d * inv;
+    const double p = (rr == j) ? inv : v[j] * inv;
+    if (rr == j) { my_inv = inv; my_l = l; }
+    v[j] = (rr == j) ? l : p;
+    if (j < 15) {
+      const double dn = fma(-p, p, v[j + 1]);            // lane j+1: the next pivot, from its own data only
+      d = __shfl_sync(0xffffffffu, dn, j + 1);
+      const double pn = __shfl_sync(0xffffffffu, p, j + 1);
+      v[j + 1] = fma(-p, pn, v[j + 1]);                  // column j+1: every row takes part (rr <= j or rr >= j+1)
+    }
+    if (j < 14) {
+      double* pj = psh + (j & 1) * 16;
+      pj[rr] = p;
+      __syncwarp();
+      double pc[16];
+#pragma unroll
+      for (int c2 = (j + 2) >> 1; c2 < 8; c2++) {
+        const double2 t2 = reinterpret_cast<const double2*>(pj)[c2];
+        pc[2 * c2] = t2.x; pc[2 * c2 + 1] = t2.y;
+      }
+      const bool up = rr <= j;
+#pragma unroll
+      for (int col = j + 2; col < 16; col++)
+        if (up || rr >= col) v[col] = fma(-p, pc[col], v[col]);
+    }
+  }
+  if (badcol >= 0 && lane == 0) atomicCAS(info, 0, gcol0 + c0 + badcol + 1);
+  if (lane < 16) {
+#pragma unroll
+    for (int col = 0; col < 16; col++) {
+      T[(c0 + col) * BP + c0 + rr] = v[col];
+      const double u = rr < col ? v[col] : (rr == col ? my_inv : 0.0);   // U(rr, col), reciprocal pivot on the diagonal
+      Pd[col * MP + rr] = u;
+      Wm[rr * MP + col] = u;                                               // W(col, rr) = U(rr, col)
+    }
+    dinv[c0 + rr] = my_inv; ldg[c0 + rr] = my_l;
+  }
+  __syncwarp();
+}
+
+// micro_diag_roll: the same column step as micro_diag_row2 as a ROLLED loop. The unrolled form is 16 x ~80 instructions of
+// straight-line code executed once per call: measured in situ (option "base_prof") the first call of a launch took 30 000
+// cycles (instruction fetch from L2 with a cold instruction cache, this is a one-CTA kernel on a fresh SM every time) and the
+// later ones 6 000-7 000 (~400 cycles per column). Here lane r keeps row r of the ACTIVE columns in v[0..15] with the current
+// column always in v[0]: the rank-1 update writes v[k-1] from v[k] (the shift costs nothing), finished columns go straight to
+// shared memory, so every column runs the same ~2 KB of code. The reciprocal square root of the NEXT pivot is started before
+// the update of the current column, in the same basic block, so that the scheduler interleaves the two.
+__device__ __forceinline__ void micro_diag_roll(double* T, int c0, double* Pd, double* Wm, double* psh, double* dinv,
+                                                double* ldg, int* info, int gcol0, int lane) {
+  const int rr = lane & 15;
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) v[q] = (rr >= q) ? T[(c0 + q) * BP + c0 + rr] : 0.0;
+  int badcol = -1;
+  double d = __shfl_sync(0xffffffffu, v[0], 0);
+  double inv = rsqrt_fast(d);
+#pragma unroll 1
+  for (int j = 0; j < 16; j++) {
+    if (!(d > 0.0) && badcol < 0) badcol = j;
+    const double l = d * inv;
+    const bool diag = rr == j;
+    const double p = diag ? inv : v[0] * inv;
+    const double dn = fma(-p, p, v[1]);                       // lane j+1: the next pivot, from its own data only
+    const double dnext = __shfl_sync(0xffffffffu, dn, (j + 1) & 15);
+    const double inv_next = rsqrt_fast(dnext);                // (j = 15: unused)
+    double* pj = psh + (j & 1) * 32;                          // [0..15] = p_j, [16..31] = 0
+    pj[rr] = p;
+    if (lane < 16) {
+      T[(c0 + j) * BP + c0 + rr] = diag ? l : p;
+      const double u = rr < j ? p : (diag ? inv : 0.0);       // U(rr, j), reciprocal pivot on the diagonal
+      Pd[j * MP + rr] = u;
+      Wm[rr * MP + j] = u;                                    // W(j, rr) = U(rr, j)
+      if (diag) { dinv[c0 + j] = inv; ldg[c0 + j] = l; }
+    }
+    __syncwarp();
+    const bool up = rr <= j;
+    const double* pc = pj + j;                                // pc[k] = p_j(j + k)
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+      const double t = fma(-p, pc[k], v[k]);
+      v[k - 1] = (up || rr >= j + k) ? t : v[k];
+    }
+    v[15] = 0.0;
+    d = dnext; inv = inv_next;
+  }
+  if (badcol >= 0 && lane == 0) atomicCAS(info, 0, gcol0 + c0 + badcol + 1);
+  __syncwarp();
+}
+
+// one row block of the micro-panel: T(rt, panel jp) <- T(rt, panel jp) W^T (in place), one warp
+__device__ __forceinline__ void micro_panel_rows(double* T, int c0, int rt, const double* Wm, int lane) {
+  const int g = lane >> 2, tg = lane & 3;
+  double* Ap = T + c0 * BP + rt * 16;
+  double af[2][4], c[2][2][2];
+#pragma unroll
+  for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+    for (int k4 = 0; k4 < 4; k4++) af[mi][k4] = Ap[(k4 * 4 + tg) * BP + mi * 8 + g];
+#pragma unroll
+  for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++) { c[mi][ni][0] = 0.0; c[mi][ni][1] = 0.0; }
+#pragma unroll
+  for (int k4 = 0; k4 < 4; k4++) {
+    double bf[2];
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++) bf[ni] = Wm[(k4 * 4 + tg) * MP + ni * 8 + g];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) dmma884(c[mi][ni][0], c[mi][ni][1], af[mi][k4], bf[ni]);
+  }
+  __syncwarp();                                       // every lane has read its A fragments: overwrite in place
+#pragma unroll
+  for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) Ap[(ni * 8 + 2 * tg + e) * BP + mi * 8 + g] = c[mi][ni][e];
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(512, 1)
+base_sweep4_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, double* __restrict__ Dinv,
+                   double* __restrict__ logdet_part, int* __restrict__ info, int gcol0, long long* __restrict__ prof) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* T = reinterpret_cast<double*>(smem_raw);   // [128][BP]
+  double* PdB = T + TILE * BP;
+  double* WmB = PdB + 2 * 16 * MP;
+  double* psh = WmB + 2 * 16 * MP;
+  double* dinv = psh + 64;                           // psh: 2 x (16 values + 16 zeros)
+  double* ldg = dinv + TILE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int BAR_A = 1, BAR_D = 3, BAR_BULK = 7;
+  // measurement (option "base_prof"): SM clock at the phase boundaries of the chain warp, slots 0..; see gpx_set_option
+#define GPX_STAMP(i) do { if (prof && tid == 0) prof[i] = clock64(); } while (0)
+  GPX_STAMP(0);
+  if (tid < 64) psh[tid] = 0.0;
+  // lower part of the tile -> shared memory, zeros above the diagonal (the inverse region starts from zero); 16-byte pieces
+#pragma unroll 8
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 512) {
+    const int row = (idx & 63) * 2, col = idx >> 6;
+    double2 v = make_double2(0.0, 0.0);
+    if (row + 1 >= col) v = *reinterpret_cast<const double2*>(S + row + (long)col * ld);
+    if (row < col) v.x = 0.0;
+    *reinterpret_cast<double2*>(T + col * BP + row) = v;
+  }
+  __syncthreads();
+  GPX_STAMP(1);
+  if (warp == 0) {
+    // ================= chain warp ======================================================================================
+    micro_diag_roll(T, 0, PdB, WmB, psh, dinv, ldg, info, gcol0, lane);
+    GPX_STAMP(2);
+    for (int jp = 0; jp < 8; jp++) {
+      const int c0 = jp * 16;
+      if (jp > 0) named_sync(BAR_D + ((jp - 1) & 1), 512);               // update of step jp-1 done: row block jp+1 is current
+      GPX_STAMP(3 + 4 * jp);
+      if (jp < 7) micro_panel_rows(T, c0, jp + 1, WmB + (jp & 1) * 16 * MP, lane);
+      named_arrive(BAR_A + (jp & 1), 512);
+      GPX_STAMP(4 + 4 * jp);
+      if (jp == 7) break;
+      micro_update<2>(T, c0, jp, jp + 1, jp + 1, 0, PdB + (jp & 1) * 16 * MP, lane);   // T(jp+1, jp+1) -= P P^T
+      __syncwarp();
+      GPX_STAMP(5 + 4 * jp);
+      micro_diag_roll(T, c0 + 16, PdB + ((jp + 1) & 1) * 16 * MP, WmB + ((jp + 1) & 1) * 16 * MP, psh, dinv, ldg, info, gcol0,
+                      lane);
+      GPX_STAMP(6 + 4 * jp);
+    }
+  } else {
+    // ================= bulk warps 1..15 =================================================================================
+    const int bw = warp - 1;
+    for (int jp = 0; jp < 8; jp++) {
+      const int c0 = jp * 16;
+      const double* Pd = PdB + (jp & 1) * 16 * MP;
+      const double* Wm = WmB + (jp & 1) * 16 * MP;
+      named_sync(BAR_A + (jp & 1), 512);
+      {   // micro-panel: the row blocks other than jp (diagonal) and jp+1 (done by the chain warp)
+        const int nrows = jp < 7 ? 6 : 7;
+        if (bw < nrows) {
+          int rt = bw;
+          if (rt >= jp) rt += (jp < 7 ? 2 : 1);
+          micro_panel_rows(T, c0, rt, Wm, lane);
+        }
+      }
+      named_sync(BAR_BULK, 480);
+      if (jp == 7) break;
+      int lin = 0;
+      for (int ct = jp + 1; ct < 8; ct++) {
+        const int nslot = jp + 1 + 8 - ct;                 // rows [0..jp] and [ct..7]
+        for (int slot = 0; slot < nslot; slot++) {
+          const int rt = slot <= jp ? slot : ct + slot - (jp + 1);
+          if (rt == jp + 1 && ct == jp + 1) continue;      // the next diagonal micro-block belongs to the chain warp
+          if (lin++ % 15 != bw) continue;
+          micro_update<2>(T, c0, jp, rt, ct, 0, Pd, lane);
+        }
+      }
+      named_arrive(BAR_D + (jp & 1), 512);
+      base_out_block(T, dinv, ldg, jp, tid - 32, 480, S, ld, Ldiag, Dinv);
+    }
+  }
+  __syncthreads();
+  GPX_STAMP(40);
+  base_out_block(T, dinv, ldg, 7, tid, 512, S, ld, Ldiag, Dinv);
+  if (tid < 32) {
+    double s = 0.0;
+    for (int j = tid; j < TILE; j += 32) s += log(ldg[j]);
+    s = warp_sum(s);
+    if (tid == 0) *logdet_part = 2.0 * s;
+  }
+  GPX_STAMP(41);
+#undef GPX_STAMP
+}
+
+static int g_base_version = 0;   // option "base" (process-wide): 0 = default / environment
+void set_base_version(int v) { g_base_version = v; }
+// option "base_prof": 1 = the fourth-generation base kernel stamps clock64() at its phase boundaries into a device buffer (the
+// last launch wins); 2 = print them (cycles since the kernel's start) to stderr. Measurement only.
+static long long* g_base_prof = nullptr;
+static bool g_base_prof_on = false;
+int set_base_prof(int v) {
+  if (v == 1) {
+    if (!g_base_prof) { GPX_CUDA(cudaMalloc(&g_base_prof, 64 * sizeof(long long))); GPX_CUDA(cudaMemset(g_base_prof, 0, 64 * sizeof(long long))); }
+    g_base_prof_on = true;
+  } else if (v == 2 && g_base_prof) {
+    long long h[64];
+    GPX_CUDA(cudaDeviceSynchronize());
+    GPX_CUDA(cudaMemcpy(h, g_base_prof, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "base_sweep4 phases (SM cycles since kernel start): load %lld | first micro-block %lld |", h[1] - h[0], h[2] - h[1]);
+    for (int jp = 0; jp < 8; jp++) {
+      fprintf(stderr, " [jp %d: wait %lld panel-piece %lld", jp, h[3 + 4 * jp] - (jp ? h[2 + 4 * jp] : h[2]), h[4 + 4 * jp] - h[3 + 4 * jp]);
+      if (jp < 7) fprintf(stderr, " update-piece %lld micro-block %lld]", h[5 + 4 * jp] - h[4 + 4 * jp], h[6 + 4 * jp] - h[5 + 4 * jp]);
+      else fprintf(stderr, "]");
+    }
+    fprintf(stderr, " | join %lld | last column block + logdet %lld | total %lld\n", h[40] - h[32], h[41] - h[40], h[41] - h[0]);
+  } else {
+    g_base_prof_on = false;
+  }
+  return 0;
+}
+
 int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
                 cudaStream_t st) {
-  static int which = -1;
-  constexpr int smem16 = (TILE * BP + 4 * 16 * MP + 32 + 2 * TILE) * 8;
-  if (which < 0) {
-    which = getenv("GPX_BASE_V1") ? 1 : 2;
+  static bool ready = false;
+  constexpr int smem16 = (TILE * BP + 4 * 16 * MP + 64 + 2 * TILE) * 8 + 16;
+  int which = g_base_version;
+  if (which <= 0) {
+    const char* e = getenv("GPX_BASE");          // 4 (default) = chain warp runs ahead, 3 = row-per-lane chain warp with block
+    which = e ? atoi(e) : (getenv("GPX_BASE_V1") ? 1 : 4);   // barriers, 2 = round-2 kernel, 1 = round-1 kernel
+    if (which < 1 || which > 4) which = 4;
+  }
+  if (!ready) {
+    ready = true;
     GPX_CUDA(cudaFuncSetAttribute(base_sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    GPX_CUDA(cudaFuncSetAttribute(base_sweep3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    GPX_CUDA(cudaFuncSetAttribute(base_sweep4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
   }
   if (which == 1) base_sweep_kernel<<<1, 512, 0, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
-  else base_sweep16_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
+  else if (which == 2) base_sweep16_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
+  else if (which == 3) base_sweep3_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
+  else base_sweep4_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0, g_base_prof_on ? g_base_prof : nullptr);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

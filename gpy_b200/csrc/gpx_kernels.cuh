@@ -16,6 +16,7 @@ struct KBuildParams {
   const double* diag_vec;              // optional per-point noise variances added on the diagonal as well (sym mode)
   int own_G, own_g, own_blk;           // multi-GPU: only row tiles with ((rt / own_blk) % own_G) == own_g (0 = all)
   int loc_rows;                        // multi-GPU: `out` holds only the owned block rows (row tile rt at loc_tile(rt, ..))
+  int rt0;                             // first row tile of this launch (the grid's y index counts from here)
   KernParams kp;
 };
 
@@ -44,6 +45,8 @@ int launch_prep_x(const double* X, long N, long ldx, const KernParams& kp, doubl
 int launch_kbuild(const KBuildParams& p, int row_tiles, int col_tiles, cudaStream_t st);
 int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
                 cudaStream_t st);
+void set_base_version(int v);   // 0 = default (3), 1..3 = generation of the base-block kernel (measurement / regression)
+int set_base_prof(int v);       // measurement: phase clocks of the base-block kernel (option "base_prof")
 int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp, double* Tm, cudaStream_t st);
 int launch_fw_block(const double* Tm, int nb, const double* yres, long ld, int P, double* t, cudaStream_t st);
 int launch_fw_panel(const double* Pb, long ldp, long rows, int nb, const double* t, long ld, int P, double* yres,

@@ -1,10 +1,11 @@
 // gpx_ozaki.cu — the trailing update and K^-1 = U U^T of the factor-and-invert sweep on the 5th-generation tensor cores.
 //
 // tcgen05.mma has no f64 kind, so fp64-grade products are formed by an Ozaki split on kind::i8 (exact s32 accumulation):
-//   every row of a panel P (rows x K) is scaled by a power of two to (-1, 1) and cut into 8 signed 7-bit digits (int8 planes),
+//   every row of a panel P (rows x K) is scaled by a power of two to (-1/2, 1/2) and cut into 8 signed digits of 7 bits, rounded
+//   to nearest (|digit| <= 64; int8 planes),
 //   P_r P_c^T = sum_{s+t <= 7} 2^(e_r + e_c - 7 (s+t+2)) D_s(r) D_t(c)^T; the 36 digit-pair products of a 32-deep k-chunk are
 //   36 tcgen05.mma (128 x 64 x 32) accumulated per exponent group g = s + t in its own 64 TMEM columns (8 groups = all 512
-//   columns of the SM), |digit product sum| <= 127^2 * K * 8 < 2^31 for K <= 16384; the epilogue converts the groups to
+//   columns of the SM), |digit product sum| <= 64^2 * K * 8 < 2^31 for K <= 65536; the epilogue converts the groups to
 //   fp64, sums them smallest first, rescales by the row/column exponents and applies the result to the fp64 target tile.
 // Replaces the same reference work as the DMMA GEMM of gpx_gemm.cu: LAPACK dpotrf / dtrtri / dpotri behind
 // GPy/util/linalg.py:58,142,209-212 (see DESIGN.md §5 for the digit budget against the 1e-8 / 1e-6 tolerances).
@@ -119,9 +120,9 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     double inv = 0.0, sc = 0.0;
     if (amax >= 1e-290 && amax <= 1e290) {   // rows of zeros (padding) and non-finite rows get all-zero digits
       int e = 0;
-      frexp(amax, &e);                        // amax = m 2^e, m in [0.5, 1): |x| 2^-e < 1 for the whole row
-      inv = ldexp(1.0, -e);
-      sc = ldexp(1.0, e - 7);                 // value = 2^e sum_s d_s 2^(-7 (s+1)); the 2^-7 of both operands folded in here
+      frexp(amax, &e);                        // amax = m 2^e, m in [0.5, 1): |x| 2^-(e+1) < 1/2 for the whole row
+      inv = ldexp(1.0, -(e + 1));
+      sc = ldexp(1.0, e + 1 - 7);             // value = 2^(e+1) sum_s d_s 2^(-7 (s+1)); the 2^-7 of both operands folded in here
     }
     sinv[rl] = inv;
     scale[row] = sc;
@@ -136,12 +137,15 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     for (int s = 0; s < OZ_S; s++) { w[s][0] = 0; w[s][1] = 0; w[s][2] = 0; w[s][3] = 0; }
 #pragma unroll
     for (int kk = 0; kk < 16; kk++) {
-      double x = prow[((long)kc * OZ_KC + half * 16 + kk) * ld] * inv;   // exact (power of two), |x| < 1
+      double x = prow[((long)kc * OZ_KC + half * 16 + kk) * ld] * inv;   // exact (power of two), |x| < 1/2
 #pragma unroll
       for (int s = 0; s < OZ_S; s++) {
-        x *= 128.0;                              // exact
-        const int d = __double2int_rz(x);        // |d| <= 127
-        x -= (double)d;                          // exact, same sign, |x| < 1
+        // round-to-nearest digits WITHOUT the conversion unit (F2I / I2F on fp64 run at a few lanes per SM and made this kernel
+        // 6x slower than its memory traffic): x + 1.5 * 2^52 rounds x to an integer whose two's complement sits in the low word
+        x *= 128.0;                                            // exact; |x| < 64 (first digit), <= 64 afterwards
+        const double t = x + 6755399441055744.0;               // 1.5 * 2^52
+        const int d = __double2loint(t);                       // rint(x), |d| <= 64
+        x -= (t - 6755399441055744.0);                         // exact remainder, |x| <= 1/2
         w[s][kk >> 2] |= ((uint32_t)d & 0xffu) << (8 * (kk & 3));
       }
     }
@@ -734,19 +738,39 @@ __global__ void __launch_bounds__(256) grad_kinv_kernel(GradKinvParams p) {
       double r2 = si + sSc[jl] - 2.0 * dot;
       if (gi == gj) r2 = 0.0;
       r2 = fmax(r2, 0.0);
-      const double rr = sqrt(r2) * inv_ls;
-      double k, dk;
-      k_dk_of_r_unit(kind, rr, k, dk);
       double aa = 0.0;
 #pragma unroll
       for (int q = 0; q < MAX_P; q++)
         if (q < P) aa = fma(ai[q], sAc[q * TILE + jl], aa);
       const double dl = 0.5 * (aa - (double)P * kinv);
-      gvar = fma(w * k, dl, gvar);
       if (gi == gj) {
         gnoise += dl;
         if (p.dnoise_out) p.dnoise_out[gi] = dl;
       }
+      if (kind == GPX_RBF) {
+        // dK/dr / r = -K for the RBF kernel (rbf.py:177-178 over stationary.py:205): neither the square root nor the division
+        // of the general form is needed; at r = 0 the reference's 1/0 := 0 multiplies (x_i - x_j)^2 = 0 either way
+        const double r2s = r2 * (inv_ls * inv_ls);
+        const double k = exp(-0.5 * r2s);
+        const double kd = w * k * dl;
+        gvar += kd;
+        const double tmpv = -variance * kd;
+        if (ard) {
+#pragma unroll
+          for (int q = 0; q < DREG; q++)
+            if (q < D) {
+              const double df = xi[q] - sXc[q * TILE + jl];
+              gq[q] = fma(tmpv, df * df, gq[q]);
+            }
+        } else {
+          giso = fma(tmpv, r2s, giso);
+        }
+        continue;
+      }
+      const double rr = sqrt(r2) * inv_ls;
+      double k, dk;
+      k_dk_of_r_unit(kind, rr, k, dk);
+      gvar = fma(w * k, dl, gvar);
       const double G = variance * dk * dl;
       if (ard) {
         const double tmpv = (rr != 0.0) ? w * G / rr : 0.0;     // stationary.py:205,225-232: 1/r with 1/0 := 0

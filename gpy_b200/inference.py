@@ -6,6 +6,7 @@ Mirrors (same names, argument meaning, return structure and error behaviour):
     GPy.inference.latent_function_inference.posterior.PosteriorExact
         GPy/inference/latent_function_inference/posterior.py:9-77,273-302
     GPy.likelihoods.Gaussian (the three one-liners on the path)  GPy/likelihoods/gaussian.py:69-79,102-110
+    GPy.likelihoods.HeteroscedasticGaussian / MixedNoise (vector noise)  GPy/likelihoods/gaussian.py:347-377, mixed_noise.py:14-53
 """
 import numpy as np
 
@@ -60,6 +61,49 @@ class HeteroscedasticGaussian(Gaussian):
         if full_cov:
             return mu, var + np.eye(var.shape[0]) * _s
         return mu, var + _s.reshape(-1, 1)
+
+
+class MixedNoise(Parameterized):
+    """GPy.likelihoods.MixedNoise (mixed_noise.py:14-53): a list of Gaussian likelihoods, data point n uses the one selected
+    by Y_metadata['output_index'][n]. For exact inference it is a heteroscedastic variance vector going in
+    (exact_gaussian_inference.py:52-56 -> gpx_exact_eval_het) and per-likelihood sums of diag(dL_dK) coming back."""
+
+    def __init__(self, likelihoods_list, name="mixed_noise"):
+        super(MixedNoise, self).__init__(name)
+        self.likelihoods_list = list(likelihoods_list)
+        if not all(isinstance(l, Gaussian) and not isinstance(l, HeteroscedasticGaussian) for l in self.likelihoods_list):
+            raise AssertionError("MixedNoise works with a list of Gaussian likelihoods")          # mixed_noise.py:24,39
+        self.link_parameters(*self.likelihoods_list)
+
+    def gaussian_variance(self, Y_metadata):
+        ind = np.asarray(Y_metadata["output_index"]).flatten()                                    # mixed_noise.py:23-29
+        variance = np.zeros(ind.size)
+        for j, lik in enumerate(self.likelihoods_list):
+            variance[ind == j] = float(lik.variance[0])
+        return variance
+
+    def betaY(self, Y, Y_metadata):
+        return Y / self.gaussian_variance(Y_metadata=Y_metadata)[:, None]                         # mixed_noise.py:31-33
+
+    def exact_inference_gradients(self, dL_dKdiag, Y_metadata):
+        ind = np.asarray(Y_metadata["output_index"]).flatten()                                    # mixed_noise.py:38-41
+        d = np.asarray(dL_dKdiag).reshape(-1)
+        return np.array([d[ind == i].sum() for i in range(len(self.likelihoods_list))])
+
+    def update_gradients(self, gradients):
+        g = np.asarray(gradients, dtype=np.float64).reshape(-1)                                   # mixed_noise.py:35-36: the
+        for lik, gi in zip(self.likelihoods_list, g):                                             # container gradient is the
+            lik.update_gradients(gi)                                                              # leaves' gradients in order
+
+    def predictive_values(self, mu, var, full_cov=False, Y_metadata=None):
+        ind = np.asarray(Y_metadata["output_index"]).flatten()                                    # mixed_noise.py:43-50
+        _variance = np.array([float(self.likelihoods_list[j].variance[0]) for j in ind])
+        if full_cov:
+            return mu, var + np.eye(var.shape[0]) * _variance
+        return mu, var + _variance.reshape(-1, 1)
+
+    def predictive_variance(self, mu, sigma, Y_metadata):
+        return self.gaussian_variance(Y_metadata) + sigma ** 2                                    # mixed_noise.py:52-54
 
 
 class PosteriorExact(object):

@@ -175,7 +175,10 @@ int gpx_measure_fp64_peak(gpx_ctx* ctx, double* tflops);
 
 /* Tunables (block sizes etc.), mainly for tests: name in {"nb", "lookahead", "profile", "ozaki" (0 = fp64 DMMA only,
  * 1 = trailing update and K^-1 on the tcgen05 int8 path where applicable, -1 = default), "oz_dig_up" (digits per operand
- * for the inverse-part tiles, 4..8), "oz_ctas" (CTAs of the persistent tcgen05 GEMM, 0 = one per SM)}. */
+ * for the inverse-part tiles, 4..8), "oz_ctas" (CTAs of the persistent tcgen05 GEMM, 0 = one per SM), "fine" (1 = 64 x 64-tile DMMA kernels inside
+ * the diagonal-block chain, 0 = 128 x 128 tiles), "chain" (1 = tcgen05 path: diagonal-block chain alone on the side stream, the
+ * rest of the panel / digit split / forward substitution on a third stream; 0 = round-2 schedule), "base" (generation of the
+ * 128 x 128 base-block kernel, process-wide: 0 = default, 1..3)}. */
 int gpx_set_option(gpx_ctx* ctx, const char* name, int64_t value);
 
 /* Multi-GPU (one process per GPU). The caller obtains a 128-byte NCCL unique id on rank 0 (gpx_comm_unique_id),

@@ -84,11 +84,12 @@ def load():
     egi = importlib.import_module("GPy.inference.latent_function_inference.exact_gaussian_inference")
     gauss = importlib.import_module("GPy.likelihoods.gaussian")
     vdtc = importlib.import_module("GPy.inference.latent_function_inference.var_dtc")
+    mixed = importlib.import_module("GPy.likelihoods.mixed_noise")
     ns = types.SimpleNamespace(
         VarDTC=vdtc.VarDTC,
         RBF=rbf.RBF, Exponential=stat.Exponential, Matern32=stat.Matern32, Matern52=stat.Matern52,
         ExactGaussianInference=egi.ExactGaussianInference, Gaussian=gauss.Gaussian,
-        HeteroscedasticGaussian=gauss.HeteroscedasticGaussian,
+        HeteroscedasticGaussian=gauss.HeteroscedasticGaussian, MixedNoise=mixed.MixedNoise,
         linalg=sys.modules["GPy.util.linalg"], diag=sys.modules["GPy.util.diag"], stationary=stat,
         __version__=open(os.path.join(REF, "GPy", "__version__.py")).read().split('"')[1])
     _loaded = ns
@@ -203,6 +204,27 @@ def evaluate_het(G, X, Y, kind, ARD, variance, lengthscale, noise_vec):
                            np.atleast_1d(kern.lengthscale.gradient).reshape(-1),
                            np.asarray(lik.variance.gradient).reshape(-1)])
     return dict(lml=float(lml), grad=grad, alpha=np.asarray(posterior.woodbury_vector))
+
+
+def evaluate_mixed(G, X, Y, kind, ARD, variance, lengthscale, noise_list, output_index):
+    """Exact inference with the reference's own MixedNoise likelihood (likelihoods/mixed_noise.py:14-41): one Gaussian per
+    output index; the three calls of GP.parameters_changed (core/gp.py:278-280). The container's gradient assignment
+    (`self.gradient = gradients`, mixed_noise.py:35-36) is paramz routing the vector to the leaves in link order; with the
+    observer-free stand-in that is done here."""
+    import numpy as np
+    N, D = X.shape
+    Y_metadata = {"output_index": np.asarray(output_index).reshape(-1, 1)}
+    kern = getattr(G, KERNELS[kind])(D, variance=variance, lengthscale=lengthscale, ARD=ARD)
+    liks = [G.Gaussian(variance=float(v), name="Gaussian_noise_%d" % j) for j, v in enumerate(noise_list)]
+    lik = G.MixedNoise(liks)
+    inf = G.ExactGaussianInference()
+    posterior, lml, grad_dict = inf.inference(kern, X, lik, Y, None, Y_metadata)   # gp.py:278
+    kern.update_gradients_full(grad_dict["dL_dK"], X)                               # gp.py:280
+    grad = np.concatenate([np.atleast_1d(kern.variance.gradient).reshape(-1),
+                           np.atleast_1d(kern.lengthscale.gradient).reshape(-1),
+                           np.asarray(grad_dict["dL_dthetaL"]).reshape(-1)])
+    return dict(lml=float(lml), grad=grad, alpha=np.asarray(posterior.woodbury_vector),
+                variance=np.asarray(lik.gaussian_variance(Y_metadata)), likelihood=lik, Y_metadata=Y_metadata)
 
 
 def evaluate_sparse(G, X, Y, Z, kind, ARD, variance, lengthscale, noise):

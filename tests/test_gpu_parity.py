@@ -442,6 +442,34 @@ def test_heteroscedastic_noise(kind, ARD, N, D, P):
     e.close()
 
 
+def test_mixed_noise_model():
+    """MixedNoise (likelihoods/mixed_noise.py:14-53) through the heteroscedastic device path: one Gaussian per output index;
+    parameter vector [variance, lengthscale, noise_0, noise_1], LML / gradients against the oracle (pinned to the reference's
+    MixedNoise objects in tests/test_reference_crosscheck.py), gradient check, prediction with Y_metadata."""
+    rng = np.random.default_rng(11)
+    N, D = 300, 2
+    X, Y = o.synthetic(N, D, 21)
+    idx = rng.integers(0, 2, N)
+    md = {"output_index": idx[:, None]}
+    lik = gpy_b200.MixedNoise([gpy_b200.Gaussian(0.04), gpy_b200.Gaussian(0.25)])
+    m = gpy_b200.GP(X, Y, gpy_b200.RBF(D, variance=1.2, lengthscale=[1.1, 1.9], ARD=True), lik, Y_metadata=md)
+    nv = np.array([0.04, 0.25])[idx]
+    lml0, g0, res = o.eval_lml_grad(X, Y, "rbf", True, 1.2, np.array([1.1, 1.9]), nv)
+    assert abs(m.log_likelihood() - lml0) <= LML_ATOL
+    dn = g0[1 + D:]
+    want = np.concatenate([g0[:1 + D], [dn[idx == 0].sum(), dn[idx == 1].sum()]])
+    assert len(m.gradient) == 1 + D + 2
+    np.testing.assert_allclose(m.gradient, want, rtol=GRAD_RTOL, atol=1e-9)
+    assert m.checkgrad()
+    Xn = rng.uniform(-2, 2, (6, D))
+    mdn = {"output_index": np.array([0, 1, 1, 0, 0, 1])[:, None]}
+    mu, var = m.predict(Xn, Y_metadata=mdn)
+    ko = o.StationaryOracle("rbf", D, 1.2, np.array([1.1, 1.9]), True)
+    mu0, var0 = o.raw_predict(ko, X, res["L"], res["alpha"], Xn)
+    np.testing.assert_allclose(mu, mu0, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var, var0 + np.array([0.04, 0.25])[mdn["output_index"]], rtol=1e-7, atol=1e-9)
+
+
 def test_sparse_golden_fixtures():
     """tests/golden/sparse/*.npz: bound, gradients and inducing-input gradients produced by the reference's own VarDTC."""
     gdir = os.path.join(os.path.dirname(__file__), "golden", "sparse")
