@@ -115,6 +115,14 @@ int gpx_create(int device, gpx_ctx** out) {
   GPX_CUDA(cudaMalloc(&c->info, sizeof(int)));
   GPX_CUDA(cudaMallocHost(&c->h_res, (MAX_D + 2 * MAX_PARTS + 8) * sizeof(double)));
   GPX_CUDA(cudaMallocHost(&c->h_info, sizeof(int)));
+  {   // keep freed temporaries of the stand-alone calls cached in the device's default pool
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = 1ull << 30;   // up to 1 GiB stays cached; anything above goes back at the next synchronisation
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   GPX_CHECK(gemm_init());
   GPX_CHECK(oz_init());
   GPX_CHECK(fine_init());
@@ -185,8 +193,9 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "lookahead")) { c->lookahead = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "base")) { set_base_version((int)std::max<int64_t>(0, std::min<int64_t>(value, 4))); return 0; }
+  if (!strcmp(name, "base")) { set_base_version((int)std::max<int64_t>(0, std::min<int64_t>(value, 5))); return 0; }
   if (!strcmp(name, "base_prof")) return set_base_prof((int)value);
+  if (!strcmp(name, "base_pdl")) { set_base_pdl((int)value); return 0; }
   if (!strcmp(name, "fine")) { c->fine = value ? 1 : 0; return 0; }
   if (!strcmp(name, "chain")) { c->chain = value ? 1 : 0; return 0; }
   GPX_FAIL("unknown option");
@@ -769,11 +778,15 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     c->oz_last = true;   // K^-1 is stored either way
     return 0;
   }
+  long grad_tiles = (long)nt * nt;
   if (oz) {
     // K^-1 was accumulated panel by panel inside the sweep (tcgen05): reduce dL_dK -> gradients from the stored tiles
-    GPX_CUDA(cudaMemsetAsync(c->partials, 0, (size_t)nt * nt * (nl + 2) * 8, st));
+    const int csplit = grad_kinv_csplit(nt, nl + 2);
+    grad_tiles = (long)nt * nt * csplit;
+    GPX_CUDA(cudaMemsetAsync(c->partials, 0, (size_t)grad_tiles * (nl + 2) * 8, st));
     GradKinvParams gk;
     memset(&gk, 0, sizeof(gk));
+    gk.csplit = csplit;
     gk.Kinv = c->Kinv; gk.ld = ld;
     gk.XsT = c->dXsT; gk.sq = c->dsq; gk.alpha = c->dAlpha; gk.ldx = c->Npad;
     gk.N = c->N; gk.P = c->P; gk.nt = nt;
@@ -784,13 +797,39 @@ static int eval_once(gpx_ctx* c, double extra_jitter, Recorder& rec) {
     GPX_CHECK(launch_grad_kinv(gk, st));
     rec.end(h);
     c->eval_launches++;
+  } else if (c->fine && nt <= 8 && !c->dist) {
+    // small matrix on the DMMA path (one block, or tcgen05 switched off): the fused LAUUM kernel has one CTA per 128 x 128 tile
+    // -- 10 CTAs for N = 512, each walking up to 512 k alone (136 us of a 0.48 ms evaluation). K^-1 = U U^T in 64 x 32 tiles
+    // (80 CTAs) into the K^-1 buffer, then the gradient pass over the stored tiles, split over the columns
+    if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)ld * ld * 8));
+    const int h = rec.begin(PH_LAUUM, 0.0);
+    FineParams fl{};
+    fl.mode = FINE_LAUUM;
+    fl.A = c->S; fl.lda = ld; fl.B = c->S; fl.ldb = ld; fl.C = c->Kinv; fl.ldc = ld; fl.K = (int)c->Npad; fl.nt = nt;
+    GPX_CHECK(launch_fine(fl, st));
+    const int csplit = grad_kinv_csplit(nt, nl + 2);
+    grad_tiles = (long)nt * nt * csplit;
+    GPX_CUDA(cudaMemsetAsync(c->partials, 0, (size_t)grad_tiles * (nl + 2) * 8, st));
+    GradKinvParams gk;
+    memset(&gk, 0, sizeof(gk));
+    gk.csplit = csplit;
+    gk.Kinv = c->Kinv; gk.ld = ld;
+    gk.XsT = c->dXsT; gk.sq = c->dsq; gk.alpha = c->dAlpha; gk.ldx = c->Npad;
+    gk.N = c->N; gk.P = c->P; gk.nt = nt;
+    gk.partials = c->partials;
+    gk.dnoise_out = c->het ? c->dDnoise : nullptr;
+    gk.kp = c->kp;
+    GPX_CHECK(launch_grad_kinv(gk, st));
+    rec.end(h);
+    c->eval_launches += 2;
+    c->oz_last = true;   // K^-1 is stored
   } else {
     GPX_CHECK(run_lauum(c, nullptr, &rec));
   }
   {
     FinalizeParams f;
     memset(&f, 0, sizeof(f));
-    f.partials = c->partials; f.ntiles = (long)nt * nt; f.nl = nl;
+    f.partials = c->partials; f.ntiles = grad_tiles; f.nl = nl;
     f.logdet_part = c->logdet_part; f.nt = nt;
     f.T = oz ? c->dTfw : c->dT; f.ld = ld; f.N = c->N; f.P = c->P;
     f.kp = c->kp;
@@ -1066,15 +1105,23 @@ static int scratch_ctx(gpx_ctx** out) {
   return 0;
 }
 
+// Temporaries of the stand-alone kernel calls and of gpx_predict: stream-ordered allocations from the device's default memory
+// pool (cudaMallocAsync / cudaFreeAsync on the context's stream; gpx_create raises the pool's release threshold so that freed
+// blocks stay cached). A plain cudaMalloc / cudaFree pair per call is a device-wide synchronisation point inside any
+// optimiser loop that uses foreign inference (round-1 review).
+#define GPX_TMP_ALLOC(ptr, bytes, st) GPX_CUDA(cudaMallocAsync((void**)(ptr), (bytes), (st)))
+#define GPX_TMP_FREE(p, st) do { if (p) cudaFreeAsync((p), (st)); } while (0)
+
 struct PointSet {
   double* raw = nullptr; double* xT = nullptr; double* sq = nullptr; long n = 0, ld = 0;
-  ~PointSet() { if (raw) cudaFree(raw); if (xT) cudaFree(xT); if (sq) cudaFree(sq); }
+  cudaStream_t st = nullptr;
+  ~PointSet() { GPX_TMP_FREE(raw, st); GPX_TMP_FREE(xT, st); GPX_TMP_FREE(sq, st); }
 };
 static int upload_points(gpx_ctx* c, const double* X, long n, const KernParams& kp, PointSet& ps) {
-  ps.n = n; ps.ld = (n + TILE - 1) / TILE * TILE;
-  GPX_CUDA(cudaMalloc(&ps.raw, (size_t)n * kp.D * 8));
-  GPX_CUDA(cudaMalloc(&ps.xT, (size_t)ps.ld * kp.D * 8));
-  GPX_CUDA(cudaMalloc(&ps.sq, (size_t)ps.ld * 8));
+  ps.n = n; ps.ld = (n + TILE - 1) / TILE * TILE; ps.st = c->st;
+  GPX_TMP_ALLOC(&ps.raw, (size_t)n * kp.D * 8, c->st);
+  GPX_TMP_ALLOC(&ps.xT, (size_t)ps.ld * kp.D * 8, c->st);
+  GPX_TMP_ALLOC(&ps.sq, (size_t)ps.ld * 8, c->st);
   GPX_CUDA(cudaMemcpyAsync(ps.raw, X, (size_t)n * kp.D * 8, cudaMemcpyHostToDevice, c->st));
   GPX_CHECK(launch_prep_x(ps.raw, n, ps.ld, kp, ps.xT, ps.sq, c->st));
   c->total_launches++;
@@ -1095,7 +1142,7 @@ int gpx_kern_K(gpx_ctx* c, int kind, int ard, double variance, const double* len
   if (X2) GPX_CHECK(upload_points(c, X2, M, kp, p2));
   PointSet& pj = X2 ? p2 : p1;   // thread-mapped operand = X2 points (contiguous index of the row-major output)
   double* dout = nullptr;
-  GPX_CUDA(cudaMalloc(&dout, (size_t)N * M * 8));
+  GPX_TMP_ALLOC(&dout, (size_t)N * M * 8, c->st);
   KBuildParams kb;
   memset(&kb, 0, sizeof(kb));
   kb.rowsT = pj.xT; kb.ld_rows = pj.ld; kb.sq_rows = pj.sq;
@@ -1117,7 +1164,7 @@ int gpx_kern_K(gpx_ctx* c, int kind, int ard, double variance, const double* len
     cudaEventElapsedTime(&c->stats.kbuild_ms, e0, e1);
     c->stats.kbuild_bytes = 8.0 * (double)N * M + 8.0 * (double)(N + M) * D;
   }
-  cudaFree(dout);
+  GPX_TMP_FREE(dout, c->st);
   return rc;
 }
 
@@ -1144,8 +1191,8 @@ int gpx_kern_grad_full(gpx_ctx* c, int kind, int ard, double variance, const dou
   double* dd = nullptr; double* dpart = nullptr;
   const int tj = (int)(pj.ld / TILE), ti = (int)(p1.ld / TILE);
   const int nl = ard ? D : 1, nred = nl + 1;
-  GPX_CUDA(cudaMalloc(&dd, (size_t)N * M * 8));
-  GPX_CUDA(cudaMalloc(&dpart, (size_t)tj * ti * nred * 8));
+  GPX_TMP_ALLOC(&dd, (size_t)N * M * 8, c->st);
+  GPX_TMP_ALLOC(&dpart, (size_t)tj * ti * nred * 8, c->st);
   GPX_CUDA(cudaMemcpyAsync(dd, dL_dK, (size_t)N * M * 8, cudaMemcpyHostToDevice, c->st));
   GradFullParams gp;
   memset(&gp, 0, sizeof(gp));
@@ -1157,7 +1204,7 @@ int gpx_kern_grad_full(gpx_ctx* c, int kind, int ard, double variance, const dou
   std::vector<double> hp((size_t)tj * ti * nred);
   if (rc == 0 && cudaMemcpyAsync(hp.data(), dpart, hp.size() * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
   if (cudaStreamSynchronize(c->st) != cudaSuccess) { gpx::set_error("gpx_kern_grad_full: device failure"); rc = -1; }
-  cudaFree(dd); cudaFree(dpart);
+  GPX_TMP_FREE(dd, c->st); GPX_TMP_FREE(dpart, c->st);
   if (rc) return rc;
   std::vector<double> tot(nred, 0.0);
   for (size_t t = 0; t < (size_t)tj * ti; t++)
@@ -1185,9 +1232,9 @@ int gpx_kern_grad_X(gpx_ctx* c, int kind, int ard, double variance, const double
   const long mchunk = ((M + nchunk - 1) / nchunk + 31) / 32 * 32;
   nchunk = (int)((M + mchunk - 1) / mchunk);
   double *dd = nullptr, *dpart = nullptr, *dout = nullptr;
-  GPX_CUDA(cudaMalloc(&dd, (size_t)N * M * 8));
-  GPX_CUDA(cudaMalloc(&dpart, (size_t)nchunk * N * D * 8));
-  GPX_CUDA(cudaMalloc(&dout, (size_t)N * D * 8));
+  GPX_TMP_ALLOC(&dd, (size_t)N * M * 8, c->st);
+  GPX_TMP_ALLOC(&dpart, (size_t)nchunk * N * D * 8, c->st);
+  GPX_TMP_ALLOC(&dout, (size_t)N * D * 8, c->st);
   GPX_CUDA(cudaMemcpyAsync(dd, dL_dK, (size_t)N * M * 8, cudaMemcpyHostToDevice, c->st));
   GradFullParams gp;
   memset(&gp, 0, sizeof(gp));
@@ -1198,7 +1245,7 @@ int gpx_kern_grad_X(gpx_ctx* c, int kind, int ard, double variance, const double
   c->total_launches += 2;
   if (rc == 0 && cudaMemcpyAsync(grad, dout, (size_t)N * D * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
   if (cudaStreamSynchronize(c->st) != cudaSuccess) { gpx::set_error("gpx_kern_grad_X: device failure"); rc = -1; }
-  cudaFree(dd); cudaFree(dpart); cudaFree(dout);
+  GPX_TMP_FREE(dd, c->st); GPX_TMP_FREE(dpart, c->st); GPX_TMP_FREE(dout, c->st);
   return rc;
 }
 
@@ -1336,10 +1383,10 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   const long ld = c->Npad, N = c->N;
   PointSet pn;
   if (c->multi) {   // composite kernel: stacked per-part scaled coordinates of the new points
-    pn.n = M; pn.ld = (M + TILE - 1) / TILE * TILE;
-    GPX_CUDA(cudaMalloc(&pn.raw, (size_t)M * c->D * 8));
-    GPX_CUDA(cudaMalloc(&pn.xT, (size_t)pn.ld * std::max(1, c->mk.sumD) * 8));
-    GPX_CUDA(cudaMalloc(&pn.sq, (size_t)pn.ld * c->mk.nparts * 8));
+    pn.n = M; pn.ld = (M + TILE - 1) / TILE * TILE; pn.st = c->st;
+    GPX_TMP_ALLOC(&pn.raw, (size_t)M * c->D * 8, c->st);
+    GPX_TMP_ALLOC(&pn.xT, (size_t)pn.ld * std::max(1, c->mk.sumD) * 8, c->st);
+    GPX_TMP_ALLOC(&pn.sq, (size_t)pn.ld * c->mk.nparts * 8, c->st);
     GPX_CUDA(cudaMemcpyAsync(pn.raw, Xnew, (size_t)M * c->D * 8, cudaMemcpyHostToDevice, st));
     GPX_CHECK(launch_prep_multi(pn.raw, M, c->D, pn.ld, c->mk, pn.xT, pn.sq, st));
     c->total_launches++;
@@ -1347,8 +1394,8 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   GPX_CHECK(upload_points(c, Xnew, M, c->kp, pn));
   // Kx as [M][ld] (each new point one zero-padded column of length ld): thread-mapped operand = training points
   double* Kx = nullptr; double* Tx = nullptr;
-  GPX_CUDA(cudaMalloc(&Kx, (size_t)pn.ld * ld * 8));
-  GPX_CUDA(cudaMalloc(&Tx, (size_t)pn.ld * ld * 8));
+  GPX_TMP_ALLOC(&Kx, (size_t)pn.ld * ld * 8, c->st);
+  GPX_TMP_ALLOC(&Tx, (size_t)pn.ld * ld * 8, c->st);
   GPX_CUDA(cudaMemsetAsync(Kx, 0, (size_t)pn.ld * ld * 8, st));
   if (dG > 1) GPX_CUDA(cudaMemsetAsync(Tx, 0, (size_t)pn.ld * ld * 8, st));   // columns of other ranks stay zero
   KBuildParams kb;
@@ -1378,7 +1425,7 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   if (!full_cov) {
     // diagonal variance: everything reduces on the device; only M (P + 1) doubles come back
     double* red = nullptr;   // [P][M] means, then [M] sums of squares
-    if (rc == 0 && cudaMalloc(&red, (size_t)(c->P + 1) * M * 8) != cudaSuccess) { gpx::set_error("gpx_predict: out of memory"); rc = -1; }
+    if (rc == 0 && cudaMallocAsync((void**)&red, (size_t)(c->P + 1) * M * 8, c->st) != cudaSuccess) { gpx::set_error("gpx_predict: out of memory"); rc = -1; }
     if (rc == 0) rc = launch_col_dot(Kx, ld, N, M, c->P, c->dAlpha, ld, red, M, st);              // mu = Kx^T alpha
     if (rc == 0) rc = launch_col_sqnorm(Tx, ld, c->Npad, M, red + (size_t)c->P * M, st);          // sum_i tmp_i^2
     if (rc == 0 && dG > 1) rc = dist_allreduce_sum(c, red + (size_t)c->P * M, (size_t)M, st);
@@ -1386,8 +1433,8 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
     std::vector<double> h((size_t)(c->P + 1) * M);
     if (rc == 0 && cudaMemcpyAsync(h.data(), red, h.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
-    cudaFree(Kx); cudaFree(Tx);
-    if (red) cudaFree(red);
+    GPX_TMP_FREE(Kx, c->st); GPX_TMP_FREE(Tx, c->st);
+    GPX_TMP_FREE(red, c->st);
     if (rc) return rc;
     for (long m = 0; m < M; m++) {
       for (int q = 0; q < c->P; q++) mu[m * c->P + q] = h[(size_t)q * M + m];
@@ -1421,7 +1468,7 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
       if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
     }
   }
-  cudaFree(Kx); cudaFree(Tx);
+  GPX_TMP_FREE(Kx, c->st); GPX_TMP_FREE(Tx, c->st);
   if (rc) return rc;
   // full covariance (small M): host epilogue mu = Kx^T alpha, var = Kxx - tmp^T tmp
   for (long m = 0; m < M; m++)
@@ -1435,12 +1482,12 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
   for (int q = 0; q < MAX_D; q++) lsv[q] = c->kp.ls[q];
   if (c->multi) {   // K(Xnew, Xnew) of the composite kernel, built on the device
     PointSet pm;
-    pm.n = M; pm.ld = (M + TILE - 1) / TILE * TILE;
+    pm.n = M; pm.ld = (M + TILE - 1) / TILE * TILE; pm.st = c->st;
     double* dk = nullptr;
-    GPX_CUDA(cudaMalloc(&pm.raw, (size_t)M * c->D * 8));
-    GPX_CUDA(cudaMalloc(&pm.xT, (size_t)pm.ld * std::max(1, c->mk.sumD) * 8));
-    GPX_CUDA(cudaMalloc(&pm.sq, (size_t)pm.ld * c->mk.nparts * 8));
-    GPX_CUDA(cudaMalloc(&dk, (size_t)M * M * 8));
+    GPX_TMP_ALLOC(&pm.raw, (size_t)M * c->D * 8, c->st);
+    GPX_TMP_ALLOC(&pm.xT, (size_t)pm.ld * std::max(1, c->mk.sumD) * 8, c->st);
+    GPX_TMP_ALLOC(&pm.sq, (size_t)pm.ld * c->mk.nparts * 8, c->st);
+    GPX_TMP_ALLOC(&dk, (size_t)M * M * 8, c->st);
     GPX_CUDA(cudaMemcpyAsync(pm.raw, Xnew, (size_t)M * c->D * 8, cudaMemcpyHostToDevice, st));
     rc = launch_prep_multi(pm.raw, M, c->D, pm.ld, c->mk, pm.xT, pm.sq, st);
     KBuildMultiParams km;
@@ -1451,7 +1498,7 @@ int gpx_predict(gpx_ctx* c, const double* Xnew, int64_t M, int full_cov, double*
     c->total_launches += 2;
     if (rc == 0 && cudaMemcpyAsync(kxx.data(), dk, (size_t)M * M * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) { gpx::set_error("gpx_predict: device failure"); rc = -1; }
-    cudaFree(dk);
+    GPX_TMP_FREE(dk, c->st);
   } else
   rc = gpx_kern_K(c, c->kp.kind, c->kp.ard, c->kp.variance, lsv, Xnew, M, nullptr, M, c->D, kxx.data());
   if (rc) return rc;

@@ -40,6 +40,12 @@ __device__ __forceinline__ bool fine_decode(const FineParams& p, int& r, int& c,
     r = slot < p.rlow ? slot : c + (slot - p.rlow);
     if (r >= p.nt) return false;
     return !(r == c && sm == 0 && sn >= 2);      // diagonal tile: rows 0..63 x columns 64..127 lie above the diagonal
+  } else if (MODE == FINE_LAUUM) {
+    r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while (r * (r + 1) / 2 > t) --r;
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    c = t - r * (r + 1) / 2;
+    return r < p.nt;
   } else {
     const int cc = t % p.nc;
     c = p.tri ? p.nc - 1 - cc : cc;      // longest k-range first
@@ -65,11 +71,15 @@ __global__ void __launch_bounds__(F_THREADS, 2) gemm_fine_kernel(const FineParam
   double* sA = reinterpret_cast<double*>(smem_raw);
   double* sB = sA + FSTAGES * F_STAGE_A;
 
+  // the base-block kernel that follows in the diagonal-block chain is launched as a programmatic dependent: let it become
+  // resident now (it warms its instruction cache and then waits for this grid to complete)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   int r, c, sm, sn;
   if (!fine_decode<MODE>(p, r, c, sm, sn)) return;
   int kmax = p.K;
   if (MODE == FINE_PANEL && p.tri) kmax = min(p.K, c * TILE + FTN * (sn + 1));
-  const int nchunk = kmax / FKC;
+  const int it0 = MODE == FINE_LAUUM ? r * (TILE / FKC) : 0;     // first k-chunk
+  const int nchunk = kmax / FKC - it0;
   const double* Aptr = p.A + (long)r * TILE + sm * FTM;
   const double* Bptr = p.B + (long)c * TILE + sn * FTN;
   const long lda = p.lda, ldb = p.ldb;
@@ -78,7 +88,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) gemm_fine_kernel(const FineParam
   auto load_stage = [&](int it) {
     if (it < nchunk) {
       const int s = it % FSTAGES;
-      const long k0 = (long)it * FKC;
+      const long k0 = (long)(it0 + it) * FKC;
       double* dA = sA + s * F_STAGE_A;
       double* dB = sB + s * F_STAGE_B;
 #pragma unroll
@@ -215,6 +225,7 @@ fine_panel_inplace_kernel(double* __restrict__ Sblk, long ld, const double* __re
 int fine_init() {
   GPX_CUDA(cudaFuncSetAttribute(gemm_fine_kernel<FINE_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
   GPX_CUDA(cudaFuncSetAttribute(gemm_fine_kernel<FINE_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+  GPX_CUDA(cudaFuncSetAttribute(gemm_fine_kernel<FINE_LAUUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
   GPX_CUDA(cudaFuncSetAttribute(fine_panel_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IP_SMEM));
   return 0;
 }
@@ -229,6 +240,10 @@ int launch_fine(const FineParams& p0, cudaStream_t st) {
     const int nslots = p.rlow + (p.nt - p.c0);
     grid = (unsigned)(nslots * p.ncols * F_SUB);
     gemm_fine_kernel<FINE_UPDATE><<<grid, F_THREADS, F_SMEM, st>>>(p);
+  } else if (p.mode == FINE_LAUUM) {
+    if (p.nt <= 0) return 0;
+    grid = (unsigned)(p.nt * (p.nt + 1) / 2 * F_SUB);
+    gemm_fine_kernel<FINE_LAUUM><<<grid, F_THREADS, F_SMEM, st>>>(p);
   } else {
     if (p.nr <= 0 || p.nc <= 0) return 0;
     grid = (unsigned)(p.nr * p.nc * F_SUB);

@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include <cstdio>
+#include <cstring>
 
 #include "gpx_kernels.cuh"
 
@@ -682,7 +683,7 @@ __device__ __forceinline__ void named_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ void micro_diag_row2(double* T, int c0, double* Pd, double* Wm, double* psh, double* dinv,
+__device__ __noinline__ void micro_diag_row2(double* T, int c0, double* Pd, double* Wm, double* psh, double* dinv,
                                                 double* ldg, int* info, int gcol0, int lane) {
   const int rr = lane & 15;
   double v[16];
@@ -817,9 +818,10 @@ __device__ __forceinline__ void micro_panel_rows(double* T, int c0, int rt, cons
   __syncwarp();
 }
 
+template <bool ROLL>
 __global__ void __launch_bounds__(512, 1)
 base_sweep4_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, double* __restrict__ Dinv,
-                   double* __restrict__ logdet_part, int* __restrict__ info, int gcol0, long long* __restrict__ prof) {
+                   double* __restrict__ logdet_part, int* __restrict__ info, int gcol0, long long* __restrict__ prof, int warm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* T = reinterpret_cast<double*>(smem_raw);   // [128][BP]
   double* PdB = T + TILE * BP;
@@ -833,6 +835,21 @@ base_sweep4_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, 
 #define GPX_STAMP(i) do { if (prof && tid == 0) prof[i] = clock64(); } while (0)
   GPX_STAMP(0);
   if (tid < 64) psh[tid] = 0.0;
+  // Launched as a programmatic dependent of the kernel before it (warm != 0): this CTA is resident while that kernel still
+  // runs. The time is used to pull the chain warp's code into the instruction cache: one column sweep on an identity block
+  // in the (still unused) tile buffer -- measured in situ, the first micro-block of a launch costs 25 000-30 000 cycles against
+  // 6 500 for the later ones. griddepcontrol.wait then blocks until the preceding kernel has completed and flushed.
+  if (warm) {
+    if (warp == 0) {
+      for (int q = lane; q < 16 * 16; q += 32) T[(q >> 4) * BP + (q & 15)] = (q >> 4) == (q & 15) ? 1.0 : 0.0;
+      __syncwarp();
+      if (ROLL) micro_diag_roll(T, 0, PdB, WmB, psh, dinv, ldg, info, gcol0, lane);
+      else micro_diag_row2(T, 0, PdB, WmB, psh, dinv, ldg, info, gcol0, lane);
+    }
+    __syncthreads();
+    if (tid < 64) psh[tid] = 0.0;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // lower part of the tile -> shared memory, zeros above the diagonal (the inverse region starts from zero); 16-byte pieces
 #pragma unroll 8
   for (int idx = tid; idx < TILE * TILE / 2; idx += 512) {
@@ -846,26 +863,28 @@ base_sweep4_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, 
   GPX_STAMP(1);
   if (warp == 0) {
     // ================= chain warp ======================================================================================
-    micro_diag_roll(T, 0, PdB, WmB, psh, dinv, ldg, info, gcol0, lane);
-    GPX_STAMP(2);
     for (int jp = 0; jp < 8; jp++) {
       const int c0 = jp * 16;
+      if (jp > 0) {
+        micro_update<2>(T, c0 - 16, jp - 1, jp, jp, 0, PdB + ((jp - 1) & 1) * 16 * MP, lane);   // T(jp, jp) -= P(jp, jp-1) P(jp, jp-1)^T
+        __syncwarp();
+        GPX_STAMP(1 + 4 * jp);
+      }
+      if (ROLL) micro_diag_roll(T, c0, PdB + (jp & 1) * 16 * MP, WmB + (jp & 1) * 16 * MP, psh, dinv, ldg, info, gcol0, lane);
+      else micro_diag_row2(T, c0, PdB + (jp & 1) * 16 * MP, WmB + (jp & 1) * 16 * MP, psh, dinv, ldg, info, gcol0, lane);
+      GPX_STAMP(2 + 4 * jp);
       if (jp > 0) named_sync(BAR_D + ((jp - 1) & 1), 512);               // update of step jp-1 done: row block jp+1 is current
       GPX_STAMP(3 + 4 * jp);
       if (jp < 7) micro_panel_rows(T, c0, jp + 1, WmB + (jp & 1) * 16 * MP, lane);
       named_arrive(BAR_A + (jp & 1), 512);
       GPX_STAMP(4 + 4 * jp);
-      if (jp == 7) break;
-      micro_update<2>(T, c0, jp, jp + 1, jp + 1, 0, PdB + (jp & 1) * 16 * MP, lane);   // T(jp+1, jp+1) -= P P^T
-      __syncwarp();
-      GPX_STAMP(5 + 4 * jp);
-      micro_diag_roll(T, c0 + 16, PdB + ((jp + 1) & 1) * 16 * MP, WmB + ((jp + 1) & 1) * 16 * MP, psh, dinv, ldg, info, gcol0,
-                      lane);
-      GPX_STAMP(6 + 4 * jp);
     }
   } else {
     // ================= bulk warps 1..15 =================================================================================
-    const int bw = warp - 1;
+    // the three warps that share the chain warp's SM sub-partition (warps 4, 8, 12) take no DMMA work: DMMA and DFMA share one
+    // pipe per sub-partition, and the chain warp's dependent fp64 operations queued behind the bulk DMMAs (its micro-blocks
+    // took 10 400 cycles beside the 34 update tiles of step 0 and 7 600 beside the 3 of step 6)
+    const int bw = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : -1;     // 0..11, or -1 = idle
     for (int jp = 0; jp < 8; jp++) {
       const int c0 = jp * 16;
       const double* Pd = PdB + (jp & 1) * 16 * MP;
@@ -873,7 +892,7 @@ base_sweep4_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, 
       named_sync(BAR_A + (jp & 1), 512);
       {   // micro-panel: the row blocks other than jp (diagonal) and jp+1 (done by the chain warp)
         const int nrows = jp < 7 ? 6 : 7;
-        if (bw < nrows) {
+        if (bw >= 0 && bw < nrows) {
           int rt = bw;
           if (rt >= jp) rt += (jp < 7 ? 2 : 1);
           micro_panel_rows(T, c0, rt, Wm, lane);
@@ -887,7 +906,7 @@ base_sweep4_kernel(double* __restrict__ S, long ld, double* __restrict__ Ldiag, 
         for (int slot = 0; slot < nslot; slot++) {
           const int rt = slot <= jp ? slot : ct + slot - (jp + 1);
           if (rt == jp + 1 && ct == jp + 1) continue;      // the next diagonal micro-block belongs to the chain warp
-          if (lin++ % 15 != bw) continue;
+          if (lin++ % 12 != bw) continue;
           micro_update<2>(T, c0, jp, rt, ct, 0, Pd, lane);
         }
       }
@@ -912,6 +931,8 @@ static int g_base_version = 0;   // option "base" (process-wide): 0 = default / 
 void set_base_version(int v) { g_base_version = v; }
 // option "base_prof": 1 = the fourth-generation base kernel stamps clock64() at its phase boundaries into a device buffer (the
 // last launch wins); 2 = print them (cycles since the kernel's start) to stderr. Measurement only.
+static int g_base_pdl = 1;        // option "base_pdl"
+void set_base_pdl(int v) { g_base_pdl = v ? 1 : 0; }
 static long long* g_base_prof = nullptr;
 static bool g_base_prof_on = false;
 int set_base_prof(int v) {
@@ -922,11 +943,12 @@ int set_base_prof(int v) {
     long long h[64];
     GPX_CUDA(cudaDeviceSynchronize());
     GPX_CUDA(cudaMemcpy(h, g_base_prof, sizeof(h), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "base_sweep4 phases (SM cycles since kernel start): load %lld | first micro-block %lld |", h[1] - h[0], h[2] - h[1]);
+    fprintf(stderr, "base_sweep4 phases (SM cycles since kernel start): prologue + load %lld |", h[1] - h[0]);
     for (int jp = 0; jp < 8; jp++) {
-      fprintf(stderr, " [jp %d: wait %lld panel-piece %lld", jp, h[3 + 4 * jp] - (jp ? h[2 + 4 * jp] : h[2]), h[4 + 4 * jp] - h[3 + 4 * jp]);
-      if (jp < 7) fprintf(stderr, " update-piece %lld micro-block %lld]", h[5 + 4 * jp] - h[4 + 4 * jp], h[6 + 4 * jp] - h[5 + 4 * jp]);
-      else fprintf(stderr, "]");
+      const long long t0 = jp ? h[4 * jp] : h[1];
+      if (jp) fprintf(stderr, " [jp %d: update-piece %lld micro-block %lld", jp, h[1 + 4 * jp] - t0, h[2 + 4 * jp] - h[1 + 4 * jp]);
+      else fprintf(stderr, " [jp 0: micro-block %lld", h[2] - t0);
+      fprintf(stderr, " wait %lld panel-piece %lld]", h[3 + 4 * jp] - h[2 + 4 * jp], h[4 + 4 * jp] - h[3 + 4 * jp]);
     }
     fprintf(stderr, " | join %lld | last column block + logdet %lld | total %lld\n", h[40] - h[32], h[41] - h[40], h[41] - h[0]);
   } else {
@@ -941,20 +963,36 @@ int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_
   constexpr int smem16 = (TILE * BP + 4 * 16 * MP + 64 + 2 * TILE) * 8 + 16;
   int which = g_base_version;
   if (which <= 0) {
-    const char* e = getenv("GPX_BASE");          // 4 (default) = chain warp runs ahead, 3 = row-per-lane chain warp with block
-    which = e ? atoi(e) : (getenv("GPX_BASE_V1") ? 1 : 4);   // barriers, 2 = round-2 kernel, 1 = round-1 kernel
-    if (which < 1 || which > 4) which = 4;
+    const char* e = getenv("GPX_BASE");          // 4 (default) = chain warp runs ahead, 5 = that with the rolled column loop (slower:
+    which = e ? atoi(e) : (getenv("GPX_BASE_V1") ? 1 : 4);   // ~600 instead of ~400 cycles per column), 3 = row-per-lane chain warp with
+    if (which < 1 || which > 5) which = 4;                   // block barriers, 2 = round-2 kernel, 1 = round-1 kernel
   }
   if (!ready) {
     ready = true;
     GPX_CUDA(cudaFuncSetAttribute(base_sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     GPX_CUDA(cudaFuncSetAttribute(base_sweep3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
-    GPX_CUDA(cudaFuncSetAttribute(base_sweep4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    GPX_CUDA(cudaFuncSetAttribute(base_sweep4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    GPX_CUDA(cudaFuncSetAttribute(base_sweep4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
   }
   if (which == 1) base_sweep_kernel<<<1, 512, 0, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
   else if (which == 2) base_sweep16_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
   else if (which == 3) base_sweep3_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0);
-  else base_sweep4_kernel<<<1, 512, smem16, st>>>(S, ld, Ldiag, Dinv, logdet_part, info, gcol0, g_base_prof_on ? g_base_prof : nullptr);
+  else {
+    // programmatic dependent launch (option "base_pdl", default on): the CTA becomes resident as soon as every CTA of the kernel
+    // before it in the stream has started (the fine GEMM issues griddepcontrol.launch_dependents first thing) and warms its
+    // instruction cache until that kernel is done; after any other kernel the launch behaves like a plain one
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem16; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_base_pdl ? 1 : 0;
+    long long* pr = g_base_prof_on ? g_base_prof : nullptr;
+    const int warm = g_base_pdl ? 1 : 0;
+    if (which == 5) GPX_CUDA(cudaLaunchKernelEx(&cfg, base_sweep4_kernel<true>, S, ld, Ldiag, Dinv, logdet_part, info, gcol0, pr, warm));
+    else GPX_CUDA(cudaLaunchKernelEx(&cfg, base_sweep4_kernel<false>, S, ld, Ldiag, Dinv, logdet_part, info, gcol0, pr, warm));
+  }
   GPX_CUDA(cudaGetLastError());
   return 0;
 }

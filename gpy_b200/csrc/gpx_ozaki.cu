@@ -102,46 +102,75 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
 // 1. digit split: row exponents + 8 signed 7-bit digit planes of a panel, written in the tiled image of gpx_ozaki.cuh
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SPLIT_ROWS = 64;
+constexpr int SPLIT_KS = 8;      // row maxima: k-slices per row (partial maxima, reduced by the digit kernel)
+constexpr int SPLIT_KCB = 4;     // digit kernel: k-chunks (of 32) per CTA
+// The split is two kernels so that both have thousands of CTAs: (1) partial row maxima over k-slices, (2) digits of a
+// 64-row x 128-column piece per CTA. As ONE kernel (a CTA walked the whole K range of its 64 rows: 256 CTAs at N = 16384, each
+// thread 2 x 256 dependent strided loads) it ran at 1.3 TB/s of HBM traffic, 211 us per 16384 x 1024 panel.
+__global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict__ P, long ld, long rows, int nkc_used,
+                                                       double* __restrict__ amax_part) {
+  __shared__ double smax[2][128];
+  const int tid = threadIdx.x, rl = tid & 127, half = tid >> 7;
+  const long row = (long)blockIdx.x * 128 + rl;
+  const long K = (long)nkc_used * OZ_KC;
+  const long kper = (K + SPLIT_KS - 1) / SPLIT_KS;
+  const long k0 = (long)blockIdx.y * kper, k1 = min(K, k0 + kper);
+  const double* prow = P + row;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  long k = k0 + half;
+  for (; k + 6 < k1; k += 8) {
+    a0 = fmax(a0, fabs(prow[k * ld]));
+    a1 = fmax(a1, fabs(prow[(k + 2) * ld]));
+    a2 = fmax(a2, fabs(prow[(k + 4) * ld]));
+    a3 = fmax(a3, fabs(prow[(k + 6) * ld]));
+  }
+  for (; k < k1; k += 2) a0 = fmax(a0, fabs(prow[k * ld]));
+  smax[half][rl] = fmax(fmax(a0, a1), fmax(a2, a3));
+  __syncthreads();
+  if (half == 0) amax_part[(long)blockIdx.y * rows + row] = fmax(smax[0][rl], smax[1][rl]);
+}
+
 // nkc = k-chunks of the plane LAYOUT (strides), nkc_used <= nkc = k-chunks actually present in this panel (a short last block)
 __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict__ P, long ld, long rows, int nkc, int nkc_used,
-                                                      int8_t* __restrict__ planes, double* __restrict__ scale) {
-  __shared__ double smax[4][SPLIT_ROWS];
+                                                      const double* __restrict__ amax_part, int8_t* __restrict__ planes,
+                                                      double* __restrict__ scale) {
   __shared__ double sinv[SPLIT_ROWS];
   const int tid = threadIdx.x, rl = tid & (SPLIT_ROWS - 1), part = tid >> 6;
   const long row = (long)blockIdx.x * SPLIT_ROWS + rl;
-  const long K = (long)nkc_used * OZ_KC;
   const double* prow = P + row;
-  double amax = 0.0;
-  for (long k = part; k < K; k += 4) amax = fmax(amax, fabs(prow[k * ld]));
-  smax[part][rl] = amax;
-  __syncthreads();
   if (part == 0) {
-    amax = fmax(fmax(smax[0][rl], smax[1][rl]), fmax(smax[2][rl], smax[3][rl]));
+    double amax = 0.0;
+#pragma unroll
+    for (int q = 0; q < SPLIT_KS; q++) amax = fmax(amax, amax_part[(long)q * rows + row]);
     double inv = 0.0, sc = 0.0;
-    if (amax >= 1e-290 && amax <= 1e290) {   // rows of zeros (padding) and non-finite rows get all-zero digits
+    if (amax >= 1e-290 && amax <= 1e290) {   // rows of zeros (padding) and rows with infinities get all-zero digits
       int e = 0;
       frexp(amax, &e);                        // amax = m 2^e, m in [0.5, 1): |x| 2^-(e+1) < 1/2 for the whole row
       inv = ldexp(1.0, -(e + 1));
       sc = ldexp(1.0, e + 1 - 7);             // value = 2^(e+1) sum_s d_s 2^(-7 (s+1)); the 2^-7 of both operands folded in here
     }
     sinv[rl] = inv;
-    scale[row] = sc;
+    if (blockIdx.y == 0) scale[row] = sc;
   }
   __syncthreads();
   const double inv = sinv[rl];
   const long ngrp = rows / 8;
-  for (int u = part; u < nkc_used * 2; u += 4) {   // unit = 16 consecutive k of one row = one 16-byte line of a core matrix
+  const int u_beg = blockIdx.y * SPLIT_KCB * 2, u_end = min(nkc_used * 2, u_beg + SPLIT_KCB * 2);
+  for (int u = u_beg + part; u < u_end; u += 4) {   // unit = 16 consecutive k of one row = one 16-byte line of a core matrix
     const int kc = u >> 1, half = u & 1;
+    double xs[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) xs[kk] = prow[((long)kc * OZ_KC + half * 16 + kk) * ld];   // 16 loads in flight
     uint32_t w[OZ_S][4];
 #pragma unroll
     for (int s = 0; s < OZ_S; s++) { w[s][0] = 0; w[s][1] = 0; w[s][2] = 0; w[s][3] = 0; }
 #pragma unroll
     for (int kk = 0; kk < 16; kk++) {
-      double x = prow[((long)kc * OZ_KC + half * 16 + kk) * ld] * inv;   // exact (power of two), |x| < 1/2
+      double x = xs[kk] * inv;                                 // exact (power of two), |x| < 1/2
 #pragma unroll
       for (int s = 0; s < OZ_S; s++) {
-        // round-to-nearest digits WITHOUT the conversion unit (F2I / I2F on fp64 run at a few lanes per SM and made this kernel
-        // 6x slower than its memory traffic): x + 1.5 * 2^52 rounds x to an integer whose two's complement sits in the low word
+        // round-to-nearest digits WITHOUT the conversion unit (F2I / I2F on fp64 run at a few lanes per SM):
+        // x + 1.5 * 2^52 rounds x to an integer whose two's complement sits in the low word
         x *= 128.0;                                            // exact; |x| < 64 (first digit), <= 64 afterwards
         const double t = x + 6755399441055744.0;               // 1.5 * 2^52
         const int d = __double2loint(t);                       // rint(x), |d| <= 64
@@ -158,7 +187,10 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
 
 int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t st) {
   if (K % OZ_KC || K / OZ_KC > pl.nkc) { set_error("launch_oz_split: bad panel width"); return -2; }
-  oz_split_kernel<<<(unsigned)(pl.rows / SPLIT_ROWS), 256, 0, st>>>(P, ld, pl.rows, pl.nkc, (int)(K / OZ_KC), pl.planes, pl.scale);
+  const int nkc_used = (int)(K / OZ_KC);
+  oz_rowmax_kernel<<<dim3((unsigned)(pl.rows / 128), SPLIT_KS), 256, 0, st>>>(P, ld, pl.rows, nkc_used, pl.amax_part);
+  oz_split_kernel<<<dim3((unsigned)(pl.rows / SPLIT_ROWS), (unsigned)((nkc_used + SPLIT_KCB - 1) / SPLIT_KCB)), 256, 0, st>>>(
+      P, ld, pl.rows, pl.nkc, nkc_used, pl.amax_part, pl.planes, pl.scale);
   GPX_CUDA(cudaGetLastError());
   return 0;
 }
@@ -663,6 +695,7 @@ int oz_planes_alloc(OzPlanes& pl, long rows, long K) {
   pl.nkc = (int)(K / OZ_KC);
   GPX_CUDA(cudaMalloc(&pl.planes, (size_t)OZ_S * rows * K));
   GPX_CUDA(cudaMalloc(&pl.scale, (size_t)rows * 8));
+  GPX_CUDA(cudaMalloc(&pl.amax_part, (size_t)rows * 8 * 8));   // SPLIT_KS partial row maxima
   if (oz_make_map(&pl.mapA, pl, OZ_TM) || oz_make_map(&pl.mapB, pl, OZ_TN)) return -1;
   return 0;
 }
@@ -670,7 +703,8 @@ int oz_planes_alloc(OzPlanes& pl, long rows, long K) {
 void oz_planes_free(OzPlanes& pl) {
   if (pl.planes) cudaFree(pl.planes);
   if (pl.scale) cudaFree(pl.scale);
-  pl.planes = nullptr; pl.scale = nullptr; pl.rows = 0; pl.nkc = 0;
+  if (pl.amax_part) cudaFree(pl.amax_part);
+  pl.planes = nullptr; pl.scale = nullptr; pl.amax_part = nullptr; pl.rows = 0; pl.nkc = 0;
 }
 
 int launch_oz_gemm(const OzPlanes& pl, const OzParams& p_in, int num_sms, cudaStream_t st) {
@@ -701,10 +735,11 @@ __global__ void __launch_bounds__(256) grad_kinv_kernel(GradKinvParams p) {
   double* sAc = sSc + TILE;                           // [P][128]
   double* sRed = sAc + (size_t)P * TILE;              // [8 warps][nred]
   // lower tiles only: blockIdx.x enumerates (r, c), c <= r
-  int r = (int)((sqrtf(8.f * (float)blockIdx.x + 1.f) - 1.f) * 0.5f);
-  while (r * (r + 1) / 2 > (int)blockIdx.x) --r;
-  while ((r + 1) * (r + 2) / 2 <= (int)blockIdx.x) ++r;
-  const int c = blockIdx.x - r * (r + 1) / 2;
+  const int csplit = p.csplit, tileidx = (int)blockIdx.x / csplit, sidx = (int)blockIdx.x % csplit;
+  int r = (int)((sqrtf(8.f * (float)tileidx + 1.f) - 1.f) * 0.5f);
+  while (r * (r + 1) / 2 > tileidx) --r;
+  while ((r + 1) * (r + 2) / 2 <= tileidx) ++r;
+  const int c = tileidx - r * (r + 1) / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int idx = tid; idx < D * TILE; idx += 256) sXc[idx] = p.XsT[(long)(idx / TILE) * p.ldx + (long)c * TILE + idx % TILE];
   for (int idx = tid; idx < P * TILE; idx += 256) sAc[idx] = p.alpha[(long)(idx / TILE) * p.ldx + (long)c * TILE + idx % TILE];
@@ -726,7 +761,8 @@ __global__ void __launch_bounds__(256) grad_kinv_kernel(GradKinvParams p) {
   double gvar = 0.0, giso = 0.0, gnoise = 0.0;
   const double* kcol = p.Kinv + gi + ((long)c * TILE + half * 64) * p.ld;
   if (gi < p.N) {
-    for (int jj = 0; jj < 64; jj++) {
+    const int jj_beg = sidx * (64 / csplit), jj_end = jj_beg + 64 / csplit;
+    for (int jj = jj_beg; jj < jj_end; jj++) {
       const int jl = half * 64 + jj;
       const long gj = (long)c * TILE + jl;
       if (gj >= p.N) break;
@@ -804,8 +840,15 @@ __global__ void __launch_bounds__(256) grad_kinv_kernel(GradKinvParams p) {
     double s = 0.0;
 #pragma unroll
     for (int wdx = 0; wdx < 8; wdx++) s += sRed[wdx * nred + tid];
-    p.partials[((long)r * p.nt + c) * nred + tid] = s;
+    p.partials[(((long)r * p.nt + c) * csplit + sidx) * nred + tid] = s;
   }
+}
+
+int grad_kinv_csplit(int nt, int nred) {
+  const int tiles = nt * (nt + 1) / 2;
+  int cs = 1;
+  while (cs < 8 && tiles * cs < 592 && (cs * 2) * nred <= MAX_D + 2) cs *= 2;   // ~4 waves of CTAs; partials sized for MAX_D + 2 per tile
+  return cs;
 }
 
 template <int DREG>
@@ -824,7 +867,8 @@ static int launch_grad_kinv_t(const GradKinvParams& p, unsigned grid, size_t sme
 int launch_grad_kinv(const GradKinvParams& p, cudaStream_t st) {
   const int D = p.kp.D;
   const size_t smem = (size_t)(D + 1 + p.P) * TILE * 8 + 8 * (MAX_D + 2) * 8;
-  const unsigned grid = (unsigned)(p.nt * (p.nt + 1) / 2);
+  if (p.csplit != 1 && p.csplit != 2 && p.csplit != 4 && p.csplit != 8) { set_error("grad_kinv: csplit must be 1, 2, 4 or 8"); return -2; }
+  const unsigned grid = (unsigned)(p.nt * (p.nt + 1) / 2 * p.csplit);
   if (D <= 8) return launch_grad_kinv_t<8>(p, grid, smem, st);
   if (D <= 16) return launch_grad_kinv_t<16>(p, grid, smem, st);
   if (D <= 32) return launch_grad_kinv_t<32>(p, grid, smem, st);

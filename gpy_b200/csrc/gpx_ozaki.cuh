@@ -23,7 +23,8 @@ constexpr int OZ_KC = 32;       // k-depth of one tcgen05.mma kind::i8 (32 bytes
 //     (((s * nkc + k/32) * (rows/8) + i/8) * 256) + ((k%32)/16)*128 + (i%8)*16 + k%16
 struct OzPlanes {
   int8_t* planes = nullptr;     // [S][nkc][rows/8][256]
-  double* scale = nullptr;      // [rows]: 2^(e_i - 7), e_i = exponent of the row maximum over the K columns of the panel
+  double* scale = nullptr;      // [rows]: 2^(e_i + 1 - 7), e_i = exponent of the row maximum over the K columns of the panel
+  double* amax_part = nullptr;  // [8][rows]: partial row maxima (scratch of the split)
   long rows = 0;
   int nkc = 0;
   CUtensorMap mapA, mapB;       // the same tensor with a 128-row and a 64-row box
@@ -66,10 +67,13 @@ struct GradKinvParams {
   const double* Kinv; long ld;
   const double* XsT; const double* sq; const double* alpha; long ldx;
   long N; int P; int nt;
-  double* partials;        // [nt*nt][nl+2], zeroed by the caller
+  double* partials;        // [nt*nt*csplit][nl+2], zeroed by the caller
+  int csplit;              // CTAs per tile (each takes 64/csplit columns of both column halves): 1, 2, 4 or 8 -- small matrices
+                           // have too few tiles to fill the machine, and a thread's 64 columns are a serial chain
   double* dnoise_out;      // optional diag(dL_dK)
   KernParams kp;
 };
 int launch_grad_kinv(const GradKinvParams& p, cudaStream_t st);
+int grad_kinv_csplit(int nt, int nred);   // the split launch_grad_kinv expects for this matrix (partials: nt*nt*(MAX_D+2) doubles)
 
 }  // namespace gpx

@@ -23,7 +23,9 @@ VARIANTS = [
     ("fine1 chain1 base4 (default)", dict(fine=1, chain=1, base=4)),
 ]
 if os.environ.get("CHAIN_AB_SHORT"):
-    VARIANTS = [VARIANTS[0], VARIANTS[-1]]
+    VARIANTS = [("round-2 (fine0 chain0 base2)", dict(fine=0, chain=0, base=2, base_pdl=0)),
+                ("default without base_pdl", dict(fine=1, chain=1, base=4, base_pdl=0)),
+                ("default (fine1 chain1 base4 pdl)", dict(fine=1, chain=1, base=4, base_pdl=1))]
 NB_SWEEP = {512: (128, 256, 512), 4096: (256, 512, 1024), 8192: (512, 1024), 16384: (512, 1024, 2048)}
 
 
@@ -100,6 +102,7 @@ def main():
         e = _ffi.Engine(0)
         e.set_data(X, Y)
         e.exact_eval("rbf", True, var, ls, noise)
+        e.set_option("base_pdl", 1)
         e.set_option("base_prof", 1)
         e.exact_eval("rbf", True, var, ls, noise)
         e.set_option("base_prof", 2)
