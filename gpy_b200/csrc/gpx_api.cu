@@ -51,6 +51,8 @@ static void free_data(gpx_ctx* c) {
   c->m_cap = 0;
   oz_planes_free(c->ozp[0]);
   oz_planes_free(c->ozp[1]);
+  oz_planes_free(c->ozpA);
+  oz_planes_free(c->ozpB);
   if (c->oz_tiles) cudaFree(c->oz_tiles);
   c->oz_tiles = nullptr;
   for (double** mp : {&c->dYres, &c->dTfw}) { if (*mp) cudaFree(*mp); *mp = nullptr; }
@@ -177,6 +179,7 @@ int gpx_set_option(gpx_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "oz_ctas")) { c->oz_ctas = (int)std::max<int64_t>(0, value); return 0; }
   if (!strcmp(name, "oz_dbg")) { c->oz_dbg = (int)value; return 0; }
   if (!strcmp(name, "oz_tpc")) { c->oz_tpc = (int)std::max<int64_t>(0, value); return 0; }
+  if (!strcmp(name, "oz_panel")) { c->oz_panel = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2)); return 0; }   // 2 = at every size
   if (!strcmp(name, "oz_sched")) { c->oz_sched = value ? 1 : 0; return 0; }
   if (!strcmp(name, "oz_u0")) { c->oz_u0 = value ? 1 : 0; return 0; }
   if (!strcmp(name, "oz_reserve")) { c->oz_reserve = (int)std::max<int64_t>(0, std::min<int64_t>(value, 64)); return 0; }
@@ -323,6 +326,8 @@ static int oz_prepare(gpx_ctx* c) {
   if (!c->oz_ready) {
     GPX_CHECK(oz_planes_alloc(c->ozp[0], Npad, NB));
     GPX_CHECK(oz_planes_alloc(c->ozp[1], Npad, NB));
+    GPX_CHECK(oz_planes_alloc(c->ozpA, Npad, NB));
+    GPX_CHECK(oz_planes_alloc(c->ozpB, NB, NB));
     if (!c->Kinv) GPX_CUDA(cudaMalloc(&c->Kinv, (size_t)Npad * Npad * 8));
     GPX_CUDA(cudaMalloc(&c->dYres, (size_t)MAX_P * Npad * 8));
     GPX_CUDA(cudaMalloc(&c->dTfw, (size_t)MAX_P * Npad * 8));
@@ -586,7 +591,24 @@ static int run_sweep_chain(gpx_ctx* c, Recorder& rec) {
       c->eval_launches++;
     }
     // ---- s3: Pr(k), split, copy-back, forward substitution --------------------------------------------------------------
-    if (nt - nbt - next_nbt > 0) {
+    // (measured, profiles/r02s2_panel_ab.txt: +3.8 % at N = 16384, +3.1 % at 8192, even at 4096, -7 % at 1300: five launches
+    // instead of one only pay once the panel GEMM is a visible share of the step)
+    if (c->oz_panel && c->oz_wide && os.pan_n > 0 && (c->oz_panel > 1 || Npad >= 4096)) {
+      // the panel GEMM itself on the tensor cores: digit planes of block column k of the workspace (A) and of L_kk^-1 (B,
+      // lower triangular: per-tile k-range), P = A B^T stored into the panel buffer. 8 digits for the Cholesky rows (they feed
+      // the log-determinant), oz_dig_up for the rows above (finished block column of U: gradients only)
+      GPX_CHECK(launch_oz_split(c->S + o * ld, ld, nb, c->ozpA, s3));
+      GPX_CHECK(launch_oz_split(c->Tm, nb, nb, c->ozpB, s3));
+      OzParams op;
+      memset(&op, 0, sizeof(op));
+      op.tiles = c->oz_tiles + os.pan_off; op.ntiles = os.pan_n; op.nkc = (int)(nb / OZ_KC);
+      op.scale = c->ozpA.scale; op.scaleB = c->ozpB.scale; op.P = Pb; op.ldp = Npad;
+      op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
+      op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg; op.wide = 1;
+      op.tpc = c->oz_ctas > 0 ? (os.pan_n + c->oz_ctas - 1) / c->oz_ctas : c->oz_tpc;
+      GPX_CHECK(launch_oz_gemm(c->ozpA, op, c->num_sms, s3, &c->ozpB));
+      c->eval_launches += 5;
+    } else if (nt - nbt - next_nbt > 0) {
       GemmParams pp = gemm_defaults();
       pp.mode = GEMM_PANEL;
       pp.A = c->S + o * ld; pp.lda = ld;

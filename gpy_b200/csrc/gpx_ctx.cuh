@@ -79,6 +79,9 @@ struct gpx_ctx {
   bool oz_ready = false;       // planes and K^-1 buffer allocated for (Npad, NB)
   bool oz_lists_ready = false; // tile lists built for (Npad, NB, oz_wide)
   gpx::OzPlanes ozp[2];        // digit planes of the current / next panel (look-ahead double buffer)
+  int oz_panel = 1;            // option "oz_panel": the panel GEMM P = S(:, block) L_kk^-T outside the chain rows on the tensor cores too
+                               // (digit planes of the block column and of L_kk^-1); 0 = fp64 DMMA panel GEMM
+  gpx::OzPlanes ozpA, ozpB;    // its operands: block column of the workspace (Npad x NB), L_kk^-1 (NB x NB)
   uint32_t* oz_tiles = nullptr;
   double* dYres = nullptr;     // [P][Npad] running right-hand side of the forward substitution carried along the sweep
   double* dTfw = nullptr;      // [P][Npad] t = L^-1 y from that substitution (quadratic form of the LML)

@@ -10,6 +10,7 @@
 // same share of lapack.dpotrf / dtrtri (GPy/util/linalg.py:58,227) as before.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "gpx_ctx.cuh"
 #include "gpx_fine.cuh"
@@ -84,6 +85,9 @@ __global__ void __launch_bounds__(F_THREADS, 2) gemm_fine_kernel(const FineParam
   const double* Bptr = p.B + (long)c * TILE + sn * FTN;
   const long lda = p.lda, ldb = p.ldb;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // this grid may itself have been launched as a programmatic dependent (of the in-place inner panel): everything above ran
+  // beside that kernel, the operands are read only after it has completed and flushed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   auto load_stage = [&](int it) {
     if (it < nchunk) {
@@ -173,6 +177,7 @@ fine_panel_inplace_kernel(double* __restrict__ Sblk, long ld, const double* __re
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sA = reinterpret_cast<double*>(smem_raw + 128);   // strip: (m, k) at k*IP_PA + m
   double* sB = sA + TILE * IP_PA;                            // Dinv:  (n, k) at k*PITCH + n   (only n >= 16*(k/16) is loaded)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the inner update behind it may become resident (it waits)
   const int slot = blockIdx.x / (TILE / IP_ROWS), part = blockIdx.x % (TILE / IP_ROWS);
   const int r = slot < d ? slot : slot + 1;
   double* strip = Sblk + (long)r * TILE + part * IP_ROWS + (long)d * TILE * ld;
@@ -230,6 +235,22 @@ int fine_init() {
   return 0;
 }
 
+// launched with the programmatic-stream-serialization attribute (option "base_pdl"): behind a kernel that issues
+// griddepcontrol.launch_dependents (the in-place inner panel, another fine GEMM) the CTAs become resident early and block in
+// griddepcontrol.wait; behind any other kernel or an event wait this is an ordinary launch
+template <int MODE>
+static int launch_fine_pdl(const FineParams& p, unsigned grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (p.pdl && get_base_pdl()) ? 1 : 0;
+  GPX_CUDA(cudaLaunchKernelEx(&cfg, gemm_fine_kernel<MODE>, p));
+  return 0;
+}
+
 int launch_fine(const FineParams& p0, cudaStream_t st) {
   FineParams p = p0;
   if (p.K <= 0 || p.K % TILE != 0) { set_error("fine GEMM: k-depth must be a positive multiple of 128"); return -2; }
@@ -239,15 +260,15 @@ int launch_fine(const FineParams& p0, cudaStream_t st) {
     if (p.ncols <= 0) return 0;
     const int nslots = p.rlow + (p.nt - p.c0);
     grid = (unsigned)(nslots * p.ncols * F_SUB);
-    gemm_fine_kernel<FINE_UPDATE><<<grid, F_THREADS, F_SMEM, st>>>(p);
+    if (launch_fine_pdl<FINE_UPDATE>(p, grid, st)) return -1;
   } else if (p.mode == FINE_LAUUM) {
     if (p.nt <= 0) return 0;
     grid = (unsigned)(p.nt * (p.nt + 1) / 2 * F_SUB);
-    gemm_fine_kernel<FINE_LAUUM><<<grid, F_THREADS, F_SMEM, st>>>(p);
+    if (launch_fine_pdl<FINE_LAUUM>(p, grid, st)) return -1;
   } else {
     if (p.nr <= 0 || p.nc <= 0) return 0;
     grid = (unsigned)(p.nr * p.nc * F_SUB);
-    gemm_fine_kernel<FINE_PANEL><<<grid, F_THREADS, F_SMEM, st>>>(p);
+    if (launch_fine_pdl<FINE_PANEL>(p, grid, st)) return -1;
   }
   GPX_CUDA(cudaGetLastError());
   return 0;
@@ -280,6 +301,7 @@ int diag_block_sweep(gpx_ctx* c, double* Sblk, long ld, int nbt, int g0, cudaStr
         pu.B = pu.A; pu.ldb = ld;
         pu.C = Sblk; pu.ldc = ld;
         pu.K = TILE; pu.nt = nbt; pu.c0 = d + 1; pu.ncols = nbt - d - 1; pu.rlow = d + 1;
+        pu.pdl = 1;
         GPX_CHECK_F(launch_fine(pu, st));
         c->eval_launches++;
       }

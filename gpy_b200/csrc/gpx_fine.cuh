@@ -26,6 +26,8 @@ struct FineParams {
   // FINE_PANEL: C(r,c) = A_r B_c^T for row tiles r in [r0, r0+nr), column tiles c in [0, nc); tri: B is lower triangular
   // (k range of output columns [32h, 32h+32) of tile c ends at c*TILE + 32(h+1))
   int r0, nr, nc, tri;
+  int pdl;                     // 1: launch as a programmatic dependent of the kernel before it in the stream (inner update of a
+                               // diagonal block behind the in-place inner panel); 0: ordinary launch
   // FINE_LAUUM: C(r,c) = sum_{k >= r*TILE} A_r(:,k) B_c(:,k)^T for the lower tiles c <= r < nt (K^-1 = U U^T of a small matrix:
   // U is upper triangular, row tile r starts at column r*TILE); K = padded order
 };

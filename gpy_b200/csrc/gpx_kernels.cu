@@ -933,6 +933,7 @@ void set_base_version(int v) { g_base_version = v; }
 // last launch wins); 2 = print them (cycles since the kernel's start) to stderr. Measurement only.
 static int g_base_pdl = 1;        // option "base_pdl"
 void set_base_pdl(int v) { g_base_pdl = v ? 1 : 0; }
+int get_base_pdl() { return g_base_pdl; }
 static long long* g_base_prof = nullptr;
 static bool g_base_prof_on = false;
 int set_base_prof(int v) {

@@ -46,6 +46,7 @@ int launch_kbuild(const KBuildParams& p, int row_tiles, int col_tiles, cudaStrea
 int launch_base(double* S, long ld, double* Ldiag, double* Dinv, double* logdet_part, int* info, int gcol0,
                 cudaStream_t st);
 void set_base_version(int v);   // 0 = default (3), 1..3 = generation of the base-block kernel (measurement / regression)
+int get_base_pdl();
 void set_base_pdl(int v);      // 1 (default) = base kernel launched as a programmatic dependent with an instruction-cache warm-up
 int set_base_prof(int v);       // measurement: phase clocks of the base-block kernel (option "base_prof")
 int launch_assemble(const double* Sblk, long ld, int nb, double* Prows, long ldp, double* Tm, cudaStream_t st);

@@ -423,11 +423,15 @@ __device__ __forceinline__ void oz2_first_chunk(uint32_t taddr, uint32_t a_lo, u
     oz2_first_chunk<G_BEG, G_END - 1, G_BASE>(taddr, a_lo, tmem_empty, usebits, issue);
   }
 }
+// k-chunks of a tile: the whole panel width, except OZ_PANEL tiles (triangular B: columns of tile c' see k < (c' + 1) * 128)
+__device__ __forceinline__ int oz2_tile_nkc(uint32_t t, int nkc) {
+  return ((t >> 25) & 3) == OZ_PANEL ? min(nkc, (int)(((t >> 12) & 0x1fff) + 1) * (OZ2_TN / OZ_KC)) : nkc;
+}
 // Warp roles: warps 0..7 = epilogue (TMEM lane quarter = warp % 4, column half = warp / 4; two warpgroups that raise their
 // register budget to 224 with setmaxnreg: 64 fp64 accumulators per thread live across the two passes), warp 8 = TMA
 // producer, warp 9 = MMA issuer, warps 10-11 idle (the third warpgroup hands its registers over: 56 each).
 __global__ void __launch_bounds__(OZ2_THREADS, 1)
-oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
+oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzParams p) {
   extern __shared__ unsigned char oz_smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + OZ2_STAGES * OZ2_STAGE_BYTES);
@@ -444,6 +448,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
     for (int s = 0; s < 4; s++) mbar_init(&tmem_empty[s], OZ_EPI_WARPS);
     fence_mbar_init();
     tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
   }
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
@@ -465,9 +470,10 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
       const uint32_t t = p.tiles[ti];
       const int r = t & 0xfff, c = (t >> 12) & 0x1fff;
       const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;   // >= 5 here: both passes always run, so that the stage
+      const int nkc_t = oz2_tile_nkc(t, nkc);
       for (int pass = 0; pass < 2; pass++) {                    // counter stays warp-uniform (descriptors in uniform registers)
         const int npl = pass == 0 ? nd : 4;        // low-order groups need every plane, groups 0..3 only planes 0..3
-        for (int kc = 0; kc < nkc; kc++, it++) {
+        for (int kc = 0; kc < nkc_t; kc++, it++) {
           const int st = it % OZ2_STAGES;
           if (p.dbg & 16) mbar_wait(&empty[st], ((it / OZ2_STAGES) & 1) ^ 1);
           else mbar_wait_backoff(&empty[st], ((it / OZ2_STAGES) & 1) ^ 1, 64);
@@ -475,7 +481,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
           unsigned char* dst = ring + st * OZ2_STAGE_BYTES;
           if (lane < npl) {
             tma_load_4d(dst + lane * OZ2_PLANE, &mapA, 0, r * (OZ_TM / 8), kc, lane, &full[st]);
-            tma_load_4d(dst + (OZ_S + lane) * OZ2_PLANE, &mapA, 0, c * (OZ2_TN / 8), kc, lane, &full[st]);
+            tma_load_4d(dst + (OZ_S + lane) * OZ2_PLANE, &mapB, 0, c * (OZ2_TN / 8), kc, lane, &full[st]);
           }
           if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)npl * 2 * OZ2_PLANE);
         }
@@ -492,11 +498,12 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
       for (int ti = ti_beg; ti < ti_end; ti++) {
         const uint32_t t = p.tiles[ti];
         const int nd = ((t >> 27) & 1) ? p.dig_up : p.dig_lo;
+        const int nkc_t = oz2_tile_nkc(t, nkc);
         // the two passes are two copies of the loop (compile-time pass): with a run-time pass variable selecting the MMA
         // block the compiler keeps the descriptors in vector registers (R2UR per operand, ~1.3x slower issue)
         auto run_pass = [&](auto pass_tag) {
           constexpr int pass = decltype(pass_tag)::value;
-          for (int kc = 0; kc < nkc; kc++) {
+          for (int kc = 0; kc < nkc_t; kc++) {
             mbar_wait(&full[st], ph);
             tc_fence_after();
             const uint32_t a_lo = ring_lo + (uint32_t)st * (OZ2_STAGE_BYTES >> 4);
@@ -576,6 +583,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const OzParams p) {
       const long gj0 = (long)c * OZ2_TN + h * 64;
       const double si = p.scale[gi];
       if (kind == OZ_UPDATE) oz_apply_row<64>(p.S + gi + gj0 * p.lds, p.lds, acc, si, p.scale + gj0, kind);
+      else if (kind == OZ_PANEL) oz_apply_row<64>(p.P + gi + gj0 * p.ldp, p.ldp, acc, si, p.scaleB + gj0, OZ_LAUUM_SET);
       else oz_apply_row<64>(p.Kinv + gi + gj0 * p.ldk, p.ldk, acc, si, p.scale + gj0, kind);
     }
   }
@@ -651,6 +659,18 @@ void oz_build_lists(long Npad, long NB, int cw, int own_G, int own_g, std::vecto
     }
     st.u2_n = (int)tiles.size() - st.u2_off;
     st.u2_up = count_up(st.u2_off, st.u2_n);
+    {   // panel GEMM on the tensor cores: P(r, c') for the rows outside the diagonal block and block k+1, c' < nb / 128
+      st.pan_off = (int)tiles.size();
+      const int nbt = kt1 - kt0;
+      std::vector<int> rows;
+      for (int r = 0; r < kt0; r++) if (mine(r)) rows.push_back(r);
+      for (int r = kt1 + next_nbt; r < nt; r++) if (mine(r)) rows.push_back(r);
+      for (size_t b = 0; b < rows.size(); b += 8)              // bands of 8 row tiles; longest k-range (last column tile) first
+        for (int cc = nbt - 1; cc >= 0; cc--)
+          for (size_t i = b; i < std::min(rows.size(), b + 8); i++) tiles.push_back(oz_tile(rows[i], cc, OZ_PANEL, rows[i] < kt0 ? 1 : 0));
+      st.pan_n = (int)tiles.size() - st.pan_off;
+      st.pan_up = count_up(st.pan_off, st.pan_n);
+    }
     steps.push_back(st);
   }
 }
@@ -707,14 +727,15 @@ void oz_planes_free(OzPlanes& pl) {
   pl.planes = nullptr; pl.scale = nullptr; pl.amax_part = nullptr; pl.rows = 0; pl.nkc = 0;
 }
 
-int launch_oz_gemm(const OzPlanes& pl, const OzParams& p_in, int num_sms, cudaStream_t st) {
+int launch_oz_gemm(const OzPlanes& pl, const OzParams& p_in, int num_sms, cudaStream_t st, const OzPlanes* plB) {
   if (p_in.ntiles <= 0) return 0;
   OzParams p = p_in;
   // default: 8 narrow / 4 wide tiles per CTA when there is enough work (measured: 1 -> 2 -> 4 -> 8 tiles per CTA = 118 / 104 / 98 / 91 ms)
   if (p.tpc <= 0) p.tpc = std::max(1, std::min(p.wide ? 4 : 8, p.ntiles / std::max(1, num_sms)));
   const int grid = (p.ntiles + p.tpc - 1) / p.tpc;
   if (p.wide && (p.dig_lo < 5 || p.dig_up < 5)) { set_error("the two-pass kernel needs at least 5 digits"); return -2; }
-  if (p.wide) oz_gemm2_kernel<<<grid, OZ2_THREADS, OZ2_SMEM, st>>>(pl.mapA, p);
+  if (plB && !p.wide) { set_error("OZ_PANEL tiles need the two-pass kernel"); return -2; }
+  if (p.wide) oz_gemm2_kernel<<<grid, OZ2_THREADS, OZ2_SMEM, st>>>(pl.mapA, plB ? plB->mapA : pl.mapA, p);
   else oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(pl.mapA, pl.mapB, p);
   GPX_CUDA(cudaGetLastError());
   return 0;

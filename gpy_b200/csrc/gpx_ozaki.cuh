@@ -31,7 +31,7 @@ struct OzPlanes {
 };
 
 // one output tile: bits 0-11 row tile (128 rows), 12-24 column tile (64 columns), 25-26 kind, 27 inverse-part tile
-enum OzKind { OZ_UPDATE = 0, OZ_LAUUM_ACC = 1, OZ_LAUUM_SET = 2 };
+enum OzKind { OZ_UPDATE = 0, OZ_LAUUM_ACC = 1, OZ_LAUUM_SET = 2, OZ_PANEL = 3 };
 inline uint32_t oz_tile(int r, int c64, int kind, int upper) {
   return (uint32_t)r | ((uint32_t)c64 << 12) | ((uint32_t)kind << 25) | ((uint32_t)upper << 27);
 }
@@ -46,20 +46,27 @@ struct OzParams {
   int dig_lo, dig_up;      // digits per operand for Cholesky-part tiles / inverse-part tiles (<= OZ_S)
   int tpc;                 // consecutive tiles per CTA (0 = default)
   int wide;                // 1: 128 x 128 tiles (two-pass kernel, column tile index in 128-column units), 0: 128 x 64 tiles
+  // OZ_PANEL tiles (two-pass kernel only): P(r, c') = A_r B_c'^T with A = digit planes of a block column of the workspace
+  // (the launch's tensor map), B = digit planes of L_kk^-1 (mapB of launch_oz_gemm), lower triangular: the k-range of output
+  // column tile c' ends at (c' + 1) * 128. Result stored (not accumulated) into P.
+  double* P; long ldp;
+  const double* scaleB;    // row scales of the B operand's planes (= column scales of the product)
   int dbg;                 // measurement only: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work (results invalid);
                            // 8 / 16 = epilogue / producer wait WITHOUT back-off, 32 = TMEM released per pass, not per slot (results valid)
 };
 
 // one panel step of the sweep: offsets into the tile list. U0: the next diagonal block only; U1: the rest of block column k+1;
 // U2 list: u2_upd update tiles, then the K^-1 tiles; *_up = inverse-part tiles among them
-struct OzStep { int u0_off, u0_n, u1_off, u1_n, u2_off, u2_n, u2_upd, u0_up, u1_up, u2_up, u2_upd_up; };
+struct OzStep { int u0_off, u0_n, u1_off, u1_n, u2_off, u2_n, u2_upd, u0_up, u1_up, u2_up, u2_upd_up;
+                // panel GEMM of the step on the tensor cores: rows outside the diagonal block and the next block
+                int pan_off, pan_n, pan_up; };
 void oz_build_lists(long Npad, long NB, int cw, int own_G, int own_g, std::vector<uint32_t>& tiles, std::vector<OzStep>& steps);
 
 int oz_init();                                                          // driver entry point + kernel attributes
 int oz_planes_alloc(OzPlanes& pl, long rows, long K);                    // buffers + tensor maps
 void oz_planes_free(OzPlanes& pl);
 int launch_oz_split(const double* P, long ld, long K, OzPlanes& pl, cudaStream_t st);   // P: rows x K column-major, K <= layout
-int launch_oz_gemm(const OzPlanes& pl, const OzParams& p, int num_sms, cudaStream_t st);
+int launch_oz_gemm(const OzPlanes& pl, const OzParams& p, int num_sms, cudaStream_t st, const OzPlanes* plB = nullptr);
 
 // gradient reductions from a stored K^-1 (lower 128 x 128 tiles, column-major, leading dimension ld): same partial sums as
 // the fused epilogue of gemm_lauum_kernel, consumed by finalize_kernel
