@@ -593,7 +593,8 @@ static int run_sweep_chain(gpx_ctx* c, Recorder& rec) {
     // ---- s3: Pr(k), split, copy-back, forward substitution --------------------------------------------------------------
     // (measured, profiles/r02s2_panel_ab.txt: +3.8 % at N = 16384, +3.1 % at 8192, even at 4096, -7 % at 1300: five launches
     // instead of one only pay once the panel GEMM is a visible share of the step)
-    if (c->oz_panel && c->oz_wide && os.pan_n > 0 && (c->oz_panel > 1 || Npad >= 4096)) {
+    const bool oz_pan = c->oz_panel && c->oz_wide && os.pan_n > 0 && (c->oz_panel > 1 || Npad >= 4096);
+    if (oz_pan) {
       // the panel GEMM itself on the tensor cores: digit planes of block column k of the workspace (A) and of L_kk^-1 (B,
       // lower triangular: per-tile k-range), P = A B^T stored into the panel buffer. 8 digits for the Cholesky rows (they feed
       // the log-determinant), oz_dig_up for the rows above (finished block column of U: gradients only)
@@ -602,7 +603,7 @@ static int run_sweep_chain(gpx_ctx* c, Recorder& rec) {
       OzParams op;
       memset(&op, 0, sizeof(op));
       op.tiles = c->oz_tiles + os.pan_off; op.ntiles = os.pan_n; op.nkc = (int)(nb / OZ_KC);
-      op.scale = c->ozpA.scale; op.scaleB = c->ozpB.scale; op.P = Pb; op.ldp = Npad;
+      op.scale = c->ozpA.scale; op.scaleB = c->ozpB.scale; op.P = Pb; op.ldp = Npad; op.Pfinal = c->S + o * ld;
       op.S = c->S; op.lds = ld; op.Kinv = c->Kinv; op.ldk = ld;
       op.dig_lo = OZ_S; op.dig_up = c->oz_dig_up; op.dbg = c->oz_dbg; op.wide = 1;
       op.tpc = c->oz_ctas > 0 ? (os.pan_n + c->oz_ctas - 1) / c->oz_ctas : c->oz_tpc;
@@ -622,11 +623,17 @@ static int run_sweep_chain(gpx_ctx* c, Recorder& rec) {
     GPX_CHECK(launch_oz_split(Pb, Npad, nb, c->ozp[kblk & 1], s3));
     c->eval_launches++;
     GPX_CHECK(link(s3, sm, nullptr));
-    if (o > 0)
-      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, Pb, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, s3));
-    if (kt1 < nt)
-      GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8, (size_t)(Npad - o - nb) * 8, nb,
-                                 cudaMemcpyDeviceToDevice, s3));
+    if (oz_pan) {   // the tensor-core panel GEMM stored its rows into the workspace itself: only the rows of block k+1 (Pc) are left
+      if (next_nbt > 0)
+        GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8, (size_t)next_nbt * TILE * 8, nb,
+                                   cudaMemcpyDeviceToDevice, s3));
+    } else {
+      if (o > 0)
+        GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld, ld * 8, Pb, Npad * 8, (size_t)o * 8, nb, cudaMemcpyDeviceToDevice, s3));
+      if (kt1 < nt)
+        GPX_CUDA(cudaMemcpy2DAsync(c->S + o * ld + (o + nb), ld * 8, Pb + (o + nb), Npad * 8, (size_t)(Npad - o - nb) * 8, nb,
+                                   cudaMemcpyDeviceToDevice, s3));
+    }
     GPX_CHECK(launch_fw_block(c->Tm, (int)nb, c->dYres + o, Npad, c->P, c->dTfw + o, s3));
     c->eval_launches++;
     GPX_CHECK(link(s3, nullptr, &ev_fw));

@@ -583,7 +583,12 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const long gj0 = (long)c * OZ2_TN + h * 64;
       const double si = p.scale[gi];
       if (kind == OZ_UPDATE) oz_apply_row<64>(p.S + gi + gj0 * p.lds, p.lds, acc, si, p.scale + gj0, kind);
-      else if (kind == OZ_PANEL) oz_apply_row<64>(p.P + gi + gj0 * p.ldp, p.ldp, acc, si, p.scaleB + gj0, OZ_LAUUM_SET);
+      else if (kind == OZ_PANEL) {
+        oz_apply_row<64>(p.P + gi + gj0 * p.ldp, p.ldp, acc, si, p.scaleB + gj0, OZ_LAUUM_SET);
+        // the panel rows also take their final place in the workspace (U block column above, L panel below the diagonal
+        // block): its digit planes were taken before this launch, nothing reads the fp64 block column any more
+        if (p.Pfinal) oz_apply_row<64>(p.Pfinal + gi + gj0 * p.lds, p.lds, acc, si, p.scaleB + gj0, OZ_LAUUM_SET);
+      }
       else oz_apply_row<64>(p.Kinv + gi + gj0 * p.ldk, p.ldk, acc, si, p.scale + gj0, kind);
     }
   }
@@ -782,11 +787,14 @@ __global__ void __launch_bounds__(256) grad_kinv_kernel(GradKinvParams p) {
   double gvar = 0.0, giso = 0.0, gnoise = 0.0;
   const double* kcol = p.Kinv + gi + ((long)c * TILE + half * 64) * p.ld;
   if (gi < p.N) {
-    const int jj_beg = sidx * (64 / csplit), jj_end = jj_beg + 64 / csplit;
+    const int jj_beg = sidx * (64 / csplit);
+    const int jj_end = (int)min((long)(jj_beg + 64 / csplit), p.N - (long)c * TILE - half * 64);   // columns beyond N are padding
+    // two columns in flight per thread: one column is a single dependent chain (dot product -> exp -> reductions) and the
+    // 16 warps an SM holds at 92 registers leave the fp64 pipe mostly idle (1.8 ms for the 134 M elements of N = 16384)
+#pragma unroll 2
     for (int jj = jj_beg; jj < jj_end; jj++) {
       const int jl = half * 64 + jj;
       const long gj = (long)c * TILE + jl;
-      if (gj >= p.N) break;
       const double kinv = kcol[(long)jj * p.ld];
       double dot = 0.0;
 #pragma unroll

@@ -50,6 +50,7 @@ struct OzParams {
   // (the launch's tensor map), B = digit planes of L_kk^-1 (mapB of launch_oz_gemm), lower triangular: the k-range of output
   // column tile c' ends at (c' + 1) * 128. Result stored (not accumulated) into P.
   double* P; long ldp;
+  double* Pfinal;          // optional second target of OZ_PANEL tiles: the block column of the workspace itself (ld = lds)
   const double* scaleB;    // row scales of the B operand's planes (= column scales of the product)
   int dbg;                 // measurement only: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work (results invalid);
                            // 8 / 16 = epilogue / producer wait WITHOUT back-off, 32 = TMEM released per pass, not per slot (results valid)
