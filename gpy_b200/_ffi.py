@@ -59,6 +59,8 @@ EXPORTS = {
     "gpx_sparse_eval": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64,
                                        ctypes.c_double, _dp, _dp, _dp]),
     "gpx_sparse_get": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
+    "gpx_sparse_eval_het": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, ctypes.c_int64,
+                                           _dp, _dp, _dp, _dp, _dp]),
     "gpx_pdinv": (ctypes.c_int, [_vp, _dp, ctypes.c_int64, ctypes.c_int, _dp, _dp, _dp, _dp, _dp]),
     "gpx_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(GpxStats)]),
     "gpx_total_launches": (ctypes.c_int64, [_vp]),
@@ -260,6 +262,25 @@ class Engine(object):
         self.sM, self._snl = M, ls.size
         self.sparse_serial = getattr(self, "sparse_serial", 0) + 1
         return lml.value, grad, dZ
+
+    def sparse_eval_het(self, kind, ARD, variance, lengthscale, Z, noise_variances):
+        """VarDTC with one noise variance per data point (var_dtc.py het_noise branches) ->
+        (lml, grad [variance, lengthscale..], dZ (M x D), dL_dR (N x P))"""
+        Z = _f64(Z)
+        M = Z.shape[0]
+        k, a, ls = _theta(kind, ARD, lengthscale, self.sD)
+        nv = _f64(np.asarray(noise_variances, dtype=np.float64).reshape(-1))
+        if nv.size != self.sN:
+            raise ValueError("one noise variance per data point expected (%d given, N = %d)" % (nv.size, self.sN))
+        lml = ctypes.c_double()
+        grad = np.zeros(ls.size + 1)
+        dZ = np.empty((M, self.sD))
+        dR = np.empty((self.sN, self.sP))
+        check(self._L.gpx_sparse_eval_het(self._h, k, a, float(variance), _ptr(ls), _ptr(Z), M, _ptr(nv),
+                                          ctypes.byref(lml), _ptr(grad), _ptr(dZ), _ptr(dR)), "gpx_sparse_eval_het")
+        self.sM, self._snl = M, ls.size
+        self.sparse_serial = getattr(self, "sparse_serial", 0) + 1
+        return lml.value, grad, dZ, dR
 
     SPARSE_GET = {"woodbury_vector": 0, "woodbury_inv": 1, "Kmm": 2, "Lm": 3}
 

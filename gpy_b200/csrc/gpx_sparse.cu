@@ -9,6 +9,9 @@
 //   dL_dKnm^T = W2 psi1^T + C (beta Y)^T (M x N, never materialised on the host) reduced straight to
 //   d/d(variance, lengthscale) and dL/dZ                                                       sparse_gp.py:112,118
 // With a communicator the data rows are sharded: A, t and the Knm gradient pieces are all-reduced (var_dtc_parallel.py).
+// Heteroscedastic noise (one variance per data point, the `het_noise` branches var_dtc.py:127-128,221-227,241-257,267-269):
+// the same evaluation with the columns of tmp scaled by sqrt(beta_n), dL_dKnm^T's columns by beta_n, and the N per-point
+// noise gradients dL_dR from three column reductions over M x N matrices (gpx_sparse_eval_het).
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -19,7 +22,8 @@
 
 using namespace gpx;
 
-static int knm_grads_device(gpx_ctx* c, double beta, double* dvariance, double* dlengthscale, double* dZ);
+static int knm_grads_device(gpx_ctx* c, double beta, const double* bvec, double* dvariance, double* dlengthscale,
+                            double* dZ);
 
 #define GPX_CHECK(x)            \
   do {                          \
@@ -51,6 +55,8 @@ struct SparseState {
   double *vec = nullptr;                             // [8][P][Mpad] small vectors
   double *red = nullptr; double *h_red = nullptr;    // scalar reductions
   double *gsum = nullptr;                            // [1 + nl + M*D] gradient pieces summed over ranks
+  double *hb = nullptr;                              // het noise: [2][Npad] sqrt(beta_n), beta_n
+  double *hs = nullptr;                              // het noise: [2 + P][Npad] column reductions s1, s2, r (see eval)
   double trYYT = 0.0;
   bool have_eval = false;
   double noise = 0.0;
@@ -67,7 +73,7 @@ void free_m(SparseState* s) {
 }
 void free_all(SparseState* s) {
   free_m(s);
-  double** ptrs[] = {&s->X, &s->XsT, &s->sqX, &s->Y, &s->Yb, &s->part, &s->red};
+  double** ptrs[] = {&s->X, &s->XsT, &s->sqX, &s->Y, &s->Yb, &s->part, &s->red, &s->hb, &s->hs};
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   if (s->h_red) { cudaFreeHost(s->h_red); s->h_red = nullptr; }
   if (s->cK) { gpx_destroy(s->cK); s->cK = nullptr; }
@@ -86,6 +92,20 @@ int ensure_part(SparseState* s, size_t bytes) {
 __global__ void scale_kernel(const double* __restrict__ in, double a, long n, double* __restrict__ out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a * in[i];
+}
+// het noise: column n of a column-major matrix (leading dimension ld, `cols` columns) times f[n]
+// (var_dtc.py:127 psi1 * sqrt(precision) carried through Lm^-1; :226 (psi1 * beta))
+__global__ void scale_cols_kernel(double* __restrict__ A, long ld, long cols, const double* __restrict__ f) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld * cols) return;
+  A[i] *= f[i / ld];
+}
+// het noise: out[q][n] = f[n] * Y[q][n]  ([P][ld] layouts)
+__global__ void ymul_kernel(const double* __restrict__ Y, const double* __restrict__ f, long ld, int P,
+                            double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld * P) return;
+  out[i] = f[i % ld] * Y[i];
 }
 // out = a X + b Y + cdiag I + d sum_p u_p u_p^T   (n x n, leading dimension ld; X, Y, U may be null)
 __global__ void combine_kernel(double* __restrict__ out, long ld, long n, double a, const double* __restrict__ X, double b,
@@ -241,13 +261,19 @@ static int psi_device(gpx_ctx* c, int kind, int ard, double variance, const doub
 
 // dL_dKnm^T = W2 psi1^T (+ rank-P term on the fly) reduced to kernel-parameter gradients and dL/dZ; W2 (device, s->W2)
 // and C (device, s->Cm as [P][Mpad]) must be in place. Results on the host.
-static int knm_grads_device(gpx_ctx* c, double beta, double* dvariance, double* dlengthscale, double* dZ) {
+// bvec (device, [Npad], per-point precisions) selects the heteroscedastic form: VVT_factor = beta_n Y_n and the columns of
+// W2 psi1^T scaled by beta_n (var_dtc.py:226); W2 is then 2 dL_dpsi2_beta without the scalar beta.
+static int knm_grads_device(gpx_ctx* c, double beta, const double* bvec, double* dvariance, double* dlengthscale,
+                            double* dZ) {
   SparseState* s = c->sparse;
   cudaStream_t st = c->st;
   const long M = s->M, Mpad = s->Mpad, N = s->N, Npad = s->Npad;
   const int D = s->D, P = s->P;
   const int mt = (int)(Mpad / TILE), ntl = (int)(Npad / TILE);
-  scale_kernel<<<(unsigned)((Npad * P + 255) / 256), 256, 0, st>>>(s->Y, beta, Npad * P, s->Yb);
+  if (bvec)
+    ymul_kernel<<<(unsigned)((Npad * P + 255) / 256), 256, 0, st>>>(s->Y, bvec, Npad, P, s->Yb);
+  else
+    scale_kernel<<<(unsigned)((Npad * P + 255) / 256), 256, 0, st>>>(s->Y, beta, Npad * P, s->Yb);
   GPX_CUDA(cudaGetLastError());
   // dLt = W2 * psi1^T  (M x N), W2 symmetric
   {
@@ -256,6 +282,11 @@ static int knm_grads_device(gpx_ctx* c, double beta, double* dvariance, double* 
     pg.A = s->W2; pg.lda = Mpad; pg.B = s->Kfu; pg.ldb = Npad; pg.C = s->dLt; pg.ldc = Mpad;
     pg.K = (int)Mpad; pg.nt = mt; pg.ncols = ntl;
     GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
+  }
+  if (bvec) {
+    scale_cols_kernel<<<(unsigned)((Mpad * N + 255) / 256), 256, 0, st>>>(s->dLt, Mpad, N, bvec);
+    GPX_CUDA(cudaGetLastError());
+    c->total_launches++;
   }
   // kernel-parameter gradients of sum(dL_dKnm * K(X, Z)): rows i = data points, columns j = inducing points
   const int nl = s->kp.ard ? D : 1, nred = nl + 1;
@@ -320,17 +351,40 @@ static int combine(gpx_ctx* c, double* out, long Mpad, long n, double a, const d
   return 0;
 }
 
-extern "C" {
-
-int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z, int64_t M,
-                    double noise, double* lml, double* grad, double* dZ) {
+// noise_vec == nullptr: scalar noise variance `noise` (grad = [variance, lengthscale.., noise variance]);
+// noise_vec (host, one variance per row held by this rank): grad = [variance, lengthscale..], dL_dR (host, N x P row-major)
+static int sparse_eval_impl(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                            int64_t M, double noise, const double* noise_vec, double* lml, double* grad, double* dZ,
+                            double* dL_dR_out) {
   if (!c || !c->sparse || !c->sparse->X) GPX_FAIL("gpx_sparse_set_data has not been called");
   if (!Z || !lml || !grad || !dZ || !lengthscale) GPX_FAIL("null argument");
   if (M < 1) GPX_FAIL("M must be positive");
+  const bool het = noise_vec != nullptr;
+  if (het && !dL_dR_out) GPX_FAIL("null argument");
   GPX_CUDA(cudaSetDevice(c->device));
   SparseState* s = c->sparse;
   cudaStream_t st = c->st;
   s->have_eval = false;
+  // per-point precisions beta_n = 1 / max(variance_n, const_jitter) (var_dtc.py:79-84) and the sums over n the bound needs
+  std::vector<double> hbeta, hsb;
+  double sum_log_beta = 0.0, sum_beta = 0.0;
+  if (het) {
+    const long Nl = s->N, Npd = s->Npad;
+    hbeta.assign((size_t)Npd, 0.0); hsb.assign((size_t)Npd, 0.0);
+    for (long n = 0; n < Nl; n++) {
+      if (!(noise_vec[n] == noise_vec[n])) GPX_FAIL("noise variance is NaN");
+      const double b = 1.0 / std::max(noise_vec[n], 1e-8);
+      hbeta[n] = b; hsb[n] = sqrt(b);
+      sum_log_beta += log(b); sum_beta += b;
+    }
+    if (!s->hb) {
+      GPX_CUDA(cudaMalloc(&s->hb, (size_t)2 * Npd * 8));
+      GPX_CUDA(cudaMalloc(&s->hs, (size_t)(2 + s->P) * Npd * 8));
+    }
+    GPX_CUDA(cudaMemcpyAsync(s->hb, hsb.data(), (size_t)Npd * 8, cudaMemcpyHostToDevice, st));
+    GPX_CUDA(cudaMemcpyAsync(s->hb + Npd, hbeta.data(), (size_t)Npd * 8, cudaMemcpyHostToDevice, st));
+    GPX_CUDA(cudaStreamSynchronize(st));   // the host vectors are pageable
+  }
   GPX_CHECK(psi_device(c, kind, ard, variance, lengthscale, Z, M));
   const long Mpad = s->Mpad, N = s->Ntot, Npad = s->Npad;
   const int D = s->D, P = s->P, mt = (int)(Mpad / TILE), ntl = (int)(Npad / TILE);
@@ -349,8 +403,11 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
          *LBi = s->mm[7], *DB = s->mm[8], *E = s->mm[9];
   double *tv = s->vec, *vv = tv + (size_t)P * Mpad, *Cv = vv + (size_t)P * Mpad, *wv = Cv + (size_t)P * Mpad,
          *xv = wv + (size_t)P * Mpad, *rpart = s->vec + (size_t)8 * P * Mpad;
-  const double beta = 1.0 / std::max(noise, 1e-8);                                       // var_dtc.py:79-80
-  s->noise = noise;
+  // scalar noise: beta multiplies A, psi1Vf and dL_dpsi2 as a number; per-point noise: it is inside tmp, Y and the columns
+  // of dL_dKnm^T already, and the same formulas run with beta = 1
+  const double beta = het ? 1.0 : 1.0 / std::max(noise, 1e-8);                           // var_dtc.py:79-80
+  s->noise = het ? 0.0 : noise;
+  const double *sbv = het ? s->hb : nullptr, *bvec = het ? s->hb + Npad : nullptr;
   // Kmm (dense, zero padded), factor-and-invert with const_jitter (var_dtc.py:93-95)
   GPX_CUDA(cudaMemsetAsync(Kd, 0, (size_t)Mpad * Mpad * 8, st));
   {
@@ -380,6 +437,17 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
     pg.K = (int)Mpad; pg.nt = mt; pg.ncols = ntl;
     GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
   }
+  const double* Yrow = s->Y;   // right-hand side of t = tmp Y
+  if (het) {
+    // s1_n = sum_a tmp[a, n]^2 (var_dtc.py:249, before the scaling); then tmp[:, n] *= sqrt(beta_n) (:127,131), Y_n likewise
+    GPX_CHECK(launch_col_sqnorm(Tuf, Mpad, M, s->N, s->hs, st));
+    scale_cols_kernel<<<(unsigned)((Mpad * s->N + 255) / 256), 256, 0, st>>>(Tuf, Mpad, s->N, sbv);
+    GPX_CUDA(cudaGetLastError());
+    ymul_kernel<<<(unsigned)((Npad * P + 255) / 256), 256, 0, st>>>(s->Y, sbv, Npad, P, s->Yb);
+    GPX_CUDA(cudaGetLastError());
+    Yrow = s->Yb;
+    c->total_launches += 3;
+  }
   {
     GemmParams pg = gemm_defaults();   // A_raw = tmp tmp^T (lower tiles), k-depth = Npad
     pg.mode = GEMM_PANEL; pg.plain = 2;
@@ -387,7 +455,7 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
     pg.K = (int)Npad; pg.nt = mt; pg.ncols = mt;
     GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
   }
-  GPX_CHECK(launch_row_dot(Tuf, Mpad, Mpad, s->N, P, s->Y, Npad, RSPLIT, rpart, tv, st));   // t = tmp Y  ([P][Mpad])
+  GPX_CHECK(launch_row_dot(Tuf, Mpad, Mpad, s->N, P, Yrow, Npad, RSPLIT, rpart, tv, st));   // t = tmp Y  ([P][Mpad])
   // row shards: A_raw and t are sums over data points -> one M x M and one M x P all-reduce
   // (the pattern of var_dtc_parallel.py:113-131 with NCCL instead of mpi4py)
   GPX_CHECK(dist_allreduce_sum(c, Ar, (size_t)Mpad * Mpad, st));
@@ -414,6 +482,28 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   GPX_CHECK(launch_col_dot(UB, Mpad, Mpad, Mpad, P, xv, Mpad, vv, Mpad, st));           // v = UB^T x = LBi x
   GPX_CHECK(launch_col_dot(LBi, Mpad, Mpad, Mpad, P, vv, Mpad, wv, Mpad, st));          // w = LBi^T v
   GPX_CHECK(launch_col_dot(Lmi, Mpad, Mpad, Mpad, P, wv, Mpad, Cv, Mpad, st));          // C = Lmi^T w
+  std::vector<double> hstat, hY;
+  if (het) {
+    // _compute_dL_dR, het_noise (var_dtc.py:241-257): per data point
+    //   r_np = (v_p^T LB^-1 Lm^-1 psi1^T)_n = w_p . tmp[:, n]     (here from the scaled tmp: r_np sqrt(beta_n))
+    //   s2_n = |LB^-1 Lm^-1 psi1^T[:, n]|^2 = |(Q psi1^T)[:, n]|^2,  Q = LB^-1 Lm^-1 (lower triangular)
+    double *s2v = s->hs + Npad, *rv = s->hs + 2 * Npad;
+    GPX_CHECK(launch_col_dot(Tuf, Mpad, M, s->N, P, wv, Mpad, rv, Npad, st));
+    GPX_CHECK(mm_nt(c, LBi, Um, T, Mpad));                                                // Q = LBi Um^T = LBi Lmi
+    {
+      GemmParams pg = gemm_defaults();
+      pg.mode = GEMM_PANEL; pg.plain = 1; pg.tri = 2;
+      pg.A = T; pg.lda = Mpad; pg.B = s->Kfu; pg.ldb = Npad; pg.C = s->dLt; pg.ldc = Mpad;
+      pg.K = (int)Mpad; pg.nt = mt; pg.ncols = ntl;
+      GPX_CHECK(launch_gemm(pg, dim3(1, 1), st));
+    }
+    GPX_CHECK(launch_col_sqnorm(s->dLt, Mpad, M, s->N, s2v, st));
+    hstat.resize((size_t)(2 + P) * Npad);
+    hY.resize((size_t)P * Npad);
+    GPX_CUDA(cudaMemcpyAsync(hstat.data(), s->hs, hstat.size() * 8, cudaMemcpyDeviceToHost, st));
+    GPX_CUDA(cudaMemcpyAsync(hY.data(), s->Y, hY.size() * 8, cudaMemcpyDeviceToHost, st));
+    c->total_launches += 3;
+  }
   // Binv = UB UB^T (lower tiles, mirrored) ; DBi = P Binv + w w^T
   GPX_CHECK(mm_nt(c, UB, UB, DB, Mpad, 2));
   {
@@ -442,7 +532,7 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   GPX_CUDA(cudaMemcpyAsync(s->Cm, Cv, (size_t)P * Mpad * 8, cudaMemcpyDeviceToDevice, st));
   double dv_knm = 0.0;
   std::vector<double> dl_knm(nl, 0.0);
-  GPX_CHECK(knm_grads_device(c, beta, &dv_knm, dl_knm.data(), dZ));                     // dZ <- Knm part
+  GPX_CHECK(knm_grads_device(c, beta, bvec, &dv_knm, dl_knm.data(), dZ));               // dZ <- Knm part
   {
     int rank = 0, G = 1;
     dist_world(c, &rank, &G);
@@ -504,10 +594,45 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   const double psi0_sum = variance * (double)N;
   const double nd = (double)N, od = (double)P;
   const double log2pi = 1.8378770664093453;
-  const double lik_1 = -0.5 * nd * od * (log2pi - log(beta)) - 0.5 * beta * s->trYYT;
-  const double lik_2 = -0.5 * od * (beta * psi0_sum - trA);
   const double lik_3 = -od * 0.5 * logdetB;
   const double lik_4 = 0.5 * data_fit;
+  if (het) {
+    // bound (var_dtc.py:267-269) and the N x P per-point noise gradients (:245-257), rows of this rank
+    const long Nl = s->N;
+    const double *s1 = hstat.data(), *s2 = s1 + Npad, *rs = s2 + Npad;
+    double sum_bY2 = 0.0;
+    for (long n = 0; n < Nl; n++) {
+      const double b = hbeta[n], b2 = b * b;
+      const double common = -0.5 * b + 0.5 * od * (variance - s1[n]) * b2 + 0.5 * s2[n] * b2;
+      for (int q = 0; q < P; q++) {
+        const double y = hY[(size_t)q * Npad + n], r = rs[(size_t)q * Npad + n] / hsb[n];
+        sum_bY2 += b * y * y;
+        dL_dR_out[n * P + q] = common + 0.5 * (b * y) * (b * y) - r * y * b2 + 0.5 * r * r * b2;
+      }
+    }
+    double sums[3] = {sum_log_beta, sum_beta, sum_bY2};
+    {
+      int rank = 0, G = 1;
+      dist_world(c, &rank, &G);
+      if (G > 1) {   // sums over this rank's rows -> totals
+        memcpy(s->h_red, sums, sizeof(sums));
+        GPX_CUDA(cudaMemcpyAsync(s->red, s->h_red, sizeof(sums), cudaMemcpyHostToDevice, st));
+        GPX_CHECK(dist_allreduce_sum(c, s->red, 3, st));
+        GPX_CUDA(cudaMemcpyAsync(s->h_red, s->red, sizeof(sums), cudaMemcpyDeviceToHost, st));
+        GPX_CUDA(cudaStreamSynchronize(st));
+        memcpy(sums, s->h_red, sizeof(sums));
+      }
+    }
+    const double lik_1h = -0.5 * nd * od * log2pi + 0.5 * od * sums[0] - 0.5 * sums[2];
+    const double lik_2h = -0.5 * od * (variance * sums[1] - trA);
+    *lml = lik_1h + lik_2h + lik_3 + lik_4;
+    grad[0] = -0.5 * od * sums[1] + dv_knm + dv_kmm;                                       // update_gradients_diag (:110)
+    for (int q = 0; q < nl; q++) grad[1 + q] = dl_knm[q] + dl_kmm[q];
+    s->have_eval = true;
+    return 0;
+  }
+  const double lik_1 = -0.5 * nd * od * (log2pi - log(beta)) - 0.5 * beta * s->trYYT;
+  const double lik_2 = -0.5 * od * (beta * psi0_sum - trA);
   *lml = lik_1 + lik_2 + lik_3 + lik_4;
   double dL_dR = -0.5 * nd * od * beta + 0.5 * s->trYYT * beta * beta;
   dL_dR += 0.5 * od * (psi0_sum * beta * beta - trA * beta);
@@ -520,6 +645,19 @@ int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double
   grad[1 + nl] = dL_dR;
   s->have_eval = true;
   return 0;
+}
+
+extern "C" {
+
+int gpx_sparse_eval(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z, int64_t M,
+                    double noise, double* lml, double* grad, double* dZ) {
+  return sparse_eval_impl(c, kind, ard, variance, lengthscale, Z, M, noise, nullptr, lml, grad, dZ, nullptr);
+}
+
+int gpx_sparse_eval_het(gpx_ctx* c, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                        int64_t M, const double* noise_variances, double* lml, double* grad, double* dZ, double* dL_dR) {
+  if (!noise_variances) GPX_FAIL("null argument");
+  return sparse_eval_impl(c, kind, ard, variance, lengthscale, Z, M, 0.0, noise_variances, lml, grad, dZ, dL_dR);
 }
 
 /* which: 0 woodbury_vector (M x P row-major), 1 woodbury_inv (M x M), 2 Kmm (+1e-8 I), 3 Lm (lower, col-major) */

@@ -4,7 +4,9 @@ Mirrors:
     GPy.inference.latent_function_inference.VarDTC.inference   GPy/inference/latent_function_inference/var_dtc.py:66-215
     GPy.core.SparseGP.parameters_changed / _update_gradients   GPy/core/sparse_gp.py:76-119
     GPy.models.SparseGPRegression                              GPy/models/sparse_gp_regression.py:33-59
-(Gaussian likelihood, homoscedastic noise, certain inputs, no mean function — BASELINE.json configs[4].)
+(Gaussian likelihood, certain inputs, no mean function — BASELINE.json configs[4]; scalar noise through gpx_sparse_eval,
+one noise variance per data point — the `het_noise` branches var_dtc.py:127-128,221-227,241-257,267-269 with a
+HeteroscedasticGaussian likelihood — through gpx_sparse_eval_het.)
 
 ONE call, gpx_sparse_eval, does the whole evaluation on the device — psi1 = K(X, Z), tmp = Lm^-1 psi1^T, A = beta tmp
 tmp^T, the two M x M factor-and-invert sweeps (Kmm, B = I + A), every M x M product, dL_dKnm = (beta Y) C^T + 2 psi1
@@ -15,7 +17,7 @@ attached to a NCCL communicator, X and Y are this rank's rows (gpy_b200.dist.sha
 import numpy as np
 
 from . import _ffi
-from .inference import Gaussian, _DataKey
+from .inference import Gaussian, HeteroscedasticGaussian, _DataKey
 from .kern import RBF, Stationary
 from .param import Logexp, Param, Parameterized
 
@@ -103,6 +105,20 @@ class VarDTC(object):
         num_data, output_dim = Y.shape
         num_inducing = Zs.shape[0]
         kind, ard, var, ls = kern._theta()
+        if precision is None:
+            gv = np.asarray(likelihood.gaussian_variance(Y_metadata), dtype=np.float64)
+            if gv.size > 1:                                                                # het_noise (var_dtc.py:82-84)
+                if gv.size != num_data:
+                    raise ValueError("one noise variance per data point expected")
+                lml, grad, dZ, dR = eng.sparse_eval_het(kind, ard, var, ls, Zs, gv.reshape(-1))
+                dL_dthetaL = likelihood.exact_inference_gradients(dR, Y_metadata)         # var_dtc.py:176
+                return LazySparsePosterior(eng), float(lml), {"dvariance": grad[0], "dlengthscale": grad[1:], "dZ": dZ,
+                                                              "dL_dthetaL": dL_dthetaL, "num_data": num_data}
+        elif np.size(precision) > 1:
+            pv = np.asarray(precision, dtype=np.float64).reshape(-1)
+            lml, grad, dZ, dR = eng.sparse_eval_het(kind, ard, var, ls, Zs, 1.0 / pv)
+            return LazySparsePosterior(eng), float(lml), {"dvariance": grad[0], "dlengthscale": grad[1:], "dZ": dZ,
+                                                          "dL_dthetaL": dR, "num_data": num_data}
         noise_var = None
         if precision is None:
             noise_var = float(np.squeeze(np.asarray(likelihood.gaussian_variance(Y_metadata))))
@@ -119,7 +135,8 @@ class SparseGPRegression(Parameterized):
     """GPy.models.SparseGPRegression (sparse_gp_regression.py:33-59) / GPy.core.SparseGP (sparse_gp.py:38-119).
     Parameter (and gradient) order as in the reference: [inducing inputs, kern.variance, kern.lengthscale, noise]."""
 
-    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, device=0, engine=None, name="sparse_gp"):
+    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, device=0, engine=None, name="sparse_gp", likelihood=None,
+                 Y_metadata=None):
         super(SparseGPRegression, self).__init__(name)
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
@@ -133,7 +150,10 @@ class SparseGPRegression(Parameterized):
             assert Z.shape[1] == input_dim
         self.X, self.Y = X, Y
         self.kern = kernel
-        self.likelihood = Gaussian()                                            # :47
+        # :47; core/sparse_gp.py:41 accepts any likelihood: a HeteroscedasticGaussian (with its Y_metadata) selects VarDTC's
+        # het_noise branches
+        self.likelihood = Gaussian() if likelihood is None else likelihood
+        self.Y_metadata = Y_metadata
         self.Z = Param("inducing inputs", np.array(Z, dtype=np.float64), transform=None)
         self.Z.values = np.array(Z, dtype=np.float64)                          # keep the M x D shape
         self.Z.gradient = np.zeros_like(self.Z.values)
@@ -148,7 +168,7 @@ class SparseGPRegression(Parameterized):
     def parameters_changed(self):
         Z = self.Z.values
         self.posterior, self._log_marginal_likelihood, gd = self.inference_method.inference(
-            self.kern, self.X, Z, self.likelihood, self.Y)
+            self.kern, self.X, Z, self.likelihood, self.Y, self.Y_metadata)
         self.grad_dict = gd
         self.likelihood.update_gradients(gd["dL_dthetaL"])                                     # :84
         self.kern.variance.gradient = np.atleast_1d(gd["dvariance"])          # :110-114 summed on the device
@@ -225,9 +245,12 @@ class SparseGPRegression(Parameterized):
         self.optimizer_array = x
         return ok
 
-    def predict(self, Xnew, full_cov=False, include_likelihood=True):
+    def predict(self, Xnew, full_cov=False, include_likelihood=True, Y_metadata=None):
         """gp.py:290-365 with the sparse posterior (predictive variable = Z)."""
         mu, var = self.posterior._raw_predict(self.kern, np.asarray(Xnew, dtype=np.float64), self.Z.values, full_cov)
         if include_likelihood:
-            mu, var = self.likelihood.predictive_values(mu, var, full_cov)
+            if isinstance(self.likelihood, HeteroscedasticGaussian) and Y_metadata is None:
+                raise ValueError("a heteroscedastic likelihood needs Y_metadata (output_index) for the new points, or "
+                                 "include_likelihood=False (gp_heteroscedastic_regression.py:13-15)")
+            mu, var = self.likelihood.predictive_values(mu, var, full_cov, Y_metadata=Y_metadata)
         return mu, var

@@ -148,6 +148,16 @@ int gpx_sparse_set_data(gpx_ctx* ctx, const double* X, int64_t N, int D, const d
 int gpx_sparse_eval(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* Z,
                     int64_t M, double noise_variance, double* lml, double* grad, double* dZ);
 int gpx_sparse_get(gpx_ctx* ctx, int which, double* out);
+/* The same evaluation with ONE NOISE VARIANCE PER DATA POINT (HeteroscedasticGaussian, likelihoods/gaussian.py:347-362):
+ * the `het_noise` branches of VarDTC.inference — tmp = Lm^-1 (psi1 sqrt(beta))^T (var_dtc.py:127-131), dL_dpsi1 += 2
+ * (dL_dpsi2_beta (psi1 beta)^T)^T (:221-227), the bound with sum(log beta_n) and sum(beta_n |Y_n|^2) (:267-269) and the
+ * per-point noise gradients dL_dR (:241-257). noise_variances: N values (this rank's rows); grad: (1 + nl) entries
+ * [variance, lengthscale..]; dL_dR: N x P row-major, what HeteroscedasticGaussian.exact_inference_gradients indexes by
+ * output_index (gaussian.py:358-359). dL_dR needs three column reductions over M x N matrices (|Lm^-1 psi1^T[:, n]|^2,
+ * |LB^-1 Lm^-1 psi1^T[:, n]|^2, v^T LB^-1 Lm^-1 psi1^T[:, n]); nothing of size N x M crosses PCIe. gpx_sparse_get serves
+ * the posterior of this evaluation as well. */
+int gpx_sparse_eval_het(gpx_ctx* ctx, int kind, int ard, double variance, const double* lengthscale, const double* Z,
+                        int64_t M, const double* noise_variances, double* lml, double* grad, double* dZ, double* dL_dR);
 
 /* Measurement hooks (bench.py): device time of the last eval between CUDA events on the launching stream, the number
  * of kernels this library launched since creation, and per-phase accounting of the last eval. */

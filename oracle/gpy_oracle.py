@@ -544,11 +544,19 @@ def backsub_both_sides(L, X, transpose="left"):
 
 
 def vardtc_inference(kern, X, Z, noise_variance, Y):
-    """var_dtc.py:66-215. Returns dict(log_marginal, dL_dKmm, dL_dKdiag, dL_dKnm, dL_dthetaL, woodbury_vector,
-    woodbury_inv, Lm, Kmm)."""
+    """var_dtc.py:66-215. `noise_variance` scalar (Gaussian) or one value per data point (HeteroscedasticGaussian:
+    `het_noise`, :82-84, the branches :127-128, :221-227, :241-257, :267-269). Returns dict(log_marginal, dL_dKmm,
+    dL_dKdiag, dL_dKnm, dL_dthetaL, woodbury_vector, woodbury_inv, Lm, Kmm); dL_dthetaL is the scalar sum for a scalar
+    noise and the N x P array dL_dR for per-point noise (heteroscedastic_gaussian.py:33-34 indexes it by output_index)."""
     num_data, output_dim = Y.shape
     num_inducing = Z.shape[0]
     precision = 1.0 / np.fmax(noise_variance, VARDTC_JITTER)  # :79-80
+    precision = np.asarray(precision, dtype=np.float64)
+    if precision.ndim == 1:  # :82-83
+        precision = precision[:, None]
+    het_noise = precision.size > 1  # :84
+    if not het_noise:
+        precision = float(precision)
     beta = precision
     VVT_factor = precision * Y  # :89
     trYYT = np.einsum("ij,ij->", Y, Y)  # :37
@@ -557,7 +565,7 @@ def vardtc_inference(kern, X, Z, noise_variance, Y):
     Lm, _ = jitchol(Kmm)  # :95
     psi0 = kern.Kdiag(X)  # :124
     psi1 = kern.K(X, Z)  # :126
-    tmp = psi1 * np.sqrt(precision)  # :130
+    tmp = psi1 * np.sqrt(precision)  # :127-130 (N x M times N x 1 for per-point noise)
     tmp, _ = dtrtrs(Lm, tmp.T, lower=1)  # :131
     A = tdot(tmp)  # :132
     B = np.eye(num_inducing) + A  # :135
@@ -574,33 +582,55 @@ def vardtc_inference(kern, X, Z, noise_variance, Y):
     delit += -0.5 * B * output_dim
     delit += output_dim * np.eye(num_inducing)
     dL_dKmm = backsub_both_sides(Lm, delit)  # :156
-    # _compute_dL_dpsi (:217-234), homoscedastic / certain inputs
+    # _compute_dL_dpsi (:217-234), certain inputs
     dL_dpsi0 = -0.5 * output_dim * (beta * np.ones([num_data, 1])).flatten()
     dL_dpsi1 = np.dot(VVT_factor, Cpsi1Vf.T)
     dL_dpsi2_beta = 0.5 * backsub_both_sides(Lm, output_dim * np.eye(num_inducing) - DBi_plus_BiPBi)
-    dL_dpsi2 = beta * dL_dpsi2_beta
-    dL_dpsi1 += 2.0 * np.dot(psi1, dL_dpsi2)
+    if het_noise:
+        dL_dpsi1 += 2.0 * np.dot(dL_dpsi2_beta, (psi1 * beta).T).T  # :226
+    else:
+        dL_dpsi2 = beta * dL_dpsi2_beta
+        dL_dpsi1 += 2.0 * np.dot(psi1, dL_dpsi2)  # :232
     # _compute_log_marginal_likelihood (:265-276)
-    lik_1 = -0.5 * num_data * output_dim * (np.log(2.0 * np.pi) - np.log(beta)) - 0.5 * beta * trYYT
-    lik_2 = -0.5 * output_dim * (np.sum(beta * psi0) - np.trace(A))
+    if het_noise:
+        lik_1 = (-0.5 * num_data * output_dim * np.log(2.0 * np.pi) + 0.5 * output_dim * np.sum(np.log(beta))
+                 - 0.5 * np.sum(beta.ravel() * np.square(Y).sum(axis=-1)))  # :268
+        lik_2 = -0.5 * output_dim * (np.sum(beta.flatten() * psi0) - np.trace(A))  # :269
+    else:
+        lik_1 = -0.5 * num_data * output_dim * (np.log(2.0 * np.pi) - np.log(beta)) - 0.5 * beta * trYYT
+        lik_2 = -0.5 * output_dim * (np.sum(beta * psi0) - np.trace(A))
     lik_3 = -output_dim * (np.sum(np.log(np.diag(LB))))
     lik_4 = 0.5 * data_fit
     log_marginal = lik_1 + lik_2 + lik_3 + lik_4
-    # _compute_dL_dR (:237-263), homoscedastic
-    dL_dR = -0.5 * num_data * output_dim * beta + 0.5 * trYYT * beta ** 2
-    dL_dR += 0.5 * output_dim * (psi0.sum() * beta ** 2 - np.trace(A) * beta)
-    dL_dR += beta * (0.5 * np.sum(A * DBi_plus_BiPBi) - data_fit)
+    # _compute_dL_dR (:237-263)
+    if het_noise:  # :241-257
+        LBi, _ = dtrtrs(LB, np.eye(LB.shape[0]))
+        Lmi_psi1, _ = dtrtrs(Lm, psi1.T, lower=1, trans=0)
+        _LBi_Lmi_psi1, _ = dtrtrs(LB, Lmi_psi1, lower=1, trans=0)
+        dL_dR = -0.5 * beta + 0.5 * VVT_factor ** 2
+        dL_dR += 0.5 * output_dim * (psi0 - np.sum(Lmi_psi1 ** 2, 0))[:, None] * beta ** 2
+        dL_dR += 0.5 * np.sum(np.dot(LBi.T, np.dot(LBi, Lmi_psi1)) * Lmi_psi1, 0)[:, None] * beta ** 2
+        dL_dR += -np.dot(_LBi_Lmi_psi1Vf.T, _LBi_Lmi_psi1).T * Y * beta ** 2
+        dL_dR += 0.5 * np.dot(_LBi_Lmi_psi1Vf.T, _LBi_Lmi_psi1).T ** 2 * beta ** 2
+        dL_dthetaL = dL_dR
+    else:
+        dL_dR = -0.5 * num_data * output_dim * beta + 0.5 * trYYT * beta ** 2
+        dL_dR += 0.5 * output_dim * (psi0.sum() * beta ** 2 - np.trace(A) * beta)
+        dL_dR += beta * (0.5 * np.sum(A * DBi_plus_BiPBi) - data_fit)
+        dL_dthetaL = float(np.sum(dL_dR))
     # posterior (:201-214)
     Bi = -dpotri(LB, lower=1)[0]
     diag_add(Bi, 1)
     woodbury_inv = backsub_both_sides(Lm, Bi)
     return dict(log_marginal=float(log_marginal), dL_dKmm=dL_dKmm, dL_dKdiag=dL_dpsi0, dL_dKnm=dL_dpsi1,
-                dL_dthetaL=float(np.sum(dL_dR)), woodbury_vector=Cpsi1Vf, woodbury_inv=woodbury_inv, Lm=Lm, Kmm=Kmm)
+                dL_dthetaL=dL_dthetaL, woodbury_vector=Cpsi1Vf, woodbury_inv=woodbury_inv, Lm=Lm, Kmm=Kmm)
 
 
 def sparse_eval(X, Y, Z, kind, ARD, variance, lengthscale, noise_variance):
     """One SparseGP.parameters_changed() (GPy/core/sparse_gp.py:76-119): returns (log_marginal,
-    grad [kern.variance, kern.lengthscale.., Gaussian_noise.variance], Z.gradient, res)."""
+    grad [kern.variance, kern.lengthscale.., Gaussian_noise.variance], Z.gradient, res). With one noise variance per data
+    point (a vector `noise_variance`) the tail of grad is dL_dR row by row (N*P entries), which
+    HeteroscedasticGaussian.exact_inference_gradients hands to its variance parameter (heteroscedastic_gaussian.py:33-34)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     Z = np.ascontiguousarray(Z, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
@@ -613,7 +643,7 @@ def sparse_eval(X, Y, Z, kind, ARD, variance, lengthscale, noise_variance):
     dlen = np.atleast_1d(dl0) + np.atleast_1d(dl1) + np.atleast_1d(dl2)
     Zgrad = kern.gradients_X(res["dL_dKmm"], Z)  # :117
     Zgrad = Zgrad + kern.gradients_X(res["dL_dKnm"].T, Z, X)  # :118
-    grad = np.concatenate([[dvar], dlen, [res["dL_dthetaL"]]])
+    grad = np.concatenate([[dvar], dlen, np.asarray(res["dL_dthetaL"], dtype=np.float64).reshape(-1)])
     return res["log_marginal"], grad, Zgrad, res
 
 

@@ -254,3 +254,33 @@ def evaluate_sparse(G, X, Y, Z, kind, ARD, variance, lengthscale, noise):
     return dict(lml=float(np.squeeze(lml)), grad=grad, Zgrad=np.asarray(Zgrad), woodbury_vector=np.asarray(post.woodbury_vector),
                 woodbury_inv=np.asarray(post.woodbury_inv), dL_dKmm=np.asarray(gd["dL_dKmm"]),
                 dL_dKnm=np.asarray(gd["dL_dKnm"]))
+
+
+def evaluate_sparse_het(G, X, Y, Z, kind, ARD, variance, lengthscale, noise_vec):
+    """One SparseGP.parameters_changed() with the reference's own VarDTC and HeteroscedasticGaussian (one noise variance
+    per data point: the `het_noise` branches var_dtc.py:127-128,221-227,241-257,267-269); gradient wiring of
+    GPy/core/sparse_gp.py:108-119, the likelihood gradient through heteroscedastic_gaussian.py:33-40."""
+    import numpy as np
+    N, D = X.shape
+    Y_metadata = {"output_index": np.arange(N)[:, None]}
+    kern = getattr(G, KERNELS[kind])(D, variance=variance, lengthscale=lengthscale, ARD=ARD)
+    lik = G.HeteroscedasticGaussian(Y_metadata)
+    lik.variance[:] = np.asarray(noise_vec).reshape(lik.variance.shape)
+    inf = G.VarDTC(limit=3)
+    post, lml, gd = inf.inference(kern, X, Z, lik, Y, Y_metadata)                 # sparse_gp.py:77-80
+
+    def kgrad():
+        return np.concatenate([np.atleast_1d(kern.variance.gradient).reshape(-1),
+                               np.atleast_1d(kern.lengthscale.gradient).reshape(-1) * np.ones(kern.lengthscale.size)])
+
+    kern.update_gradients_diag(gd["dL_dKdiag"], X)                                 # :110
+    kerngrad = kgrad().copy()
+    kern.update_gradients_full(gd["dL_dKnm"], X, Z)                                # :112
+    kerngrad += kgrad()
+    kern.update_gradients_full(gd["dL_dKmm"], Z, None)                             # :114
+    kerngrad += kgrad()
+    Zgrad = kern.gradients_X(gd["dL_dKmm"], Z)                                     # :117
+    Zgrad = Zgrad + kern.gradients_X(gd["dL_dKnm"].T, Z, X)                        # :118
+    grad = np.concatenate([kerngrad, np.asarray(gd["dL_dthetaL"], dtype=np.float64).reshape(-1)])
+    return dict(lml=float(np.squeeze(lml)), grad=grad, Zgrad=np.asarray(Zgrad), woodbury_vector=np.asarray(post.woodbury_vector),
+                woodbury_inv=np.asarray(post.woodbury_inv))

@@ -127,7 +127,44 @@ def main_sparse():
         print("%-36s lml %.10f source %s" % (name, lml, source))
 
 
+SPARSE_HET_CASES = [("sparse_het_rbf_ard_n300_m40_d3", "rbf", True, 300, 40, 3, 1, 31),
+                    ("sparse_het_matern32_iso_n450_m130_d2", "matern32", False, 450, 130, 2, 1, 32)]
+
+
+def main_sparse_het():
+    """tests/golden/sparse_het/*.npz: VarDTC with one noise variance per data point (the het_noise branches
+    var_dtc.py:127-128,221-227,241-257,267-269), produced by the reference's own VarDTC + HeteroscedasticGaussian."""
+    GPy = try_reference()
+    os.makedirs(os.path.join(HERE, "sparse_het"), exist_ok=True)
+    for name, kind, ARD, N, M, D, P, seed in SPARSE_HET_CASES:
+        rng = np.random.default_rng(100 + seed)
+        X = rng.uniform(-3, 3, (N, D))
+        Y = np.sin(X).sum(1, keepdims=True) / np.sqrt(D) + 0.1 * rng.standard_normal((N, P))
+        Z = X[rng.permutation(N)[:M]].copy() + 0.01 * rng.standard_normal((M, D))
+        var = float(rng.uniform(0.5, 2.0))
+        ls = np.sqrt(D) * rng.uniform(0.6, 1.5, D) if ARD else float(np.sqrt(D) * rng.uniform(0.6, 1.5))
+        nv = rng.uniform(0.01, 0.3, N)
+        lml, grad, Zg, res = o.sparse_eval(X, Y, Z, kind, ARD, var, ls, nv)
+        wv, wi, source = res["woodbury_vector"], res["woodbury_inv"], "oracle"
+        if GPy is not None:
+            from oracle import ref_gpy
+            r = ref_gpy.evaluate_sparse_het(GPy, X, Y, Z, kind, ARD, var, ls, nv)
+            assert abs(r["lml"] - lml) <= 1e-8 * max(1, abs(lml)), (name, r["lml"], lml)
+            np.testing.assert_allclose(r["grad"], grad, rtol=1e-6, atol=1e-7, err_msg=name)
+            np.testing.assert_allclose(r["Zgrad"], Zg, rtol=1e-6, atol=1e-7, err_msg=name)
+            lml, grad, Zg, wv, wi = r["lml"], r["grad"], r["Zgrad"], r["woodbury_vector"], r["woodbury_inv"]
+            source = "GPy %s (unmodified /root/reference via oracle/paramz_shim)" % GPy.__version__
+        np.savez_compressed(os.path.join(HERE, "sparse_het", name + ".npz"), X=X, Y=Y, Z=Z, kind=kind, ARD=ARD, variance=var,
+                            lengthscale=ls, noise_variances=nv, lml=lml, grad=grad, Zgrad=Zg, woodbury_vector=wv,
+                            woodbury_inv=wi, source=source)
+        print("%-40s lml %.10f source %s" % (name, lml, source))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sparse_het":   # only the fixtures added last (the others stay byte-identical)
+        main_sparse_het()
+        sys.exit(0)
     main()
     main_het()
     main_sparse()
+    main_sparse_het()

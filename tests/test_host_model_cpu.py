@@ -235,3 +235,77 @@ def test_normalizer_and_pickle_round_trip():
     m2.inference_method._engine = FakeEngine()           # stands for the lazily re-created device context
     m2.parameters_changed()
     assert abs(m2.log_likelihood() - lml0) < 1e-9 and m2.inference_method._engine.calls == ["set_data", "exact_eval"]
+
+
+class FakeSparseEngine(object):
+    """test double for the sparse entry points of gpy_b200._ffi.Engine: numbers from the oracle's VarDTC."""
+
+    def __init__(self):
+        self.calls, self.sparse_serial = [], 0
+
+    def sparse_set_data(self, X, Y):
+        self.X, self.Y = np.array(X), np.array(Y)
+        self.calls.append("sparse_set_data")
+
+    def sparse_eval(self, kind, ARD, variance, lengthscale, Z, noise_variance):
+        self.calls.append("sparse_eval")
+        self.sparse_serial += 1
+        lml, g, Zg, self.res = o.sparse_eval(self.X, self.Y, Z, kind, ARD, variance, lengthscale, noise_variance)
+        return lml, g, Zg
+
+    def sparse_eval_het(self, kind, ARD, variance, lengthscale, Z, noise_variances):
+        self.calls.append("sparse_eval_het")
+        self.sparse_serial += 1
+        lml, g, Zg, self.res = o.sparse_eval(self.X, self.Y, Z, kind, ARD, variance, lengthscale,
+                                             np.asarray(noise_variances).reshape(-1))
+        nk = g.size - self.X.shape[0] * self.Y.shape[1]
+        return lml, g[:nk], Zg, g[nk:].reshape(self.X.shape[0], self.Y.shape[1])
+
+    def sparse_get(self, what):
+        return {"woodbury_vector": self.res["woodbury_vector"], "woodbury_inv": self.res["woodbury_inv"],
+                "Kmm": self.res["Kmm"], "Lm": self.res["Lm"]}[what]
+
+
+def test_sparse_model_selects_the_heteroscedastic_branch_from_the_likelihood():
+    """core/sparse_gp.py:76-119 with a HeteroscedasticGaussian likelihood: VarDTC.inference must take the het_noise route
+    (precision.size > 1, var_dtc.py:82-84), hand dL_dR to the likelihood by output_index (gaussian.py:358-359), and the
+    model's gradient must be the derivative of its own objective (finite differences in the optimizer space)."""
+    import gpy_b200
+    rng = np.random.default_rng(5)
+    N, M, D = 90, 12, 2
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.sin(X).sum(1, keepdims=True) + 0.1 * rng.standard_normal((N, 1))
+    Z = X[rng.permutation(N)[:M]] + 0.01
+    meta = {"output_index": np.arange(N)[:, None]}
+    lik = gpy_b200.HeteroscedasticGaussian(meta)
+    nv = rng.uniform(0.02, 0.3, N)
+    lik.variance.values[...] = nv
+    eng = FakeSparseEngine()
+
+    class HostRBF(gpy_b200.RBF):
+        """answers K / Kdiag from the oracle (no device here)"""
+        def K(self, X, X2=None):
+            return o.StationaryOracle("rbf", self.input_dim, float(self.variance[0]), self.lengthscale.values, self.ARD).K(X, X2)
+        def Kdiag(self, X):
+            return np.full(X.shape[0], float(self.variance[0]))
+
+    m = gpy_b200.SparseGPRegression(X, Y, kernel=HostRBF(D, variance=1.2, lengthscale=[1.1, 1.8], ARD=True), Z=Z,
+                                    engine=eng, likelihood=lik, Y_metadata=meta)
+    assert "sparse_eval_het" in eng.calls and "sparse_eval" not in eng.calls
+    lml0, g0, Zg0, _ = o.sparse_eval(X, Y, Z, "rbf", True, 1.2, np.array([1.1, 1.8]), nv)
+    assert abs(m.log_likelihood() - lml0) <= 1e-10 * abs(lml0)
+    g = np.concatenate([m.kern.variance.gradient, m.kern.lengthscale.gradient, m.likelihood.variance.gradient])
+    np.testing.assert_allclose(g, g0, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(m.Z.gradient, Zg0, rtol=1e-12, atol=1e-12)
+    assert m.optimizer_array.size == M * D + 1 + 2 + N
+    assert m.checkgrad(step=1e-5)
+    mu, var = m.predict(X[:4], include_likelihood=False)
+    assert mu.shape == (4, 1) and var.shape == (4, 1)
+    with pytest.raises(ValueError):
+        m.predict(X[:4])                                           # no noise model away from the training points
+    mu2, var2 = m.predict(X[:4], Y_metadata={"output_index": np.arange(4)[:, None]})
+    np.testing.assert_allclose(var2, var + nv[:4, None], rtol=1e-12)
+    # a scalar-noise model on the same engine class takes the homoscedastic entry point
+    eng2 = FakeSparseEngine()
+    gpy_b200.SparseGPRegression(X, Y, kernel=gpy_b200.RBF(D), Z=Z, engine=eng2)
+    assert "sparse_eval" in eng2.calls and "sparse_eval_het" not in eng2.calls

@@ -167,6 +167,41 @@ def test_golden_sparse_fixtures_reproduce():
         np.testing.assert_allclose(Zg, z["Zgrad"], rtol=1e-6, atol=1e-8, err_msg=fn)
 
 
+def test_golden_sparse_heteroscedastic_fixtures_reproduce():
+    """tests/golden/sparse_het/*.npz: VarDTC with one noise variance per data point (var_dtc.py:127-128,221-227,241-257,
+    267-269), numbers produced by the reference's own VarDTC + HeteroscedasticGaussian objects."""
+    gdir = os.path.join(os.path.dirname(__file__), "golden", "sparse_het")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".npz"))
+    assert files
+    for fn in files:
+        z = np.load(os.path.join(gdir, fn))
+        assert "GPy" in str(z["source"]), fn
+        kind, ARD = str(z["kind"]), bool(z["ARD"])
+        ls = z["lengthscale"] if ARD else float(z["lengthscale"])
+        lml, g, Zg, res = o.sparse_eval(z["X"], z["Y"], z["Z"], kind, ARD, float(z["variance"]), ls, z["noise_variances"])
+        assert g.size == z["grad"].size == 1 + np.size(ls) + z["X"].shape[0] * z["Y"].shape[1], fn
+        assert abs(lml - float(z["lml"])) <= 1e-8 * max(1.0, abs(float(z["lml"]))), fn
+        np.testing.assert_allclose(g, z["grad"], rtol=1e-6, atol=1e-7, err_msg=fn)
+        np.testing.assert_allclose(Zg, z["Zgrad"], rtol=1e-6, atol=1e-7, err_msg=fn)
+        np.testing.assert_allclose(res["woodbury_vector"], z["woodbury_vector"], rtol=1e-6, atol=1e-8, err_msg=fn)
+
+
+def test_sparse_heteroscedastic_reduces_to_homoscedastic():
+    """A constant per-point noise vector gives the bound and kernel gradients of the scalar-noise branch, and the N
+    per-point noise gradients sum to the scalar one (the het_noise branch is the same bound, differentiated per point)."""
+    rng = np.random.default_rng(3)
+    N, M, D = 120, 17, 2
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.sin(X).sum(1, keepdims=True) + 0.1 * rng.standard_normal((N, 1))
+    Z = X[:M] + 0.01
+    l0, g0, Z0, _ = o.sparse_eval(X, Y, Z, "rbf", True, 1.2, np.array([1.1, 1.9]), 0.04)
+    l1, g1, Z1, _ = o.sparse_eval(X, Y, Z, "rbf", True, 1.2, np.array([1.1, 1.9]), np.full(N, 0.04))
+    assert abs(l0 - l1) <= 1e-9 * abs(l0)
+    np.testing.assert_allclose(g1[:3], g0[:3], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(g1[3:].sum(), g0[3], rtol=1e-7)
+    np.testing.assert_allclose(Z1, Z0, rtol=1e-7, atol=1e-9)
+
+
 def test_logexp_roundtrip():
     x = np.linspace(-20, 50, 50)
     np.testing.assert_allclose(o.logexp_finv(o.logexp_f(x)), x, rtol=1e-9, atol=1e-6)

@@ -108,6 +108,29 @@ def test_oracle_vardtc_equals_reference(G, kind, ARD):
     np.testing.assert_allclose(res["dL_dKnm"], r["dL_dKnm"], rtol=1e-8, atol=1e-12)
 
 
+@pytest.mark.parametrize("kind,ARD,P", [("rbf", True, 1), ("matern52", False, 1), ("exponential", True, 2)])
+def test_oracle_vardtc_heteroscedastic_equals_reference(G, kind, ARD, P):
+    """Sparse GP regression with one noise variance per data point: the het_noise branches of the unmodified
+    var_dtc.py (:127-128, :221-227, :241-257, :267-269) with the reference's HeteroscedasticGaussian, against
+    oracle.vardtc_inference with a noise vector."""
+    from oracle import ref_gpy
+    rng = np.random.default_rng(14)
+    N, M = 260, 24
+    X = rng.uniform(-3, 3, (N, 3))
+    Y = np.stack([np.sin(X).sum(1) + 0.2 * rng.standard_normal(N) for _ in range(P)], 1)
+    Z = X[rng.permutation(N)[:M]].copy()
+    ls = np.array([1.2, 1.7, 2.1]) if ARD else 1.6
+    nv = rng.uniform(0.01, 0.4, N)
+    r = ref_gpy.evaluate_sparse_het(G, X, Y, Z, kind, ARD, 1.3, ls, nv)
+    lml, g, Zg, res = o.sparse_eval(X, Y, Z, kind, ARD, 1.3, ls, nv)
+    assert abs(lml - r["lml"]) <= 1e-9 * abs(r["lml"])
+    assert g.shape == r["grad"].shape
+    np.testing.assert_allclose(g, r["grad"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(Zg, r["Zgrad"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(res["woodbury_vector"], r["woodbury_vector"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(res["woodbury_inv"], r["woodbury_inv"], rtol=1e-7, atol=1e-10)
+
+
 @pytest.mark.parametrize("kind,ARD", [("rbf", True), ("matern32", False)])
 def test_oracle_heteroscedastic_equals_reference(G, kind, ARD):
     """One noise variance per data point: oracle restatement against the reference's HeteroscedasticGaussian +
