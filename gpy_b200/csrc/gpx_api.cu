@@ -91,7 +91,7 @@ int gpx::fill_kp(KernParams& kp, int kind, int ard, int D, double variance, cons
 extern "C" {
 
 const char* gpx_last_error(void) { return gpx::g_err.c_str(); }
-const char* gpx_version(void) { return "gpx 0.1 (sm_100a, fp64 DMMA)"; }
+const char* gpx_version(void) { return "gpx 0.2 (sm_100a: tcgen05 int8 digit-split GEMM + fp64 DMMA)"; }
 
 int gpx_device_count(void) {
   int n = 0;

@@ -106,6 +106,16 @@ class Parameterized(Parameterizable, metaclass=ParametersChangedMeta):
         ps = self.flattened_parameters()
         return np.concatenate([np.asarray(p.gradient, dtype=np.float64).reshape(-1) for p in ps]) if ps else np.zeros(0)
 
+    @gradient.setter
+    def gradient(self, val):
+        """paramz keeps ONE flat gradient array and hands out views; `node.gradient = v` / `node.gradient += v` write through
+        to the leaves in link order (core/sparse_gp.py:115 `self.kern.gradient += kerngrad`)"""
+        val = np.asarray(val, dtype=np.float64).reshape(-1)
+        i = 0
+        for p in self.flattened_parameters():
+            p.gradient = val[i:i + p.size].reshape(p.shape)
+            i += p.size
+
     @property
     def size(self):
         return sum(p.size for p in self.flattened_parameters())

@@ -140,6 +140,31 @@ def load_models():
     return _models
 
 
+_sparse_models = None
+
+
+def load_sparse_models():
+    """-> namespace with the reference's own SparseGP (GPy/core/sparse_gp.py executed verbatim on top of `load_models()`):
+    SparseGP.__init__ / parameters_changed / _update_gradients (:41-119) and, through GP, optimize and predict. The model
+    class GPy/models/sparse_gp_regression.py derives from SparseGP_MPI, whose module imports the mini-batch / MPI inference
+    (var_dtc_parallel.py -> mpi4py optional, VarDTC_minibatch); it is loaded too when that import chain succeeds, else
+    `SparseGPRegression` is None and the tests build the model the way sparse_gp_regression.py:33-59 does, from SparseGP."""
+    global _sparse_models
+    if _sparse_models is not None:
+        return _sparse_models
+    M = load_models()
+    sgp = importlib.import_module("GPy.core.sparse_gp")
+    sys.modules["GPy.core"].SparseGP = sgp.SparseGP
+    reg = None
+    try:
+        importlib.import_module("GPy.core.sparse_gp_mpi")
+        reg = importlib.import_module("GPy.models.sparse_gp_regression").SparseGPRegression
+    except Exception:  # noqa: BLE001
+        reg = None
+    _sparse_models = types.SimpleNamespace(SparseGP=sgp.SparseGP, SparseGPRegression=reg, GP=M.GP, G=M.G)
+    return _sparse_models
+
+
 _comb = None
 
 

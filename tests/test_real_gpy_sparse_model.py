@@ -1,0 +1,196 @@
+"""The reference's OWN sparse model loop driving the plugin: unmodified GPy/core/sparse_gp.py (SparseGP.__init__,
+parameters_changed :76-81, _update_gradients :83-119) on top of GPy/core/gp.py (optimize, predict), executed from
+/root/reference through oracle/ref_gpy.load_sparse_models():
+
+    m = SparseGP(X, Y, Z, B.RBF(D, ARD=True), Gaussian(), inference_method=B.VarDTC())
+
+`B.VarDTC.inference` makes ONE engine call per evaluation; `SparseGP._update_gradients` then calls the plugin kernel's
+update_gradients_diag / update_gradients_full / gradients_X exactly as written in the reference and receives the gradients
+the device already reduced (the N x M matrix dL_dKnm never exists). The CPU test replaces the C ABI by a test double
+answering from the oracle — what is tested is that the stock SparseGP / paramz loop runs UNCHANGED on the plugin pair and
+lands where the stock pair (reference VarDTC + reference kernel) lands; the GPU test runs the same on the device and is
+skipped where the reference tree does not exist (the GPU box)."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from oracle import gpy_oracle as o
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.environ.get("GPX_REFERENCE", "/root/reference") + "/GPy"),
+                                reason="reference tree not present")
+
+
+class FakeSparseEngine(object):
+    """test double of the sparse entry points of _ffi.Engine: numbers from the oracle's VarDTC restatement."""
+
+    def __init__(self, device=0):
+        self.calls, self.sparse_serial = [], 0
+
+    def sparse_set_data(self, X, Y):
+        self.X, self.Y = np.array(X), np.array(Y)
+        self.calls.append("sparse_set_data")
+
+    def sparse_eval(self, kind, ARD, variance, lengthscale, Z, noise_variance):
+        self.calls.append("sparse_eval")
+        self.sparse_serial += 1
+        lml, g, Zg, self.res = o.sparse_eval(self.X, self.Y, Z, kind, ARD, variance, lengthscale, noise_variance)
+        return lml, g, Zg
+
+    def sparse_eval_het(self, kind, ARD, variance, lengthscale, Z, noise_variances):
+        self.calls.append("sparse_eval_het")
+        self.sparse_serial += 1
+        lml, g, Zg, self.res = o.sparse_eval(self.X, self.Y, Z, kind, ARD, variance, lengthscale,
+                                             np.asarray(noise_variances).reshape(-1))
+        nk = g.size - self.X.shape[0] * self.Y.shape[1]
+        return lml, g[:nk], Zg, g[nk:].reshape(self.X.shape[0], self.Y.shape[1])
+
+    def sparse_get(self, what):
+        return {"woodbury_vector": self.res["woodbury_vector"], "woodbury_inv": self.res["woodbury_inv"],
+                "Kmm": self.res["Kmm"], "Lm": self.res["Lm"]}[what]
+
+
+def fake_sparse_ffi():
+    from test_gpy_plugin_cpu import fake_ffi
+    f = fake_ffi()
+
+    def kern_grad_X(kind, ARD, var, ls, X, dL_dK, X2=None):
+        return o.StationaryOracle(kind, X.shape[1], var, ls, ARD).gradients_X(dL_dK, X, X2)
+
+    return types.SimpleNamespace(kern_K=f.kern_K, kern_Kdiag=f.kern_Kdiag, kern_grad_full=f.kern_grad_full,
+                                 kern_grad_X=kern_grad_X, Engine=FakeSparseEngine)
+
+
+def _plugin(ffi=None):
+    from oracle import ref_gpy
+    from gpy_b200 import gpy_plugin
+    S = ref_gpy.load_sparse_models()
+    G = S.G
+    kw = {} if ffi is None else {"ffi": ffi}
+    B = gpy_plugin.make(G.RBF, G.Exponential, G.Matern32, G.Matern52, G.ExactGaussianInference, VarDTC=G.VarDTC, **kw)
+    return S, G, B
+
+
+def _data(N, M, D, P=1, seed=3):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.stack([np.sin(X).sum(1) / np.sqrt(D) + 0.1 * rng.standard_normal(N) for _ in range(P)], 1)
+    Z = X[rng.permutation(N)[:M]].copy() + 0.01 * rng.standard_normal((M, D))
+    return X, Y, Z
+
+
+def _run_pair(S, G, B, N, M, D, kname, ARD, max_iters, lml_tol=1e-8):
+    X, Y, Z = _data(N, M, D)
+    ls = (np.sqrt(D) * np.linspace(0.8, 1.3, D)) if ARD else float(np.sqrt(D))
+    stock = S.SparseGP(X, Y, Z.copy(), getattr(G, kname)(D, variance=1.2, lengthscale=ls, ARD=ARD),
+                       G.Gaussian(variance=0.05), inference_method=G.VarDTC(limit=3))
+    plug = S.SparseGP(X, Y, Z.copy(), getattr(B, kname)(D, variance=1.2, lengthscale=ls, ARD=ARD),
+                      G.Gaussian(variance=0.05), inference_method=B.VarDTC())
+    assert type(plug) is type(stock)                                     # the reference's own model class, untouched
+    assert isinstance(plug.inference_method, G.VarDTC)                   # and a real VarDTC
+    l_s, l_p = float(np.squeeze(stock.log_likelihood())), float(np.squeeze(plug.log_likelihood()))
+    assert abs(l_p - l_s) <= lml_tol * max(1.0, abs(l_s))
+    # parameter order of the reference: [inducing inputs, kern.variance, kern.lengthscale, Gaussian_noise.variance]
+    np.testing.assert_allclose(plug.gradient, stock.gradient, rtol=1e-6, atol=1e-7 * np.abs(stock.gradient).max())
+    plug.kern.variance[:] = 0.9                                          # paramz observer chain -> one evaluation
+    stock.kern.variance[:] = 0.9
+    assert abs(float(np.squeeze(plug.log_likelihood())) - float(np.squeeze(stock.log_likelihood()))) <= lml_tol * max(1.0, abs(l_s))
+    if N <= 200:
+        assert plug.checkgrad(step=1e-5)
+    rs, rp = stock.optimize(max_iters=max_iters), plug.optimize(max_iters=max_iters)
+    ls_, lp_ = float(np.squeeze(stock.log_likelihood())), float(np.squeeze(plug.log_likelihood()))
+    assert lp_ > l_p and abs(lp_ - ls_) <= 1e-3 * max(1.0, abs(ls_))     # same optimizer, same objective, same trajectory
+    Xn = np.random.default_rng(0).uniform(-2, 2, (6, D))
+    mu_p, var_p = plug.predict(Xn)                                       # GP.predict -> posterior._raw_predict(pred_var = Z)
+    ko = o.StationaryOracle({"RBF": "rbf", "Matern32": "matern32", "Matern52": "matern52", "Exponential": "exponential"}[kname],
+                            D, float(plug.kern.variance[0]), np.asarray(plug.kern.lengthscale).reshape(-1) if ARD
+                            else float(plug.kern.lengthscale[0]), ARD)
+    _, _, _, res = o.sparse_eval(X, Y, np.asarray(plug.Z), ko.kind if hasattr(ko, "kind") else None or
+                                 {"RBF": "rbf", "Matern32": "matern32", "Matern52": "matern52",
+                                  "Exponential": "exponential"}[kname], ARD, float(plug.kern.variance[0]),
+                                 np.asarray(plug.kern.lengthscale).reshape(-1) if ARD else float(plug.kern.lengthscale[0]),
+                                 float(plug.likelihood.variance[0]))
+    mu0, var0 = o.sparse_raw_predict(ko, np.asarray(plug.Z), res["woodbury_vector"], res["woodbury_inv"], Xn)
+    np.testing.assert_allclose(mu_p, mu0, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(var_p, var0 + float(plug.likelihood.variance[0]), rtol=1e-4, atol=1e-7)
+    return plug, rp
+
+
+def test_stock_sparse_gp_optimizes_through_the_plugin_cpu():
+    S, G, B = _plugin(fake_sparse_ffi())
+    for (kname, ARD, D) in (("RBF", True, 2), ("Matern32", False, 3)):
+        plug, run = _run_pair(S, G, B, 150, 14, D, kname, ARD, 25)
+        calls = plug.inference_method.engine.calls
+        assert calls[0] == "sparse_set_data" and calls.count("sparse_set_data") == 1   # X, Y stayed resident
+        assert calls.count("sparse_eval") >= run.funct_eval and "sparse_eval_het" not in calls
+
+
+def test_heteroscedastic_vardtc_through_the_plugin_equals_the_stock_inference_cpu():
+    """The reference's HeteroscedasticGaussian with VarDTC: B.VarDTC takes the het_noise entry point and hands dL_dR to the
+    likelihood's own exact_inference_gradients (var_dtc.py:176, gaussian.py:358-359). Compared at the level of
+    VarDTC.inference + the gradient wiring of core/sparse_gp.py:108-119, because the reference cannot run this pair as a
+    MODEL: `dL_dR[output_index]` is N x 1 (x 1) and `Gaussian.update_gradients` cannot assign it to the variance parameter
+    (likelihoods/gaussian.py:73) — the branch is reachable from the inference API only."""
+    S, G, B = _plugin(fake_sparse_ffi())
+    N, M, D = 120, 12, 2
+    X, Y, Z = _data(N, M, D, seed=8)
+    meta = {"output_index": np.arange(N)[:, None]}
+    nv = np.random.default_rng(1).uniform(0.02, 0.3, N)
+
+    def run(K, inf):
+        lik = G.HeteroscedasticGaussian(meta)
+        lik.variance[:] = nv.reshape(lik.variance.shape)
+        kern = K.RBF(D, variance=1.1, lengthscale=[1.3, 1.9], ARD=True)
+        post, lml, gd = inf.inference(kern, X, Z, lik, Y, meta)
+        kern.update_gradients_diag(gd["dL_dKdiag"], X)                        # sparse_gp.py:110-118
+        kg = kern.gradient.copy()
+        kern.update_gradients_full(gd["dL_dKnm"], X, Z)
+        kg += kern.gradient
+        kern.update_gradients_full(gd["dL_dKmm"], Z, None)
+        kg += kern.gradient
+        Zg = kern.gradients_X(gd["dL_dKmm"], Z) + kern.gradients_X(gd["dL_dKnm"].T, Z, X)
+        return float(np.squeeze(lml)), kg, Zg, np.asarray(gd["dL_dthetaL"]).reshape(-1), post
+
+    l_s, kg_s, Zg_s, dn_s, post_s = run(G, G.VarDTC(limit=3))
+    infp = B.VarDTC()
+    l_p, kg_p, Zg_p, dn_p, post_p = run(B, infp)
+    assert abs(l_p - l_s) <= 1e-9 * abs(l_s)
+    np.testing.assert_allclose(kg_p, kg_s, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(Zg_p, Zg_s, rtol=1e-8, atol=1e-10)
+    assert dn_p.shape == dn_s.shape == (N,)
+    np.testing.assert_allclose(dn_p, dn_s, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(post_p.woodbury_vector, post_s.woodbury_vector, rtol=1e-8, atol=1e-12)
+    assert infp.engine.calls == ["sparse_set_data", "sparse_eval_het"]
+
+
+def test_unsupported_sparse_cases_fall_back_to_the_stock_method_and_handles_do_not_become_arrays():
+    S, G, B = _plugin(fake_sparse_ffi())
+    X, Y, Z = _data(60, 7, 2)
+    inf = B.VarDTC()
+    post, lml, gd = inf.inference(G.RBF(2), X, Z, G.Gaussian(variance=0.1), Y)       # stock kernel -> stock VarDTC
+    assert isinstance(gd["dL_dKnm"], np.ndarray) and inf._engine is None
+    kp = B.RBF(2, variance=1.3, lengthscale=1.4)
+    post, lml, gd = inf.inference(kp, X, Z, G.Gaussian(variance=0.1), Y)
+    assert gd["dL_dKnm"].shape == (60, 7) and gd["dL_dKnm"].T.shape == (7, 60) and gd["dL_dKmm"].shape == (7, 7)
+    with pytest.raises(TypeError):
+        np.asarray(gd["dL_dKnm"])
+    kp.variance[:] = 2.0                                                             # stale handle must not be served
+    with pytest.raises(ValueError):
+        kp.update_gradients_full(gd["dL_dKnm"], X, Z)
+    # a plain ndarray dL_dK takes the generic reductions (stationary.py:193-252)
+    dL = np.random.default_rng(2).standard_normal((60, 7))
+    ks = G.RBF(2, variance=2.0, lengthscale=1.4)
+    np.testing.assert_allclose(kp.gradients_X(dL.T, Z, X), ks.gradients_X(dL.T, Z, X), rtol=1e-10, atol=1e-12)
+    st = inf.__getstate__()                                 # var_dtc.py:39-48 pickles as its cache limit; the device
+    assert st == {"limit": inf.limit, "device": 0}          # handle is dropped the same way
+    inf2 = B.VarDTC.__new__(B.VarDTC)
+    inf2.__setstate__(st)
+    assert inf2._engine is None and inf2.limit == inf.limit and callable(inf2.get_trYYT)
+
+
+@pytest.mark.gpu
+def test_stock_sparse_gp_optimizes_through_the_plugin_gpu():
+    S, G, B = _plugin()
+    for (kname, ARD, D, N, M) in (("RBF", True, 3, 1200, 60), ("Matern52", False, 2, 700, 130)):
+        _run_pair(S, G, B, N, M, D, kname, ARD, 25)
