@@ -215,3 +215,96 @@ def test_two_rank_gloo_sparse_row_shards():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _sparse_het_worker(rank, world, port, q):
+    """Row-sharded VarDTC with one noise variance per data point, in the form gpx_sparse_eval_het computes it: tmp = Lm^-1
+    psi1^T of the local rows with its COLUMNS scaled by sqrt(beta_n), A and tmp Y all-reduced, the M x M algebra with
+    beta = 1, dL_dKnm^T columns scaled by beta_n, per-point noise gradients from the three column reductions
+    (s1 = |tmp[:, n]|^2 before the scaling, r = w . tmp[:, n], s2 = |Q psi1^T[:, n]|^2 with Q = LB^-1 Lm^-1); the sums
+    over n of log beta, beta and beta |Y_n|^2 are all-reduced. Checked against the oracle (het_noise branches of
+    var_dtc.py) on the whole data set; each rank checks ITS rows of dL_dR."""
+    import torch
+    import torch.distributed as dist
+    from oracle import gpy_oracle as o
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, M, D, P = 301, 29, 2, 2
+        rng = np.random.default_rng(6)
+        X = rng.uniform(-3, 3, (N, D))
+        Y = np.stack([np.sin(X).sum(1) + 0.1 * rng.standard_normal(N) for _ in range(P)], 1)
+        Z = X[rng.permutation(N)[:M]] + 0.01 * rng.standard_normal((M, D))
+        ls, var = np.array([1.2, 1.8]), 1.1
+        nv = rng.uniform(0.01, 0.3, N)
+        lml0, g0, Zg0, res0 = o.sparse_eval(X, Y, Z, "rbf", True, var, ls, nv)
+        rows = gdist.shard_rows(N, rank, world)
+        Xl, Yl, beta = X[rows], Y[rows], 1.0 / np.fmax(nv[rows], 1e-8)
+        sb = np.sqrt(beta)
+        kern = o.StationaryOracle("rbf", D, var, ls, True)
+
+        def allsum(a):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).copy())
+            dist.all_reduce(t)
+            return t.numpy()
+
+        psi1 = kern.K(Xl, Z)
+        ntot = allsum(np.array([float(Xl.shape[0])]))[0]
+        Kmm = kern.K(Z) + 1e-8 * np.eye(M)
+        Lm = np.linalg.cholesky(Kmm); Lmi = np.linalg.inv(Lm); Um = Lmi.T
+        tmp = Lmi @ psi1.T                                   # M x n_local
+        s1 = (tmp * tmp).sum(0)
+        tmp_s = tmp * sb[None, :]
+        Ar = allsum(tmp_s @ tmp_s.T)
+        t = allsum(tmp_s @ (sb[:, None] * Yl))
+        B = np.eye(M) + Ar
+        LB = np.linalg.cholesky(B); LBi = np.linalg.inv(LB); UB = LBi.T
+        v = LBi @ t; w = UB @ v; C = Um @ w
+        DBi = P * (UB @ UB.T) + w @ w.T
+        dKmm = Um @ (-0.5 * DBi - 0.5 * P * B + P * np.eye(M)) @ Um.T
+        W2 = Um @ (P * np.eye(M) - DBi) @ Um.T
+        r = (w.T @ tmp_s).T / sb[:, None]                    # n_local x P
+        Q = LBi @ Lmi
+        V2 = Q @ psi1.T
+        s2 = (V2 * V2).sum(0)
+        sums = allsum(np.array([np.log(beta).sum(), beta.sum(), (beta[:, None] * Yl * Yl).sum()]))
+        data_fit, trA = float((v * v).sum()), np.trace(Ar)
+        lml = (-0.5 * ntot * P * np.log(2 * np.pi) + 0.5 * P * sums[0] - 0.5 * sums[2]
+               - 0.5 * P * (var * sums[1] - trA) - P * np.log(np.diag(LB)).sum() + 0.5 * data_fit)
+        b2 = (beta ** 2)[:, None]
+        dR = (-0.5 * beta[:, None] + 0.5 * (beta[:, None] * Yl) ** 2 + 0.5 * P * ((var - s1) * beta ** 2)[:, None]
+              + 0.5 * (s2 * beta ** 2)[:, None] - r * Yl * b2 + 0.5 * r ** 2 * b2)
+        dKnmT = (W2 @ psi1.T) * beta[None, :] + C @ (beta[:, None] * Yl).T
+        dv1, dl1 = kern.update_gradients_full(dKnmT.T, Xl, Z)
+        dZ1 = kern.gradients_X(dKnmT, Z, Xl)
+        pieces = allsum(np.concatenate([[dv1], np.atleast_1d(dl1), dZ1.ravel()]))
+        dv2, dl2 = kern.update_gradients_full(dKmm, Z, None)
+        dvar = -0.5 * P * sums[1] + pieces[0] + dv2
+        dlen = pieces[1:1 + D] + np.atleast_1d(dl2)
+        Zg = pieces[1 + D:].reshape(M, D) + kern.gradients_X(dKmm, Z)
+        assert abs(lml - lml0) < 1e-8 * max(1.0, abs(lml0))
+        np.testing.assert_allclose(np.concatenate([[dvar], dlen]), g0[:1 + D], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(Zg, Zg0, rtol=1e-6, atol=1e-8)
+        dR0 = g0[1 + D:].reshape(N, P)[rows]
+        np.testing.assert_allclose(dR, dR0, rtol=1e-6, atol=1e-7 * np.abs(dR0).max())
+        np.testing.assert_allclose(C, res0["woodbury_vector"], rtol=1e-6, atol=1e-8)
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sparse_heteroscedastic_row_shards():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sparse_het_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
