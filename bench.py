@@ -485,12 +485,23 @@ def run_sparse(args):
         from oracle import gpy_oracle as o
         Ns = min(N, 16384)                         # bounded sample: the first Ns rows, same Z / theta (CPU work is ~ linear in N)
         ts = time.perf_counter()
-        o.sparse_eval(X[:Ns], Y[:Ns], Z, "rbf", True, 1.0, ls0, 0.05)
+        lml_c, g_c, Zg_c, _ = o.sparse_eval(X[:Ns], Y[:Ns], Z, "rbf", True, 1.0, ls0, 0.05)
         dt = time.perf_counter() - ts
         threads, _ = cpu_threads()
         cpu = {"value": 1.0 / (dt * N / Ns), "unit": "evals/s", "cores": threads, "kind": "port",
                "sample": "oracle VarDTC (var_dtc.py:66-276 restated) on the first %d of %d rows, same Z and theta: %.1f s, "
                          "scaled by N/Ns (the N-dependent work is linear in N)" % (Ns, N, dt), "seconds_sample": dt}
+        try:   # parity of the device evaluation on the SAME sample (outside the timed regions; never breaks the line)
+            e2 = gpy_b200._ffi.Engine(local)
+            e2.sparse_set_data(X[:Ns], Y[:Ns])
+            lml_g, g_g, Zg_g = e2.sparse_eval("rbf", True, 1.0, ls0, Z, 0.05)
+            e2.close()
+            cpu["parity_vs_gpu_on_sample"] = {
+                "lml_rel": abs(lml_g - lml_c) / max(1.0, abs(lml_c)),
+                "grad_rel_max": float(np.max(np.abs(g_g - g_c) / np.maximum(np.abs(g_c), 1e-300))),
+                "dZ_max_over_largest": float(np.max(np.abs(Zg_g - Zg_c)) / max(float(np.abs(Zg_c).max()), 1e-300))}
+        except Exception as ex:  # noqa: BLE001
+            cpu["parity_vs_gpu_on_sample"] = {"error": repr(ex)}
     line = {"metric": "SparseGPRegression VarDTC bound+gradient evals/sec (fp64) at N=%d M=%d D=%d" % (N, M, D),
             "value": args.steps / t_res, "unit": "evals/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
