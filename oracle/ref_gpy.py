@@ -147,8 +147,9 @@ def load_sparse_models():
     """-> namespace with the reference's own SparseGP (GPy/core/sparse_gp.py executed verbatim on top of `load_models()`):
     SparseGP.__init__ / parameters_changed / _update_gradients (:41-119) and, through GP, optimize and predict. The model
     class GPy/models/sparse_gp_regression.py derives from SparseGP_MPI, whose module imports the mini-batch / MPI inference
-    (var_dtc_parallel.py -> mpi4py optional, VarDTC_minibatch); it is loaded too when that import chain succeeds, else
-    `SparseGPRegression` is None and the tests build the model the way sparse_gp_regression.py:33-59 does, from SparseGP."""
+    (var_dtc_parallel.py -> mpi4py optional, VarDTC_minibatch); it loads here too (the one name it takes from the stub
+    package, `VarDTC`, is set from the reference's own module); should that chain fail, `SparseGPRegression` is None and the
+    tests fall back to SparseGP, which sparse_gp_regression.py:33-59 only wraps."""
     global _sparse_models
     if _sparse_models is not None:
         return _sparse_models
@@ -156,6 +157,7 @@ def load_sparse_models():
     sgp = importlib.import_module("GPy.core.sparse_gp")
     sys.modules["GPy.core"].SparseGP = sgp.SparseGP
     reg = None
+    sys.modules["GPy.inference.latent_function_inference"].VarDTC = M.G.VarDTC   # name sparse_gp_regression.py:9 imports
     try:
         importlib.import_module("GPy.core.sparse_gp_mpi")
         reg = importlib.import_module("GPy.models.sparse_gp_regression").SparseGPRegression
