@@ -54,7 +54,12 @@ class HeteroscedasticGaussian(Gaussian):
         return np.asarray(dL_dKdiag)[np.asarray(Y_metadata["output_index"]).flatten()]            # gaussian.py:358-359
 
     def update_gradients(self, grad):
-        self.variance.gradient = np.asarray(grad, dtype=np.float64).reshape(-1)
+        g = np.asarray(grad, dtype=np.float64).reshape(-1)
+        if g.size != self.variance.values.size:
+            # the reference assigns the array to the parameter's gradient and fails on the shape the same way
+            # (gaussian.py:73): with P > 1 outputs VarDTC's dL_dR is N x P (var_dtc.py:245-257), not one value per variance
+            raise ValueError("noise gradient of %d entries for %d noise variances" % (g.size, self.variance.values.size))
+        self.variance.gradient = g
 
     def predictive_values(self, mu, var, full_cov=False, Y_metadata=None):
         _s = self.gaussian_variance(Y_metadata)                                                  # gaussian.py:364-373
