@@ -31,9 +31,15 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_committed_product_line_has_the_contract_keys():
-    p = os.path.join(ROOT, "profiles", "r01_bench_ours_n16384.json")
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r01_bench_ours_n16384.json", "r02s3_final_bench_ours.json"])
+def test_committed_product_line_has_the_contract_keys(name):
+    p = os.path.join(ROOT, "profiles", name)
     d = json.loads([l for l in open(p).read().splitlines() if l.startswith("{")][-1])
+    assert d["roofline"]["unit"] in ("TFLOP/s", "GB/s") and "peak" in d["roofline"] and "achieved" in d["roofline"]
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and "workload" in d["config"] and "l2" in d["config"]
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
         assert key in d, key
