@@ -153,3 +153,17 @@ def test_plugin_heteroscedastic_likelihood_equals_stock_reference(setup):
     stock.update_gradients_full(gd_s["dL_dK"], X); plug.update_gradients_full(gd_p["dL_dK"], X)
     np.testing.assert_allclose(plug.variance.gradient, stock.variance.gradient, rtol=1e-10)
     np.testing.assert_allclose(plug.lengthscale.gradient, stock.lengthscale.gradient, rtol=1e-10)
+
+
+def test_plugin_inference_serialises_as_the_stock_class(setup):
+    """`to_dict()` (exact_gaussian_inference.py:24-35) is inherited: a model saved to JSON names the stock class, so it loads
+    on a machine without the library (CPU-equivalent fallback on load, like pickling: GPy/kern/src/rbf.py:313-318)."""
+    G, B = setup
+    d = B.ExactGaussianInference().to_dict()
+    assert d["class"] == "GPy.inference.latent_function_inference.exact_gaussian_inference.ExactGaussianInference"
+    import pickle
+    inf = B.ExactGaussianInference()
+    X, Y = o.synthetic(30, 2, 1)
+    inf.inference(B.RBF(2), X, G.Gaussian(variance=0.1), Y)
+    st = inf.__getstate__()
+    assert st["_engine"] is None                       # the device handle does not travel
