@@ -378,7 +378,9 @@ def run_ours(args):
                         "fp64_equivalent_tflops": upd_flops / upd_ms * 1e-9,
                         "algorithmic_flops_per_step": upd_flops / args.steps,
                         "traffic": None,
-                        "traffic_note": "per-launch DRAM traffic differs launch to launch (16 panels); see profiles/ for the ncu capture",
+                        "traffic_note": "not measured in this run; per-launch DRAM traffic differs launch to launch (16 panels): the ncu "
+                                        "capture of the same path (profiles/r02s3_final_oz_traffic.txt) has 2.61 GB per large launch "
+                                        "(1.8 GB read + 0.9 GB written) at N=16384",
                         "grad_from_kinv_ms_per_step": lau_ms / args.steps}
         else:
             ach = upd_flops / upd_ms * 1e-9 if upd_ms > 0 else 0.0
