@@ -3,7 +3,10 @@
  * This is the drop-in boundary for ONE hot path of SheffieldML/GPy:
  *     GPRegression -> GP.parameters_changed -> ExactGaussianInference.inference -> Kern.K/Kdiag/update_gradients_full
  * Each entry point names the reference interface it replaces (paths relative to the GPy repository root).
- * Plain C: pointers and sizes only, no torch / numpy types. All arithmetic is IEEE fp64.
+ * Plain C: pointers and sizes only, no torch / numpy types. All inputs, outputs and stored matrices are IEEE fp64; the N^3
+ * products run on fp64 tensor instructions (DMMA) or, from N = 8192 on one GPU, as int8 digit-split products on the tcgen05
+ * tensor cores whose exact s32 sums are recombined in fp64 (8 digits for the Cholesky part, 7 for the inverse part:
+ * |dLML| <= 1e-8 and 1e-6 relative on gradients against the reference; option "ozaki" selects).
  *
  * Conventions
  *   - Return value: 0 ok; >0 "matrix not positive definite, leading minor <ret>" (the caller raises
