@@ -605,7 +605,8 @@ static int sparse_eval_impl(gpx_ctx* c, int kind, int ard, double variance, cons
       const double b = hbeta[n], b2 = b * b;
       const double common = -0.5 * b + 0.5 * od * (variance - s1[n]) * b2 + 0.5 * s2[n] * b2;
       for (int q = 0; q < P; q++) {
-        const double y = hY[(size_t)q * Npad + n], r = rs[(size_t)q * Npad + n] / hsb[n];
+        // r was formed from the scaled tmp: undo sqrt(beta_n); an infinite noise variance (beta_n = 0) switches the point off
+        const double y = hY[(size_t)q * Npad + n], r = hsb[n] > 0.0 ? rs[(size_t)q * Npad + n] / hsb[n] : 0.0;
         sum_bY2 += b * y * y;
         dL_dR_out[n * P + q] = common + 0.5 * (b * y) * (b * y) - r * y * b2 + 0.5 * r * r * b2;
       }
